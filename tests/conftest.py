@@ -1,0 +1,36 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def checkers():
+    """Build the test-only checker libraries once per session."""
+    import _checkers
+    _checkers.build_checkers()
+    return _checkers
+
+
+def golden_cases():
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "manifest.json")) as f:
+        return json.load(f)["cases"]
+
+
+def load_golden(case):
+    import numpy as np
+    g = os.path.join(ROOT, "tests", "golden")
+    x = np.load(os.path.join(g, case["name"] + ".pcm.npy"))
+    with open(os.path.join(g, case["name"] + ".flac"), "rb") as f:
+        flac = f.read()
+    return x, flac
