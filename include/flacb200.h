@@ -1,0 +1,119 @@
+/*
+ * flacb200.h -- C ABI of libflacb200.so, the B200-native FLAC encode/decode engine.
+ *
+ * Two layers, both plain C (pointers + sizes, no torch / C++ types):
+ *
+ *  (1) BATCH ABI (additive; the only way to keep a GPU busy): many independent streams per call,
+ *      PCM either resident in HBM (e.g. a torch tensor's data_ptr) or in host memory.
+ *      This is what bench.py times and what the per-handle layer is built on.
+ *
+ *  (2) DROP-IN ABI: the subset of libFLAC's stream encoder/decoder C API that pyFLAC's cffi
+ *      modules bind, with identical names, signatures, status values and callback contracts:
+ *        encoder  -- /root/reference/pyflac/builder/encoder.py:251-256 (callbacks), :266-322 (functions),
+ *                    called from pyflac/encoder.py:77,115,132,141,145-231,319,401
+ *        decoder  -- /root/reference/pyflac/builder/decoder.py:368-375 (callbacks), :387-475 (functions),
+ *                    called from pyflac/decoder.py:85,99,108,170,196,271,294,372,388
+ *      Repointing pyFLAC's build_args.py:49-51 at this library is the whole integration
+ *      (INTEGRATION.md).  Declared in flacb200_flac_api.h.
+ *
+ * Every compute entry point fails loudly (non-zero status + flacb200_last_error) when no CUDA
+ * device is usable; there is no CPU fallback.
+ */
+#ifndef FLACB200_H
+#define FLACB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct flacb200_ctx flacb200_ctx;
+
+enum {
+    FLACB200_OK = 0,
+    FLACB200_ERR_NO_DEVICE = 1,      /* CUDA runtime reports no usable device */
+    FLACB200_ERR_CUDA = 2,           /* a CUDA call failed; see flacb200_last_error */
+    FLACB200_ERR_CONFIG = 3,         /* settings libFLAC itself would reject (status in flacb200_last_error) */
+    FLACB200_ERR_UNSUPPORTED = 4,    /* valid FLAC settings outside this build's range (see DESIGN.md "limits") */
+    FLACB200_ERR_ARG = 5,
+    FLACB200_ERR_BITSTREAM = 6       /* decode: malformed input */
+};
+
+/* Encoder settings == what pyFLAC can set (encoder.py:293-316): everything else follows
+ * libFLAC's compression-level table (stream_encoder.h:845-853). */
+typedef struct {
+    uint32_t sample_rate;
+    uint32_t channels;
+    uint32_t bits_per_sample;     /* 8..24 in this build */
+    uint32_t compression_level;   /* 0..8 */
+    uint32_t blocksize;           /* 0 = libFLAC default (1152 for levels 0-2, else 4096) */
+    uint32_t container_bytes;     /* PCM element size in memory: 2 (int16, bps<=16) or 4 (int32) */
+    uint32_t write_prologue;      /* 1: every stream's bytes in the arena start with fLaC+STREAMINFO+VORBIS_COMMENT (== FileEncoder output) */
+    uint32_t do_md5;              /* 1: STREAMINFO carries the MD5 of the PCM (libFLAC default) */
+    uint32_t streamable_subset;   /* validation only (stream_encoder.h:1005-1017) */
+    uint32_t debug_trace;         /* 1: keep per-signal analysis traces (tests) */
+} flacb200_enc_config;
+
+typedef struct {
+    uint64_t total_samples;
+    uint64_t byte_off;            /* offset of the stream's first byte in the arena */
+    uint64_t byte_len;
+    uint32_t min_framesize, max_framesize;
+    uint32_t n_frames, pad;
+    uint8_t  md5[16];
+} flacb200_stream_info;
+
+typedef struct {
+    uint64_t total_bytes;         /* bytes used in the arena */
+    uint32_t n_frames;
+    uint32_t n_streams;
+    uint64_t log_guard_hits;      /* decisions inside the libm-log guard band (0 in every test) */
+    /* device pointers (owned by the ctx, valid until the next call on it) */
+    const uint8_t  *d_arena;
+    const uint64_t *d_frame_off;
+    const uint32_t *d_frame_len;
+} flacb200_enc_result;
+
+int  flacb200_create(flacb200_ctx **out, int device);
+void flacb200_destroy(flacb200_ctx *ctx);
+const char *flacb200_last_error(const flacb200_ctx *ctx);
+/* Run all work of this ctx on an existing CUDA stream (cudaStream_t as void*, e.g. torch's current
+ * stream) so callers can bracket it with their own events.  NULL = ctx-owned stream. */
+int  flacb200_set_stream(flacb200_ctx *ctx, void *cuda_stream);
+int  flacb200_sync(flacb200_ctx *ctx);
+
+/* libFLAC's init-time validation for these settings: returns the FLAC__StreamEncoderInitStatus
+ * value (0 = OK), pyflac/builder/encoder.py:65-80. */
+int  flacb200_enc_validate(const flacb200_enc_config *cfg);
+
+/* Encode n_streams independent streams.  Stream s = stream_samples[s] inter-channel samples starting
+ * at ELEMENT offset stream_off[s] of `pcm` (interleaved [sample][channel], container_bytes each).
+ * first_frame_number may be NULL (all zero).  Asynchronous on the ctx stream when pcm_is_device;
+ * results are fetched with flacb200_encode_result / flacb200_encode_fetch. */
+int  flacb200_encode_batch(flacb200_ctx *ctx, const flacb200_enc_config *cfg,
+                           const void *pcm, int pcm_is_device, uint64_t pcm_elems,
+                           uint32_t n_streams, const uint64_t *stream_off, const uint64_t *stream_samples,
+                           const uint32_t *first_frame_number);
+/* Synchronises, then reports sizes and device pointers. */
+int  flacb200_encode_result(flacb200_ctx *ctx, flacb200_enc_result *res);
+/* Copy results to host memory (any pointer may be NULL). arena_cap in bytes. */
+int  flacb200_encode_fetch(flacb200_ctx *ctx, uint8_t *arena, size_t arena_cap,
+                           uint64_t *frame_off, uint32_t *frame_len, uint32_t *frame_samples,
+                           uint32_t *frame_stream, flacb200_stream_info *streams);
+/* Debug: copy the analysis traces of the last batch (debug_trace=1). Layout = fb::SignalDebug / SubframePlan. */
+int  flacb200_encode_fetch_trace(flacb200_ctx *ctx, void *plans, size_t plans_bytes, uint8_t *frame_ca,
+                                 void *debug, size_t debug_bytes);
+/* One-call host->host convenience used for end-to-end timing: H2D, encode, D2H of the arena + index. */
+int  flacb200_encode_batch_host(flacb200_ctx *ctx, const flacb200_enc_config *cfg,
+                                const void *pcm_host, uint64_t pcm_elems,
+                                uint32_t n_streams, const uint64_t *stream_off, const uint64_t *stream_samples,
+                                uint8_t *arena, size_t arena_cap, uint64_t *total_bytes,
+                                uint64_t *frame_off, uint32_t *frame_len, flacb200_stream_info *streams);
+/* Kernel launches issued by this ctx so far (bench.py's gpu_launches). */
+uint64_t flacb200_launch_count(const flacb200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,214 @@
+"""ctypes binding of libflacb200.so (include/flacb200.h).
+
+The library is built in-tree by pyflac_b200/build.py (nvcc, sm_100a).  Importing this module never
+touches CUDA; creating an engine (``Engine()``) does and raises ``NoCudaDevice`` when no GPU is
+usable -- there is deliberately no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libflacb200.so")
+
+
+class NoCudaDevice(RuntimeError):
+    pass
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"flacb200 error {code}: {msg}")
+        self.code = code
+
+
+class EncConfig(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32),
+                ("compression_level", C.c_uint32), ("blocksize", C.c_uint32), ("container_bytes", C.c_uint32),
+                ("write_prologue", C.c_uint32), ("do_md5", C.c_uint32), ("streamable_subset", C.c_uint32),
+                ("debug_trace", C.c_uint32)]
+
+
+class StreamInfo(C.Structure):
+    _fields_ = [("total_samples", C.c_uint64), ("byte_off", C.c_uint64), ("byte_len", C.c_uint64),
+                ("min_framesize", C.c_uint32), ("max_framesize", C.c_uint32), ("n_frames", C.c_uint32),
+                ("pad", C.c_uint32), ("md5", C.c_uint8 * 16)]
+
+
+class EncResult(C.Structure):
+    _fields_ = [("total_bytes", C.c_uint64), ("n_frames", C.c_uint32), ("n_streams", C.c_uint32),
+                ("log_guard_hits", C.c_uint64), ("d_arena", C.c_void_p), ("d_frame_off", C.c_void_p),
+                ("d_frame_len", C.c_void_p)]
+
+
+K_MAX_ORDER, K_MAX_PARTS, K_MAX_APOD, K_MAX_LAGS = 12, 64, 9, 13
+
+
+class SubframePlan(C.Structure):
+    _fields_ = [("type", C.c_uint8), ("order", C.c_uint8), ("wasted", C.c_uint8), ("sbps", C.c_uint8),
+                ("precision", C.c_uint8), ("part_order", C.c_uint8), ("rice2", C.c_uint8), ("pad0", C.c_uint8),
+                ("shift", C.c_int32), ("bits_est", C.c_uint32), ("qlp", C.c_int32 * K_MAX_ORDER),
+                ("rice", C.c_uint8 * K_MAX_PARTS)]
+
+
+class SignalDebug(C.Structure):
+    _fields_ = [("fixed_err", C.c_uint64 * 5), ("fixed_order", C.c_int32), ("fixed_bits", C.c_uint32),
+                ("is_constant", C.c_int32), ("n_apod", C.c_int32),
+                ("autoc", (C.c_double * (K_MAX_LAGS + 1)) * K_MAX_APOD),
+                ("lpc_err", (C.c_double * K_MAX_ORDER) * K_MAX_APOD),
+                ("lpc_order", C.c_int32 * K_MAX_APOD), ("lpc_bits", C.c_uint32 * K_MAX_APOD)]
+
+
+assert C.sizeof(SubframePlan) == 128
+
+_lib = None
+
+
+def lib():
+    """Load libflacb200.so (building it first if the sources are newer and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    L = C.CDLL(LIB_PATH)
+    L.flacb200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.flacb200_destroy.argtypes = [C.c_void_p]
+    L.flacb200_last_error.restype = C.c_char_p
+    L.flacb200_last_error.argtypes = [C.c_void_p]
+    L.flacb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.flacb200_sync.argtypes = [C.c_void_p]
+    L.flacb200_enc_validate.argtypes = [C.POINTER(EncConfig)]
+    L.flacb200_encode_batch.argtypes = [C.c_void_p, C.POINTER(EncConfig), C.c_void_p, C.c_int, C.c_uint64, C.c_uint32,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    L.flacb200_encode_result.argtypes = [C.c_void_p, C.POINTER(EncResult)]
+    L.flacb200_encode_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+    L.flacb200_encode_fetch_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.flacb200_encode_batch_host.argtypes = [C.c_void_p, C.POINTER(EncConfig), C.c_void_p, C.c_uint64, C.c_uint32,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64),
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
+    L.flacb200_launch_count.restype = C.c_uint64
+    L.flacb200_launch_count.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+class Engine:
+    """One engine == one CUDA device context of the batch encoder/decoder."""
+
+    def __init__(self, device=0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.flacb200_create(C.byref(h), device)
+        if rc == 1:
+            raise NoCudaDevice("libflacb200: no usable CUDA device (this package has no CPU fallback)")
+        if rc != 0:
+            raise NativeError(rc, "flacb200_create failed")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.flacb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NativeError(rc, self._L.flacb200_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._L.flacb200_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        self._check(self._L.flacb200_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._L.flacb200_launch_count(self._h))
+
+    # ------------------------------------------------------------ encode
+    @staticmethod
+    def make_config(sample_rate, channels, bits_per_sample, compression_level=5, blocksize=0, container_bytes=None,
+                    write_prologue=True, do_md5=True, streamable_subset=True, debug_trace=False):
+        if container_bytes is None:
+            container_bytes = 2 if bits_per_sample <= 16 else 4
+        return EncConfig(sample_rate, channels, bits_per_sample, compression_level, blocksize, container_bytes,
+                         int(write_prologue), int(do_md5), int(streamable_subset), int(debug_trace))
+
+    def encode_device(self, cfg, pcm_ptr, pcm_elems, stream_off, stream_samples, first_frame_number=None):
+        """Asynchronous batch encode of PCM resident in HBM. stream_off/stream_samples: uint64 numpy arrays."""
+        so = np.ascontiguousarray(stream_off, np.uint64)
+        ss = np.ascontiguousarray(stream_samples, np.uint64)
+        ff = None if first_frame_number is None else np.ascontiguousarray(first_frame_number, np.uint32)
+        self._keep = (so, ss, ff)
+        self._check(self._L.flacb200_encode_batch(self._h, C.byref(cfg), C.c_void_p(pcm_ptr), 1, pcm_elems, len(so),
+                                                  so.ctypes.data, ss.ctypes.data, ff.ctypes.data if ff is not None else None))
+
+    def encode_host(self, cfg, pcm, stream_off, stream_samples, first_frame_number=None):
+        pcm = np.ascontiguousarray(pcm)
+        so = np.ascontiguousarray(stream_off, np.uint64)
+        ss = np.ascontiguousarray(stream_samples, np.uint64)
+        ff = None if first_frame_number is None else np.ascontiguousarray(first_frame_number, np.uint32)
+        self._keep = (pcm, so, ss, ff)
+        self._check(self._L.flacb200_encode_batch(self._h, C.byref(cfg), pcm.ctypes.data, 0, pcm.size, len(so),
+                                                  so.ctypes.data, ss.ctypes.data, ff.ctypes.data if ff is not None else None))
+
+    def result(self):
+        r = EncResult()
+        self._check(self._L.flacb200_encode_result(self._h, C.byref(r)))
+        return r
+
+    def fetch(self):
+        """-> dict(arena=uint8 array, frame_off, frame_len, frame_samples, frame_stream, streams=[StreamInfo])"""
+        r = self.result()
+        arena = np.empty(max(int(r.total_bytes), 1), np.uint8)
+        nf, ns = r.n_frames, r.n_streams
+        off = np.zeros(max(nf, 1), np.uint64)
+        ln = np.zeros(max(nf, 1), np.uint32)
+        smp = np.zeros(max(nf, 1), np.uint32)
+        stm = np.zeros(max(nf, 1), np.uint32)
+        infos = (StreamInfo * max(ns, 1))()
+        self._check(self._L.flacb200_encode_fetch(self._h, arena.ctypes.data, arena.size, off.ctypes.data, ln.ctypes.data,
+                                                  smp.ctypes.data, stm.ctypes.data, C.cast(infos, C.c_void_p)))
+        return dict(arena=arena[:int(r.total_bytes)], frame_off=off[:nf], frame_len=ln[:nf], frame_samples=smp[:nf],
+                    frame_stream=stm[:nf], streams=[infos[i] for i in range(ns)], log_guard_hits=int(r.log_guard_hits),
+                    total_bytes=int(r.total_bytes))
+
+    def fetch_trace(self, n_signals, want_debug=True):
+        r = self.result()
+        n = r.n_frames * n_signals
+        plans = (SubframePlan * max(n, 1))()
+        ca = np.zeros(max(r.n_frames, 1), np.uint8)
+        dbg = (SignalDebug * max(n, 1))() if want_debug else None
+        self._check(self._L.flacb200_encode_fetch_trace(self._h, C.cast(plans, C.c_void_p), C.sizeof(plans), ca.ctypes.data,
+                                                        C.cast(dbg, C.c_void_p) if dbg is not None else None,
+                                                        C.sizeof(dbg) if dbg is not None else 0))
+        return plans, ca[:r.n_frames], dbg
+
+
+def encode_streams(engine, streams, sample_rate, bits_per_sample, compression_level=5, blocksize=0, **kw):
+    """Convenience: encode a list of (n, ch) integer arrays -> list of bytes (complete .flac images)."""
+    chs = {(s.shape[1] if s.ndim == 2 else 1) for s in streams}
+    assert len(chs) == 1
+    ch = chs.pop()
+    dt = np.int16 if bits_per_sample <= 16 else np.int32
+    flat = [np.ascontiguousarray(s, dt).reshape(-1) for s in streams]
+    sizes = np.array([f.size for f in flat], np.uint64)
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64) if len(flat) else np.zeros(0, np.uint64)
+    pcm = np.concatenate(flat) if flat else np.zeros(0, dt)
+    cfg = Engine.make_config(sample_rate, ch, bits_per_sample, compression_level, blocksize,
+                             container_bytes=pcm.dtype.itemsize, **kw)
+    engine.encode_host(cfg, pcm, offs, sizes // ch)
+    out = engine.fetch()
+    res = []
+    for si in out["streams"]:
+        res.append(out["arena"][int(si.byte_off):int(si.byte_off + si.byte_len)].tobytes())
+    return res, out

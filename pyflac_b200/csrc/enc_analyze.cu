@@ -1,0 +1,473 @@
+// enc_analyze.cu -- encode analysis kernel: one CTA per frame, one warp per signal.
+//
+// For every signal (channel, or mid / side) the warp reproduces libFLAC 1.4.3's process_subframe_
+// decision sequence (SURVEY A.3-A.9, rows E2-E11 of the scope table): wasted bits, fixed-predictor
+// error sums, window + sequential-double autocorrelation, Levinson-Durbin, order guess, coefficient
+// quantisation, residual -> partition sums -> Rice parameter / partition-order search, and keeps the
+// candidate with the smallest libFLAC bit estimate.  Thread 0 then picks the channel assignment.
+// Output: one 128-byte SubframePlan per signal + one channel-assignment byte per frame.  The pack
+// kernel (enc_pack.cu) turns plans into bits.
+//
+// Exactness: integer work is exact; floating point follows fb_math.cuh (unfused, RN); the
+// autocorrelation is one DFMA chain per lag in ascending sample order (products of two floats are
+// exact in double, so fma == mul+add as libFLAC computes it).  No tensor cores: this is integer /
+// bit-serial work bounded by dependent-issue latency, not by a dense contraction.
+#include "fb_common.cuh"
+#include "fb_math.cuh"
+
+namespace fb {
+
+struct __align__(16) WarpScratch {
+    double   ring[64];                 // windowed samples as doubles, 2 x 32 rolling
+    double   ac[16];                   // autocorrelation of the current apodization step
+    double   lperr[kMaxOrder];         // Levinson error per order
+    double   lpc[kMaxOrder];           // Levinson recursion state
+    float    lp[kMaxOrder * kMaxOrder];
+    unsigned long long psum[2 * kMaxParts];   // partition |residual| sums, all orders (max order first)
+    int32_t  q[16];                    // quantised coefficients of the current candidate
+    int32_t  misc[8];
+    SubframePlan plan;                 // best candidate so far
+};
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ int load_pcm(const T* p, uint64_t idx) { return (int)__ldg(p + idx); }
+
+// r[i] = x[i] - ((sum_j q[j] * x[i-1-j]) >> shift) with partition sums of |r| at the maximum
+// partition order.  Fixed predictors are the same formula with binomial coefficients and shift 0
+// (up: fixed.c FLAC__fixed_compute_residual == lpc residual with q = {1},{2,-1},{3,-3,1},{4,-6,4,-1}).
+// WIDE: 64-bit accumulate (up: FLAC__lpc_compute_residual_from_qlp_coefficients_wide); the 32-bit
+// form is used exactly when libFLAC proves it cannot overflow (max_prediction_before_shift_bps <= 32).
+// check_limit reproduces the _limit_residual rejection (residual must fit int32, INT32_MIN excluded).
+template <int ORDER, bool WIDE>
+__device__ __forceinline__ bool residual_partition_sums(const int32_t* __restrict__ x, int N, const int32_t* qs,
+                                                        int shift, int psize, int nparts, bool narrow_sums,
+                                                        bool check_limit, unsigned long long* psum, int lane) {
+    int32_t q[ORDER > 0 ? ORDER : 1];
+#pragma unroll
+    for (int j = 0; j < ORDER; j++) q[j] = qs[j];
+    bool bad = false;
+    for (int p = 0; p < nparts; p++) {
+        int lo = p * psize;
+        const int hi = lo + psize;
+        if (p == 0) lo = ORDER;
+        unsigned long long acc = 0;
+        for (int i = lo + lane; i < hi; i += 32) {
+            long long r;
+            if (WIDE) {
+                long long s = 0;
+#pragma unroll
+                for (int j = 0; j < ORDER; j++) s += (long long)q[j] * (long long)x[i - 1 - j];
+                r = (long long)x[i] - (s >> shift);
+                if (check_limit && (r <= (long long)INT32_MIN || r > (long long)INT32_MAX)) bad = true;
+            } else {
+                int s = 0;
+#pragma unroll
+                for (int j = 0; j < ORDER; j++) s += q[j] * x[i - 1 - j];
+                r = (long long)(x[i] - (s >> shift));
+            }
+            acc += (unsigned long long)(r < 0 ? -r : r);
+        }
+        unsigned long long tot;
+        if (__reduce_or_sync(0xffffffffu, (unsigned)(acc >> 27)) == 0u) tot = __reduce_add_sync(0xffffffffu, (unsigned)acc);
+        else tot = warp_sum_u64(acc);
+        if (lane == 0) psum[p] = narrow_sums ? (tot & 0xffffffffull) : tot;
+    }
+    return __any_sync(0xffffffffu, bad);
+}
+
+template <bool WIDE>
+__device__ bool residual_dispatch(int order, const int32_t* x, int N, const int32_t* q, int shift, int psize,
+                                  int nparts, bool narrow, bool limit, unsigned long long* psum, int lane) {
+    switch (order) {
+        case 0: return residual_partition_sums<0, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 1: return residual_partition_sums<1, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 2: return residual_partition_sums<2, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 3: return residual_partition_sums<3, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 4: return residual_partition_sums<4, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 5: return residual_partition_sums<5, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 6: return residual_partition_sums<6, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 7: return residual_partition_sums<7, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 8: return residual_partition_sums<8, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 9: return residual_partition_sums<9, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 10: return residual_partition_sums<10, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 11: return residual_partition_sums<11, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        default: return residual_partition_sums<12, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+    }
+}
+
+// up: stream_encoder.c find_best_partition_order_ / set_partitioned_rice_: given the sums at
+// the maximum order in psum[0 .. 2^omax), search orders omax..0 (first strict minimum), merging pairwise.
+// Lane p owns partitions p and p+32.  Returns estimated residual bits; best parameters land in k0/k1.
+__device__ __forceinline__ uint32_t rice_search(unsigned long long* psum, int N, int pred_order, int omax,
+                                                uint32_t rice_limit, int lane, int* best_order_out,
+                                                uint32_t* k0_out, uint32_t* k1_out) {
+    uint32_t best_bits = 0, bk0 = 0, bk1 = 0;
+    int best_o = 0, off = 0;
+    for (int o = omax; o >= 0; o--) {
+        const int parts = 1 << o;
+        const uint32_t psb = (uint32_t)N >> o;
+        unsigned long long lane_bits = 0;
+        uint32_t k0 = 0, k1 = 0;
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const int p = lane + 32 * t;
+            if (p < parts) {
+                const uint32_t n = psb - (p == 0 ? (uint32_t)pred_order : 0u);
+                const unsigned long long s = psum[off + p];
+                const uint32_t k = rice_parameter(s, n, rice_limit);
+                lane_bits += rice_partition_bits(k, n, s);
+                if (t == 0) k0 = k; else k1 = k;
+            }
+        }
+        unsigned long long tot = warp_sum_u64(lane_bits) + 6ull;
+        const uint32_t bits = tot < 0xffffffffull ? (uint32_t)tot : 0xffffffffu;
+        if (best_bits == 0 || bits < best_bits) { best_bits = bits; best_o = o; bk0 = k0; bk1 = k1; }
+        if (o > 0) {
+            const int half = parts >> 1;
+            for (int p2 = lane; p2 < half; p2 += 32) psum[off + parts + p2] = psum[off + 2 * p2] + psum[off + 2 * p2 + 1];
+            off += parts;
+        }
+        __syncwarp();
+    }
+    *best_order_out = best_o; *k0_out = bk0; *k1_out = bk1;
+    return best_bits;
+}
+
+__device__ __forceinline__ uint32_t add_sat(uint32_t est, uint32_t bits) {
+    return bits < 0xffffffffu - est ? est + bits : 0xffffffffu;
+}
+
+// Sequential double autocorrelation of a windowed segment (up: lpc.c FLAC__lpc_compute_autocorrelation,
+// SURVEY A.6 / E5): lane j accumulates lag j over ascending i.  The segment is produced 32 samples at a
+// time into a rolling buffer of doubles (up: FLAC__lpc_window_data / _partial):
+//   i <  part          : x[dshift+i] * w[i]
+//   part <= i < 2*part : x[dshift+i] * w[N-2*part+i]
+//   i == 2*part        : 0                      (full window: part = N, nothing else applies)
+__device__ __forceinline__ double windowed_autoc(const int32_t* __restrict__ x, const float* __restrict__ w, int N,
+                                                 int dshift, int part, int len, int nlags, double* ring, int lane) {
+    double acc = 0.0;
+    const bool full = (part >= N);
+    for (int base = 0; base < len; base += 32) {
+        const int i = base + lane;
+        float d = 0.0f;
+        if (i < len) {
+            if (full) d = FB_FMUL(__int2float_rn(x[i]), __ldg(w + i));
+            else if (i < part) d = FB_FMUL(__int2float_rn(x[dshift + i]), __ldg(w + i));
+            else if (i < 2 * part) d = FB_FMUL(__int2float_rn(x[dshift + i]), __ldg(w + (N - 2 * part + i)));
+        }
+        ring[i & 63] = (double)d;
+        __syncwarp();
+        if (lane < nlags) {
+            const int cnt = min(32, len - base);
+            if (base >= 32 || lane == 0) {
+#pragma unroll 8
+                for (int s = 0; s < cnt; s++) {
+                    const int ii = base + s;
+                    acc = fma(ring[ii & 63], ring[(ii - lane) & 63], acc);
+                }
+            } else {
+                for (int s = lane; s < cnt; s++) {
+                    const int ii = base + s;
+                    acc = fma(ring[ii & 63], ring[(ii - lane) & 63], acc);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    return acc;
+}
+
+template <typename PcmT>
+__global__ void __launch_bounds__(32 * kMaxSignals)
+analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, const float* __restrict__ windows,
+               EncParams P, SubframePlan* __restrict__ plans, uint8_t* __restrict__ frame_ca,
+               SignalDebug* __restrict__ dbg, EncStats* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, sig = threadIdx.x >> 5;
+    const int nsig = (int)P.n_signals;
+    const FrameDesc fd = frames[blockIdx.x];
+    const int N = (int)fd.blocksize;
+    const int ch = (int)P.channels;
+
+    int32_t* xall = reinterpret_cast<int32_t*>(smem_raw);
+    WarpScratch* wsall = reinterpret_cast<WarpScratch*>(smem_raw + (size_t)nsig * P.smem_stride * 4);
+    uint32_t* sig_bits = reinterpret_cast<uint32_t*>(wsall + nsig);
+
+    // kMaxOrder zero words in front of every signal keep x[i-1-j] in bounds for the rare lanes whose
+    // results are discarded; real history never reads them (loops start at i >= order).
+    int32_t* x = xall + (size_t)sig * P.smem_stride + 16;
+    WarpScratch& ws = wsall[sig];
+    SignalDebug* dg = dbg ? dbg + (size_t)blockIdx.x * nsig + sig : nullptr;
+
+    // ---- load the signal, wasted bits (up: process_subframes_ + get_wasted_bits_) ----
+    uint32_t orv = 0;
+    {
+        const PcmT* base = pcm + fd.pcm_off;
+        for (int i = lane; i < N; i += 32) {
+            int v;
+            if (sig < ch) v = load_pcm(base, (uint64_t)i * ch + sig);
+            else {
+                const int l = load_pcm(base, (uint64_t)i * ch), r = load_pcm(base, (uint64_t)i * ch + 1);
+                v = (sig == ch) ? ((l + r) >> 1) : (l - r);
+            }
+            x[i] = v;
+            orv |= (uint32_t)v;
+        }
+    }
+    orv = __reduce_or_sync(0xffffffffu, orv);
+    int wasted = orv ? (__ffs((int)orv) - 1) : 0;
+    if (wasted > (int)P.bps) wasted = (int)P.bps;
+    const int sbps = (int)P.bps - wasted + ((P.do_mid_side && sig == ch + 1) ? 1 : 0);
+    __syncwarp();
+    if (wasted) {
+        for (int i = lane; i < N; i += 32) x[i] >>= wasted;
+        __syncwarp();
+    }
+
+    // ---- baseline: verbatim (up: evaluate_verbatim_subframe_) ----
+    reinterpret_cast<uint32_t*>(&ws.plan)[lane] = 0u;
+    __syncwarp();
+    uint32_t best_bits = 8u + (uint32_t)wasted + (uint32_t)N * (uint32_t)sbps;
+    if (lane == 0) {
+        SubframePlan& pl = ws.plan;
+        pl.type = kVerbatim; pl.order = 0; pl.wasted = (uint8_t)wasted; pl.sbps = (uint8_t)sbps;
+        pl.precision = 0; pl.part_order = 0; pl.rice2 = 0; pl.pad0 = 0; pl.shift = 0; pl.bits_est = best_bits;
+    }
+    if (dg && lane == 0) { dg->n_apod = 0; dg->fixed_bits = 0; dg->is_constant = 0; dg->fixed_order = 0; for (int k = 0; k < 5; k++) dg->fixed_err[k] = 0; }
+
+    // per-frame partition geometry (up: process_subframes_ max_partition_order = min(level max, ctz(N)))
+    int omax_frame = min((int)P.max_part_order, N ? (__ffs(N) - 1) : 0);
+
+    if (N > 4) {
+        // ---- fixed predictor error sums (up: fixed.c FLAC__fixed_compute_best_predictor[_wide]) ----
+        unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
+        for (int i = 4 + lane; i < N; i += 32) {
+            const int x0 = x[i], x1 = x[i - 1], x2 = x[i - 2], x3 = x[i - 3], x4 = x[i - 4];
+            const int a1 = x0 - x1, b1 = x1 - x2, c1 = x2 - x3, d1 = x3 - x4;
+            const int a2 = a1 - b1, b2 = b1 - c1, c2 = c1 - d1;
+            const int a3 = a2 - b2, b3 = b2 - c2;
+            const int a4 = a3 - b3;
+            e0 += (unsigned)abs(x0); e1 += (unsigned)abs(a1); e2 += (unsigned)abs(a2); e3 += (unsigned)abs(a3); e4 += (unsigned)abs(a4);
+        }
+        e0 = warp_sum_u64(e0); e1 = warp_sum_u64(e1); e2 = warp_sum_u64(e2); e3 = warp_sum_u64(e3); e4 = warp_sum_u64(e4);
+        const unsigned long long e1_true = e1;   // constant detection must not be fooled by the 32-bit wrap below
+        if ((uint32_t)sbps + ilog2_u32((uint32_t)N - 4u) + 1u < 32u) {   // libFLAC's 32-bit accumulators wrap
+            e0 &= 0xffffffffull; e1 &= 0xffffffffull; e2 &= 0xffffffffull; e3 &= 0xffffffffull; e4 &= 0xffffffffull;
+        }
+        int forder;
+        {
+            const unsigned long long m34 = min(e3, e4), m234 = min(e2, m34), m1234 = min(e1, m234);
+            if (e0 <= m1234) forder = 0; else if (e1 <= m234) forder = 1; else if (e2 <= m34) forder = 2; else if (e3 <= e4) forder = 3; else forder = 4;
+        }
+        bool constant = false;
+        if (e1_true == 0) {   // samples 3..N-1 are equal; the rest is 4 compares
+            constant = (x[0] == x[1]) && (x[1] == x[2]) && (x[2] == x[3]) && (x[3] == x[4]);
+        }
+        if (dg && lane == 0) { dg->fixed_err[0] = e0; dg->fixed_err[1] = e1; dg->fixed_err[2] = e2; dg->fixed_err[3] = e3; dg->fixed_err[4] = e4; dg->fixed_order = forder; dg->is_constant = constant; }
+
+        if (constant) {
+            const uint32_t bits = 8u + (uint32_t)wasted + (uint32_t)sbps;     // up: evaluate_constant_subframe_
+            if (bits < best_bits) { best_bits = bits; if (lane == 0) { ws.plan.type = kConstant; ws.plan.bits_est = bits; } }
+        } else {
+            // ---- fixed candidate at the guessed order (up: evaluate_fixed_subframe_) ----
+            {
+                int fo = forder; if (fo >= N) fo = N - 1;
+                int omax = omax_frame;
+                while (omax > 0 && (N >> omax) <= fo) omax--;
+                const int nparts = 1 << omax, psize = N >> omax;
+                const bool narrow = (uint32_t)sbps + 4u < 32u - ilog2_u32((uint32_t)psize);
+                if (lane == 0) {
+                    // binomial coefficients: x[i] - sum q_j x[i-1-j]
+                    const int32_t c[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+                    for (int j = 0; j < 4; j++) ws.q[j] = c[fo][j];
+                }
+                __syncwarp();
+                // fixed residual of <=24-bit input fits 32-bit arithmetic (|4th difference| < 2^(sbps+4))
+                if (sbps + 4 <= 31) residual_dispatch<false>(fo, x, N, ws.q, 0, psize, nparts, narrow, false, ws.psum, lane);
+                else residual_dispatch<true>(fo, x, N, ws.q, 0, psize, nparts, narrow, false, ws.psum, lane);
+                __syncwarp();
+                int po; uint32_t k0, k1;
+                const uint32_t rb = rice_search(ws.psum, N, fo, omax, P.rice_limit, lane, &po, &k0, &k1);
+                const uint32_t est = add_sat(8u + (uint32_t)wasted + (uint32_t)fo * (uint32_t)sbps, rb);
+                if (dg && lane == 0) dg->fixed_bits = est;
+                if (est < best_bits) {
+                    best_bits = est;
+                    SubframePlan& pl = ws.plan;
+                    if (lane < (1 << po)) pl.rice[lane] = (uint8_t)k0;
+                    if (lane + 32 < (1 << po)) pl.rice[lane + 32] = (uint8_t)k1;
+                    const bool r2 = __any_sync(0xffffffffu, (lane < (1 << po) && k0 >= 15u) || (lane + 32 < (1 << po) && k1 >= 15u));
+                    if (lane == 0) { pl.type = kFixed; pl.order = (uint8_t)fo; pl.part_order = (uint8_t)po; pl.rice2 = r2; pl.bits_est = est; pl.shift = 0; pl.precision = 0; }
+                }
+                __syncwarp();
+            }
+
+            // ---- LPC candidates, one per apodization step (up: apply_apodization_ + evaluate_lpc_subframe_) ----
+            if (P.max_lpc_order > 0) {
+                const int max_lpc = ((int)P.max_lpc_order >= N) ? N - 1 : (int)P.max_lpc_order;
+                const float* w = windows + fd.window_off;
+                double ac_root = 0.0, ac_cur = 0.0;     // lane j holds lag j
+                int step = 0;
+                // (b, c) walk of set_next_subdivide_tukey; b == 1 is the full window
+                int b = 1, c = 0;
+                bool done = false;
+                while (!done && max_lpc > 0) {
+                    int max_this = max_lpc;
+                    bool have = true;
+                    if (b == 1) {
+                        ac_cur = windowed_autoc(x, w, N, 0, N, N, max_this + 1, ws.ring, lane);
+                        if (P.apod_parts > 1) { ac_root = ac_cur; b = 2; c = 0; } else done = true;
+                    } else {
+                        if (N / b <= 32) have = false;
+                        else if (!(c & 1)) {
+                            const int part = N / b / 2, dshift = (c / 2 * N) / b;
+                            ac_cur = windowed_autoc(x, w, N, dshift, part, N / b, max_this + 1, ws.ring, lane);
+                        } else {
+                            // punch-out: root minus previous partial for lags < max order only (1.4.3 off-by-one)
+                            if (lane < max_this) ac_cur = FB_DSUB(ac_root, ac_cur);
+                        }
+                        if (b == 2) { if (c == 0) c = 2; else { c = 0; b++; } }
+                        else if (c < 2 * b - 1) c++;
+                        else { c = 0; b++; }
+                        if (b > (int)P.apod_parts) done = true;
+                    }
+                    if (!have) continue;
+                    if (lane <= max_this) ws.ac[lane] = ac_cur;
+                    __syncwarp();
+                    if (dg && step < kMaxApodSteps) { if (lane <= max_this) dg->autoc[step][lane] = ac_cur; if (lane == 0) { dg->lpc_order[step] = 0; dg->lpc_bits[step] = 0; } }
+                    if (ws.ac[0] == 0.0) { step++; continue; }
+
+                    if (lane == 0) ws.misc[0] = levinson(ws.ac, max_this, ws.lp, ws.lperr, ws.lpc);
+                    __syncwarp();
+                    max_this = ws.misc[0];
+
+                    // up: lpc.c FLAC__lpc_compute_best_order -- first strict minimum, initial best (uint32_t)-1
+                    int guess;
+                    {
+                        const double escale = FB_DDIV(0.5, (double)N);
+                        const uint32_t overhead = (uint32_t)sbps + P.qlp_precision;
+                        double bits = 1.7976931348623157e308; bool ul = false;
+                        if (lane >= 1 && lane <= max_this) {
+                            const double e = expected_bits_per_sample(ws.lperr[lane - 1], escale, &ul);
+                            bits = FB_DADD(FB_DMUL(e, (double)(N - lane)), (double)((uint32_t)lane * overhead));
+                        }
+                        double bb = bits; int bi = lane;
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) {
+                            const double ob = __shfl_xor_sync(0xffffffffu, bb, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (ob < bb || (ob == bb && oi < bi)) { bb = ob; bi = oi; }
+                        }
+                        guess = (bb < 4294967295.0) ? bi : 1;
+                        // guard band: a runner-up within 1e-9 relative of the winner could flip under a libm log that
+                        // differs in the last ulp (DESIGN.md "log guard"); counted, never silently ignored
+                        const int ul_best = __shfl_sync(0xffffffffu, (int)ul, guess & 31);
+                        const bool amb = (lane >= 1 && lane <= max_this && lane != guess) && (ul || ul_best) &&
+                                         fabs(bits - bb) <= 1e-9 * fabs(bb);
+                        if (__any_sync(0xffffffffu, amb) && lane == 0 && stats) atomicAdd(&stats->log_ambiguous, 1ull);
+                    }
+                    if (dg && step < kMaxApodSteps) { if (lane < max_this) dg->lpc_err[step][lane] = ws.lperr[lane]; if (lane == 0) dg->lpc_order[step] = guess; }
+
+                    const int order = guess;
+                    bool ul2;
+                    const double rbps = expected_bits_per_sample(ws.lperr[order - 1], FB_DDIV(0.5, (double)(N - order)), &ul2);
+                    if (ul2 && fabs(rbps - (double)sbps) <= 1e-9 * (double)sbps && lane == 0 && stats) atomicAdd(&stats->log_ambiguous, 1ull);
+                    if (!(rbps >= (double)sbps)) {
+                        int prec = (int)P.qlp_precision;
+                        if (sbps <= 17) prec = min(prec, 32 - sbps - (int)ilog2_u32((uint32_t)order));
+                        if (lane == 0) {
+                            int sh = 0;
+                            const int rc = quantize_coefficients(ws.lp + (order - 1) * kMaxOrder, order, prec, ws.q, &sh);
+                            int32_t asum = 0;
+                            for (int j = 0; j < order; j++) asum += abs(ws.q[j]);
+                            if (asum == 0) asum = 1;
+                            ws.misc[1] = rc; ws.misc[2] = sh; ws.misc[3] = (int)silog2((int64_t)asum);
+                        }
+                        __syncwarp();
+                        if (ws.misc[1] == 0) {
+                            const int shift = ws.misc[2];
+                            // up: lpc.c FLAC__lpc_max_prediction_before_shift_bps / FLAC__lpc_max_residual_bps
+                            const int pred_bps = sbps + ws.misc[3];
+                            const int resid_bps = ((sbps > pred_bps - shift) ? sbps : pred_bps - shift) + 1;
+                            const bool limit = resid_bps > 32;
+                            int omax = omax_frame;
+                            while (omax > 0 && (N >> omax) <= order) omax--;
+                            const int nparts = 1 << omax, psize = N >> omax;
+                            const bool narrow = (uint32_t)sbps + 4u < 32u - ilog2_u32((uint32_t)psize);
+                            bool rejected;
+                            if (!limit && pred_bps <= 32) rejected = residual_dispatch<false>(order, x, N, ws.q, shift, psize, nparts, narrow, false, ws.psum, lane);
+                            else rejected = residual_dispatch<true>(order, x, N, ws.q, shift, psize, nparts, narrow, limit, ws.psum, lane);
+                            __syncwarp();
+                            if (!rejected) {
+                                int po; uint32_t k0, k1;
+                                const uint32_t rb = rice_search(ws.psum, N, order, omax, P.rice_limit, lane, &po, &k0, &k1);
+                                const uint32_t est = add_sat(8u + (uint32_t)wasted + 4u + 5u + (uint32_t)order * (uint32_t)(prec + sbps), rb);
+                                if (dg && lane == 0 && step < kMaxApodSteps) dg->lpc_bits[step] = est;
+                                if (est < best_bits) {
+                                    best_bits = est;
+                                    SubframePlan& pl = ws.plan;
+                                    if (lane < (1 << po)) pl.rice[lane] = (uint8_t)k0;
+                                    if (lane + 32 < (1 << po)) pl.rice[lane + 32] = (uint8_t)k1;
+                                    const bool r2 = __any_sync(0xffffffffu, (lane < (1 << po) && k0 >= 15u) || (lane + 32 < (1 << po) && k1 >= 15u));
+                                    if (lane < order) pl.qlp[lane] = ws.q[lane];
+                                    if (lane == 0) { pl.type = kLpc; pl.order = (uint8_t)order; pl.part_order = (uint8_t)po; pl.rice2 = r2; pl.bits_est = est; pl.shift = shift; pl.precision = (uint8_t)prec; }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    step++;
+                }
+                if (dg && lane == 0) dg->n_apod = step;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- publish the plan ----
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&ws.plan);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(plans + (size_t)blockIdx.x * nsig + sig);
+        dst[lane] = src[lane];     // 128 bytes = 32 words
+        if (lane == 0) sig_bits[sig] = best_bits;
+    }
+    __syncthreads();
+
+    // ---- channel assignment (up: process_subframes_): first minimum of {L+R, L+S, R+S, M+S} ----
+    if (threadIdx.x == 0) {
+        int ca = 0;
+        if (P.do_mid_side) {
+            const uint32_t bL = sig_bits[0], bR = sig_bits[1], bM = sig_bits[2], bS = sig_bits[3];
+            uint32_t minb = bL + bR;
+            if (bL + bS < minb) { minb = bL + bS; ca = 1; }
+            if (bR + bS < minb) { minb = bR + bS; ca = 2; }
+            if (bM + bS < minb) { minb = bM + bS; ca = 3; }
+        }
+        frame_ca[blockIdx.x] = (uint8_t)ca;
+    }
+}
+
+// host-visible launcher (called from engine.cu)
+void launch_analyze(const void* pcm, const FrameDesc* frames, const float* windows, const EncParams& P, int n_frames,
+                    SubframePlan* plans, uint8_t* frame_ca, SignalDebug* dbg, EncStats* stats, size_t smem_bytes,
+                    cudaStream_t stream) {
+    const dim3 grid((unsigned)n_frames), block(32u * P.n_signals);
+    if (P.container_bytes == 2) {
+        cudaFuncSetAttribute(analyze_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        analyze_kernel<int16_t><<<grid, block, smem_bytes, stream>>>((const int16_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats);
+    } else {
+        cudaFuncSetAttribute(analyze_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        analyze_kernel<int32_t><<<grid, block, smem_bytes, stream>>>((const int32_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats);
+    }
+}
+
+size_t analyze_smem_bytes(const EncParams& P) {
+    return (size_t)P.n_signals * P.smem_stride * 4 + (size_t)P.n_signals * sizeof(WarpScratch) + 64;
+}
+
+}  // namespace fb

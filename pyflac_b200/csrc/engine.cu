@@ -1,0 +1,416 @@
+// engine.cu -- host side of the batch encoder: settings resolution, frame slicing, window tables,
+// device buffers, kernel sequencing.  C ABI in include/flacb200.h.
+//
+// Pipeline per batch (all on one CUDA stream, MD5 forked onto a side stream):
+//   [H2D pcm if host] -> analyze_kernel -> pack_kernel -> scan_kernel -> compact_kernel -> finalize_kernel
+//                     \-> md5_kernel ---------------------------------------------------/
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/flacb200.h"
+#include "fb_common.cuh"
+
+namespace fb {
+void launch_analyze(const void*, const FrameDesc*, const float*, const EncParams&, int, SubframePlan*, uint8_t*,
+                    SignalDebug*, EncStats*, size_t, cudaStream_t);
+size_t analyze_smem_bytes(const EncParams&);
+void launch_pack(const void*, const FrameDesc*, const EncParams&, int, const SubframePlan*, const uint8_t*, uint8_t*,
+                 uint32_t, uint32_t*, cudaStream_t);
+size_t pack_smem_bytes(const EncParams&, uint32_t);
+void launch_md5(const void*, uint32_t, const uint64_t*, const uint64_t*, int, uint32_t, uint32_t, uint8_t*, cudaStream_t);
+void launch_layout(const uint32_t*, const FrameDesc*, int, uint32_t, uint64_t*, uint64_t*, cudaStream_t);
+void launch_compact(const uint8_t*, uint32_t, const uint32_t*, const uint64_t*, uint8_t*, int, cudaStream_t);
+void launch_finalize(const uint32_t*, const uint64_t*, const uint32_t*, const uint32_t*, const uint64_t*, const uint8_t*,
+                     int, const EncParams&, uint32_t, uint8_t*, StreamInfoOut*, cudaStream_t);
+}  // namespace fb
+
+using namespace fb;
+
+// growable device buffer
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct flacb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr, md5_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int max_smem_optin = 0;
+
+    // last batch
+    EncParams P{};
+    flacb200_enc_config cfg{};
+    int n_frames = 0, n_streams = 0;
+    uint32_t scratch_stride = 0;
+    bool have_batch = false, debug = false;
+    std::vector<FrameDesc> h_frames;
+    std::vector<uint32_t> h_stream_first, h_stream_nframes;
+    std::vector<uint64_t> h_stream_off, h_stream_samples;
+    std::vector<uint32_t> h_first_frame;
+    std::vector<float> h_windows;
+    std::map<uint32_t, uint32_t> window_off;   // blocksize -> float offset in h_windows
+    float window_p = -1.0f;
+
+    DevBuf d_pcm, d_frames, d_windows, d_plans, d_ca, d_scratch, d_flen, d_foff, d_arena, d_total, d_stats;
+    DevBuf d_sfirst, d_snframes, d_soff, d_ssamples, d_md5, d_sinfo, d_debug;
+};
+
+static int fail(flacb200_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    if (c) c->err = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, FLACB200_ERR_CUDA, #call, e_); } while (0)
+
+// ---------------------------------------------------------------- settings ----
+// ref: pyflac/include/FLAC/stream_encoder.h:845-853 -- the compression-level table
+static const struct { int ms, loose; uint32_t max_lpc, max_po; int parts; } kLevels[9] = {
+    {0, 0, 0, 3, 1}, {1, 1, 0, 3, 1}, {1, 0, 0, 3, 1}, {0, 0, 6, 4, 1}, {1, 1, 8, 4, 1},
+    {1, 0, 8, 5, 1}, {1, 0, 8, 6, 2}, {1, 0, 12, 6, 2}, {1, 0, 12, 6, 3}};
+
+extern "C" int flacb200_enc_validate(const flacb200_enc_config* c) {
+    // order of checks follows FLAC__stream_encoder_init_stream (verified against the reference binary);
+    // values: pyflac/builder/encoder.py:65-80
+    if (c->channels == 0 || c->channels > 8) return 4;
+    if (c->bits_per_sample < 4 || c->bits_per_sample > 32) return 5;
+    if (c->sample_rate > 1048575u) return 6;
+    const uint32_t lvl = c->compression_level > 8 ? 8 : c->compression_level;
+    const uint32_t maxlpc = kLevels[lvl].max_lpc;
+    uint32_t bs = c->blocksize ? c->blocksize : (maxlpc == 0 ? 1152u : 4096u);
+    if (bs < 16 || bs > 65535) return 7;
+    if (bs < maxlpc) return 10;
+    if (c->streamable_subset) {
+        const uint32_t b = c->bits_per_sample;
+        if (!(b == 8 || b == 12 || b == 16 || b == 20 || b == 24 || b == 32)) return 11;
+        if (c->sample_rate <= 48000 && (bs > 4608 || maxlpc > 12)) return 11;
+        if (bs > 16384) return 11;
+    }
+    return 0;
+}
+
+static int resolve_params(flacb200_ctx* ctx, const flacb200_enc_config& c, EncParams& P) {
+    const int st = flacb200_enc_validate(&c);
+    if (st != 0) { char b[64]; snprintf(b, sizeof b, "init status %d", st); return fail(ctx, FLACB200_ERR_CONFIG, b); }
+    const uint32_t lvl = c.compression_level > 8 ? 8 : c.compression_level;
+    memset(&P, 0, sizeof P);
+    P.channels = c.channels; P.bps = c.bits_per_sample; P.sample_rate = c.sample_rate;
+    P.max_lpc_order = kLevels[lvl].max_lpc;
+    P.blocksize = c.blocksize ? c.blocksize : (P.max_lpc_order == 0 ? 1152u : 4096u);
+    P.do_mid_side = (kLevels[lvl].ms && c.channels == 2) ? 1u : 0u;
+    P.max_part_order = kLevels[lvl].max_po;
+    P.apod_parts = (uint32_t)kLevels[lvl].parts;
+    P.rice_limit = c.bits_per_sample > 16 ? 31u : 15u;
+    P.container_bytes = c.container_bytes;
+    P.n_signals = c.channels + (P.do_mid_side ? 2u : 0u);
+    if (c.bits_per_sample < 16) { uint32_t p = 2 + c.bits_per_sample / 2; P.qlp_precision = p < 5 ? 5 : p; }
+    else if (c.bits_per_sample == 16) {
+        const uint32_t b = P.blocksize;
+        P.qlp_precision = b <= 192 ? 7 : b <= 384 ? 8 : b <= 576 ? 9 : b <= 1152 ? 10 : b <= 2304 ? 11 : b <= 4608 ? 12 : 13;
+    } else {
+        const uint32_t b = P.blocksize;
+        P.qlp_precision = b <= 384 ? 13 : b <= 1152 ? 14 : 15;
+    }
+    // limits of this build (DESIGN.md "limits")
+    if (kLevels[lvl].loose && c.channels == 2) return fail(ctx, FLACB200_ERR_UNSUPPORTED, "loose mid/side (levels 1 and 4 on stereo) not built yet");
+    if (c.bits_per_sample > 24) return fail(ctx, FLACB200_ERR_UNSUPPORTED, "bits_per_sample > 24 not built yet");
+    if (c.container_bytes != 2 && c.container_bytes != 4) return fail(ctx, FLACB200_ERR_ARG, "container_bytes must be 2 or 4");
+    if (c.container_bytes == 2 && c.bits_per_sample > 16) return fail(ctx, FLACB200_ERR_ARG, "int16 container needs bits_per_sample <= 16");
+    P.smem_stride = ((P.blocksize + 16 + 3) / 4) * 4;
+    return 0;
+}
+
+// up: window.c FLAC__window_tukey -- generated on the host with the same libm cosf the reference
+// binary imports (cosf@GLIBC), never on the device
+static void window_tukey(float* w, int32_t L, float p) {
+    for (int32_t n = 0; n < L; n++) w[n] = 1.0f;
+    if (p <= 0.0f) return;
+    if (p >= 1.0f) { const int32_t N = L - 1; for (int32_t n = 0; n < L; n++) w[n] = (float)(0.5f - 0.5f * cosf(2.0f * (float)M_PI * n / N)); return; }
+    const int32_t Np = (int32_t)(p / 2.0f * L) - 1;
+    if (Np > 0) {
+        for (int32_t n = 0; n <= Np; n++) {
+            w[n] = (float)(0.5f - 0.5f * cosf((float)(M_PI * n / Np)));
+            w[L - Np - 1 + n] = (float)(0.5f - 0.5f * cosf((float)(M_PI * (n + Np) / Np)));
+        }
+    }
+}
+
+static uint32_t max_frame_bytes(const EncParams& P) {
+    // header <= 16, per channel: 8-bit subframe header + unary wasted + N*(bps+1) + Rice slack (N/2 + params), CRC-16
+    const uint64_t per_ch_bits = 8 + 32 + (uint64_t)P.blocksize * (P.bps + 1) + P.blocksize / 2 + 64 * 5 + 64;
+    uint64_t bytes = 16 + (uint64_t)P.channels * ((per_ch_bits + 7) / 8 + 1) + 2 + 16;
+    return (uint32_t)((bytes + 15) / 16 * 16);
+}
+
+// ---------------------------------------------------------------- ctx ----
+extern "C" int flacb200_create(flacb200_ctx** out, int device) {
+    if (!out) return FLACB200_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return FLACB200_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return FLACB200_ERR_ARG;
+    flacb200_ctx* ctx = new flacb200_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return FLACB200_ERR_NO_DEVICE; }
+    cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->md5_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return FLACB200_OK;
+}
+
+extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_pcm, &ctx->d_frames, &ctx->d_windows, &ctx->d_plans, &ctx->d_ca, &ctx->d_scratch, &ctx->d_flen,
+                      &ctx->d_foff, &ctx->d_arena, &ctx->d_total, &ctx->d_stats, &ctx->d_sfirst, &ctx->d_snframes, &ctx->d_soff,
+                      &ctx->d_ssamples, &ctx->d_md5, &ctx->d_sinfo, &ctx->d_debug};
+    for (DevBuf* b : bufs) b->release();
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->own_stream); cudaStreamDestroy(ctx->md5_stream);
+    delete ctx;
+}
+
+extern "C" const char* flacb200_last_error(const flacb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
+extern "C" int flacb200_set_stream(flacb200_ctx* ctx, void* s) { if (!ctx) return FLACB200_ERR_ARG; ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return 0; }
+extern "C" int flacb200_sync(flacb200_ctx* ctx) { if (!ctx) return FLACB200_ERR_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+extern "C" uint64_t flacb200_launch_count(const flacb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------- batch encode ----
+static bool same_layout(const flacb200_ctx* c, const flacb200_enc_config& cfg, uint32_t ns, const uint64_t* off,
+                        const uint64_t* smp, const uint32_t* ffn) {
+    if (!c->have_batch || memcmp(&c->cfg, &cfg, sizeof cfg) != 0 || (uint32_t)c->n_streams != ns) return false;
+    if (memcmp(c->h_stream_off.data(), off, ns * sizeof(uint64_t)) != 0) return false;
+    if (memcmp(c->h_stream_samples.data(), smp, ns * sizeof(uint64_t)) != 0) return false;
+    for (uint32_t s = 0; s < ns; s++) if (c->h_first_frame[s] != (ffn ? ffn[s] : 0u)) return false;
+    return true;
+}
+
+static int plan_batch(flacb200_ctx* ctx, const flacb200_enc_config& cfg, uint32_t ns, const uint64_t* off,
+                      const uint64_t* smp, const uint32_t* ffn) {
+    EncParams P;
+    int rc = resolve_params(ctx, cfg, P);
+    if (rc) return rc;
+    const float wp = P.apod_parts == 1 ? 0.5f : 0.5f / (float)P.apod_parts;   // up: set_apodization: p/parts in float
+    if (wp != ctx->window_p) { ctx->h_windows.clear(); ctx->window_off.clear(); ctx->window_p = wp; }
+    ctx->h_frames.clear();
+    ctx->h_stream_first.assign(ns, 0); ctx->h_stream_nframes.assign(ns, 0);
+    ctx->h_stream_off.assign(off, off + ns); ctx->h_stream_samples.assign(smp, smp + ns);
+    ctx->h_first_frame.assign(ns, 0);
+    bool windows_grew = false;
+    for (uint32_t s = 0; s < ns; s++) {
+        ctx->h_stream_first[s] = (uint32_t)ctx->h_frames.size();
+        ctx->h_first_frame[s] = ffn ? ffn[s] : 0u;
+        uint32_t fn = ctx->h_first_frame[s];
+        for (uint64_t done = 0; done < smp[s];) {
+            const uint32_t N = (smp[s] - done >= P.blocksize) ? P.blocksize : (uint32_t)(smp[s] - done);
+            FrameDesc fd;
+            fd.pcm_off = off[s] + done * P.channels;
+            fd.blocksize = N; fd.frame_number = fn++; fd.stream = s; fd.window_off = 0;
+            if (P.max_lpc_order > 0) {
+                auto it = ctx->window_off.find(N);
+                if (it == ctx->window_off.end()) {
+                    const uint32_t o = (uint32_t)ctx->h_windows.size();
+                    ctx->h_windows.resize(o + N);
+                    window_tukey(ctx->h_windows.data() + o, (int32_t)N, wp);
+                    it = ctx->window_off.emplace(N, o).first;
+                    windows_grew = true;
+                }
+                fd.window_off = it->second;
+            }
+            ctx->h_frames.push_back(fd);
+            done += N;
+        }
+        ctx->h_stream_nframes[s] = (uint32_t)ctx->h_frames.size() - ctx->h_stream_first[s];
+    }
+    ctx->P = P; ctx->cfg = cfg; ctx->n_streams = (int)ns; ctx->n_frames = (int)ctx->h_frames.size();
+    ctx->scratch_stride = max_frame_bytes(P);
+    ctx->debug = cfg.debug_trace != 0;
+
+    const size_t sa = analyze_smem_bytes(P), sp = pack_smem_bytes(P, ctx->scratch_stride);
+    if ((int)sa > ctx->max_smem_optin || (int)sp > ctx->max_smem_optin)
+        return fail(ctx, FLACB200_ERR_UNSUPPORTED, "blocksize x channels exceeds the shared-memory frame tile of this build");
+
+    const int nf = ctx->n_frames;
+    cudaStream_t st = ctx->stream;
+    CK(ctx->d_frames.reserve(sizeof(FrameDesc) * (size_t)(nf ? nf : 1)));
+    CK(ctx->d_plans.reserve(sizeof(SubframePlan) * (size_t)(nf ? nf : 1) * P.n_signals));
+    CK(ctx->d_ca.reserve((size_t)nf + 16));
+    CK(ctx->d_scratch.reserve((size_t)nf * ctx->scratch_stride + 64));
+    CK(ctx->d_flen.reserve(sizeof(uint32_t) * (size_t)(nf + 1)));
+    CK(ctx->d_foff.reserve(sizeof(uint64_t) * (size_t)(nf + 1)));
+    CK(ctx->d_arena.reserve((size_t)nf * ctx->scratch_stride + (size_t)ns * kStreamPrologueBytes + 64));
+    CK(ctx->d_total.reserve(64));
+    CK(ctx->d_stats.reserve(sizeof(EncStats)));
+    CK(ctx->d_sfirst.reserve(sizeof(uint32_t) * (ns + 1)));
+    CK(ctx->d_snframes.reserve(sizeof(uint32_t) * (ns + 1)));
+    CK(ctx->d_soff.reserve(sizeof(uint64_t) * (ns + 1)));
+    CK(ctx->d_ssamples.reserve(sizeof(uint64_t) * (ns + 1)));
+    CK(ctx->d_md5.reserve(16 * (size_t)(ns + 1)));
+    CK(ctx->d_sinfo.reserve(sizeof(StreamInfoOut) * (size_t)(ns + 1)));
+    if (ctx->debug) CK(ctx->d_debug.reserve(sizeof(SignalDebug) * (size_t)(nf ? nf : 1) * P.n_signals));
+    if (nf) CK(cudaMemcpyAsync(ctx->d_frames.p, ctx->h_frames.data(), sizeof(FrameDesc) * nf, cudaMemcpyHostToDevice, st));
+    if (ns) {
+        CK(cudaMemcpyAsync(ctx->d_sfirst.p, ctx->h_stream_first.data(), sizeof(uint32_t) * ns, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_snframes.p, ctx->h_stream_nframes.data(), sizeof(uint32_t) * ns, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_soff.p, ctx->h_stream_off.data(), sizeof(uint64_t) * ns, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_ssamples.p, ctx->h_stream_samples.data(), sizeof(uint64_t) * ns, cudaMemcpyHostToDevice, st));
+    }
+    if (windows_grew || (ctx->d_windows.cap < ctx->h_windows.size() * sizeof(float))) {
+        CK(ctx->d_windows.reserve(ctx->h_windows.size() * sizeof(float) + 64));
+        windows_grew = true;
+    }
+    if (windows_grew && !ctx->h_windows.empty())
+        CK(cudaMemcpyAsync(ctx->d_windows.p, ctx->h_windows.data(), ctx->h_windows.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    // the host vectors above are pageable: make sure the copies are done before they can change
+    CK(cudaStreamSynchronize(st));
+    ctx->have_batch = true;
+    return 0;
+}
+
+static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
+    const EncParams& P = ctx->P;
+    const int nf = ctx->n_frames, ns = ctx->n_streams;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(ctx->d_stats.p, 0, sizeof(EncStats), st));
+    CK(cudaMemsetAsync(ctx->d_total.p, 0, 8, st));
+    if (nf == 0) return 0;
+    const bool md5 = ctx->cfg.do_md5 != 0;
+    if (md5) {
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->md5_stream, ctx->ev_fork, 0));
+        launch_md5(d_pcm, P.container_bytes, (const uint64_t*)ctx->d_soff.p, (const uint64_t*)ctx->d_ssamples.p, ns, P.channels, P.bps,
+                   (uint8_t*)ctx->d_md5.p, ctx->md5_stream);
+        CK(cudaEventRecord(ctx->ev_join, ctx->md5_stream));
+        ctx->launches++;
+    }
+    launch_analyze(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, (SubframePlan*)ctx->d_plans.p,
+                   (uint8_t*)ctx->d_ca.p, ctx->debug ? (SignalDebug*)ctx->d_debug.p : nullptr, (EncStats*)ctx->d_stats.p,
+                   analyze_smem_bytes(P), st);
+    launch_pack(d_pcm, (const FrameDesc*)ctx->d_frames.p, P, nf, (const SubframePlan*)ctx->d_plans.p, (const uint8_t*)ctx->d_ca.p,
+                (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)ctx->d_flen.p, st);
+    const uint32_t pro = ctx->cfg.write_prologue ? (uint32_t)kStreamPrologueBytes : 0u;
+    launch_layout((const uint32_t*)ctx->d_flen.p, (const FrameDesc*)ctx->d_frames.p, nf, pro, (uint64_t*)ctx->d_foff.p,
+                  (uint64_t*)ctx->d_total.p, st);
+    launch_compact((const uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (const uint32_t*)ctx->d_flen.p, (const uint64_t*)ctx->d_foff.p,
+                   (uint8_t*)ctx->d_arena.p, nf, st);
+    if (md5) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    launch_finalize((const uint32_t*)ctx->d_flen.p, (const uint64_t*)ctx->d_foff.p, (const uint32_t*)ctx->d_sfirst.p,
+                    (const uint32_t*)ctx->d_snframes.p, (const uint64_t*)ctx->d_ssamples.p, md5 ? (const uint8_t*)ctx->d_md5.p : nullptr, ns, P,
+                    pro ? 1u : 0u, (uint8_t*)ctx->d_arena.p, (StreamInfoOut*)ctx->d_sinfo.p, st);
+    ctx->launches += 5;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int flacb200_encode_batch(flacb200_ctx* ctx, const flacb200_enc_config* cfg, const void* pcm, int pcm_is_device,
+                                     uint64_t pcm_elems, uint32_t n_streams, const uint64_t* stream_off,
+                                     const uint64_t* stream_samples, const uint32_t* first_frame_number) {
+    if (!ctx) return FLACB200_ERR_NO_DEVICE;
+    if (!cfg || (!pcm && pcm_elems) || (n_streams && (!stream_off || !stream_samples))) return fail(ctx, FLACB200_ERR_ARG, "null argument");
+    cudaSetDevice(ctx->device);
+    for (uint32_t s = 0; s < n_streams; s++)
+        if (stream_off[s] + stream_samples[s] * cfg->channels > pcm_elems) return fail(ctx, FLACB200_ERR_ARG, "stream exceeds pcm buffer");
+    if (!same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, first_frame_number)) {
+        ctx->have_batch = false;
+        int rc = plan_batch(ctx, *cfg, n_streams, stream_off, stream_samples, first_frame_number);
+        if (rc) return rc;
+    }
+    const void* d_pcm = pcm;
+    if (!pcm_is_device) {
+        const size_t bytes = (size_t)pcm_elems * cfg->container_bytes;
+        CK(ctx->d_pcm.reserve(bytes + 64));
+        CK(cudaMemcpyAsync(ctx->d_pcm.p, pcm, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_pcm = ctx->d_pcm.p;
+    }
+    return run_batch(ctx, d_pcm);
+}
+
+extern "C" int flacb200_encode_result(flacb200_ctx* ctx, flacb200_enc_result* res) {
+    if (!ctx || !res) return FLACB200_ERR_ARG;
+    if (!ctx->have_batch) return fail(ctx, FLACB200_ERR_ARG, "no batch");
+    cudaSetDevice(ctx->device);
+    uint64_t total = 0; EncStats stt{};
+    CK(cudaMemcpyAsync(&total, ctx->d_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&stt, ctx->d_stats.p, sizeof stt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    res->total_bytes = total; res->n_frames = (uint32_t)ctx->n_frames; res->n_streams = (uint32_t)ctx->n_streams;
+    res->log_guard_hits = stt.log_ambiguous;
+    res->d_arena = (const uint8_t*)ctx->d_arena.p; res->d_frame_off = (const uint64_t*)ctx->d_foff.p; res->d_frame_len = (const uint32_t*)ctx->d_flen.p;
+    return 0;
+}
+
+extern "C" int flacb200_encode_fetch(flacb200_ctx* ctx, uint8_t* arena, size_t arena_cap, uint64_t* frame_off, uint32_t* frame_len,
+                                     uint32_t* frame_samples, uint32_t* frame_stream, flacb200_stream_info* streams) {
+    flacb200_enc_result r;
+    int rc = flacb200_encode_result(ctx, &r);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    if (arena) {
+        if (arena_cap < r.total_bytes) return fail(ctx, FLACB200_ERR_ARG, "arena too small");
+        if (r.total_bytes) CK(cudaMemcpyAsync(arena, ctx->d_arena.p, r.total_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    const int nf = ctx->n_frames;
+    if (frame_off && nf) CK(cudaMemcpyAsync(frame_off, ctx->d_foff.p, sizeof(uint64_t) * nf, cudaMemcpyDeviceToHost, st));
+    if (frame_len && nf) CK(cudaMemcpyAsync(frame_len, ctx->d_flen.p, sizeof(uint32_t) * nf, cudaMemcpyDeviceToHost, st));
+    static_assert(sizeof(flacb200_stream_info) == sizeof(StreamInfoOut), "stream info layout");
+    if (streams && ctx->n_streams) CK(cudaMemcpyAsync(streams, ctx->d_sinfo.p, sizeof(StreamInfoOut) * ctx->n_streams, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int f = 0; f < nf; f++) {
+        if (frame_samples) frame_samples[f] = ctx->h_frames[f].blocksize;
+        if (frame_stream) frame_stream[f] = ctx->h_frames[f].stream;
+    }
+    return 0;
+}
+
+extern "C" int flacb200_encode_fetch_trace(flacb200_ctx* ctx, void* plans, size_t plans_bytes, uint8_t* frame_ca, void* debug, size_t debug_bytes) {
+    if (!ctx || !ctx->have_batch) return FLACB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const size_t np = sizeof(SubframePlan) * (size_t)ctx->n_frames * ctx->P.n_signals;
+    const size_t nd = sizeof(SignalDebug) * (size_t)ctx->n_frames * ctx->P.n_signals;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (plans) { if (plans_bytes < np) return fail(ctx, FLACB200_ERR_ARG, "plans buffer too small"); CK(cudaMemcpy(plans, ctx->d_plans.p, np, cudaMemcpyDeviceToHost)); }
+    if (frame_ca) CK(cudaMemcpy(frame_ca, ctx->d_ca.p, (size_t)ctx->n_frames, cudaMemcpyDeviceToHost));
+    if (debug) {
+        if (!ctx->debug) return fail(ctx, FLACB200_ERR_ARG, "batch was not run with debug_trace");
+        if (debug_bytes < nd) return fail(ctx, FLACB200_ERR_ARG, "debug buffer too small");
+        CK(cudaMemcpy(debug, ctx->d_debug.p, nd, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_config* cfg, const void* pcm_host, uint64_t pcm_elems,
+                                          uint32_t n_streams, const uint64_t* stream_off, const uint64_t* stream_samples,
+                                          uint8_t* arena, size_t arena_cap, uint64_t* total_bytes, uint64_t* frame_off,
+                                          uint32_t* frame_len, flacb200_stream_info* streams) {
+    int rc = flacb200_encode_batch(ctx, cfg, pcm_host, 0, pcm_elems, n_streams, stream_off, stream_samples, nullptr);
+    if (rc) return rc;
+    rc = flacb200_encode_fetch(ctx, arena, arena_cap, frame_off, frame_len, nullptr, nullptr, streams);
+    if (rc) return rc;
+    if (total_bytes) { flacb200_enc_result r; flacb200_encode_result(ctx, &r); *total_bytes = r.total_bytes; }
+    return 0;
+}
