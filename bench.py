@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: FLAC encode MSamples/s at compression_level=5 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], per GPU): 256 independent 48 kHz stereo int16 streams of 10 s
+(480 000 samples), blocksize 4096, level 5 -- 30 208 frames, 245.76 M channel-samples, 491.5 MB of PCM
+(larger than the 126 MB L2, so consecutive timed steps cannot be served from cache).
+One *step* = one pass of the whole encode path over the batch.  1 sample = 1 channel-sample.
+
+  value      device-resident throughput: PCM already in HBM -> packed .flac images in HBM, CUDA events on
+             the launching stream, max over ranks.
+  e2e        same metric through the C-ABI call with HOST (pinned) buffers: H2D of the PCM and D2H of the
+             packed bytes + index inside the timed region.
+  roofline   dominant kernel's algorithmic bytes (PCM read once + FLAC bytes written once) / its CUDA-event time
+             vs the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the reference's own libFLAC 1.4.3 (oracle/_ref) on the host cores, same PCM, bytes compared.
+
+Multi-GPU: streams are independent, so ranks shard them with no data-path collective (weak scaling: every
+rank encodes its own 256 streams); torch.distributed is used for the barrier and the max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_STREAMS = 256
+N_SAMPLES = 480000
+CHANNELS = 2
+SAMPLE_RATE = 48000
+BPS = 16
+LEVEL = 5
+BLOCKSIZE = 4096
+METRIC = "encode_msamples_per_s_level5"
+UNIT = "MSamples/s"
+
+
+def workload_config():
+    return {"workload": "StreamEncoder: 256 parallel 48kHz stereo int16 streams x 10 s, blocksize=4096, level=5 (BASELINE configs[1]) per GPU",
+            "n_streams_per_gpu": N_STREAMS, "samples_per_stream": N_SAMPLES, "channels": CHANNELS,
+            "bits_per_sample": BPS, "compression_level": LEVEL, "blocksize": BLOCKSIZE,
+            "l2_policy": "inputs (491.5 MB/step) larger than L2 (126 MB); no explicit flush",
+            "parallelism": "streams sharded across ranks, no data-path collective"}
+
+
+def make_pcm(rank, n_streams=N_STREAMS):
+    """Deterministic synthetic music-like PCM; 32 distinct seeds per rank, tiled with a
+    per-stream circular shift + gain so every stream is different but generation stays fast."""
+    from pyflac_b200.synth import music_like
+    base = [music_like(N_SAMPLES, CHANNELS, SAMPLE_RATE, BPS, seed=1000 * rank + s) for s in range(32)]
+    out = np.empty((n_streams, N_SAMPLES, CHANNELS), np.int16)
+    for s in range(n_streams):
+        b = base[s % 32]
+        k = s // 32
+        if k == 0:
+            out[s] = b
+        else:
+            out[s] = np.roll(b, 7919 * k, axis=0)
+            out[s] = (out[s].astype(np.int32) * (16 - k) // 16).astype(np.int16)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                if t0 <= t <= t1 + 0.2:
+                    sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            if t0 <= t <= t1 + 0.2:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(pcm, n_threads, keep_bytes=False):
+    """libFLAC 1.4.3 (the binary pyFLAC bundles) over pthreads -- test/bench infrastructure from oracle/_ref."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _checkers as ck
+    if not ck.ref_available():
+        ck.build_checkers()
+    return ck.ref_encode_mt(pcm, SAMPLE_RATE, BPS, LEVEL, BLOCKSIZE, n_threads, keep_bytes=keep_bytes)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation on the host cores, same config/metric."""
+    if rank != 0:
+        return
+    hw = host_threads()
+    n_sample = N_STREAMS
+    pcm = make_pcm(0, n_sample)
+    # pick the thread count libFLAC scales best with on this host (all hardware threads is not always it)
+    cand = sorted({max(1, hw // 4), max(1, hw // 2), hw})
+    probe = {t: cpu_reference_run(pcm, t)[0] for t in cand}
+    threads = min(probe, key=probe.get)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, _, _ = cpu_reference_run(pcm, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    val = n_sample * N_SAMPLES * CHANNELS / t / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32/f64 (libFLAC)", "data": "synthetic", "config": workload_config(),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": f"{n_sample} of the {N_STREAMS} streams per step, {threads} pthreads, libFLAC 1.4.3 from oracle/_ref"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pyflac_b200 import _native as nat
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    pcm = make_pcm(rank)
+    total_samples = pcm.size                       # channel-samples per rank per step
+    pcm_bytes = pcm.nbytes
+    h_pcm = torch.from_numpy(pcm.reshape(-1)).pin_memory()
+    d_pcm = h_pcm.to(dev, non_blocking=False)
+    stream_off = (np.arange(N_STREAMS, dtype=np.uint64) * np.uint64(N_SAMPLES * CHANNELS))
+    stream_samples = np.full(N_STREAMS, N_SAMPLES, np.uint64)
+
+    eng = nat.Engine(local_rank)
+    # a real (non-legacy) torch stream: the engine launches on it and torch.cuda.Event times that same stream
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    eng.set_stream(work_stream.cuda_stream)
+    eng.set_profiling(True)
+    cfg = nat.Engine.make_config(SAMPLE_RATE, CHANNELS, BPS, LEVEL, BLOCKSIZE, container_bytes=2)
+
+    def step_device():
+        eng.encode_device(cfg, d_pcm.data_ptr(), d_pcm.numel(), stream_off, stream_samples)
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    res = eng.result()
+    out_bytes = int(res.total_bytes)
+    guard_hits = int(res.log_guard_hits)
+
+    # ---------------- device-resident timing ----------------
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kt_acc = {}
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    kt_acc = eng.kernel_times()                    # per-kernel CUDA-event times of the last timed step
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # ---------------- end to end (host buffers through the C ABI) ----------------
+    arena_cap = pcm_bytes + (64 << 20)
+    h_arena = torch.empty(arena_cap, dtype=torch.uint8).pin_memory()
+    n_frames = int(res.n_frames)
+    h_foff = np.zeros(n_frames, np.uint64)
+    h_flen = np.zeros(n_frames, np.uint32)
+    infos = (nat.StreamInfo * N_STREAMS)()
+    import ctypes as C
+    tot = C.c_uint64(0)
+    L = nat.lib()
+
+    def step_e2e():
+        rc = L.flacb200_encode_batch_host(eng._h, C.byref(cfg), h_pcm.data_ptr(), h_pcm.numel(), N_STREAMS,
+                                          stream_off.ctypes.data, stream_samples.ctypes.data, h_arena.data_ptr(), arena_cap,
+                                          C.byref(tot), h_foff.ctypes.data, h_flen.ctypes.data, C.cast(infos, C.c_void_p))
+        if rc != 0:
+            raise RuntimeError(L.flacb200_last_error(eng._h).decode())
+
+    for _ in range(max(1, args.warmup - 1)):
+        step_e2e()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - e0
+    if world > 1:
+        dist.barrier()
+
+    # ---------------- reduce over ranks ----------------
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max, e2e_ms_max = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_per_step = ms_total_max / args.steps
+        value = world * total_samples / (ms_per_step * 1e-3) / 1e6
+        e2e_val = world * total_samples / (e2e_ms_max / args.steps * 1e-3) / 1e6
+        peak, peak_src = hbm_peak()
+        dom = max(("analyze", "pack", "md5"), key=lambda k: kt_acc.get(k, 0.0))
+        alg_bytes = pcm_bytes + out_bytes
+        achieved = alg_bytes / (kt_acc[dom] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 (+f32 window, f64 autocorrelation/Levinson, as libFLAC)", "data": "synthetic",
+            "config": workload_config(),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": pcm_bytes,
+                    "d2h_bytes_per_step": out_bytes + n_frames * 12 + N_STREAMS * 56, "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": kt_acc},
+            "frames_per_step": n_frames * world, "compressed_bytes_per_step": out_bytes, "ratio": out_bytes / pcm_bytes,
+            "log_guard_hits": guard_hits,
+        }
+        if not args.no_cpu_baseline:
+            threads = host_threads()
+            n_sample = N_STREAMS
+            _, _, blobs = cpu_reference_run(pcm[:n_sample], threads, keep_bytes=True)
+            # same-run byte equality of every stream against the GPU output of the last e2e step
+            arena = h_arena.numpy()
+            equal = all(bytes(arena[int(infos[s].byte_off): int(infos[s].byte_off + infos[s].byte_len)]) == blobs[s].tobytes()
+                        for s in range(n_sample))
+            del blobs
+            # libFLAC does not scale to every hardware thread on a shared box: report the best of a thread sweep
+            sweep = {}
+            for t in sorted({1, max(1, threads // 4), max(1, threads // 2), threads}):
+                best = min(cpu_reference_run(pcm[:n_sample] if t > 1 else pcm[:8], t)[0] for _ in range(2))
+                sweep[t] = (n_sample if t > 1 else 8) * N_SAMPLES * CHANNELS / best / 1e6
+            tbest = max(sweep, key=sweep.get)
+            line["cpu_baseline"] = {"value": sweep[tbest], "unit": UNIT, "cores": tbest, "kind": "reference",
+                                    "sample": f"all {n_sample} streams of the step (8 for the 1-thread point), one FLAC__StreamEncoder per pthread, "
+                                              f"libFLAC 1.4.3 from oracle/_ref; best of thread sweep",
+                                    "thread_sweep_msamples_per_s": {str(k): v for k, v in sweep.items()},
+                                    "host_threads": threads, "bytes_identical_to_gpu": bool(equal)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

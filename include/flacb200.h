@@ -110,6 +110,10 @@ int  flacb200_encode_batch_host(flacb200_ctx *ctx, const flacb200_enc_config *cf
                                 uint32_t n_streams, const uint64_t *stream_off, const uint64_t *stream_samples,
                                 uint8_t *arena, size_t arena_cap, uint64_t *total_bytes,
                                 uint64_t *frame_off, uint32_t *frame_len, flacb200_stream_info *streams);
+/* Per-kernel device times of the last batch, measured with CUDA events on the launching streams:
+ * ms[0..5] = analyze, pack, scan, compact, finalize(+MD5 join), md5 (side stream). */
+int  flacb200_set_profiling(flacb200_ctx *ctx, int on);
+int  flacb200_kernel_times(flacb200_ctx *ctx, float *ms);
 /* Kernel launches issued by this ctx so far (bench.py's gpu_launches). */
 uint64_t flacb200_launch_count(const flacb200_ctx *ctx);
 

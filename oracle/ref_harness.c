@@ -236,6 +236,7 @@ typedef struct {
     uint64_t nsamples;
     uint32_t n_streams, n_threads, tid;
     uint64_t bytes_out;
+    uint8_t *out_all; size_t out_stride; uint64_t *out_lens;   /* optional: keep every stream's bytes for comparison */
     int fail;
 } enc_job;
 
@@ -253,7 +254,11 @@ static void *enc_worker(void *arg)
             for (size_t i = 0; i < n; i++) wide[i] = p[i];
             src = wide;
         } else src = j->pcm + (size_t)s * n;
-        long r = ref_encode_stream(j->cfg, src, j->nsamples, 0, out, cap, 0, 0, 0, 0, 0);
+        long r;
+        if (j->out_all) {
+            r = ref_encode_stream(j->cfg, src, j->nsamples, 0, j->out_all + (size_t)s * j->out_stride, j->out_stride, 0, 0, 0, 0, 0);
+            if (r >= 0) j->out_lens[s] = (uint64_t)r;
+        } else r = ref_encode_stream(j->cfg, src, j->nsamples, 0, out, cap, 0, 0, 0, 0, 0);
         if (r < 0) j->fail = 1; else j->bytes_out += (uint64_t)r;
     }
     free(out); free(wide);
@@ -265,7 +270,8 @@ static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t
 /* Encode n_streams equal-length streams on n_threads pthreads (streams dealt round-robin).
  * Exactly one of pcm32 / pcm16 is non-NULL. Returns elapsed seconds (<0 on failure). */
 double ref_encode_mt(const ref_enc_cfg *cfg, const int32_t *pcm32, const int16_t *pcm16, uint64_t nsamples,
-                     uint32_t n_streams, uint32_t n_threads, uint64_t *bytes_out)
+                     uint32_t n_streams, uint32_t n_threads, uint64_t *bytes_out,
+                     uint8_t *out_all, size_t out_stride, uint64_t *out_lens)
 {
     pthread_t *th = (pthread_t *)calloc(n_threads, sizeof *th);
     enc_job *jobs = (enc_job *)calloc(n_threads, sizeof *jobs);
@@ -273,6 +279,7 @@ double ref_encode_mt(const ref_enc_cfg *cfg, const int32_t *pcm32, const int16_t
     for (uint32_t t = 0; t < n_threads; t++) {
         jobs[t].cfg = cfg; jobs[t].pcm = pcm32; jobs[t].pcm16 = pcm16; jobs[t].nsamples = nsamples;
         jobs[t].n_streams = n_streams; jobs[t].n_threads = n_threads; jobs[t].tid = t;
+        jobs[t].out_all = out_all; jobs[t].out_stride = out_stride; jobs[t].out_lens = out_lens;
         pthread_create(&th[t], 0, enc_worker, &jobs[t]);
     }
     uint64_t total = 0; int fail = 0;

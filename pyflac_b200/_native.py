@@ -90,6 +90,8 @@ def lib():
     L.flacb200_encode_batch_host.argtypes = [C.c_void_p, C.POINTER(EncConfig), C.c_void_p, C.c_uint64, C.c_uint32,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64),
                                              C.c_void_p, C.c_void_p, C.c_void_p]
+    L.flacb200_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.flacb200_kernel_times.argtypes = [C.c_void_p, C.c_void_p]
     L.flacb200_launch_count.restype = C.c_uint64
     L.flacb200_launch_count.argtypes = [C.c_void_p]
     _lib = L
@@ -129,6 +131,15 @@ class Engine:
 
     def sync(self):
         self._check(self._L.flacb200_sync(self._h))
+
+    def set_profiling(self, on=True):
+        self._check(self._L.flacb200_set_profiling(self._h, int(on)))
+
+    def kernel_times(self):
+        """Device ms of the last batch: dict(analyze, pack, scan, compact, finalize, md5)."""
+        ms = np.zeros(6, np.float32)
+        self._check(self._L.flacb200_kernel_times(self._h, ms.ctypes.data))
+        return dict(zip(["analyze", "pack", "scan", "compact", "finalize", "md5"], [float(v) for v in ms]))
 
     @property
     def launch_count(self):

@@ -14,19 +14,19 @@
 namespace fb {
 
 constexpr int kPackThreads = 256;
+constexpr int kPackWarps = kPackThreads / 32;
+constexpr int kTileK = 16;                                  // residuals kept in registers per thread and tile
+constexpr int kTileSamples = kPackThreads * kTileK;         // 4096 samples per tile
+constexpr int kSegSamples = 32 * kTileK;                    // contiguous samples owned by one warp within a tile
 
 struct PackShared {
     SubframePlan plan[kMaxChannels];
-    uint32_t partbits[kMaxChannels][kMaxParts];
-    uint32_t partstart[kMaxChannels][kMaxParts];
-    uint32_t sfstart[kMaxChannels];      // absolute bit where the subframe begins
-    uint32_t sfhdr[kMaxChannels];        // subframe bits before the first partition parameter
-    uint32_t sflen[kMaxChannels];
+    uint32_t segtot[kPackWarps];         // code bits produced by each warp in the current tile
     int32_t  sigidx[kMaxChannels];       // which analysed signal is coded as channel c
     uint16_t crc_tab[256];
-    uint16_t crc_part[kPackThreads];
+    uint16_t crc_warp[kPackWarps];
     uint8_t  hdr[16];
-    uint32_t hdr_len, total_bits, x1;
+    uint32_t hdr_len, x1;
 };
 
 __device__ __forceinline__ void put_bits(uint32_t* buf, uint32_t pos, uint32_t val, uint32_t n) {
@@ -41,20 +41,103 @@ __device__ __forceinline__ void put_bits(uint32_t* buf, uint32_t pos, uint32_t v
     }
 }
 
-// residual of coded channel c at sample i (i >= order); x = wasted-shifted coded signal
-__device__ __forceinline__ int32_t plan_residual(const SubframePlan& pl, const int32_t* __restrict__ x, int i) {
-    const int order = pl.order;
-    long long s = 0;
-    if (pl.type == kLpc) {
-        for (int j = 0; j < order; j++) s += (long long)pl.qlp[j] * (long long)x[i - 1 - j];
-        return (int32_t)((long long)x[i] - (s >> pl.shift));
+// Rice-coded body of one subframe (up: add_residual_partitioned_rice_ + FLAC__bitwriter_write_rice_signed_block).
+// The whole CTA works on one subframe at a time, tile by tile: thread (warp w, lane l) owns samples
+//   i = t0 + w*512 + k*32 + l,  k = 0..15
+// computes each residual ONCE (kept zig-zag folded in registers), the warp sums its code lengths, a
+// CTA barrier publishes the 8 segment totals, then every 32-sample group runs a warp-shuffle prefix
+// scan of code lengths to get absolute bit positions and ORs its codes into the frame image.
+//   bit position of sample i = body + (code bits of all earlier samples) + plen * (partition(i) + 1)
+// (a partition's parameter field sits right before its first sample's code).  Returns the body length in bits.
+// Residual arithmetic: r = x[i] - ((sum q_j x[i-1-j]) >> shift); fixed predictors are the same formula with
+// binomial coefficients and shift 0.  WIDE = 64-bit accumulate, chosen exactly as the analysis kernel does.
+template <int ORDER, bool WIDE>
+__device__ __forceinline__ uint32_t pack_rice_body(const SubframePlan& pl, const int32_t* __restrict__ qs, int shift,
+                                                   const int32_t* __restrict__ x, int N, uint32_t body, uint32_t* obuf,
+                                                   PackShared& S, int warp, int lane) {
+    int32_t q[ORDER > 0 ? ORDER : 1];
+#pragma unroll
+    for (int j = 0; j < ORDER; j++) q[j] = qs[j];
+    const uint32_t plen = pl.rice2 ? 5u : 4u;
+    const uint32_t psize = (uint32_t)N >> pl.part_order;
+    const uint32_t magic = (uint32_t)((0x100000000ull + psize - 1u) / psize);   // i / psize == umulhi(i, magic) for i, psize < 2^16
+    uint32_t done_bits = 0;                                                      // code bits of all previous tiles
+    for (int t0 = 0; t0 < N; t0 += kTileSamples) {
+        uint32_t u[kTileK];
+        uint32_t mybits = 0;
+        const int seg0 = t0 + warp * kSegSamples;
+#pragma unroll
+        for (int k = 0; k < kTileK; k++) {
+            const int i = seg0 + k * 32 + lane;
+            u[k] = 0xffffffffu;                                  // marks "no sample"
+            if (i >= ORDER && i < N) {
+                int32_t r;
+                if (WIDE) {
+                    long long sacc = 0;
+#pragma unroll
+                    for (int j = 0; j < ORDER; j++) sacc += (long long)q[j] * (long long)x[i - 1 - j];
+                    r = (int32_t)((long long)x[i] - (sacc >> shift));
+                } else {
+                    int sacc = 0;
+#pragma unroll
+                    for (int j = 0; j < ORDER; j++) sacc += q[j] * x[i - 1 - j];
+                    r = x[i] - (sacc >> shift);
+                }
+                const uint32_t uu = ((uint32_t)r << 1) ^ (uint32_t)(r >> 31);
+                const uint32_t kk = pl.rice[__umulhi((uint32_t)i, magic)];
+                u[k] = uu;
+                mybits += (uu >> kk) + 1u + kk;
+            }
+        }
+        mybits = __reduce_add_sync(0xffffffffu, mybits);
+        if (lane == 0) S.segtot[warp] = mybits;
+        __syncthreads();
+        uint32_t wpos = body + done_bits, tile_bits = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kPackWarps; w2++) { const uint32_t t = S.segtot[w2]; if (w2 < warp) wpos += t; tile_bits += t; }
+#pragma unroll
+        for (int k = 0; k < kTileK; k++) {
+            const int i = seg0 + k * 32 + lane;
+            const bool valid = (i >= ORDER && i < N);
+            uint32_t kk = 0, part = 0, len = 0;
+            if (valid) {
+                part = __umulhi((uint32_t)i, magic);
+                kk = pl.rice[part];
+                len = (u[k] >> kk) + 1u + kk;
+            }
+            uint32_t incl = len;                                  // warp-shuffle inclusive prefix scan of code lengths
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (valid) {
+                const uint32_t pos = wpos + (incl - len) + plen * (part + 1u);
+                put_bits(obuf, pos + (u[k] >> kk), (1u << kk) | (u[k] & ((1u << kk) - 1u)), kk + 1u);
+                if ((uint32_t)i == part * psize || i == ORDER) put_bits(obuf, pos - plen, kk, plen);   // first sample of its partition
+            }
+            wpos += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        done_bits += tile_bits;
+        __syncthreads();                                          // segtot is reused by the next tile / subframe
     }
+    return done_bits + plen * (1u << pl.part_order);
+}
+
+template <bool WIDE>
+__device__ uint32_t pack_rice_dispatch(int order, const SubframePlan& pl, const int32_t* q, int shift, const int32_t* x, int N,
+                                       uint32_t body, uint32_t* obuf, PackShared& S, int warp, int lane) {
     switch (order) {
-        case 0: return x[i];
-        case 1: return x[i] - x[i - 1];
-        case 2: return x[i] - 2 * x[i - 1] + x[i - 2];
-        case 3: return x[i] - 3 * x[i - 1] + 3 * x[i - 2] - x[i - 3];
-        default: return x[i] - 4 * x[i - 1] + 6 * x[i - 2] - 4 * x[i - 3] + x[i - 4];
+        case 0: return pack_rice_body<0, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        case 1: return pack_rice_body<1, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        case 2: return pack_rice_body<2, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        case 3: return pack_rice_body<3, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        case 4: return pack_rice_body<4, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        case 5: return pack_rice_body<5, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        case 6: return pack_rice_body<6, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        case 7: return pack_rice_body<7, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        case 8: return pack_rice_body<8, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        case 9: return pack_rice_body<9, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        case 10: return pack_rice_body<10, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        case 11: return pack_rice_body<11, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
+        default: return pack_rice_body<12, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
     }
 }
 
@@ -73,7 +156,7 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
     uint32_t* obuf = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ch * P.smem_stride * 4);
     PackShared& S = *reinterpret_cast<PackShared*>(smem_raw + (size_t)ch * P.smem_stride * 4 + (size_t)obuf_words * 4);
 
-    // ---- S0: zero the frame image, fetch plans, build header + CRC table ----
+    // ---- zero the frame image, CRC table, coded-signal map, frame header ----
     for (uint32_t i = tid; i < obuf_words; i += kPackThreads) obuf[i] = 0u;
     {
         uint16_t c = (uint16_t)(tid << 8);
@@ -99,7 +182,7 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
     }
     __syncthreads();
 
-    // ---- S1: rebuild the coded signals (wasted bits removed) ----
+    // ---- rebuild the coded signals (wasted bits removed) ----
     {
         const PcmT* base = pcm + fd.pcm_off;
         for (int c = 0; c < ch; c++) {
@@ -116,160 +199,112 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
             }
         }
     }
-    __syncthreads();
-
-    // ---- S3: exact bit length of every Rice partition (parameter field included) ----
-    for (int c = 0; c < ch; c++) {
-        const SubframePlan& pl = S.plan[c];
-        if (pl.type != kFixed && pl.type != kLpc) continue;
-        const int32_t* x = xall + (size_t)c * P.smem_stride;
-        const int parts = 1 << pl.part_order, psize = N >> pl.part_order, order = pl.order;
-        const uint32_t plen = pl.rice2 ? 5u : 4u;
-        for (int p = warp; p < parts; p += kPackThreads / 32) {
-            const uint32_t k = pl.rice[p];
-            int lo = p * psize; const int hi = lo + psize;
-            if (p == 0) lo = order;
-            uint32_t bits = 0;
-            for (int i = lo + lane; i < hi; i += 32) {
-                const int32_t r = plan_residual(pl, x, i);
-                const uint32_t u = ((uint32_t)r << 1) ^ (uint32_t)(r >> 31);
-                bits += (u >> k) + 1u + k;
-            }
-            bits = __reduce_add_sync(0xffffffffu, bits);
-            if (lane == 0) S.partbits[c][p] = bits + plen;
-        }
-    }
-    __syncthreads();
-
-    // ---- S4: subframe lengths and absolute bit positions ----
-    if (tid < ch) {
-        const SubframePlan& pl = S.plan[tid];
-        const uint32_t sbps = pl.sbps, order = pl.order;
-        uint32_t hdr = 8u + pl.wasted, len;
-        if (pl.type == kConstant) len = hdr + sbps;
-        else if (pl.type == kVerbatim) len = hdr + (uint32_t)N * sbps;
-        else {
-            hdr += order * sbps;
-            if (pl.type == kLpc) hdr += 4u + 5u + order * pl.precision;
-            len = hdr + 6u;
-            const int parts = 1 << pl.part_order;
-            for (int p = 0; p < parts; p++) len += S.partbits[tid][p];
-        }
-        S.sfhdr[tid] = hdr; S.sflen[tid] = len;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t pos = S.hdr_len * 8u;
-        for (int c = 0; c < ch; c++) { S.sfstart[c] = pos; pos += S.sflen[c]; }
-        S.total_bits = pos;
-    }
-    __syncthreads();
-    if (tid < ch) {
-        const SubframePlan& pl = S.plan[tid];
-        if (pl.type == kFixed || pl.type == kLpc) {
-            uint32_t pos = S.sfstart[tid] + S.sfhdr[tid] + 6u;
-            const int parts = 1 << pl.part_order;
-            for (int p = 0; p < parts; p++) { S.partstart[tid][p] = pos; pos += S.partbits[tid][p]; }
-        }
-    }
-    __syncthreads();
-
-    // ---- S5: emit ----
     if (tid < (int)S.hdr_len) put_bits(obuf, (uint32_t)tid * 8u, S.hdr[tid], 8);
-    if (tid >= 32 && tid < 32 + ch) {   // subframe headers, warm-up, predictor description: one thread per channel
-        const int c = tid - 32;
+    __syncthreads();
+
+    // ---- subframes, in channel order (each one starts where the previous one ended) ----
+    uint32_t pos = S.hdr_len * 8u;
+    for (int c = 0; c < ch; c++) {
         const SubframePlan& pl = S.plan[c];
         const int32_t* x = xall + (size_t)c * P.smem_stride;
         const uint32_t sbps = pl.sbps, order = pl.order, wf = pl.wasted ? 1u : 0u;
-        uint32_t pos = S.sfstart[c], tb;
-        switch (pl.type) {
-            case kConstant: tb = 0x00u; break;
-            case kVerbatim: tb = 0x02u; break;
-            case kFixed: tb = 0x10u | (order << 1); break;
-            default: tb = 0x40u | ((order - 1u) << 1); break;
-        }
-        put_bits(obuf, pos, tb | wf, 8); pos += 8;
-        if (pl.wasted) { put_bits(obuf, pos, 1u, pl.wasted); pos += pl.wasted; }   // unary: wasted-1 zeros, then 1
-        if (pl.type == kConstant) put_bits(obuf, pos, (uint32_t)x[0], sbps);
-        else if (pl.type != kVerbatim) {
-            for (uint32_t i = 0; i < order; i++) { put_bits(obuf, pos, (uint32_t)x[i], sbps); pos += sbps; }
-            if (pl.type == kLpc) {
-                put_bits(obuf, pos, (uint32_t)pl.precision - 1u, 4); pos += 4;
-                put_bits(obuf, pos, (uint32_t)pl.shift, 5); pos += 5;
-                for (uint32_t i = 0; i < order; i++) { put_bits(obuf, pos, (uint32_t)pl.qlp[i], pl.precision); pos += pl.precision; }
+        const uint32_t after_hdr = pos + 8u + pl.wasted;
+        if (warp == 0) {   // subframe header, warm-up, predictor description: one lane per field
+            if (lane == 0) {
+                uint32_t tb;
+                switch (pl.type) {
+                    case kConstant: tb = 0x00u; break;
+                    case kVerbatim: tb = 0x02u; break;
+                    case kFixed: tb = 0x10u | (order << 1); break;
+                    default: tb = 0x40u | ((order - 1u) << 1); break;
+                }
+                put_bits(obuf, pos, tb | wf, 8);
+                if (pl.wasted) put_bits(obuf, pos + 8u, 1u, pl.wasted);        // unary: wasted-1 zeros, then 1
+                if (pl.type == kConstant) put_bits(obuf, after_hdr, (uint32_t)x[0], sbps);
             }
-            put_bits(obuf, pos, pl.rice2 ? 1u : 0u, 2); pos += 2;
-            put_bits(obuf, pos, pl.part_order, 4);
+            if (pl.type == kFixed || pl.type == kLpc) {
+                if ((uint32_t)lane < order) put_bits(obuf, after_hdr + (uint32_t)lane * sbps, (uint32_t)x[lane], sbps);
+                uint32_t p2 = after_hdr + order * sbps;
+                if (pl.type == kLpc) {
+                    if (lane == 12) put_bits(obuf, p2, (((uint32_t)pl.precision - 1u) << 5) | ((uint32_t)pl.shift & 31u), 9);
+                    if (lane >= 16 && (uint32_t)(lane - 16) < order) put_bits(obuf, p2 + 9u + (uint32_t)(lane - 16) * pl.precision, (uint32_t)pl.qlp[lane - 16], pl.precision);
+                    p2 += 9u + order * pl.precision;
+                }
+                if (lane == 31) put_bits(obuf, p2, ((pl.rice2 ? 1u : 0u) << 4) | pl.part_order, 6);
+            }
         }
-    }
-    for (int c = 0; c < ch; c++) {
-        const SubframePlan& pl = S.plan[c];
-        const int32_t* x = xall + (size_t)c * P.smem_stride;
-        if (pl.type == kVerbatim) {
-            const uint32_t sbps = pl.sbps, base = S.sfstart[c] + 8u + pl.wasted;
-            for (int i = tid; i < N; i += kPackThreads) put_bits(obuf, base + (uint32_t)i * sbps, (uint32_t)x[i], sbps);
-        } else if (pl.type == kFixed || pl.type == kLpc) {
-            const int parts = 1 << pl.part_order, psize = N >> pl.part_order, order = pl.order;
-            const uint32_t plen = pl.rice2 ? 5u : 4u;
-            for (int p = warp; p < parts; p += kPackThreads / 32) {
-                const uint32_t k = pl.rice[p];
-                uint32_t pos = S.partstart[c][p];
-                if (lane == 0) put_bits(obuf, pos, k, plen);
-                pos += plen;
-                int lo = p * psize; const int hi = lo + psize;
-                if (p == 0) lo = order;
-                for (int i0 = lo; i0 < hi; i0 += 32) {
-                    const int i = i0 + lane;
-                    uint32_t u = 0, len = 0;
-                    if (i < hi) {
-                        const int32_t r = plan_residual(pl, x, i);
-                        u = ((uint32_t)r << 1) ^ (uint32_t)(r >> 31);
-                        len = (u >> k) + 1u + k;
-                    }
-                    uint32_t incl = len;     // warp-shuffle inclusive prefix scan of code lengths
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                    if (i < hi) put_bits(obuf, pos + (incl - len) + (u >> k), (1u << k) | (u & ((1u << k) - 1u)), k + 1u);
-                    pos += __shfl_sync(0xffffffffu, incl, 31);
+        if (pl.type == kConstant) pos = after_hdr + sbps;
+        else if (pl.type == kVerbatim) {
+            for (int i = tid; i < N; i += kPackThreads) put_bits(obuf, after_hdr + (uint32_t)i * sbps, (uint32_t)x[i], sbps);
+            pos = after_hdr + (uint32_t)N * sbps;
+        } else {
+            uint32_t body = after_hdr + order * sbps + 6u, blen;
+            if (pl.type == kLpc) {
+                body += 9u + order * pl.precision;
+                int32_t asum = 0;
+                for (uint32_t j = 0; j < order; j++) asum += abs(pl.qlp[j]);
+                if (asum == 0) asum = 1;
+                // same accumulator-width rule as the analysis kernel (up: FLAC__lpc_max_prediction_before_shift_bps)
+                if ((int)sbps + (int)silog2((int64_t)asum) <= 32) blen = pack_rice_dispatch<false>((int)order, pl, pl.qlp, pl.shift, x, N, body, obuf, S, warp, lane);
+                else blen = pack_rice_dispatch<true>((int)order, pl, pl.qlp, pl.shift, x, N, body, obuf, S, warp, lane);
+            } else {
+                const int32_t cfix[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+                switch (order) {
+                    case 0: blen = pack_rice_body<0, false>(pl, cfix[0], 0, x, N, body, obuf, S, warp, lane); break;
+                    case 1: blen = pack_rice_body<1, false>(pl, cfix[1], 0, x, N, body, obuf, S, warp, lane); break;
+                    case 2: blen = pack_rice_body<2, false>(pl, cfix[2], 0, x, N, body, obuf, S, warp, lane); break;
+                    case 3: blen = pack_rice_body<3, false>(pl, cfix[3], 0, x, N, body, obuf, S, warp, lane); break;
+                    default: blen = pack_rice_body<4, false>(pl, cfix[4], 0, x, N, body, obuf, S, warp, lane); break;
                 }
             }
+            pos = body + blen;
         }
     }
     __syncthreads();
 
-    // ---- S6: CRC-16 over the byte-padded frame, append, store ----
-    const uint32_t nb = (S.total_bits + 7u) >> 3;
+    // ---- CRC-16 over the byte-padded frame, append, store ----
+    const uint32_t nb = (pos + 7u) >> 3;
     const uint32_t csize = 64u * ((nb + 64u * kPackThreads - 1u) / (64u * kPackThreads));   // bytes per chunk, <= 256 chunks
     const uint32_t nchunks = (nb + csize - 1u) / csize;
-    if (tid == 0) {   // x^(8*csize) mod P by square-and-multiply
+    uint16_t xs;
+    {   // x^(8*csize) mod P by square-and-multiply (uniform, every thread computes it)
         uint16_t result = 1, basep = 2; uint32_t e = 8u * csize;
         while (e) { if (e & 1u) result = crc16_mulmod(result, basep); basep = crc16_mulmod(basep, basep); e >>= 1; }
-        S.x1 = result;
+        xs = result;
     }
+    uint16_t crc = 0;
     {
-        // chunk boundaries are aligned from the END of the frame (leading zero bytes do not change a CRC with init 0)
-        const int t = tid - (int)(kPackThreads - nchunks);     // real chunk index, < 0 => virtual empty chunk
-        uint16_t c = 0;
+        // chunk boundaries are aligned from the END of the frame (leading zero bytes do not change a CRC with init 0);
+        // thread t owns chunk t - (256 - nchunks); lower threads own virtual empty chunks
+        const int t = tid - (int)(kPackThreads - nchunks);
         if (t >= 0) {
             const long long end = (long long)nb - (long long)(nchunks - 1u - (uint32_t)t) * csize;
             long long beg = end - csize; if (beg < 0) beg = 0;
             for (long long j = beg; j < end; j++) {
-                const uint8_t b = (uint8_t)(obuf[j >> 2] >> (24 - 8 * (int)(j & 3)));
-                c = (uint16_t)((c << 8) ^ S.crc_tab[(c >> 8) ^ b]);
+                const uint8_t bb = (uint8_t)(obuf[j >> 2] >> (24 - 8 * (int)(j & 3)));
+                crc = (uint16_t)((crc << 8) ^ S.crc_tab[(crc >> 8) ^ bb]);
             }
         }
-        S.crc_part[tid] = c;
     }
+    // combine: crc(A||B) = crc(A) * x^(8|B|) + crc(B) in GF(2)[x]/(x^16+x^15+x^2+1); tree over lanes, then over warps
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const uint16_t other = (uint16_t)__shfl_down_sync(0xffffffffu, (uint32_t)crc, s);
+        if ((lane & (2 * s - 1)) == 0) crc = (uint16_t)(crc16_mulmod(crc, xs) ^ other);
+        xs = crc16_mulmod(xs, xs);
+    }
+    if (lane == 0) S.crc_warp[warp] = crc;
     __syncthreads();
-    {
-        uint16_t xs = (uint16_t)S.x1;
-        for (int s = 1; s < kPackThreads; s <<= 1) {
-            if ((tid & (2 * s - 1)) == 0) S.crc_part[tid] = (uint16_t)(crc16_mulmod(S.crc_part[tid], xs) ^ S.crc_part[tid + s]);
+    if (warp == 0) {
+        uint16_t c2 = lane < kPackWarps ? S.crc_warp[lane] : (uint16_t)0;
+#pragma unroll
+        for (int s = 1; s < kPackWarps; s <<= 1) {
+            const uint16_t other = (uint16_t)__shfl_down_sync(0xffffffffu, (uint32_t)c2, s);
+            if ((lane & (2 * s - 1)) == 0) c2 = (uint16_t)(crc16_mulmod(c2, xs) ^ other);
             xs = crc16_mulmod(xs, xs);
-            __syncthreads();
         }
+        if (lane == 0) put_bits(obuf, nb * 8u, c2, 16);
     }
-    if (tid == 0) put_bits(obuf, nb * 8u, S.crc_part[0], 16);
     __syncthreads();
     {
         const uint32_t total = nb + 2u;
@@ -403,7 +438,6 @@ __global__ void finalize_kernel(const uint32_t* __restrict__ frame_len, const ui
 // Serial per stream by construction (Merkle-Damgard chain); one thread per stream, runs on a side
 // CUDA stream concurrently with analysis/packing.  `state` carries (a,b,c,d,len,buffered bytes)
 // across calls so that streaming callers can feed a stream in pieces.
-struct Md5State { uint32_t h[4]; uint64_t len; uint32_t fill; uint8_t buf[64]; uint32_t pad; };
 
 __device__ __forceinline__ uint32_t rotl32(uint32_t v, int s) { return __funnelshift_l(v, v, s); }
 
@@ -418,7 +452,8 @@ __device__ void md5_block(uint32_t h[4], const uint32_t w[16]) {
         0xf4292244,0x432aff97,0xab9423a7,0xfc93a039,0x655b59c3,0x8f0ccc92,0xffeff47d,0x85845dd1,
         0x6fa87e4f,0xfe2ce6e0,0xa3014314,0x4e0811a1,0xf7537e82,0xbd3af235,0x2ad7d2bb,0xeb86d391 };
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3];
-#define FB_MD5_STEP(f, g, s, i) { uint32_t t = a + (f) + K[i] + w[g]; a = d; d = c; c = b; b = b + rotl32(t, s); }
+// critical path per step: LOP3 (f depends on the fresh b) -> IADD -> SHF -> IADD; a + K + w[g] is ready early
+#define FB_MD5_STEP(f, g, s, i) { const uint32_t akw = a + (K[i] + w[g]); const uint32_t t = akw + (f); a = d; d = c; c = b; b = b + rotl32(t, s); }
 #pragma unroll
     for (int i = 0; i < 16; i++) { const int sh[4] = {7, 12, 17, 22}; FB_MD5_STEP((b & c) | (~b & d), i, sh[i & 3], i) }
 #pragma unroll
@@ -431,6 +466,37 @@ __device__ void md5_block(uint32_t h[4], const uint32_t w[16]) {
     h[0] += a; h[1] += b; h[2] += c; h[3] += d;
 }
 
+// Generic feeder: packs (bps+7)/8 little-endian bytes of each sample into 32-bit words, one sample at a time.
+struct Md5Feeder {
+    uint32_t h[4]; uint32_t w[16]; uint64_t acc; uint32_t accbits, widx;
+    __device__ void init() { h[0] = 0x67452301u; h[1] = 0xefcdab89u; h[2] = 0x98badcfeu; h[3] = 0x10325476u; acc = 0; accbits = 0; widx = 0; }
+    __device__ void flush_words() {
+        while (accbits >= 32) {
+            // static indexing keeps w[] in registers
+#pragma unroll
+            for (int t = 0; t < 16; t++) if ((int)widx == t) w[t] = (uint32_t)acc;
+            widx++; acc >>= 32; accbits -= 32;
+            if (widx == 16) { md5_block(h, w); widx = 0; }
+        }
+    }
+    __device__ void push(uint32_t v, uint32_t nbytes) {
+        acc |= (uint64_t)(nbytes == 4 ? v : (v & ((1u << (8 * nbytes)) - 1u))) << accbits;
+        accbits += 8 * nbytes;
+        flush_words();
+    }
+    __device__ void finish(uint64_t total_bytes, uint8_t* out) {
+        push(0x80u, 1);
+        while (!(accbits == 0 && widx == 14)) push(0u, 1);
+        w[14] = (uint32_t)(total_bytes * 8ull); w[15] = (uint32_t)((total_bytes * 8ull) >> 32);
+        md5_block(h, w);
+        for (int i = 0; i < 16; i++) out[i] = (uint8_t)(h[i >> 2] >> (8 * (i & 3)));
+    }
+};
+
+// One thread per stream.  Fast path (the container bytes ARE the hashed bytes: int16 container with 16-bit
+// samples, int32 with 32-bit): 64-byte blocks are fetched with four 16-byte loads and the next block is
+// prefetched while the current one is hashed, so the serial MD5 chain (about 16 dependent-issue cycles per
+// step, 64 steps per block) is the only thing on the critical path.
 template <typename PcmT>
 __global__ void md5_kernel(const PcmT* __restrict__ pcm, const uint64_t* __restrict__ stream_pcm_off,
                            const uint64_t* __restrict__ stream_samples, int n_streams, uint32_t channels, uint32_t bps,
@@ -440,34 +506,27 @@ __global__ void md5_kernel(const PcmT* __restrict__ pcm, const uint64_t* __restr
     const uint32_t bytes_per = (bps + 7) / 8;
     const PcmT* p = pcm + stream_pcm_off[s];
     const uint64_t nvals = stream_samples[s] * channels;
-    uint32_t h[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
-    uint32_t w[16];
-    uint64_t acc = 0; uint32_t accbits = 0, widx = 0;
-    for (uint64_t i = 0; i < nvals; i++) {
-        const uint32_t v = (uint32_t)(int)__ldg(p + i);
-        acc |= (uint64_t)(bytes_per == 4 ? v : (v & ((1u << (8 * bytes_per)) - 1u))) << accbits;
-        accbits += 8 * bytes_per;
-        if (accbits >= 32) {
-            w[widx++] = (uint32_t)acc; acc >>= 32; accbits -= 32;
-            if (widx == 16) { md5_block(h, w); widx = 0; }
+    Md5Feeder f; f.init();
+    uint64_t i = 0;
+    if (bytes_per == sizeof(PcmT) && (((uintptr_t)p) & 15u) == 0) {
+        const uint64_t nblocks = (nvals * sizeof(PcmT)) / 64;
+        const uint4* p4 = reinterpret_cast<const uint4*>(p);
+        uint4 n0, n1, n2, n3;
+        if (nblocks) { n0 = __ldg(p4); n1 = __ldg(p4 + 1); n2 = __ldg(p4 + 2); n3 = __ldg(p4 + 3); }
+        for (uint64_t b = 0; b < nblocks; b++) {
+            uint32_t w[16] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, n3.z, n3.w};
+            if (b + 1 < nblocks) { const uint4* q4 = p4 + 4 * (b + 1); n0 = __ldg(q4); n1 = __ldg(q4 + 1); n2 = __ldg(q4 + 2); n3 = __ldg(q4 + 3); }
+            md5_block(f.h, w);
         }
+        i = nblocks * (64 / sizeof(PcmT));
     }
-    // padding: 0x80, zeros, 64-bit bit length
-    const uint64_t total_bits = nvals * bytes_per * 8ull;
-    acc |= (uint64_t)0x80 << accbits; accbits += 8;
-    for (;;) {
-        while (accbits >= 32) { w[widx++] = (uint32_t)acc; acc >>= 32; accbits -= 32; if (widx == 16) { md5_block(h, w); widx = 0; } }
-        if (accbits == 0 && widx == 14) break;
-        // pad one zero byte at a time until 56 mod 64
-        accbits += 8;
-    }
-    w[14] = (uint32_t)total_bits; w[15] = (uint32_t)(total_bits >> 32);
-    md5_block(h, w);
-    for (int i = 0; i < 16; i++) digest_out[(size_t)s * 16 + i] = (uint8_t)(h[i >> 2] >> (8 * (i & 3)));
+    for (; i < nvals; i++) f.push((uint32_t)(int)__ldg(p + i), bytes_per);
+    f.finish(nvals * bytes_per, digest_out + (size_t)s * 16);
 }
 
 void launch_md5(const void* pcm, uint32_t container_bytes, const uint64_t* stream_pcm_off, const uint64_t* stream_samples,
                 int n_streams, uint32_t channels, uint32_t bps, uint8_t* digest_out, cudaStream_t stream) {
+    // one warp per CTA: the chains are latency-bound, spreading them over SMs costs nothing
     const int threads = 32, blocks = (n_streams + threads - 1) / threads;
     if (container_bytes == 2) md5_kernel<int16_t><<<blocks, threads, 0, stream>>>((const int16_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
     else md5_kernel<int32_t><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);

@@ -20,6 +20,7 @@ namespace fb {
 void launch_analyze(const void*, const FrameDesc*, const float*, const EncParams&, int, SubframePlan*, uint8_t*,
                     SignalDebug*, EncStats*, size_t, cudaStream_t);
 size_t analyze_smem_bytes(const EncParams&);
+void analyze_layout(EncParams&);
 void launch_pack(const void*, const FrameDesc*, const EncParams&, int, const SubframePlan*, const uint8_t*, uint8_t*,
                  uint32_t, uint32_t*, cudaStream_t);
 size_t pack_smem_bytes(const EncParams&, uint32_t);
@@ -51,6 +52,8 @@ struct flacb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr, md5_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool profiling = false;
+    cudaEvent_t ev_k[8] = {nullptr};       // analyze start, analyze end, pack end, layout end, compact end, finalize end, md5 start, md5 end
     std::string err;
     uint64_t launches = 0;
     int max_smem_optin = 0;
@@ -135,7 +138,8 @@ static int resolve_params(flacb200_ctx* ctx, const flacb200_enc_config& c, EncPa
     if (c.bits_per_sample > 24) return fail(ctx, FLACB200_ERR_UNSUPPORTED, "bits_per_sample > 24 not built yet");
     if (c.container_bytes != 2 && c.container_bytes != 4) return fail(ctx, FLACB200_ERR_ARG, "container_bytes must be 2 or 4");
     if (c.container_bytes == 2 && c.bits_per_sample > 16) return fail(ctx, FLACB200_ERR_ARG, "int16 container needs bits_per_sample <= 16");
-    P.smem_stride = ((P.blocksize + 16 + 3) / 4) * 4;
+    P.smem_stride = ((P.blocksize + 3) / 4) * 4;
+    analyze_layout(P);
     return 0;
 }
 
@@ -177,6 +181,7 @@ extern "C" int flacb200_create(flacb200_ctx** out, int device) {
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    for (auto& e : ctx->ev_k) cudaEventCreate(&e);
     ctx->stream = ctx->own_stream;
     *out = ctx;
     return FLACB200_OK;
@@ -191,6 +196,7 @@ extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
                       &ctx->d_ssamples, &ctx->d_md5, &ctx->d_sinfo, &ctx->d_debug};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    for (auto& e : ctx->ev_k) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own_stream); cudaStreamDestroy(ctx->md5_stream);
     delete ctx;
 }
@@ -198,6 +204,18 @@ extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
 extern "C" const char* flacb200_last_error(const flacb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
 extern "C" int flacb200_set_stream(flacb200_ctx* ctx, void* s) { if (!ctx) return FLACB200_ERR_ARG; ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return 0; }
 extern "C" int flacb200_sync(flacb200_ctx* ctx) { if (!ctx) return FLACB200_ERR_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+extern "C" int flacb200_set_profiling(flacb200_ctx* ctx, int on) { if (!ctx) return FLACB200_ERR_ARG; ctx->profiling = on != 0; return 0; }
+// ms[0..5] = analyze, pack, layout(scan), compact, finalize (incl. waiting for MD5), md5 (side stream) of the last batch
+extern "C" int flacb200_kernel_times(flacb200_ctx* ctx, float* ms) {
+    if (!ctx || !ms || !ctx->profiling || !ctx->have_batch) return FLACB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->md5_stream));
+    for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&ms[i], ctx->ev_k[i], ctx->ev_k[i + 1]));
+    ms[5] = 0.0f;
+    if (ctx->cfg.do_md5) CK(cudaEventElapsedTime(&ms[5], ctx->ev_k[6], ctx->ev_k[7]));
+    return 0;
+}
 extern "C" uint64_t flacb200_launch_count(const flacb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---------------------------------------------------------------- batch encode ----
@@ -303,25 +321,34 @@ static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
     if (md5) {
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->md5_stream, ctx->ev_fork, 0));
+        if (ctx->profiling) CK(cudaEventRecord(ctx->ev_k[6], ctx->md5_stream));
         launch_md5(d_pcm, P.container_bytes, (const uint64_t*)ctx->d_soff.p, (const uint64_t*)ctx->d_ssamples.p, ns, P.channels, P.bps,
                    (uint8_t*)ctx->d_md5.p, ctx->md5_stream);
+        if (ctx->profiling) CK(cudaEventRecord(ctx->ev_k[7], ctx->md5_stream));
         CK(cudaEventRecord(ctx->ev_join, ctx->md5_stream));
         ctx->launches++;
     }
+    const bool prof = ctx->profiling;
+    if (prof) CK(cudaEventRecord(ctx->ev_k[0], st));
     launch_analyze(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, (SubframePlan*)ctx->d_plans.p,
                    (uint8_t*)ctx->d_ca.p, ctx->debug ? (SignalDebug*)ctx->d_debug.p : nullptr, (EncStats*)ctx->d_stats.p,
                    analyze_smem_bytes(P), st);
+    if (prof) CK(cudaEventRecord(ctx->ev_k[1], st));
     launch_pack(d_pcm, (const FrameDesc*)ctx->d_frames.p, P, nf, (const SubframePlan*)ctx->d_plans.p, (const uint8_t*)ctx->d_ca.p,
                 (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)ctx->d_flen.p, st);
+    if (prof) CK(cudaEventRecord(ctx->ev_k[2], st));
     const uint32_t pro = ctx->cfg.write_prologue ? (uint32_t)kStreamPrologueBytes : 0u;
     launch_layout((const uint32_t*)ctx->d_flen.p, (const FrameDesc*)ctx->d_frames.p, nf, pro, (uint64_t*)ctx->d_foff.p,
                   (uint64_t*)ctx->d_total.p, st);
+    if (prof) CK(cudaEventRecord(ctx->ev_k[3], st));
     launch_compact((const uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (const uint32_t*)ctx->d_flen.p, (const uint64_t*)ctx->d_foff.p,
                    (uint8_t*)ctx->d_arena.p, nf, st);
+    if (prof) CK(cudaEventRecord(ctx->ev_k[4], st));
     if (md5) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     launch_finalize((const uint32_t*)ctx->d_flen.p, (const uint64_t*)ctx->d_foff.p, (const uint32_t*)ctx->d_sfirst.p,
                     (const uint32_t*)ctx->d_snframes.p, (const uint64_t*)ctx->d_ssamples.p, md5 ? (const uint8_t*)ctx->d_md5.p : nullptr, ns, P,
                     pro ? 1u : 0u, (uint8_t*)ctx->d_arena.p, (StreamInfoOut*)ctx->d_sinfo.p, st);
+    if (prof) CK(cudaEventRecord(ctx->ev_k[5], st));
     ctx->launches += 5;
     CK(cudaGetLastError());
     return 0;

@@ -33,6 +33,8 @@ struct EncParams {
     uint32_t container_bytes;    // 2 = int16 samples in HBM, 4 = int32
     uint32_t n_signals;          // channels (+2 when do_mid_side)
     uint32_t smem_stride;        // int32 words reserved per signal in shared memory (>= max blocksize, multiple of 4)
+    uint32_t pool_bytes;         // analysis kernel: partition-sum area aliased with the autocorrelation rings
+    uint32_t ac_gsz;             // analysis kernel: (signal, window) jobs packed per warp in the autocorrelation phase
 };
 
 struct FrameDesc {

@@ -1,0 +1,402 @@
+// flac_api_enc.cu -- drop-in FLAC__stream_encoder_* layer (include/flacb200_flac_api.h) on top of the batch engine.
+//
+// Host logic only: settings, the libFLAC framing rules (a frame is produced once blocksize+1
+// samples are buffered; finish() flushes the remainder as a short frame), stream prologue, STREAMINFO
+// rewrite through seek/tell, callback dispatch in order.  All per-frame arithmetic happens in the CUDA
+// kernels via flacb200_encode_batch; one process_interleaved() call encodes every complete frame it holds
+// in ONE batch.  MD5 of a handle-fed stream is accumulated incrementally on the host as the samples arrive
+// (the batch ABI hashes on the GPU; see DESIGN.md "MD5 placement").
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+
+#include "../../include/flacb200.h"
+#include "../../include/flacb200_flac_api.h"
+#include "fb_common.cuh"
+
+extern "C" {
+// libFLAC 1.4.3 string tables (values read from the reference binary; pyflac/encoder.py:42,54)
+const char *const FLAC__StreamEncoderStateString[] = {
+    "FLAC__STREAM_ENCODER_OK", "FLAC__STREAM_ENCODER_UNINITIALIZED", "FLAC__STREAM_ENCODER_OGG_ERROR",
+    "FLAC__STREAM_ENCODER_VERIFY_DECODER_ERROR", "FLAC__STREAM_ENCODER_VERIFY_MISMATCH_IN_AUDIO_DATA",
+    "FLAC__STREAM_ENCODER_CLIENT_ERROR", "FLAC__STREAM_ENCODER_IO_ERROR", "FLAC__STREAM_ENCODER_FRAMING_ERROR",
+    "FLAC__STREAM_ENCODER_MEMORY_ALLOCATION_ERROR"};
+const char *const FLAC__StreamEncoderInitStatusString[] = {
+    "FLAC__STREAM_ENCODER_INIT_STATUS_OK", "FLAC__STREAM_ENCODER_INIT_STATUS_ENCODER_ERROR",
+    "FLAC__STREAM_ENCODER_INIT_STATUS_UNSUPPORTED_CONTAINER", "FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_CALLBACKS",
+    "FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_NUMBER_OF_CHANNELS", "FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_BITS_PER_SAMPLE",
+    "FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_SAMPLE_RATE", "FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_BLOCK_SIZE",
+    "FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_MAX_LPC_ORDER", "FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_QLP_COEFF_PRECISION",
+    "FLAC__STREAM_ENCODER_INIT_STATUS_BLOCK_SIZE_TOO_SMALL_FOR_LPC_ORDER", "FLAC__STREAM_ENCODER_INIT_STATUS_NOT_STREAMABLE",
+    "FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_METADATA", "FLAC__STREAM_ENCODER_INIT_STATUS_ALREADY_INITIALIZED"};
+const char *FLAC__VENDOR_STRING = "reference libFLAC 1.4.3 20230623";   // byte-identical files need the oracle's vendor string
+}
+
+namespace {
+
+enum { ST_OK = 0, ST_UNINITIALIZED = 1, ST_VERIFY_DECODER_ERROR = 3, ST_CLIENT_ERROR = 5, ST_IO_ERROR = 6, ST_FRAMING_ERROR = 7, ST_MEMORY_ALLOCATION_ERROR = 8 };
+enum { INIT_OK = 0, INIT_ENCODER_ERROR = 1, INIT_UNSUPPORTED_CONTAINER = 2, INIT_INVALID_CALLBACKS = 3, INIT_ALREADY_INITIALIZED = 13 };
+
+// RFC 1321, incremental (host side of the handle API only)
+struct Md5 {
+    uint32_t h[4]; uint64_t len; uint8_t buf[64]; uint32_t fill;
+    void init() { h[0] = 0x67452301u; h[1] = 0xefcdab89u; h[2] = 0x98badcfeu; h[3] = 0x10325476u; len = 0; fill = 0; }
+    static uint32_t rol(uint32_t v, int s) { return (v << s) | (v >> (32 - s)); }
+    void block(const uint8_t* p) {
+        static const uint32_t K[64] = {
+            0xd76aa478,0xe8c7b756,0x242070db,0xc1bdceee,0xf57c0faf,0x4787c62a,0xa8304613,0xfd469501,0x698098d8,0x8b44f7af,0xffff5bb1,0x895cd7be,
+            0x6b901122,0xfd987193,0xa679438e,0x49b40821,0xf61e2562,0xc040b340,0x265e5a51,0xe9b6c7aa,0xd62f105d,0x02441453,0xd8a1e681,0xe7d3fbc8,
+            0x21e1cde6,0xc33707d6,0xf4d50d87,0x455a14ed,0xa9e3e905,0xfcefa3f8,0x676f02d9,0x8d2a4c8a,0xfffa3942,0x8771f681,0x6d9d6122,0xfde5380c,
+            0xa4beea44,0x4bdecfa9,0xf6bb4b60,0xbebfbc70,0x289b7ec6,0xeaa127fa,0xd4ef3085,0x04881d05,0xd9d4d039,0xe6db99e5,0x1fa27cf8,0xc4ac5665,
+            0xf4292244,0x432aff97,0xab9423a7,0xfc93a039,0x655b59c3,0x8f0ccc92,0xffeff47d,0x85845dd1,0x6fa87e4f,0xfe2ce6e0,0xa3014314,0x4e0811a1,
+            0xf7537e82,0xbd3af235,0x2ad7d2bb,0xeb86d391};
+        static const int S[64] = {7,12,17,22,7,12,17,22,7,12,17,22,7,12,17,22,5,9,14,20,5,9,14,20,5,9,14,20,5,9,14,20,
+                                  4,11,16,23,4,11,16,23,4,11,16,23,4,11,16,23,6,10,15,21,6,10,15,21,6,10,15,21,6,10,15,21};
+        uint32_t w[16], a = h[0], b = h[1], c = h[2], d = h[3];
+        for (int i = 0; i < 16; i++) w[i] = (uint32_t)p[4 * i] | (uint32_t)p[4 * i + 1] << 8 | (uint32_t)p[4 * i + 2] << 16 | (uint32_t)p[4 * i + 3] << 24;
+        for (int i = 0; i < 64; i++) {
+            uint32_t f; int g;
+            if (i < 16) { f = (b & c) | (~b & d); g = i; }
+            else if (i < 32) { f = (d & b) | (~d & c); g = (5 * i + 1) & 15; }
+            else if (i < 48) { f = b ^ c ^ d; g = (3 * i + 5) & 15; }
+            else { f = c ^ (b | ~d); g = (7 * i) & 15; }
+            const uint32_t t = a + f + K[i] + w[g];
+            a = d; d = c; c = b; b = b + rol(t, S[i]);
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d;
+    }
+    void update(const uint8_t* p, size_t n) {
+        len += n;
+        while (n) {
+            size_t k = 64 - fill; if (k > n) k = n;
+            memcpy(buf + fill, p, k); fill += (uint32_t)k; p += k; n -= k;
+            if (fill == 64) { block(buf); fill = 0; }
+        }
+    }
+    void final(uint8_t out[16]) {
+        const uint64_t bits = len * 8; const uint8_t pad = 0x80, z = 0; uint8_t lb[8];
+        update(&pad, 1);
+        while (fill != 56) update(&z, 1);
+        for (int i = 0; i < 8; i++) lb[i] = (uint8_t)(bits >> (8 * i));
+        update(lb, 8);
+        for (int i = 0; i < 16; i++) out[i] = (uint8_t)(h[i >> 2] >> (8 * (i & 3)));
+    }
+};
+
+// one engine context per process for the handle API, created on first use
+std::mutex g_mu;
+flacb200_ctx* g_ctx = nullptr;
+int g_ctx_rc = -1;
+flacb200_ctx* shared_ctx() {
+    if (g_ctx_rc == -1) g_ctx_rc = flacb200_create(&g_ctx, 0);
+    return g_ctx_rc == 0 ? g_ctx : nullptr;
+}
+
+struct EncImpl {
+    // settings (libFLAC defaults: stream_encoder.h set_defaults_: 2 ch, 16 bit, 44.1 kHz, level 5)
+    FLAC__bool verify = 0, streamable_subset = 1, limit_min_bitrate = 0;
+    uint32_t channels = 2, bps = 16, sample_rate = 44100, level = 5, blocksize = 0;
+    uint64_t total_samples_estimate = 0;
+    bool custom_tuning = false;            // a fine-grained setter moved away from the level presets
+    int state = ST_UNINITIALIZED;
+    // session
+    FLAC__StreamEncoderWriteCallback write_cb = nullptr; FLAC__StreamEncoderSeekCallback seek_cb = nullptr;
+    FLAC__StreamEncoderTellCallback tell_cb = nullptr; FLAC__StreamEncoderMetadataCallback meta_cb = nullptr;
+    FLAC__StreamEncoderProgressCallback progress_cb = nullptr;
+    void* client = nullptr;
+    FILE* file = nullptr; bool own_file = false;
+    uint32_t N = 0;                        // resolved blocksize
+    std::vector<int32_t> pending;          // interleaved samples not yet framed
+    uint32_t frame_number = 0;
+    uint64_t samples_written = 0, bytes_written = 0;
+    uint32_t min_fs = 0, max_fs = 0, frames_written = 0;
+    uint64_t streaminfo_offset = 0;        // byte position of the STREAMINFO block header as told by the tell callback
+    Md5 md5;
+    std::vector<uint8_t> arena; std::vector<uint64_t> foff; std::vector<uint32_t> flen, fsmp;
+};
+
+struct Handle { FLAC__StreamEncoder pub; EncImpl impl; };
+inline EncImpl* I(const FLAC__StreamEncoder* e) { return e ? (EncImpl*)e->private_ : nullptr; }
+
+void reset_settings(EncImpl* m) {
+    m->verify = 0; m->streamable_subset = 1; m->limit_min_bitrate = 0;
+    m->channels = 2; m->bps = 16; m->sample_rate = 44100; m->level = 5; m->blocksize = 0;
+    m->total_samples_estimate = 0; m->custom_tuning = false;
+}
+
+// ref: format.h:546-557 -- the 34-byte STREAMINFO body
+void put_streaminfo(uint8_t* p, const EncImpl* m, uint32_t min_fs, uint32_t max_fs, uint64_t total, const uint8_t md5[16]) {
+    p[0] = (uint8_t)(m->N >> 8); p[1] = (uint8_t)m->N; p[2] = p[0]; p[3] = p[1];
+    p[4] = (uint8_t)(min_fs >> 16); p[5] = (uint8_t)(min_fs >> 8); p[6] = (uint8_t)min_fs;
+    p[7] = (uint8_t)(max_fs >> 16); p[8] = (uint8_t)(max_fs >> 8); p[9] = (uint8_t)max_fs;
+    const uint64_t v = ((uint64_t)m->sample_rate << 44) | ((uint64_t)(m->channels - 1) << 41) | ((uint64_t)(m->bps - 1) << 36) | (total & 0xFFFFFFFFFull);
+    for (int i = 0; i < 8; i++) p[10 + i] = (uint8_t)(v >> (56 - 8 * i));
+    memcpy(p + 18, md5, 16);
+}
+
+// deliver bytes: user callback (stream mode) or stdio (file mode); bookkeeping as libFLAC's write_frame_
+bool deliver(FLAC__StreamEncoder* e, const uint8_t* buf, size_t bytes, uint32_t samples, uint32_t frame) {
+    EncImpl* m = I(e);
+    if (m->file) {
+        if (fwrite(buf, 1, bytes, m->file) != bytes) { m->state = ST_IO_ERROR; return false; }
+        if (samples > 0 && m->progress_cb)
+            m->progress_cb(e, m->bytes_written + bytes, m->samples_written + samples, m->frames_written + 1, 0, m->client);
+    } else {
+        // up: write_frame_ -- tell (if given) before every write; remember where the STREAMINFO block went by
+        if (m->tell_cb) {
+            FLAC__uint64 posn = 0;
+            const int ts = m->tell_cb(e, &posn, m->client);
+            if (ts == 1) { m->state = ST_CLIENT_ERROR; return false; }           // TELL_STATUS_ERROR
+            if (ts == 0 && samples == 0 && bytes > 0 && (buf[0] & 0x7f) == 0 && m->streaminfo_offset == 0) m->streaminfo_offset = posn;
+        }
+        if (m->write_cb(e, buf, bytes, samples, frame, m->client) != 0) { m->state = ST_CLIENT_ERROR; return false; }
+    }
+    m->bytes_written += bytes;
+    if (samples > 0) {
+        m->samples_written += samples; m->frames_written++;
+        if (m->min_fs == 0 || bytes < m->min_fs) m->min_fs = (uint32_t)bytes;
+        if (bytes > m->max_fs) m->max_fs = (uint32_t)bytes;
+    }
+    return true;
+}
+
+// encode `n` pending inter-channel samples (whole frames, or everything at finish) in one GPU batch
+bool encode_pending(FLAC__StreamEncoder* e, uint64_t n) {
+    EncImpl* m = I(e);
+    if (n == 0) return true;
+    std::lock_guard<std::mutex> lk(g_mu);
+    flacb200_ctx* ctx = shared_ctx();
+    if (!ctx) { m->state = ST_MEMORY_ALLOCATION_ERROR; return false; }
+    flacb200_enc_config cfg{};
+    cfg.sample_rate = m->sample_rate; cfg.channels = m->channels; cfg.bits_per_sample = m->bps;
+    cfg.compression_level = m->level; cfg.blocksize = m->N; cfg.container_bytes = 4;
+    cfg.write_prologue = 0; cfg.do_md5 = 0; cfg.streamable_subset = 0; cfg.debug_trace = 0;
+    const uint64_t off = 0, cnt = n; const uint32_t ffn = m->frame_number;
+    if (flacb200_encode_batch(ctx, &cfg, m->pending.data(), 0, n * m->channels, 1, &off, &cnt, &ffn) != 0) { m->state = ST_FRAMING_ERROR; return false; }
+    flacb200_enc_result r;
+    if (flacb200_encode_result(ctx, &r) != 0) { m->state = ST_FRAMING_ERROR; return false; }
+    m->arena.resize(r.total_bytes ? r.total_bytes : 1); m->foff.resize(r.n_frames); m->flen.resize(r.n_frames); m->fsmp.resize(r.n_frames);
+    if (flacb200_encode_fetch(ctx, m->arena.data(), m->arena.size(), m->foff.data(), m->flen.data(), m->fsmp.data(), nullptr, nullptr) != 0) { m->state = ST_FRAMING_ERROR; return false; }
+    // MD5 over (bps+7)/8 little-endian bytes per sample, interleaved (up: md5.c FLAC__MD5Accumulate)
+    {
+        const uint32_t bytes = (m->bps + 7) / 8;
+        const size_t vals = (size_t)n * m->channels;
+        std::vector<uint8_t> tmp(vals * bytes);
+        size_t k = 0;
+        for (size_t i = 0; i < vals; i++) { const uint32_t v = (uint32_t)m->pending[i]; for (uint32_t b = 0; b < bytes; b++) tmp[k++] = (uint8_t)(v >> (8 * b)); }
+        m->md5.update(tmp.data(), tmp.size());
+    }
+    for (uint32_t f = 0; f < r.n_frames; f++) {
+        if (!deliver(e, m->arena.data() + m->foff[f], m->flen[f], m->fsmp[f], m->frame_number)) return false;
+        m->frame_number++;
+    }
+    m->pending.erase(m->pending.begin(), m->pending.begin() + (size_t)n * m->channels);
+    return true;
+}
+
+int init_common(FLAC__StreamEncoder* e) {
+    EncImpl* m = I(e);
+    flacb200_enc_config cfg{};
+    cfg.sample_rate = m->sample_rate; cfg.channels = m->channels; cfg.bits_per_sample = m->bps; cfg.compression_level = m->level;
+    cfg.blocksize = m->blocksize; cfg.container_bytes = 4; cfg.streamable_subset = (uint32_t)m->streamable_subset;
+    const int st = flacb200_enc_validate(&cfg);
+    if (st != 0) return st;
+    static const uint32_t kMaxLpc[9] = {0, 0, 0, 6, 8, 8, 8, 12, 12};
+    const uint32_t lvl = m->level > 8 ? 8 : m->level;
+    m->N = m->blocksize ? m->blocksize : (kMaxLpc[lvl] == 0 ? 1152u : 4096u);
+    // limits of this build fail loudly here instead of producing a different stream (DESIGN.md "limits")
+    const bool loose = (lvl == 1 || lvl == 4) && m->channels == 2;
+    if (m->custom_tuning || loose || m->bps > 24 || m->limit_min_bitrate) { m->state = ST_FRAMING_ERROR; return INIT_ENCODER_ERROR; }
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!shared_ctx()) { m->state = ST_MEMORY_ALLOCATION_ERROR; return INIT_ENCODER_ERROR; }   // no CUDA device: no CPU fallback
+    }
+    m->pending.clear(); m->frame_number = 0; m->samples_written = 0; m->bytes_written = 0; m->min_fs = m->max_fs = 0; m->frames_written = 0; m->streaminfo_offset = 0;
+    m->md5.init();
+    m->state = ST_OK;
+    // stream prologue: "fLaC", STREAMINFO (frame sizes / MD5 zero, total = estimate), VORBIS_COMMENT
+    uint8_t b[64];
+    memcpy(b, "fLaC", 4);
+    if (!deliver(e, b, 4, 0, 0)) return INIT_ENCODER_ERROR;
+    uint8_t zero[16] = {0};
+    b[0] = 0x00; b[1] = 0; b[2] = 0; b[3] = 34;
+    put_streaminfo(b + 4, m, 0, 0, m->total_samples_estimate, zero);
+    if (!deliver(e, b, 38, 0, 0)) return INIT_ENCODER_ERROR;
+    const uint32_t vl = (uint32_t)strlen(FLAC__VENDOR_STRING), len = 4 + vl + 4;
+    b[0] = 0x84; b[1] = (uint8_t)(len >> 16); b[2] = (uint8_t)(len >> 8); b[3] = (uint8_t)len;
+    b[4] = (uint8_t)vl; b[5] = (uint8_t)(vl >> 8); b[6] = (uint8_t)(vl >> 16); b[7] = (uint8_t)(vl >> 24);
+    memcpy(b + 8, FLAC__VENDOR_STRING, vl);
+    memset(b + 8 + vl, 0, 4);
+    if (!deliver(e, b, 4 + len, 0, 0)) return INIT_ENCODER_ERROR;
+    return INIT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+FLAC__StreamEncoder* FLAC__stream_encoder_new(void) {
+    Handle* h = new Handle();
+    h->pub.protected_ = nullptr; h->pub.private_ = &h->impl;
+    return &h->pub;
+}
+void FLAC__stream_encoder_delete(FLAC__StreamEncoder* e) {
+    if (!e) return;
+    if (I(e)->state != ST_UNINITIALIZED) FLAC__stream_encoder_finish(e);
+    delete reinterpret_cast<Handle*>(e);
+}
+
+#define SETTER(name, type, field) FLAC__bool FLAC__stream_encoder_set_##name(FLAC__StreamEncoder* e, type v) { \
+    EncImpl* m = I(e); if (!m || m->state != ST_UNINITIALIZED) return 0; m->field = v; return 1; }
+SETTER(verify, FLAC__bool, verify)
+SETTER(channels, uint32_t, channels)
+SETTER(bits_per_sample, uint32_t, bps)
+SETTER(sample_rate, uint32_t, sample_rate)
+SETTER(blocksize, uint32_t, blocksize)
+SETTER(streamable_subset, FLAC__bool, streamable_subset)
+SETTER(limit_min_bitrate, FLAC__bool, limit_min_bitrate)
+SETTER(total_samples_estimate, FLAC__uint64, total_samples_estimate)
+#undef SETTER
+FLAC__bool FLAC__stream_encoder_set_compression_level(FLAC__StreamEncoder* e, uint32_t v) {
+    EncImpl* m = I(e); if (!m || m->state != ST_UNINITIALIZED) return 0;
+    m->level = v > 8 ? 8 : v; m->custom_tuning = false; return 1;
+}
+// tuning knobs outside pyFLAC's surface: remember that the presets were left, init then refuses (fails loudly)
+#define TUNING(name, type) FLAC__bool FLAC__stream_encoder_set_##name(FLAC__StreamEncoder* e, type) { \
+    EncImpl* m = I(e); if (!m || m->state != ST_UNINITIALIZED) return 0; m->custom_tuning = true; return 1; }
+TUNING(do_mid_side_stereo, FLAC__bool)
+TUNING(loose_mid_side_stereo, FLAC__bool)
+TUNING(apodization, const char*)
+TUNING(max_lpc_order, uint32_t)
+TUNING(qlp_coeff_precision, uint32_t)
+TUNING(do_qlp_coeff_prec_search, FLAC__bool)
+TUNING(do_exhaustive_model_search, FLAC__bool)
+TUNING(min_residual_partition_order, uint32_t)
+TUNING(max_residual_partition_order, uint32_t)
+TUNING(rice_parameter_search_dist, uint32_t)
+#undef TUNING
+
+int FLAC__stream_encoder_get_state(const FLAC__StreamEncoder* e) { return I(e) ? I(e)->state : ST_UNINITIALIZED; }
+const char* FLAC__stream_encoder_get_resolved_state_string(const FLAC__StreamEncoder* e) { return FLAC__StreamEncoderStateString[FLAC__stream_encoder_get_state(e)]; }
+void FLAC__stream_encoder_get_verify_decoder_error_stats(const FLAC__StreamEncoder*, FLAC__uint64* a, uint32_t* f, uint32_t* c, uint32_t* s, FLAC__int32* x, FLAC__int32* g) {
+    if (a) *a = 0; if (f) *f = 0; if (c) *c = 0; if (s) *s = 0; if (x) *x = 0; if (g) *g = 0;
+}
+FLAC__bool FLAC__stream_encoder_get_verify(const FLAC__StreamEncoder* e) { return I(e)->verify; }
+FLAC__bool FLAC__stream_encoder_get_streamable_subset(const FLAC__StreamEncoder* e) { return I(e)->streamable_subset; }
+uint32_t FLAC__stream_encoder_get_channels(const FLAC__StreamEncoder* e) { return I(e)->channels; }
+uint32_t FLAC__stream_encoder_get_bits_per_sample(const FLAC__StreamEncoder* e) { return I(e)->bps; }
+uint32_t FLAC__stream_encoder_get_sample_rate(const FLAC__StreamEncoder* e) { return I(e)->sample_rate; }
+uint32_t FLAC__stream_encoder_get_blocksize(const FLAC__StreamEncoder* e) { return I(e)->state == ST_UNINITIALIZED ? I(e)->blocksize : I(e)->N; }
+// level presets (stream_encoder.h:845-853)
+static const struct { int ms, loose; uint32_t lpc, po; } kLv[9] = {{0,0,0,3},{1,1,0,3},{1,0,0,3},{0,0,6,4},{1,1,8,4},{1,0,8,5},{1,0,8,6},{1,0,12,6},{1,0,12,6}};
+FLAC__bool FLAC__stream_encoder_get_do_mid_side_stereo(const FLAC__StreamEncoder* e) { return kLv[I(e)->level].ms; }
+FLAC__bool FLAC__stream_encoder_get_loose_mid_side_stereo(const FLAC__StreamEncoder* e) { return kLv[I(e)->level].loose; }
+uint32_t FLAC__stream_encoder_get_max_lpc_order(const FLAC__StreamEncoder* e) { return kLv[I(e)->level].lpc; }
+uint32_t FLAC__stream_encoder_get_qlp_coeff_precision(const FLAC__StreamEncoder*) { return 0; }
+FLAC__bool FLAC__stream_encoder_get_do_qlp_coeff_prec_search(const FLAC__StreamEncoder*) { return 0; }
+FLAC__bool FLAC__stream_encoder_get_do_escape_coding(const FLAC__StreamEncoder*) { return 0; }
+FLAC__bool FLAC__stream_encoder_get_do_exhaustive_model_search(const FLAC__StreamEncoder*) { return 0; }
+uint32_t FLAC__stream_encoder_get_min_residual_partition_order(const FLAC__StreamEncoder*) { return 0; }
+uint32_t FLAC__stream_encoder_get_max_residual_partition_order(const FLAC__StreamEncoder* e) { return kLv[I(e)->level].po; }
+uint32_t FLAC__stream_encoder_get_rice_parameter_search_dist(const FLAC__StreamEncoder*) { return 0; }
+FLAC__uint64 FLAC__stream_encoder_get_total_samples_estimate(const FLAC__StreamEncoder* e) { return I(e)->total_samples_estimate; }
+FLAC__bool FLAC__stream_encoder_get_limit_min_bitrate(const FLAC__StreamEncoder* e) { return I(e)->limit_min_bitrate; }
+
+int FLAC__stream_encoder_init_stream(FLAC__StreamEncoder* e, FLAC__StreamEncoderWriteCallback w, FLAC__StreamEncoderSeekCallback s,
+                                     FLAC__StreamEncoderTellCallback t, FLAC__StreamEncoderMetadataCallback mcb, void* client) {
+    EncImpl* m = I(e);
+    if (m->state != ST_UNINITIALIZED) return INIT_ALREADY_INITIALIZED;
+    if (!w || (s && !t)) return INIT_INVALID_CALLBACKS;          // up: init_stream_internal_ (tests/test_encoder.py:202-207)
+    m->write_cb = w; m->seek_cb = s; m->tell_cb = t; m->meta_cb = mcb; m->progress_cb = nullptr; m->client = client; m->file = nullptr; m->own_file = false;
+    return init_common(e);
+}
+int FLAC__stream_encoder_init_FILE(FLAC__StreamEncoder* e, FILE* f, FLAC__StreamEncoderProgressCallback p, void* client) {
+    EncImpl* m = I(e);
+    if (m->state != ST_UNINITIALIZED) return INIT_ALREADY_INITIALIZED;
+    if (!f) { m->state = ST_IO_ERROR; return INIT_ENCODER_ERROR; }
+    m->write_cb = nullptr; m->seek_cb = nullptr; m->tell_cb = nullptr; m->meta_cb = nullptr; m->progress_cb = p; m->client = client; m->file = f; m->own_file = true;
+    const int rc = init_common(e);
+    if (rc != INIT_OK && m->file) { fclose(m->file); m->file = nullptr; }
+    return rc;
+}
+int FLAC__stream_encoder_init_file(FLAC__StreamEncoder* e, const char* filename, FLAC__StreamEncoderProgressCallback p, void* client) {
+    EncImpl* m = I(e);
+    if (m->state != ST_UNINITIALIZED) return INIT_ALREADY_INITIALIZED;
+    FILE* f = filename ? fopen(filename, "w+b") : stdout;
+    if (!f) { m->state = ST_IO_ERROR; return INIT_ENCODER_ERROR; }
+    return FLAC__stream_encoder_init_FILE(e, f, p, client);
+}
+int FLAC__stream_encoder_init_ogg_stream(FLAC__StreamEncoder*, FLAC__StreamEncoderReadCallback, FLAC__StreamEncoderWriteCallback, FLAC__StreamEncoderSeekCallback,
+                                         FLAC__StreamEncoderTellCallback, FLAC__StreamEncoderMetadataCallback, void*) { return INIT_UNSUPPORTED_CONTAINER; }
+int FLAC__stream_encoder_init_ogg_FILE(FLAC__StreamEncoder*, FILE*, FLAC__StreamEncoderProgressCallback, void*) { return INIT_UNSUPPORTED_CONTAINER; }
+int FLAC__stream_encoder_init_ogg_file(FLAC__StreamEncoder*, const char*, FLAC__StreamEncoderProgressCallback, void*) { return INIT_UNSUPPORTED_CONTAINER; }
+
+FLAC__bool FLAC__stream_encoder_process_interleaved(FLAC__StreamEncoder* e, const FLAC__int32 buffer[], uint32_t samples) {
+    EncImpl* m = I(e);
+    if (!m || m->state != ST_OK) return 0;
+    m->pending.insert(m->pending.end(), buffer, buffer + (size_t)samples * m->channels);
+    const uint64_t have = m->pending.size() / m->channels;
+    // a frame needs blocksize+1 buffered samples (the over-read sample stays pending): SURVEY A.2
+    if (have > m->N) {
+        const uint64_t frames = (have - 1) / m->N;
+        if (!encode_pending(e, frames * m->N)) return 0;
+    }
+    return 1;
+}
+FLAC__bool FLAC__stream_encoder_process(FLAC__StreamEncoder* e, const FLAC__int32* const buffer[], uint32_t samples) {
+    EncImpl* m = I(e);
+    if (!m || m->state != ST_OK) return 0;
+    std::vector<int32_t> tmp((size_t)samples * m->channels);
+    for (uint32_t i = 0; i < samples; i++) for (uint32_t c = 0; c < m->channels; c++) tmp[(size_t)i * m->channels + c] = buffer[c][i];
+    return FLAC__stream_encoder_process_interleaved(e, tmp.data(), samples);
+}
+
+FLAC__bool FLAC__stream_encoder_finish(FLAC__StreamEncoder* e) {
+    EncImpl* m = I(e);
+    if (!m || m->state == ST_UNINITIALIZED) return 1;
+    bool ok = (m->state == ST_OK);
+    if (ok) {
+        const uint64_t have = m->pending.size() / m->channels;
+        if (have > 0) ok = encode_pending(e, have);           // remainder -> final (possibly short) frame
+    }
+    uint8_t digest[16];
+    m->md5.final(digest);
+    if (ok) {
+        // up: update_metadata_ -- rewrite STREAMINFO in place: MD5 @26 (16 B), total samples @21 (5 B), frame sizes @12 (6 B)
+        uint8_t si[34];
+        put_streaminfo(si, m, m->min_fs, m->max_fs, m->samples_written, digest);
+        // offsets are relative to the STREAMINFO block header (4 when the stream starts at byte 0): +22, +17, +8
+        const uint64_t so = m->file ? 4 : (m->streaminfo_offset ? m->streaminfo_offset : 4);
+        struct { uint64_t off; const uint8_t* p; size_t n; } patch[3] = {{so + 22, si + 18, 16}, {so + 17, si + 13, 5}, {so + 8, si + 4, 6}};
+        if (m->file) {
+            for (auto& q : patch) { if (fseek(m->file, (long)q.off, SEEK_SET) != 0 || fwrite(q.p, 1, q.n, m->file) != q.n) { ok = false; m->state = ST_IO_ERROR; break; } }
+            fseek(m->file, 0, SEEK_END);
+        } else if (m->seek_cb) {
+            for (auto& q : patch) {
+                if (m->seek_cb(e, q.off, m->client) != 0) { ok = false; m->state = ST_CLIENT_ERROR; break; }
+                if (m->write_cb(e, q.p, q.n, 0, 0, m->client) != 0) { ok = false; m->state = ST_CLIENT_ERROR; break; }
+            }
+        }
+        if (m->meta_cb) {
+            FLAC__StreamMetadata md; memset(&md, 0, sizeof md);
+            md.type = 0; md.is_last = 0; md.length = 34;
+            md.data.stream_info.min_blocksize = md.data.stream_info.max_blocksize = m->N;
+            md.data.stream_info.min_framesize = m->min_fs; md.data.stream_info.max_framesize = m->max_fs;
+            md.data.stream_info.sample_rate = m->sample_rate; md.data.stream_info.channels = m->channels;
+            md.data.stream_info.bits_per_sample = m->bps; md.data.stream_info.total_samples = m->samples_written;
+            memcpy(md.data.stream_info.md5sum, digest, 16);
+            m->meta_cb(e, &md, m->client);
+        }
+    }
+    if (m->file && m->own_file) { if (m->file != stdout) fclose(m->file); }
+    m->file = nullptr;
+    m->pending.clear();
+    reset_settings(m);                                         // stream_encoder.h:225-227: back to defaults
+    m->state = ST_UNINITIALIZED;
+    return ok ? 1 : 0;
+}
+
+}  // extern "C"

@@ -81,7 +81,7 @@ def ref_lib():
         L.ref_decode_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p]
         L.ref_encode_mt.restype = C.c_double
         L.ref_encode_mt.argtypes = [C.POINTER(RefEncCfg), C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
-                                    C.c_uint32, C.POINTER(C.c_uint64)]
+                                    C.c_uint32, C.POINTER(C.c_uint64), C.c_void_p, C.c_size_t, C.c_void_p]
         L.ref_decode_mt.restype = C.c_double
         L.ref_decode_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                     C.POINTER(C.c_uint64)]
@@ -203,3 +203,30 @@ def oracle_decode(data):
     if n2 != n:
         raise RuntimeError(f"fo_decode_stream failed: {n2}")
     return out, dict(channels=int(info[0]), bps=int(info[1]), sample_rate=int(info[2]), blocksize=int(info[3]))
+
+
+def ref_encode_mt(pcm, sample_rate, bps, level=5, blocksize=0, n_threads=1, keep_bytes=False):
+    """Time libFLAC on `n_threads` pthreads over a batch pcm[(streams, n, ch)] (int16 or int32 container).
+    Returns (seconds, total_bytes, list_of_bytes or None)."""
+    pcm = np.ascontiguousarray(pcm)
+    ns, n, ch = pcm.shape
+    cfg = RefEncCfg(sample_rate, ch, bps, level, blocksize, 1, 0, 1, 1)
+    total = C.c_uint64(0)
+    p16 = pcm.ctypes.data if pcm.dtype == np.int16 else None
+    p32 = pcm.ctypes.data if pcm.dtype == np.int32 else None
+    assert p16 or p32
+    out_all = lens = None
+    stride = 0
+    if keep_bytes:
+        stride = n * ch * pcm.dtype.itemsize + n * ch // 2 + 65536
+        out_all = np.empty(ns * stride, np.uint8)
+        lens = np.zeros(ns, np.uint64)
+    dt = ref_lib().ref_encode_mt(C.byref(cfg), p32, p16, n, ns, n_threads, C.byref(total),
+                                 out_all.ctypes.data if keep_bytes else None, stride,
+                                 lens.ctypes.data if keep_bytes else None)
+    if dt < 0:
+        raise RuntimeError("ref_encode_mt failed")
+    blobs = None
+    if keep_bytes:
+        blobs = [out_all[s * stride: s * stride + int(lens[s])] for s in range(ns)]
+    return dt, int(total.value), blobs

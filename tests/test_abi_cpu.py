@@ -1,0 +1,136 @@
+"""CPU tests of the boundary: libflacb200.so loads without a GPU, exports every symbol include/*.h declares,
+validates settings like libFLAC, refuses to compute without a device (no CPU fallback), and the host build of the
+decision arithmetic (fb_math.cuh) agrees with the oracle."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_cases, load_golden
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pyflac_b200 import build, _native
+    build.build()
+    return _native.lib()
+
+
+def declared_symbols():
+    syms = set()
+    for h in os.listdir(os.path.join(ROOT, "include")):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        syms |= set(re.findall(r"\b((?:flacb200|FLAC__)\w+)\s*\(", txt))
+        syms |= set(re.findall(r"extern\s+[\w\s\*]+?\b((?:flacb200|FLAC__)\w+)\s*(?:\[\])?\s*;", txt))
+    return {s for s in syms if not s.endswith("Callback")}
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from pyflac_b200 import _native
+    out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    missing = sorted(s for s in declared_symbols() if s not in exported)
+    assert not missing, missing
+
+
+def test_no_device_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from pyflac_b200 import _native
+    with pytest.raises(_native.NoCudaDevice):
+        _native.Engine(0)
+
+
+def test_validate_matches_oracle(lib, checkers):
+    from pyflac_b200 import _native as nat
+    L = checkers.oracle_lib()
+    for sr, ch, bps, lvl, bs, sub in [(48000, 2, 16, 5, 0, 1), (2000000, 2, 16, 5, 0, 1), (48000, 2, 16, 5, 1000000, 1),
+                                      (48000, 2, 16, 5, 65535, 1), (48000, 2, 16, 5, 65535, 0), (48000, 9, 16, 5, 0, 1),
+                                      (48000, 2, 3, 5, 0, 1), (48000, 2, 17, 5, 0, 1), (48000, 2, 17, 5, 0, 0),
+                                      (96000, 2, 16, 5, 16385, 1), (48000, 2, 16, 8, 8, 0), (48000, 2, 16, 0, 15, 0)]:
+        cfg = nat.EncConfig(sr, ch, bps, lvl, bs, 2, 1, 1, sub, 0)
+        ocfg = checkers.FoEncCfg(sr, ch, bps, lvl, bs, 0, 0, sub)
+        assert lib.flacb200_enc_validate(C.byref(cfg)) == L.fo_encoder_init_status(C.byref(ocfg), 1, 0, 0), (sr, ch, bps, lvl, bs, sub)
+
+
+@pytest.fixture(scope="module")
+def fbmath():
+    d = os.path.join(ROOT, "tests", "cpu_shim")
+    so = os.path.join(d, "libfbmath_host.so")
+    subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-std=c++17", "-o", so,
+                    os.path.join(d, "fb_math_host.cpp")], check=True)
+    L = C.CDLL(so)
+    L.t_crc16_mulmod.restype = C.c_uint16
+    L.t_crc16_byte.restype = C.c_uint16
+    L.t_rice_parameter.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
+    L.t_rice_bits.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+    return L
+
+
+def test_fb_math_host_build_matches_oracle_traces(fbmath, checkers):
+    """frame headers, Levinson errors and quantised coefficients of the kernel's scalar code (host build)"""
+    maxlpc = {0: 0, 1: 0, 2: 0, 3: 6, 4: 8, 5: 8, 6: 8, 7: 12, 8: 12}
+    nlev = nq = 0
+    for case in golden_cases():
+        x, flac = load_golden(case)
+        _, traces = checkers.oracle_encode(x, case["sample_rate"], case["bps"], case["level"], case["blocksize"], with_trace=True)
+        for f, o in enumerate(case["frame_off"]):
+            t = traces[f]
+            hdr = np.zeros(16, np.uint8)
+            n = fbmath.t_frame_header(hdr.ctypes.data, case["channels"], case["bps"], case["sample_rate"], t.blocksize,
+                                      t.frame_number, t.channel_assignment)
+            assert hdr[:n].tobytes() == flac[o:o + n]
+            for s in range(t.n_signals):
+                sg = t.sig[s]
+                b = sg.best
+                first = next((k for k in range(sg.n_apod) if sg.lpc_bits[k] == b.bits_est), -1)
+                for st in range(sg.n_apod):
+                    if sg.lpc_order[st] == 0:
+                        continue
+                    mo = min(maxlpc[case["level"]], t.blocksize - 1)
+                    ac = np.array(list(sg.autoc[st])[:mo + 1])
+                    lp = np.zeros(144, np.float32)
+                    err = np.zeros(12)
+                    nm = fbmath.t_levinson(ac.ctypes.data, mo, lp.ctypes.data, err.ctypes.data)
+                    assert np.array_equal(err[:nm], np.array(list(sg.lpc_err[st])[:nm]))
+                    nlev += 1
+                    if b.type == 3 and st == first:
+                        q = np.zeros(16, np.int32)
+                        sh = C.c_int(0)
+                        rc = fbmath.t_quantize(lp[(b.order - 1) * 12:].ctypes.data, b.order, b.precision, q.ctypes.data, C.byref(sh))
+                        assert rc == 0 and sh.value == b.shift and list(q[:b.order]) == list(b.qlp)[:b.order]
+                        nq += 1
+    assert nlev > 100 and nq > 30
+
+
+def test_rice_parameter_fixed_point_quirk(fbmath):
+    """n=4095, sum=65536 -> k=4 (truncated 18-bit reciprocal), not the exact ceil-log2's 5"""
+    assert fbmath.t_rice_parameter(65536, 4095, 15) == 4
+    assert fbmath.t_rice_parameter(0, 128, 15) == 0 and fbmath.t_rice_parameter(1, 128, 15) == 0
+    assert fbmath.t_rice_parameter(1 << 40, 128, 15) == 14 and fbmath.t_rice_parameter(1 << 40, 128, 31) == 30
+    assert fbmath.t_rice_bits(0, 100, 10) == 4 + 100 + 20 - 50
+
+
+def test_crc16_chunk_combination(fbmath):
+    rng = np.random.default_rng(0)
+    a, b = rng.integers(0, 256, 300).astype(np.uint8), rng.integers(0, 256, 77).astype(np.uint8)
+
+    def crc(bs):
+        c = 0
+        for v in bs:
+            c = fbmath.t_crc16_byte(c, int(v))
+        return c
+    xp, base, e = 1, 2, 8 * len(b)
+    while e:
+        if e & 1:
+            xp = fbmath.t_crc16_mulmod(xp, base)
+        base = fbmath.t_crc16_mulmod(base, base)
+        e >>= 1
+    assert crc(np.concatenate([a, b])) == (fbmath.t_crc16_mulmod(crc(a), xp) ^ crc(b))
+    assert crc(b"123456789") == 0xFEE8

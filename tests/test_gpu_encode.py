@@ -1,0 +1,120 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libflacb200.so via pyflac_b200/_native.py); the oracle / reference binary are only the checkers."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden
+from pyflac_b200.synth import corpus_signal, CORPUS_KINDS, music_like
+
+pytestmark = pytest.mark.gpu
+CASES = [c for c in golden_cases() if not (c["level"] in (1, 4) and c["channels"] == 2)]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from pyflac_b200 import _native as nat
+    return nat.Engine(0)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_encode_matches_golden(eng, case):
+    """bit-exact against bytes produced by the reference's libFLAC 1.4.3 (tests/golden)."""
+    from pyflac_b200 import _native as nat
+    x, flac = load_golden(case)
+    got, out = nat.encode_streams(eng, [x], case["sample_rate"], case["bps"], case["level"], case["blocksize"])
+    assert got[0] == flac
+    assert [int(v) for v in out["frame_len"]] == case["frame_len"]
+    assert out["log_guard_hits"] == 0
+
+
+@pytest.mark.parametrize("level", [0, 2, 3, 5, 6, 7, 8])
+def test_encode_corpus_vs_oracle(eng, checkers, level):
+    """every corpus kind (each subframe type / branch), 16-bit stereo + 24-bit mono + odd blocksize, one batch per level"""
+    from pyflac_b200 import _native as nat
+    for ch, bps, n, bs, sr in [(2, 16, 4096 * 2 + 768, 0, 48000), (1, 24, 4096 + 100, 4096, 192000), (1, 16, 3000, 1000, 44100),
+                               (2, 16, 700, 192, 22050)]:
+        xs = [corpus_signal(kind, n, ch, bps, seed=level * 7 + ch) for kind in CORPUS_KINDS]
+        got, out = nat.encode_streams(eng, xs, sr, bps, level, bs)
+        for kind, x, g in zip(CORPUS_KINDS, xs, got):
+            assert g == checkers.oracle_encode(x, sr, bps, level, bs), (level, kind, ch, bps, n, bs)
+        assert out["log_guard_hits"] == 0
+
+
+def test_encode_edge_lengths(eng, checkers):
+    """ragged batch: streams of different lengths incl. 1..5 samples, N*k, N*k+1, N*k+768"""
+    from pyflac_b200 import _native as nat
+    lens = [1, 2, 4, 5, 16, 4095, 4096, 4097, 8192, 8193, 4096 * 2 + 768, 100]
+    xs = [corpus_signal("music", n, 2, 16, seed=n) for n in lens]
+    got, out = nat.encode_streams(eng, xs, 44100, 16, 5, 0)
+    for n, x, g in zip(lens, xs, got):
+        assert g == checkers.oracle_encode(x, 44100, 16, 5, 0), n
+
+
+def test_encode_multichannel_and_depths(eng, checkers):
+    from pyflac_b200 import _native as nat
+    for ch in [1, 3, 6, 8]:
+        x = corpus_signal("lr_uncorr", 5000, ch, 16, seed=ch)
+        got, _ = nat.encode_streams(eng, [x], 48000, 16, 5, 0)
+        assert got[0] == checkers.oracle_encode(x, 48000, 16, 5, 0), ch
+    for bps in [8, 12, 20, 24]:
+        for kind in ["music", "wasted"]:
+            x = corpus_signal(kind if bps >= 12 else "music", 6000, 2, bps, seed=bps)
+            got, _ = nat.encode_streams(eng, [x], 96000, bps, 5, 0)
+            assert got[0] == checkers.oracle_encode(x, 96000, bps, 5, 0), (bps, kind)
+
+
+def test_encode_sample_rates_and_frame_numbers(eng, checkers):
+    from pyflac_b200 import _native as nat
+    for sr in [8000, 12345, 50001, 65535, 96000, 176400, 655350]:
+        x = corpus_signal("music", 3000, 2, 16, seed=1)
+        got, _ = nat.encode_streams(eng, [x], sr, 16, 5, 1024, streamable_subset=False)
+        assert got[0] == checkers.oracle_encode(x, sr, 16, 5, 1024, streamable_subset=False), sr
+    x = corpus_signal("music", 16 * 70000, 1, 16, seed=5)       # frame numbers up to 3 UTF-8 bytes
+    got, _ = nat.encode_streams(eng, [x], 48000, 16, 0, 16)
+    assert got[0] == checkers.oracle_encode(x, 48000, 16, 0, 16)
+
+
+def test_encode_vs_reference_binary_live(eng, checkers):
+    """same-run comparison with the reference binary itself when oracle/_ref travelled to this box"""
+    if not checkers.ref_available():
+        pytest.skip("oracle/_ref not present")
+    from pyflac_b200 import _native as nat
+    xs = [music_like(4096 * 5 + 333, 2, 48000, 16, seed=100 + s) for s in range(16)]
+    for level in (5, 8):
+        got, _ = nat.encode_streams(eng, xs, 48000, 16, level, 4096)
+        for x, g in zip(xs, got):
+            assert g == checkers.ref_encode(x, 48000, 16, level, 4096)
+
+
+def test_full_size_properties(eng, checkers):
+    """BASELINE configs[1] shape (256 x 480000 x 2 int16, L5): size-independent properties on the whole batch +
+    oracle decode round trip and byte equality on a sample of streams."""
+    from pyflac_b200 import _native as nat
+    import bench
+    pcm = bench.make_pcm(0)
+    cfg = nat.Engine.make_config(48000, 2, 16, 5, 4096)
+    off = np.arange(256, dtype=np.uint64) * np.uint64(480000 * 2)
+    eng.encode_host(cfg, pcm.reshape(-1), off, np.full(256, 480000, np.uint64))
+    out = eng.fetch()
+    assert out["log_guard_hits"] == 0
+    assert len(out["frame_len"]) == 256 * 118
+    arena = out["arena"]
+    for s, si in enumerate(out["streams"]):
+        blob = arena[int(si.byte_off): int(si.byte_off + si.byte_len)]
+        assert bytes(blob[:4]) == b"fLaC"
+        assert si.n_frames == 118 and si.total_samples == 480000
+        # checksum of checksums: STREAMINFO MD5 == MD5 of the little-endian PCM
+        assert bytes(si.md5) == hashlib.md5(pcm[s].tobytes()).digest()
+        assert bytes(blob[26:42]) == bytes(si.md5)
+    fo, fl = out["frame_off"], out["frame_len"]
+    assert np.all(fo[1:] >= fo[:-1] + fl[:-1])                      # frames laid out in order without overlap
+    assert np.all(arena[fo.astype(np.int64)] == 0xFF)               # every frame starts with the sync code
+    for s in (0, 17, 255):                                          # encode -> decode round trip + byte equality
+        si = out["streams"][s]
+        blob = arena[int(si.byte_off): int(si.byte_off + si.byte_len)].tobytes()
+        dec, info = checkers.oracle_decode(blob)                    # validates every CRC-8/CRC-16 and the MD5
+        assert np.array_equal(dec, pcm[s].astype(np.int32))
+        assert blob == checkers.oracle_encode(pcm[s], 48000, 16, 5, 4096)
