@@ -110,6 +110,42 @@ int  flacb200_encode_batch_host(flacb200_ctx *ctx, const flacb200_enc_config *cf
                                 uint32_t n_streams, const uint64_t *stream_off, const uint64_t *stream_samples,
                                 uint8_t *arena, size_t arena_cap, uint64_t *total_bytes,
                                 uint64_t *frame_off, uint32_t *frame_len, flacb200_stream_info *streams);
+/* ------------------------------------------------------------------ batch decode ----
+ * n_streams independent FLAC byte strings (stream s = stream_len[s] bytes at byte offset stream_off[s] of `blob`).
+ * Output: interleaved PCM [sample][channel] per stream, back to back in stream order, in `out_container_bytes`
+ * sized elements (2 = int16 for <=16-bit streams, 4 = int32; 0 = choose 2 when every stream is <=16 bit).
+ * raw != NULL switches to headerless input: every "stream" is a run of frames without fLaC/metadata and raw
+ * supplies what STREAMINFO would (used by the drop-in stream decoder to decode as bytes arrive). */
+typedef struct {
+    uint64_t total_samples;       /* inter-channel samples decoded */
+    uint64_t pcm_off;             /* ELEMENT offset of the stream's first sample in the output */
+    uint64_t consumed;            /* bytes covered by metadata + successfully chained frames */
+    uint32_t n_frames;
+    int32_t  status;              /* 0 ok; 2 not FLAC, 3 bad metadata, 4 bad frame, 5 incomplete frame, 6 lost sync, 7 CRC-16 mismatch, 8 unsupported */
+    uint32_t sample_rate, channels, bits_per_sample, max_blocksize;
+} flacb200_dec_stream_info;
+
+typedef struct { uint32_t sample_rate, channels, bits_per_sample; } flacb200_dec_raw_params;
+
+typedef struct {
+    uint64_t total_elems;         /* PCM elements (samples x channels) produced over all streams */
+    uint32_t n_streams, n_frames;
+    uint32_t out_container_bytes;
+    uint32_t n_candidates;        /* frame-start candidates examined (>= n_frames) */
+    const void *d_pcm;            /* device pointer, valid until the next call on the ctx */
+} flacb200_dec_result;
+
+int  flacb200_decode_batch(flacb200_ctx *ctx, const uint8_t *blob, int blob_is_device, uint64_t blob_bytes,
+                           uint32_t n_streams, const uint64_t *stream_off, const uint64_t *stream_len,
+                           uint32_t out_container_bytes, const flacb200_dec_raw_params *raw);
+int  flacb200_decode_result(flacb200_ctx *ctx, flacb200_dec_result *res);
+/* Copy PCM and per-stream info to host (either may be NULL). pcm_cap in bytes.  frame_samples (optional,
+ * cap entries) receives the blocksize of every decoded frame in stream order. */
+int  flacb200_decode_fetch(flacb200_ctx *ctx, void *pcm, size_t pcm_cap, flacb200_dec_stream_info *streams,
+                           uint32_t *frame_samples, uint32_t frame_cap);
+/* ms[0..5] = metadata+sync scan, candidate decode, chain+layout, post (CRC/interleave), 0, 0 */
+int  flacb200_decode_kernel_times(flacb200_ctx *ctx, float *ms);
+
 /* Per-kernel device times of the last batch, measured with CUDA events on the launching streams:
  * ms[0..5] = analyze, pack, scan, compact, finalize(+MD5 join), md5 (side stream). */
 int  flacb200_set_profiling(flacb200_ctx *ctx, int on);

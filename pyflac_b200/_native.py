@@ -223,3 +223,102 @@ def encode_streams(engine, streams, sample_rate, bits_per_sample, compression_le
     for si in out["streams"]:
         res.append(out["arena"][int(si.byte_off):int(si.byte_off + si.byte_len)].tobytes())
     return res, out
+
+
+# ------------------------------------------------------------------ decode (batch ABI)
+class DecStreamInfo(C.Structure):
+    _fields_ = [("total_samples", C.c_uint64), ("pcm_off", C.c_uint64), ("consumed", C.c_uint64), ("n_frames", C.c_uint32),
+                ("status", C.c_int32), ("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32),
+                ("max_blocksize", C.c_uint32)]
+
+
+class DecResult(C.Structure):
+    _fields_ = [("total_elems", C.c_uint64), ("n_streams", C.c_uint32), ("n_frames", C.c_uint32),
+                ("out_container_bytes", C.c_uint32), ("n_candidates", C.c_uint32), ("d_pcm", C.c_void_p)]
+
+
+class DecRawParams(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32)]
+
+
+DEC_STATUS = {0: "ok", 2: "not FLAC", 3: "bad metadata", 4: "bad frame", 5: "incomplete frame", 6: "lost sync",
+              7: "CRC-16 mismatch", 8: "unsupported"}
+
+
+def _dec_proto(L):
+    if getattr(L, "_dec_proto_done", False):
+        return
+    L.flacb200_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
+                                        C.c_uint32, C.c_void_p]
+    L.flacb200_decode_result.argtypes = [C.c_void_p, C.POINTER(DecResult)]
+    L.flacb200_decode_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.flacb200_decode_kernel_times.argtypes = [C.c_void_p, C.c_void_p]
+    L._dec_proto_done = True
+
+
+def _engine_decode_device(self, blob_ptr, blob_bytes, stream_off, stream_len, out_container_bytes=0):
+    """Asynchronous-ish batch decode of FLAC bytes resident in HBM (sizes force 3 internal syncs)."""
+    _dec_proto(self._L)
+    so = np.ascontiguousarray(stream_off, np.uint64)
+    sl = np.ascontiguousarray(stream_len, np.uint64)
+    self._keep_dec = (so, sl)
+    self._check(self._L.flacb200_decode_batch(self._h, C.c_void_p(blob_ptr), 1, blob_bytes, len(so), so.ctypes.data,
+                                              sl.ctypes.data, out_container_bytes, None))
+
+
+def _engine_decode_host(self, blob, stream_off, stream_len, out_container_bytes=0, raw=None):
+    _dec_proto(self._L)
+    blob = np.ascontiguousarray(blob, np.uint8)
+    so = np.ascontiguousarray(stream_off, np.uint64)
+    sl = np.ascontiguousarray(stream_len, np.uint64)
+    rp = DecRawParams(*raw) if raw else None
+    self._keep_dec = (blob, so, sl, rp)
+    self._check(self._L.flacb200_decode_batch(self._h, blob.ctypes.data, 0, blob.size, len(so), so.ctypes.data, sl.ctypes.data,
+                                              out_container_bytes, C.byref(rp) if rp else None))
+
+
+def _engine_decode_result(self):
+    _dec_proto(self._L)
+    r = DecResult()
+    self._check(self._L.flacb200_decode_result(self._h, C.byref(r)))
+    return r
+
+
+def _engine_decode_fetch(self):
+    """-> (pcm flat array in the output container, [DecStreamInfo], frame_samples)"""
+    r = self.decode_result()
+    dt = np.int16 if r.out_container_bytes == 2 else np.int32
+    pcm = np.empty(max(int(r.total_elems), 1), dt)
+    infos = (DecStreamInfo * max(r.n_streams, 1))()
+    fs = np.zeros(max(r.n_frames, 1), np.uint32)
+    self._check(self._L.flacb200_decode_fetch(self._h, pcm.ctypes.data, pcm.nbytes, C.cast(infos, C.c_void_p), fs.ctypes.data, r.n_frames))
+    return pcm[:int(r.total_elems)], [infos[i] for i in range(r.n_streams)], fs[:r.n_frames]
+
+
+def _engine_decode_kernel_times(self):
+    _dec_proto(self._L)
+    ms = np.zeros(6, np.float32)
+    self._check(self._L.flacb200_decode_kernel_times(self._h, ms.ctypes.data))
+    return dict(zip(["sync_scan", "frame_decode", "chain_layout", "post"], [float(v) for v in ms[:4]]))
+
+
+Engine.decode_device = _engine_decode_device
+Engine.decode_host = _engine_decode_host
+Engine.decode_result = _engine_decode_result
+Engine.decode_fetch = _engine_decode_fetch
+Engine.decode_kernel_times = _engine_decode_kernel_times
+
+
+def decode_streams(engine, blobs, out_container_bytes=0):
+    """Convenience: decode a list of .flac byte strings -> list of (n, ch) arrays + infos."""
+    sizes = np.array([len(b) for b in blobs], np.uint64)
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64) if len(blobs) else np.zeros(0, np.uint64)
+    blob = np.frombuffer(b"".join(blobs) + bytes(16), np.uint8)
+    engine.decode_host(blob, offs, sizes, out_container_bytes)
+    pcm, infos, _ = engine.decode_fetch()
+    out = []
+    for si in infos:
+        ch = max(int(si.channels), 1)
+        n = int(si.total_samples)
+        out.append(pcm[int(si.pcm_off): int(si.pcm_off) + n * ch].reshape(n, ch))
+    return out, infos

@@ -1,0 +1,247 @@
+// dec_engine.cu -- host side of the batch decoder (include/flacb200.h "batch decode").
+//
+//   [H2D blob if host] -> meta -> sync(count) -> scan -> sync(write) -> size+scan -> frames -> chain -> scan -> post
+// Two host synchronisations per batch (candidate count, decoded PCM size) because device buffers are sized from them.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/flacb200.h"
+#include "fb_common.cuh"
+#include "dec_common.cuh"
+
+struct flacb200_ctx;
+int fb_ctx_device(flacb200_ctx*);
+cudaStream_t fb_ctx_stream(flacb200_ctx*);
+void** fb_ctx_dec_slot(flacb200_ctx*, void (*)(void*));
+int fb_ctx_fail(flacb200_ctx*, int, const char*, cudaError_t);
+void fb_ctx_add_launches(flacb200_ctx*, uint64_t);
+
+namespace fb {
+void launch_dec_meta(const uint8_t*, const uint64_t*, const uint64_t*, int, int, const DecStreamMeta&, DecStreamMeta*, cudaStream_t);
+void launch_dec_sync(const uint8_t*, const uint64_t*, const uint64_t*, const DecStreamMeta*, const DecSegment*, int, int, uint32_t*, const uint32_t*, DecCand*, cudaStream_t);
+void launch_dec_scan(const uint32_t*, int, uint32_t*, uint64_t*, uint64_t*, cudaStream_t);
+void launch_dec_cand_size(const DecCand*, int, uint32_t*, cudaStream_t);
+void launch_dec_frames(const uint8_t*, const uint64_t*, const uint64_t*, DecCand*, int, const uint64_t*, int32_t*, cudaStream_t);
+void launch_dec_chain(DecCand*, const uint32_t*, const DecStreamMeta*, const uint64_t*, int, DecStreamResult*, uint32_t*, cudaStream_t);
+void launch_dec_assign(DecStreamResult*, const uint64_t*, int, cudaStream_t);
+void launch_dec_post(const uint8_t*, const uint64_t*, DecCand*, int, const uint64_t*, const int32_t*, DecStreamResult*, void*, int, cudaStream_t);
+}
+using namespace fb;
+
+namespace {
+
+struct Buf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DecState {
+    Buf blob, soff, slen, meta, segs, segcount, segbase, cands, sizes, slotoff, samples, candfirst, res, ss32, pcmoff, pcm, total;
+    std::vector<DecSegment> h_segs;
+    std::vector<uint32_t> h_first_seg;      // first segment of each stream (+1 sentinel)
+    int n_streams = 0, n_cands = 0;
+    uint64_t total_elems = 0;
+    uint32_t out_bytes = 0;
+    bool have = false;
+    cudaEvent_t ev[5] = {nullptr};
+    std::vector<DecStreamResult> h_res;
+};
+
+void dec_free(void* p) {
+    DecState* d = (DecState*)p;
+    Buf* bufs[] = {&d->blob, &d->soff, &d->slen, &d->meta, &d->segs, &d->segcount, &d->segbase, &d->cands, &d->sizes, &d->slotoff, &d->samples,
+                   &d->candfirst, &d->res, &d->ss32, &d->pcmoff, &d->pcm, &d->total};
+    for (Buf* b : bufs) b->release();
+    for (auto& e : d->ev) if (e) cudaEventDestroy(e);
+    delete d;
+}
+
+DecState* state(flacb200_ctx* ctx) {
+    void** slot = fb_ctx_dec_slot(ctx, dec_free);
+    if (!*slot) { DecState* d = new DecState(); for (auto& e : d->ev) cudaEventCreate(&e); *slot = d; }
+    return (DecState*)*slot;
+}
+
+}  // namespace
+
+#define CKD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fb_ctx_fail(ctx, FLACB200_ERR_CUDA, #call, e_); } while (0)
+
+extern "C" int flacb200_decode_batch(flacb200_ctx* ctx, const uint8_t* blob, int blob_is_device, uint64_t blob_bytes,
+                                     uint32_t n_streams, const uint64_t* stream_off, const uint64_t* stream_len,
+                                     uint32_t out_container_bytes, const flacb200_dec_raw_params* raw) {
+    if (!ctx) return FLACB200_ERR_NO_DEVICE;
+    if ((!blob && blob_bytes) || (n_streams && (!stream_off || !stream_len))) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "null argument", cudaSuccess);
+    if (out_container_bytes != 0 && out_container_bytes != 2 && out_container_bytes != 4) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "out_container_bytes must be 0, 2 or 4", cudaSuccess);
+    cudaSetDevice(fb_ctx_device(ctx));
+    DecState* d = state(ctx);
+    cudaStream_t st = fb_ctx_stream(ctx);
+    d->have = false;
+    const int ns = (int)n_streams;
+    for (int s = 0; s < ns; s++) {
+        if (stream_off[s] + stream_len[s] > blob_bytes) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "stream exceeds blob", cudaSuccess);
+        if (stream_len[s] >= 0xFFFFFFF0ull) return fb_ctx_fail(ctx, FLACB200_ERR_UNSUPPORTED, "streams of 4 GiB or more are not supported", cudaSuccess);
+    }
+    // segments: every stream is cut into 4096-byte pieces scanned by one warp each
+    d->h_segs.clear(); d->h_first_seg.assign(ns + 1, 0);
+    for (int s = 0; s < ns; s++) {
+        d->h_first_seg[s] = (uint32_t)d->h_segs.size();
+        for (uint64_t o = 0; o < stream_len[s]; o += kDecSegBytes) {
+            DecSegment g; g.stream = (uint32_t)s; g.start = (uint32_t)o;
+            g.bytes = (uint32_t)((stream_len[s] - o < kDecSegBytes) ? (stream_len[s] - o) : kDecSegBytes);
+            d->h_segs.push_back(g);
+        }
+    }
+    d->h_first_seg[ns] = (uint32_t)d->h_segs.size();
+    const int nsegs = (int)d->h_segs.size();
+    d->n_streams = ns; d->n_cands = 0; d->total_elems = 0;
+    if (ns == 0) { d->have = true; d->out_bytes = out_container_bytes ? out_container_bytes : 2; return 0; }
+
+    const uint8_t* d_blob = blob;
+    if (!blob_is_device) {
+        CKD(d->blob.reserve(blob_bytes + 64));
+        CKD(cudaMemcpyAsync(d->blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, st));
+        CKD(cudaMemsetAsync((uint8_t*)d->blob.p + blob_bytes, 0, 16, st));
+        d_blob = (const uint8_t*)d->blob.p;
+    }
+    CKD(d->soff.reserve(8 * (size_t)(ns + 1))); CKD(d->slen.reserve(8 * (size_t)(ns + 1)));
+    CKD(d->meta.reserve(sizeof(DecStreamMeta) * (size_t)ns));
+    CKD(d->segs.reserve(sizeof(DecSegment) * (size_t)(nsegs + 1)));
+    CKD(d->segcount.reserve(4 * (size_t)(nsegs + 1))); CKD(d->segbase.reserve(4 * (size_t)(nsegs + 2)));
+    CKD(d->candfirst.reserve(4 * (size_t)(ns + 2)));
+    CKD(d->res.reserve(sizeof(DecStreamResult) * (size_t)ns)); CKD(d->ss32.reserve(4 * (size_t)(ns + 1)));
+    CKD(d->pcmoff.reserve(8 * (size_t)(ns + 1))); CKD(d->total.reserve(64));
+    CKD(cudaMemcpyAsync(d->soff.p, stream_off, 8 * (size_t)ns, cudaMemcpyHostToDevice, st));
+    CKD(cudaMemcpyAsync(d->slen.p, stream_len, 8 * (size_t)ns, cudaMemcpyHostToDevice, st));
+    if (nsegs) CKD(cudaMemcpyAsync(d->segs.p, d->h_segs.data(), sizeof(DecSegment) * (size_t)nsegs, cudaMemcpyHostToDevice, st));
+
+    DecStreamMeta rawp; memset(&rawp, 0, sizeof rawp);
+    if (raw) { rawp.sample_rate = raw->sample_rate; rawp.channels = raw->channels; rawp.bps = raw->bits_per_sample; }
+    CKD(cudaEventRecord(d->ev[0], st));
+    launch_dec_meta(d_blob, (const uint64_t*)d->soff.p, (const uint64_t*)d->slen.p, ns, raw ? 1 : 0, rawp, (DecStreamMeta*)d->meta.p, st);
+    uint64_t h_total = 0;
+    if (nsegs) {
+        launch_dec_sync(d_blob, (const uint64_t*)d->soff.p, (const uint64_t*)d->slen.p, (const DecStreamMeta*)d->meta.p, (const DecSegment*)d->segs.p, nsegs, 0,
+                        (uint32_t*)d->segcount.p, nullptr, nullptr, st);
+        launch_dec_scan((const uint32_t*)d->segcount.p, nsegs, (uint32_t*)d->segbase.p, nullptr, (uint64_t*)d->total.p, st);
+        CKD(cudaMemcpyAsync(&h_total, d->total.p, 8, cudaMemcpyDeviceToHost, st));
+        CKD(cudaStreamSynchronize(st));                                  // sync #1: number of candidates
+    }
+    const int nc = (int)h_total;
+    d->n_cands = nc;
+    CKD(d->cands.reserve(sizeof(DecCand) * (size_t)(nc + 1)));
+    CKD(d->sizes.reserve(4 * (size_t)(nc + 1))); CKD(d->slotoff.reserve(8 * (size_t)(nc + 1)));
+    if (nsegs && nc)
+        launch_dec_sync(d_blob, (const uint64_t*)d->soff.p, (const uint64_t*)d->slen.p, (const DecStreamMeta*)d->meta.p, (const DecSegment*)d->segs.p, nsegs, 1,
+                        (uint32_t*)d->segcount.p, (const uint32_t*)d->segbase.p, (DecCand*)d->cands.p, st);
+    // first candidate of each stream = scan value at the stream's first segment (+ sentinel = nc)
+    {
+        std::vector<uint32_t> h_base((size_t)nsegs + 1, 0);
+        if (nsegs) CKD(cudaMemcpyAsync(h_base.data(), d->segbase.p, 4 * (size_t)nsegs, cudaMemcpyDeviceToHost, st));
+        CKD(cudaStreamSynchronize(st));
+        h_base[nsegs] = (uint32_t)nc;
+        std::vector<uint32_t> cf(ns + 1);
+        for (int s = 0; s <= ns; s++) cf[s] = h_base[d->h_first_seg[s]];
+        CKD(cudaMemcpy(d->candfirst.p, cf.data(), 4 * (size_t)(ns + 1), cudaMemcpyHostToDevice));
+    }
+    CKD(cudaEventRecord(d->ev[1], st));
+    uint64_t h_slots = 0;
+    if (nc) {
+        launch_dec_cand_size((const DecCand*)d->cands.p, nc, (uint32_t*)d->sizes.p, st);
+        launch_dec_scan((const uint32_t*)d->sizes.p, nc, nullptr, (uint64_t*)d->slotoff.p, (uint64_t*)d->total.p, st);
+        CKD(cudaMemcpyAsync(&h_slots, d->total.p, 8, cudaMemcpyDeviceToHost, st));
+        CKD(cudaStreamSynchronize(st));                                  // sync #2: scratch size for candidate samples
+        CKD(d->samples.reserve(4 * (size_t)(h_slots + 16)));
+        launch_dec_frames(d_blob, (const uint64_t*)d->soff.p, (const uint64_t*)d->slen.p, (DecCand*)d->cands.p, nc, (const uint64_t*)d->slotoff.p, (int32_t*)d->samples.p, st);
+    }
+    CKD(cudaEventRecord(d->ev[2], st));
+    launch_dec_chain((DecCand*)d->cands.p, (const uint32_t*)d->candfirst.p, (const DecStreamMeta*)d->meta.p, (const uint64_t*)d->slen.p, ns,
+                     (DecStreamResult*)d->res.p, (uint32_t*)d->ss32.p, st);
+    launch_dec_scan((const uint32_t*)d->ss32.p, ns, nullptr, (uint64_t*)d->pcmoff.p, (uint64_t*)d->total.p, st);
+    launch_dec_assign((DecStreamResult*)d->res.p, (const uint64_t*)d->pcmoff.p, ns, st);
+    d->h_res.resize(ns);
+    uint64_t h_elems = 0;
+    CKD(cudaMemcpyAsync(&h_elems, d->total.p, 8, cudaMemcpyDeviceToHost, st));
+    CKD(cudaMemcpyAsync(d->h_res.data(), d->res.p, sizeof(DecStreamResult) * (size_t)ns, cudaMemcpyDeviceToHost, st));
+    CKD(cudaStreamSynchronize(st));                                      // sync #3: PCM size
+    uint32_t ob = out_container_bytes;
+    if (ob == 0) { ob = 2; for (int s = 0; s < ns; s++) if (d->h_res[s].bps > 16) ob = 4; }
+    for (int s = 0; s < ns; s++) if (ob == 2 && d->h_res[s].bps > 16 && d->h_res[s].n_frames) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "int16 output requested for a >16-bit stream", cudaSuccess);
+    d->out_bytes = ob; d->total_elems = h_elems;
+    CKD(d->pcm.reserve((size_t)h_elems * ob + 64));
+    CKD(cudaEventRecord(d->ev[3], st));
+    launch_dec_post(d_blob, (const uint64_t*)d->soff.p, (DecCand*)d->cands.p, nc, (const uint64_t*)d->slotoff.p, (const int32_t*)d->samples.p,
+                    (DecStreamResult*)d->res.p, d->pcm.p, (int)ob, st);
+    CKD(cudaEventRecord(d->ev[4], st));
+    CKD(cudaGetLastError());
+    fb_ctx_add_launches(ctx, 11);
+    d->have = true;
+    return 0;
+}
+
+extern "C" int flacb200_decode_result(flacb200_ctx* ctx, flacb200_dec_result* res) {
+    if (!ctx || !res) return FLACB200_ERR_ARG;
+    DecState* d = state(ctx);
+    if (!d->have) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "no decode batch", cudaSuccess);
+    cudaSetDevice(fb_ctx_device(ctx));
+    cudaStream_t st = fb_ctx_stream(ctx);
+    if (d->n_streams) {
+        CKD(cudaMemcpyAsync(d->h_res.data(), d->res.p, sizeof(DecStreamResult) * (size_t)d->n_streams, cudaMemcpyDeviceToHost, st));   // post may have flagged CRC errors
+    }
+    CKD(cudaStreamSynchronize(st));
+    uint32_t nf = 0;
+    for (int s = 0; s < d->n_streams; s++) nf += d->h_res[s].n_frames;
+    res->total_elems = d->total_elems; res->n_streams = (uint32_t)d->n_streams; res->n_frames = nf; res->out_container_bytes = d->out_bytes;
+    res->n_candidates = (uint32_t)d->n_cands; res->d_pcm = d->pcm.p;
+    return 0;
+}
+
+extern "C" int flacb200_decode_fetch(flacb200_ctx* ctx, void* pcm, size_t pcm_cap, flacb200_dec_stream_info* streams, uint32_t* frame_samples, uint32_t frame_cap) {
+    flacb200_dec_result r;
+    int rc = flacb200_decode_result(ctx, &r);
+    if (rc) return rc;
+    DecState* d = state(ctx);
+    cudaStream_t st = fb_ctx_stream(ctx);
+    if (pcm) {
+        const size_t bytes = (size_t)r.total_elems * r.out_container_bytes;
+        if (pcm_cap < bytes) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "pcm buffer too small", cudaSuccess);
+        if (bytes) CKD(cudaMemcpyAsync(pcm, d->pcm.p, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<DecCand> hc;
+    if (frame_samples && d->n_cands) {
+        hc.resize(d->n_cands);
+        CKD(cudaMemcpyAsync(hc.data(), d->cands.p, sizeof(DecCand) * (size_t)d->n_cands, cudaMemcpyDeviceToHost, st));
+    }
+    CKD(cudaStreamSynchronize(st));
+    if (streams) {
+        for (int s = 0; s < d->n_streams; s++) {
+            const DecStreamResult& h = d->h_res[s];
+            flacb200_dec_stream_info& o = streams[s];
+            o.total_samples = h.total_samples; o.pcm_off = h.pcm_off; o.consumed = h.consumed; o.n_frames = h.n_frames; o.status = h.status;
+            o.sample_rate = h.sample_rate; o.channels = h.channels; o.bits_per_sample = h.bps; o.max_blocksize = h.max_blocksize;
+        }
+    }
+    if (frame_samples) { uint32_t k = 0; for (auto& c : hc) if (c.valid && k < frame_cap) frame_samples[k++] = c.blocksize; }
+    return 0;
+}
+
+extern "C" int flacb200_decode_kernel_times(flacb200_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return FLACB200_ERR_ARG;
+    DecState* d = state(ctx);
+    if (!d->have || !d->n_streams) return FLACB200_ERR_ARG;
+    cudaSetDevice(fb_ctx_device(ctx));
+    CKD(cudaStreamSynchronize(fb_ctx_stream(ctx)));
+    for (int i = 0; i < 4; i++) CKD(cudaEventElapsedTime(&ms[i], d->ev[i], d->ev[i + 1]));
+    ms[4] = ms[5] = 0.0f;
+    return 0;
+}

@@ -1,0 +1,464 @@
+// dec_kernels.cu -- decode path kernels (scope rows D1-D5).
+//
+// FLAC frames carry no length field and Rice codes are only self-delimiting sequentially, so the batch decoder is
+// organised as: (1) find every byte position that COULD start a frame (sync code + plausible header + CRC-8),
+// in parallel over all bytes of all streams; (2) decode every candidate independently, one thread per candidate
+// frame (bit-serial Rice unpack + fixed/LPC synthesis -- a serial recurrence per subframe); (3) per stream, walk
+// the chain "next frame starts where this one ended" from the first frame: true frames are always candidates,
+// false candidates are never reached by the chain, so the result equals libFLAC's sequential parse;
+// (4) post-process the chained frames with one CTA each: CRC-16, wasted bits are already applied, undo
+// left/side, right/side, mid/side, narrow and interleave to the caller's container with coalesced stores.
+// up: stream_decoder.c frame_sync_ / read_frame_header_ / read_subframe_* / read_residual_partitioned_rice_,
+//     bitreader.c FLAC__bitreader_read_rice_signed_block, lpc.c FLAC__lpc_restore_signal[_wide],
+//     fixed.c FLAC__fixed_restore_signal (ref: format.h:209-475, stream_decoder.h:1440-1513).
+#include "fb_common.cuh"
+#include "fb_math.cuh"
+#include "dec_common.cuh"
+
+namespace fb {
+
+// ------------------------------------------------------------------ metadata walk (one thread per stream) ----
+__global__ void dec_meta_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off,
+                                const uint64_t* __restrict__ stream_len, int n_streams, int raw_frames, DecStreamMeta raw_params,
+                                DecStreamMeta* __restrict__ meta) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    DecStreamMeta m;
+    if (raw_frames) { m = raw_params; m.first_frame = 0; m.status = kDecOk; meta[s] = m; return; }
+    m.first_frame = 0; m.sample_rate = 0; m.channels = 0; m.bps = 0; m.min_blocksize = 0; m.max_blocksize = 0; m.total_samples = 0; m.status = kDecOk;
+    for (int i = 0; i < 16; i++) m.md5[i] = 0;
+    const uint8_t* p = blob + stream_off[s];
+    const uint64_t len = stream_len[s];
+    if (len < 8 || p[0] != 'f' || p[1] != 'L' || p[2] != 'a' || p[3] != 'C') { m.status = kDecNotFlac; meta[s] = m; return; }
+    uint64_t pos = 4; bool last = false, have_si = false;
+    while (!last) {
+        if (pos + 4 > len) { m.status = kDecBadMetadata; break; }
+        const uint32_t type = p[pos] & 0x7f, blen = (uint32_t)p[pos + 1] << 16 | (uint32_t)p[pos + 2] << 8 | p[pos + 3];
+        last = (p[pos] >> 7) != 0; pos += 4;
+        if (pos + blen > len) { m.status = kDecBadMetadata; break; }
+        if (type == 0 && blen >= 34) {   // STREAMINFO (ref: format.h:546-557)
+            const uint8_t* q = p + pos;
+            m.min_blocksize = (uint32_t)q[0] << 8 | q[1]; m.max_blocksize = (uint32_t)q[2] << 8 | q[3];
+            m.sample_rate = (uint32_t)q[10] << 12 | (uint32_t)q[11] << 4 | (q[12] >> 4);
+            m.channels = ((q[12] >> 1) & 7) + 1;
+            m.bps = (((uint32_t)q[12] & 1) << 4 | (q[13] >> 4)) + 1;
+            m.total_samples = ((uint64_t)(q[13] & 0xF) << 32) | (uint64_t)q[14] << 24 | (uint64_t)q[15] << 16 | (uint64_t)q[16] << 8 | q[17];
+            for (int i = 0; i < 16; i++) m.md5[i] = q[18 + i];
+            have_si = true;
+        }
+        pos += blen;
+    }
+    if (m.status == kDecOk && !have_si) m.status = kDecBadMetadata;
+    m.first_frame = (uint32_t)pos;
+    meta[s] = m;
+}
+
+// ------------------------------------------------------------------ frame-start candidates ----
+// up: stream_decoder.c frame_sync_ + read_frame_header_.  Header layout: SURVEY Appendix B.
+__device__ __forceinline__ bool parse_header(const uint8_t* __restrict__ p, uint64_t avail, const DecStreamMeta& m, DecCand& c) {
+    if (avail < 5) return false;
+    if (p[0] != 0xFF || (p[1] & 0xFE) != 0xF8) return false;            // sync 0x3ffe + reserved 0
+    const uint32_t variable = p[1] & 1u;
+    const uint32_t bs_code = p[2] >> 4, sr_code = p[2] & 0xF, ca_code = p[3] >> 4, bps_code = (p[3] >> 1) & 7;
+    if (p[3] & 1) return false;
+    if (bs_code == 0 || sr_code == 15) return false;
+    if (ca_code > 10) return false;
+    if (bps_code == 3) return false;
+    // UTF-8 style coded number
+    uint32_t n = 4; uint64_t number;
+    {
+        const uint32_t b0 = p[n++];
+        uint32_t extra;
+        if (!(b0 & 0x80)) { number = b0; extra = 0; }
+        else if ((b0 & 0xE0) == 0xC0) { number = b0 & 0x1F; extra = 1; }
+        else if ((b0 & 0xF0) == 0xE0) { number = b0 & 0x0F; extra = 2; }
+        else if ((b0 & 0xF8) == 0xF0) { number = b0 & 0x07; extra = 3; }
+        else if ((b0 & 0xFC) == 0xF8) { number = b0 & 0x03; extra = 4; }
+        else if ((b0 & 0xFE) == 0xFC) { number = b0 & 0x01; extra = 5; }
+        else if (b0 == 0xFE && variable) { number = 0; extra = 6; }
+        else return false;
+        if (n + extra + 1 > avail) return false;
+        for (uint32_t i = 0; i < extra; i++) { const uint32_t b = p[n++]; if ((b & 0xC0) != 0x80) return false; number = (number << 6) | (b & 0x3F); }
+    }
+    uint32_t N;
+    switch (bs_code) {
+        case 1: N = 192; break;
+        case 2: case 3: case 4: case 5: N = 576u << (bs_code - 2); break;
+        case 6: if (n + 2 > avail) return false; N = (uint32_t)p[n] + 1; n += 1; break;
+        case 7: if (n + 3 > avail) return false; N = ((uint32_t)p[n] << 8 | p[n + 1]) + 1; n += 2; break;
+        default: N = 256u << (bs_code - 8); break;
+    }
+    uint32_t sr;
+    switch (sr_code) {
+        case 0: sr = m.sample_rate; break; case 1: sr = 88200; break; case 2: sr = 176400; break; case 3: sr = 192000; break;
+        case 4: sr = 8000; break; case 5: sr = 16000; break; case 6: sr = 22050; break; case 7: sr = 24000; break;
+        case 8: sr = 32000; break; case 9: sr = 44100; break; case 10: sr = 48000; break; case 11: sr = 96000; break;
+        case 12: if (n + 2 > avail) return false; sr = (uint32_t)p[n] * 1000u; n += 1; break;
+        case 13: if (n + 3 > avail) return false; sr = (uint32_t)p[n] << 8 | p[n + 1]; n += 2; break;
+        default: if (n + 3 > avail) return false; sr = ((uint32_t)p[n] << 8 | p[n + 1]) * 10u; n += 2; break;
+    }
+    uint32_t bps;
+    switch (bps_code) { case 0: bps = m.bps; break; case 1: bps = 8; break; case 2: bps = 12; break; case 4: bps = 16; break;
+                        case 5: bps = 20; break; case 6: bps = 24; break; default: bps = 32; break; }
+    if (bps == 0) return false;
+    if (n + 1 > avail) return false;
+    uint8_t crc = 0;
+    for (uint32_t i = 0; i < n; i++) crc = crc8_byte(crc, p[i]);
+    if (crc != p[n]) return false;
+    c.blocksize = N; c.hdr_bytes = n + 1; c.sample_rate = sr; c.bps = (uint8_t)bps;
+    c.channels = (uint8_t)(ca_code < 8 ? ca_code + 1 : 2); c.ca = (uint8_t)(ca_code < 8 ? 0 : ca_code - 7);
+    c.variable = (uint8_t)variable; c.number = number;
+    return true;
+}
+
+// One warp per 4096-byte segment; pass 0 counts candidates, pass 1 writes them in position order.
+__global__ void __launch_bounds__(128)
+dec_sync_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, const uint64_t* __restrict__ stream_len,
+                const DecStreamMeta* __restrict__ meta, const DecSegment* __restrict__ segs, int n_segs, int pass,
+                uint32_t* __restrict__ seg_count, const uint32_t* __restrict__ seg_base, DecCand* __restrict__ cands) {
+    const int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (seg >= n_segs) return;
+    const DecSegment sg = segs[seg];
+    const DecStreamMeta m = meta[sg.stream];
+    const uint8_t* sbase = blob + stream_off[sg.stream];
+    const uint64_t slen = stream_len[sg.stream];
+    uint32_t count = 0;
+    const uint32_t out0 = pass ? seg_base[seg] : 0u;
+    if (m.status == kDecOk) {
+        for (uint32_t o = 0; o < kDecSegBytes; o += 32) {
+            const uint64_t pos = (uint64_t)sg.start + o + lane;
+            DecCand c; bool hit = false;
+            if (pos + 1 < slen && o + lane < sg.bytes && pos >= m.first_frame) {
+                if (sbase[pos] == 0xFF && (sbase[pos + 1] & 0xFE) == 0xF8) {
+                    hit = parse_header(sbase + pos, slen - pos, m, c);
+                    // frames of one stream keep channels / bps (cheap plausibility filter; the chain decides anyway)
+                    if (hit && (c.channels != m.channels || c.bps != m.bps) && m.channels) hit = false;
+                }
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            if (pass && hit) {
+                c.stream = sg.stream; c.pos = (uint32_t)pos;
+                c.status = kDecPending; c.end_pos = 0; c.sample_slot = 0; c.valid = 0; c.sample_off = 0;
+                cands[out0 + count + __popc(mask & ((1u << lane) - 1u))] = c;
+            }
+            count += __popc(mask);
+        }
+    }
+    if (!pass && lane == 0) seg_count[seg] = count;
+}
+
+// Generic single-CTA exclusive scan of uint32 -> uint64 (counts are small; n up to a few million)
+__global__ void __launch_bounds__(1024)
+dec_scan_u32_kernel(const uint32_t* __restrict__ in, int n, uint32_t* __restrict__ out32, uint64_t* __restrict__ out64, uint64_t* __restrict__ total) {
+    __shared__ unsigned long long part[1024];
+    const int tid = threadIdx.x, per = (n + 1023) / 1024;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    unsigned long long s = 0;
+    for (int i = lo; i < hi; i++) s += in[i];
+    part[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned long long v = (tid >= o) ? part[tid - o] : 0ull;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    unsigned long long run = part[tid] - s;
+    for (int i = lo; i < hi; i++) { if (out32) out32[i] = (uint32_t)run; if (out64) out64[i] = run; run += in[i]; }
+    if (tid == 1023 && total) *total = part[1023];
+}
+
+__global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, uint32_t* __restrict__ sizes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sizes[i] = cands[i].blocksize * cands[i].channels;
+}
+
+// ------------------------------------------------------------------ frame decode: one thread per candidate ----
+struct BitReader {
+    const uint8_t* __restrict__ base;   // stream start
+    uint64_t pos, end;                  // next byte to fetch, stream length
+    uint64_t acc; int n;                // n valid bits at the top of acc
+    bool overrun;
+    __device__ __forceinline__ void init(const uint8_t* b, uint64_t start, uint64_t e) { base = b; pos = start; end = e; acc = 0; n = 0; overrun = false; }
+    __device__ __forceinline__ void refill() {
+        while (n <= 56) {
+            uint64_t byte = 0;
+            if (pos < end) byte = __ldg(base + pos); else if (pos >= end + 8) overrun = true;
+            pos++;
+            acc |= byte << (56 - n);
+            n += 8;
+        }
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t k) {          // k <= 32
+        if (k == 0) return 0u;
+        if (n < (int)k) refill();
+        const uint32_t v = (uint32_t)(acc >> (64 - k));
+        acc <<= k; n -= (int)k;
+        return v;
+    }
+    __device__ __forceinline__ int32_t get_signed(uint32_t k) {
+        if (k == 0) return 0;
+        const uint32_t v = get(k);
+        return (int32_t)(v << (32 - k)) >> (32 - k);
+    }
+    __device__ __forceinline__ int64_t get_signed64(uint32_t k) {  // k <= 33
+        if (k <= 32) return (int64_t)get_signed(k);
+        const int64_t hi = (int64_t)get_signed(k - 32);
+        return (hi << 32) | (int64_t)get(32);
+    }
+    __device__ __forceinline__ uint32_t unary() {
+        uint32_t q = 0;
+        for (;;) {
+            if (n == 0) refill();
+            if (acc != 0) {
+                const int z = __clzll((long long)acc);
+                q += (uint32_t)z;
+                acc <<= (z + 1); n -= (z + 1);
+                return q;
+            }
+            q += (uint32_t)n; n = 0;
+            if (overrun || q > (1u << 26)) { overrun = true; return q; }
+        }
+    }
+    __device__ __forceinline__ uint64_t bit_position() const { return pos * 8ull - (uint64_t)n; }
+};
+
+// per-thread history ring and coefficients live in shared memory, [index][thread] so lanes hit distinct banks
+template <int THREADS>
+struct DecShared { int32_t hist[32][THREADS]; int32_t q[32][THREADS]; };
+
+constexpr int kDecFrameThreads = 64;
+
+__global__ void __launch_bounds__(kDecFrameThreads)
+dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, const uint64_t* __restrict__ stream_len,
+                 DecCand* __restrict__ cands, int n_cands, const uint64_t* __restrict__ slot_off, int32_t* __restrict__ samples) {
+    __shared__ DecShared<kDecFrameThreads> sh;
+    const int t = threadIdx.x, ci = blockIdx.x * kDecFrameThreads + t;
+    if (ci >= n_cands) return;
+    DecCand c = cands[ci];
+    const uint8_t* sbase = blob + stream_off[c.stream];
+    const uint64_t slen = stream_len[c.stream];
+    BitReader br; br.init(sbase, (uint64_t)c.pos + c.hdr_bytes, slen);
+    const uint32_t N = c.blocksize;
+    int32_t* out = samples + slot_off[ci];
+    int status = kDecOk;
+    for (uint32_t chn = 0; chn < c.channels && status == kDecOk; chn++) {
+        int32_t* o = out + (size_t)chn * N;
+        uint32_t bps = c.bps + (((c.ca == 1 && chn == 1) || (c.ca == 2 && chn == 0) || (c.ca == 3 && chn == 1)) ? 1u : 0u);
+        const uint32_t hdr = br.get(8);
+        if (hdr & 0x80) { status = kDecBadFrame; break; }
+        uint32_t wasted = 0;
+        if (hdr & 1) { wasted = br.unary() + 1; if (wasted >= bps) { status = kDecBadFrame; break; } bps -= wasted; }
+        const uint32_t type = (hdr >> 1) & 0x3f;
+        if (bps > 32) { status = kDecUnsupported; break; }                     // 33-bit side channel of 32-bit streams: not built yet
+        if (type == 0) {                                                        // CONSTANT
+            const int32_t v = br.get_signed(bps) << wasted;
+            for (uint32_t i = 0; i < N; i++) o[i] = v;
+        } else if (type == 1) {                                                 // VERBATIM
+            for (uint32_t i = 0; i < N; i++) o[i] = br.get_signed(bps) << wasted;
+        } else {
+            uint32_t order; int shift = 0; bool lpc;
+            if (type >= 8 && type <= 12) { order = type - 8; lpc = false; }
+            else if (type >= 32) { order = type - 31; lpc = true; }
+            else { status = kDecBadFrame; break; }
+            if (order > N) { status = kDecBadFrame; break; }
+            for (uint32_t i = 0; i < order; i++) { const int32_t v = br.get_signed(bps); sh.hist[i & 31][t] = v; o[i] = v << wasted; }
+            uint32_t prec = 0;
+            if (lpc) {
+                prec = br.get(4) + 1; if (prec == 16) { status = kDecBadFrame; break; }
+                shift = br.get_signed(5); if (shift < 0) { status = kDecBadFrame; break; }
+                for (uint32_t j = 0; j < order; j++) sh.q[j][t] = br.get_signed(prec);
+            } else {
+                const int32_t cf[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+                for (uint32_t j = 0; j < order; j++) sh.q[j][t] = cf[order][j];
+            }
+            // up: lpc.c FLAC__lpc_restore_signal vs _wide: 32-bit accumulate is exact iff bps + precision + ilog2(order) <= 32
+            const bool wide = lpc ? (bps + prec + ilog2_u32(order ? order : 1) > 32) : (bps + order > 31);
+            // residual: method, partition order, then per partition a parameter and its symbols
+            const uint32_t method = br.get(2);
+            if (method > 1) { status = kDecBadFrame; break; }
+            const uint32_t po = br.get(4), parts = 1u << po, plen = method ? 5u : 4u, pesc = method ? 31u : 15u;
+            if ((N >> po) < order || (po > 0 && (N & (parts - 1)))) { status = kDecBadFrame; break; }
+            uint32_t i = order;
+            for (uint32_t p = 0; p < parts && !br.overrun; p++) {
+                const uint32_t cnt = (N >> po) - (p == 0 ? order : 0u);
+                const uint32_t k = br.get(plen);
+                const uint32_t raw = (k == pesc) ? br.get(5) : 0u;
+                for (uint32_t e = 0; e < cnt; e++, i++) {
+                    int32_t r;
+                    if (k == pesc) r = br.get_signed(raw);
+                    else {
+                        const uint32_t qv = br.unary();
+                        const uint32_t u = (qv << k) | br.get(k);
+                        r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1u);
+                    }
+                    int32_t v;
+                    if (wide) {
+                        long long s = 0;
+                        for (uint32_t j = 0; j < order; j++) s += (long long)sh.q[j][t] * (long long)sh.hist[(i - 1 - j) & 31][t];
+                        v = (int32_t)((long long)r + (s >> shift));
+                    } else {
+                        int s = 0;
+                        for (uint32_t j = 0; j < order; j++) s += sh.q[j][t] * sh.hist[(i - 1 - j) & 31][t];
+                        v = r + (s >> shift);
+                    }
+                    sh.hist[i & 31][t] = v;
+                    o[i] = v << wasted;
+                }
+                if (br.overrun) break;
+            }
+        }
+        if (br.overrun) status = kDecIncomplete;
+    }
+    uint64_t endbit = br.bit_position();
+    if (status == kDecOk) {
+        // zero padding to the byte boundary, then CRC-16 (checked by the post kernel)
+        const uint32_t padbits = (uint32_t)((8 - (endbit & 7)) & 7);
+        if (padbits && br.get(padbits) != 0) status = kDecBadFrame;
+        endbit += padbits;
+        const uint64_t endbyte = endbit >> 3;
+        if (endbyte + 2 > slen) status = kDecIncomplete;
+        c.end_pos = (uint32_t)(endbyte + 2);
+    }
+    cands[ci].status = status;
+    cands[ci].end_pos = c.end_pos;
+}
+
+// ------------------------------------------------------------------ chain walk: one thread per stream ----
+__global__ void dec_chain_kernel(DecCand* __restrict__ cands, const uint32_t* __restrict__ cand_first, const DecStreamMeta* __restrict__ meta,
+                                 const uint64_t* __restrict__ stream_len, int n_streams, DecStreamResult* __restrict__ res, uint32_t* __restrict__ stream_samples32) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    DecStreamResult r; r.total_samples = 0; r.n_frames = 0; r.status = meta[s].status; r.consumed = meta[s].first_frame; r.max_blocksize = 0; r.pcm_off = 0;
+    r.sample_rate = meta[s].sample_rate; r.channels = meta[s].channels; r.bps = meta[s].bps;
+    if (r.status == kDecOk) {
+        uint64_t expect = meta[s].first_frame;
+        uint32_t i = cand_first[s];
+        const uint32_t iend = cand_first[s + 1];
+        const uint64_t slen = stream_len[s];
+        while (expect < slen) {
+            while (i < iend && cands[i].pos < expect) i++;
+            if (i >= iend || cands[i].pos != expect) { r.status = kDecLostSync; break; }
+            const int st = cands[i].status;
+            if (st != kDecOk) { r.status = st; break; }
+            if (r.n_frames == 0) { r.sample_rate = cands[i].sample_rate; r.channels = cands[i].channels; r.bps = cands[i].bps; }
+            cands[i].valid = 1; cands[i].sample_off = r.total_samples;
+            r.total_samples += cands[i].blocksize; r.n_frames++;
+            if (cands[i].blocksize > r.max_blocksize) r.max_blocksize = cands[i].blocksize;
+            expect = cands[i].end_pos;
+            r.consumed = expect;
+            i++;
+        }
+    }
+    res[s] = r;
+    stream_samples32[s] = (uint32_t)(r.total_samples * (r.channels ? r.channels : 1));   // elements; streams < 2^32 elements
+}
+
+__global__ void dec_assign_kernel(DecStreamResult* __restrict__ res, const uint64_t* __restrict__ pcm_off, int n_streams) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_streams) res[s].pcm_off = pcm_off[s];
+}
+
+// ------------------------------------------------------------------ post: one CTA per chained frame ----
+// CRC-16 of the frame bytes (chunked, combined in GF(2)[x]/P like the encoder), undo channel decorrelation
+// (ref: format.h:388-393), narrow to the caller's container, interleave [sample][channel], coalesced stores.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+dec_post_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, DecCand* __restrict__ cands,
+                const uint64_t* __restrict__ slot_off, const int32_t* __restrict__ samples, DecStreamResult* __restrict__ res,
+                OutT* __restrict__ pcm_out) {
+    __shared__ uint16_t crc_tab[256];
+    __shared__ uint16_t crc_warp[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DecCand c = cands[blockIdx.x];
+    if (!c.valid) return;
+    {
+        uint16_t v = (uint16_t)(tid << 8);
+#pragma unroll
+        for (int i = 0; i < 8; i++) v = (uint16_t)((v & 0x8000) ? ((v << 1) ^ 0x8005) : (v << 1));
+        crc_tab[tid] = v;
+    }
+    __syncthreads();
+    const uint8_t* fb = blob + stream_off[c.stream] + c.pos;
+    const uint32_t nb = c.end_pos - c.pos - 2u;
+    const uint32_t csize = 64u * ((nb + 64u * 256u - 1u) / (64u * 256u)), nchunks = (nb + csize - 1u) / csize;
+    uint16_t xs;
+    { uint16_t result = 1, basep = 2; uint32_t e = 8u * csize; while (e) { if (e & 1u) result = crc16_mulmod(result, basep); basep = crc16_mulmod(basep, basep); e >>= 1; } xs = result; }
+    uint16_t crc = 0;
+    {
+        const int tt = tid - (int)(256u - nchunks);
+        if (tt >= 0) {
+            const long long end = (long long)nb - (long long)(nchunks - 1u - (uint32_t)tt) * csize;
+            long long beg = end - csize; if (beg < 0) beg = 0;
+            for (long long j = beg; j < end; j++) crc = (uint16_t)((crc << 8) ^ crc_tab[(crc >> 8) ^ __ldg(fb + j)]);
+        }
+    }
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const uint16_t other = (uint16_t)__shfl_down_sync(0xffffffffu, (uint32_t)crc, s);
+        if ((lane & (2 * s - 1)) == 0) crc = (uint16_t)(crc16_mulmod(crc, xs) ^ other);
+        xs = crc16_mulmod(xs, xs);
+    }
+    if (lane == 0) crc_warp[warp] = crc;
+    __syncthreads();
+    if (warp == 0) {
+        uint16_t c2 = lane < 8 ? crc_warp[lane] : (uint16_t)0;
+#pragma unroll
+        for (int s = 1; s < 8; s <<= 1) {
+            const uint16_t other = (uint16_t)__shfl_down_sync(0xffffffffu, (uint32_t)c2, s);
+            if ((lane & (2 * s - 1)) == 0) c2 = (uint16_t)(crc16_mulmod(c2, xs) ^ other);
+            xs = crc16_mulmod(xs, xs);
+        }
+        if (lane == 0) {
+            const uint16_t stored = (uint16_t)((uint16_t)fb[nb] << 8 | fb[nb + 1]);
+            if (c2 != stored) { res[c.stream].status = kDecCrcMismatch; cands[blockIdx.x].status = kDecCrcMismatch; }
+        }
+    }
+    const uint32_t N = c.blocksize, ch = c.channels;
+    const int32_t* in = samples + slot_off[blockIdx.x];
+    OutT* out = pcm_out + res[c.stream].pcm_off + c.sample_off * ch;
+    if (c.ca == 0) {
+        for (uint32_t e = tid; e < N * ch; e += 256) { const uint32_t i = e / ch, k = e - i * ch; out[e] = (OutT)in[(size_t)k * N + i]; }
+    } else {
+        for (uint32_t i = tid; i < N; i += 256) {
+            const int32_t a = in[i], b = in[N + i];
+            int32_t l, r;
+            if (c.ca == 1) { l = a; r = a - b; }
+            else if (c.ca == 2) { l = a + b; r = b; }
+            else { const int32_t m2 = (int32_t)(((uint32_t)a << 1) | ((uint32_t)b & 1u)); l = (m2 + b) >> 1; r = (m2 - b) >> 1; }
+            out[2 * i] = (OutT)l; out[2 * i + 1] = (OutT)r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ launchers ----
+void launch_dec_meta(const uint8_t* blob, const uint64_t* soff, const uint64_t* slen, int ns, int raw, const DecStreamMeta& rawp, DecStreamMeta* meta, cudaStream_t st) {
+    dec_meta_kernel<<<(ns + 127) / 128, 128, 0, st>>>(blob, soff, slen, ns, raw, rawp, meta);
+}
+void launch_dec_sync(const uint8_t* blob, const uint64_t* soff, const uint64_t* slen, const DecStreamMeta* meta, const DecSegment* segs, int nsegs, int pass,
+                     uint32_t* seg_count, const uint32_t* seg_base, DecCand* cands, cudaStream_t st) {
+    dec_sync_kernel<<<(nsegs + 3) / 4, 128, 0, st>>>(blob, soff, slen, meta, segs, nsegs, pass, seg_count, seg_base, cands);
+}
+void launch_dec_scan(const uint32_t* in, int n, uint32_t* out32, uint64_t* out64, uint64_t* total, cudaStream_t st) {
+    dec_scan_u32_kernel<<<1, 1024, 0, st>>>(in, n, out32, out64, total);
+}
+void launch_dec_cand_size(const DecCand* cands, int n, uint32_t* sizes, cudaStream_t st) {
+    if (n) dec_cand_size_kernel<<<(n + 255) / 256, 256, 0, st>>>(cands, n, sizes);
+}
+void launch_dec_frames(const uint8_t* blob, const uint64_t* soff, const uint64_t* slen, DecCand* cands, int n, const uint64_t* slot_off, int32_t* samples, cudaStream_t st) {
+    if (n) dec_frame_kernel<<<(n + kDecFrameThreads - 1) / kDecFrameThreads, kDecFrameThreads, 0, st>>>(blob, soff, slen, cands, n, slot_off, samples);
+}
+void launch_dec_chain(DecCand* cands, const uint32_t* cand_first, const DecStreamMeta* meta, const uint64_t* slen, int ns, DecStreamResult* res, uint32_t* ss32, cudaStream_t st) {
+    dec_chain_kernel<<<(ns + 127) / 128, 128, 0, st>>>(cands, cand_first, meta, slen, ns, res, ss32);
+}
+void launch_dec_assign(DecStreamResult* res, const uint64_t* pcm_off, int ns, cudaStream_t st) {
+    dec_assign_kernel<<<(ns + 127) / 128, 128, 0, st>>>(res, pcm_off, ns);
+}
+void launch_dec_post(const uint8_t* blob, const uint64_t* soff, DecCand* cands, int n, const uint64_t* slot_off, const int32_t* samples, DecStreamResult* res,
+                     void* pcm_out, int out_bytes, cudaStream_t st) {
+    if (!n) return;
+    if (out_bytes == 2) dec_post_kernel<int16_t><<<n, 256, 0, st>>>(blob, soff, cands, slot_off, samples, res, (int16_t*)pcm_out);
+    else dec_post_kernel<int32_t><<<n, 256, 0, st>>>(blob, soff, cands, slot_off, samples, res, (int32_t*)pcm_out);
+}
+
+}  // namespace fb

@@ -338,7 +338,7 @@ size_t pack_smem_bytes(const EncParams& P, uint32_t scratch_stride) {
 // per-stream prologue gap, so that every stream's .flac image is contiguous in the output arena.
 __global__ void __launch_bounds__(1024)
 scan_kernel(const uint32_t* __restrict__ frame_len, const FrameDesc* __restrict__ frames, int n_frames,
-            uint32_t prologue_bytes, uint64_t* __restrict__ frame_off, uint64_t* __restrict__ total_bytes) {
+            uint32_t prologue_bytes, uint64_t base, uint64_t* __restrict__ frame_off, uint64_t* __restrict__ total_bytes) {
     __shared__ unsigned long long part[1024];
     const int tid = threadIdx.x;
     const int per = (n_frames + 1023) / 1024;
@@ -356,7 +356,7 @@ scan_kernel(const uint32_t* __restrict__ frame_len, const FrameDesc* __restrict_
         part[tid] += v;
         __syncthreads();
     }
-    unsigned long long run = part[tid] - s;
+    unsigned long long run = base + part[tid] - s;
     for (int f = lo; f < hi; f++) {
         const bool first = (f == 0) || (frames[f].stream != frames[f - 1].stream);
         if (first) run += prologue_bytes;
@@ -532,9 +532,9 @@ void launch_md5(const void* pcm, uint32_t container_bytes, const uint64_t* strea
     else md5_kernel<int32_t><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
 }
 
-void launch_layout(const uint32_t* frame_len, const FrameDesc* frames, int n_frames, uint32_t prologue_bytes,
+void launch_layout(const uint32_t* frame_len, const FrameDesc* frames, int n_frames, uint32_t prologue_bytes, uint64_t base,
                    uint64_t* frame_off, uint64_t* total_bytes, cudaStream_t stream) {
-    scan_kernel<<<1, 1024, 0, stream>>>(frame_len, frames, n_frames, prologue_bytes, frame_off, total_bytes);
+    scan_kernel<<<1, 1024, 0, stream>>>(frame_len, frames, n_frames, prologue_bytes, base, frame_off, total_bytes);
 }
 void launch_compact(const uint8_t* scratch, uint32_t stride, const uint32_t* frame_len, const uint64_t* frame_off,
                     uint8_t* arena, int n_frames, cudaStream_t stream) {

@@ -9,12 +9,16 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <atomic>
 #include <map>
+#include <thread>
 #include <string>
 #include <vector>
 
 #include "../../include/flacb200.h"
 #include "fb_common.cuh"
+#include "md5_host.h"
 
 namespace fb {
 void launch_analyze(const void*, const FrameDesc*, const float*, const EncParams&, int, SubframePlan*, uint8_t*,
@@ -25,7 +29,7 @@ void launch_pack(const void*, const FrameDesc*, const EncParams&, int, const Sub
                  uint32_t, uint32_t*, cudaStream_t);
 size_t pack_smem_bytes(const EncParams&, uint32_t);
 void launch_md5(const void*, uint32_t, const uint64_t*, const uint64_t*, int, uint32_t, uint32_t, uint8_t*, cudaStream_t);
-void launch_layout(const uint32_t*, const FrameDesc*, int, uint32_t, uint64_t*, uint64_t*, cudaStream_t);
+void launch_layout(const uint32_t*, const FrameDesc*, int, uint32_t, uint64_t, uint64_t*, uint64_t*, cudaStream_t);
 void launch_compact(const uint8_t*, uint32_t, const uint32_t*, const uint64_t*, uint8_t*, int, cudaStream_t);
 void launch_finalize(const uint32_t*, const uint64_t*, const uint32_t*, const uint32_t*, const uint64_t*, const uint8_t*,
                      int, const EncParams&, uint32_t, uint8_t*, StreamInfoOut*, cudaStream_t);
@@ -71,6 +75,16 @@ struct flacb200_ctx {
     std::vector<float> h_windows;
     std::map<uint32_t, uint32_t> window_off;   // blocksize -> float offset in h_windows
     float window_p = -1.0f;
+
+    // host<->device pipeline of flacb200_encode_batch_host: copy streams, per-chunk events, host MD5 workers
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    static constexpr int kMaxChunks = 16;
+    cudaEvent_t ev_h2d[kMaxChunks] = {nullptr}, ev_done[kMaxChunks] = {nullptr};
+    void* dec = nullptr;                   // decode engine state (dec_engine.cu)
+    void (*dec_free)(void*) = nullptr;
+    uint64_t* h_totals = nullptr;          // pinned: per-chunk arena byte counts
+    DevBuf d_totals;
+    uint64_t e2e_last_bytes = 0;
 
     DevBuf d_pcm, d_frames, d_windows, d_plans, d_ca, d_scratch, d_flen, d_foff, d_arena, d_total, d_stats;
     DevBuf d_sfirst, d_snframes, d_soff, d_ssamples, d_md5, d_sinfo, d_debug;
@@ -182,6 +196,11 @@ extern "C" int flacb200_create(flacb200_ctx** out, int device) {
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     for (auto& e : ctx->ev_k) cudaEventCreate(&e);
+    cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
+    for (auto& e : ctx->ev_h2d) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& e : ctx->ev_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaHostAlloc((void**)&ctx->h_totals, sizeof(uint64_t) * flacb200_ctx::kMaxChunks, cudaHostAllocDefault);
     ctx->stream = ctx->own_stream;
     *out = ctx;
     return FLACB200_OK;
@@ -197,6 +216,12 @@ extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& e : ctx->ev_k) cudaEventDestroy(e);
+    for (auto& e : ctx->ev_h2d) cudaEventDestroy(e);
+    for (auto& e : ctx->ev_done) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->h2d_stream); cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->dec && ctx->dec_free) ctx->dec_free(ctx->dec);
+    if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+    ctx->d_totals.release();
     cudaStreamDestroy(ctx->own_stream); cudaStreamDestroy(ctx->md5_stream);
     delete ctx;
 }
@@ -204,6 +229,13 @@ extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
 extern "C" const char* flacb200_last_error(const flacb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
 extern "C" int flacb200_set_stream(flacb200_ctx* ctx, void* s) { if (!ctx) return FLACB200_ERR_ARG; ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return 0; }
 extern "C" int flacb200_sync(flacb200_ctx* ctx) { if (!ctx) return FLACB200_ERR_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+// accessors for the decode engine (dec_engine.cu keeps its own state behind ctx->dec)
+int fb_ctx_device(flacb200_ctx* c) { return c->device; }
+cudaStream_t fb_ctx_stream(flacb200_ctx* c) { return c->stream; }
+void** fb_ctx_dec_slot(flacb200_ctx* c, void (*freer)(void*)) { c->dec_free = freer; return &c->dec; }
+int fb_ctx_fail(flacb200_ctx* c, int code, const char* what, cudaError_t e) { return fail(c, code, what, e); }
+void fb_ctx_add_launches(flacb200_ctx* c, uint64_t n) { c->launches += n; }
+
 extern "C" int flacb200_set_profiling(flacb200_ctx* ctx, int on) { if (!ctx) return FLACB200_ERR_ARG; ctx->profiling = on != 0; return 0; }
 // ms[0..5] = analyze, pack, layout(scan), compact, finalize (incl. waiting for MD5), md5 (side stream) of the last batch
 extern "C" int flacb200_kernel_times(flacb200_ctx* ctx, float* ms) {
@@ -281,7 +313,7 @@ static int plan_batch(flacb200_ctx* ctx, const flacb200_enc_config& cfg, uint32_
     CK(ctx->d_scratch.reserve((size_t)nf * ctx->scratch_stride + 64));
     CK(ctx->d_flen.reserve(sizeof(uint32_t) * (size_t)(nf + 1)));
     CK(ctx->d_foff.reserve(sizeof(uint64_t) * (size_t)(nf + 1)));
-    CK(ctx->d_arena.reserve((size_t)nf * ctx->scratch_stride + (size_t)ns * kStreamPrologueBytes + 64));
+    CK(ctx->d_arena.reserve((size_t)nf * ctx->scratch_stride + (size_t)ns * kStreamPrologueBytes + 64 + 256 * (flacb200_ctx::kMaxChunks + 1)));
     CK(ctx->d_total.reserve(64));
     CK(ctx->d_stats.reserve(sizeof(EncStats)));
     CK(ctx->d_sfirst.reserve(sizeof(uint32_t) * (ns + 1)));
@@ -338,7 +370,7 @@ static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
                 (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)ctx->d_flen.p, st);
     if (prof) CK(cudaEventRecord(ctx->ev_k[2], st));
     const uint32_t pro = ctx->cfg.write_prologue ? (uint32_t)kStreamPrologueBytes : 0u;
-    launch_layout((const uint32_t*)ctx->d_flen.p, (const FrameDesc*)ctx->d_frames.p, nf, pro, (uint64_t*)ctx->d_foff.p,
+    launch_layout((const uint32_t*)ctx->d_flen.p, (const FrameDesc*)ctx->d_frames.p, nf, pro, 0ull, (uint64_t*)ctx->d_foff.p,
                   (uint64_t*)ctx->d_total.p, st);
     if (prof) CK(cudaEventRecord(ctx->ev_k[3], st));
     launch_compact((const uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (const uint32_t*)ctx->d_flen.p, (const uint64_t*)ctx->d_foff.p,
@@ -430,14 +462,158 @@ extern "C" int flacb200_encode_fetch_trace(flacb200_ctx* ctx, void* plans, size_
     return 0;
 }
 
+// Host -> host path (what a pyFLAC-style caller has: PCM in host memory, packed bytes wanted in host memory).
+// Streams are cut into up to 8 chunks of whole streams; chunk c+1's H2D copy, chunk c's kernels and chunk c-1's
+// D2H copy run concurrently on three CUDA streams, and the MD5 digests (serial chain per stream) are computed
+// by host threads straight from the caller's PCM while the GPU encodes (md5_host.h; DESIGN.md "MD5 placement").
+// The host arena is contiguous: stream images back to back in stream order; frame_off / streams[].byte_off index it.
 extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_config* cfg, const void* pcm_host, uint64_t pcm_elems,
                                           uint32_t n_streams, const uint64_t* stream_off, const uint64_t* stream_samples,
                                           uint8_t* arena, size_t arena_cap, uint64_t* total_bytes, uint64_t* frame_off,
                                           uint32_t* frame_len, flacb200_stream_info* streams) {
-    int rc = flacb200_encode_batch(ctx, cfg, pcm_host, 0, pcm_elems, n_streams, stream_off, stream_samples, nullptr);
-    if (rc) return rc;
-    rc = flacb200_encode_fetch(ctx, arena, arena_cap, frame_off, frame_len, nullptr, nullptr, streams);
-    if (rc) return rc;
-    if (total_bytes) { flacb200_enc_result r; flacb200_encode_result(ctx, &r); *total_bytes = r.total_bytes; }
+    if (!ctx) return FLACB200_ERR_NO_DEVICE;
+    if (!cfg || !pcm_host || !arena || (n_streams && (!stream_off || !stream_samples))) return fail(ctx, FLACB200_ERR_ARG, "null argument");
+    cudaSetDevice(ctx->device);
+    for (uint32_t s = 0; s < n_streams; s++)
+        if (stream_off[s] + stream_samples[s] * cfg->channels > pcm_elems) return fail(ctx, FLACB200_ERR_ARG, "stream exceeds pcm buffer");
+    if (!same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr)) {
+        ctx->have_batch = false;
+        int rc = plan_batch(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr);
+        if (rc) return rc;
+    }
+    const EncParams& P = ctx->P;
+    const int nf = ctx->n_frames, ns = ctx->n_streams;
+    const uint32_t cont = cfg->container_bytes;
+    if (total_bytes) *total_bytes = 0;
+    if (nf == 0) return 0;
+    cudaStream_t st = ctx->stream;
+    CK(ctx->d_pcm.reserve((size_t)pcm_elems * cont + 64));
+    CK(ctx->d_totals.reserve(sizeof(uint64_t) * flacb200_ctx::kMaxChunks));
+
+    // ---- chunk boundaries (whole streams, roughly equal sample counts) ----
+    const int nchunks = ns < 8 ? ns : 8;
+    std::vector<int> cs(nchunks + 1, 0);
+    {
+        uint64_t tot = 0; for (int s = 0; s < ns; s++) tot += stream_samples[s];
+        uint64_t acc = 0; int c = 1;
+        for (int s = 0; s < ns && c < nchunks; s++) {
+            acc += stream_samples[s];
+            if (acc * nchunks >= tot * c && s + 1 >= c) { cs[c++] = s + 1; }
+        }
+        for (; c <= nchunks; c++) cs[c] = ns;
+        cs[nchunks] = ns;
+    }
+
+    // ---- host MD5 workers (one serial chain per stream) ----
+    const bool want_md5 = cfg->do_md5 != 0;
+    std::vector<uint8_t> digests((size_t)ns * 16, 0);
+    std::vector<std::thread> workers;
+    std::atomic<int> next_stream{0};
+    if (want_md5) {
+        unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 8;
+        const unsigned nt = std::min<unsigned>(std::min<unsigned>(hw, 64u), (unsigned)ns);
+        const uint32_t bytes_per = (P.bps + 7) / 8, chn = P.channels;
+        for (unsigned t = 0; t < nt; t++)
+            workers.emplace_back([&, bytes_per, chn]() {
+                for (;;) {
+                    const int s = next_stream.fetch_add(1);
+                    if (s >= ns) break;
+                    fb::Md5 m; m.init();
+                    m.update_samples((const uint8_t*)pcm_host + stream_off[s] * cont, (size_t)stream_samples[s] * chn, cont, bytes_per);
+                    m.final(&digests[(size_t)s * 16]);
+                }
+            });
+    }
+    auto join_workers = [&]() { for (auto& w : workers) if (w.joinable()) w.join(); };
+
+    // ---- enqueue: H2D per chunk, then kernels per chunk ----
+    auto bail = [&](int code) { join_workers(); return code; };
+#define CKJ(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(ctx, FLACB200_ERR_CUDA, #call, e_)); } while (0)
+    CKJ(cudaMemsetAsync(ctx->d_stats.p, 0, sizeof(EncStats), st));
+    bool monotonic = true;
+    for (int s = 1; s < ns; s++) if (stream_off[s] < stream_off[s - 1] + stream_samples[s - 1] * P.channels) { monotonic = false; break; }
+    for (int c = 0; c < nchunks; c++) {
+        const int s0 = cs[c], s1 = cs[c + 1];
+        if (s1 > s0) {
+            if (monotonic) {
+                const uint64_t e0 = stream_off[s0], e1 = stream_off[s1 - 1] + stream_samples[s1 - 1] * P.channels;
+                CKJ(cudaMemcpyAsync((uint8_t*)ctx->d_pcm.p + e0 * cont, (const uint8_t*)pcm_host + e0 * cont, (e1 - e0) * cont, cudaMemcpyHostToDevice, ctx->h2d_stream));
+            } else {
+                for (int s = s0; s < s1; s++)
+                    CKJ(cudaMemcpyAsync((uint8_t*)ctx->d_pcm.p + stream_off[s] * cont, (const uint8_t*)pcm_host + stream_off[s] * cont,
+                                        stream_samples[s] * P.channels * cont, cudaMemcpyHostToDevice, ctx->h2d_stream));
+            }
+        }
+        CKJ(cudaEventRecord(ctx->ev_h2d[c], ctx->h2d_stream));
+    }
+    const uint32_t pro = cfg->write_prologue ? (uint32_t)kStreamPrologueBytes : 0u;
+    std::vector<uint64_t> dev_base(nchunks + 1, 0);
+    for (int c = 0; c < nchunks; c++) {
+        const int s0 = cs[c], s1 = cs[c + 1];
+        const int f0 = s0 < ns ? (int)ctx->h_stream_first[s0] : nf, f1 = s1 < ns ? (int)ctx->h_stream_first[s1] : nf;
+        const int cnf = f1 - f0, cns = s1 - s0;
+        dev_base[c + 1] = dev_base[c] + (((uint64_t)cnf * ctx->scratch_stride + (uint64_t)cns * kStreamPrologueBytes + 255) / 256) * 256;
+        CKJ(cudaStreamWaitEvent(st, ctx->ev_h2d[c], 0));
+        if (cnf > 0) {
+            launch_analyze(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf,
+                           (SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals, (uint8_t*)ctx->d_ca.p + f0, nullptr, (EncStats*)ctx->d_stats.p,
+                           analyze_smem_bytes(P), st);
+            launch_pack(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, P, cnf, (const SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals,
+                        (const uint8_t*)ctx->d_ca.p + f0, (uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride,
+                        (uint32_t*)ctx->d_flen.p + f0, st);
+            launch_layout((const uint32_t*)ctx->d_flen.p + f0, (const FrameDesc*)ctx->d_frames.p + f0, cnf, pro, dev_base[c],
+                          (uint64_t*)ctx->d_foff.p + f0, (uint64_t*)ctx->d_totals.p + c, st);
+            launch_compact((const uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride, (const uint32_t*)ctx->d_flen.p + f0,
+                           (const uint64_t*)ctx->d_foff.p + f0, (uint8_t*)ctx->d_arena.p, cnf, st);
+            launch_finalize((const uint32_t*)ctx->d_flen.p, (const uint64_t*)ctx->d_foff.p, (const uint32_t*)ctx->d_sfirst.p + s0,
+                            (const uint32_t*)ctx->d_snframes.p + s0, (const uint64_t*)ctx->d_ssamples.p + s0, nullptr, cns, P, pro ? 1u : 0u,
+                            (uint8_t*)ctx->d_arena.p, (StreamInfoOut*)ctx->d_sinfo.p + s0, st);
+            ctx->launches += 5;
+        } else {
+            CKJ(cudaMemsetAsync((uint64_t*)ctx->d_totals.p + c, 0, 8, st));
+        }
+        CKJ(cudaMemcpyAsync(ctx->h_totals + c, (uint64_t*)ctx->d_totals.p + c, 8, cudaMemcpyDeviceToHost, st));
+        CKJ(cudaEventRecord(ctx->ev_done[c], st));
+    }
+    if (dev_base[nchunks] > ctx->d_arena.cap) return bail(fail(ctx, FLACB200_ERR_CUDA, "device arena too small"));
+
+    // ---- drain: as each chunk finishes, copy exactly its bytes to the next free spot of the host arena ----
+    std::vector<uint64_t> host_base(nchunks + 1, 0);
+    for (int c = 0; c < nchunks; c++) {
+        CKJ(cudaEventSynchronize(ctx->ev_done[c]));
+        const uint64_t bytes = ctx->h_totals[c];
+        if (host_base[c] + bytes > arena_cap) return bail(fail(ctx, FLACB200_ERR_ARG, "arena too small"));
+        if (bytes) CKJ(cudaMemcpyAsync(arena + host_base[c], (const uint8_t*)ctx->d_arena.p + dev_base[c], bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        host_base[c + 1] = host_base[c] + bytes;
+    }
+    std::vector<uint64_t> tmp_off;
+    uint64_t* foff_host = frame_off;
+    if (!foff_host) { tmp_off.resize(nf); foff_host = tmp_off.data(); }
+    CKJ(cudaMemcpyAsync(foff_host, ctx->d_foff.p, sizeof(uint64_t) * nf, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (frame_len) CKJ(cudaMemcpyAsync(frame_len, ctx->d_flen.p, sizeof(uint32_t) * nf, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    std::vector<flacb200_stream_info> tmp_info;
+    flacb200_stream_info* info_host = streams;
+    if (!info_host) { tmp_info.resize(ns); info_host = tmp_info.data(); }
+    CKJ(cudaMemcpyAsync(info_host, ctx->d_sinfo.p, sizeof(StreamInfoOut) * ns, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CKJ(cudaStreamSynchronize(ctx->d2h_stream));
+    CKJ(cudaGetLastError());
+#undef CKJ
+    join_workers();
+    // device-arena offsets -> host-arena offsets; MD5 digests into STREAMINFO
+    for (int c = 0; c < nchunks; c++) {
+        const int s0 = cs[c], s1 = cs[c + 1];
+        const int f0 = s0 < ns ? (int)ctx->h_stream_first[s0] : nf, f1 = s1 < ns ? (int)ctx->h_stream_first[s1] : nf;
+        for (int f = f0; f < f1; f++) foff_host[f] = foff_host[f] - dev_base[c] + host_base[c];
+        for (int s = s0; s < s1; s++) {
+            flacb200_stream_info& si = info_host[s];
+            if (si.n_frames) si.byte_off = si.byte_off - dev_base[c] + host_base[c];
+            if (want_md5) {
+                memcpy(si.md5, &digests[(size_t)s * 16], 16);
+                if (pro && si.n_frames) memcpy(arena + si.byte_off + 26, si.md5, 16);
+            }
+        }
+    }
+    ctx->e2e_last_bytes = host_base[nchunks];
+    if (total_bytes) *total_bytes = host_base[nchunks];
     return 0;
 }

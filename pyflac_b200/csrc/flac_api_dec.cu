@@ -1,0 +1,347 @@
+// flac_api_dec.cu -- drop-in FLAC__stream_decoder_* layer (include/flacb200_flac_api.h) on top of the batch decoder.
+//
+// libFLAC pulls bytes through the read callback and parses sequentially; here the handle pulls a large slice,
+// parses the metadata blocks on the host (a few dozen bytes), hands every complete frame it holds to the GPU in
+// ONE flacb200_decode_batch call (headerless "raw" mode with the STREAMINFO parameters), and then fires the
+// write callback once per frame, in order, with the same payload pyFLAC reads (decoder.py:482-527:
+// frame.header.{blocksize,sample_rate,channels,bits_per_sample} and one int32 plane per channel).  Bytes of a
+// frame that is still incomplete stay buffered until more input arrives.  Errors surface through the error
+// callback with libFLAC's status values (LOST_SYNC, BAD_HEADER, FRAME_CRC_MISMATCH, UNPARSEABLE_STREAM).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <deque>
+#include <mutex>
+#include <vector>
+
+#include "../../include/flacb200.h"
+#include "../../include/flacb200_flac_api.h"
+
+extern "C" {
+// values read from the reference binary (pyflac/decoder.py:46,60,546)
+const char *const FLAC__StreamDecoderStateString[] = {
+    "FLAC__STREAM_DECODER_SEARCH_FOR_METADATA", "FLAC__STREAM_DECODER_READ_METADATA", "FLAC__STREAM_DECODER_SEARCH_FOR_FRAME_SYNC",
+    "FLAC__STREAM_DECODER_READ_FRAME", "FLAC__STREAM_DECODER_END_OF_STREAM", "FLAC__STREAM_DECODER_OGG_ERROR", "FLAC__STREAM_DECODER_SEEK_ERROR",
+    "FLAC__STREAM_DECODER_ABORTED", "FLAC__STREAM_DECODER_MEMORY_ALLOCATION_ERROR", "FLAC__STREAM_DECODER_UNINITIALIZED"};
+const char *const FLAC__StreamDecoderInitStatusString[] = {
+    "FLAC__STREAM_DECODER_INIT_STATUS_OK", "FLAC__STREAM_DECODER_INIT_STATUS_UNSUPPORTED_CONTAINER", "FLAC__STREAM_DECODER_INIT_STATUS_INVALID_CALLBACKS",
+    "FLAC__STREAM_DECODER_INIT_STATUS_MEMORY_ALLOCATION_ERROR", "FLAC__STREAM_DECODER_INIT_STATUS_ERROR_OPENING_FILE",
+    "FLAC__STREAM_DECODER_INIT_STATUS_ALREADY_INITIALIZED"};
+const char *const FLAC__StreamDecoderErrorStatusString[] = {
+    "FLAC__STREAM_DECODER_ERROR_STATUS_LOST_SYNC", "FLAC__STREAM_DECODER_ERROR_STATUS_BAD_HEADER", "FLAC__STREAM_DECODER_ERROR_STATUS_FRAME_CRC_MISMATCH",
+    "FLAC__STREAM_DECODER_ERROR_STATUS_UNPARSEABLE_STREAM", "FLAC__STREAM_DECODER_ERROR_STATUS_BAD_METADATA"};
+}
+
+namespace {
+
+enum { DS_SEARCH_FOR_METADATA = 0, DS_READ_METADATA = 1, DS_SEARCH_FOR_FRAME_SYNC = 2, DS_READ_FRAME = 3, DS_END_OF_STREAM = 4,
+       DS_ABORTED = 7, DS_MEMORY_ALLOCATION_ERROR = 8, DS_UNINITIALIZED = 9 };
+enum { DI_OK = 0, DI_UNSUPPORTED_CONTAINER = 1, DI_INVALID_CALLBACKS = 2, DI_MEMORY_ALLOCATION_ERROR = 3, DI_ERROR_OPENING_FILE = 4, DI_ALREADY_INITIALIZED = 5 };
+enum { ERR_LOST_SYNC = 0, ERR_BAD_HEADER = 1, ERR_FRAME_CRC_MISMATCH = 2, ERR_UNPARSEABLE_STREAM = 3, ERR_BAD_METADATA = 4 };
+
+std::mutex g_dec_mu;
+flacb200_ctx* g_dec_ctx = nullptr;
+int g_dec_rc = -1;
+flacb200_ctx* dec_ctx() {
+    if (g_dec_rc == -1) g_dec_rc = flacb200_create(&g_dec_ctx, 0);
+    return g_dec_rc == 0 ? g_dec_ctx : nullptr;
+}
+
+struct PendingFrame { uint32_t blocksize; std::vector<int32_t> planar; };   // [channel][sample]
+
+struct DecImpl {
+    int state = DS_UNINITIALIZED;
+    FLAC__bool md5_checking = 0;
+    FLAC__StreamDecoderReadCallback read_cb = nullptr; FLAC__StreamDecoderWriteCallback write_cb = nullptr;
+    FLAC__StreamDecoderErrorCallback error_cb = nullptr; FLAC__StreamDecoderMetadataCallback meta_cb = nullptr;
+    void* client = nullptr;
+    FILE* file = nullptr;
+    std::vector<uint8_t> in;              // bytes not yet consumed
+    bool eof = false, metadata_done = false;
+    uint32_t sample_rate = 0, channels = 0, bps = 0, blocksize = 0;
+    uint64_t total_samples = 0, frame_index = 0, bytes_consumed = 0;
+    std::deque<PendingFrame> ready;       // decoded frames not yet delivered
+    FLAC__Frame frame;                    // callback payload (header filled per frame)
+};
+struct DHandle { FLAC__StreamDecoder pub; DecImpl impl; };
+inline DecImpl* D(const FLAC__StreamDecoder* d) { return d ? (DecImpl*)d->private_ : nullptr; }
+
+void report(FLAC__StreamDecoder* d, int status) { DecImpl* m = D(d); if (m->error_cb) m->error_cb(d, status, m->client); }
+
+// pull one slice of input; returns false on abort
+bool pull(FLAC__StreamDecoder* d, size_t want) {
+    DecImpl* m = D(d);
+    if (m->eof) return true;
+    const size_t old = m->in.size();
+    m->in.resize(old + want);
+    size_t got = want; int st;
+    if (m->file) { got = fread(m->in.data() + old, 1, want, m->file); st = got == 0 ? 1 : 0; }
+    else st = m->read_cb(d, m->in.data() + old, &got, m->client);
+    if (st == 2) { m->in.resize(old); m->state = DS_ABORTED; return false; }
+    if (st == 1) { m->eof = true; if (got > want) got = 0; }
+    m->in.resize(old + (st == 1 && !m->file ? got : got));
+    if (got == 0 && st != 1 && !m->file) { /* spurious empty read: treat like libFLAC (abort) */ m->state = DS_ABORTED; return false; }
+    return true;
+}
+
+// parse "fLaC" + metadata blocks once enough bytes are buffered. returns 1 done, 0 need more, -1 fatal
+int parse_metadata(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    if (m->in.size() < 4) return m->eof ? -1 : 0;
+    if (memcmp(m->in.data(), "fLaC", 4) != 0) {
+        // libFLAC would hunt for a frame sync in arbitrary data and report LOST_SYNC; without STREAMINFO there is nothing
+        // this build can decode (pyFLAC's tests expect the error, tests/test_decoder.py:59-66)
+        report(d, ERR_LOST_SYNC);
+        return -1;
+    }
+    size_t pos = 4; bool last = false, have_si = false;
+    while (!last) {
+        if (pos + 4 > m->in.size()) return m->eof ? -1 : 0;
+        const uint8_t* p = m->in.data() + pos;
+        const uint32_t type = p[0] & 0x7f, len = (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+        last = (p[0] >> 7) != 0;
+        if (pos + 4 + len > m->in.size()) return m->eof ? -1 : 0;
+        if (type == 0 && len >= 34) {
+            const uint8_t* q = p + 4;
+            m->blocksize = (uint32_t)q[2] << 8 | q[3];
+            m->sample_rate = (uint32_t)q[10] << 12 | (uint32_t)q[11] << 4 | (q[12] >> 4);
+            m->channels = ((q[12] >> 1) & 7) + 1;
+            m->bps = (((uint32_t)q[12] & 1) << 4 | (q[13] >> 4)) + 1;
+            m->total_samples = ((uint64_t)(q[13] & 0xF) << 32) | (uint64_t)q[14] << 24 | (uint64_t)q[15] << 16 | (uint64_t)q[16] << 8 | q[17];
+            have_si = true;
+            if (m->meta_cb) {
+                FLAC__StreamMetadata md; memset(&md, 0, sizeof md);
+                md.type = 0; md.is_last = last; md.length = len;
+                md.data.stream_info.min_blocksize = (uint32_t)q[0] << 8 | q[1]; md.data.stream_info.max_blocksize = m->blocksize;
+                md.data.stream_info.min_framesize = (uint32_t)q[4] << 16 | (uint32_t)q[5] << 8 | q[6];
+                md.data.stream_info.max_framesize = (uint32_t)q[7] << 16 | (uint32_t)q[8] << 8 | q[9];
+                md.data.stream_info.sample_rate = m->sample_rate; md.data.stream_info.channels = m->channels;
+                md.data.stream_info.bits_per_sample = m->bps; md.data.stream_info.total_samples = m->total_samples;
+                memcpy(md.data.stream_info.md5sum, q + 18, 16);
+                m->meta_cb(d, &md, m->client);
+            }
+        }
+        pos += 4 + len;
+    }
+    if (!have_si) { report(d, ERR_BAD_METADATA); return -1; }
+    m->in.erase(m->in.begin(), m->in.begin() + (long)pos);
+    m->bytes_consumed += pos;
+    m->metadata_done = true;
+    m->state = DS_SEARCH_FOR_FRAME_SYNC;
+    return 1;
+}
+
+// decode every complete frame currently buffered (one GPU batch); returns false on fatal error
+bool decode_buffered(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    if (m->in.empty()) return true;
+    std::lock_guard<std::mutex> lk(g_dec_mu);
+    flacb200_ctx* ctx = dec_ctx();
+    if (!ctx) { m->state = DS_MEMORY_ALLOCATION_ERROR; return false; }
+    flacb200_dec_raw_params raw{m->sample_rate, m->channels, m->bps};
+    const uint64_t off = 0, len = m->in.size();
+    if (flacb200_decode_batch(ctx, m->in.data(), 0, len, 1, &off, &len, 4, &raw) != 0) { report(d, ERR_UNPARSEABLE_STREAM); m->state = DS_ABORTED; return false; }
+    flacb200_dec_result r;
+    if (flacb200_decode_result(ctx, &r) != 0) { m->state = DS_ABORTED; return false; }
+    std::vector<int32_t> pcm((size_t)r.total_elems + 1);
+    std::vector<uint32_t> fs(r.n_frames + 1);
+    flacb200_dec_stream_info si;
+    if (flacb200_decode_fetch(ctx, pcm.data(), pcm.size() * 4, &si, fs.data(), r.n_frames) != 0) { m->state = DS_ABORTED; return false; }
+    // queue frames (planar int32 per channel, as libFLAC hands them to the write callback)
+    size_t base = 0;
+    const uint32_t ch = si.channels ? si.channels : m->channels;
+    for (uint32_t f = 0; f < si.n_frames; f++) {
+        PendingFrame pf; pf.blocksize = fs[f]; pf.planar.resize((size_t)fs[f] * ch);
+        for (uint32_t i = 0; i < fs[f]; i++) for (uint32_t c = 0; c < ch; c++) pf.planar[(size_t)c * fs[f] + i] = pcm[base + (size_t)i * ch + c];
+        base += (size_t)fs[f] * ch;
+        m->ready.push_back(std::move(pf));
+    }
+    if (si.n_frames) { m->channels = ch; if (si.sample_rate) m->sample_rate = si.sample_rate; if (si.bits_per_sample) m->bps = si.bits_per_sample; }
+    const size_t consumed = (size_t)si.consumed;
+    // what stopped the chain?
+    if (si.status == 7) report(d, ERR_FRAME_CRC_MISMATCH);
+    else if (si.status == 4) report(d, ERR_BAD_HEADER);
+    else if (si.status == 8) report(d, ERR_UNPARSEABLE_STREAM);
+    else if (si.status == 6 || si.status == 5) {
+        // no frame where one should start / frame cut short: fine while more input may come, LOST_SYNC at end of stream
+        if (m->eof && consumed < m->in.size()) report(d, ERR_LOST_SYNC);
+    }
+    size_t drop = consumed;
+    if (si.status == 7 || si.status == 4 || si.status == 8) drop = m->in.size();      // unrecoverable here: discard the slice
+    else if (si.status == 6 && !m->eof && consumed < m->in.size()) {
+        // garbage where a frame should start: skip to the last few bytes (a sync code may straddle the slice end)
+        if (si.n_frames == 0 && m->in.size() > 65536) { report(d, ERR_LOST_SYNC); drop = m->in.size() - 16; }
+    }
+    if (m->eof && (si.status == 6 || si.status == 5)) drop = m->in.size();
+    m->in.erase(m->in.begin(), m->in.begin() + (long)drop);
+    m->bytes_consumed += drop;
+    return true;
+}
+
+// deliver one queued frame through the write callback; returns false if the client aborted
+bool deliver_one(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    PendingFrame& pf = m->ready.front();
+    const int32_t* planes[8] = {nullptr};
+    for (uint32_t c = 0; c < m->channels && c < 8; c++) planes[c] = pf.planar.data() + (size_t)c * pf.blocksize;
+    memset(&m->frame.header, 0, sizeof m->frame.header);
+    m->frame.header.blocksize = pf.blocksize; m->frame.header.sample_rate = m->sample_rate; m->frame.header.channels = m->channels;
+    m->frame.header.channel_assignment = 0; m->frame.header.bits_per_sample = m->bps; m->frame.header.number_type = 0;
+    m->frame.header.number.frame_number = (uint32_t)m->frame_index;
+    m->state = DS_READ_FRAME;
+    const int st = m->write_cb(d, &m->frame, planes, m->client);
+    m->frame_index++;
+    m->ready.pop_front();
+    if (st != 0) { m->state = DS_ABORTED; return false; }
+    m->state = DS_SEARCH_FOR_FRAME_SYNC;
+    return true;
+}
+
+// make progress: returns 1 if something was delivered/parsed, 0 at end of stream, -1 on abort/fatal
+int step(FLAC__StreamDecoder* d, bool until_end) {
+    DecImpl* m = D(d);
+    const size_t kSlice = until_end ? (1u << 20) : (1u << 16);
+    for (;;) {
+        if (m->state == DS_ABORTED || m->state == DS_END_OF_STREAM) return m->state == DS_ABORTED ? -1 : 0;
+        if (!m->ready.empty()) return deliver_one(d) ? 1 : -1;
+        if (!m->metadata_done) {
+            const int r = parse_metadata(d);
+            if (r == 1) return 1;
+            if (r < 0) { m->state = m->eof ? DS_END_OF_STREAM : DS_ABORTED; return m->eof ? 0 : -1; }
+            if (!pull(d, kSlice)) return -1;
+            continue;
+        }
+        // need more frames: decode what is buffered once a slice (or the tail) is available
+        if (!m->eof && m->in.size() < 16) { if (!pull(d, kSlice)) return -1; continue; }
+        const size_t before = m->in.size();
+        if (!decode_buffered(d)) return -1;
+        if (!m->ready.empty()) continue;
+        if (m->eof && (m->in.empty() || m->in.size() == before)) { m->state = DS_END_OF_STREAM; return 0; }
+        if (!m->eof && m->in.size() == before) { if (!pull(d, kSlice)) return -1; }   // frame larger than what is buffered
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+FLAC__StreamDecoder* FLAC__stream_decoder_new(void) {
+    DHandle* h = new DHandle();
+    h->pub.protected_ = nullptr; h->pub.private_ = &h->impl;
+    return &h->pub;
+}
+void FLAC__stream_decoder_delete(FLAC__StreamDecoder* d) {
+    if (!d) return;
+    FLAC__stream_decoder_finish(d);
+    delete reinterpret_cast<DHandle*>(d);
+}
+FLAC__bool FLAC__stream_decoder_set_md5_checking(FLAC__StreamDecoder* d, FLAC__bool v) { DecImpl* m = D(d); if (m->state != DS_UNINITIALIZED) return 0; m->md5_checking = v; return 1; }
+FLAC__bool FLAC__stream_decoder_set_metadata_respond(FLAC__StreamDecoder* d, int) { return D(d)->state == DS_UNINITIALIZED; }
+FLAC__bool FLAC__stream_decoder_set_metadata_respond_application(FLAC__StreamDecoder* d, const FLAC__byte*) { return D(d)->state == DS_UNINITIALIZED; }
+FLAC__bool FLAC__stream_decoder_set_metadata_respond_all(FLAC__StreamDecoder* d) { return D(d)->state == DS_UNINITIALIZED; }
+FLAC__bool FLAC__stream_decoder_set_metadata_ignore(FLAC__StreamDecoder* d, int) { return D(d)->state == DS_UNINITIALIZED; }
+FLAC__bool FLAC__stream_decoder_set_metadata_ignore_application(FLAC__StreamDecoder* d, const FLAC__byte*) { return D(d)->state == DS_UNINITIALIZED; }
+FLAC__bool FLAC__stream_decoder_set_metadata_ignore_all(FLAC__StreamDecoder* d) { return D(d)->state == DS_UNINITIALIZED; }
+int FLAC__stream_decoder_get_state(const FLAC__StreamDecoder* d) { return D(d)->state; }
+const char* FLAC__stream_decoder_get_resolved_state_string(const FLAC__StreamDecoder* d) { return FLAC__StreamDecoderStateString[D(d)->state]; }
+FLAC__bool FLAC__stream_decoder_get_md5_checking(const FLAC__StreamDecoder* d) { return D(d)->md5_checking; }
+FLAC__uint64 FLAC__stream_decoder_get_total_samples(const FLAC__StreamDecoder* d) { return D(d)->total_samples; }
+uint32_t FLAC__stream_decoder_get_channels(const FLAC__StreamDecoder* d) { return D(d)->channels; }
+int FLAC__stream_decoder_get_channel_assignment(const FLAC__StreamDecoder*) { return 0; }
+uint32_t FLAC__stream_decoder_get_bits_per_sample(const FLAC__StreamDecoder* d) { return D(d)->bps; }
+uint32_t FLAC__stream_decoder_get_sample_rate(const FLAC__StreamDecoder* d) { return D(d)->sample_rate; }
+uint32_t FLAC__stream_decoder_get_blocksize(const FLAC__StreamDecoder* d) { return D(d)->blocksize; }
+FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder* d, FLAC__uint64* p) { if (!p) return 0; *p = D(d)->bytes_consumed; return 1; }
+
+static int init_common(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    m->in.clear(); m->eof = false; m->metadata_done = false; m->ready.clear(); m->frame_index = 0; m->bytes_consumed = 0;
+    m->sample_rate = m->channels = m->bps = m->blocksize = 0; m->total_samples = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_dec_mu);
+        if (!dec_ctx()) { m->state = DS_MEMORY_ALLOCATION_ERROR; return DI_MEMORY_ALLOCATION_ERROR; }     // no CUDA device: fail loudly, no CPU fallback
+    }
+    m->state = DS_SEARCH_FOR_METADATA;
+    return DI_OK;
+}
+int FLAC__stream_decoder_init_stream(FLAC__StreamDecoder* d, FLAC__StreamDecoderReadCallback r, FLAC__StreamDecoderSeekCallback s, FLAC__StreamDecoderTellCallback t,
+                                     FLAC__StreamDecoderLengthCallback l, FLAC__StreamDecoderEofCallback e, FLAC__StreamDecoderWriteCallback w,
+                                     FLAC__StreamDecoderMetadataCallback mcb, FLAC__StreamDecoderErrorCallback ecb, void* client) {
+    DecImpl* m = D(d);
+    if (m->state != DS_UNINITIALIZED) return DI_ALREADY_INITIALIZED;
+    if (!r || !w || !ecb || (s && (!t || !l || !e))) return DI_INVALID_CALLBACKS;
+    m->read_cb = r; m->write_cb = w; m->error_cb = ecb; m->meta_cb = mcb; m->client = client; m->file = nullptr;
+    return init_common(d);
+}
+int FLAC__stream_decoder_init_FILE(FLAC__StreamDecoder* d, FILE* f, FLAC__StreamDecoderWriteCallback w, FLAC__StreamDecoderMetadataCallback mcb,
+                                   FLAC__StreamDecoderErrorCallback ecb, void* client) {
+    DecImpl* m = D(d);
+    if (m->state != DS_UNINITIALIZED) return DI_ALREADY_INITIALIZED;
+    if (!f || !w || !ecb) return DI_INVALID_CALLBACKS;
+    m->read_cb = nullptr; m->write_cb = w; m->error_cb = ecb; m->meta_cb = mcb; m->client = client; m->file = f;
+    return init_common(d);
+}
+int FLAC__stream_decoder_init_file(FLAC__StreamDecoder* d, const char* filename, FLAC__StreamDecoderWriteCallback w, FLAC__StreamDecoderMetadataCallback mcb,
+                                   FLAC__StreamDecoderErrorCallback ecb, void* client) {
+    DecImpl* m = D(d);
+    if (m->state != DS_UNINITIALIZED) return DI_ALREADY_INITIALIZED;
+    if (!w || !ecb) return DI_INVALID_CALLBACKS;
+    FILE* f = filename ? fopen(filename, "rb") : stdin;
+    if (!f) return DI_ERROR_OPENING_FILE;                     // tests/test_decoder.py:107-111
+    const int rc = FLAC__stream_decoder_init_FILE(d, f, w, mcb, ecb, client);
+    if (rc != DI_OK && f != stdin) fclose(f);
+    return rc;
+}
+int FLAC__stream_decoder_init_ogg_stream(FLAC__StreamDecoder*, FLAC__StreamDecoderReadCallback, FLAC__StreamDecoderSeekCallback, FLAC__StreamDecoderTellCallback,
+                                         FLAC__StreamDecoderLengthCallback, FLAC__StreamDecoderEofCallback, FLAC__StreamDecoderWriteCallback,
+                                         FLAC__StreamDecoderMetadataCallback, FLAC__StreamDecoderErrorCallback, void*) { return DI_UNSUPPORTED_CONTAINER; }
+int FLAC__stream_decoder_init_ogg_FILE(FLAC__StreamDecoder*, FILE*, FLAC__StreamDecoderWriteCallback, FLAC__StreamDecoderMetadataCallback, FLAC__StreamDecoderErrorCallback, void*) { return DI_UNSUPPORTED_CONTAINER; }
+int FLAC__stream_decoder_init_ogg_file(FLAC__StreamDecoder*, const char*, FLAC__StreamDecoderWriteCallback, FLAC__StreamDecoderMetadataCallback, FLAC__StreamDecoderErrorCallback, void*) { return DI_UNSUPPORTED_CONTAINER; }
+
+FLAC__bool FLAC__stream_decoder_finish(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    if (m->state == DS_UNINITIALIZED) return 1;
+    if (m->file && m->file != stdin) fclose(m->file);
+    m->file = nullptr; m->in.clear(); m->ready.clear();
+    m->read_cb = nullptr; m->write_cb = nullptr; m->error_cb = nullptr; m->meta_cb = nullptr; m->client = nullptr;   // stream_decoder.h: finish resets the callbacks too
+    m->md5_checking = 0;
+    m->state = DS_UNINITIALIZED;
+    return 1;
+}
+FLAC__bool FLAC__stream_decoder_flush(FLAC__StreamDecoder* d) { DecImpl* m = D(d); if (m->state == DS_UNINITIALIZED) return 0; m->in.clear(); m->ready.clear(); m->state = DS_SEARCH_FOR_FRAME_SYNC; return 1; }
+FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) { DecImpl* m = D(d); if (m->state == DS_UNINITIALIZED) return 0; m->in.clear(); m->ready.clear(); m->metadata_done = false; m->eof = false; m->state = DS_SEARCH_FOR_METADATA; return 1; }
+
+FLAC__bool FLAC__stream_decoder_process_single(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED) return 0;
+    if (m->state == DS_END_OF_STREAM) return 1;
+    return step(d, false) >= 0;
+}
+FLAC__bool FLAC__stream_decoder_process_until_end_of_metadata(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED) return 0;
+    while (!m->metadata_done && m->state != DS_END_OF_STREAM) if (step(d, false) < 0) return 0;
+    return 1;
+}
+FLAC__bool FLAC__stream_decoder_process_until_end_of_stream(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED) return 0;
+    for (;;) {
+        const int r = step(d, true);
+        if (r < 0) return 0;
+        if (r == 0) return 1;
+    }
+}
+FLAC__bool FLAC__stream_decoder_skip_single_frame(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED) return 0;
+    FLAC__StreamDecoderWriteCallback keep = m->write_cb;
+    m->write_cb = [](const FLAC__StreamDecoder*, const FLAC__Frame*, const FLAC__int32* const*, void*) -> int { return 0; };
+    const int r = step(d, false);
+    m->write_cb = keep;
+    return r >= 0;
+}
+FLAC__bool FLAC__stream_decoder_seek_absolute(FLAC__StreamDecoder*, FLAC__uint64) { return 0; }   // seeking is out of scope
+
+}  // extern "C"

@@ -231,6 +231,8 @@ int init_common(FLAC__StreamEncoder* e) {
     memcpy(b + 8, FLAC__VENDOR_STRING, vl);
     memset(b + 8 + vl, 0, 4);
     if (!deliver(e, b, 4 + len, 0, 0)) return INIT_ENCODER_ERROR;
+    // up: init_stream_internal_ asks for the position once more after the metadata (audio_offset); observed on the reference binary
+    if (!m->file && m->tell_cb) { FLAC__uint64 posn = 0; if (m->tell_cb(e, &posn, m->client) == 1) { m->state = ST_CLIENT_ERROR; return INIT_ENCODER_ERROR; } }
     return INIT_OK;
 }
 

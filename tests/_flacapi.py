@@ -1,0 +1,178 @@
+"""Drive the libFLAC stream-encoder/decoder C API of ANY shared library through ctypes and log what the callbacks see.
+
+Used by the tests to run the same session against (a) libflacb200.so's drop-in layer and (b) the reference's
+libFLAC 1.4.3 (oracle/_ref) and compare the callback streams byte for byte -- the contract pyFLAC's cffi
+trampolines rely on (pyflac/encoder.py:429-494, pyflac/decoder.py:394-549).
+"""
+import ctypes as C
+
+import numpy as np
+
+WRITE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ubyte), C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p)
+SEEK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
+TELL_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p)
+META_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)
+
+DEC_READ_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_size_t), C.c_void_p)
+DEC_WRITE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(C.c_int32)), C.c_void_p)
+DEC_ERROR_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p)
+
+
+class StreamInfoView(C.Structure):
+    _fields_ = [("type", C.c_int), ("is_last", C.c_int), ("length", C.c_uint32), ("pad", C.c_uint32),
+                ("min_blocksize", C.c_uint32), ("max_blocksize", C.c_uint32), ("min_framesize", C.c_uint32),
+                ("max_framesize", C.c_uint32), ("sample_rate", C.c_uint32), ("channels", C.c_uint32),
+                ("bits_per_sample", C.c_uint32), ("pad2", C.c_uint32), ("total_samples", C.c_uint64), ("md5sum", C.c_ubyte * 16)]
+
+
+class FrameHeaderView(C.Structure):
+    _fields_ = [("blocksize", C.c_uint32), ("sample_rate", C.c_uint32), ("channels", C.c_uint32),
+                ("channel_assignment", C.c_int), ("bits_per_sample", C.c_uint32), ("number_type", C.c_int),
+                ("number", C.c_uint64), ("crc", C.c_uint8)]
+
+
+def _proto(L):
+    L.FLAC__stream_encoder_new.restype = C.c_void_p
+    for n in ["delete", "finish"]:
+        getattr(L, "FLAC__stream_encoder_" + n).argtypes = [C.c_void_p]
+    for n in ["set_verify", "set_channels", "set_bits_per_sample", "set_sample_rate", "set_compression_level", "set_blocksize",
+              "set_streamable_subset", "set_limit_min_bitrate"]:
+        f = getattr(L, "FLAC__stream_encoder_" + n)
+        f.argtypes = [C.c_void_p, C.c_uint32]
+        f.restype = C.c_int
+    for n in ["get_state", "get_verify", "get_channels", "get_bits_per_sample", "get_sample_rate", "get_blocksize",
+              "get_streamable_subset", "get_limit_min_bitrate"]:
+        f = getattr(L, "FLAC__stream_encoder_" + n)
+        f.argtypes = [C.c_void_p]
+        f.restype = C.c_uint32
+    L.FLAC__stream_encoder_init_stream.argtypes = [C.c_void_p, WRITE_CB, SEEK_CB, TELL_CB, META_CB, C.c_void_p]
+    L.FLAC__stream_encoder_init_stream.restype = C.c_int
+    L.FLAC__stream_encoder_init_file.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
+    L.FLAC__stream_encoder_init_file.restype = C.c_int
+    L.FLAC__stream_encoder_process_interleaved.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.FLAC__stream_encoder_process_interleaved.restype = C.c_int
+    L.FLAC__stream_encoder_finish.restype = C.c_int
+    return L
+
+
+def encode_session(L, pcm, sample_rate, bps, level=5, blocksize=0, chunks=None, seekable=True, metadata=True,
+                   verify=False, streamable_subset=True, init_only=False, no_tell=False):
+    """Run one StreamEncoder session; returns dict(init_status, log=[(event, ...)], file=bytes image, ok=bool).
+    log events: ('write', bytes, samples, frame) | ('seek', off) | ('tell', off) | ('meta', dict)."""
+    _proto(L)
+    x = np.ascontiguousarray(pcm)
+    if x.ndim == 1:
+        x = x[:, None]
+    n, ch = x.shape
+    x32 = np.ascontiguousarray(x.astype(np.int32))
+    log, image, pos = [], bytearray(), [0]
+
+    def w(enc, buf, nbytes, samples, frame, cd):
+        b = bytes(buf[:nbytes])
+        log.append(("write", b, samples, frame))
+        image[pos[0]:pos[0] + nbytes] = b
+        pos[0] += nbytes
+        return 0
+
+    def s(enc, off, cd):
+        log.append(("seek", off))
+        pos[0] = off
+        return 0
+
+    def t(enc, poff, cd):
+        poff[0] = pos[0]
+        log.append(("tell", pos[0]))
+        return 0
+
+    def m(enc, md, cd):
+        v = C.cast(md, C.POINTER(StreamInfoView)).contents
+        log.append(("meta", dict(type=v.type, length=v.length, min_blocksize=v.min_blocksize, max_blocksize=v.max_blocksize,
+                                 min_framesize=v.min_framesize, max_framesize=v.max_framesize, sample_rate=v.sample_rate,
+                                 channels=v.channels, bits_per_sample=v.bits_per_sample, total_samples=v.total_samples,
+                                 md5=bytes(v.md5sum))))
+
+    wcb, scb, tcb, mcb = WRITE_CB(w), SEEK_CB(s), TELL_CB(t), META_CB(m)
+    e = L.FLAC__stream_encoder_new()
+    L.FLAC__stream_encoder_set_verify(e, int(verify))
+    L.FLAC__stream_encoder_set_channels(e, ch)
+    L.FLAC__stream_encoder_set_bits_per_sample(e, bps)
+    L.FLAC__stream_encoder_set_sample_rate(e, sample_rate)
+    L.FLAC__stream_encoder_set_compression_level(e, level)
+    L.FLAC__stream_encoder_set_blocksize(e, blocksize)
+    L.FLAC__stream_encoder_set_streamable_subset(e, int(streamable_subset))
+    null = lambda T: C.cast(None, T)  # noqa: E731
+    st = L.FLAC__stream_encoder_init_stream(e, wcb, scb if seekable else null(SEEK_CB),
+                                            null(TELL_CB) if (not seekable or no_tell) else tcb,
+                                            mcb if metadata else null(META_CB), None)
+    res = dict(init_status=st, log=log, ok=True)
+    if st == 0 and not init_only:
+        res["state_after_init"] = L.FLAC__stream_encoder_get_state(e)
+        if chunks is None:
+            chunks = [n]
+        done = 0
+        for cnum in chunks:
+            cnum = min(cnum, n - done)
+            if cnum <= 0:
+                break
+            seg = x32[done:done + cnum]
+            if not L.FLAC__stream_encoder_process_interleaved(e, seg.ctypes.data, cnum):
+                res["ok"] = False
+                break
+            done += cnum
+        res["finish"] = L.FLAC__stream_encoder_finish(e)
+        res["state_after_finish"] = L.FLAC__stream_encoder_get_state(e)
+    L.FLAC__stream_encoder_delete(e)
+    res["file"] = bytes(image)
+    return res
+
+
+def decode_session(L, data, read_chunk=8192):
+    """Run one StreamDecoder session over a .flac byte string; returns dict(pcm=(n,ch) int32, frames=[headers], errors=[...], ok)."""
+    L.FLAC__stream_decoder_new.restype = C.c_void_p
+    L.FLAC__stream_decoder_delete.argtypes = [C.c_void_p]
+    L.FLAC__stream_decoder_finish.argtypes = [C.c_void_p]
+    L.FLAC__stream_decoder_finish.restype = C.c_int
+    L.FLAC__stream_decoder_get_state.argtypes = [C.c_void_p]
+    L.FLAC__stream_decoder_process_until_end_of_stream.argtypes = [C.c_void_p]
+    L.FLAC__stream_decoder_process_until_end_of_stream.restype = C.c_int
+    L.FLAC__stream_decoder_init_stream.argtypes = [C.c_void_p, DEC_READ_CB, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   DEC_WRITE_CB, C.c_void_p, DEC_ERROR_CB, C.c_void_p]
+    L.FLAC__stream_decoder_init_stream.restype = C.c_int
+    pos = [0]
+    blocks, frames, errors = [], [], []
+
+    def r(dec, buf, pbytes, cd):
+        want = min(pbytes[0], read_chunk)
+        k = min(want, len(data) - pos[0])
+        if k == 0:
+            pbytes[0] = 0
+            return 1
+        C.memmove(buf, data[pos[0]:pos[0] + k], k)
+        pos[0] += k
+        pbytes[0] = k
+        return 0
+
+    def w(dec, frame, buffers, cd):
+        h = C.cast(frame, C.POINTER(FrameHeaderView)).contents
+        frames.append(dict(blocksize=h.blocksize, sample_rate=h.sample_rate, channels=h.channels,
+                           bits_per_sample=h.bits_per_sample, channel_assignment=h.channel_assignment))
+        blk = np.empty((h.blocksize, h.channels), np.int32)
+        for c in range(h.channels):
+            blk[:, c] = np.ctypeslib.as_array(buffers[c], shape=(h.blocksize,))
+        blocks.append(blk)
+        return 0
+
+    def e(dec, status, cd):
+        errors.append(status)
+
+    rcb, wcb, ecb = DEC_READ_CB(r), DEC_WRITE_CB(w), DEC_ERROR_CB(e)
+    d = L.FLAC__stream_decoder_new()
+    st = L.FLAC__stream_decoder_init_stream(d, rcb, None, None, None, None, wcb, None, ecb, None)
+    res = dict(init_status=st, frames=frames, errors=errors)
+    if st == 0:
+        res["ok"] = bool(L.FLAC__stream_decoder_process_until_end_of_stream(d))
+        res["state"] = L.FLAC__stream_decoder_get_state(d)
+        L.FLAC__stream_decoder_finish(d)
+    L.FLAC__stream_decoder_delete(d)
+    res["pcm"] = np.concatenate(blocks) if blocks else np.zeros((0, 1), np.int32)
+    return res

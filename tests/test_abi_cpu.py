@@ -27,7 +27,8 @@ def declared_symbols():
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
         syms |= set(re.findall(r"\b((?:flacb200|FLAC__)\w+)\s*\(", txt))
         syms |= set(re.findall(r"extern\s+[\w\s\*]+?\b((?:flacb200|FLAC__)\w+)\s*(?:\[\])?\s*;", txt))
-    return {s for s in syms if not s.endswith("Callback")}
+    types = {"FLAC__bool", "FLAC__byte", "FLAC__int32", "FLAC__uint64"}
+    return {s for s in syms if not s.endswith("Callback") and s not in types}
 
 
 def test_library_exports_every_declared_symbol(lib):

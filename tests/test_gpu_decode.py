@@ -1,0 +1,82 @@
+"""GPU decode parity tests (pytest -m gpu): CUDA decode path through the C ABI vs the oracle / golden PCM."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden
+from pyflac_b200.synth import corpus_signal, CORPUS_KINDS, music_like
+
+pytestmark = pytest.mark.gpu
+CASES = golden_cases()
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from pyflac_b200 import _native as nat
+    return nat.Engine(0)
+
+
+def test_decode_golden_batch(eng):
+    """all golden .flac files (libFLAC 1.4.3 output, levels 0-8, 8..24 bit, 1..6 ch) in one ragged batch -> bit-exact PCM"""
+    from pyflac_b200 import _native as nat
+    xs, blobs = zip(*[load_golden(c) for c in CASES])
+    for grp in ([c for c in range(len(CASES)) if CASES[c]["bps"] <= 16], [c for c in range(len(CASES)) if CASES[c]["bps"] > 16]):
+        out, infos = nat.decode_streams(eng, [blobs[i] for i in grp])
+        for k, i in enumerate(grp):
+            assert infos[k].status == 0, (CASES[i]["name"], nat.DEC_STATUS.get(infos[k].status))
+            assert infos[k].channels == CASES[i]["channels"] and infos[k].bits_per_sample == CASES[i]["bps"]
+            assert infos[k].n_frames == CASES[i]["frames"]
+            x = xs[i].reshape(xs[i].shape[0], -1)
+            assert np.array_equal(out[k].astype(np.int64), x.astype(np.int64)), CASES[i]["name"]
+
+
+def test_decode_corpus_vs_oracle(eng, checkers):
+    from pyflac_b200 import _native as nat
+    for level in (0, 5, 8):
+        blobs, xs = [], []
+        for kind in CORPUS_KINDS:
+            x = corpus_signal(kind, 4096 * 2 + 777, 2, 16, seed=level + 3)
+            blobs.append(checkers.oracle_encode(x, 44100, 16, level, 0))
+            xs.append(x)
+        out, infos = nat.decode_streams(eng, blobs)
+        for kind, x, o, si in zip(CORPUS_KINDS, xs, out, infos):
+            assert si.status == 0, (kind, si.status)
+            assert np.array_equal(o, x), (level, kind)
+
+
+def test_decode_reference_binary_streams(eng, checkers):
+    """streams produced live by the reference binary: escape-free Rice, all channel assignments, wasted bits, 24-bit"""
+    if not checkers.ref_available():
+        pytest.skip("oracle/_ref not present")
+    from pyflac_b200 import _native as nat
+    x24 = [corpus_signal(k, 5000, 1, 24, seed=9) for k in ("music", "wasted", "noise")]
+    out, infos = nat.decode_streams(eng, [checkers.ref_encode(x, 192000, 24, 8, 4096) for x in x24])
+    for x, o, si in zip(x24, out, infos):
+        assert si.status == 0 and si.bits_per_sample == 24 and np.array_equal(o, x)
+    x6 = corpus_signal("lr_uncorr", 9000, 6, 16, seed=2)
+    out, infos = nat.decode_streams(eng, [checkers.ref_encode(x6, 48000, 16, 5, 0)])
+    assert infos[0].status == 0 and np.array_equal(out[0], x6)
+
+
+def test_decode_errors_are_reported(eng, checkers):
+    from pyflac_b200 import _native as nat
+    x = music_like(9000, 2, 48000, 16, seed=1)
+    good = checkers.oracle_encode(x, 48000, 16, 5, 0)
+    bad_crc = bytearray(good); bad_crc[len(good) // 2] ^= 0x10
+    trunc = good[: len(good) - 1000]
+    rng = np.random.default_rng(0)
+    junk = rng.integers(0, 256, 100000).astype(np.uint8).tobytes()
+    out, infos = nat.decode_streams(eng, [good, bytes(bad_crc), trunc, junk])
+    assert infos[0].status == 0 and np.array_equal(out[0], x)
+    assert infos[1].status != 0
+    assert infos[2].status != 0 and infos[2].n_frames >= 1 and np.array_equal(out[2], x[: out[2].shape[0]])
+    assert infos[3].status == 2
+
+
+def test_encode_decode_roundtrip_full_size(eng):
+    """encode -> decode on the GPU for a BASELINE configs[3]-shaped slice (stereo s16 L5 streams), bit-exact PCM"""
+    from pyflac_b200 import _native as nat
+    xs = [music_like(131072, 2, 48000, 16, seed=50 + s) for s in range(64)]
+    blobs, _ = nat.encode_streams(eng, xs, 48000, 16, 5, 4096)
+    out, infos = nat.decode_streams(eng, blobs)
+    for x, o, si in zip(xs, out, infos):
+        assert si.status == 0 and si.n_frames == 32 and np.array_equal(o, x)

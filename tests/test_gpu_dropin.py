@@ -1,0 +1,90 @@
+"""GPU tests of the DROP-IN layer: the FLAC__stream_encoder_* / FLAC__stream_decoder_* symbols of libflacb200.so driven
+exactly like pyFLAC's cffi trampolines drive libFLAC, compared callback-for-callback with the reference binary."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from pyflac_b200.synth import corpus_signal, music_like
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ours():
+    from pyflac_b200 import _native
+    return C.CDLL(_native.LIB_PATH)
+
+
+@pytest.fixture(scope="module")
+def ref(checkers):
+    if not checkers.ref_available():
+        pytest.skip("oracle/_ref not present")
+    return C.CDLL(os.path.join(checkers.ORACLE_DIR, "_ref", "libFLAC-12.1.0.so"))
+
+
+def _norm(log):
+    return [e if e[0] != "meta" else ("meta", tuple(sorted(e[1].items()))) for e in log]
+
+
+@pytest.mark.parametrize("chunks", [None, [4096, 1, 4095, 1, 4195], [1000] * 30])
+def test_stream_encoder_callback_sequence_matches_libflac(ours, ref, chunks):
+    """over-read framing, 3 prologue writes, tell before every write, STREAMINFO rewrite at 26/21/12, metadata callback"""
+    from _flacapi import encode_session
+    x = corpus_signal("music", 4096 * 3 + 100, 2, 16, seed=4)
+    a = encode_session(ours, x, 48000, 16, 5, 0, chunks=chunks)
+    b = encode_session(ref, x, 48000, 16, 5, 0, chunks=chunks)
+    assert a["init_status"] == b["init_status"] == 0
+    assert _norm(a["log"]) == _norm(b["log"])
+    assert a["file"] == b["file"] and a["finish"] == b["finish"] and a["state_after_finish"] == b["state_after_finish"] == 1
+
+
+def test_stream_encoder_without_seek_and_levels(ours, ref):
+    from _flacapi import encode_session
+    x = corpus_signal("mixed", 4096 * 2 + 50, 2, 16, seed=2)
+    for level in (0, 2, 3, 5, 8):
+        a = encode_session(ours, x, 44100, 16, level, 0, seekable=False)
+        b = encode_session(ref, x, 44100, 16, level, 0, seekable=False)
+        assert _norm(a["log"]) == _norm(b["log"]), level
+    x24 = corpus_signal("music", 9000, 1, 24, seed=1)
+    a = encode_session(ours, x24, 192000, 24, 8, 4096)
+    b = encode_session(ref, x24, 192000, 24, 8, 4096)
+    assert a["file"] == b["file"]
+
+
+def test_stream_encoder_init_errors(ours, ref):
+    """reference tests/test_encoder.py:139-164,202-207"""
+    from _flacapi import encode_session
+    x = np.zeros((16, 2), np.int16)
+    for kw in [dict(sample_rate=2000000), dict(blocksize=1000000), dict(blocksize=65535), dict(blocksize=65535, streamable_subset=False)]:
+        args = dict(sample_rate=48000, blocksize=0, streamable_subset=True)
+        args.update(kw)
+        a = encode_session(ours, x, args["sample_rate"], 16, 5, args["blocksize"], streamable_subset=args["streamable_subset"], init_only=True)
+        b = encode_session(ref, x, args["sample_rate"], 16, 5, args["blocksize"], streamable_subset=args["streamable_subset"], init_only=True)
+        assert a["init_status"] == b["init_status"], kw
+    a = encode_session(ours, x, 48000, 16, 5, 0, no_tell=True, init_only=True)
+    b = encode_session(ref, x, 48000, 16, 5, 0, no_tell=True, init_only=True)
+    assert a["init_status"] == b["init_status"] == 3        # INVALID_CALLBACKS
+
+
+def test_stream_decoder_matches_libflac(ours, ref, checkers):
+    from _flacapi import decode_session
+    x = music_like(4096 * 4 + 321, 2, 44100, 16, seed=8)
+    data = checkers.ref_encode(x, 44100, 16, 5, 0)
+    for rc in (8192, 1000, 1 << 20):
+        a = decode_session(ours, data, rc)
+        b = decode_session(ref, data, 8192)
+        assert a["init_status"] == 0 and a["ok"] and not a["errors"]
+        assert np.array_equal(a["pcm"], b["pcm"]) and np.array_equal(a["pcm"], x)
+        assert [f["blocksize"] for f in a["frames"]] == [f["blocksize"] for f in b["frames"]]
+        assert a["frames"][0]["sample_rate"] == 44100 and a["frames"][0]["channels"] == 2 and a["frames"][0]["bits_per_sample"] == 16
+        assert a["state"] == b["state"] == 4                # END_OF_STREAM
+
+
+def test_stream_decoder_garbage_reports_error(ours):
+    """reference tests/test_decoder.py:59-66: random bytes -> error callback fires"""
+    from _flacapi import decode_session
+    junk = np.random.default_rng(1).integers(0, 256, 100000).astype(np.uint8).tobytes()
+    a = decode_session(ours, junk)
+    assert a["errors"] and a["pcm"].shape[0] == 0
