@@ -266,14 +266,56 @@ def main():
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - e0
+    hp = (C.c_double * 6)()
+    L.flacb200_host_path_times(eng._h, hp)
+    host_path_ms = {"enqueued": hp[1], "kernels_done": hp[2], "d2h_done": hp[3], "md5_joined": hp[4], "total": hp[5]}
     if world > 1:
         dist.barrier()
 
+    # ---------------- decode (second half of the metric): the streams just encoded, device-resident and host->host ----------------
+    arena_np = h_arena.numpy()
+    total_flac = int(tot.value)
+    d_flac = torch.from_numpy(arena_np[:total_flac + 16].copy()).to(dev)
+    s_off = np.array([infos[s].byte_off for s in range(N_STREAMS)], np.uint64)
+    s_len = np.array([infos[s].byte_len for s in range(N_STREAMS)], np.uint64)
+    for _ in range(2):
+        eng.decode_device(d_flac.data_ptr(), total_flac, s_off, s_len, 2)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dv0, dv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dv0.record()
+    for _ in range(args.steps):
+        eng.decode_device(d_flac.data_ptr(), total_flac, s_off, s_len, 2)
+    dv1.record()
+    torch.cuda.synchronize()
+    dec_ms = dv0.elapsed_time(dv1)
+    dec_kt = eng.decode_kernel_times()
+    dres = eng.decode_result()
+    dec_ok = int(dres.total_elems) == total_samples
+    h_out = torch.empty(total_samples, dtype=torch.int16).pin_memory()
+    dinfos = (nat.DecStreamInfo * N_STREAMS)()
+
+    def step_dec_e2e():
+        eng.decode_host(arena_np[:total_flac + 16], s_off, s_len, 2)
+        rc = L.flacb200_decode_fetch(eng._h, h_out.data_ptr(), h_out.numel() * 2, C.cast(dinfos, C.c_void_p), None, 0)
+        if rc != 0:
+            raise RuntimeError(L.flacb200_last_error(eng._h).decode())
+    step_dec_e2e()
+    torch.cuda.synchronize()
+    d0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_dec_e2e()
+    torch.cuda.synchronize()
+    dec_e2e_s = time.perf_counter() - d0
+    dec_ok = dec_ok and bool(np.array_equal(h_out.numpy(), pcm.reshape(-1))) and all(dinfos[s].status == 0 for s in range(N_STREAMS))
+    del d_flac
+
     # ---------------- reduce over ranks ----------------
-    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s * 1e3, dec_ms, dec_e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_total_max, e2e_ms_max, dec_ms_max, dec_e2e_ms_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         ms_per_step = ms_total_max / args.steps
@@ -289,13 +331,24 @@ def main():
             "dtype": "int32 (+f32 window, f64 autocorrelation/Levinson, as libFLAC)", "data": "synthetic",
             "config": workload_config(),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": pcm_bytes,
-                    "d2h_bytes_per_step": out_bytes + n_frames * 12 + N_STREAMS * 56, "ms_per_step": e2e_ms_max / args.steps},
+                    "d2h_bytes_per_step": out_bytes + n_frames * 12 + N_STREAMS * 56, "ms_per_step": e2e_ms_max / args.steps,
+                    "last_call_breakdown_ms": host_path_ms},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": kt_acc},
+            "decode": {"metric": "decode_msamples_per_s", "unit": UNIT,
+                       "value": world * total_samples / (dec_ms_max / args.steps * 1e-3) / 1e6,
+                       "e2e_value": world * total_samples / (dec_e2e_ms_max / args.steps * 1e-3) / 1e6,
+                       "ms_per_step": dec_ms_max / args.steps, "e2e_ms_per_step": dec_e2e_ms_max / args.steps,
+                       "workload": "the 256 streams produced by the encode step (libFLAC-identical bytes) -> int16 PCM",
+                       "pcm_identical_to_input": bool(dec_ok), "kernel_ms": dec_kt,
+                       "roofline": {"bound": "hbm", "kernel": "dec_frame_kernel",
+                                    "achieved": (out_bytes + pcm_bytes) / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9,
+                                    "peak": peak, "unit": "GB/s",
+                                    "frac": (out_bytes + pcm_bytes) / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9 / peak}},
             "frames_per_step": n_frames * world, "compressed_bytes_per_step": out_bytes, "ratio": out_bytes / pcm_bytes,
             "log_guard_hits": guard_hits,
         }
@@ -314,11 +367,15 @@ def main():
                 best = min(cpu_reference_run(pcm[:n_sample] if t > 1 else pcm[:8], t)[0] for _ in range(2))
                 sweep[t] = (n_sample if t > 1 else 8) * N_SAMPLES * CHANNELS / best / 1e6
             tbest = max(sweep, key=sweep.get)
+            import _checkers as ck
+            ddt = min(ck.ref_decode_mt(arena_np[:total_flac + 16], s_off, s_len, tbest)[0] for _ in range(2))
+            cpu_decode = total_samples / ddt / 1e6
             line["cpu_baseline"] = {"value": sweep[tbest], "unit": UNIT, "cores": tbest, "kind": "reference",
                                     "sample": f"all {n_sample} streams of the step (8 for the 1-thread point), one FLAC__StreamEncoder per pthread, "
                                               f"libFLAC 1.4.3 from oracle/_ref; best of thread sweep",
                                     "thread_sweep_msamples_per_s": {str(k): v for k, v in sweep.items()},
-                                    "host_threads": threads, "bytes_identical_to_gpu": bool(equal)}
+                                    "host_threads": threads, "bytes_identical_to_gpu": bool(equal),
+                                    "decode_value": cpu_decode, "decode_cores": tbest}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

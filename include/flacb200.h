@@ -150,6 +150,9 @@ int  flacb200_decode_kernel_times(flacb200_ctx *ctx, float *ms);
  * ms[0..5] = analyze, pack, scan, compact, finalize(+MD5 join), md5 (side stream). */
 int  flacb200_set_profiling(flacb200_ctx *ctx, int on);
 int  flacb200_kernel_times(flacb200_ctx *ctx, float *ms);
+/* Wall-clock breakdown (ms since entry) of the last flacb200_encode_batch_host call:
+ * ms[1] work enqueued, ms[2] all chunks' kernels finished, ms[3] D2H finished, ms[4] host MD5 joined, ms[5] return. */
+int  flacb200_host_path_times(flacb200_ctx *ctx, double *ms);
 /* Kernel launches issued by this ctx so far (bench.py's gpu_launches). */
 uint64_t flacb200_launch_count(const flacb200_ctx *ctx);
 

@@ -174,24 +174,49 @@ __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, u
 }
 
 // ------------------------------------------------------------------ frame decode: one thread per candidate ----
+// MSB-first bit reader over global memory.  The refill is word-granular and branch-free (one predicated aligned
+// 32-bit load that tops the 64-bit window up to >= 32 valid bits), so the 32 lanes of a warp -- each decoding its
+// own frame -- stay converged: a byte-wise refill loop entered by every lane at a different symbol would serialise.
 struct BitReader {
-    const uint8_t* __restrict__ base;   // stream start
-    uint64_t pos, end;                  // next byte to fetch, stream length
+    const uint32_t* __restrict__ wp;    // next aligned word to fetch
+    const uint32_t* wend;               // first word past the stream (aligned up)
+    const uint8_t* sbase;               // stream start (for bit positions)
     uint64_t acc; int n;                // n valid bits at the top of acc
-    bool overrun;
-    __device__ __forceinline__ void init(const uint8_t* b, uint64_t start, uint64_t e) { base = b; pos = start; end = e; acc = 0; n = 0; overrun = false; }
-    __device__ __forceinline__ void refill() {
-        while (n <= 56) {
-            uint64_t byte = 0;
-            if (pos < end) byte = __ldg(base + pos); else if (pos >= end + 8) overrun = true;
-            pos++;
-            acc |= byte << (56 - n);
-            n += 8;
+    uint32_t nextw;                     // word fetched one refill ahead (hides the load latency)
+    int over;                           // words consumed past the end of the stream
+    __device__ __forceinline__ void init(const uint8_t* base, uint64_t start, uint64_t slen) {
+        sbase = base;
+        const uint8_t* p = base + start;
+        const uintptr_t a = (uintptr_t)p;
+        wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        wend = reinterpret_cast<const uint32_t*>(((uintptr_t)(base + slen) + 3) & ~(uintptr_t)3);
+        over = 0;
+        const uint32_t skip = (uint32_t)(a & 3) * 8u;
+        uint32_t w = 0;
+        if (wp < wend) w = __byte_perm(__ldg(wp), 0, 0x0123);
+        wp++;
+        acc = ((uint64_t)w << 32) << skip;
+        n = 32 - (int)skip;
+        nextw = 0;
+        if (wp < wend) nextw = __byte_perm(__ldg(wp), 0, 0x0123);
+        fill();
+    }
+    // invariant after fill(): n >= 32 (n <= 32 before => exactly one word is added)
+    __device__ __forceinline__ void fill() {
+        if (n <= 32) {
+            const uint32_t w = nextw;
+            if (wp >= wend) over++;
+            wp++;
+            nextw = 0;
+            if (wp < wend) nextw = __byte_perm(__ldg(wp), 0, 0x0123);
+            acc |= (uint64_t)w << (32 - n);
+            n += 32;
         }
     }
+    __device__ __forceinline__ bool overrun() const { return over > 2; }
     __device__ __forceinline__ uint32_t get(uint32_t k) {          // k <= 32
+        fill();
         if (k == 0) return 0u;
-        if (n < (int)k) refill();
         const uint32_t v = (uint32_t)(acc >> (64 - k));
         acc <<= k; n -= (int)k;
         return v;
@@ -201,33 +226,33 @@ struct BitReader {
         const uint32_t v = get(k);
         return (int32_t)(v << (32 - k)) >> (32 - k);
     }
-    __device__ __forceinline__ int64_t get_signed64(uint32_t k) {  // k <= 33
-        if (k <= 32) return (int64_t)get_signed(k);
-        const int64_t hi = (int64_t)get_signed(k - 32);
-        return (hi << 32) | (int64_t)get(32);
-    }
     __device__ __forceinline__ uint32_t unary() {
+        fill();
         uint32_t q = 0;
-        for (;;) {
-            if (n == 0) refill();
-            if (acc != 0) {
-                const int z = __clzll((long long)acc);
-                q += (uint32_t)z;
-                acc <<= (z + 1); n -= (z + 1);
-                return q;
-            }
-            q += (uint32_t)n; n = 0;
-            if (overrun || q > (1u << 26)) { overrun = true; return q; }
+        uint32_t hi = (uint32_t)(acc >> 32);
+        while (hi == 0) {                                          // rare: more than 31 zeros in a row
+            q += 32; acc <<= 32; n -= 32;
+            fill();
+            hi = (uint32_t)(acc >> 32);
+            if (over > 2 || q > (1u << 26)) { over = 3; return q; }
         }
+        const int z = __clz((int)hi);
+        q += (uint32_t)z;
+        acc <<= (z + 1); n -= (z + 1);
+        return q;
     }
-    __device__ __forceinline__ uint64_t bit_position() const { return pos * 8ull - (uint64_t)n; }
+    // bit offset (from the stream start) of the next unread bit
+    __device__ __forceinline__ uint64_t bit_position() const { return (uint64_t)((const uint8_t*)wp - sbase) * 8ull - (uint64_t)n; }
 };
+
 
 // per-thread history ring and coefficients live in shared memory, [index][thread] so lanes hit distinct banks
 template <int THREADS>
 struct DecShared { int32_t hist[32][THREADS]; int32_t q[32][THREADS]; };
 
 constexpr int kDecFrameThreads = 64;
+
+constexpr int kDecFastOrder = 12;      // predictor orders up to this use the register shift-register path
 
 __global__ void __launch_bounds__(kDecFrameThreads)
 dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, const uint64_t* __restrict__ stream_len,
@@ -262,37 +287,78 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
             else if (type >= 32) { order = type - 31; lpc = true; }
             else { status = kDecBadFrame; break; }
             if (order > N) { status = kDecBadFrame; break; }
-            for (uint32_t i = 0; i < order; i++) { const int32_t v = br.get_signed(bps); sh.hist[i & 31][t] = v; o[i] = v << wasted; }
+            // warm-up samples: newest first in h[] (h[j] = sample i-1-j); orders above kDecFastOrder use the shared ring
+            int32_t h[kDecFastOrder], q[kDecFastOrder];
+#pragma unroll
+            for (int j = 0; j < kDecFastOrder; j++) { h[j] = 0; q[j] = 0; }
+            const bool fast = order <= (uint32_t)kDecFastOrder;
+            for (uint32_t i = 0; i < order; i++) {
+                const int32_t v = br.get_signed(bps);
+                o[i] = v << wasted;
+                if (fast) {
+#pragma unroll
+                    for (int j = kDecFastOrder - 1; j > 0; j--) h[j] = h[j - 1];
+                    h[0] = v;
+                } else sh.hist[i & 31][t] = v;
+            }
             uint32_t prec = 0;
             if (lpc) {
                 prec = br.get(4) + 1; if (prec == 16) { status = kDecBadFrame; break; }
                 shift = br.get_signed(5); if (shift < 0) { status = kDecBadFrame; break; }
-                for (uint32_t j = 0; j < order; j++) sh.q[j][t] = br.get_signed(prec);
+                for (uint32_t j = 0; j < order; j++) {
+                    const int32_t cv = br.get_signed(prec);
+                    if (fast) {
+#pragma unroll
+                        for (int jj = 0; jj < kDecFastOrder; jj++) if ((uint32_t)jj == j) q[jj] = cv;
+                    } else sh.q[j][t] = cv;
+                }
             } else {
                 const int32_t cf[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
-                for (uint32_t j = 0; j < order; j++) sh.q[j][t] = cf[order][j];
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) q[jj] = cf[order][jj];
             }
             // up: lpc.c FLAC__lpc_restore_signal vs _wide: 32-bit accumulate is exact iff bps + precision + ilog2(order) <= 32
             const bool wide = lpc ? (bps + prec + ilog2_u32(order ? order : 1) > 32) : (bps + order > 31);
-            // residual: method, partition order, then per partition a parameter and its symbols
+            // residual: method, partition order, then per partition a parameter and its symbols (one flat loop over samples
+            // with a per-lane "symbols left in this partition" counter keeps lanes with different partition orders converged)
             const uint32_t method = br.get(2);
             if (method > 1) { status = kDecBadFrame; break; }
-            const uint32_t po = br.get(4), parts = 1u << po, plen = method ? 5u : 4u, pesc = method ? 31u : 15u;
-            if ((N >> po) < order || (po > 0 && (N & (parts - 1)))) { status = kDecBadFrame; break; }
-            uint32_t i = order;
-            for (uint32_t p = 0; p < parts && !br.overrun; p++) {
-                const uint32_t cnt = (N >> po) - (p == 0 ? order : 0u);
-                const uint32_t k = br.get(plen);
-                const uint32_t raw = (k == pesc) ? br.get(5) : 0u;
-                for (uint32_t e = 0; e < cnt; e++, i++) {
-                    int32_t r;
-                    if (k == pesc) r = br.get_signed(raw);
-                    else {
-                        const uint32_t qv = br.unary();
-                        const uint32_t u = (qv << k) | br.get(k);
-                        r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1u);
+            const uint32_t po = br.get(4), plen = method ? 5u : 4u, pesc = method ? 31u : 15u;
+            if ((N >> po) < order || (po > 0 && (N & ((1u << po) - 1)))) { status = kDecBadFrame; break; }
+            uint32_t left = 0, k = 0, raw = 0;
+            bool first = true;
+            for (uint32_t i = order; i < N; i++) {
+                if (left == 0) {
+                    left = (N >> po) - (first ? order : 0u);
+                    first = false;
+                    k = br.get(plen);
+                    raw = (k == pesc) ? br.get(5) : 0u;
+                }
+                left--;
+                int32_t r;
+                if (k == pesc) r = br.get_signed(raw);
+                else {
+                    const uint32_t qv = br.unary();
+                    const uint32_t u = (qv << k) | br.get(k);
+                    r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1u);
+                }
+                int32_t v;
+                if (fast) {
+                    if (wide) {
+                        long long s = 0;
+#pragma unroll
+                        for (int j = 0; j < kDecFastOrder; j++) s += (long long)q[j] * (long long)h[j];
+                        v = (int32_t)((long long)r + (s >> shift));
+                    } else {
+                        int s = 0;
+#pragma unroll
+                        for (int j = 0; j < kDecFastOrder; j++) s += q[j] * h[j];
+                        v = r + (s >> shift);
                     }
-                    int32_t v;
+#pragma unroll
+                    for (int j = kDecFastOrder - 1; j > 0; j--) h[j] = h[j - 1];
+                    h[0] = v;
+                } else {
                     if (wide) {
                         long long s = 0;
                         for (uint32_t j = 0; j < order; j++) s += (long long)sh.q[j][t] * (long long)sh.hist[(i - 1 - j) & 31][t];
@@ -303,12 +369,12 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
                         v = r + (s >> shift);
                     }
                     sh.hist[i & 31][t] = v;
-                    o[i] = v << wasted;
                 }
-                if (br.overrun) break;
+                o[i] = v << wasted;
+                if (br.overrun()) break;
             }
         }
-        if (br.overrun) status = kDecIncomplete;
+        if (br.overrun()) status = kDecIncomplete;
     }
     uint64_t endbit = br.bit_position();
     if (status == kDecOk) {

@@ -11,6 +11,7 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <thread>
 #include <string>
@@ -19,6 +20,7 @@
 #include "../../include/flacb200.h"
 #include "fb_common.cuh"
 #include "md5_host.h"
+#include "md5_mb.h"
 
 namespace fb {
 void launch_analyze(const void*, const FrameDesc*, const float*, const EncParams&, int, SubframePlan*, uint8_t*,
@@ -85,6 +87,7 @@ struct flacb200_ctx {
     uint64_t* h_totals = nullptr;          // pinned: per-chunk arena byte counts
     DevBuf d_totals;
     uint64_t e2e_last_bytes = 0;
+    double e2e_ms[6] = {0};               // last host call: plan, enqueue, kernels drained, d2h done, md5 join, total
 
     DevBuf d_pcm, d_frames, d_windows, d_plans, d_ca, d_scratch, d_flen, d_foff, d_arena, d_total, d_stats;
     DevBuf d_sfirst, d_snframes, d_soff, d_ssamples, d_md5, d_sinfo, d_debug;
@@ -235,6 +238,8 @@ cudaStream_t fb_ctx_stream(flacb200_ctx* c) { return c->stream; }
 void** fb_ctx_dec_slot(flacb200_ctx* c, void (*freer)(void*)) { c->dec_free = freer; return &c->dec; }
 int fb_ctx_fail(flacb200_ctx* c, int code, const char* what, cudaError_t e) { return fail(c, code, what, e); }
 void fb_ctx_add_launches(flacb200_ctx* c, uint64_t n) { c->launches += n; }
+
+extern "C" int flacb200_host_path_times(flacb200_ctx* ctx, double* ms) { if (!ctx || !ms) return FLACB200_ERR_ARG; for (int i = 0; i < 6; i++) ms[i] = ctx->e2e_ms[i]; return 0; }
 
 extern "C" int flacb200_set_profiling(flacb200_ctx* ctx, int on) { if (!ctx) return FLACB200_ERR_ARG; ctx->profiling = on != 0; return 0; }
 // ms[0..5] = analyze, pack, layout(scan), compact, finalize (incl. waiting for MD5), md5 (side stream) of the last batch
@@ -511,21 +516,34 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     std::atomic<int> next_stream{0};
     if (want_md5) {
         unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 8;
-        const unsigned nt = std::min<unsigned>(std::min<unsigned>(hw, 64u), (unsigned)ns);
+        const unsigned nt = std::min<unsigned>(std::min<unsigned>(hw / 2 ? hw / 2 : 1u, 32u), (unsigned)((ns + 7) / 8));
         const uint32_t bytes_per = (P.bps + 7) / 8, chn = P.channels;
+        const bool raw_bytes = (bytes_per == cont);          // the container bytes are the hashed bytes: 8 streams per SIMD pass
         for (unsigned t = 0; t < nt; t++)
-            workers.emplace_back([&, bytes_per, chn]() {
+            workers.emplace_back([&, bytes_per, chn, raw_bytes]() {
                 for (;;) {
-                    const int s = next_stream.fetch_add(1);
-                    if (s >= ns) break;
-                    fb::Md5 m; m.init();
-                    m.update_samples((const uint8_t*)pcm_host + stream_off[s] * cont, (size_t)stream_samples[s] * chn, cont, bytes_per);
-                    m.final(&digests[(size_t)s * 16]);
+                    const int g = next_stream.fetch_add(8);
+                    if (g >= ns) break;
+                    const int n = std::min(8, ns - g);
+                    if (raw_bytes) {
+                        const uint8_t* d[8]; size_t l[8]; uint8_t dig[8][16];
+                        for (int i = 0; i < n; i++) { d[i] = (const uint8_t*)pcm_host + stream_off[g + i] * cont; l[i] = (size_t)stream_samples[g + i] * chn * cont; }
+                        fb::md5_group8(d, l, n, dig);
+                        for (int i = 0; i < n; i++) memcpy(&digests[(size_t)(g + i) * 16], dig[i], 16);
+                    } else {
+                        for (int i = 0; i < n; i++) {
+                            fb::Md5 m; m.init();
+                            m.update_samples((const uint8_t*)pcm_host + stream_off[g + i] * cont, (size_t)stream_samples[g + i] * chn, cont, bytes_per);
+                            m.final(&digests[(size_t)(g + i) * 16]);
+                        }
+                    }
                 }
             });
     }
     auto join_workers = [&]() { for (auto& w : workers) if (w.joinable()) w.join(); };
 
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     // ---- enqueue: H2D per chunk, then kernels per chunk ----
     auto bail = [&](int code) { join_workers(); return code; };
 #define CKJ(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(ctx, FLACB200_ERR_CUDA, #call, e_)); } while (0)
@@ -577,6 +595,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     }
     if (dev_base[nchunks] > ctx->d_arena.cap) return bail(fail(ctx, FLACB200_ERR_CUDA, "device arena too small"));
 
+    ctx->e2e_ms[1] = since();
     // ---- drain: as each chunk finishes, copy exactly its bytes to the next free spot of the host arena ----
     std::vector<uint64_t> host_base(nchunks + 1, 0);
     for (int c = 0; c < nchunks; c++) {
@@ -586,6 +605,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         if (bytes) CKJ(cudaMemcpyAsync(arena + host_base[c], (const uint8_t*)ctx->d_arena.p + dev_base[c], bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
         host_base[c + 1] = host_base[c] + bytes;
     }
+    ctx->e2e_ms[2] = since();
     std::vector<uint64_t> tmp_off;
     uint64_t* foff_host = frame_off;
     if (!foff_host) { tmp_off.resize(nf); foff_host = tmp_off.data(); }
@@ -598,7 +618,9 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     CKJ(cudaStreamSynchronize(ctx->d2h_stream));
     CKJ(cudaGetLastError());
 #undef CKJ
+    ctx->e2e_ms[3] = since();
     join_workers();
+    ctx->e2e_ms[4] = since();
     // device-arena offsets -> host-arena offsets; MD5 digests into STREAMINFO
     for (int c = 0; c < nchunks; c++) {
         const int s0 = cs[c], s1 = cs[c + 1];
@@ -614,6 +636,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         }
     }
     ctx->e2e_last_bytes = host_base[nchunks];
+    ctx->e2e_ms[5] = since();
     if (total_bytes) *total_bytes = host_base[nchunks];
     return 0;
 }

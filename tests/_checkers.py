@@ -230,3 +230,16 @@ def ref_encode_mt(pcm, sample_rate, bps, level=5, blocksize=0, n_threads=1, keep
     if keep_bytes:
         blobs = [out_all[s * stride: s * stride + int(lens[s])] for s in range(ns)]
     return dt, int(total.value), blobs
+
+
+def ref_decode_mt(blob, offs, lens, n_threads):
+    """Time libFLAC decode of many .flac byte strings (uint8 array + uint64 offsets/lengths) on n_threads pthreads.
+    Returns (seconds, inter-channel samples decoded)."""
+    blob = np.ascontiguousarray(blob, np.uint8)
+    offs = np.ascontiguousarray(offs, np.uint64)
+    lens = np.ascontiguousarray(lens, np.uint64)
+    total = C.c_uint64(0)
+    dt = ref_lib().ref_decode_mt(blob.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(offs), n_threads, C.byref(total))
+    if dt < 0:
+        raise RuntimeError("ref_decode_mt failed")
+    return dt, int(total.value)

@@ -1,0 +1,101 @@
+"""CPU tests of host-side logic: WAV I/O, stream sharding + rank reductions over gloo (world_size 2), package surface."""
+import os
+import struct
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+from conftest import ROOT
+
+
+def test_wav_reader_writer_roundtrip():
+    from pyflac_b200 import wav
+    rng = np.random.default_rng(0)
+    x = rng.integers(-30000, 30000, (1000, 2)).astype(np.int16)
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "a.wav")
+        w = wav.Pcm16Writer(p, 44100, 2)
+        w.write(x[:400]); w.write(x[400:]); w.close()
+        i = wav.info(p)
+        assert (i.samplerate, i.channels, i.frames, i.subtype) == (44100, 2, 1000, "PCM_16")
+        y, sr = wav.read_pcm(p)
+        assert sr == 44100 and np.array_equal(x, y)
+        f, _ = wav.read_float64(p)
+        assert f.dtype == np.float64 and np.array_equal(np.rint(f * 32768).astype(np.int16), x)
+        # WAVE_FORMAT_EXTENSIBLE + extra chunk before data, 32-bit
+        x32 = rng.integers(-2**31, 2**31 - 1, (50, 1)).astype(np.int32)
+        fmt = struct.pack("<HHIIHH", 0xFFFE, 1, 48000, 48000 * 4, 4, 32) + struct.pack("<HHI", 22, 32, 4) + \
+            struct.pack("<H", 1) + b"\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71"
+        raw = x32.astype("<i4").tobytes()
+        body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"LIST" + struct.pack("<I", 4) + b"abcd" + b"data" + struct.pack("<I", len(raw)) + raw
+        with open(p, "wb") as fh:
+            fh.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+        y, sr = wav.read_pcm(p)
+        assert sr == 48000 and np.array_equal(y, x32)
+        # 8-bit input is rejected like the reference (encoder.py:372-378)
+        fmt8 = struct.pack("<HHIIHH", 1, 1, 8000, 8000, 1, 8)
+        body = b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt8 + b"data" + struct.pack("<I", 4) + b"\x80\x80\x80\x80"
+        with open(p, "wb") as fh:
+            fh.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+        try:
+            wav.read_pcm(p)
+            assert False
+        except ValueError:
+            pass
+
+
+def test_shard_range_covers_everything():
+    from pyflac_b200.dist import shard_range
+    for n in (0, 1, 7, 256, 32768):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from pyflac_b200.dist import shard_range, reduce_max, reduce_sum
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+lo, hi = shard_range(257, r, w)
+mx = reduce_max([10.0 + r, float(hi - lo)])
+sm = reduce_sum([float(hi - lo)])
+dist.barrier()
+if r == 0:
+    print("RESULT", mx[0], mx[1], sm[0])
+dist.destroy_process_group()
+'''
+
+
+def test_rank_reductions_gloo_world2():
+    """the N>1 path of bench.py (barrier, max-over-ranks timing, summed work) on the gloo backend"""
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(_WORKER)
+        path = f.name
+    try:
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                              "--master-port", "29577", path, ROOT], capture_output=True, text=True, timeout=240, env=env)
+        line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
+        assert line, out.stdout + out.stderr
+        _, a, b, c = line[0].split()
+        assert float(a) == 11.0 and float(b) == 129.0 and float(c) == 257.0
+    finally:
+        os.unlink(path)
+
+
+def test_package_surface_matches_reference_names():
+    import pyflac_b200 as pf
+    for name in ["StreamEncoder", "FileEncoder", "EncoderState", "EncoderInitException", "EncoderProcessException",
+                 "StreamDecoder", "FileDecoder", "OneShotDecoder", "DecoderState", "DecoderInitException", "DecoderProcessException"]:
+        assert hasattr(pf, name)
+    assert str(pf.EncoderState.UNINITIALIZED) == "FLAC__STREAM_ENCODER_UNINITIALIZED"
+    assert str(pf.DecoderState.UNINITIALIZED) == "FLAC__STREAM_DECODER_UNINITIALIZED"
+    assert str(pf.EncoderInitException(3)) == "FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_CALLBACKS"
+    assert str(pf.DecoderInitException(4)) == "FLAC__STREAM_DECODER_INIT_STATUS_ERROR_OPENING_FILE"
