@@ -228,6 +228,7 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         step_device()
+    eng.join()                                      # MD5 / finalize side streams of the in-flight steps end inside the timed region
     ev1.record()
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()

@@ -82,6 +82,11 @@ const char *flacb200_last_error(const flacb200_ctx *ctx);
  * stream) so callers can bracket it with their own events.  NULL = ctx-owned stream. */
 int  flacb200_set_stream(flacb200_ctx *ctx, void *cuda_stream);
 int  flacb200_sync(flacb200_ctx *ctx);
+/* Batches overlap: the MD5 + STREAMINFO finalisation of a batch run on a side stream while the next batch's kernels
+ * start (three rotating output sets).  flacb200_join makes the ctx stream wait for all of them, so that an event
+ * recorded on it afterwards covers every batch issued so far; result/fetch/sync do this implicitly.  The PCM of a
+ * batch must stay unchanged until then. */
+int  flacb200_join(flacb200_ctx *ctx);
 
 /* libFLAC's init-time validation for these settings: returns the FLAC__StreamEncoderInitStatus
  * value (0 = OK), pyflac/builder/encoder.py:65-80. */

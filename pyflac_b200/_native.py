@@ -80,6 +80,7 @@ def lib():
     L.flacb200_last_error.argtypes = [C.c_void_p]
     L.flacb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.flacb200_sync.argtypes = [C.c_void_p]
+    L.flacb200_join.argtypes = [C.c_void_p]
     L.flacb200_enc_validate.argtypes = [C.POINTER(EncConfig)]
     L.flacb200_encode_batch.argtypes = [C.c_void_p, C.POINTER(EncConfig), C.c_void_p, C.c_int, C.c_uint64, C.c_uint32,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
@@ -131,6 +132,10 @@ class Engine:
 
     def sync(self):
         self._check(self._L.flacb200_sync(self._h))
+
+    def join(self):
+        """Make the engine stream wait for the side-stream work (MD5, finalize) of all in-flight batches."""
+        self._check(self._L.flacb200_join(self._h))
 
     def set_profiling(self, on=True):
         self._check(self._L.flacb200_set_profiling(self._h, int(on)))

@@ -89,10 +89,25 @@ struct flacb200_ctx {
     uint64_t e2e_last_bytes = 0;
     double e2e_ms[6] = {0};               // last host call: plan, enqueue, kernels drained, d2h done, md5 join, total
 
-    DevBuf d_pcm, d_frames, d_windows, d_plans, d_ca, d_scratch, d_flen, d_foff, d_arena, d_total, d_stats;
-    DevBuf d_sfirst, d_snframes, d_soff, d_ssamples, d_md5, d_sinfo, d_debug;
+    DevBuf d_pcm, d_frames, d_windows, d_plans, d_ca, d_scratch;
+    DevBuf d_sfirst, d_snframes, d_soff, d_ssamples, d_debug;
+
+    // Output buffers exist three times and rotate per batch: the MD5 of a batch (a serial chain per stream, longer
+    // than analysis + packing for long streams) and the STREAMINFO finalisation that needs it run on the set's own
+    // side stream, so the next batch's kernels do not wait for them; a set is reused only after its finalize is done.
+    struct OutSet {
+        DevBuf flen, foff, arena, sinfo, md5, total, stats;
+        cudaStream_t side = nullptr;
+        cudaEvent_t ev_main = nullptr, ev_free = nullptr;
+        bool busy = false;
+    };
+    static constexpr int kSets = 3;
+    OutSet sets[kSets];
+    int cur = 0;
+    OutSet& set() { return sets[cur]; }
 };
 
+static int wait_all_sets(flacb200_ctx* ctx, cudaStream_t st);
 static int fail(flacb200_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
     char buf[512];
     if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
@@ -195,6 +210,11 @@ extern "C" int flacb200_create(flacb200_ctx** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return FLACB200_ERR_NO_DEVICE; }
     cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->md5_stream, cudaStreamNonBlocking);
+    for (auto& S : ctx->sets) {
+        cudaStreamCreateWithFlags(&S.side, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&S.ev_main, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&S.ev_free, cudaEventDisableTiming);
+    }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -213,10 +233,17 @@ extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_pcm, &ctx->d_frames, &ctx->d_windows, &ctx->d_plans, &ctx->d_ca, &ctx->d_scratch, &ctx->d_flen,
-                      &ctx->d_foff, &ctx->d_arena, &ctx->d_total, &ctx->d_stats, &ctx->d_sfirst, &ctx->d_snframes, &ctx->d_soff,
-                      &ctx->d_ssamples, &ctx->d_md5, &ctx->d_sinfo, &ctx->d_debug};
+    DevBuf* bufs[] = {&ctx->d_pcm, &ctx->d_frames, &ctx->d_windows, &ctx->d_plans, &ctx->d_ca, &ctx->d_scratch, &ctx->d_sfirst, &ctx->d_snframes,
+                      &ctx->d_soff, &ctx->d_ssamples, &ctx->d_debug};
     for (DevBuf* b : bufs) b->release();
+    for (auto& S : ctx->sets) {
+        if (S.side) cudaStreamSynchronize(S.side);
+        DevBuf* sb[] = {&S.flen, &S.foff, &S.arena, &S.sinfo, &S.md5, &S.total, &S.stats};
+        for (DevBuf* b : sb) b->release();
+        if (S.ev_main) cudaEventDestroy(S.ev_main);
+        if (S.ev_free) cudaEventDestroy(S.ev_free);
+        if (S.side) cudaStreamDestroy(S.side);
+    }
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& e : ctx->ev_k) cudaEventDestroy(e);
     for (auto& e : ctx->ev_h2d) cudaEventDestroy(e);
@@ -231,13 +258,23 @@ extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
 
 extern "C" const char* flacb200_last_error(const flacb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
 extern "C" int flacb200_set_stream(flacb200_ctx* ctx, void* s) { if (!ctx) return FLACB200_ERR_ARG; ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return 0; }
-extern "C" int flacb200_sync(flacb200_ctx* ctx) { if (!ctx) return FLACB200_ERR_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+extern "C" int flacb200_sync(flacb200_ctx* ctx) {
+    if (!ctx) return FLACB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& S : ctx->sets) if (S.busy) CK(cudaStreamSynchronize(S.side));
+    return 0;
+}
 // accessors for the decode engine (dec_engine.cu keeps its own state behind ctx->dec)
 int fb_ctx_device(flacb200_ctx* c) { return c->device; }
 cudaStream_t fb_ctx_stream(flacb200_ctx* c) { return c->stream; }
 void** fb_ctx_dec_slot(flacb200_ctx* c, void (*freer)(void*)) { c->dec_free = freer; return &c->dec; }
 int fb_ctx_fail(flacb200_ctx* c, int code, const char* what, cudaError_t e) { return fail(c, code, what, e); }
 void fb_ctx_add_launches(flacb200_ctx* c, uint64_t n) { c->launches += n; }
+
+// Make the ctx stream wait for every side stream (MD5 + finalize of in-flight batches): after this, an event recorded
+// on the ctx stream covers all work issued so far.
+extern "C" int flacb200_join(flacb200_ctx* ctx) { if (!ctx) return FLACB200_ERR_ARG; cudaSetDevice(ctx->device); return wait_all_sets(ctx, ctx->stream); }
 
 extern "C" int flacb200_host_path_times(flacb200_ctx* ctx, double* ms) { if (!ctx || !ms) return FLACB200_ERR_ARG; for (int i = 0; i < 6; i++) ms[i] = ctx->e2e_ms[i]; return 0; }
 
@@ -247,7 +284,7 @@ extern "C" int flacb200_kernel_times(flacb200_ctx* ctx, float* ms) {
     if (!ctx || !ms || !ctx->profiling || !ctx->have_batch) return FLACB200_ERR_ARG;
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaStreamSynchronize(ctx->md5_stream));
+    for (auto& S : ctx->sets) CK(cudaStreamSynchronize(S.side));
     for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&ms[i], ctx->ev_k[i], ctx->ev_k[i + 1]));
     ms[5] = 0.0f;
     if (ctx->cfg.do_md5) CK(cudaEventElapsedTime(&ms[5], ctx->ev_k[6], ctx->ev_k[7]));
@@ -316,17 +353,17 @@ static int plan_batch(flacb200_ctx* ctx, const flacb200_enc_config& cfg, uint32_
     CK(ctx->d_plans.reserve(sizeof(SubframePlan) * (size_t)(nf ? nf : 1) * P.n_signals));
     CK(ctx->d_ca.reserve((size_t)nf + 16));
     CK(ctx->d_scratch.reserve((size_t)nf * ctx->scratch_stride + 64));
-    CK(ctx->d_flen.reserve(sizeof(uint32_t) * (size_t)(nf + 1)));
-    CK(ctx->d_foff.reserve(sizeof(uint64_t) * (size_t)(nf + 1)));
-    CK(ctx->d_arena.reserve((size_t)nf * ctx->scratch_stride + (size_t)ns * kStreamPrologueBytes + 64 + 256 * (flacb200_ctx::kMaxChunks + 1)));
-    CK(ctx->d_total.reserve(64));
-    CK(ctx->d_stats.reserve(sizeof(EncStats)));
+    for (auto& S : ctx->sets) CK(S.flen.reserve(sizeof(uint32_t) * (size_t)(nf + 1)));
+    for (auto& S : ctx->sets) CK(S.foff.reserve(sizeof(uint64_t) * (size_t)(nf + 1)));
+    for (auto& S : ctx->sets) CK(S.arena.reserve((size_t)nf * ctx->scratch_stride + (size_t)ns * kStreamPrologueBytes + 64 + 256 * (flacb200_ctx::kMaxChunks + 1)));
+    for (auto& S : ctx->sets) CK(S.total.reserve(64));
+    for (auto& S : ctx->sets) CK(S.stats.reserve(sizeof(EncStats)));
     CK(ctx->d_sfirst.reserve(sizeof(uint32_t) * (ns + 1)));
     CK(ctx->d_snframes.reserve(sizeof(uint32_t) * (ns + 1)));
     CK(ctx->d_soff.reserve(sizeof(uint64_t) * (ns + 1)));
     CK(ctx->d_ssamples.reserve(sizeof(uint64_t) * (ns + 1)));
-    CK(ctx->d_md5.reserve(16 * (size_t)(ns + 1)));
-    CK(ctx->d_sinfo.reserve(sizeof(StreamInfoOut) * (size_t)(ns + 1)));
+    for (auto& S : ctx->sets) CK(S.md5.reserve(16 * (size_t)(ns + 1)));
+    for (auto& S : ctx->sets) CK(S.sinfo.reserve(sizeof(StreamInfoOut) * (size_t)(ns + 1)));
     if (ctx->debug) CK(ctx->d_debug.reserve(sizeof(SignalDebug) * (size_t)(nf ? nf : 1) * P.n_signals));
     if (nf) CK(cudaMemcpyAsync(ctx->d_frames.p, ctx->h_frames.data(), sizeof(FrameDesc) * nf, cudaMemcpyHostToDevice, st));
     if (ns) {
@@ -347,45 +384,54 @@ static int plan_batch(flacb200_ctx* ctx, const flacb200_enc_config& cfg, uint32_
     return 0;
 }
 
+// make sure no side stream still owns any output set (host path and teardown use this)
+static int wait_all_sets(flacb200_ctx* ctx, cudaStream_t st) {
+    for (auto& S : ctx->sets) if (S.busy) { CK(cudaStreamWaitEvent(st, S.ev_free, 0)); }
+    return 0;
+}
+
 static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
     const EncParams& P = ctx->P;
     const int nf = ctx->n_frames, ns = ctx->n_streams;
     cudaStream_t st = ctx->stream;
-    CK(cudaMemsetAsync(ctx->d_stats.p, 0, sizeof(EncStats), st));
-    CK(cudaMemsetAsync(ctx->d_total.p, 0, 8, st));
+    ctx->cur = (ctx->cur + 1) % flacb200_ctx::kSets;
+    flacb200_ctx::OutSet& S = ctx->set();
+    if (S.busy) { CK(cudaStreamWaitEvent(st, S.ev_free, 0)); S.busy = false; }   // its previous finalize must be done before reuse
+    CK(cudaMemsetAsync(S.stats.p, 0, sizeof(EncStats), st));
+    CK(cudaMemsetAsync(S.total.p, 0, 8, st));
     if (nf == 0) return 0;
     const bool md5 = ctx->cfg.do_md5 != 0;
+    const bool prof = ctx->profiling;
     if (md5) {
         CK(cudaEventRecord(ctx->ev_fork, st));
-        CK(cudaStreamWaitEvent(ctx->md5_stream, ctx->ev_fork, 0));
-        if (ctx->profiling) CK(cudaEventRecord(ctx->ev_k[6], ctx->md5_stream));
+        CK(cudaStreamWaitEvent(S.side, ctx->ev_fork, 0));
+        if (prof) CK(cudaEventRecord(ctx->ev_k[6], S.side));
         launch_md5(d_pcm, P.container_bytes, (const uint64_t*)ctx->d_soff.p, (const uint64_t*)ctx->d_ssamples.p, ns, P.channels, P.bps,
-                   (uint8_t*)ctx->d_md5.p, ctx->md5_stream);
-        if (ctx->profiling) CK(cudaEventRecord(ctx->ev_k[7], ctx->md5_stream));
-        CK(cudaEventRecord(ctx->ev_join, ctx->md5_stream));
+                   (uint8_t*)S.md5.p, S.side);
+        if (prof) CK(cudaEventRecord(ctx->ev_k[7], S.side));
         ctx->launches++;
     }
-    const bool prof = ctx->profiling;
     if (prof) CK(cudaEventRecord(ctx->ev_k[0], st));
     launch_analyze(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, (SubframePlan*)ctx->d_plans.p,
-                   (uint8_t*)ctx->d_ca.p, ctx->debug ? (SignalDebug*)ctx->d_debug.p : nullptr, (EncStats*)ctx->d_stats.p,
+                   (uint8_t*)ctx->d_ca.p, ctx->debug ? (SignalDebug*)ctx->d_debug.p : nullptr, (EncStats*)S.stats.p,
                    analyze_smem_bytes(P), st);
     if (prof) CK(cudaEventRecord(ctx->ev_k[1], st));
     launch_pack(d_pcm, (const FrameDesc*)ctx->d_frames.p, P, nf, (const SubframePlan*)ctx->d_plans.p, (const uint8_t*)ctx->d_ca.p,
-                (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)ctx->d_flen.p, st);
+                (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)S.flen.p, st);
     if (prof) CK(cudaEventRecord(ctx->ev_k[2], st));
     const uint32_t pro = ctx->cfg.write_prologue ? (uint32_t)kStreamPrologueBytes : 0u;
-    launch_layout((const uint32_t*)ctx->d_flen.p, (const FrameDesc*)ctx->d_frames.p, nf, pro, 0ull, (uint64_t*)ctx->d_foff.p,
-                  (uint64_t*)ctx->d_total.p, st);
+    launch_layout((const uint32_t*)S.flen.p, (const FrameDesc*)ctx->d_frames.p, nf, pro, 0ull, (uint64_t*)S.foff.p, (uint64_t*)S.total.p, st);
     if (prof) CK(cudaEventRecord(ctx->ev_k[3], st));
-    launch_compact((const uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (const uint32_t*)ctx->d_flen.p, (const uint64_t*)ctx->d_foff.p,
-                   (uint8_t*)ctx->d_arena.p, nf, st);
+    launch_compact((const uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (const uint32_t*)S.flen.p, (const uint64_t*)S.foff.p, (uint8_t*)S.arena.p, nf, st);
     if (prof) CK(cudaEventRecord(ctx->ev_k[4], st));
-    if (md5) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    launch_finalize((const uint32_t*)ctx->d_flen.p, (const uint64_t*)ctx->d_foff.p, (const uint32_t*)ctx->d_sfirst.p,
-                    (const uint32_t*)ctx->d_snframes.p, (const uint64_t*)ctx->d_ssamples.p, md5 ? (const uint8_t*)ctx->d_md5.p : nullptr, ns, P,
-                    pro ? 1u : 0u, (uint8_t*)ctx->d_arena.p, (StreamInfoOut*)ctx->d_sinfo.p, st);
-    if (prof) CK(cudaEventRecord(ctx->ev_k[5], st));
+    // finalize (STREAMINFO with MD5) follows the MD5 on the set's side stream; the main stream moves on to the next batch
+    cudaStream_t fs = md5 ? S.side : st;
+    if (md5) { CK(cudaEventRecord(S.ev_main, st)); CK(cudaStreamWaitEvent(S.side, S.ev_main, 0)); }
+    launch_finalize((const uint32_t*)S.flen.p, (const uint64_t*)S.foff.p, (const uint32_t*)ctx->d_sfirst.p, (const uint32_t*)ctx->d_snframes.p,
+                    (const uint64_t*)ctx->d_ssamples.p, md5 ? (const uint8_t*)S.md5.p : nullptr, ns, P, pro ? 1u : 0u, (uint8_t*)S.arena.p,
+                    (StreamInfoOut*)S.sinfo.p, fs);
+    if (prof) CK(cudaEventRecord(ctx->ev_k[5], fs));
+    if (md5) { CK(cudaEventRecord(S.ev_free, S.side)); S.busy = true; }
     ctx->launches += 5;
     CK(cudaGetLastError());
     return 0;
@@ -401,6 +447,7 @@ extern "C" int flacb200_encode_batch(flacb200_ctx* ctx, const flacb200_enc_confi
         if (stream_off[s] + stream_samples[s] * cfg->channels > pcm_elems) return fail(ctx, FLACB200_ERR_ARG, "stream exceeds pcm buffer");
     if (!same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, first_frame_number)) {
         ctx->have_batch = false;
+        for (auto& S : ctx->sets) if (S.busy) { CK(cudaStreamSynchronize(S.side)); S.busy = false; }
         int rc = plan_batch(ctx, *cfg, n_streams, stream_off, stream_samples, first_frame_number);
         if (rc) return rc;
     }
@@ -419,12 +466,13 @@ extern "C" int flacb200_encode_result(flacb200_ctx* ctx, flacb200_enc_result* re
     if (!ctx->have_batch) return fail(ctx, FLACB200_ERR_ARG, "no batch");
     cudaSetDevice(ctx->device);
     uint64_t total = 0; EncStats stt{};
-    CK(cudaMemcpyAsync(&total, ctx->d_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(&stt, ctx->d_stats.p, sizeof stt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&total, ctx->set().total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&stt, ctx->set().stats.p, sizeof stt, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->set().busy) CK(cudaStreamSynchronize(ctx->set().side));     // MD5 + STREAMINFO of this batch live on the set's side stream
     res->total_bytes = total; res->n_frames = (uint32_t)ctx->n_frames; res->n_streams = (uint32_t)ctx->n_streams;
     res->log_guard_hits = stt.log_ambiguous;
-    res->d_arena = (const uint8_t*)ctx->d_arena.p; res->d_frame_off = (const uint64_t*)ctx->d_foff.p; res->d_frame_len = (const uint32_t*)ctx->d_flen.p;
+    res->d_arena = (const uint8_t*)ctx->set().arena.p; res->d_frame_off = (const uint64_t*)ctx->set().foff.p; res->d_frame_len = (const uint32_t*)ctx->set().flen.p;
     return 0;
 }
 
@@ -436,13 +484,13 @@ extern "C" int flacb200_encode_fetch(flacb200_ctx* ctx, uint8_t* arena, size_t a
     cudaStream_t st = ctx->stream;
     if (arena) {
         if (arena_cap < r.total_bytes) return fail(ctx, FLACB200_ERR_ARG, "arena too small");
-        if (r.total_bytes) CK(cudaMemcpyAsync(arena, ctx->d_arena.p, r.total_bytes, cudaMemcpyDeviceToHost, st));
+        if (r.total_bytes) CK(cudaMemcpyAsync(arena, ctx->set().arena.p, r.total_bytes, cudaMemcpyDeviceToHost, st));
     }
     const int nf = ctx->n_frames;
-    if (frame_off && nf) CK(cudaMemcpyAsync(frame_off, ctx->d_foff.p, sizeof(uint64_t) * nf, cudaMemcpyDeviceToHost, st));
-    if (frame_len && nf) CK(cudaMemcpyAsync(frame_len, ctx->d_flen.p, sizeof(uint32_t) * nf, cudaMemcpyDeviceToHost, st));
+    if (frame_off && nf) CK(cudaMemcpyAsync(frame_off, ctx->set().foff.p, sizeof(uint64_t) * nf, cudaMemcpyDeviceToHost, st));
+    if (frame_len && nf) CK(cudaMemcpyAsync(frame_len, ctx->set().flen.p, sizeof(uint32_t) * nf, cudaMemcpyDeviceToHost, st));
     static_assert(sizeof(flacb200_stream_info) == sizeof(StreamInfoOut), "stream info layout");
-    if (streams && ctx->n_streams) CK(cudaMemcpyAsync(streams, ctx->d_sinfo.p, sizeof(StreamInfoOut) * ctx->n_streams, cudaMemcpyDeviceToHost, st));
+    if (streams && ctx->n_streams) CK(cudaMemcpyAsync(streams, ctx->set().sinfo.p, sizeof(StreamInfoOut) * ctx->n_streams, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     for (int f = 0; f < nf; f++) {
         if (frame_samples) frame_samples[f] = ctx->h_frames[f].blocksize;
@@ -483,6 +531,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         if (stream_off[s] + stream_samples[s] * cfg->channels > pcm_elems) return fail(ctx, FLACB200_ERR_ARG, "stream exceeds pcm buffer");
     if (!same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr)) {
         ctx->have_batch = false;
+        for (auto& S : ctx->sets) if (S.busy) { CK(cudaStreamSynchronize(S.side)); S.busy = false; }
         int rc = plan_batch(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr);
         if (rc) return rc;
     }
@@ -547,7 +596,8 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     // ---- enqueue: H2D per chunk, then kernels per chunk ----
     auto bail = [&](int code) { join_workers(); return code; };
 #define CKJ(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(ctx, FLACB200_ERR_CUDA, #call, e_)); } while (0)
-    CKJ(cudaMemsetAsync(ctx->d_stats.p, 0, sizeof(EncStats), st));
+    { int wrc = wait_all_sets(ctx, st); if (wrc) return bail(wrc); }
+    CKJ(cudaMemsetAsync(ctx->set().stats.p, 0, sizeof(EncStats), st));
     bool monotonic = true;
     for (int s = 1; s < ns; s++) if (stream_off[s] < stream_off[s - 1] + stream_samples[s - 1] * P.channels) { monotonic = false; break; }
     for (int c = 0; c < nchunks; c++) {
@@ -574,18 +624,18 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         CKJ(cudaStreamWaitEvent(st, ctx->ev_h2d[c], 0));
         if (cnf > 0) {
             launch_analyze(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf,
-                           (SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals, (uint8_t*)ctx->d_ca.p + f0, nullptr, (EncStats*)ctx->d_stats.p,
+                           (SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals, (uint8_t*)ctx->d_ca.p + f0, nullptr, (EncStats*)ctx->set().stats.p,
                            analyze_smem_bytes(P), st);
             launch_pack(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, P, cnf, (const SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals,
                         (const uint8_t*)ctx->d_ca.p + f0, (uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride,
-                        (uint32_t*)ctx->d_flen.p + f0, st);
-            launch_layout((const uint32_t*)ctx->d_flen.p + f0, (const FrameDesc*)ctx->d_frames.p + f0, cnf, pro, dev_base[c],
-                          (uint64_t*)ctx->d_foff.p + f0, (uint64_t*)ctx->d_totals.p + c, st);
-            launch_compact((const uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride, (const uint32_t*)ctx->d_flen.p + f0,
-                           (const uint64_t*)ctx->d_foff.p + f0, (uint8_t*)ctx->d_arena.p, cnf, st);
-            launch_finalize((const uint32_t*)ctx->d_flen.p, (const uint64_t*)ctx->d_foff.p, (const uint32_t*)ctx->d_sfirst.p + s0,
+                        (uint32_t*)ctx->set().flen.p + f0, st);
+            launch_layout((const uint32_t*)ctx->set().flen.p + f0, (const FrameDesc*)ctx->d_frames.p + f0, cnf, pro, dev_base[c],
+                          (uint64_t*)ctx->set().foff.p + f0, (uint64_t*)ctx->d_totals.p + c, st);
+            launch_compact((const uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride, (const uint32_t*)ctx->set().flen.p + f0,
+                           (const uint64_t*)ctx->set().foff.p + f0, (uint8_t*)ctx->set().arena.p, cnf, st);
+            launch_finalize((const uint32_t*)ctx->set().flen.p, (const uint64_t*)ctx->set().foff.p, (const uint32_t*)ctx->d_sfirst.p + s0,
                             (const uint32_t*)ctx->d_snframes.p + s0, (const uint64_t*)ctx->d_ssamples.p + s0, nullptr, cns, P, pro ? 1u : 0u,
-                            (uint8_t*)ctx->d_arena.p, (StreamInfoOut*)ctx->d_sinfo.p + s0, st);
+                            (uint8_t*)ctx->set().arena.p, (StreamInfoOut*)ctx->set().sinfo.p + s0, st);
             ctx->launches += 5;
         } else {
             CKJ(cudaMemsetAsync((uint64_t*)ctx->d_totals.p + c, 0, 8, st));
@@ -593,7 +643,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         CKJ(cudaMemcpyAsync(ctx->h_totals + c, (uint64_t*)ctx->d_totals.p + c, 8, cudaMemcpyDeviceToHost, st));
         CKJ(cudaEventRecord(ctx->ev_done[c], st));
     }
-    if (dev_base[nchunks] > ctx->d_arena.cap) return bail(fail(ctx, FLACB200_ERR_CUDA, "device arena too small"));
+    if (dev_base[nchunks] > ctx->set().arena.cap) return bail(fail(ctx, FLACB200_ERR_CUDA, "device arena too small"));
 
     ctx->e2e_ms[1] = since();
     // ---- drain: as each chunk finishes, copy exactly its bytes to the next free spot of the host arena ----
@@ -602,19 +652,19 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         CKJ(cudaEventSynchronize(ctx->ev_done[c]));
         const uint64_t bytes = ctx->h_totals[c];
         if (host_base[c] + bytes > arena_cap) return bail(fail(ctx, FLACB200_ERR_ARG, "arena too small"));
-        if (bytes) CKJ(cudaMemcpyAsync(arena + host_base[c], (const uint8_t*)ctx->d_arena.p + dev_base[c], bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (bytes) CKJ(cudaMemcpyAsync(arena + host_base[c], (const uint8_t*)ctx->set().arena.p + dev_base[c], bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
         host_base[c + 1] = host_base[c] + bytes;
     }
     ctx->e2e_ms[2] = since();
     std::vector<uint64_t> tmp_off;
     uint64_t* foff_host = frame_off;
     if (!foff_host) { tmp_off.resize(nf); foff_host = tmp_off.data(); }
-    CKJ(cudaMemcpyAsync(foff_host, ctx->d_foff.p, sizeof(uint64_t) * nf, cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    if (frame_len) CKJ(cudaMemcpyAsync(frame_len, ctx->d_flen.p, sizeof(uint32_t) * nf, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CKJ(cudaMemcpyAsync(foff_host, ctx->set().foff.p, sizeof(uint64_t) * nf, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (frame_len) CKJ(cudaMemcpyAsync(frame_len, ctx->set().flen.p, sizeof(uint32_t) * nf, cudaMemcpyDeviceToHost, ctx->d2h_stream));
     std::vector<flacb200_stream_info> tmp_info;
     flacb200_stream_info* info_host = streams;
     if (!info_host) { tmp_info.resize(ns); info_host = tmp_info.data(); }
-    CKJ(cudaMemcpyAsync(info_host, ctx->d_sinfo.p, sizeof(StreamInfoOut) * ns, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CKJ(cudaMemcpyAsync(info_host, ctx->set().sinfo.p, sizeof(StreamInfoOut) * ns, cudaMemcpyDeviceToHost, ctx->d2h_stream));
     CKJ(cudaStreamSynchronize(ctx->d2h_stream));
     CKJ(cudaGetLastError());
 #undef CKJ

@@ -80,3 +80,18 @@ def test_encode_decode_roundtrip_full_size(eng):
     out, infos = nat.decode_streams(eng, blobs)
     for x, o, si in zip(xs, out, infos):
         assert si.status == 0 and si.n_frames == 32 and np.array_equal(o, x)
+
+
+def test_full_size_config4_decode_4096_streams(eng):
+    """BASELINE configs[3] shape: 4096 stereo s16 streams of 131072 samples -> int16 PCM (64 distinct, tiled)."""
+    from pyflac_b200 import _native as nat
+    uniq = [music_like(131072, 2, 48000, 16, seed=700 + s) for s in range(64)]
+    blobs64, _ = nat.encode_streams(eng, uniq, 48000, 16, 5, 4096)
+    blobs = blobs64 * 64
+    out, infos = nat.decode_streams(eng, blobs, 2)
+    assert len(out) == 4096
+    assert all(si.status == 0 and si.n_frames == 32 and si.total_samples == 131072 for si in infos)
+    for s in range(0, 4096, 97):
+        assert np.array_equal(out[s], uniq[s % 64])
+    total = sum(int(si.total_samples) for si in infos)
+    assert total == 4096 * 131072

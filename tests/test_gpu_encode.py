@@ -118,3 +118,34 @@ def test_full_size_properties(eng, checkers):
         dec, info = checkers.oracle_decode(blob)                    # validates every CRC-8/CRC-16 and the MD5
         assert np.array_equal(dec, pcm[s].astype(np.int32))
         assert blob == checkers.oracle_encode(pcm[s], 48000, 16, 5, 4096)
+
+
+def test_full_size_config3_24bit_mono_level8(eng, checkers):
+    """BASELINE configs[2] shape: 4096 streams x 262144 mono 24-bit (int32 container), 192 kHz, level 8.
+    64 distinct streams tiled 64x (identical streams must give identical bytes); properties on the whole batch,
+    byte equality with the oracle + decode round trip on samples."""
+    from pyflac_b200 import _native as nat
+    uniq = [music_like(262144, 1, 192000, 24, seed=900 + s) for s in range(64)]
+    pcm = np.concatenate([u.reshape(-1) for u in uniq] * 64)
+    n_streams = 4096
+    off = np.arange(n_streams, dtype=np.uint64) * np.uint64(262144)
+    cfg = nat.Engine.make_config(192000, 1, 24, 8, 4096, container_bytes=4)
+    eng.encode_host(cfg, pcm, off, np.full(n_streams, 262144, np.uint64))
+    out = eng.fetch()
+    assert out["log_guard_hits"] == 0
+    assert len(out["frame_len"]) == n_streams * 64
+    arena = out["arena"]
+    blobs = [arena[int(si.byte_off): int(si.byte_off + si.byte_len)] for si in out["streams"]]
+    for s in range(64):                                                   # the 64 tiles of each distinct stream are identical
+        for k in range(1, 64, 21):
+            assert np.array_equal(blobs[s], blobs[s + 64 * k])
+    for s in (0, 31, 63):
+        b = blobs[s].tobytes()
+        assert b == checkers.oracle_encode(uniq[s], 192000, 24, 8, 4096)
+        dec, info = checkers.oracle_decode(b)
+        assert info["bps"] == 24 and np.array_equal(dec, uniq[s].astype(np.int32))
+    import hashlib
+    for s in (5, 4095):
+        x = uniq[s % 64].astype("<i4").tobytes()
+        le24 = b"".join(x[i:i + 3] for i in range(0, len(x), 4))
+        assert bytes(out["streams"][s].md5) == hashlib.md5(le24).digest()
