@@ -30,17 +30,46 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _deps_mtime():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    inc = os.path.join(HERE, "..", "include")
+    deps += [os.path.join(inc, f) for f in os.listdir(inc)]
+    return max(os.path.getmtime(d) for d in deps)
+
+
 def build(force=False, verbose=False):
+    """One nvcc -c per source (in parallel, objects cached under csrc/_obj), then one link."""
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources() + ["-lpthread"]
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f not in ("-shared",)]
+    cflags = cflags[:cflags.index("-cudart")]          # link-only flags stay out of the compile step
+    hdr_t = _deps_mtime()
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, ""
+        cmd = [nvcc] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed on " + src)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        res = list(ex.map(compile_one, sources()))
+    if verbose:
+        for _, log in res:
+            print(log)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB] + [o for o, _ in res] + ["-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libflacb200.so")
-    if verbose:
-        print(r.stderr)
+        raise RuntimeError("nvcc failed linking libflacb200.so")
     return LIB
 
 

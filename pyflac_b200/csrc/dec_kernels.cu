@@ -434,7 +434,7 @@ dec_post_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ s
                 const uint64_t* __restrict__ slot_off, const int32_t* __restrict__ samples, DecStreamResult* __restrict__ res,
                 OutT* __restrict__ pcm_out) {
     __shared__ uint16_t crc_tab[256];
-    __shared__ uint16_t crc_warp[8];
+    __shared__ uint32_t crc_warp[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DecCand c = cands[blockIdx.x];
     if (!c.valid) return;
@@ -447,35 +447,9 @@ dec_post_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ s
     __syncthreads();
     const uint8_t* fb = blob + stream_off[c.stream] + c.pos;
     const uint32_t nb = c.end_pos - c.pos - 2u;
-    const uint32_t csize = 64u * ((nb + 64u * 256u - 1u) / (64u * 256u)), nchunks = (nb + csize - 1u) / csize;
-    uint16_t xs;
-    { uint16_t result = 1, basep = 2; uint32_t e = 8u * csize; while (e) { if (e & 1u) result = crc16_mulmod(result, basep); basep = crc16_mulmod(basep, basep); e >>= 1; } xs = result; }
-    uint16_t crc = 0;
     {
-        const int tt = tid - (int)(256u - nchunks);
-        if (tt >= 0) {
-            const long long end = (long long)nb - (long long)(nchunks - 1u - (uint32_t)tt) * csize;
-            long long beg = end - csize; if (beg < 0) beg = 0;
-            for (long long j = beg; j < end; j++) crc = (uint16_t)((crc << 8) ^ crc_tab[(crc >> 8) ^ __ldg(fb + j)]);
-        }
-    }
-#pragma unroll
-    for (int s = 1; s < 32; s <<= 1) {
-        const uint16_t other = (uint16_t)__shfl_down_sync(0xffffffffu, (uint32_t)crc, s);
-        if ((lane & (2 * s - 1)) == 0) crc = (uint16_t)(crc16_mulmod(crc, xs) ^ other);
-        xs = crc16_mulmod(xs, xs);
-    }
-    if (lane == 0) crc_warp[warp] = crc;
-    __syncthreads();
-    if (warp == 0) {
-        uint16_t c2 = lane < 8 ? crc_warp[lane] : (uint16_t)0;
-#pragma unroll
-        for (int s = 1; s < 8; s <<= 1) {
-            const uint16_t other = (uint16_t)__shfl_down_sync(0xffffffffu, (uint32_t)c2, s);
-            if ((lane & (2 * s - 1)) == 0) c2 = (uint16_t)(crc16_mulmod(c2, xs) ^ other);
-            xs = crc16_mulmod(xs, xs);
-        }
-        if (lane == 0) {
+        const uint16_t c2 = cta_crc16<256>([&](uint32_t j) { return __ldg(fb + j); }, nb, crc_tab, crc_warp, tid);
+        if (tid == 0) {
             const uint16_t stored = (uint16_t)((uint16_t)fb[nb] << 8 | fb[nb + 1]);
             if (c2 != stored) { res[c.stream].status = kDecCrcMismatch; cands[blockIdx.x].status = kDecCrcMismatch; }
         }

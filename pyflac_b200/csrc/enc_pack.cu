@@ -24,7 +24,7 @@ struct PackShared {
     uint32_t segtot[kPackWarps];         // code bits produced by each warp in the current tile
     int32_t  sigidx[kMaxChannels];       // which analysed signal is coded as channel c
     uint16_t crc_tab[256];
-    uint16_t crc_warp[kPackWarps];
+    uint32_t crc_warp[kPackWarps];
     uint8_t  hdr[16];
     uint32_t hdr_len, x1;
 };
@@ -264,46 +264,10 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
 
     // ---- CRC-16 over the byte-padded frame, append, store ----
     const uint32_t nb = (pos + 7u) >> 3;
-    const uint32_t csize = 64u * ((nb + 64u * kPackThreads - 1u) / (64u * kPackThreads));   // bytes per chunk, <= 256 chunks
-    const uint32_t nchunks = (nb + csize - 1u) / csize;
-    uint16_t xs;
-    {   // x^(8*csize) mod P by square-and-multiply (uniform, every thread computes it)
-        uint16_t result = 1, basep = 2; uint32_t e = 8u * csize;
-        while (e) { if (e & 1u) result = crc16_mulmod(result, basep); basep = crc16_mulmod(basep, basep); e >>= 1; }
-        xs = result;
-    }
-    uint16_t crc = 0;
     {
-        // chunk boundaries are aligned from the END of the frame (leading zero bytes do not change a CRC with init 0);
-        // thread t owns chunk t - (256 - nchunks); lower threads own virtual empty chunks
-        const int t = tid - (int)(kPackThreads - nchunks);
-        if (t >= 0) {
-            const long long end = (long long)nb - (long long)(nchunks - 1u - (uint32_t)t) * csize;
-            long long beg = end - csize; if (beg < 0) beg = 0;
-            for (long long j = beg; j < end; j++) {
-                const uint8_t bb = (uint8_t)(obuf[j >> 2] >> (24 - 8 * (int)(j & 3)));
-                crc = (uint16_t)((crc << 8) ^ S.crc_tab[(crc >> 8) ^ bb]);
-            }
-        }
-    }
-    // combine: crc(A||B) = crc(A) * x^(8|B|) + crc(B) in GF(2)[x]/(x^16+x^15+x^2+1); tree over lanes, then over warps
-#pragma unroll
-    for (int s = 1; s < 32; s <<= 1) {
-        const uint16_t other = (uint16_t)__shfl_down_sync(0xffffffffu, (uint32_t)crc, s);
-        if ((lane & (2 * s - 1)) == 0) crc = (uint16_t)(crc16_mulmod(crc, xs) ^ other);
-        xs = crc16_mulmod(xs, xs);
-    }
-    if (lane == 0) S.crc_warp[warp] = crc;
-    __syncthreads();
-    if (warp == 0) {
-        uint16_t c2 = lane < kPackWarps ? S.crc_warp[lane] : (uint16_t)0;
-#pragma unroll
-        for (int s = 1; s < kPackWarps; s <<= 1) {
-            const uint16_t other = (uint16_t)__shfl_down_sync(0xffffffffu, (uint32_t)c2, s);
-            if ((lane & (2 * s - 1)) == 0) c2 = (uint16_t)(crc16_mulmod(c2, xs) ^ other);
-            xs = crc16_mulmod(xs, xs);
-        }
-        if (lane == 0) put_bits(obuf, nb * 8u, c2, 16);
+        const uint16_t c2 = cta_crc16<kPackThreads>([&](uint32_t j) { return (uint8_t)(obuf[j >> 2] >> (24 - 8 * (int)(j & 3u))); },
+                                                    nb, S.crc_tab, S.crc_warp, tid);
+        if (tid == 0) put_bits(obuf, nb * 8u, c2, 16);
     }
     __syncthreads();
     {

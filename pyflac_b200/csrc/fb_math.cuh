@@ -184,6 +184,58 @@ FB_HD uint16_t crc16_mulmod(uint16_t a, uint16_t b) {
     return (uint16_t)r;
 }
 
+#if defined(__CUDACC__)
+// Positional weights for a CTA-parallel CRC-16: the frame is cut into 64-byte chunks counted from its END,
+// chunk j's CRC is multiplied by x^(512 j) mod P (so that it stands where the chunk stands) and everything is
+// XORed: crc(A||B) = crc(A) * x^(8|B|) + crc(B).  lo[j] = x^(512 j), j < 256; hi[h] = x^(512*256*h), h < 16.
+// Built at compile time; one mulmod per chunk instead of a log-depth tree of them.
+struct CrcPosTable { uint16_t lo[256]; uint16_t hi[16]; };
+constexpr uint16_t crc16_mulmod_c(uint16_t a, uint16_t b) {
+    uint32_t r = 0;
+    for (int i = 15; i >= 0; i--) { r <<= 1; if (r & 0x10000u) r ^= 0x18005u; if ((b >> i) & 1) r ^= a; }
+    return (uint16_t)r;
+}
+constexpr CrcPosTable make_crc_pos_table() {
+    CrcPosTable t{};
+    uint16_t x512 = 2;
+    for (int i = 0; i < 9; i++) x512 = crc16_mulmod_c(x512, x512);
+    t.lo[0] = 1;
+    for (int j = 1; j < 256; j++) t.lo[j] = crc16_mulmod_c(t.lo[j - 1], x512);
+    const uint16_t step_hi = crc16_mulmod_c(t.lo[255], x512);
+    t.hi[0] = 1;
+    for (int j = 1; j < 16; j++) t.hi[j] = crc16_mulmod_c(t.hi[j - 1], step_hi);
+    return t;
+}
+static __device__ const CrcPosTable g_crc_pos = make_crc_pos_table();
+
+// CRC-16 (poly 0x8005, init 0) of nb bytes by a whole CTA of THREADS threads.  byte_at(j) returns byte j;
+// crc_tab is the 256-entry byte table in shared memory; warp_x is THREADS/32 words of shared scratch.
+// The result is valid on warp 0 (all lanes) after the call; contains one __syncthreads().
+template <int THREADS, typename ByteAt>
+__device__ __forceinline__ uint16_t cta_crc16(ByteAt byte_at, uint32_t nb, const uint16_t* crc_tab, uint32_t* warp_x, int tid) {
+    const uint32_t nchunks = (nb + 63u) >> 6;
+    uint32_t acc = 0;
+    for (uint32_t j = (uint32_t)tid; j < nchunks; j += THREADS) {          // j counts chunks from the end of the frame
+        const uint32_t end = nb - (j << 6);
+        const uint32_t beg = end >= 64u ? end - 64u : 0u;
+        uint16_t crc = 0;
+        for (uint32_t b = beg; b < end; b++) crc = (uint16_t)((crc << 8) ^ crc_tab[(crc >> 8) ^ byte_at(b)]);
+        if (j) crc = crc16_mulmod(crc, g_crc_pos.lo[j & 255u]);
+        if (j >> 8) crc = crc16_mulmod(crc, g_crc_pos.hi[(j >> 8) & 15u]);
+        acc ^= crc;
+    }
+    acc = __reduce_xor_sync(0xffffffffu, acc);
+    if ((tid & 31) == 0) warp_x[tid >> 5] = acc;
+    __syncthreads();
+    uint32_t r = 0;
+    if (tid < 32) {
+        r = (tid < THREADS / 32) ? warp_x[tid] : 0u;
+        r = __reduce_xor_sync(0xffffffffu, r);
+    }
+    return (uint16_t)r;
+}
+#endif
+
 // ---------------------------------------------------------------- frame header ----
 // up: stream_encoder_framing.c FLAC__frame_add_header (ref: format.h:416-462).
 // Writes at most 16 bytes (incl. CRC-8) into out[], returns the byte count.

@@ -9,7 +9,7 @@ fname = ""
 agg = {}
 hdr = None
 for r in rows:
-    if len(r) >= 2 and r[0] == "File Name":
+    if len(r) >= 2 and r[0] in ("File Name", "File Path"):
         fname = r[1].split("/")[-1]
         continue
     if len(r) > 8 and r[0] == "Line No":
