@@ -45,7 +45,7 @@ enum {
 typedef struct {
     uint32_t sample_rate;
     uint32_t channels;
-    uint32_t bits_per_sample;     /* 8..24 in this build */
+    uint32_t bits_per_sample;     /* 4..24 in this build */
     uint32_t compression_level;   /* 0..8 */
     uint32_t blocksize;           /* 0 = libFLAC default (1152 for levels 0-2, else 4096) */
     uint32_t container_bytes;     /* PCM element size in memory: 2 (int16, bps<=16) or 4 (int32) */
@@ -53,6 +53,7 @@ typedef struct {
     uint32_t do_md5;              /* 1: STREAMINFO carries the MD5 of the PCM (libFLAC default) */
     uint32_t streamable_subset;   /* validation only (stream_encoder.h:1005-1017) */
     uint32_t debug_trace;         /* 1: keep per-signal analysis traces (tests) */
+    uint32_t limit_min_bitrate;   /* FLAC__stream_encoder_set_limit_min_bitrate (stream_encoder.h:1105-1115) */
 } flacb200_enc_config;
 
 typedef struct {
@@ -100,6 +101,14 @@ int  flacb200_encode_batch(flacb200_ctx *ctx, const flacb200_enc_config *cfg,
                            const void *pcm, int pcm_is_device, uint64_t pcm_elems,
                            uint32_t n_streams, const uint64_t *stream_off, const uint64_t *stream_samples,
                            const uint32_t *first_frame_number);
+/* Loose mid/side (compression levels 1 and 4 on stereo, stream_encoder.h:881-909) decides between independent and
+ * mid/side coding once every round(0.4 s) of frames and the frames in between follow that decision.  A batch whose
+ * streams continue earlier batches (first_frame_number not a multiple of that period) needs each stream's channel
+ * assignment of the frame before the batch: prev_assignment[s] in 0..3 (format.h:388-393 order).  Applies to the
+ * next flacb200_encode_batch call only; NULL / not called = every stream starts at a decision frame or with 0. */
+int  flacb200_encode_set_prev_assignment(flacb200_ctx *ctx, const uint8_t *prev_assignment, uint32_t n_streams);
+/* Channel assignment chosen for every frame of the last batch (n_frames bytes). */
+int  flacb200_encode_fetch_assignments(flacb200_ctx *ctx, uint8_t *frame_ca, size_t cap);
 /* Synchronises, then reports sizes and device pointers. */
 int  flacb200_encode_result(flacb200_ctx *ctx, flacb200_enc_result *res);
 /* Copy results to host memory (any pointer may be NULL). arena_cap in bytes. */

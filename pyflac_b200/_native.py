@@ -27,7 +27,7 @@ class EncConfig(C.Structure):
     _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32),
                 ("compression_level", C.c_uint32), ("blocksize", C.c_uint32), ("container_bytes", C.c_uint32),
                 ("write_prologue", C.c_uint32), ("do_md5", C.c_uint32), ("streamable_subset", C.c_uint32),
-                ("debug_trace", C.c_uint32)]
+                ("debug_trace", C.c_uint32), ("limit_min_bitrate", C.c_uint32)]
 
 
 class StreamInfo(C.Structure):
@@ -85,6 +85,8 @@ def lib():
     L.flacb200_encode_batch.argtypes = [C.c_void_p, C.POINTER(EncConfig), C.c_void_p, C.c_int, C.c_uint64, C.c_uint32,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
     L.flacb200_encode_result.argtypes = [C.c_void_p, C.POINTER(EncResult)]
+    L.flacb200_encode_set_prev_assignment.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.flacb200_encode_fetch_assignments.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.flacb200_encode_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
     L.flacb200_encode_fetch_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -153,11 +155,11 @@ class Engine:
     # ------------------------------------------------------------ encode
     @staticmethod
     def make_config(sample_rate, channels, bits_per_sample, compression_level=5, blocksize=0, container_bytes=None,
-                    write_prologue=True, do_md5=True, streamable_subset=True, debug_trace=False):
+                    write_prologue=True, do_md5=True, streamable_subset=True, debug_trace=False, limit_min_bitrate=False):
         if container_bytes is None:
             container_bytes = 2 if bits_per_sample <= 16 else 4
         return EncConfig(sample_rate, channels, bits_per_sample, compression_level, blocksize, container_bytes,
-                         int(write_prologue), int(do_md5), int(streamable_subset), int(debug_trace))
+                         int(write_prologue), int(do_md5), int(streamable_subset), int(debug_trace), int(limit_min_bitrate))
 
     def encode_device(self, cfg, pcm_ptr, pcm_elems, stream_off, stream_samples, first_frame_number=None):
         """Asynchronous batch encode of PCM resident in HBM. stream_off/stream_samples: uint64 numpy arrays."""

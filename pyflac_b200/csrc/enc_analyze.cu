@@ -259,13 +259,25 @@ template <typename PcmT>
 __global__ void __launch_bounds__(32 * kMaxSignals, 1)
 analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, const float* __restrict__ windows,
                EncParams P, SubframePlan* __restrict__ plans, uint8_t* __restrict__ frame_ca,
-               SignalDebug* __restrict__ dbg, EncStats* __restrict__ stats) {
+               SignalDebug* __restrict__ dbg, EncStats* __restrict__ stats, int pass) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, sig = threadIdx.x >> 5;
     const int nsig = (int)P.n_signals;
     const FrameDesc fd = frames[blockIdx.x];
     const int N = (int)fd.blocksize;
     const int ch = (int)P.channels;
+    // up: process_subframes_ loose_mid_side_stereo -- decision frames (pass 0) analyse L, R, M, S and choose between
+    // independent and mid/side only; the frames that follow (pass 1) analyse just the pair that decision picked.
+    int mode = 0;                           // 0 = all signals, 1 = independent channels only, 2 = mid/side only
+    if (P.loose_frames) {
+        if (fd.lead == 0u) { if (pass != 0) return; }
+        else {
+            if (pass == 0) return;
+            const int pca = (fd.lead & kLeadForced) ? (int)(fd.lead & 3u) : (int)frame_ca[blockIdx.x - fd.lead];
+            mode = (pca == 0) ? 1 : 2;
+        }
+    }
+    const bool active = mode == 0 || (mode == 1 ? sig < ch : sig >= ch);
 
     int32_t* xall = reinterpret_cast<int32_t*>(smem_raw);
     // [signals | pool: partition sums (phases 1,3) aliased with the autocorrelation rings (phase 2) | per-warp scratch | ...]
@@ -279,6 +291,7 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
     int* need_list = reinterpret_cast<int*>(sig_bits + kMaxSignals);           // signals that go through LPC analysis
     int* need_flag = need_list + kMaxSignals;
     int* nneed_p = need_flag + kMaxSignals;
+    int* const_flag = nneed_p + 4;
 
     int32_t* x = xall + (size_t)sig * P.smem_stride;
     WarpScratch& ws = wsall[sig];
@@ -287,7 +300,7 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
     // =================== phase 1 (one warp per signal): load, wasted bits, fixed predictors ===================
     // up: process_subframes_ + get_wasted_bits_
     uint32_t orv = 0;
-    {
+    if (active) {
         const PcmT* base = pcm + fd.pcm_off;
         for (int i = lane; i < N; i += 32) {
             int v;
@@ -324,8 +337,10 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
     const int omax_frame = min((int)P.max_part_order, N ? (__ffs(N) - 1) : 0);
     const int max_lpc = (N > 4 && P.max_lpc_order > 0) ? (((int)P.max_lpc_order >= N) ? N - 1 : (int)P.max_lpc_order) : 0;
     bool want_lpc = false;
+    bool constant = false;
+    int forder = 0;
 
-    if (N > 4) {
+    if (active && N > 4) {
         // fixed predictor error sums (up: fixed.c FLAC__fixed_compute_best_predictor[_wide])
         unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
         for (int i = 4 + lane; i < N; i += 32) {
@@ -341,16 +356,25 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
         if ((uint32_t)sbps + ilog2_u32((uint32_t)N - 4u) + 1u < 32u) {   // libFLAC's 32-bit accumulators wrap
             e0 &= 0xffffffffull; e1 &= 0xffffffffull; e2 &= 0xffffffffull; e3 &= 0xffffffffull; e4 &= 0xffffffffull;
         }
-        int forder;
         {
             const unsigned long long m34 = min(e3, e4), m234 = min(e2, m34), m1234 = min(e1, m234);
             if (e0 <= m1234) forder = 0; else if (e1 <= m234) forder = 1; else if (e2 <= m34) forder = 2; else if (e3 <= e4) forder = 3; else forder = 4;
         }
-        bool constant = false;
         if (e1_true == 0) constant = (x[0] == x[1]) && (x[1] == x[2]) && (x[2] == x[3]) && (x[3] == x[4]);   // samples 3..N-1 are equal already
         if (dg && lane == 0) { dg->fixed_err[0] = e0; dg->fixed_err[1] = e1; dg->fixed_err[2] = e2; dg->fixed_err[3] = e3; dg->fixed_err[4] = e4; dg->fixed_order = forder; dg->is_constant = constant; }
 
-        if (constant) {
+    }
+    // up: process_subframes_ limit_min_bitrate -- when every earlier channel came out constant, the last channel
+    // (and mid/side after it) may not use a constant subframe, so the frame never shrinks to headers only
+    if (lane == 0) const_flag[sig] = constant ? 1 : 0;
+    __syncthreads();
+    bool disable_const = false;
+    if (P.limit_min_bitrate && mode != 2 && sig >= ch - 1) {
+        disable_const = true;
+        for (int c2 = 0; c2 < ch - 1; c2++) if (!const_flag[c2]) disable_const = false;
+    }
+    if (active && N > 4) {
+        if (constant && !disable_const) {
             const uint32_t bits = 8u + (uint32_t)wasted + (uint32_t)sbps;     // up: evaluate_constant_subframe_
             if (bits < best_bits) { best_bits = bits; if (lane == 0) { ws.plan.type = kConstant; ws.plan.bits_est = bits; } }
         } else {
@@ -531,7 +555,10 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
     // ---- channel assignment (up: process_subframes_): first minimum of {L+R, L+S, R+S, M+S} ----
     if (threadIdx.x == 0) {
         int ca = 0;
-        if (P.do_mid_side) {
+        if (P.loose_frames) {
+            if (mode == 0) ca = (sig_bits[2] + sig_bits[3] < sig_bits[0] + sig_bits[1]) ? 3 : 0;
+            else ca = (mode == 1) ? 0 : 3;
+        } else if (P.do_mid_side) {
             const uint32_t bL = sig_bits[0], bR = sig_bits[1], bM = sig_bits[2], bS = sig_bits[3];
             uint32_t minb = bL + bR;
             if (bL + bS < minb) { minb = bL + bS; ca = 1; }
@@ -547,12 +574,15 @@ void launch_analyze(const void* pcm, const FrameDesc* frames, const float* windo
                     SubframePlan* plans, uint8_t* frame_ca, SignalDebug* dbg, EncStats* stats, size_t smem_bytes,
                     cudaStream_t stream) {
     const dim3 grid((unsigned)n_frames), block(32u * P.n_signals);
-    if (P.container_bytes == 2) {
-        cudaFuncSetAttribute(analyze_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        analyze_kernel<int16_t><<<grid, block, smem_bytes, stream>>>((const int16_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats);
-    } else {
-        cudaFuncSetAttribute(analyze_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        analyze_kernel<int32_t><<<grid, block, smem_bytes, stream>>>((const int32_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats);
+    // loose mid/side: decision frames first, then the frames that follow them (they read the decision from frame_ca)
+    for (int pass = 0; pass < (P.loose_frames ? 2 : 1); pass++) {
+        if (P.container_bytes == 2) {
+            cudaFuncSetAttribute(analyze_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            analyze_kernel<int16_t><<<grid, block, smem_bytes, stream>>>((const int16_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats, pass);
+        } else {
+            cudaFuncSetAttribute(analyze_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            analyze_kernel<int32_t><<<grid, block, smem_bytes, stream>>>((const int32_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats, pass);
+        }
     }
 }
 
@@ -575,7 +605,7 @@ void analyze_layout(EncParams& P) {
 
 size_t analyze_smem_bytes(const EncParams& P) {
     return (size_t)P.n_signals * P.smem_stride * 4 + P.pool_bytes + (size_t)P.n_signals * sizeof(WarpScratch) +
-           (size_t)P.n_signals * (P.apod_parts * (P.apod_parts + 1) / 2) * kAcStoreStride * sizeof(double) + kMaxSignals * 4 * 3 + 64;
+           (size_t)P.n_signals * (P.apod_parts * (P.apod_parts + 1) / 2) * kAcStoreStride * sizeof(double) + kMaxSignals * 4 * 4 + 64;
 }
 
 }  // namespace fb

@@ -74,6 +74,8 @@ struct flacb200_ctx {
     std::vector<uint32_t> h_stream_first, h_stream_nframes;
     std::vector<uint64_t> h_stream_off, h_stream_samples;
     std::vector<uint32_t> h_first_frame;
+    std::vector<uint8_t> prev_ca;              // loose mid/side: channel assignment before the batch, per stream (one-shot)
+    bool prev_ca_pending = false;
     std::vector<float> h_windows;
     std::map<uint32_t, uint32_t> window_off;   // blocksize -> float offset in h_windows
     float window_p = -1.0f;
@@ -165,8 +167,13 @@ static int resolve_params(flacb200_ctx* ctx, const flacb200_enc_config& c, EncPa
         const uint32_t b = P.blocksize;
         P.qlp_precision = b <= 384 ? 13 : b <= 1152 ? 14 : 15;
     }
+    // up: FLAC__stream_encoder_init_*: loose_mid_side_stereo_frames = (uint32_t)(sample_rate * 0.4 / blocksize + 0.5), at least 1
+    if (kLevels[lvl].loose && P.do_mid_side) {
+        P.loose_frames = (uint32_t)((double)c.sample_rate * 0.4 / (double)P.blocksize + 0.5);
+        if (P.loose_frames == 0) P.loose_frames = 1;
+    }
+    P.limit_min_bitrate = c.limit_min_bitrate ? 1u : 0u;
     // limits of this build (DESIGN.md "limits")
-    if (kLevels[lvl].loose && c.channels == 2) return fail(ctx, FLACB200_ERR_UNSUPPORTED, "loose mid/side (levels 1 and 4 on stereo) not built yet");
     if (c.bits_per_sample > 24) return fail(ctx, FLACB200_ERR_UNSUPPORTED, "bits_per_sample > 24 not built yet");
     if (c.container_bytes != 2 && c.container_bytes != 4) return fail(ctx, FLACB200_ERR_ARG, "container_bytes must be 2 or 4");
     if (c.container_bytes == 2 && c.bits_per_sample > 16) return fail(ctx, FLACB200_ERR_ARG, "int16 container needs bits_per_sample <= 16");
@@ -322,7 +329,12 @@ static int plan_batch(flacb200_ctx* ctx, const flacb200_enc_config& cfg, uint32_
             const uint32_t N = (smp[s] - done >= P.blocksize) ? P.blocksize : (uint32_t)(smp[s] - done);
             FrameDesc fd;
             fd.pcm_off = off[s] + done * P.channels;
-            fd.blocksize = N; fd.frame_number = fn++; fd.stream = s; fd.window_off = 0;
+            fd.blocksize = N; fd.frame_number = fn; fd.stream = s; fd.window_off = 0; fd.lead = 0; fd.pad = 0;
+            if (P.loose_frames) {
+                const uint32_t phase = fn % P.loose_frames, k = fn - ctx->h_first_frame[s];     // k = index within this batch
+                if (phase != 0) fd.lead = (k >= phase) ? phase : (kLeadForced | (ctx->prev_ca.size() > s ? (ctx->prev_ca[s] & 3u) : 0u));
+            }
+            fn++;
             if (P.max_lpc_order > 0) {
                 auto it = ctx->window_off.find(N);
                 if (it == ctx->window_off.end()) {
@@ -339,6 +351,7 @@ static int plan_batch(flacb200_ctx* ctx, const flacb200_enc_config& cfg, uint32_
         }
         ctx->h_stream_nframes[s] = (uint32_t)ctx->h_frames.size() - ctx->h_stream_first[s];
     }
+    ctx->prev_ca.clear(); ctx->prev_ca_pending = false;       // one-shot: the next batch starts fresh unless set again
     ctx->P = P; ctx->cfg = cfg; ctx->n_streams = (int)ns; ctx->n_frames = (int)ctx->h_frames.size();
     ctx->scratch_stride = max_frame_bytes(P);
     ctx->debug = cfg.debug_trace != 0;
@@ -432,7 +445,7 @@ static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
                     (StreamInfoOut*)S.sinfo.p, fs);
     if (prof) CK(cudaEventRecord(ctx->ev_k[5], fs));
     if (md5) { CK(cudaEventRecord(S.ev_free, S.side)); S.busy = true; }
-    ctx->launches += 5;
+    ctx->launches += 5 + (P.loose_frames ? 1 : 0);
     CK(cudaGetLastError());
     return 0;
 }
@@ -445,7 +458,7 @@ extern "C" int flacb200_encode_batch(flacb200_ctx* ctx, const flacb200_enc_confi
     cudaSetDevice(ctx->device);
     for (uint32_t s = 0; s < n_streams; s++)
         if (stream_off[s] + stream_samples[s] * cfg->channels > pcm_elems) return fail(ctx, FLACB200_ERR_ARG, "stream exceeds pcm buffer");
-    if (!same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, first_frame_number)) {
+    if (ctx->prev_ca_pending || !same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, first_frame_number)) {
         ctx->have_batch = false;
         for (auto& S : ctx->sets) if (S.busy) { CK(cudaStreamSynchronize(S.side)); S.busy = false; }
         int rc = plan_batch(ctx, *cfg, n_streams, stream_off, stream_samples, first_frame_number);
@@ -459,6 +472,26 @@ extern "C" int flacb200_encode_batch(flacb200_ctx* ctx, const flacb200_enc_confi
         d_pcm = ctx->d_pcm.p;
     }
     return run_batch(ctx, d_pcm);
+}
+
+extern "C" int flacb200_encode_set_prev_assignment(flacb200_ctx* ctx, const uint8_t* prev, uint32_t n_streams) {
+    if (!ctx) return FLACB200_ERR_NO_DEVICE;
+    ctx->prev_ca.clear();
+    if (prev) ctx->prev_ca.assign(prev, prev + n_streams);
+    ctx->prev_ca_pending = true;           // forces a re-plan: the cached layout may carry other forced decisions
+    return 0;
+}
+
+extern "C" int flacb200_encode_fetch_assignments(flacb200_ctx* ctx, uint8_t* frame_ca, size_t cap) {
+    if (!ctx || !frame_ca) return FLACB200_ERR_ARG;
+    if (!ctx->have_batch) return fail(ctx, FLACB200_ERR_ARG, "no batch");
+    if (cap < (size_t)ctx->n_frames) return fail(ctx, FLACB200_ERR_ARG, "assignment buffer too small");
+    cudaSetDevice(ctx->device);
+    if (ctx->n_frames) {
+        CK(cudaMemcpyAsync(frame_ca, ctx->d_ca.p, (size_t)ctx->n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
 }
 
 extern "C" int flacb200_encode_result(flacb200_ctx* ctx, flacb200_enc_result* res) {
@@ -529,7 +562,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     cudaSetDevice(ctx->device);
     for (uint32_t s = 0; s < n_streams; s++)
         if (stream_off[s] + stream_samples[s] * cfg->channels > pcm_elems) return fail(ctx, FLACB200_ERR_ARG, "stream exceeds pcm buffer");
-    if (!same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr)) {
+    if (ctx->prev_ca_pending || !same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr)) {
         ctx->have_batch = false;
         for (auto& S : ctx->sets) if (S.busy) { CK(cudaStreamSynchronize(S.side)); S.busy = false; }
         int rc = plan_batch(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr);
@@ -636,7 +669,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
             launch_finalize((const uint32_t*)ctx->set().flen.p, (const uint64_t*)ctx->set().foff.p, (const uint32_t*)ctx->d_sfirst.p + s0,
                             (const uint32_t*)ctx->d_snframes.p + s0, (const uint64_t*)ctx->d_ssamples.p + s0, nullptr, cns, P, pro ? 1u : 0u,
                             (uint8_t*)ctx->set().arena.p, (StreamInfoOut*)ctx->set().sinfo.p + s0, st);
-            ctx->launches += 5;
+            ctx->launches += 5 + (P.loose_frames ? 1 : 0);
         } else {
             CKJ(cudaMemsetAsync((uint64_t*)ctx->d_totals.p + c, 0, 8, st));
         }

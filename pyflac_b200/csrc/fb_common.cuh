@@ -35,6 +35,8 @@ struct EncParams {
     uint32_t smem_stride;        // int32 words reserved per signal in shared memory (>= max blocksize, multiple of 4)
     uint32_t pool_bytes;         // analysis kernel: partition-sum area aliased with the autocorrelation rings
     uint32_t ac_gsz;             // analysis kernel: (signal, window) jobs packed per warp in the autocorrelation phase
+    uint32_t loose_frames;       // loose mid/side (levels 1, 4 on stereo): a full L/R/M/S decision every this many frames; 0 = off
+    uint32_t limit_min_bitrate;  // up: process_subframes_ -- never emit a frame made of constant subframes only
 };
 
 struct FrameDesc {
@@ -43,7 +45,12 @@ struct FrameDesc {
     uint32_t frame_number;
     uint32_t window_off;         // float offset of this blocksize's window in the window table
     uint32_t stream;
+    // loose mid/side: 0 = this frame makes the decision (full analysis); k > 0 = follow the channel assignment of the
+    // frame k places earlier in the batch; kLeadForced | ca = follow a decision made before this batch
+    uint32_t lead;
+    uint32_t pad;
 };
+constexpr uint32_t kLeadForced = 0x80000000u;
 
 // What the analysis kernel decides for one signal and the pack kernel turns into bits.
 struct alignas(16) SubframePlan {

@@ -111,6 +111,7 @@ struct EncImpl {
     uint32_t N = 0;                        // resolved blocksize
     std::vector<int32_t> pending;          // interleaved samples not yet framed
     uint32_t frame_number = 0;
+    uint8_t last_ca = 0;                   // loose mid/side: channel assignment of the last frame delivered
     uint64_t samples_written = 0, bytes_written = 0;
     uint32_t min_fs = 0, max_fs = 0, frames_written = 0;
     uint64_t streaminfo_offset = 0;        // byte position of the STREAMINFO block header as told by the tell callback
@@ -174,7 +175,10 @@ bool encode_pending(FLAC__StreamEncoder* e, uint64_t n) {
     cfg.sample_rate = m->sample_rate; cfg.channels = m->channels; cfg.bits_per_sample = m->bps;
     cfg.compression_level = m->level; cfg.blocksize = m->N; cfg.container_bytes = 4;
     cfg.write_prologue = 0; cfg.do_md5 = 0; cfg.streamable_subset = 0; cfg.debug_trace = 0;
+    cfg.limit_min_bitrate = m->limit_min_bitrate ? 1u : 0u;
     const uint64_t off = 0, cnt = n; const uint32_t ffn = m->frame_number;
+    const bool loose = (m->level == 1 || m->level == 4) && m->channels == 2;
+    if (loose && flacb200_encode_set_prev_assignment(ctx, &m->last_ca, 1) != 0) { m->state = ST_FRAMING_ERROR; return false; }
     if (flacb200_encode_batch(ctx, &cfg, m->pending.data(), 0, n * m->channels, 1, &off, &cnt, &ffn) != 0) { m->state = ST_FRAMING_ERROR; return false; }
     flacb200_enc_result r;
     if (flacb200_encode_result(ctx, &r) != 0) { m->state = ST_FRAMING_ERROR; return false; }
@@ -188,6 +192,11 @@ bool encode_pending(FLAC__StreamEncoder* e, uint64_t n) {
         size_t k = 0;
         for (size_t i = 0; i < vals; i++) { const uint32_t v = (uint32_t)m->pending[i]; for (uint32_t b = 0; b < bytes; b++) tmp[k++] = (uint8_t)(v >> (8 * b)); }
         m->md5.update(tmp.data(), tmp.size());
+    }
+    if (loose && r.n_frames) {
+        std::vector<uint8_t> ca(r.n_frames);
+        if (flacb200_encode_fetch_assignments(ctx, ca.data(), ca.size()) != 0) { m->state = ST_FRAMING_ERROR; return false; }
+        m->last_ca = ca.back();
     }
     for (uint32_t f = 0; f < r.n_frames; f++) {
         if (!deliver(e, m->arena.data() + m->foff[f], m->flen[f], m->fsmp[f], m->frame_number)) return false;
@@ -208,13 +217,12 @@ int init_common(FLAC__StreamEncoder* e) {
     const uint32_t lvl = m->level > 8 ? 8 : m->level;
     m->N = m->blocksize ? m->blocksize : (kMaxLpc[lvl] == 0 ? 1152u : 4096u);
     // limits of this build fail loudly here instead of producing a different stream (DESIGN.md "limits")
-    const bool loose = (lvl == 1 || lvl == 4) && m->channels == 2;
-    if (m->custom_tuning || loose || m->bps > 24 || m->limit_min_bitrate) { m->state = ST_FRAMING_ERROR; return INIT_ENCODER_ERROR; }
+    if (m->custom_tuning || m->bps > 24) { m->state = ST_FRAMING_ERROR; return INIT_ENCODER_ERROR; }
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (!shared_ctx()) { m->state = ST_MEMORY_ALLOCATION_ERROR; return INIT_ENCODER_ERROR; }   // no CUDA device: no CPU fallback
     }
-    m->pending.clear(); m->frame_number = 0; m->samples_written = 0; m->bytes_written = 0; m->min_fs = m->max_fs = 0; m->frames_written = 0; m->streaminfo_offset = 0;
+    m->pending.clear(); m->frame_number = 0; m->last_ca = 0; m->samples_written = 0; m->bytes_written = 0; m->min_fs = m->max_fs = 0; m->frames_written = 0; m->streaminfo_offset = 0;
     m->md5.init();
     m->state = ST_OK;
     // stream prologue: "fLaC", STREAMINFO (frame sizes / MD5 zero, total = estimate), VORBIS_COMMENT

@@ -43,7 +43,7 @@ def test_stream_encoder_callback_sequence_matches_libflac(ours, ref, chunks):
 def test_stream_encoder_without_seek_and_levels(ours, ref):
     from _flacapi import encode_session
     x = corpus_signal("mixed", 4096 * 2 + 50, 2, 16, seed=2)
-    for level in (0, 2, 3, 5, 8):
+    for level in (0, 1, 2, 3, 4, 5, 8):
         a = encode_session(ours, x, 44100, 16, level, 0, seekable=False)
         b = encode_session(ref, x, 44100, 16, level, 0, seekable=False)
         assert _norm(a["log"]) == _norm(b["log"]), level
@@ -51,6 +51,25 @@ def test_stream_encoder_without_seek_and_levels(ours, ref):
     a = encode_session(ours, x24, 192000, 24, 8, 4096)
     b = encode_session(ref, x24, 192000, 24, 8, 4096)
     assert a["file"] == b["file"]
+
+
+def test_stream_encoder_loose_mid_side_across_calls(ours, ref):
+    """levels 1/4: the decision made in one process_interleaved() call governs frames encoded by later calls"""
+    from _flacapi import encode_session
+    n = 1152 * 40 + 77
+    a0 = corpus_signal("music", n, 2, 16, seed=11)
+    b0 = corpus_signal("lr_uncorr", n, 2, 16, seed=12)
+    x = a0.copy(); x[n // 2:] = b0[n // 2:]
+    for level, bs in [(1, 0), (4, 576), (4, 0)]:
+        for chunks in ([5000] * 20, [1153, 1, 1151] * 40, None):
+            a = encode_session(ours, x, 44100, 16, level, bs, chunks=chunks)
+            b = encode_session(ref, x, 44100, 16, level, bs, chunks=chunks)
+            assert _norm(a["log"]) == _norm(b["log"]), (level, bs, chunks and chunks[0])
+            assert a["file"] == b["file"]
+    sil = np.zeros((4096 * 2 + 10, 2), np.int16)
+    a = encode_session(ours, sil, 48000, 16, 5, 0, limit_min_bitrate=True)
+    b = encode_session(ref, sil, 48000, 16, 5, 0, limit_min_bitrate=True)
+    assert _norm(a["log"]) == _norm(b["log"]) and a["file"] == b["file"]
 
 
 def test_stream_encoder_init_errors(ours, ref):

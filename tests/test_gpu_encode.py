@@ -10,7 +10,7 @@ from conftest import golden_cases, load_golden
 from pyflac_b200.synth import corpus_signal, CORPUS_KINDS, music_like
 
 pytestmark = pytest.mark.gpu
-CASES = [c for c in golden_cases() if not (c["level"] in (1, 4) and c["channels"] == 2)]
+CASES = golden_cases()
 
 
 @pytest.fixture(scope="module")
@@ -30,7 +30,7 @@ def test_encode_matches_golden(eng, case):
     assert out["log_guard_hits"] == 0
 
 
-@pytest.mark.parametrize("level", [0, 2, 3, 5, 6, 7, 8])
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_encode_corpus_vs_oracle(eng, checkers, level):
     """every corpus kind (each subframe type / branch), 16-bit stereo + 24-bit mono + odd blocksize, one batch per level"""
     from pyflac_b200 import _native as nat
@@ -41,6 +41,60 @@ def test_encode_corpus_vs_oracle(eng, checkers, level):
         for kind, x, g in zip(CORPUS_KINDS, xs, got):
             assert g == checkers.oracle_encode(x, sr, bps, level, bs), (level, kind, ch, bps, n, bs)
         assert out["log_guard_hits"] == 0
+
+
+def test_encode_loose_mid_side(eng, checkers):
+    """levels 1 and 4 on stereo: one L/R-vs-M/S decision every round(0.4 s) of frames, followers analyse only that pair
+    (up: process_subframes_ loose_mid_side_stereo).  Signals whose best assignment changes along the stream, several
+    decision periods (blocksize / sample rate), a stream shorter than one period, and a mono stream in the same level."""
+    from pyflac_b200 import _native as nat
+    rng = np.random.default_rng(5)
+    n = 4096 * 14 + 300
+    a = corpus_signal("music", n, 2, 16, seed=31)
+    b = corpus_signal("lr_uncorr", n, 2, 16, seed=32)
+    sw = a.copy()
+    sw[n // 3: 2 * n // 3] = b[n // 3: 2 * n // 3]                       # correlated -> uncorrelated -> correlated
+    wide = a.copy(); wide[:, 1] = -wide[:, 0]                            # side-heavy
+    for level in (1, 4):
+        for sr, bs in [(44100, 0), (8000, 1152), (96000, 256), (48000, 4608)]:
+            xs = [sw, wide, a[:3000], b]
+            got, out = nat.encode_streams(eng, xs, sr, 16, level, bs)
+            for i, (x, g) in enumerate(zip(xs, got)):
+                assert g == checkers.oracle_encode(x, sr, 16, level, bs), (level, sr, bs, i)
+            assert out["log_guard_hits"] == 0
+        m = corpus_signal("music", 9000, 1, 16, seed=3)
+        got, _ = nat.encode_streams(eng, [m], 44100, 16, level, 0)
+        assert got[0] == checkers.oracle_encode(m, 44100, 16, level, 0)
+    x24 = corpus_signal("music", 4096 * 6, 2, 24, seed=9)
+    got, _ = nat.encode_streams(eng, [x24], 96000, 24, 4, 4096)
+    assert got[0] == checkers.oracle_encode(x24, 96000, 24, 4, 4096)
+
+
+def test_encode_limit_min_bitrate(eng, checkers):
+    """FLAC__stream_encoder_set_limit_min_bitrate: a frame may not consist of constant subframes only
+    (up: process_subframes_; ref: stream_encoder.h:1105-1115)"""
+    from pyflac_b200 import _native as nat
+    n = 4096 * 3 + 100
+    sil = np.zeros((n, 2), np.int16)
+    dc = np.full((n, 2), 1234, np.int16)
+    half = corpus_signal("music", n, 2, 16, seed=4); half[:, 0] = 77               # first channel constant, second not
+    half2 = corpus_signal("music", n, 2, 16, seed=5); half2[:, 1] = -5             # second channel constant
+    part = corpus_signal("music", n, 2, 16, seed=6); part[4096:8192] = 0           # one silent frame in the middle
+    for level in (0, 1, 2, 5, 8):
+        xs = [sil, dc, half, half2, part]
+        got, _ = nat.encode_streams(eng, xs, 48000, 16, level, 0, limit_min_bitrate=True)
+        for i, (x, g) in enumerate(zip(xs, got)):
+            assert g == checkers.oracle_encode(x, 48000, 16, level, 0, limit_min_bitrate=True), (level, i)
+        got0, _ = nat.encode_streams(eng, xs, 48000, 16, level, 0)
+        assert got0[0] != got[0]
+    for ch in (1, 3):
+        z = np.zeros((5000, ch), np.int16)
+        got, _ = nat.encode_streams(eng, [z], 44100, 16, 5, 0, limit_min_bitrate=True)
+        assert got[0] == checkers.oracle_encode(z, 44100, 16, 5, 0, limit_min_bitrate=True), ch
+    ref = checkers.ref_encode(sil, 48000, 16, 5, 0, limit_min_bitrate=True) if checkers.ref_available() else None
+    if ref is not None:
+        got, _ = nat.encode_streams(eng, [sil], 48000, 16, 5, 0, limit_min_bitrate=True)
+        assert got[0] == ref
 
 
 def test_encode_edge_lengths(eng, checkers):
