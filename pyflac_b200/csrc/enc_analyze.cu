@@ -1,26 +1,70 @@
-// enc_analyze.cu -- encode analysis kernel: one CTA per frame, one warp per signal.
+// enc_analyze.cu -- encode analysis kernel (scope rows E2-E11): one CTA of four warps per frame.
 //
-// For every signal (channel, or mid / side) the warp reproduces libFLAC 1.4.3's process_subframe_
-// decision sequence (SURVEY A.3-A.9, rows E2-E11 of the scope table): wasted bits, fixed-predictor
-// error sums, window + sequential-double autocorrelation, Levinson-Durbin, order guess, coefficient
-// quantisation, residual -> partition sums -> Rice parameter / partition-order search, and keeps the
-// candidate with the smallest libFLAC bit estimate.  Thread 0 then picks the channel assignment.
-// Output: one 128-byte SubframePlan per signal + one channel-assignment byte per frame.  The pack
-// kernel (enc_pack.cu) turns plans into bits.
+// For every signal of the frame (a channel, or mid / side) the kernel reproduces libFLAC 1.4.3's
+// process_subframe_ decision sequence: wasted bits, fixed-predictor error sums,
+// window + sequential-double autocorrelation, Levinson-Durbin, order guess, coefficient quantisation,
+// residual -> partition sums -> Rice parameter / partition-order search, and keeps the candidate with the
+// smallest libFLAC bit estimate.  Output: one 128-byte SubframePlan per signal + one channel-assignment
+// byte per frame; the pack kernel (enc_pack.cu) turns plans into bits.
 //
-// Exactness: integer work is exact; floating point follows fb_math.cuh (unfused, RN); the
-// autocorrelation is one DFMA chain per lag in ascending sample order (products of two floats are
-// exact in double, so fma == mul+add as libFLAC computes it).  No tensor cores: this is integer /
-// bit-serial work bounded by dependent-issue latency, not by a dense contraction.
+// Layout of the work (B200: latency/issue bound, so the design minimises instructions and keeps many
+// frames resident per SM):
+//  * The frame is staged ONCE into shared memory in its container form -- for 16-bit stereo the raw
+//    interleaved words (L | R << 16), 16 KiB per 4096-sample frame, mid/side derived on the fly; for every
+//    other shape one int32 row block per signal.  Rows of B0 = ceil(N/32) samples, row stride odd, so both
+//    access patterns below are bank-conflict free.
+//  * Streaming passes (fixed-predictor sums, residual + partition sums) give lane p the contiguous samples
+//    [p*B0, (p+1)*B0): one shared load per sample, the predictor history lives in registers (statically
+//    rotated window), partition sums leave the lane through a handful of shared atomics.
+//  * The autocorrelation is one DFMA chain per lag in ascending sample order (products of two floats are
+//    exact in double, so fma == libFLAC's mul+add).  A lane owns the two chains (2p, 2p+1) of one
+//    (signal, window) job, up to four jobs per warp: one warp carries all four signals of a stereo frame.
+//  * Work items (autocorrelation groups, per-signal fixed analysis, per (signal, apodization step) LPC
+//    evaluation) are handed to the four warps through a shared-memory queue, long items first.
+//
+// Exactness: integer work is exact; floating point follows fb_math.cuh (unfused, RN).  No tensor cores:
+// this is integer / bit-serial work, not a dense contraction.
 #include "fb_common.cuh"
 #include "fb_math.cuh"
 
 namespace fb {
 
-constexpr int kAcJobsMax = 3;          // (signal, window) chains packed into one warp: floor(32 / lags)
-constexpr int kAcBufStride = 112;      // doubles per job: 16 mirror + 3 slots of 32
-constexpr int kMaxWindows = 6;         // full + 2 halves + 3 thirds (subdivide_tukey(3))
-constexpr int kAcStoreStride = 13;     // lags kept per (signal, window)
+constexpr int kAnThreads = 128;
+constexpr int kAnWarps = kAnThreads / 32;
+constexpr int kAcJobsMax = 4;          // (signal, window) jobs carried by one warp
+constexpr int kAcRing = 112;           // doubles per job: 16 mirror + 3 slots of 32
+constexpr int kAcStoreStride = 14;     // lags kept per (signal, window): 13 + the unused odd partner
+constexpr int kMaxSteps = kMaxApodSteps;
+
+// Signals of the packed layout (16-bit stereo staged as raw words L | R << 16); plain layouts index their own row block.
+enum SigKind : int { kLo16 = 0, kHi16 = 1, kMid16 = 2, kSide16 = 3, kPlain = 4 };
+
+// How a warp reads one signal out of the staged frame.  Packed: value = (lo * ca + hi * cb) >> sh with
+// (ca, cb, sh) = (1,0,w) left, (0,1,w) right, (1,1,1+w) mid, (1,-1,w) side, w = wasted bits -- one code path for
+// all four signals keeps the instruction working set of a CTA (whose warps run different signals) small.
+struct SigView {
+    const int32_t* base;     // packed: the frame's words; plain: the signal's own row block (wasted bits already removed)
+    int ca, cb, sh;
+};
+
+struct FrameGeo {
+    int N, B0, RS, pad;      // samples, samples per row, row stride in words, RS - B0
+    uint32_t magic;          // ceil(2^32 / B0) (pad != 0 only)
+};
+
+__device__ __forceinline__ int pidx(const FrameGeo& G, int i) {
+    return G.pad ? i + (int)__umulhi((uint32_t)i, G.magic) : i;
+}
+
+template <bool PACKED>
+__device__ __forceinline__ int sig_word(int w, const SigView& V) {
+    if constexpr (PACKED) {
+        const int lo = (int)(short)w, hi = w >> 16;
+        return (lo * V.ca + hi * V.cb) >> V.sh;
+    } else {
+        return w;
+    }
+}
 
 struct __align__(16) WarpScratch {
     double   ac[16];                   // autocorrelation of the current apodization step
@@ -29,7 +73,6 @@ struct __align__(16) WarpScratch {
     float    lp[kMaxOrder * kMaxOrder];
     int32_t  q[16];                    // quantised coefficients of the current candidate
     int32_t  misc[8];
-    SubframePlan plan;                 // best candidate so far
 };
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
@@ -38,78 +81,103 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
-template <typename T>
-__device__ __forceinline__ int load_pcm(const T* p, uint64_t idx) { return (int)__ldg(p + idx); }
-
-// r[i] = x[i] - ((sum_j q[j] * x[i-1-j]) >> shift) with partition sums of |r| at the maximum
-// partition order.  Fixed predictors are the same formula with binomial coefficients and shift 0
-// (up: fixed.c FLAC__fixed_compute_residual == lpc residual with q = {1},{2,-1},{3,-3,1},{4,-6,4,-1}).
-// WIDE: 64-bit accumulate (up: FLAC__lpc_compute_residual_from_qlp_coefficients_wide); the 32-bit
-// form is used exactly when libFLAC proves it cannot overflow (max_prediction_before_shift_bps <= 32).
-// check_limit reproduces the _limit_residual rejection (residual must fit int32, INT32_MIN excluded).
-template <int ORDER, bool WIDE>
-__device__ __forceinline__ bool residual_partition_sums(const int32_t* __restrict__ x, int N, const int32_t* qs,
-                                                        int shift, int psize, int nparts, bool narrow_sums,
-                                                        bool check_limit, unsigned long long* psum, int lane) {
-    int32_t q[ORDER > 0 ? ORDER : 1];
+// ------------------------------------------------------------------------------------------------
+// r[i] = x[i] - ((sum_j q[j] * x[i-1-j]) >> shift), sum of |r| per partition at the maximum partition order.
+// Fixed predictors are the same formula with binomial coefficients and shift 0 (up: fixed.c
+// FLAC__fixed_compute_residual == lpc residual with q = {1},{2,-1},{3,-3,1},{4,-6,4,-1}).
+// WIDE: 64-bit accumulate (up: FLAC__lpc_compute_residual_from_qlp_coefficients_wide); the 32-bit form is
+// used exactly when libFLAC proves it cannot overflow.  check_limit reproduces the _limit_residual rejection.
+//
+// Lane p walks its own contiguous samples; h[] is the predictor history, rotated statically: inside a group
+// of ORDER samples, sample u reads h[(u-1-j) mod ORDER] and then overwrites h[u] (the tap that just expired).
+// psum must be zeroed by the caller; partition totals arrive through shared atomics (<= 3 per lane).
+template <int ORDER, bool WIDE, bool PACKED>
+__device__ __noinline__ bool residual_partition_sums(SigView V, FrameGeo G, const int32_t* __restrict__ qs, int shift,
+                                                     int psize, bool check_limit, unsigned long long* psum, int lane) {
+    constexpr int O = ORDER > 0 ? ORDER : 1;
+    int32_t q[O];
 #pragma unroll
     for (int j = 0; j < ORDER; j++) q[j] = qs[j];
     bool bad = false;
-    for (int p = 0; p < nparts; p++) {
-        int lo = p * psize;
-        const int hi = lo + psize;
-        if (p == 0) lo = ORDER;
+    const int blk_lo = lane * G.B0, blk_hi = min(G.N, blk_lo + G.B0);
+    int lo = max(blk_lo, ORDER);
+    const int32_t* rowp = V.base + lane * G.RS - blk_lo;      // rowp[i] is sample i for blk_lo <= i < blk_hi
+    while (lo < blk_hi) {
+        const int part = lo / psize;
+        const int hi = min(blk_hi, (part + 1) * psize);
+        int32_t h[O];
+#pragma unroll
+        for (int k = 0; k < ORDER; k++) h[k] = sig_word<PACKED>(V.base[pidx(G, lo - ORDER + k)], V);
         unsigned long long acc = 0;
-        for (int i = lo + lane; i < hi; i += 32) {
-            long long r;
-            if (WIDE) {
-                long long s = 0;
+        for (int g = lo; g < hi; g += O) {
 #pragma unroll
-                for (int j = 0; j < ORDER; j++) s += (long long)q[j] * (long long)x[i - 1 - j];
-                r = (long long)x[i] - (s >> shift);
-                if (check_limit && (r <= (long long)INT32_MIN || r > (long long)INT32_MAX)) bad = true;
-            } else {
-                int s = 0;
+            for (int u = 0; u < O; u++) {
+                if (g + u < hi) {
+                    const int xv = sig_word<PACKED>(rowp[g + u], V);
+                    long long r;
+                    if (WIDE) {
+                        long long s = 0;
 #pragma unroll
-                for (int j = 0; j < ORDER; j++) s += q[j] * x[i - 1 - j];
-                r = (long long)(x[i] - (s >> shift));
+                        for (int j = 0; j < ORDER; j++) s += (long long)q[j] * (long long)h[(u - 1 - j + 2 * O) % O];
+                        r = (long long)xv - (s >> shift);
+                        if (check_limit && (r <= (long long)INT32_MIN || r > (long long)INT32_MAX)) bad = true;
+                    } else {
+                        int s = 0;
+#pragma unroll
+                        for (int j = 0; j < ORDER; j++) s += q[j] * h[(u - 1 - j + 2 * O) % O];
+                        r = (long long)(xv - (s >> shift));
+                    }
+                    acc += (unsigned long long)(r < 0 ? -r : r);
+                    if (ORDER > 0) h[u] = xv;
+                }
             }
-            acc += (unsigned long long)(r < 0 ? -r : r);
         }
-        unsigned long long tot;
-        if (__reduce_or_sync(0xffffffffu, (unsigned)(acc >> 27)) == 0u) tot = __reduce_add_sync(0xffffffffu, (unsigned)acc);
-        else tot = warp_sum_u64(acc);
-        if (lane == 0) psum[p] = narrow_sums ? (tot & 0xffffffffull) : tot;
+        atomicAdd(&psum[part], acc);
+        lo = hi;
     }
+    __syncwarp();
     return __any_sync(0xffffffffu, bad);
 }
 
-template <bool WIDE>
-__device__ bool residual_dispatch(int order, const int32_t* x, int N, const int32_t* q, int shift, int psize,
-                                  int nparts, bool narrow, bool limit, unsigned long long* psum, int lane) {
+template <bool WIDE, bool PACKED>
+__device__ __forceinline__ bool residual_order(int order, const SigView& V, const FrameGeo& G, const int32_t* q, int shift,
+                                               int psize, bool limit, unsigned long long* psum, int lane) {
     switch (order) {
-        case 0: return residual_partition_sums<0, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        case 1: return residual_partition_sums<1, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        case 2: return residual_partition_sums<2, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        case 3: return residual_partition_sums<3, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        case 4: return residual_partition_sums<4, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        case 5: return residual_partition_sums<5, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        case 6: return residual_partition_sums<6, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        case 7: return residual_partition_sums<7, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        case 8: return residual_partition_sums<8, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        case 9: return residual_partition_sums<9, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        case 10: return residual_partition_sums<10, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        case 11: return residual_partition_sums<11, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
-        default: return residual_partition_sums<12, WIDE>(x, N, q, shift, psize, nparts, narrow, limit, psum, lane);
+        case 0: return residual_partition_sums<0, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        case 1: return residual_partition_sums<1, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        case 2: return residual_partition_sums<2, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        case 3: return residual_partition_sums<3, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        case 4: return residual_partition_sums<4, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        case 5: return residual_partition_sums<5, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        case 6: return residual_partition_sums<6, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        case 7: return residual_partition_sums<7, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        case 8: return residual_partition_sums<8, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        case 9: return residual_partition_sums<9, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        case 10: return residual_partition_sums<10, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        case 11: return residual_partition_sums<11, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
+        default: return residual_partition_sums<12, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
     }
+}
+
+template <bool PACKED>
+__device__ __forceinline__ bool residual_dispatch(bool wide, int order, const SigView& V, const FrameGeo& G, const int32_t* q,
+                                                  int shift, int psize, int nparts, bool limit, unsigned long long* psum, int lane) {
+    for (int p = lane; p < nparts; p += 32) psum[p] = 0ull;
+    __syncwarp();
+    return wide ? residual_order<true, PACKED>(order, V, G, q, shift, psize, limit, psum, lane)
+                : residual_order<false, PACKED>(order, V, G, q, shift, psize, limit, psum, lane);
 }
 
 // up: stream_encoder.c find_best_partition_order_ / set_partitioned_rice_: given the sums at
 // the maximum order in psum[0 .. 2^omax), search orders omax..0 (first strict minimum), merging pairwise.
 // Lane p owns partitions p and p+32.  Returns estimated residual bits; best parameters land in k0/k1.
-__device__ __forceinline__ uint32_t rice_search(unsigned long long* psum, int N, int pred_order, int omax,
+__device__ __forceinline__ uint32_t rice_search(unsigned long long* psum, int N, int pred_order, int omax, bool narrow_sums,
                                                 uint32_t rice_limit, int lane, int* best_order_out,
                                                 uint32_t* k0_out, uint32_t* k1_out) {
+    if (narrow_sums) {      // libFLAC's 32-bit partition accumulators wrap
+        for (int p = lane; p < (1 << omax); p += 32) psum[p] &= 0xffffffffull;
+        __syncwarp();
+    }
     uint32_t best_bits = 0, bk0 = 0, bk1 = 0;
     int best_o = 0, off = 0;
     for (int o = omax; o >= 0; o--) {
@@ -146,122 +214,149 @@ __device__ __forceinline__ uint32_t add_sat(uint32_t est, uint32_t bits) {
     return bits < 0xffffffffu - est ? est + bits : 0xffffffffu;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fixed-predictor error sums (up: fixed.c FLAC__fixed_compute_best_predictor[_wide]):
+// sum |k-th difference| over samples 4..N-1, k = 0..4.  Lane p streams its own samples; the running
+// differences live in registers; 32-bit lane partials are flushed into 64-bit totals every `flush` samples
+// (flush * 2^(sbps+4) < 2^32).  Returns the warp totals in e[0..4] (every lane).
+template <bool PACKED>
+__device__ __noinline__ void fixed_error_sums(SigView V, FrameGeo G, int flush, int lane, unsigned long long* e) {
+    const int blk_lo = lane * G.B0, blk_hi = min(G.N, blk_lo + G.B0);
+    const int lo = max(blk_lo, 4);
+    unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
+    if (lo < blk_hi) {
+        const int32_t* rowp = V.base + lane * G.RS - blk_lo;
+        int x1 = sig_word<PACKED>(V.base[pidx(G, lo - 1)], V), x2 = sig_word<PACKED>(V.base[pidx(G, lo - 2)], V);
+        const int x3 = sig_word<PACKED>(V.base[pidx(G, lo - 3)], V), x4 = sig_word<PACKED>(V.base[pidx(G, lo - 4)], V);
+        int d1 = x1 - x2, d2 = d1 - (x2 - x3), d3 = d2 - ((x2 - x3) - (x3 - x4));
+        for (int g = lo; g < blk_hi; g += flush) {
+            uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+            const int ge = min(blk_hi, g + flush);
+#pragma unroll 4
+            for (int i = g; i < ge; i++) {
+                const int x0 = sig_word<PACKED>(rowp[i], V);
+                const int a1 = x0 - x1, a2 = a1 - d1, a3 = a2 - d2, a4 = a3 - d3;
+                s0 += (uint32_t)abs(x0); s1 += (uint32_t)abs(a1); s2 += (uint32_t)abs(a2); s3 += (uint32_t)abs(a3); s4 += (uint32_t)abs(a4);
+                x1 = x0; d1 = a1; d2 = a2; d3 = a3;
+            }
+            e0 += s0; e1 += s1; e2 += s2; e3 += s3; e4 += s4;
+        }
+    }
+    e[0] = warp_sum_u64(e0); e[1] = warp_sum_u64(e1); e[2] = warp_sum_u64(e2); e[3] = warp_sum_u64(e3); e[4] = warp_sum_u64(e4);
+}
+
+template <bool PACKED>
+__device__ __forceinline__ void fixed_error_sums_rt(const SigView& V, const FrameGeo& G, int sbps, int lane, unsigned long long* e) {
+    const int room = 32 - (sbps + 4);
+    const int flush = room >= 6 ? 64 : (room >= 1 ? (1 << room) : 1);
+    fixed_error_sums<PACKED>(V, G, flush, lane, e);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Sequential double autocorrelation (up: lpc.c FLAC__lpc_compute_autocorrelation) of
-// windowed segments (up: FLAC__lpc_window_data / _partial), for every (signal, window) "job"
-// of the frame.  Jobs of equal length are packed into lane blocks of `L` lanes (lane = lag), up to
-// floor(32 / L) jobs per warp, so that one DFMA instruction advances several chains: this phase is
-// bound by dependent-issue latency, not by HBM or FP64 throughput.  Each chain is strictly sequential in
-// i (one rounding per add, ascending i) -- parallelism comes from lags x signals x windows only.
+// windowed segments (up: FLAC__lpc_window_data / _partial) for a group of up to four
+// (signal, window) jobs of equal length.  Lane = (job, pair): it owns the chains of lags 2*pair and
+// 2*pair+1; the second chain reuses the first one's lagged operand of the previous step, so two steps cost
+// one 16-byte shared load for the current values, one for the lagged values and four DFMAs.
+// Each chain is strictly sequential in i (one rounding per add, ascending i).
 //
 // Per job a ring of three 32-sample slots of doubles (plus a 16-entry mirror of slot 2's tail in front of
-// slot 0, so "i - lag" is always a plain negative offset).  While the 32 fused steps of chunk c run
-//      acc = fma(slot[s], slot[s - lag], acc)          (immediate-offset shared loads, no index math)
-// the same warp windows chunk c+1 (f32 multiply, widen to f64) into the next slot: the loads and
-// conversions sit in the same basic block as the DFMA chain, so they fill its issue gaps.
-// Terms with i < lag multiply zero history and leave the accumulator unchanged, as do zero-padded tail terms.
-//   segment sample i:  i <  part          : x[dshift+i] * w[i]
-//                      part <= i < 2*part : x[dshift+i] * w[N-2*part+i]
+// slot 0, so "i - lag" is always a plain negative offset).  While the 32 steps of chunk c run, the same warp
+// windows chunk c+1 (f32 multiply, widen to f64) into the next slot.
+//   segment sample i:  i <  part          : x[off+i] * w[i]
+//                      part <= i < 2*part : x[off+i] * w[N-2*part+i]
 //                      i == 2*part        : 0            (full window: part = N)
-struct AcJobs { const int32_t* xs[kAcJobsMax]; int cnt; };
+struct AcGroup {
+    SigView v[kAcJobsMax];
+    int off[kAcJobsMax];
+    int cnt;
+};
 
-__device__ __forceinline__ void ac_window_store(double* __restrict__ buf, const AcJobs& J, const float* __restrict__ w,
-                                                int N, int part, int len, int base, int slot, int lane) {
+template <bool PACKED>
+__device__ __forceinline__ void ac_fetch(const AcGroup& J, const FrameGeo& G, const float* __restrict__ w, int part, int len,
+                                         int base, int lane, float& wv, int (&xv)[kAcJobsMax]) {
     const int i = base + lane;
     const bool in = (i < len) && (i < 2 * part);
-    float wv = 0.0f;
-    if (in) wv = __ldg(w + (i < part ? i : N - 2 * part + i));
+    wv = 0.0f;
 #pragma unroll
-    for (int b2 = 0; b2 < kAcJobsMax; b2++) {
-        if (b2 < J.cnt) {
-            const double d = in ? (double)FB_FMUL(__int2float_rn(J.xs[b2][i]), wv) : 0.0;
-            buf[b2 * kAcBufStride + 16 + slot * 32 + lane] = d;
-            if (slot == 2 && lane >= 16) buf[b2 * kAcBufStride + lane - 16] = d;
+    for (int b = 0; b < kAcJobsMax; b++) xv[b] = 0;
+    if (in) {
+        wv = __ldg(w + (i < part ? i : G.N - 2 * part + i));
+#pragma unroll
+        for (int b = 0; b < kAcJobsMax; b++) if (b < J.cnt) xv[b] = sig_word<PACKED>(J.v[b].base[pidx(G, J.off[b] + i)], J.v[b]);
+    }
+}
+
+// windowed samples of one chunk -> ring slot `slot` (slot 2 also feeds the mirror in front of slot 0)
+__device__ __forceinline__ void ac_store(double* __restrict__ buf, int cnt, int slot, float wv, const int (&xv)[kAcJobsMax], int lane) {
+#pragma unroll
+    for (int b = 0; b < kAcJobsMax; b++) {
+        if (b < cnt) {
+            const double d = (double)FB_FMUL(__int2float_rn(xv[b]), wv);
+            buf[b * kAcRing + 16 + slot * 32 + lane] = d;
+            if (slot == 2 && lane >= 16) buf[b * kAcRing + lane - 16] = d;
         }
     }
 }
 
-template <int SLOT>
-__device__ __forceinline__ void ac_chunk(double& acc, double* __restrict__ buf, const double* __restrict__ jobbuf, int lag,
-                                         const AcJobs& J, const float* __restrict__ w, int N, int part, int len,
-                                         int next_base, int lane) {
-    constexpr int NEXT = (SLOT + 1) % 3;
-    // inputs of the next chunk first (their latency hides under the DFMA chain below)
-    const int i = next_base + lane;
-    const bool in = (i < len) && (i < 2 * part);
-    float wv = 0.0f;
-    int xv[kAcJobsMax];
-    if (in) wv = __ldg(w + (i < part ? i : N - 2 * part + i));
-#pragma unroll
-    for (int b2 = 0; b2 < kAcJobsMax; b2++) xv[b2] = (in && b2 < J.cnt) ? J.xs[b2][i] : 0;
-    const double* curp = jobbuf + 16 + SLOT * 32;
-    const double* lagp = curp - lag;
-#pragma unroll
-    for (int s = 0; s < 32; s += 2) {
-        const double2 c2 = *reinterpret_cast<const double2*>(curp + s);
-        acc = fma(c2.x, lagp[s], acc);
-        acc = fma(c2.y, lagp[s + 1], acc);
-    }
-#pragma unroll
-    for (int b2 = 0; b2 < kAcJobsMax; b2++) {
-        if (b2 < J.cnt) {
-            const double d = (double)FB_FMUL(__int2float_rn(xv[b2]), wv);
-            buf[b2 * kAcBufStride + 16 + NEXT * 32 + lane] = d;
-            if (NEXT == 2 && lane >= 16) buf[b2 * kAcBufStride + lane - 16] = d;
-        }
+template <bool PACKED>
+__device__ __noinline__ void autoc_group(const AcGroup& J, FrameGeo G, const float* __restrict__ w, int part, int len, int pairs,
+                                         double* __restrict__ buf, int lane, double& out_a, double& out_b) {
+    const int jb = lane / pairs, pr = lane - jb * pairs;
+    const bool active = jb < J.cnt;
+    const double* jobbuf = buf + (active ? jb : 0) * kAcRing;
+    const int lag2 = active ? 2 * pr : 0;
+    for (int idx = lane; idx < J.cnt * 16; idx += 32) buf[(idx >> 4) * kAcRing + (idx & 15)] = 0.0;
+    {
+        float wv; int xv[kAcJobsMax];
+        ac_fetch<PACKED>(J, G, w, part, len, 0, lane, wv, xv);
+        ac_store(buf, J.cnt, 0, wv, xv, lane);
     }
     __syncwarp();
-}
-
-__device__ __forceinline__ void autoc_phase(const int32_t* __restrict__ xall, int smem_stride, const float* __restrict__ w,
-                                            int N, int L, int parts, int nwin, const int* __restrict__ need_list, int nneed,
-                                            double* __restrict__ buf, double* __restrict__ acstore, int warp, int nwarps,
-                                            int lane) {
-    const int gmax = min(kAcJobsMax, 32 / L);
-    const int jb = lane / L, lag = lane - jb * L;
-    int g = 0;
-    for (int b = 1; b <= parts; b++) {
-        if (b > 1 && N / b <= 32) continue;
-        const int len = N / b, part = (b == 1) ? N : N / b / 2;
-        const int nj = nneed * b;
-        const int ngrp = (nj + gmax - 1) / gmax, gsz = (nj + ngrp - 1) / ngrp;      // balanced lane blocks
-        for (int j0 = 0; j0 < nj; j0 += gsz, g++) {
-            if (g % nwarps != warp) continue;
-            AcJobs J;
-            J.cnt = min(gsz, nj - j0);
+    double acc_a = 0.0, acc_b = 0.0;
+    const int nchunks = (len + 31) >> 5;
+    int slot = 0;
+    for (int c = 0; c < nchunks; c++) {
+        float wv; int xv[kAcJobsMax];
+        ac_fetch<PACKED>(J, G, w, part, len, (c + 1) * 32, lane, wv, xv);   // inputs of the next chunk: latency hides under the chains
+        const double* curp = jobbuf + 16 + slot * 32;
+        const double* lagp = curp - lag2;
+        double prev = lagp[-1];
 #pragma unroll
-            for (int b2 = 0; b2 < kAcJobsMax; b2++) {
-                const int j = min(j0 + b2, nj - 1), sidx = need_list[j / b], k = j - (j / b) * b;
-                J.xs[b2] = xall + (size_t)sidx * smem_stride + (k * N) / b;
-            }
-            const bool active = jb < J.cnt;
-            const double* jobbuf = buf + (active ? jb : 0) * kAcBufStride;
-            const int lag_eff = active ? lag : 0;
-            for (int idx = lane; idx < J.cnt * 16; idx += 32) buf[(idx >> 4) * kAcBufStride + (idx & 15)] = 0.0;
-            ac_window_store(buf, J, w, N, part, len, 0, 0, lane);
-            __syncwarp();
-            double acc = 0.0;
-            const int nchunks = (len + 31) >> 5;
-            for (int c = 0; c < nchunks; c += 3) {
-                ac_chunk<0>(acc, buf, jobbuf, lag_eff, J, w, N, part, len, (c + 1) * 32, lane);
-                if (c + 1 < nchunks) ac_chunk<1>(acc, buf, jobbuf, lag_eff, J, w, N, part, len, (c + 2) * 32, lane);
-                if (c + 2 < nchunks) ac_chunk<2>(acc, buf, jobbuf, lag_eff, J, w, N, part, len, (c + 3) * 32, lane);
-            }
-            if (active) {
-                const int j = j0 + jb, sidx = need_list[j / b], k = j - (j / b) * b;
-                acstore[((size_t)sidx * nwin + (b - 1) * b / 2 + k) * kAcStoreStride + lag] = acc;
-            }
-            __syncwarp();
+        for (int s = 0; s < 32; s += 2) {
+            const double2 c2 = *reinterpret_cast<const double2*>(curp + s);
+            const double2 l2 = *reinterpret_cast<const double2*>(lagp + s);
+            acc_a = fma(c2.x, l2.x, acc_a);
+            acc_b = fma(c2.x, prev, acc_b);
+            acc_a = fma(c2.y, l2.y, acc_a);
+            acc_b = fma(c2.y, l2.x, acc_b);
+            prev = l2.y;
         }
+        slot = (slot == 2) ? 0 : slot + 1;
+        ac_store(buf, J.cnt, slot, wv, xv, lane);
+        __syncwarp();
     }
+    out_a = acc_a; out_b = acc_b;
 }
 
-template <typename PcmT>
-__global__ void __launch_bounds__(32 * kMaxSignals, 1)
+// ------------------------------------------------------------------------------------------------
+struct AnShared {
+    uint32_t sig_or[kMaxSignals], sig_and[kMaxSignals];
+    uint32_t best_bits[kMaxSignals];                 // winner of the fixed task, then of the whole signal
+    uint32_t step_bits[kMaxSignals][kMaxSteps];      // LPC candidate estimate per apodization step (0xffffffff = none)
+    int      need_list[kMaxSignals];
+    int      nneed;
+    int      queue_a, queue_b;
+    int32_t  fixed_q[kAnWarps][4];                   // binomial coefficients of the fixed candidate a warp is evaluating
+};
+
+template <typename PcmT, bool PACKED>
+__global__ void __launch_bounds__(kAnThreads, PACKED ? 8 : 3)
 analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, const float* __restrict__ windows,
                EncParams P, SubframePlan* __restrict__ plans, uint8_t* __restrict__ frame_ca,
                SignalDebug* __restrict__ dbg, EncStats* __restrict__ stats, int pass) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, sig = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nsig = (int)P.n_signals;
     const FrameDesc fd = frames[blockIdx.x];
     const int N = (int)fd.blocksize;
@@ -277,289 +372,374 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
             mode = (pca == 0) ? 1 : 2;
         }
     }
-    const bool active = mode == 0 || (mode == 1 ? sig < ch : sig >= ch);
+    auto sig_active = [&](int s) { return mode == 0 || (mode == 1 ? s < ch : s >= ch); };
 
-    int32_t* xall = reinterpret_cast<int32_t*>(smem_raw);
-    // [signals | pool: partition sums (phases 1,3) aliased with the autocorrelation rings (phase 2) | per-warp scratch | ...]
-    unsigned char* pool = smem_raw + (size_t)nsig * P.smem_stride * 4;
-    WarpScratch* wsall = reinterpret_cast<WarpScratch*>(pool + P.pool_bytes);
-    unsigned long long* psum = reinterpret_cast<unsigned long long*>(pool) + (size_t)(threadIdx.x >> 5) * 2 * kMaxParts;
-    double* acbuf = reinterpret_cast<double*>(pool) + (size_t)(threadIdx.x >> 5) * P.ac_gsz * kAcBufStride;
+    FrameGeo G;
+    G.N = N; G.B0 = (N + 31) >> 5; G.pad = (G.B0 & 1) ? 0 : 1; G.RS = G.B0 + G.pad;
+    G.magic = G.pad ? (uint32_t)((0x100000000ull + (uint32_t)G.B0 - 1ull) / (uint32_t)G.B0) : 0u;
+
+    // ---- shared memory carve-up (sizes mirrored by analyze_smem_bytes) ----
+    const int sig_words = (int)P.an_stride;                                // words per staged signal (or per packed frame)
+    const int n_steps = (int)P.ac_gsz;                                     // apodization steps per signal
     const int nwin = (int)(P.apod_parts * (P.apod_parts + 1) / 2);
-    double* acstore = reinterpret_cast<double*>(wsall + nsig);                 // [nsig][nwin][kAcStoreStride]
-    uint32_t* sig_bits = reinterpret_cast<uint32_t*>(acstore + (size_t)nsig * nwin * kAcStoreStride);
-    int* need_list = reinterpret_cast<int*>(sig_bits + kMaxSignals);           // signals that go through LPC analysis
-    int* need_flag = need_list + kMaxSignals;
-    int* nneed_p = need_flag + kMaxSignals;
-    int* const_flag = nneed_p + 4;
+    int32_t* xall = reinterpret_cast<int32_t*>(smem_raw);
+    unsigned char* cur = smem_raw + (size_t)(PACKED ? 1 : nsig) * sig_words * 4;
+    double* acbuf_all = reinterpret_cast<double*>(cur);                          // phase A: autocorrelation rings ...
+    WarpScratch* wsall = reinterpret_cast<WarpScratch*>(cur);                    cur += (size_t)P.pool_bytes;   // ... phase B: LPC scratch
+    double* acstore = reinterpret_cast<double*>(cur);                            cur += (size_t)nsig * nwin * kAcStoreStride * sizeof(double);
+    unsigned long long* psum_all = reinterpret_cast<unsigned long long*>(cur);   cur += (size_t)kAnWarps * 2 * kMaxParts * 8;
+    SubframePlan* base_plan = reinterpret_cast<SubframePlan*>(cur);              cur += (size_t)nsig * sizeof(SubframePlan);
+    SubframePlan* step_plan = reinterpret_cast<SubframePlan*>(cur);              cur += (size_t)nsig * n_steps * sizeof(SubframePlan);
+    AnShared& S = *reinterpret_cast<AnShared*>(cur);
 
-    int32_t* x = xall + (size_t)sig * P.smem_stride;
-    WarpScratch& ws = wsall[sig];
-    SignalDebug* dg = dbg ? dbg + (size_t)blockIdx.x * nsig + sig : nullptr;
+    unsigned long long* psum = psum_all + (size_t)warp * 2 * kMaxParts;
+    WarpScratch& ws = wsall[warp];
 
-    // =================== phase 1 (one warp per signal): load, wasted bits, fixed predictors ===================
+    if (tid < kMaxSignals) { S.sig_or[tid] = 0u; S.sig_and[tid] = 0xffffffffu; S.best_bits[tid] = 0u; }
+    if (tid == 0) { S.queue_a = 0; S.queue_b = 0; S.nneed = 0; }
+    for (int i = tid; i < kMaxSignals * kMaxSteps; i += kAnThreads) (&S.step_bits[0][0])[i] = 0xffffffffu;
+    __syncthreads();
+
+    // =================== stage the frame; OR / AND of every signal (wasted bits, constant detection) ===================
     // up: process_subframes_ + get_wasted_bits_
-    uint32_t orv = 0;
-    if (active) {
+    {
         const PcmT* base = pcm + fd.pcm_off;
-        for (int i = lane; i < N; i += 32) {
-            int v;
-            if (sig < ch) v = load_pcm(base, (uint64_t)i * ch + sig);
-            else {
-                const int l = load_pcm(base, (uint64_t)i * ch), r = load_pcm(base, (uint64_t)i * ch + 1);
-                v = (sig == ch) ? ((l + r) >> 1) : (l - r);
+        if (PACKED) {
+            uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0, a0 = ~0u, a1 = ~0u, a2 = ~0u, a3 = ~0u;
+            const bool aligned = ((reinterpret_cast<uintptr_t>(base) & 3u) == 0);
+            for (int i = tid; i < N; i += kAnThreads) {
+                int wd;
+                if (aligned) wd = __ldg(reinterpret_cast<const int*>(base) + i);
+                else wd = (int)((uint32_t)(uint16_t)__ldg(base + 2 * i) | ((uint32_t)(uint16_t)__ldg(base + 2 * i + 1) << 16));
+                xall[pidx(G, i)] = wd;
+                const int lo = (int)(short)wd, hi = wd >> 16, m = (lo + hi) >> 1, sd = lo - hi;
+                o0 |= (uint32_t)lo; o1 |= (uint32_t)hi; o2 |= (uint32_t)m; o3 |= (uint32_t)sd;
+                a0 &= (uint32_t)lo; a1 &= (uint32_t)hi; a2 &= (uint32_t)m; a3 &= (uint32_t)sd;
             }
-            x[i] = v;
-            orv |= (uint32_t)v;
+            o0 = __reduce_or_sync(0xffffffffu, o0); o1 = __reduce_or_sync(0xffffffffu, o1);
+            o2 = __reduce_or_sync(0xffffffffu, o2); o3 = __reduce_or_sync(0xffffffffu, o3);
+            a0 = __reduce_and_sync(0xffffffffu, a0); a1 = __reduce_and_sync(0xffffffffu, a1);
+            a2 = __reduce_and_sync(0xffffffffu, a2); a3 = __reduce_and_sync(0xffffffffu, a3);
+            if (lane == 0) {
+                atomicOr(&S.sig_or[0], o0); atomicOr(&S.sig_or[1], o1); atomicAnd(&S.sig_and[0], a0); atomicAnd(&S.sig_and[1], a1);
+                if (nsig > 2) { atomicOr(&S.sig_or[2], o2); atomicOr(&S.sig_or[3], o3); atomicAnd(&S.sig_and[2], a2); atomicAnd(&S.sig_and[3], a3); }
+            }
+        } else {
+            for (int s = 0; s < nsig; s++) {
+                if (!sig_active(s)) continue;
+                int32_t* x = xall + (size_t)s * sig_words;
+                uint32_t o = 0, a = ~0u;
+                for (int i = tid; i < N; i += kAnThreads) {
+                    int v;
+                    if (s < ch) v = (int)__ldg(base + (uint64_t)i * ch + s);
+                    else {
+                        const int l = (int)__ldg(base + (uint64_t)i * ch), r = (int)__ldg(base + (uint64_t)i * ch + 1);
+                        v = (s == ch) ? ((l + r) >> 1) : (l - r);
+                    }
+                    x[pidx(G, i)] = v;
+                    o |= (uint32_t)v; a &= (uint32_t)v;
+                }
+                o = __reduce_or_sync(0xffffffffu, o); a = __reduce_and_sync(0xffffffffu, a);
+                if (lane == 0) { atomicOr(&S.sig_or[s], o); atomicAnd(&S.sig_and[s], a); }
+            }
         }
     }
-    orv = __reduce_or_sync(0xffffffffu, orv);
-    int wasted = orv ? (__ffs((int)orv) - 1) : 0;
-    if (wasted > (int)P.bps) wasted = (int)P.bps;
-    const int sbps = (int)P.bps - wasted + ((P.do_mid_side && sig == ch + 1) ? 1 : 0);
-    __syncwarp();
-    if (wasted) {
-        for (int i = lane; i < N; i += 32) x[i] >>= wasted;
-        __syncwarp();
-    }
+    __syncthreads();
 
-    // baseline: verbatim (up: evaluate_verbatim_subframe_)
-    reinterpret_cast<uint32_t*>(&ws.plan)[lane] = 0u;
-    __syncwarp();
-    uint32_t best_bits = 8u + (uint32_t)wasted + (uint32_t)N * (uint32_t)sbps;
-    if (lane == 0) {
-        SubframePlan& pl = ws.plan;
-        pl.type = kVerbatim; pl.wasted = (uint8_t)wasted; pl.sbps = (uint8_t)sbps; pl.bits_est = best_bits;
+    // per-signal facts every thread can derive on its own
+    auto sig_wasted = [&](int s) { const uint32_t o = S.sig_or[s]; const int wst = o ? (__ffs((int)o) - 1) : 0; return wst > (int)P.bps ? (int)P.bps : wst; };
+    auto sig_sbps = [&](int s) { return (int)P.bps - sig_wasted(s) + ((P.do_mid_side && s == ch + 1) ? 1 : 0); };
+    auto sig_view = [&](int s) {
+        SigView V;
+        if (PACKED) { V.base = xall; V.ca = (s != 1); V.cb = (s == 0) ? 0 : (s == 3 ? -1 : 1); V.sh = sig_wasted(s) + (s == 2 ? 1 : 0); }
+        else { V.base = xall + (size_t)s * sig_words; V.ca = 1; V.cb = 0; V.sh = 0; }
+        return V;
+    };
+    if (!PACKED) {      // plain rows are stored with the wasted bits already removed
+        for (int s = 0; s < nsig; s++) {
+            const int wst = sig_active(s) ? sig_wasted(s) : 0;
+            if (wst) { int32_t* x = xall + (size_t)s * sig_words; for (int i = tid; i < sig_words; i += kAnThreads) x[i] >>= wst; }
+        }
     }
-    if (dg && lane == 0) { dg->n_apod = 0; dg->fixed_bits = 0; dg->is_constant = 0; dg->fixed_order = 0; for (int k = 0; k < 5; k++) dg->fixed_err[k] = 0; }
-
-    // per-frame partition geometry (up: process_subframes_ max_partition_order = min(level max, ctz(N)))
+    // up: process_subframe_ constant test + process_subframes_ limit_min_bitrate: when every earlier channel is
+    // constant, the last channel (and mid/side after it) may not use a constant subframe
+    auto sig_const = [&](int s) { return N > 4 && S.sig_or[s] == S.sig_and[s]; };
+    auto sig_disable_const = [&](int s) {
+        if (!(P.limit_min_bitrate && mode != 2 && s >= ch - 1)) return false;
+        for (int c2 = 0; c2 < ch - 1; c2++) if (!sig_const(c2)) return false;
+        return true;
+    };
     const int omax_frame = min((int)P.max_part_order, N ? (__ffs(N) - 1) : 0);
     const int max_lpc = (N > 4 && P.max_lpc_order > 0) ? (((int)P.max_lpc_order >= N) ? N - 1 : (int)P.max_lpc_order) : 0;
-    bool want_lpc = false;
-    bool constant = false;
-    int forder = 0;
-
-    if (active && N > 4) {
-        // fixed predictor error sums (up: fixed.c FLAC__fixed_compute_best_predictor[_wide])
-        unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
-        for (int i = 4 + lane; i < N; i += 32) {
-            const int x0 = x[i], x1 = x[i - 1], x2 = x[i - 2], x3 = x[i - 3], x4 = x[i - 4];
-            const int a1 = x0 - x1, b1 = x1 - x2, c1 = x2 - x3, d1 = x3 - x4;
-            const int a2 = a1 - b1, b2 = b1 - c1, c2 = c1 - d1;
-            const int a3 = a2 - b2, b3 = b2 - c2;
-            const int a4 = a3 - b3;
-            e0 += (unsigned)abs(x0); e1 += (unsigned)abs(a1); e2 += (unsigned)abs(a2); e3 += (unsigned)abs(a3); e4 += (unsigned)abs(a4);
-        }
-        e0 = warp_sum_u64(e0); e1 = warp_sum_u64(e1); e2 = warp_sum_u64(e2); e3 = warp_sum_u64(e3); e4 = warp_sum_u64(e4);
-        const unsigned long long e1_true = e1;   // constant detection must not be fooled by the 32-bit wrap below
-        if ((uint32_t)sbps + ilog2_u32((uint32_t)N - 4u) + 1u < 32u) {   // libFLAC's 32-bit accumulators wrap
-            e0 &= 0xffffffffull; e1 &= 0xffffffffull; e2 &= 0xffffffffull; e3 &= 0xffffffffull; e4 &= 0xffffffffull;
-        }
-        {
-            const unsigned long long m34 = min(e3, e4), m234 = min(e2, m34), m1234 = min(e1, m234);
-            if (e0 <= m1234) forder = 0; else if (e1 <= m234) forder = 1; else if (e2 <= m34) forder = 2; else if (e3 <= e4) forder = 3; else forder = 4;
-        }
-        if (e1_true == 0) constant = (x[0] == x[1]) && (x[1] == x[2]) && (x[2] == x[3]) && (x[3] == x[4]);   // samples 3..N-1 are equal already
-        if (dg && lane == 0) { dg->fixed_err[0] = e0; dg->fixed_err[1] = e1; dg->fixed_err[2] = e2; dg->fixed_err[3] = e3; dg->fixed_err[4] = e4; dg->fixed_order = forder; dg->is_constant = constant; }
-
-    }
-    // up: process_subframes_ limit_min_bitrate -- when every earlier channel came out constant, the last channel
-    // (and mid/side after it) may not use a constant subframe, so the frame never shrinks to headers only
-    if (lane == 0) const_flag[sig] = constant ? 1 : 0;
-    __syncthreads();
-    bool disable_const = false;
-    if (P.limit_min_bitrate && mode != 2 && sig >= ch - 1) {
-        disable_const = true;
-        for (int c2 = 0; c2 < ch - 1; c2++) if (!const_flag[c2]) disable_const = false;
-    }
-    if (active && N > 4) {
-        if (constant && !disable_const) {
-            const uint32_t bits = 8u + (uint32_t)wasted + (uint32_t)sbps;     // up: evaluate_constant_subframe_
-            if (bits < best_bits) { best_bits = bits; if (lane == 0) { ws.plan.type = kConstant; ws.plan.bits_est = bits; } }
-        } else {
-            // fixed candidate at the guessed order (up: evaluate_fixed_subframe_)
-            int fo = forder; if (fo >= N) fo = N - 1;
-            int omax = omax_frame;
-            while (omax > 0 && (N >> omax) <= fo) omax--;
-            const int nparts = 1 << omax, psize = N >> omax;
-            const bool narrow = (uint32_t)sbps + 4u < 32u - ilog2_u32((uint32_t)psize);
-            if (lane == 0) {
-                const int32_t c[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};   // x[i] - sum q_j x[i-1-j]
-                for (int j = 0; j < 4; j++) ws.q[j] = c[fo][j];
-            }
-            __syncwarp();
-            // fixed residual of <=24-bit input fits 32-bit arithmetic (|4th difference| < 2^(sbps+4))
-            if (sbps + 4 <= 31) residual_dispatch<false>(fo, x, N, ws.q, 0, psize, nparts, narrow, false, psum, lane);
-            else residual_dispatch<true>(fo, x, N, ws.q, 0, psize, nparts, narrow, false, psum, lane);
-            __syncwarp();
-            int po; uint32_t k0, k1;
-            const uint32_t rb = rice_search(psum, N, fo, omax, P.rice_limit, lane, &po, &k0, &k1);
-            const uint32_t est = add_sat(8u + (uint32_t)wasted + (uint32_t)fo * (uint32_t)sbps, rb);
-            if (dg && lane == 0) dg->fixed_bits = est;
-            if (est < best_bits) {
-                best_bits = est;
-                SubframePlan& pl = ws.plan;
-                if (lane < (1 << po)) pl.rice[lane] = (uint8_t)k0;
-                if (lane + 32 < (1 << po)) pl.rice[lane + 32] = (uint8_t)k1;
-                const bool r2 = __any_sync(0xffffffffu, (lane < (1 << po) && k0 >= 15u) || (lane + 32 < (1 << po) && k1 >= 15u));
-                if (lane == 0) { pl.type = kFixed; pl.order = (uint8_t)fo; pl.part_order = (uint8_t)po; pl.rice2 = r2; pl.bits_est = est; pl.shift = 0; pl.precision = 0; }
-            }
-            __syncwarp();
-            want_lpc = max_lpc > 0;
-        }
-    }
-    if (lane == 0) need_flag[sig] = want_lpc ? 1 : 0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         int n = 0;
-        for (int s2 = 0; s2 < nsig; s2++) if (need_flag[s2]) need_list[n++] = s2;
-        *nneed_p = n;
+        for (int s = 0; s < nsig; s++)
+            if (sig_active(s) && N > 4 && max_lpc > 0 && !(sig_const(s) && !sig_disable_const(s))) S.need_list[n++] = s;
+        S.nneed = n;
     }
     __syncthreads();
+    const int nneed = S.nneed;
 
-    // =================== phase 2 (packed lane blocks): all autocorrelations of the frame ===================
-    const int nneed = *nneed_p;
+    // =================== phase A: autocorrelation groups (long) and per-signal fixed analysis, from a queue ===================
+    const int L = max_lpc + 1, pairs = (L + 1) >> 1;
+    const int gmax = min(kAcJobsMax, 32 / pairs);
+    // group enumeration (identical on every warp): for each window depth b, the nneed*b jobs in balanced groups
+    int n_groups = 0;
     if (nneed > 0)
-        autoc_phase(xall, (int)P.smem_stride, windows + fd.window_off, N, max_lpc + 1, (int)P.apod_parts, nwin, need_list, nneed,
-                    acbuf, acstore, sig, nsig, lane);
-    __syncthreads();
-
-    // =================== phase 3 (one warp per signal): LPC candidates, one per apodization step ===================
-    // up: apply_apodization_ + evaluate_lpc_subframe_
-    if (want_lpc) {
-        const double* myac = acstore + (size_t)sig * nwin * kAcStoreStride;
-        double ac_root = 0.0, ac_cur = 0.0;     // lane j holds lag j
-        int step = 0;
-        int b = 1, c = 0;                        // (depth, part) walk of set_next_subdivide_tukey; b == 1 is the full window
-        bool done = false;
-        while (!done) {
-            int max_this = max_lpc;
-            bool have = true;
-            if (b == 1) {
-                if (lane <= max_this) ac_cur = myac[lane];
-                if (P.apod_parts > 1) { ac_root = ac_cur; b = 2; c = 0; } else done = true;
-            } else {
-                if (N / b <= 32) have = false;
-                else if (!(c & 1)) {
-                    if (lane <= max_this) ac_cur = myac[((b - 1) * b / 2 + c / 2) * kAcStoreStride + lane];
-                } else {
-                    // punch-out: root minus previous partial for lags < max order only (1.4.3 off-by-one)
-                    if (lane < max_this) ac_cur = FB_DSUB(ac_root, ac_cur);
-                }
-                if (b == 2) { if (c == 0) c = 2; else { c = 0; b++; } }
-                else if (c < 2 * b - 1) c++;
-                else { c = 0; b++; }
-                if (b > (int)P.apod_parts) done = true;
+        for (int b = 1; b <= (int)P.apod_parts; b++) {
+            if (b > 1 && N / b <= 32) continue;
+            n_groups += (nneed * b + gmax - 1) / gmax;
+        }
+    const int n_tasks_a = n_groups + nsig;
+    const float* wtab = windows + fd.window_off;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&S.queue_a, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tasks_a) break;
+        if (t < n_groups) {
+            // ---- locate group t ----
+            int b = 1, g0 = 0, j0 = 0, gsz = 1, nj = 0;
+            for (;; b++) {
+                if (b > 1 && N / b <= 32) continue;
+                nj = nneed * b;
+                const int ngrp = (nj + gmax - 1) / gmax;
+                gsz = (nj + ngrp - 1) / ngrp;
+                if (t < g0 + ngrp) { j0 = (t - g0) * gsz; break; }
+                g0 += ngrp;
             }
-            if (!have) continue;
-            if (lane <= max_this) ws.ac[lane] = ac_cur;
-            __syncwarp();
-            if (dg && step < kMaxApodSteps) { if (lane <= max_this) dg->autoc[step][lane] = ac_cur; if (lane == 0) { dg->lpc_order[step] = 0; dg->lpc_bits[step] = 0; } }
-            if (ws.ac[0] == 0.0) { step++; __syncwarp(); continue; }
-
-            if (lane == 0) ws.misc[0] = levinson(ws.ac, max_this, ws.lp, ws.lperr, ws.lpc);
-            __syncwarp();
-            max_this = ws.misc[0];
-
-            // up: lpc.c FLAC__lpc_compute_best_order -- first strict minimum, initial best (uint32_t)-1
-            int guess;
-            {
-                const double escale = FB_DDIV(0.5, (double)N);
-                const uint32_t overhead = (uint32_t)sbps + P.qlp_precision;
-                double bits = 1.7976931348623157e308; bool ul = false;
-                if (lane >= 1 && lane <= max_this) {
-                    const double e = expected_bits_per_sample(ws.lperr[lane - 1], escale, &ul);
-                    bits = FB_DADD(FB_DMUL(e, (double)(N - lane)), (double)((uint32_t)lane * overhead));
-                }
-                double bb = bits; int bi = lane;
+            const int len = N / b, part = (b == 1) ? N : N / b / 2;
+            AcGroup J;
+            J.cnt = min(gsz, nj - j0);
 #pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, bb, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (ob < bb || (ob == bb && oi < bi)) { bb = ob; bi = oi; }
-                }
-                guess = (bb < 4294967295.0) ? bi : 1;
-                // guard band: a runner-up within 1e-9 relative of the winner could flip under a libm log that
-                // differs in the last ulp (DESIGN.md "log guard"); counted, never silently ignored
-                const int ul_best = __shfl_sync(0xffffffffu, (int)ul, guess & 31);
-                const bool amb = (lane >= 1 && lane <= max_this && lane != guess) && (ul || ul_best) &&
-                                 fabs(bits - bb) <= 1e-9 * fabs(bb);
-                if (__any_sync(0xffffffffu, amb) && lane == 0 && stats) atomicAdd(&stats->log_ambiguous, 1ull);
+            for (int q = 0; q < kAcJobsMax; q++) {
+                const int j = min(j0 + q, nj - 1), sidx = S.need_list[j / b], k = j - (j / b) * b;
+                J.v[q] = sig_view(sidx); J.off[q] = (k * N) / b;
             }
-            if (dg && step < kMaxApodSteps) { if (lane < max_this) dg->lpc_err[step][lane] = ws.lperr[lane]; if (lane == 0) dg->lpc_order[step] = guess; }
-
-            const int order = guess;
-            bool ul2;
-            const double rbps = expected_bits_per_sample(ws.lperr[order - 1], FB_DDIV(0.5, (double)(N - order)), &ul2);
-            if (ul2 && fabs(rbps - (double)sbps) <= 1e-9 * (double)sbps && lane == 0 && stats) atomicAdd(&stats->log_ambiguous, 1ull);
-            if (!(rbps >= (double)sbps)) {
-                int prec = (int)P.qlp_precision;
-                if (sbps <= 17) prec = min(prec, 32 - sbps - (int)ilog2_u32((uint32_t)order));
-                if (lane == 0) {
-                    int sh = 0;
-                    const int rc = quantize_coefficients(ws.lp + (order - 1) * kMaxOrder, order, prec, ws.q, &sh);
-                    int32_t asum = 0;
-                    for (int j = 0; j < order; j++) asum += abs(ws.q[j]);
-                    if (asum == 0) asum = 1;
-                    ws.misc[1] = rc; ws.misc[2] = sh; ws.misc[3] = (int)silog2((int64_t)asum);
-                }
-                __syncwarp();
-                if (ws.misc[1] == 0) {
-                    const int shift = ws.misc[2];
-                    // up: lpc.c FLAC__lpc_max_prediction_before_shift_bps / FLAC__lpc_max_residual_bps
-                    const int pred_bps = sbps + ws.misc[3];
-                    const int resid_bps = ((sbps > pred_bps - shift) ? sbps : pred_bps - shift) + 1;
-                    const bool limit = resid_bps > 32;
+            double* buf = acbuf_all + (size_t)(n_groups < kAnWarps ? t : warp) * kAcJobsMax * kAcRing;
+            double ra, rb;
+            autoc_group<PACKED>(J, G, wtab, part, len, pairs, buf, lane, ra, rb);
+            const int jb = lane / pairs, pr = lane - jb * pairs;
+            if (jb < J.cnt) {
+                const int j = j0 + jb, sidx = S.need_list[j / b], k = j - (j / b) * b;
+                double* dst = acstore + ((size_t)sidx * nwin + (b - 1) * b / 2 + k) * kAcStoreStride;
+                dst[2 * pr] = ra; dst[2 * pr + 1] = rb;
+            }
+            __syncwarp();
+        } else {
+            // ---- fixed analysis of signal s: verbatim baseline, constant, or the guessed fixed order ----
+            const int s = t - n_groups;
+            SubframePlan& pl = base_plan[s];
+            reinterpret_cast<uint32_t*>(&pl)[lane] = 0u;
+            __syncwarp();
+            if (!sig_active(s)) continue;
+            const int wasted = sig_wasted(s), sbps = sig_sbps(s);
+            SignalDebug* dg = dbg ? dbg + (size_t)blockIdx.x * nsig + s : nullptr;
+            uint32_t best_bits = 8u + (uint32_t)wasted + (uint32_t)N * (uint32_t)sbps;      // up: evaluate_verbatim_subframe_
+            if (lane == 0) { pl.type = kVerbatim; pl.wasted = (uint8_t)wasted; pl.sbps = (uint8_t)sbps; pl.bits_est = best_bits; }
+            if (dg && lane == 0) { dg->n_apod = 0; dg->fixed_bits = 0; dg->is_constant = 0; dg->fixed_order = 0; for (int k = 0; k < 5; k++) dg->fixed_err[k] = 0; }
+            if (N > 4) {
+                const bool constant = sig_const(s);
+                if (constant && !sig_disable_const(s)) {
+                    const uint32_t bits = 8u + (uint32_t)wasted + (uint32_t)sbps;     // up: evaluate_constant_subframe_
+                    if (dg && lane == 0) dg->is_constant = 1;
+                    if (bits < best_bits) { best_bits = bits; if (lane == 0) { pl.type = kConstant; pl.bits_est = bits; } }
+                } else {
+                    const SigView V = sig_view(s);
+                    unsigned long long e[5];
+                    fixed_error_sums_rt<PACKED>(V, G, sbps, lane, e);
+                    if ((uint32_t)sbps + ilog2_u32((uint32_t)N - 4u) + 1u < 32u) {   // libFLAC's 32-bit accumulators wrap
+#pragma unroll
+                        for (int k = 0; k < 5; k++) e[k] &= 0xffffffffull;
+                    }
+                    int forder;
+                    {
+                        const unsigned long long m34 = min(e[3], e[4]), m234 = min(e[2], m34), m1234 = min(e[1], m234);
+                        if (e[0] <= m1234) forder = 0; else if (e[1] <= m234) forder = 1; else if (e[2] <= m34) forder = 2; else if (e[3] <= e[4]) forder = 3; else forder = 4;
+                    }
+                    if (dg && lane == 0) { for (int k = 0; k < 5; k++) dg->fixed_err[k] = e[k]; dg->fixed_order = forder; dg->is_constant = constant; }
+                    // fixed candidate at the guessed order (up: evaluate_fixed_subframe_)
+                    int fo = forder; if (fo >= N) fo = N - 1;
                     int omax = omax_frame;
-                    while (omax > 0 && (N >> omax) <= order) omax--;
+                    while (omax > 0 && (N >> omax) <= fo) omax--;
                     const int nparts = 1 << omax, psize = N >> omax;
                     const bool narrow = (uint32_t)sbps + 4u < 32u - ilog2_u32((uint32_t)psize);
-                    bool rejected;
-                    if (!limit && pred_bps <= 32) rejected = residual_dispatch<false>(order, x, N, ws.q, shift, psize, nparts, narrow, false, psum, lane);
-                    else rejected = residual_dispatch<true>(order, x, N, ws.q, shift, psize, nparts, narrow, limit, psum, lane);
+                    if (lane == 0) {
+                        const int32_t c[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};   // x[i] - sum q_j x[i-1-j]
+                        for (int j = 0; j < 4; j++) S.fixed_q[warp][j] = c[fo][j];
+                    }
                     __syncwarp();
-                    if (!rejected) {
-                        int po; uint32_t k0, k1;
-                        const uint32_t rb = rice_search(psum, N, order, omax, P.rice_limit, lane, &po, &k0, &k1);
-                        const uint32_t est = add_sat(8u + (uint32_t)wasted + 4u + 5u + (uint32_t)order * (uint32_t)(prec + sbps), rb);
-                        if (dg && lane == 0 && step < kMaxApodSteps) dg->lpc_bits[step] = est;
-                        if (est < best_bits) {
-                            best_bits = est;
-                            SubframePlan& pl = ws.plan;
-                            if (lane < (1 << po)) pl.rice[lane] = (uint8_t)k0;
-                            if (lane + 32 < (1 << po)) pl.rice[lane + 32] = (uint8_t)k1;
-                            const bool r2 = __any_sync(0xffffffffu, (lane < (1 << po) && k0 >= 15u) || (lane + 32 < (1 << po) && k1 >= 15u));
-                            if (lane < order) pl.qlp[lane] = ws.q[lane];
-                            if (lane == 0) { pl.type = kLpc; pl.order = (uint8_t)order; pl.part_order = (uint8_t)po; pl.rice2 = r2; pl.bits_est = est; pl.shift = shift; pl.precision = (uint8_t)prec; }
-                        }
+                    // fixed residual of <=24-bit input fits 32-bit arithmetic (|4th difference| < 2^(sbps+4))
+                    residual_dispatch<PACKED>(sbps + 4 > 31, fo, V, G, S.fixed_q[warp], 0, psize, nparts, false, psum, lane);
+                    int po; uint32_t k0, k1;
+                    const uint32_t rb = rice_search(psum, N, fo, omax, narrow, P.rice_limit, lane, &po, &k0, &k1);
+                    const uint32_t est = add_sat(8u + (uint32_t)wasted + (uint32_t)fo * (uint32_t)sbps, rb);
+                    if (dg && lane == 0) dg->fixed_bits = est;
+                    if (est < best_bits) {
+                        best_bits = est;
+                        if (lane < (1 << po)) pl.rice[lane] = (uint8_t)k0;
+                        if (lane + 32 < (1 << po)) pl.rice[lane + 32] = (uint8_t)k1;
+                        const bool r2 = __any_sync(0xffffffffu, (lane < (1 << po) && k0 >= 15u) || (lane + 32 < (1 << po) && k1 >= 15u));
+                        if (lane == 0) { pl.type = kFixed; pl.order = (uint8_t)fo; pl.part_order = (uint8_t)po; pl.rice2 = r2; pl.bits_est = est; pl.shift = 0; pl.precision = 0; }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) S.best_bits[s] = best_bits;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // =================== phase B: one LPC candidate per (signal, apodization step), from a queue ===================
+    // up: apply_apodization_ + evaluate_lpc_subframe_.  Step list of set_next_subdivide_tukey:
+    // full window, then for depth b = 2..parts: partial windows c = 0,2,.. interleaved with their punch-outs.
+    const int n_tasks_b = nneed * n_steps;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&S.queue_b, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tasks_b) break;
+        const int s = S.need_list[t / n_steps], step = t - (t / n_steps) * n_steps;
+        // ---- step -> (b, c): depth and position in libFLAC's walk; b == 1 is the full window ----
+        int b = 1, c = 0;
+        {
+            int k = step;
+            if (k > 0) {
+                k -= 1; b = 2;
+                for (;;) { const int cnt = (b == 2) ? 2 : 2 * b; if (k < cnt) break; k -= cnt; b++; }
+                c = (b == 2) ? 2 * k : k;        // depth 2 visits c = 0 and c = 2 only (its punch-outs equal the other half)
+            }
+        }
+        if (b > 1 && N / b <= 32) continue;      // window too short: libFLAC skips the step
+        const int wasted = sig_wasted(s), sbps = sig_sbps(s);
+        SignalDebug* dg = dbg ? dbg + (size_t)blockIdx.x * nsig + s : nullptr;
+        const double* myac = acstore + (size_t)s * nwin * kAcStoreStride;
+        int max_this = max_lpc;
+        double ac_cur = 0.0;                     // lane j holds lag j
+        if (b == 1) { if (lane <= max_this) ac_cur = myac[lane]; }
+        else if (!(c & 1)) { if (lane <= max_this) ac_cur = myac[((b - 1) * b / 2 + c / 2) * kAcStoreStride + lane]; }
+        else if (lane <= max_this) {
+            // punch-out: root minus the partial window before it, for lags < max order only (1.4.3 off-by-one)
+            const double partial = myac[((b - 1) * b / 2 + c / 2) * kAcStoreStride + lane];
+            ac_cur = (lane < max_this) ? FB_DSUB(myac[lane], partial) : partial;
+        }
+        if (lane <= max_this) ws.ac[lane] = ac_cur;
+        __syncwarp();
+        if (dg && step < kMaxApodSteps) { if (lane <= max_this) dg->autoc[step][lane] = ac_cur; if (lane == 0) { dg->lpc_order[step] = 0; dg->lpc_bits[step] = 0; } }
+        if (ws.ac[0] == 0.0) { __syncwarp(); continue; }
+
+        if (lane == 0) ws.misc[0] = levinson(ws.ac, max_this, ws.lp, ws.lperr, ws.lpc);
+        __syncwarp();
+        max_this = ws.misc[0];
+
+        // up: lpc.c FLAC__lpc_compute_best_order -- first strict minimum, initial best (uint32_t)-1
+        int guess;
+        {
+            const double escale = FB_DDIV(0.5, (double)N);
+            const uint32_t overhead = (uint32_t)sbps + P.qlp_precision;
+            double bits = 1.7976931348623157e308; bool ul = false;
+            if (lane >= 1 && lane <= max_this) {
+                const double e = expected_bits_per_sample(ws.lperr[lane - 1], escale, &ul);
+                bits = FB_DADD(FB_DMUL(e, (double)(N - lane)), (double)((uint32_t)lane * overhead));
+            }
+            double bb = bits; int bi = lane;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, bb, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob < bb || (ob == bb && oi < bi)) { bb = ob; bi = oi; }
+            }
+            guess = (bb < 4294967295.0) ? bi : 1;
+            // guard band: a runner-up within 1e-9 relative of the winner could flip under a libm log that
+            // differs in the last ulp (DESIGN.md "log guard"); counted, never silently ignored
+            const int ul_best = __shfl_sync(0xffffffffu, (int)ul, guess & 31);
+            const bool amb = (lane >= 1 && lane <= max_this && lane != guess) && (ul || ul_best) &&
+                             fabs(bits - bb) <= 1e-9 * fabs(bb);
+            if (__any_sync(0xffffffffu, amb) && lane == 0 && stats) atomicAdd(&stats->log_ambiguous, 1ull);
+        }
+        if (dg && step < kMaxApodSteps) { if (lane < max_this) dg->lpc_err[step][lane] = ws.lperr[lane]; if (lane == 0) dg->lpc_order[step] = guess; }
+
+        const int order = guess;
+        bool ul2;
+        const double rbps = expected_bits_per_sample(ws.lperr[order - 1], FB_DDIV(0.5, (double)(N - order)), &ul2);
+        if (ul2 && fabs(rbps - (double)sbps) <= 1e-9 * (double)sbps && lane == 0 && stats) atomicAdd(&stats->log_ambiguous, 1ull);
+        if (!(rbps >= (double)sbps)) {
+            int prec = (int)P.qlp_precision;
+            if (sbps <= 17) prec = min(prec, 32 - sbps - (int)ilog2_u32((uint32_t)order));
+            if (lane == 0) {
+                int sh = 0;
+                const int rc = quantize_coefficients(ws.lp + (order - 1) * kMaxOrder, order, prec, ws.q, &sh);
+                int32_t asum = 0;
+                for (int j = 0; j < order; j++) asum += abs(ws.q[j]);
+                if (asum == 0) asum = 1;
+                ws.misc[1] = rc; ws.misc[2] = sh; ws.misc[3] = (int)silog2((int64_t)asum);
+            }
+            __syncwarp();
+            if (ws.misc[1] == 0) {
+                const int shift = ws.misc[2];
+                // up: lpc.c FLAC__lpc_max_prediction_before_shift_bps / FLAC__lpc_max_residual_bps
+                const int pred_bps = sbps + ws.misc[3];
+                const int resid_bps = ((sbps > pred_bps - shift) ? sbps : pred_bps - shift) + 1;
+                const bool limit = resid_bps > 32;
+                int omax = omax_frame;
+                while (omax > 0 && (N >> omax) <= order) omax--;
+                const int nparts = 1 << omax, psize = N >> omax;
+                const bool narrow = (uint32_t)sbps + 4u < 32u - ilog2_u32((uint32_t)psize);
+                const SigView V = sig_view(s);
+                const bool rejected = residual_dispatch<PACKED>(limit || pred_bps > 32, order, V, G, ws.q, shift, psize, nparts, limit, psum, lane);
+                if (!rejected) {
+                    int po; uint32_t k0, k1;
+                    const uint32_t rb = rice_search(psum, N, order, omax, narrow, P.rice_limit, lane, &po, &k0, &k1);
+                    const uint32_t est = add_sat(8u + (uint32_t)wasted + 4u + 5u + (uint32_t)order * (uint32_t)(prec + sbps), rb);
+                    if (dg && lane == 0 && step < kMaxApodSteps) dg->lpc_bits[step] = est;
+                    SubframePlan& pl = step_plan[(size_t)s * n_steps + step];
+                    reinterpret_cast<uint32_t*>(&pl)[lane] = 0u;
+                    __syncwarp();
+                    if (lane < (1 << po)) pl.rice[lane] = (uint8_t)k0;
+                    if (lane + 32 < (1 << po)) pl.rice[lane + 32] = (uint8_t)k1;
+                    const bool r2 = __any_sync(0xffffffffu, (lane < (1 << po) && k0 >= 15u) || (lane + 32 < (1 << po) && k1 >= 15u));
+                    if (lane < order) pl.qlp[lane] = ws.q[lane];
+                    if (lane == 0) {
+                        pl.type = kLpc; pl.order = (uint8_t)order; pl.part_order = (uint8_t)po; pl.rice2 = r2; pl.bits_est = est; pl.shift = shift;
+                        pl.precision = (uint8_t)prec; pl.wasted = (uint8_t)wasted; pl.sbps = (uint8_t)sbps;
+                        S.step_bits[s][step] = est;
                     }
                 }
-                __syncwarp();
             }
-            step++;
+            __syncwarp();
         }
-        if (dg && lane == 0) dg->n_apod = step;
     }
-    __syncwarp();
+    __syncthreads();
 
-    // ---- publish the plan ----
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&ws.plan);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(plans + (size_t)blockIdx.x * nsig + sig);
+    // =================== selection: candidates in libFLAC's order, replace only on strict < ===================
+    for (int s = warp; s < nsig; s += kAnWarps) {
+        uint32_t best = S.best_bits[s];
+        int pick = -1;
+        if (sig_active(s))
+            for (int k = 0; k < n_steps; k++) { const uint32_t e = S.step_bits[s][k]; if (e < best) { best = e; pick = k; } }
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(pick < 0 ? &base_plan[s] : &step_plan[(size_t)s * n_steps + pick]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(plans + (size_t)blockIdx.x * nsig + s);
         dst[lane] = src[lane];     // 128 bytes = 32 words
-        if (lane == 0) sig_bits[sig] = best_bits;
+        if (lane == 0) {
+            if (dbg) {
+                bool need = false;
+                for (int k = 0; k < nneed; k++) need = need || (S.need_list[k] == s);
+                (dbg + (size_t)blockIdx.x * nsig + s)->n_apod = need ? n_steps : 0;
+            }
+            S.best_bits[s] = best;
+        }
     }
     __syncthreads();
 
     // ---- channel assignment (up: process_subframes_): first minimum of {L+R, L+S, R+S, M+S} ----
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         int ca = 0;
         if (P.loose_frames) {
-            if (mode == 0) ca = (sig_bits[2] + sig_bits[3] < sig_bits[0] + sig_bits[1]) ? 3 : 0;
+            if (mode == 0) ca = (S.best_bits[2] + S.best_bits[3] < S.best_bits[0] + S.best_bits[1]) ? 3 : 0;
             else ca = (mode == 1) ? 0 : 3;
         } else if (P.do_mid_side) {
-            const uint32_t bL = sig_bits[0], bR = sig_bits[1], bM = sig_bits[2], bS = sig_bits[3];
+            const uint32_t bL = S.best_bits[0], bR = S.best_bits[1], bM = S.best_bits[2], bS = S.best_bits[3];
             uint32_t minb = bL + bR;
             if (bL + bS < minb) { minb = bL + bS; ca = 1; }
             if (bR + bS < minb) { minb = bR + bS; ca = 2; }
@@ -569,43 +749,57 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
     }
 }
 
+// ------------------------------------------------------------------------------------------------ host side
+static bool packed_layout(const EncParams& P) { return P.container_bytes == 2 && P.channels == 2; }
+
+static uint32_t apod_steps(const EncParams& P) {
+    // up: set_next_subdivide_tukey: 1 (full) + 2 (depth 2) + 2b (depth b >= 3)
+    uint32_t n = 1;
+    for (uint32_t b = 2; b <= P.apod_parts; b++) n += (b == 2) ? 2u : 2u * b;
+    return P.max_lpc_order ? n : 0u;
+}
+
 // host-visible launcher (called from engine.cu)
 void launch_analyze(const void* pcm, const FrameDesc* frames, const float* windows, const EncParams& P, int n_frames,
                     SubframePlan* plans, uint8_t* frame_ca, SignalDebug* dbg, EncStats* stats, size_t smem_bytes,
                     cudaStream_t stream) {
-    const dim3 grid((unsigned)n_frames), block(32u * P.n_signals);
+    const dim3 grid((unsigned)n_frames), block(kAnThreads);
     // loose mid/side: decision frames first, then the frames that follow them (they read the decision from frame_ca)
     for (int pass = 0; pass < (P.loose_frames ? 2 : 1); pass++) {
-        if (P.container_bytes == 2) {
-            cudaFuncSetAttribute(analyze_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            analyze_kernel<int16_t><<<grid, block, smem_bytes, stream>>>((const int16_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats, pass);
+        if (packed_layout(P)) {
+            cudaFuncSetAttribute(analyze_kernel<int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            analyze_kernel<int16_t, true><<<grid, block, smem_bytes, stream>>>((const int16_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats, pass);
+        } else if (P.container_bytes == 2) {
+            cudaFuncSetAttribute(analyze_kernel<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            analyze_kernel<int16_t, false><<<grid, block, smem_bytes, stream>>>((const int16_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats, pass);
         } else {
-            cudaFuncSetAttribute(analyze_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            analyze_kernel<int32_t><<<grid, block, smem_bytes, stream>>>((const int32_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats, pass);
+            cudaFuncSetAttribute(analyze_kernel<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            analyze_kernel<int32_t, false><<<grid, block, smem_bytes, stream>>>((const int32_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats, pass);
         }
     }
 }
 
-// Shared-memory plan of the analysis kernel; fills P.pool_bytes / P.ac_gsz (called by the host before launching).
+// Shared-memory plan of the analysis kernel; fills P.pool_bytes (autocorrelation rings), P.ac_gsz (apodization
+// steps per signal) and P.an_stride (staged words per signal).  Called by the host before launching.
 void analyze_layout(EncParams& P) {
-    const uint32_t nsig = P.n_signals, L = (P.max_lpc_order ? P.max_lpc_order : 1) + 1;
-    const uint32_t gmax = (32 / L) < (uint32_t)kAcJobsMax ? (32 / L) : (uint32_t)kAcJobsMax;
-    uint32_t groups = 0, gsz_max = 1;
-    for (uint32_t b = 1; b <= P.apod_parts; b++) {
-        const uint32_t nj = nsig * b, ngrp = (nj + gmax - 1) / gmax, gsz = (nj + ngrp - 1) / ngrp;
-        groups += ngrp;
-        if (gsz > gsz_max) gsz_max = gsz;
-    }
-    const uint32_t active = groups < nsig ? groups : nsig;
-    const uint32_t ac_bytes = P.max_lpc_order ? active * gsz_max * kAcBufStride * 8u : 0u;
-    const uint32_t psum_bytes = nsig * 2u * kMaxParts * 8u;
-    P.ac_gsz = gsz_max;
-    P.pool_bytes = ((ac_bytes > psum_bytes ? ac_bytes : psum_bytes) + 15u) / 16u * 16u;
+    const uint32_t nsig = P.n_signals, L = (P.max_lpc_order ? P.max_lpc_order : 1) + 1, pairs = (L + 1) / 2;
+    const uint32_t gmax = (32 / pairs) < (uint32_t)kAcJobsMax ? (32 / pairs) : (uint32_t)kAcJobsMax;
+    uint32_t groups = 0;
+    for (uint32_t b = 1; b <= P.apod_parts; b++) groups += (nsig * b + gmax - 1) / gmax;
+    const uint32_t areas = groups < (uint32_t)kAnWarps ? groups : (uint32_t)kAnWarps;
+    const uint32_t ring_bytes = P.max_lpc_order ? areas * kAcJobsMax * kAcRing * 8u : 0u, ws_bytes = (uint32_t)(kAnWarps * sizeof(WarpScratch));
+    P.pool_bytes = ring_bytes > ws_bytes ? ring_bytes : ws_bytes;     // rings (phase A) and LPC scratch (phase B) share the pool
+    P.ac_gsz = apod_steps(P);
+    // 32 rows of ceil(N/32) samples with an odd row stride
+    const uint32_t b0 = (P.blocksize + 31) / 32, rs = b0 | 1u;
+    P.an_stride = ((32u * rs + 3u) / 4u) * 4u;
 }
 
 size_t analyze_smem_bytes(const EncParams& P) {
-    return (size_t)P.n_signals * P.smem_stride * 4 + P.pool_bytes + (size_t)P.n_signals * sizeof(WarpScratch) +
-           (size_t)P.n_signals * (P.apod_parts * (P.apod_parts + 1) / 2) * kAcStoreStride * sizeof(double) + kMaxSignals * 4 * 4 + 64;
+    const size_t nsig = P.n_signals, nwin = P.apod_parts * (P.apod_parts + 1) / 2;
+    return (size_t)(packed_layout(P) ? 1 : nsig) * P.an_stride * 4 + P.pool_bytes + nsig * nwin * kAcStoreStride * sizeof(double) +
+           (size_t)kAnWarps * 2 * kMaxParts * 8 + nsig * sizeof(SubframePlan) +
+           nsig * P.ac_gsz * sizeof(SubframePlan) + sizeof(AnShared) + 64;
 }
 
 }  // namespace fb

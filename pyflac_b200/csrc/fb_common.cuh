@@ -35,6 +35,7 @@ struct EncParams {
     uint32_t smem_stride;        // int32 words reserved per signal in shared memory (>= max blocksize, multiple of 4)
     uint32_t pool_bytes;         // analysis kernel: partition-sum area aliased with the autocorrelation rings
     uint32_t ac_gsz;             // analysis kernel: (signal, window) jobs packed per warp in the autocorrelation phase
+    uint32_t an_stride;          // analysis kernel: int32 words staged per signal (32 padded rows)
     uint32_t loose_frames;       // loose mid/side (levels 1, 4 on stereo): a full L/R/M/S decision every this many frames; 0 = off
     uint32_t limit_min_bitrate;  // up: process_subframes_ -- never emit a frame made of constant subframes only
 };
