@@ -7,20 +7,21 @@
 // smallest libFLAC bit estimate.  Output: one 128-byte SubframePlan per signal + one channel-assignment
 // byte per frame; the pack kernel (enc_pack.cu) turns plans into bits.
 //
-// Layout of the work (B200: latency/issue bound, so the design minimises instructions and keeps many
-// frames resident per SM):
-//  * The frame is staged ONCE into shared memory in its container form -- for 16-bit stereo the raw
-//    interleaved words (L | R << 16), 16 KiB per 4096-sample frame, mid/side derived on the fly; for every
-//    other shape one int32 row block per signal.  Rows of B0 = ceil(N/32) samples, row stride odd, so both
-//    access patterns below are bank-conflict free.
-//  * Streaming passes (fixed-predictor sums, residual + partition sums) give lane p the contiguous samples
-//    [p*B0, (p+1)*B0): one shared load per sample, the predictor history lives in registers (statically
-//    rotated window), partition sums leave the lane through a handful of shared atomics.
-//  * The autocorrelation is one DFMA chain per lag in ascending sample order (products of two floats are
-//    exact in double, so fma == libFLAC's mul+add).  A lane owns the two chains (2p, 2p+1) of one
-//    (signal, window) job, up to four jobs per warp: one warp carries all four signals of a stereo frame.
-//  * Work items (autocorrelation groups, per-signal fixed analysis, per (signal, apodization step) LPC
-//    evaluation) are handed to the four warps through a shared-memory queue, long items first.
+// Three kernels per batch (B200: this path is latency/issue bound, so each kernel keeps its warps doing one kind of
+// work, minimises instructions and keeps many frames resident per SM):
+//  * frame_bits_kernel -- OR / AND of every signal of every frame (wasted bits, constant detection): one warp per
+//    frame, pure streaming.
+//  * autoc_kernel -- the autocorrelations of all (frame, signal, window) jobs.  One DFMA chain per lag in ascending
+//    sample order (products of two floats are exact in double, so fma == libFLAC's mul+add).  A lane owns four
+//    consecutive lags of one job, a warp carries up to eight jobs (two stereo frames), jobs are independent warps:
+//    no barriers, PCM read straight from HBM/L2, a 640-byte ring of windowed doubles per job in shared memory.
+//  * analyze_kernel -- one CTA of four warps per frame.  The frame is staged ONCE into shared memory in its
+//    container form -- for 16-bit stereo the raw interleaved words (L | R << 16), 16 KiB per 4096-sample frame,
+//    mid/side derived on the fly; for every other shape one int32 row block per signal.  Rows of B0 = ceil(N/32)
+//    samples with an odd row stride: lane p streams the contiguous samples [p*B0, (p+1)*B0) bank-conflict free, one
+//    shared load per sample, predictor history in registers (statically rotated window), partition sums leave the
+//    lane through a handful of shared atomics.  Work items (per-signal fixed analysis, then one LPC evaluation per
+//    (signal, apodization step)) are handed to the four warps through a shared-memory queue.
 //
 // Exactness: integer work is exact; floating point follows fb_math.cuh (unfused, RN).  No tensor cores:
 // this is integer / bit-serial work, not a dense contraction.
@@ -31,8 +32,9 @@ namespace fb {
 
 constexpr int kAnThreads = 128;
 constexpr int kAnWarps = kAnThreads / 32;
-constexpr int kAcJobsMax = 4;          // (signal, window) jobs carried by one warp
-constexpr int kAcRing = 112;           // doubles per job: 16 mirror + 3 slots of 32
+constexpr int kAcJobsMax = 8;          // (frame, signal, window) jobs carried by one warp of the autocorrelation kernel
+constexpr int kAcRing = 82;            // doubles per job: 16 mirror + 2 slots of 32 (+2: jobs land in different bank groups)
+constexpr int kAcThreads = 128;        // autocorrelation kernel: four independent warps per CTA
 constexpr int kAcStoreStride = 14;     // lags kept per (signal, window): 13 + the unused odd partner
 constexpr int kMaxSteps = kMaxApodSteps;
 
@@ -253,90 +255,268 @@ __device__ __forceinline__ void fixed_error_sums_rt(const SigView& V, const Fram
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-frame record shared by the three kernels: OR / AND of every signal, then the autocorrelations
+// [signal][window][kAcStoreStride] (doubles).
+struct FrameBits { uint32_t or_[kMaxSignals], and_[kMaxSignals]; };
+__device__ __forceinline__ const FrameBits* frame_bits(const unsigned char* work, size_t stride, int f) {
+    return reinterpret_cast<const FrameBits*>(work + (size_t)f * stride);
+}
+__device__ __forceinline__ double* frame_ac(unsigned char* work, size_t stride, int f) {
+    return reinterpret_cast<double*>(work + (size_t)f * stride + sizeof(FrameBits));
+}
+__device__ __forceinline__ int wasted_from_or(uint32_t o, int bps) { const int w = o ? (__ffs((int)o) - 1) : 0; return w > bps ? bps : w; }
+
+// up: process_subframes_ + get_wasted_bits_: OR of all samples gives the wasted bits, OR == AND means
+// every sample is equal (constant subframe).  One warp per frame.
+template <typename PcmT, bool PACKED>
+__global__ void __launch_bounds__(128)
+frame_bits_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, int n_frames, EncParams P,
+                  unsigned char* __restrict__ work, size_t work_stride) {
+    const int lane = threadIdx.x & 31, f = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (f >= n_frames) return;
+    const FrameDesc fd = frames[f];
+    const int N = (int)fd.blocksize, ch = (int)P.channels, nsig = (int)P.n_signals;
+    const PcmT* base = pcm + fd.pcm_off;
+    FrameBits* out = reinterpret_cast<FrameBits*>(work + (size_t)f * work_stride);
+    if (PACKED) {
+        uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0, a0 = ~0u, a1 = ~0u, a2 = ~0u, a3 = ~0u;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(base) & 3u) == 0);
+        for (int i = lane; i < N; i += 32) {
+            int wd;
+            if (aligned) wd = __ldg(reinterpret_cast<const int*>(base) + i);
+            else wd = (int)((uint32_t)(uint16_t)__ldg(base + 2 * i) | ((uint32_t)(uint16_t)__ldg(base + 2 * i + 1) << 16));
+            const int lo = (int)(short)wd, hi = wd >> 16, m = (lo + hi) >> 1, sd = lo - hi;
+            o0 |= (uint32_t)lo; o1 |= (uint32_t)hi; o2 |= (uint32_t)m; o3 |= (uint32_t)sd;
+            a0 &= (uint32_t)lo; a1 &= (uint32_t)hi; a2 &= (uint32_t)m; a3 &= (uint32_t)sd;
+        }
+        o0 = __reduce_or_sync(0xffffffffu, o0); o1 = __reduce_or_sync(0xffffffffu, o1);
+        o2 = __reduce_or_sync(0xffffffffu, o2); o3 = __reduce_or_sync(0xffffffffu, o3);
+        a0 = __reduce_and_sync(0xffffffffu, a0); a1 = __reduce_and_sync(0xffffffffu, a1);
+        a2 = __reduce_and_sync(0xffffffffu, a2); a3 = __reduce_and_sync(0xffffffffu, a3);
+        if (lane == 0) {
+            out->or_[0] = o0; out->or_[1] = o1; out->or_[2] = o2; out->or_[3] = o3;
+            out->and_[0] = a0; out->and_[1] = a1; out->and_[2] = a2; out->and_[3] = a3;
+        }
+    } else {
+        for (int s = 0; s < nsig; s++) {
+            uint32_t o = 0, a = ~0u;
+            for (int i = lane; i < N; i += 32) {
+                int v;
+                if (s < ch) v = (int)__ldg(base + (uint64_t)i * ch + s);
+                else {
+                    const int l = (int)__ldg(base + (uint64_t)i * ch), r = (int)__ldg(base + (uint64_t)i * ch + 1);
+                    v = (s == ch) ? ((l + r) >> 1) : (l - r);
+                }
+                o |= (uint32_t)v; a &= (uint32_t)v;
+            }
+            o = __reduce_or_sync(0xffffffffu, o); a = __reduce_and_sync(0xffffffffu, a);
+            if (lane == 0) { out->or_[s] = o; out->and_[s] = a; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Sequential double autocorrelation (up: lpc.c FLAC__lpc_compute_autocorrelation) of
-// windowed segments (up: FLAC__lpc_window_data / _partial) for a group of up to four
-// (signal, window) jobs of equal length.  Lane = (job, pair): it owns the chains of lags 2*pair and
-// 2*pair+1; the second chain reuses the first one's lagged operand of the previous step, so two steps cost
-// one 16-byte shared load for the current values, one for the lagged values and four DFMAs.
-// Each chain is strictly sequential in i (one rounding per add, ascending i).
+// windowed segments (up: FLAC__lpc_window_data / _partial).
 //
-// Per job a ring of three 32-sample slots of doubles (plus a 16-entry mirror of slot 2's tail in front of
-// slot 0, so "i - lag" is always a plain negative offset).  While the 32 steps of chunk c run, the same warp
-// windows chunk c+1 (f32 multiply, widen to f64) into the next slot.
+// A job = one (frame, signal, window).  Jobs of one window depth b are numbered frame-major and dealt to warps in
+// runs of kAcJobsMax; the warp runs max(len) steps (shorter jobs continue with zero samples, which leave their
+// accumulators unchanged).  Lane = (job, quad): it owns the chains of lags 4q .. 4q+3; lags beyond the first reuse
+// the lagged operands of the previous steps from registers, so two steps cost one 16-byte shared load for the
+// current values, one for the lagged values and eight DFMAs.  Each chain is strictly sequential in i (one rounding
+// per add, ascending i).
+//
+// Per job a ring of two 32-sample slots of doubles (plus a 16-entry mirror of slot 1's tail in front of slot 0, so
+// "i - lag" is always a plain negative offset).  The inputs of chunk c+1 are fetched from HBM/L2 before the chains of
+// chunk c run and are windowed (f32 multiply, widen to f64) into the other slot after them.
 //   segment sample i:  i <  part          : x[off+i] * w[i]
 //                      part <= i < 2*part : x[off+i] * w[N-2*part+i]
 //                      i == 2*part        : 0            (full window: part = N)
-struct AcGroup {
-    SigView v[kAcJobsMax];
-    int off[kAcJobsMax];
-    int cnt;
+struct __align__(16) AcJob {
+    const void* base;        // first container element of the segment (frame base + off * channels)
+    int32_t  sel;            // c0 | c1 << 8 | (ca & 0xff) << 16 | (cb & 0xff) << 24: value = (x[c0]*ca + x[c1]*cb) >> sh
+    int32_t  sh;
+    int32_t  len, part, N;
+    uint32_t woff;           // window table offset of the frame's blocksize
 };
 
-template <bool PACKED>
-__device__ __forceinline__ void ac_fetch(const AcGroup& J, const FrameGeo& G, const float* __restrict__ w, int part, int len,
-                                         int base, int lane, float& wv, int (&xv)[kAcJobsMax]) {
-    const int i = base + lane;
-    const bool in = (i < len) && (i < 2 * part);
-    wv = 0.0f;
-#pragma unroll
-    for (int b = 0; b < kAcJobsMax; b++) xv[b] = 0;
-    if (in) {
-        wv = __ldg(w + (i < part ? i : G.N - 2 * part + i));
-#pragma unroll
-        for (int b = 0; b < kAcJobsMax; b++) if (b < J.cnt) xv[b] = sig_word<PACKED>(J.v[b].base[pidx(G, J.off[b] + i)], J.v[b]);
+template <typename PcmT, bool PACKED>
+__device__ __forceinline__ float ac_fetch(const AcJob& J, const float* __restrict__ windows, int ch, int i) {
+    const bool in = (i < J.len) && (i < 2 * J.part);
+    if (!in) return 0.0f;
+    const float wv = __ldg(windows + J.woff + (i < J.part ? i : J.N - 2 * J.part + i));
+    const int ca = (int)(signed char)(J.sel >> 16), cb = (int)(signed char)(J.sel >> 24);
+    int v;
+    if (PACKED) {
+        const PcmT* b = reinterpret_cast<const PcmT*>(J.base);
+        int wd;
+        if ((reinterpret_cast<uintptr_t>(b) & 3u) == 0) wd = __ldg(reinterpret_cast<const int*>(b) + i);
+        else wd = (int)((uint32_t)(uint16_t)__ldg(b + 2 * i) | ((uint32_t)(uint16_t)__ldg(b + 2 * i + 1) << 16));
+        const int lo = (int)(short)wd, hi = wd >> 16;
+        v = (lo * ca + hi * cb) >> J.sh;
+    } else {
+        const PcmT* b = reinterpret_cast<const PcmT*>(J.base) + (size_t)i * ch;
+        const int x0 = (int)__ldg(b + (J.sel & 0xff));
+        v = x0 * ca;
+        if (cb) v += (int)__ldg(b + ((J.sel >> 8) & 0xff)) * cb;
+        v >>= J.sh;
     }
+    return FB_FMUL(__int2float_rn(v), wv);
 }
 
-// windowed samples of one chunk -> ring slot `slot` (slot 2 also feeds the mirror in front of slot 0)
-__device__ __forceinline__ void ac_store(double* __restrict__ buf, int cnt, int slot, float wv, const int (&xv)[kAcJobsMax], int lane) {
+struct AcSource {            // packed layout: what the nsig jobs of one (frame, window) share
+    const int16_t* base;
+    int len, part;
+    int wofs, wtail;         // window index = wofs + i (i < part) or wtail + i (part <= i < 2*part)
+    uint32_t shpack;         // right shift of signal s in byte s (wasted bits; +1 for mid)
+};
+
+template <typename PcmT, bool PACKED>
+__device__ __forceinline__ void ac_fetch_all(float (&dv)[kAcJobsMax], const AcSource (&src)[2], const AcJob* __restrict__ jobs,
+                                             int jobs_per_warp, int nsig, const float* __restrict__ windows, int ch, int i) {
+    if (PACKED) {
 #pragma unroll
-    for (int b = 0; b < kAcJobsMax; b++) {
-        if (b < cnt) {
-            const double d = (double)FB_FMUL(__int2float_rn(xv[b]), wv);
-            buf[b * kAcRing + 16 + slot * 32 + lane] = d;
-            if (slot == 2 && lane >= 16) buf[b * kAcRing + lane - 16] = d;
+        for (int u = 0; u < 2; u++) {
+            float wv = 0.0f; int lo = 0, hi = 0;
+            if (i < src[u].len && i < 2 * src[u].part) {
+                wv = __ldg(windows + (i < src[u].part ? src[u].wofs : src[u].wtail) + i);
+                int wd;
+                if ((reinterpret_cast<uintptr_t>(src[u].base) & 3u) == 0) wd = __ldg(reinterpret_cast<const int*>(src[u].base) + i);
+                else wd = (int)((uint32_t)(uint16_t)__ldg(src[u].base + 2 * i) | ((uint32_t)(uint16_t)__ldg(src[u].base + 2 * i + 1) << 16));
+                lo = (int)(short)wd; hi = wd >> 16;
+            }
+            const uint32_t sp = src[u].shpack;
+            dv[4 * u + 0] = FB_FMUL(__int2float_rn(lo >> (sp & 0xff)), wv);
+            dv[4 * u + 1] = FB_FMUL(__int2float_rn(hi >> ((sp >> 8) & 0xff)), wv);
+            if (nsig > 2) {
+                dv[4 * u + 2] = FB_FMUL(__int2float_rn((lo + hi) >> ((sp >> 16) & 0xff)), wv);
+                dv[4 * u + 3] = FB_FMUL(__int2float_rn((lo - hi) >> (sp >> 24)), wv);
+            } else {        // two signals per source: jobs 0,1 | 2,3 (sources beyond the second stay empty)
+                dv[4 * u + 2] = 0.0f; dv[4 * u + 3] = 0.0f;
+            }
         }
+        if (nsig == 2) { dv[2] = dv[4]; dv[3] = dv[5]; dv[4] = dv[5] = 0.0f; }
+    } else {
+#pragma unroll
+        for (int q = 0; q < kAcJobsMax; q++) dv[q] = (q < jobs_per_warp) ? ac_fetch<PcmT, PACKED>(jobs[q], windows, ch, i) : 0.0f;
     }
 }
 
-template <bool PACKED>
-__device__ __noinline__ void autoc_group(const AcGroup& J, FrameGeo G, const float* __restrict__ w, int part, int len, int pairs,
-                                         double* __restrict__ buf, int lane, double& out_a, double& out_b) {
-    const int jb = lane / pairs, pr = lane - jb * pairs;
-    const bool active = jb < J.cnt;
-    const double* jobbuf = buf + (active ? jb : 0) * kAcRing;
-    const int lag2 = active ? 2 * pr : 0;
-    for (int idx = lane; idx < J.cnt * 16; idx += 32) buf[(idx >> 4) * kAcRing + (idx & 15)] = 0.0;
-    {
-        float wv; int xv[kAcJobsMax];
-        ac_fetch<PACKED>(J, G, w, part, len, 0, lane, wv, xv);
-        ac_store(buf, J.cnt, 0, wv, xv, lane);
+template <typename PcmT, bool PACKED>
+__global__ void __launch_bounds__(kAcThreads, 8)
+autoc_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, int n_frames, const float* __restrict__ windows,
+             EncParams P, unsigned char* __restrict__ work, size_t work_stride, int lanes_per_job, int jobs_per_warp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nsig = (int)P.n_signals, ch = (int)P.channels;
+    const int nwin = (int)(P.apod_parts * (P.apod_parts + 1) / 2);
+    double* ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * kAcJobsMax * kAcRing;
+    AcJob* jobs = reinterpret_cast<AcJob*>(smem_raw + (size_t)(kAcThreads / 32) * kAcJobsMax * kAcRing * 8) + warp * kAcJobsMax;
+
+    // ---- which jobs does this warp own?  depth b = 1..parts, each depth padded to whole warps ----
+    long long W = (long long)blockIdx.x * (kAcThreads / 32) + warp;
+    int b = 1;
+    for (;; b++) {
+        if (b > (int)P.apod_parts) return;
+        const long long nj = (long long)n_frames * nsig * b, nw = (nj + jobs_per_warp - 1) / jobs_per_warp;
+        if (W < nw) break;
+        W -= nw;
     }
+    const long long r0 = W * jobs_per_warp, nj = (long long)n_frames * nsig * b;
+    if (lane < jobs_per_warp) {
+        AcJob J;
+        J.base = nullptr; J.sel = 0; J.sh = 0; J.len = 0; J.part = 0; J.N = 0; J.woff = 0;
+        const long long r = r0 + lane;
+        if (r < nj) {
+            const int f = (int)(r / (nsig * b)), rem = (int)(r - (long long)f * (nsig * b)), k = rem / nsig, s = rem - k * nsig;
+            const FrameDesc fd = frames[f];
+            const int N = (int)fd.blocksize;
+            if (N > 4 && !(b > 1 && N / b <= 32)) {
+                const FrameBits* fb = frame_bits(work, work_stride, f);
+                const int wst = wasted_from_or(fb->or_[s], (int)P.bps);
+                const int off = (k * N) / b;
+                J.base = pcm + fd.pcm_off + (size_t)off * ch;
+                int c0, c1, ca, cb, sh = wst;
+                if (s < ch) { c0 = s; c1 = s; ca = 1; cb = 0; if (PACKED && s == 1) { ca = 0; cb = 1; } }
+                else if (s == ch) { c0 = 0; c1 = 1; ca = 1; cb = 1; sh = wst + 1; }
+                else { c0 = 0; c1 = 1; ca = 1; cb = -1; }
+                J.sel = c0 | (c1 << 8) | ((ca & 0xff) << 16) | ((cb & 0xff) << 24);
+                J.sh = sh; J.len = N / b; J.part = (b == 1) ? N : N / b / 2; J.N = N; J.woff = fd.window_off;
+            }
+        }
+        jobs[lane] = J;
+    }
+    for (int idx = lane; idx < jobs_per_warp * 16; idx += 32) ring[(idx >> 4) * kAcRing + (idx & 15)] = 0.0;
     __syncwarp();
-    double acc_a = 0.0, acc_b = 0.0;
-    const int nchunks = (len + 31) >> 5;
-    int slot = 0;
-    for (int c = 0; c < nchunks; c++) {
-        float wv; int xv[kAcJobsMax];
-        ac_fetch<PACKED>(J, G, w, part, len, (c + 1) * 32, lane, wv, xv);   // inputs of the next chunk: latency hides under the chains
-        const double* curp = jobbuf + 16 + slot * 32;
-        const double* lagp = curp - lag2;
-        double prev = lagp[-1];
+    int maxlen = 0;
+    for (int q = 0; q < jobs_per_warp; q++) maxlen = max(maxlen, jobs[q].len);
+    if (maxlen == 0) return;
+
+    // Packed 16-bit stereo: the nsig jobs of one (frame, window) read the same words and window values, so the warp
+    // fetches per SOURCE (two of them) and derives left / right / mid / side from the one word; their geometry lives
+    // in registers.  Other layouts fetch per job from the descriptors in shared memory.
+    AcSource src[2];
+    if (PACKED) {
 #pragma unroll
-        for (int s = 0; s < 32; s += 2) {
-            const double2 c2 = *reinterpret_cast<const double2*>(curp + s);
-            const double2 l2 = *reinterpret_cast<const double2*>(lagp + s);
-            acc_a = fma(c2.x, l2.x, acc_a);
-            acc_b = fma(c2.x, prev, acc_b);
-            acc_a = fma(c2.y, l2.y, acc_a);
-            acc_b = fma(c2.y, l2.x, acc_b);
-            prev = l2.y;
+        for (int u = 0; u < 2; u++) {
+            const AcJob& J0 = jobs[u * nsig < jobs_per_warp ? u * nsig : 0];
+            src[u].base = reinterpret_cast<const int16_t*>(J0.base); src[u].len = (u * nsig < jobs_per_warp) ? J0.len : 0;
+            src[u].part = J0.part; src[u].wofs = (int)J0.woff; src[u].wtail = (int)J0.woff + J0.N - 2 * J0.part;
+            uint32_t shp = 0;
+            for (int s2 = 0; s2 < nsig; s2++) shp |= (uint32_t)(jobs[(u * nsig + s2) < jobs_per_warp ? u * nsig + s2 : 0].sh & 0xff) << (8 * s2);
+            src[u].shpack = shp;
         }
-        slot = (slot == 2) ? 0 : slot + 1;
-        ac_store(buf, J.cnt, slot, wv, xv, lane);
+    }
+    float dv[kAcJobsMax];
+    ac_fetch_all<PcmT, PACKED>(dv, src, jobs, jobs_per_warp, nsig, windows, ch, lane);
+#pragma unroll
+    for (int q = 0; q < kAcJobsMax; q++) if (q < jobs_per_warp) ring[q * kAcRing + 16 + lane] = (double)dv[q];
+    __syncwarp();
+
+    const int jb = lane / lanes_per_job, qd = lane - jb * lanes_per_job;
+    const bool active = jb < jobs_per_warp;
+    const double* jobring = ring + (active ? jb : 0) * kAcRing;
+    const int lag0 = 4 * qd;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;       // chains of lags lag0 .. lag0+3
+    double p1 = 0.0, p2 = 0.0, p3 = 0.0;                 // lagged operands of the three previous steps
+    const int nchunks = (maxlen + 31) >> 5;
+    for (int c = 0; c < nchunks; c++) {
+        const int slot = c & 1;
+        ac_fetch_all<PcmT, PACKED>(dv, src, jobs, jobs_per_warp, nsig, windows, ch, (c + 1) * 32 + lane);
+        if (active) {
+            const double* curp = jobring + 16 + slot * 32;
+            const double* lagp = curp - lag0;
+#pragma unroll
+            for (int s = 0; s < 32; s += 2) {
+                const double2 c2 = *reinterpret_cast<const double2*>(curp + s);
+                const double2 l2 = *reinterpret_cast<const double2*>(lagp + s);
+                a0 = fma(c2.x, l2.x, a0); a1 = fma(c2.x, p1, a1); a2 = fma(c2.x, p2, a2); a3 = fma(c2.x, p3, a3);
+                a0 = fma(c2.y, l2.y, a0); a1 = fma(c2.y, l2.x, a1); a2 = fma(c2.y, p1, a2); a3 = fma(c2.y, p2, a3);
+                p3 = p1; p2 = l2.x; p1 = l2.y;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < kAcJobsMax; q++) {
+            if (q < jobs_per_warp) {
+                const double d = (double)dv[q];
+                ring[q * kAcRing + 16 + (slot ^ 1) * 32 + lane] = d;
+                if (slot == 0 && lane >= 16) ring[q * kAcRing + lane - 16] = d;      // slot 1's tail mirrored in front of slot 0
+            }
+        }
         __syncwarp();
     }
-    out_a = acc_a; out_b = acc_b;
+    if (active) {
+        const long long r = r0 + jb;
+        if (r < nj && jobs[jb].len > 0) {
+            const int f = (int)(r / (nsig * b)), rem = (int)(r - (long long)f * (nsig * b)), k = rem / nsig, s = rem - k * nsig;
+            double* dst = frame_ac(work, work_stride, f) + ((size_t)s * nwin + (b - 1) * b / 2 + k) * kAcStoreStride + lag0;
+            if (lag0 + 0 < kAcStoreStride) dst[0] = a0;
+            if (lag0 + 1 < kAcStoreStride) dst[1] = a1;
+            if (lag0 + 2 < kAcStoreStride) dst[2] = a2;
+            if (lag0 + 3 < kAcStoreStride) dst[3] = a3;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -354,7 +534,8 @@ template <typename PcmT, bool PACKED>
 __global__ void __launch_bounds__(kAnThreads, PACKED ? 8 : 3)
 analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, const float* __restrict__ windows,
                EncParams P, SubframePlan* __restrict__ plans, uint8_t* __restrict__ frame_ca,
-               SignalDebug* __restrict__ dbg, EncStats* __restrict__ stats, int pass) {
+               SignalDebug* __restrict__ dbg, EncStats* __restrict__ stats, int pass,
+               unsigned char* __restrict__ work, size_t work_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nsig = (int)P.n_signals;
@@ -384,9 +565,8 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
     const int nwin = (int)(P.apod_parts * (P.apod_parts + 1) / 2);
     int32_t* xall = reinterpret_cast<int32_t*>(smem_raw);
     unsigned char* cur = smem_raw + (size_t)(PACKED ? 1 : nsig) * sig_words * 4;
-    double* acbuf_all = reinterpret_cast<double*>(cur);                          // phase A: autocorrelation rings ...
-    WarpScratch* wsall = reinterpret_cast<WarpScratch*>(cur);                    cur += (size_t)P.pool_bytes;   // ... phase B: LPC scratch
-    double* acstore = reinterpret_cast<double*>(cur);                            cur += (size_t)nsig * nwin * kAcStoreStride * sizeof(double);
+    WarpScratch* wsall = reinterpret_cast<WarpScratch*>(cur);                    cur += (size_t)kAnWarps * sizeof(WarpScratch);
+    const double* acstore = frame_ac(work, work_stride, (int)blockIdx.x);        // [nsig][nwin][kAcStoreStride], written by autoc_kernel
     unsigned long long* psum_all = reinterpret_cast<unsigned long long*>(cur);   cur += (size_t)kAnWarps * 2 * kMaxParts * 8;
     SubframePlan* base_plan = reinterpret_cast<SubframePlan*>(cur);              cur += (size_t)nsig * sizeof(SubframePlan);
     SubframePlan* step_plan = reinterpret_cast<SubframePlan*>(cur);              cur += (size_t)nsig * n_steps * sizeof(SubframePlan);
@@ -395,40 +575,29 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
     unsigned long long* psum = psum_all + (size_t)warp * 2 * kMaxParts;
     WarpScratch& ws = wsall[warp];
 
-    if (tid < kMaxSignals) { S.sig_or[tid] = 0u; S.sig_and[tid] = 0xffffffffu; S.best_bits[tid] = 0u; }
+    if (tid < kMaxSignals) {
+        const FrameBits* fb = frame_bits(work, work_stride, (int)blockIdx.x);
+        S.sig_or[tid] = tid < nsig ? fb->or_[tid] : 0u; S.sig_and[tid] = tid < nsig ? fb->and_[tid] : 0xffffffffu; S.best_bits[tid] = 0u;
+    }
     if (tid == 0) { S.queue_a = 0; S.queue_b = 0; S.nneed = 0; }
     for (int i = tid; i < kMaxSignals * kMaxSteps; i += kAnThreads) (&S.step_bits[0][0])[i] = 0xffffffffu;
-    __syncthreads();
 
-    // =================== stage the frame; OR / AND of every signal (wasted bits, constant detection) ===================
-    // up: process_subframes_ + get_wasted_bits_
+    // =================== stage the frame (container form) ===================
     {
         const PcmT* base = pcm + fd.pcm_off;
         if (PACKED) {
-            uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0, a0 = ~0u, a1 = ~0u, a2 = ~0u, a3 = ~0u;
             const bool aligned = ((reinterpret_cast<uintptr_t>(base) & 3u) == 0);
             for (int i = tid; i < N; i += kAnThreads) {
                 int wd;
                 if (aligned) wd = __ldg(reinterpret_cast<const int*>(base) + i);
                 else wd = (int)((uint32_t)(uint16_t)__ldg(base + 2 * i) | ((uint32_t)(uint16_t)__ldg(base + 2 * i + 1) << 16));
                 xall[pidx(G, i)] = wd;
-                const int lo = (int)(short)wd, hi = wd >> 16, m = (lo + hi) >> 1, sd = lo - hi;
-                o0 |= (uint32_t)lo; o1 |= (uint32_t)hi; o2 |= (uint32_t)m; o3 |= (uint32_t)sd;
-                a0 &= (uint32_t)lo; a1 &= (uint32_t)hi; a2 &= (uint32_t)m; a3 &= (uint32_t)sd;
-            }
-            o0 = __reduce_or_sync(0xffffffffu, o0); o1 = __reduce_or_sync(0xffffffffu, o1);
-            o2 = __reduce_or_sync(0xffffffffu, o2); o3 = __reduce_or_sync(0xffffffffu, o3);
-            a0 = __reduce_and_sync(0xffffffffu, a0); a1 = __reduce_and_sync(0xffffffffu, a1);
-            a2 = __reduce_and_sync(0xffffffffu, a2); a3 = __reduce_and_sync(0xffffffffu, a3);
-            if (lane == 0) {
-                atomicOr(&S.sig_or[0], o0); atomicOr(&S.sig_or[1], o1); atomicAnd(&S.sig_and[0], a0); atomicAnd(&S.sig_and[1], a1);
-                if (nsig > 2) { atomicOr(&S.sig_or[2], o2); atomicOr(&S.sig_or[3], o3); atomicAnd(&S.sig_and[2], a2); atomicAnd(&S.sig_and[3], a3); }
             }
         } else {
             for (int s = 0; s < nsig; s++) {
                 if (!sig_active(s)) continue;
                 int32_t* x = xall + (size_t)s * sig_words;
-                uint32_t o = 0, a = ~0u;
+                const int wst = wasted_from_or(frame_bits(work, work_stride, (int)blockIdx.x)->or_[s], (int)P.bps);   // rows hold the signal with wasted bits removed
                 for (int i = tid; i < N; i += kAnThreads) {
                     int v;
                     if (s < ch) v = (int)__ldg(base + (uint64_t)i * ch + s);
@@ -436,18 +605,15 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
                         const int l = (int)__ldg(base + (uint64_t)i * ch), r = (int)__ldg(base + (uint64_t)i * ch + 1);
                         v = (s == ch) ? ((l + r) >> 1) : (l - r);
                     }
-                    x[pidx(G, i)] = v;
-                    o |= (uint32_t)v; a &= (uint32_t)v;
+                    x[pidx(G, i)] = v >> wst;
                 }
-                o = __reduce_or_sync(0xffffffffu, o); a = __reduce_and_sync(0xffffffffu, a);
-                if (lane == 0) { atomicOr(&S.sig_or[s], o); atomicAnd(&S.sig_and[s], a); }
             }
         }
     }
     __syncthreads();
 
     // per-signal facts every thread can derive on its own
-    auto sig_wasted = [&](int s) { const uint32_t o = S.sig_or[s]; const int wst = o ? (__ffs((int)o) - 1) : 0; return wst > (int)P.bps ? (int)P.bps : wst; };
+    auto sig_wasted = [&](int s) { return wasted_from_or(S.sig_or[s], (int)P.bps); };
     auto sig_sbps = [&](int s) { return (int)P.bps - sig_wasted(s) + ((P.do_mid_side && s == ch + 1) ? 1 : 0); };
     auto sig_view = [&](int s) {
         SigView V;
@@ -455,12 +621,6 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
         else { V.base = xall + (size_t)s * sig_words; V.ca = 1; V.cb = 0; V.sh = 0; }
         return V;
     };
-    if (!PACKED) {      // plain rows are stored with the wasted bits already removed
-        for (int s = 0; s < nsig; s++) {
-            const int wst = sig_active(s) ? sig_wasted(s) : 0;
-            if (wst) { int32_t* x = xall + (size_t)s * sig_words; for (int i = tid; i < sig_words; i += kAnThreads) x[i] >>= wst; }
-        }
-    }
     // up: process_subframe_ constant test + process_subframes_ limit_min_bitrate: when every earlier channel is
     // constant, the last channel (and mid/side after it) may not use a constant subframe
     auto sig_const = [&](int s) { return N > 4 && S.sig_or[s] == S.sig_and[s]; };
@@ -480,55 +640,15 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
     __syncthreads();
     const int nneed = S.nneed;
 
-    // =================== phase A: autocorrelation groups (long) and per-signal fixed analysis, from a queue ===================
-    const int L = max_lpc + 1, pairs = (L + 1) >> 1;
-    const int gmax = min(kAcJobsMax, 32 / pairs);
-    // group enumeration (identical on every warp): for each window depth b, the nneed*b jobs in balanced groups
-    int n_groups = 0;
-    if (nneed > 0)
-        for (int b = 1; b <= (int)P.apod_parts; b++) {
-            if (b > 1 && N / b <= 32) continue;
-            n_groups += (nneed * b + gmax - 1) / gmax;
-        }
-    const int n_tasks_a = n_groups + nsig;
-    const float* wtab = windows + fd.window_off;
+    // =================== phase A: per-signal fixed analysis, from a queue ===================
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(&S.queue_a, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_tasks_a) break;
-        if (t < n_groups) {
-            // ---- locate group t ----
-            int b = 1, g0 = 0, j0 = 0, gsz = 1, nj = 0;
-            for (;; b++) {
-                if (b > 1 && N / b <= 32) continue;
-                nj = nneed * b;
-                const int ngrp = (nj + gmax - 1) / gmax;
-                gsz = (nj + ngrp - 1) / ngrp;
-                if (t < g0 + ngrp) { j0 = (t - g0) * gsz; break; }
-                g0 += ngrp;
-            }
-            const int len = N / b, part = (b == 1) ? N : N / b / 2;
-            AcGroup J;
-            J.cnt = min(gsz, nj - j0);
-#pragma unroll
-            for (int q = 0; q < kAcJobsMax; q++) {
-                const int j = min(j0 + q, nj - 1), sidx = S.need_list[j / b], k = j - (j / b) * b;
-                J.v[q] = sig_view(sidx); J.off[q] = (k * N) / b;
-            }
-            double* buf = acbuf_all + (size_t)(n_groups < kAnWarps ? t : warp) * kAcJobsMax * kAcRing;
-            double ra, rb;
-            autoc_group<PACKED>(J, G, wtab, part, len, pairs, buf, lane, ra, rb);
-            const int jb = lane / pairs, pr = lane - jb * pairs;
-            if (jb < J.cnt) {
-                const int j = j0 + jb, sidx = S.need_list[j / b], k = j - (j / b) * b;
-                double* dst = acstore + ((size_t)sidx * nwin + (b - 1) * b / 2 + k) * kAcStoreStride;
-                dst[2 * pr] = ra; dst[2 * pr + 1] = rb;
-            }
-            __syncwarp();
-        } else {
+        if (t >= nsig) break;
+        {
             // ---- fixed analysis of signal s: verbatim baseline, constant, or the guessed fixed order ----
-            const int s = t - n_groups;
+            const int s = t;
             SubframePlan& pl = base_plan[s];
             reinterpret_cast<uint32_t*>(&pl)[lane] = 0u;
             __syncwarp();
@@ -759,36 +879,51 @@ static uint32_t apod_steps(const EncParams& P) {
     return P.max_lpc_order ? n : 0u;
 }
 
-// host-visible launcher (called from engine.cu)
-void launch_analyze(const void* pcm, const FrameDesc* frames, const float* windows, const EncParams& P, int n_frames,
-                    SubframePlan* plans, uint8_t* frame_ca, SignalDebug* dbg, EncStats* stats, size_t smem_bytes,
-                    cudaStream_t stream) {
-    const dim3 grid((unsigned)n_frames), block(kAnThreads);
-    // loose mid/side: decision frames first, then the frames that follow them (they read the decision from frame_ca)
-    for (int pass = 0; pass < (P.loose_frames ? 2 : 1); pass++) {
-        if (packed_layout(P)) {
-            cudaFuncSetAttribute(analyze_kernel<int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            analyze_kernel<int16_t, true><<<grid, block, smem_bytes, stream>>>((const int16_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats, pass);
-        } else if (P.container_bytes == 2) {
-            cudaFuncSetAttribute(analyze_kernel<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            analyze_kernel<int16_t, false><<<grid, block, smem_bytes, stream>>>((const int16_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats, pass);
-        } else {
-            cudaFuncSetAttribute(analyze_kernel<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            analyze_kernel<int32_t, false><<<grid, block, smem_bytes, stream>>>((const int32_t*)pcm, frames, windows, P, plans, frame_ca, dbg, stats, pass);
-        }
-    }
+// bytes of per-frame scratch in HBM: OR/AND record + autocorrelations of every (signal, window)
+size_t analyze_work_stride(const EncParams& P) {
+    const size_t nwin = P.apod_parts * (P.apod_parts + 1) / 2;
+    return sizeof(FrameBits) + (size_t)P.n_signals * nwin * kAcStoreStride * sizeof(double);
 }
 
-// Shared-memory plan of the analysis kernel; fills P.pool_bytes (autocorrelation rings), P.ac_gsz (apodization
-// steps per signal) and P.an_stride (staged words per signal).  Called by the host before launching.
+template <typename PcmT, bool PACKED>
+static void launch_all(const PcmT* pcm, const FrameDesc* frames, const float* windows, const EncParams& P, int n_frames,
+                       SubframePlan* plans, uint8_t* frame_ca, SignalDebug* dbg, EncStats* stats, size_t smem_bytes,
+                       unsigned char* work, cudaStream_t stream) {
+    const size_t stride = analyze_work_stride(P);
+    frame_bits_kernel<PcmT, PACKED><<<(n_frames + 3) / 4, 128, 0, stream>>>(pcm, frames, n_frames, P, work, stride);
+    if (P.max_lpc_order > 0) {
+        const int lags = (int)P.max_lpc_order + 1, lpj = (lags + 3) / 4;
+        int jpw = (32 / lpj) < kAcJobsMax ? (32 / lpj) : kAcJobsMax;
+        if (PACKED && jpw > 2 * (int)P.n_signals) jpw = 2 * (int)P.n_signals;     // packed layout: a warp fetches for two (frame, window) sources
+        if (PACKED) jpw = jpw / (int)P.n_signals * (int)P.n_signals;
+        long long warps = 0;
+        for (uint32_t b = 1; b <= P.apod_parts; b++) warps += ((long long)n_frames * P.n_signals * b + jpw - 1) / jpw;
+        const size_t ac_smem = (size_t)(kAcThreads / 32) * kAcJobsMax * (kAcRing * 8 + sizeof(AcJob));
+        const unsigned blocks = (unsigned)((warps + kAcThreads / 32 - 1) / (kAcThreads / 32));
+        autoc_kernel<PcmT, PACKED><<<blocks, kAcThreads, ac_smem, stream>>>(pcm, frames, n_frames, windows, P, work, stride, lpj, jpw);
+    }
+    cudaFuncSetAttribute(analyze_kernel<PcmT, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    // loose mid/side: decision frames first, then the frames that follow them (they read the decision from frame_ca)
+    for (int pass = 0; pass < (P.loose_frames ? 2 : 1); pass++)
+        analyze_kernel<PcmT, PACKED><<<(unsigned)n_frames, kAnThreads, smem_bytes, stream>>>(pcm, frames, windows, P, plans, frame_ca, dbg, stats,
+                                                                                            pass, work, stride);
+}
+
+// host-visible launcher (called from engine.cu); `work` = n_frames * analyze_work_stride(P) bytes of device scratch.
+// Returns the number of kernels launched.
+int launch_analyze(const void* pcm, const FrameDesc* frames, const float* windows, const EncParams& P, int n_frames,
+                   SubframePlan* plans, uint8_t* frame_ca, SignalDebug* dbg, EncStats* stats, size_t smem_bytes,
+                   void* work, cudaStream_t stream) {
+    if (packed_layout(P)) launch_all<int16_t, true>((const int16_t*)pcm, frames, windows, P, n_frames, plans, frame_ca, dbg, stats, smem_bytes, (unsigned char*)work, stream);
+    else if (P.container_bytes == 2) launch_all<int16_t, false>((const int16_t*)pcm, frames, windows, P, n_frames, plans, frame_ca, dbg, stats, smem_bytes, (unsigned char*)work, stream);
+    else launch_all<int32_t, false>((const int32_t*)pcm, frames, windows, P, n_frames, plans, frame_ca, dbg, stats, smem_bytes, (unsigned char*)work, stream);
+    return 1 + (P.max_lpc_order > 0 ? 1 : 0) + (P.loose_frames ? 2 : 1);
+}
+
+// Shared-memory plan of the analysis kernel; fills P.ac_gsz (apodization steps per signal) and P.an_stride (staged
+// words per signal).  Called by the host before launching.
 void analyze_layout(EncParams& P) {
-    const uint32_t nsig = P.n_signals, L = (P.max_lpc_order ? P.max_lpc_order : 1) + 1, pairs = (L + 1) / 2;
-    const uint32_t gmax = (32 / pairs) < (uint32_t)kAcJobsMax ? (32 / pairs) : (uint32_t)kAcJobsMax;
-    uint32_t groups = 0;
-    for (uint32_t b = 1; b <= P.apod_parts; b++) groups += (nsig * b + gmax - 1) / gmax;
-    const uint32_t areas = groups < (uint32_t)kAnWarps ? groups : (uint32_t)kAnWarps;
-    const uint32_t ring_bytes = P.max_lpc_order ? areas * kAcJobsMax * kAcRing * 8u : 0u, ws_bytes = (uint32_t)(kAnWarps * sizeof(WarpScratch));
-    P.pool_bytes = ring_bytes > ws_bytes ? ring_bytes : ws_bytes;     // rings (phase A) and LPC scratch (phase B) share the pool
+    P.pool_bytes = 0;
     P.ac_gsz = apod_steps(P);
     // 32 rows of ceil(N/32) samples with an odd row stride
     const uint32_t b0 = (P.blocksize + 31) / 32, rs = b0 | 1u;
@@ -796,8 +931,8 @@ void analyze_layout(EncParams& P) {
 }
 
 size_t analyze_smem_bytes(const EncParams& P) {
-    const size_t nsig = P.n_signals, nwin = P.apod_parts * (P.apod_parts + 1) / 2;
-    return (size_t)(packed_layout(P) ? 1 : nsig) * P.an_stride * 4 + P.pool_bytes + nsig * nwin * kAcStoreStride * sizeof(double) +
+    const size_t nsig = P.n_signals;
+    return (size_t)(packed_layout(P) ? 1 : nsig) * P.an_stride * 4 + (size_t)kAnWarps * sizeof(WarpScratch) +
            (size_t)kAnWarps * 2 * kMaxParts * 8 + nsig * sizeof(SubframePlan) +
            nsig * P.ac_gsz * sizeof(SubframePlan) + sizeof(AnShared) + 64;
 }

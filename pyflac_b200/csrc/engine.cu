@@ -23,9 +23,10 @@
 #include "md5_mb.h"
 
 namespace fb {
-void launch_analyze(const void*, const FrameDesc*, const float*, const EncParams&, int, SubframePlan*, uint8_t*,
-                    SignalDebug*, EncStats*, size_t, cudaStream_t);
+int launch_analyze(const void*, const FrameDesc*, const float*, const EncParams&, int, SubframePlan*, uint8_t*,
+                   SignalDebug*, EncStats*, size_t, void*, cudaStream_t);
 size_t analyze_smem_bytes(const EncParams&);
+size_t analyze_work_stride(const EncParams&);
 void analyze_layout(EncParams&);
 void launch_pack(const void*, const FrameDesc*, const EncParams&, int, const SubframePlan*, const uint8_t*, uint8_t*,
                  uint32_t, uint32_t*, cudaStream_t);
@@ -91,7 +92,7 @@ struct flacb200_ctx {
     uint64_t e2e_last_bytes = 0;
     double e2e_ms[6] = {0};               // last host call: plan, enqueue, kernels drained, d2h done, md5 join, total
 
-    DevBuf d_pcm, d_frames, d_windows, d_plans, d_ca, d_scratch;
+    DevBuf d_pcm, d_frames, d_windows, d_plans, d_ca, d_scratch, d_work;
     DevBuf d_sfirst, d_snframes, d_soff, d_ssamples, d_debug;
 
     // Output buffers exist three times and rotate per batch: the MD5 of a batch (a serial chain per stream, longer
@@ -240,7 +241,7 @@ extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_pcm, &ctx->d_frames, &ctx->d_windows, &ctx->d_plans, &ctx->d_ca, &ctx->d_scratch, &ctx->d_sfirst, &ctx->d_snframes,
+    DevBuf* bufs[] = {&ctx->d_pcm, &ctx->d_frames, &ctx->d_windows, &ctx->d_plans, &ctx->d_ca, &ctx->d_scratch, &ctx->d_work, &ctx->d_sfirst, &ctx->d_snframes,
                       &ctx->d_soff, &ctx->d_ssamples, &ctx->d_debug};
     for (DevBuf* b : bufs) b->release();
     for (auto& S : ctx->sets) {
@@ -364,6 +365,7 @@ static int plan_batch(flacb200_ctx* ctx, const flacb200_enc_config& cfg, uint32_
     cudaStream_t st = ctx->stream;
     CK(ctx->d_frames.reserve(sizeof(FrameDesc) * (size_t)(nf ? nf : 1)));
     CK(ctx->d_plans.reserve(sizeof(SubframePlan) * (size_t)(nf ? nf : 1) * P.n_signals));
+    CK(ctx->d_work.reserve(analyze_work_stride(P) * (size_t)(nf ? nf : 1)));
     CK(ctx->d_ca.reserve((size_t)nf + 16));
     CK(ctx->d_scratch.reserve((size_t)nf * ctx->scratch_stride + 64));
     for (auto& S : ctx->sets) CK(S.flen.reserve(sizeof(uint32_t) * (size_t)(nf + 1)));
@@ -425,9 +427,9 @@ static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
         ctx->launches++;
     }
     if (prof) CK(cudaEventRecord(ctx->ev_k[0], st));
-    launch_analyze(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, (SubframePlan*)ctx->d_plans.p,
-                   (uint8_t*)ctx->d_ca.p, ctx->debug ? (SignalDebug*)ctx->d_debug.p : nullptr, (EncStats*)S.stats.p,
-                   analyze_smem_bytes(P), st);
+    const int n_an = launch_analyze(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, (SubframePlan*)ctx->d_plans.p,
+                                    (uint8_t*)ctx->d_ca.p, ctx->debug ? (SignalDebug*)ctx->d_debug.p : nullptr, (EncStats*)S.stats.p,
+                                    analyze_smem_bytes(P), ctx->d_work.p, st);
     if (prof) CK(cudaEventRecord(ctx->ev_k[1], st));
     launch_pack(d_pcm, (const FrameDesc*)ctx->d_frames.p, P, nf, (const SubframePlan*)ctx->d_plans.p, (const uint8_t*)ctx->d_ca.p,
                 (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)S.flen.p, st);
@@ -445,7 +447,7 @@ static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
                     (StreamInfoOut*)S.sinfo.p, fs);
     if (prof) CK(cudaEventRecord(ctx->ev_k[5], fs));
     if (md5) { CK(cudaEventRecord(S.ev_free, S.side)); S.busy = true; }
-    ctx->launches += 5 + (P.loose_frames ? 1 : 0);
+    ctx->launches += 4 + n_an;
     CK(cudaGetLastError());
     return 0;
 }
@@ -656,9 +658,9 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         dev_base[c + 1] = dev_base[c] + (((uint64_t)cnf * ctx->scratch_stride + (uint64_t)cns * kStreamPrologueBytes + 255) / 256) * 256;
         CKJ(cudaStreamWaitEvent(st, ctx->ev_h2d[c], 0));
         if (cnf > 0) {
-            launch_analyze(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf,
-                           (SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals, (uint8_t*)ctx->d_ca.p + f0, nullptr, (EncStats*)ctx->set().stats.p,
-                           analyze_smem_bytes(P), st);
+            const int n_an = launch_analyze(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf,
+                                            (SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals, (uint8_t*)ctx->d_ca.p + f0, nullptr, (EncStats*)ctx->set().stats.p,
+                                            analyze_smem_bytes(P), (uint8_t*)ctx->d_work.p + (size_t)f0 * analyze_work_stride(P), st);
             launch_pack(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, P, cnf, (const SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals,
                         (const uint8_t*)ctx->d_ca.p + f0, (uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride,
                         (uint32_t*)ctx->set().flen.p + f0, st);
@@ -669,7 +671,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
             launch_finalize((const uint32_t*)ctx->set().flen.p, (const uint64_t*)ctx->set().foff.p, (const uint32_t*)ctx->d_sfirst.p + s0,
                             (const uint32_t*)ctx->d_snframes.p + s0, (const uint64_t*)ctx->d_ssamples.p + s0, nullptr, cns, P, pro ? 1u : 0u,
                             (uint8_t*)ctx->set().arena.p, (StreamInfoOut*)ctx->set().sinfo.p + s0, st);
-            ctx->launches += 5 + (P.loose_frames ? 1 : 0);
+            ctx->launches += 4 + n_an;
         } else {
             CKJ(cudaMemsetAsync((uint64_t*)ctx->d_totals.p + c, 0, 8, st));
         }
