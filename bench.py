@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -269,7 +269,7 @@ def main():
     e2e_s = time.perf_counter() - e0
     hp = (C.c_double * 6)()
     L.flacb200_host_path_times(eng._h, hp)
-    host_path_ms = {"enqueued": hp[1], "kernels_done": hp[2], "d2h_done": hp[3], "md5_joined": hp[4], "total": hp[5]}
+    host_path_ms = {"md5_workers_done": hp[0], "enqueued": hp[1], "kernels_done": hp[2], "d2h_done": hp[3], "md5_joined": hp[4], "total": hp[5]}
     if world > 1:
         dist.barrier()
 
@@ -323,7 +323,9 @@ def main():
         value = world * total_samples / (ms_per_step * 1e-3) / 1e6
         e2e_val = world * total_samples / (e2e_ms_max / args.steps * 1e-3) / 1e6
         peak, peak_src = hbm_peak()
-        dom = max(("analyze", "pack", "md5"), key=lambda k: kt_acc.get(k, 0.0))
+        # dominant kernel = the longest one on the encode stream (the step's critical path).  md5_kernel runs on a side
+        # stream under the next batches (a 256-thread serial chain, pure latency) and is listed in kernel_ms / roofline_md5.
+        dom = max(("autoc", "analyze", "pack"), key=lambda k: kt_acc.get(k, 0.0))
         alg_bytes = pcm_bytes + out_bytes
         achieved = alg_bytes / (kt_acc[dom] * 1e-3) / 1e9
         line = {
@@ -340,6 +342,10 @@ def main():
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": kt_acc},
+            "roofline_md5": {"bound": "hbm", "kernel": "md5_kernel (side stream, overlapped with the next batches)",
+                             "achieved": pcm_bytes / (max(kt_acc.get("md5", 0.0), 1e-6) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": pcm_bytes / (max(kt_acc.get("md5", 0.0), 1e-6) * 1e-3) / 1e9 / peak,
+                             "algorithmic_bytes_per_launch": pcm_bytes},
             "decode": {"metric": "decode_msamples_per_s", "unit": UNIT,
                        "value": world * total_samples / (dec_ms_max / args.steps * 1e-3) / 1e6,
                        "e2e_value": world * total_samples / (dec_e2e_ms_max / args.steps * 1e-3) / 1e6,

@@ -84,7 +84,7 @@ const char *flacb200_last_error(const flacb200_ctx *ctx);
 int  flacb200_set_stream(flacb200_ctx *ctx, void *cuda_stream);
 int  flacb200_sync(flacb200_ctx *ctx);
 /* Batches overlap: the MD5 + STREAMINFO finalisation of a batch run on a side stream while the next batch's kernels
- * start (three rotating output sets).  flacb200_join makes the ctx stream wait for all of them, so that an event
+ * start (five rotating output sets).  flacb200_join makes the ctx stream wait for all of them, so that an event
  * recorded on it afterwards covers every batch issued so far; result/fetch/sync do this implicitly.  The PCM of a
  * batch must stay unchanged until then. */
 int  flacb200_join(flacb200_ctx *ctx);
@@ -161,7 +161,8 @@ int  flacb200_decode_fetch(flacb200_ctx *ctx, void *pcm, size_t pcm_cap, flacb20
 int  flacb200_decode_kernel_times(flacb200_ctx *ctx, float *ms);
 
 /* Per-kernel device times of the last batch, measured with CUDA events on the launching streams:
- * ms[0..5] = analyze, pack, scan, compact, finalize(+MD5 join), md5 (side stream). */
+ * ms[0..8] = analysis (all three kernels), pack, scan, compact, finalize(+MD5 join), md5 (side stream), then the
+ * analysis split into its kernels: frame_bits (OR/AND), autoc (autocorrelation), analyze (decisions). */
 int  flacb200_set_profiling(flacb200_ctx *ctx, int on);
 int  flacb200_kernel_times(flacb200_ctx *ctx, float *ms);
 /* Wall-clock breakdown (ms since entry) of the last flacb200_encode_batch_host call:

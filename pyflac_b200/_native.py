@@ -143,10 +143,11 @@ class Engine:
         self._check(self._L.flacb200_set_profiling(self._h, int(on)))
 
     def kernel_times(self):
-        """Device ms of the last batch: dict(analyze, pack, scan, compact, finalize, md5)."""
-        ms = np.zeros(6, np.float32)
+        """Device ms of the last batch: analysis (its three kernels together), pack, scan, compact, finalize, md5, then
+        the analysis split: frame_bits, autoc, analyze."""
+        ms = np.zeros(9, np.float32)
         self._check(self._L.flacb200_kernel_times(self._h, ms.ctypes.data))
-        return dict(zip(["analyze", "pack", "scan", "compact", "finalize", "md5"], [float(v) for v in ms]))
+        return dict(zip(["analysis", "pack", "scan", "compact", "finalize", "md5", "frame_bits", "autoc", "analyze"], [float(v) for v in ms]))
 
     @property
     def launch_count(self):

@@ -888,9 +888,10 @@ size_t analyze_work_stride(const EncParams& P) {
 template <typename PcmT, bool PACKED>
 static void launch_all(const PcmT* pcm, const FrameDesc* frames, const float* windows, const EncParams& P, int n_frames,
                        SubframePlan* plans, uint8_t* frame_ca, SignalDebug* dbg, EncStats* stats, size_t smem_bytes,
-                       unsigned char* work, cudaStream_t stream) {
+                       unsigned char* work, cudaStream_t stream, cudaEvent_t* ev) {
     const size_t stride = analyze_work_stride(P);
     frame_bits_kernel<PcmT, PACKED><<<(n_frames + 3) / 4, 128, 0, stream>>>(pcm, frames, n_frames, P, work, stride);
+    if (ev) cudaEventRecord(ev[0], stream);
     if (P.max_lpc_order > 0) {
         const int lags = (int)P.max_lpc_order + 1, lpj = (lags + 3) / 4;
         int jpw = (32 / lpj) < kAcJobsMax ? (32 / lpj) : kAcJobsMax;
@@ -902,6 +903,7 @@ static void launch_all(const PcmT* pcm, const FrameDesc* frames, const float* wi
         const unsigned blocks = (unsigned)((warps + kAcThreads / 32 - 1) / (kAcThreads / 32));
         autoc_kernel<PcmT, PACKED><<<blocks, kAcThreads, ac_smem, stream>>>(pcm, frames, n_frames, windows, P, work, stride, lpj, jpw);
     }
+    if (ev) cudaEventRecord(ev[1], stream);
     cudaFuncSetAttribute(analyze_kernel<PcmT, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     // loose mid/side: decision frames first, then the frames that follow them (they read the decision from frame_ca)
     for (int pass = 0; pass < (P.loose_frames ? 2 : 1); pass++)
@@ -910,13 +912,14 @@ static void launch_all(const PcmT* pcm, const FrameDesc* frames, const float* wi
 }
 
 // host-visible launcher (called from engine.cu); `work` = n_frames * analyze_work_stride(P) bytes of device scratch.
+// ev (optional): two events recorded after the OR/AND kernel and after the autocorrelation kernel.
 // Returns the number of kernels launched.
 int launch_analyze(const void* pcm, const FrameDesc* frames, const float* windows, const EncParams& P, int n_frames,
                    SubframePlan* plans, uint8_t* frame_ca, SignalDebug* dbg, EncStats* stats, size_t smem_bytes,
-                   void* work, cudaStream_t stream) {
-    if (packed_layout(P)) launch_all<int16_t, true>((const int16_t*)pcm, frames, windows, P, n_frames, plans, frame_ca, dbg, stats, smem_bytes, (unsigned char*)work, stream);
-    else if (P.container_bytes == 2) launch_all<int16_t, false>((const int16_t*)pcm, frames, windows, P, n_frames, plans, frame_ca, dbg, stats, smem_bytes, (unsigned char*)work, stream);
-    else launch_all<int32_t, false>((const int32_t*)pcm, frames, windows, P, n_frames, plans, frame_ca, dbg, stats, smem_bytes, (unsigned char*)work, stream);
+                   void* work, cudaStream_t stream, cudaEvent_t* ev) {
+    if (packed_layout(P)) launch_all<int16_t, true>((const int16_t*)pcm, frames, windows, P, n_frames, plans, frame_ca, dbg, stats, smem_bytes, (unsigned char*)work, stream, ev);
+    else if (P.container_bytes == 2) launch_all<int16_t, false>((const int16_t*)pcm, frames, windows, P, n_frames, plans, frame_ca, dbg, stats, smem_bytes, (unsigned char*)work, stream, ev);
+    else launch_all<int32_t, false>((const int32_t*)pcm, frames, windows, P, n_frames, plans, frame_ca, dbg, stats, smem_bytes, (unsigned char*)work, stream, ev);
     return 1 + (P.max_lpc_order > 0 ? 1 : 0) + (P.loose_frames ? 2 : 1);
 }
 

@@ -24,7 +24,7 @@
 
 namespace fb {
 int launch_analyze(const void*, const FrameDesc*, const float*, const EncParams&, int, SubframePlan*, uint8_t*,
-                   SignalDebug*, EncStats*, size_t, void*, cudaStream_t);
+                   SignalDebug*, EncStats*, size_t, void*, cudaStream_t, cudaEvent_t*);
 size_t analyze_smem_bytes(const EncParams&);
 size_t analyze_work_stride(const EncParams&);
 void analyze_layout(EncParams&);
@@ -60,7 +60,7 @@ struct flacb200_ctx {
     cudaStream_t stream = nullptr, own_stream = nullptr, md5_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool profiling = false;
-    cudaEvent_t ev_k[8] = {nullptr};       // analyze start, analyze end, pack end, layout end, compact end, finalize end, md5 start, md5 end
+    cudaEvent_t ev_k[10] = {nullptr};      // analysis start, analysis end, pack end, layout end, compact end, finalize end, md5 start, md5 end, OR/AND end, autocorrelation end
     std::string err;
     uint64_t launches = 0;
     int max_smem_optin = 0;
@@ -104,7 +104,7 @@ struct flacb200_ctx {
         cudaEvent_t ev_main = nullptr, ev_free = nullptr;
         bool busy = false;
     };
-    static constexpr int kSets = 3;
+    static constexpr int kSets = 5;
     OutSet sets[kSets];
     int cur = 0;
     OutSet& set() { return sets[cur]; }
@@ -287,7 +287,8 @@ extern "C" int flacb200_join(flacb200_ctx* ctx) { if (!ctx) return FLACB200_ERR_
 extern "C" int flacb200_host_path_times(flacb200_ctx* ctx, double* ms) { if (!ctx || !ms) return FLACB200_ERR_ARG; for (int i = 0; i < 6; i++) ms[i] = ctx->e2e_ms[i]; return 0; }
 
 extern "C" int flacb200_set_profiling(flacb200_ctx* ctx, int on) { if (!ctx) return FLACB200_ERR_ARG; ctx->profiling = on != 0; return 0; }
-// ms[0..5] = analyze, pack, layout(scan), compact, finalize (incl. waiting for MD5), md5 (side stream) of the last batch
+// ms[0..8] = analysis (3 kernels), pack, layout(scan), compact, finalize (incl. waiting for MD5), md5 (side stream),
+// then the analysis split: OR/AND, autocorrelation, decisions -- of the last batch
 extern "C" int flacb200_kernel_times(flacb200_ctx* ctx, float* ms) {
     if (!ctx || !ms || !ctx->profiling || !ctx->have_batch) return FLACB200_ERR_ARG;
     cudaSetDevice(ctx->device);
@@ -296,6 +297,10 @@ extern "C" int flacb200_kernel_times(flacb200_ctx* ctx, float* ms) {
     for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&ms[i], ctx->ev_k[i], ctx->ev_k[i + 1]));
     ms[5] = 0.0f;
     if (ctx->cfg.do_md5) CK(cudaEventElapsedTime(&ms[5], ctx->ev_k[6], ctx->ev_k[7]));
+    // the three kernels of the analysis: ms[6] OR/AND, ms[7] autocorrelation (0 when the level has no LPC), ms[8] decisions
+    CK(cudaEventElapsedTime(&ms[6], ctx->ev_k[0], ctx->ev_k[8]));
+    CK(cudaEventElapsedTime(&ms[7], ctx->ev_k[8], ctx->ev_k[9]));
+    CK(cudaEventElapsedTime(&ms[8], ctx->ev_k[9], ctx->ev_k[1]));
     return 0;
 }
 extern "C" uint64_t flacb200_launch_count(const flacb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -429,7 +434,7 @@ static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
     if (prof) CK(cudaEventRecord(ctx->ev_k[0], st));
     const int n_an = launch_analyze(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, (SubframePlan*)ctx->d_plans.p,
                                     (uint8_t*)ctx->d_ca.p, ctx->debug ? (SignalDebug*)ctx->d_debug.p : nullptr, (EncStats*)S.stats.p,
-                                    analyze_smem_bytes(P), ctx->d_work.p, st);
+                                    analyze_smem_bytes(P), ctx->d_work.p, st, prof ? &ctx->ev_k[8] : nullptr);
     if (prof) CK(cudaEventRecord(ctx->ev_k[1], st));
     launch_pack(d_pcm, (const FrameDesc*)ctx->d_frames.p, P, nf, (const SubframePlan*)ctx->d_plans.p, (const uint8_t*)ctx->d_ca.p,
                 (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)S.flen.p, st);
@@ -593,6 +598,9 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         cs[nchunks] = ns;
     }
 
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+    std::atomic<uint64_t> md5_done_us{0};
     // ---- host MD5 workers (one serial chain per stream) ----
     const bool want_md5 = cfg->do_md5 != 0;
     std::vector<uint8_t> digests((size_t)ns * 16, 0);
@@ -600,19 +608,43 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     std::atomic<int> next_stream{0};
     if (want_md5) {
         unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 8;
-        const unsigned nt = std::min<unsigned>(std::min<unsigned>(hw / 2 ? hw / 2 : 1u, 32u), (unsigned)((ns + 7) / 8));
+        // the calling thread only enqueues copies and waits, so every hardware thread can hash; groups of 16 streams
+        // (AVX-512) or 8 (AVX2) per SIMD pass
+        const int G = fb::md5_mb16_available() ? 16 : 8;
+        // Hashing competes with the H2D DMA for host memory bandwidth (measured: 8+ threads finish the MD5s in 6 ms but
+        // stretch the 491 MB copy from 11 to 13.5 ms), so use just enough threads to finish when the transfer does:
+        // threads = (bytes / calibrated per-thread rate) / (bytes / ~42 GB/s PCIe), at most all cores but one.
+        static const double gbps_per_thread = [] {
+            std::vector<uint8_t> buf(16u << 16, 0x5a);
+            const uint8_t* d[16]; size_t l[16]; uint8_t dig[16][16];
+            for (int i = 0; i < 16; i++) { d[i] = buf.data() + ((size_t)i << 16); l[i] = 1u << 16; }
+            fb::md5_group16(d, l, 16, dig);
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int r = 0; r < 4; r++) fb::md5_group16(d, l, 16, dig);
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            return sec > 0 ? 4.0 * buf.size() / sec / 1e9 : 4.0;
+        }();
+        unsigned want = (unsigned)(42.0 / gbps_per_thread + 0.5);
+        if (want < 1) want = 1;
+        if (want > (hw > 2 ? hw - 1 : hw)) want = hw > 2 ? hw - 1 : hw;
+        if (const char* ev = getenv("FLACB200_MD5_THREADS")) { const int v = atoi(ev); if (v > 0) want = (unsigned)v; }
+        const unsigned nt = std::min<unsigned>(std::min<unsigned>(want, 64u), (unsigned)((ns + G - 1) / G));
         const uint32_t bytes_per = (P.bps + 7) / 8, chn = P.channels;
-        const bool raw_bytes = (bytes_per == cont);          // the container bytes are the hashed bytes: 8 streams per SIMD pass
+        const bool raw_bytes = (bytes_per == cont);          // the container bytes are the hashed bytes
         for (unsigned t = 0; t < nt; t++)
-            workers.emplace_back([&, bytes_per, chn, raw_bytes]() {
+            workers.emplace_back([&, bytes_per, chn, raw_bytes, G]() {
                 for (;;) {
-                    const int g = next_stream.fetch_add(8);
-                    if (g >= ns) break;
-                    const int n = std::min(8, ns - g);
+                    const int g = next_stream.fetch_add(G);
+                    if (g >= ns) {
+                        const uint64_t now = (uint64_t)(since() * 1000.0); uint64_t prev = md5_done_us.load();
+                        while (prev < now && !md5_done_us.compare_exchange_weak(prev, now)) {}
+                        break;
+                    }
+                    const int n = std::min(G, ns - g);
                     if (raw_bytes) {
-                        const uint8_t* d[8]; size_t l[8]; uint8_t dig[8][16];
+                        const uint8_t* d[16]; size_t l[16]; uint8_t dig[16][16];
                         for (int i = 0; i < n; i++) { d[i] = (const uint8_t*)pcm_host + stream_off[g + i] * cont; l[i] = (size_t)stream_samples[g + i] * chn * cont; }
-                        fb::md5_group8(d, l, n, dig);
+                        fb::md5_group16(d, l, n, dig);
                         for (int i = 0; i < n; i++) memcpy(&digests[(size_t)(g + i) * 16], dig[i], 16);
                     } else {
                         for (int i = 0; i < n; i++) {
@@ -626,8 +658,6 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     }
     auto join_workers = [&]() { for (auto& w : workers) if (w.joinable()) w.join(); };
 
-    const auto t_start = std::chrono::steady_clock::now();
-    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     // ---- enqueue: H2D per chunk, then kernels per chunk ----
     auto bail = [&](int code) { join_workers(); return code; };
 #define CKJ(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(ctx, FLACB200_ERR_CUDA, #call, e_)); } while (0)
@@ -660,7 +690,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         if (cnf > 0) {
             const int n_an = launch_analyze(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf,
                                             (SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals, (uint8_t*)ctx->d_ca.p + f0, nullptr, (EncStats*)ctx->set().stats.p,
-                                            analyze_smem_bytes(P), (uint8_t*)ctx->d_work.p + (size_t)f0 * analyze_work_stride(P), st);
+                                            analyze_smem_bytes(P), (uint8_t*)ctx->d_work.p + (size_t)f0 * analyze_work_stride(P), st, nullptr);
             launch_pack(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, P, cnf, (const SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals,
                         (const uint8_t*)ctx->d_ca.p + f0, (uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride,
                         (uint32_t*)ctx->set().flen.p + f0, st);
@@ -706,6 +736,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     ctx->e2e_ms[3] = since();
     join_workers();
     ctx->e2e_ms[4] = since();
+    ctx->e2e_ms[0] = (double)md5_done_us.load() / 1000.0;       // when the last MD5 worker ran out of streams
     // device-arena offsets -> host-arena offsets; MD5 digests into STREAMINFO
     for (int c = 0; c < nchunks; c++) {
         const int s0 = cs[c], s1 = cs[c + 1];
