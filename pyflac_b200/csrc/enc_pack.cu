@@ -15,7 +15,7 @@ namespace fb {
 
 constexpr int kPackThreads = 256;
 constexpr int kPackWarps = kPackThreads / 32;
-constexpr int kTileK = 16;                                  // residuals kept in registers per thread and tile
+constexpr int kTileK = 4;                                   // residuals kept in registers per thread and tile
 constexpr int kTileSamples = kPackThreads * kTileK;         // 4096 samples per tile
 constexpr int kSegSamples = 32 * kTileK;                    // contiguous samples owned by one warp within a tile
 

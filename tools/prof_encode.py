@@ -1,4 +1,4 @@
-"""Small encode-only workload for ncu captures (64 of the bench streams, level from argv): python tools/prof_encode.py [level]"""
+"""Encode-only workload for ncu captures (n of the bench streams): python tools/prof_encode.py [level] [n_streams]"""
 import sys
 
 sys.path.insert(0, ".")
@@ -6,8 +6,9 @@ import bench
 from pyflac_b200 import _native as nat
 
 level = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-pcm = bench.make_pcm(0, 64)
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+pcm = bench.make_pcm(0, n)
 eng = nat.Engine(0)
 for _ in range(2):
-    blobs, out = nat.encode_streams(eng, [pcm[s] for s in range(64)], 48000, 16, level, 4096)
+    blobs, out = nat.encode_streams(eng, [pcm[s] for s in range(n)], 48000, 16, level, 4096)
 print("ok", out["total_bytes"], eng.launch_count)
