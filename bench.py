@@ -295,13 +295,11 @@ def main():
     dres = eng.decode_result()
     dec_ok = int(dres.total_elems) == total_samples
     h_out = torch.empty(total_samples, dtype=torch.int16).pin_memory()
-    dinfos = (nat.DecStreamInfo * N_STREAMS)()
+    dinfos = [None] * N_STREAMS
 
     def step_dec_e2e():
-        eng.decode_host(arena_np[:total_flac + 16], s_off, s_len, 2)
-        rc = L.flacb200_decode_fetch(eng._h, h_out.data_ptr(), h_out.numel() * 2, C.cast(dinfos, C.c_void_p), None, 0)
-        if rc != 0:
-            raise RuntimeError(L.flacb200_last_error(eng._h).decode())
+        tot_e, dinf = eng.decode_host_pipelined(arena_np[:total_flac + 16], s_off, s_len, h_out.numpy(), 2)
+        dinfos[:] = dinf[:N_STREAMS]
     step_dec_e2e()
     torch.cuda.synchronize()
     d0 = time.perf_counter()

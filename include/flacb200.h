@@ -157,6 +157,13 @@ int  flacb200_decode_result(flacb200_ctx *ctx, flacb200_dec_result *res);
  * cap entries) receives the blocksize of every decoded frame in stream order. */
 int  flacb200_decode_fetch(flacb200_ctx *ctx, void *pcm, size_t pcm_cap, flacb200_dec_stream_info *streams,
                            uint32_t *frame_samples, uint32_t frame_cap);
+/* One-call host -> host decode used for end-to-end work: chunks of streams are pipelined (H2D of the next chunk,
+ * kernels of the current one, D2H of the previous one run concurrently).  out_container_bytes must be 2 or 4.
+ * PCM lands in `pcm` in stream order; streams[s].pcm_off (elements) indexes it; *total_elems = elements written. */
+int  flacb200_decode_batch_host(flacb200_ctx *ctx, const uint8_t *blob, uint64_t blob_bytes, uint32_t n_streams,
+                                const uint64_t *stream_off, const uint64_t *stream_len, uint32_t out_container_bytes,
+                                const flacb200_dec_raw_params *raw, void *pcm, size_t pcm_cap, uint64_t *total_elems,
+                                flacb200_dec_stream_info *streams);
 /* ms[0..5] = metadata+sync scan, candidate decode, chain+layout, post (CRC/interleave), 0, 0 */
 int  flacb200_decode_kernel_times(flacb200_ctx *ctx, float *ms);
 

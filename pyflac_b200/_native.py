@@ -261,6 +261,8 @@ def _dec_proto(L):
     L.flacb200_decode_result.argtypes = [C.c_void_p, C.POINTER(DecResult)]
     L.flacb200_decode_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32]
     L.flacb200_decode_kernel_times.argtypes = [C.c_void_p, C.c_void_p]
+    L.flacb200_decode_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                             C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L._dec_proto_done = True
 
 
@@ -283,6 +285,22 @@ def _engine_decode_host(self, blob, stream_off, stream_len, out_container_bytes=
     self._keep_dec = (blob, so, sl, rp)
     self._check(self._L.flacb200_decode_batch(self._h, blob.ctypes.data, 0, blob.size, len(so), so.ctypes.data, sl.ctypes.data,
                                               out_container_bytes, C.byref(rp) if rp else None))
+
+
+def _engine_decode_host_pipelined(self, blob, stream_off, stream_len, out, out_container_bytes=2, raw=None):
+    """Host -> host decode in one pipelined call (H2D / kernels / D2H of different chunks overlap).
+    `out`: preallocated (ideally pinned) int16/int32 array; returns (total_elems, [DecStreamInfo])."""
+    _dec_proto(self._L)
+    blob = np.ascontiguousarray(blob, np.uint8)
+    so = np.ascontiguousarray(stream_off, np.uint64)
+    sl = np.ascontiguousarray(stream_len, np.uint64)
+    rp = DecRawParams(*raw) if raw else None
+    infos = (DecStreamInfo * max(len(so), 1))()
+    tot = C.c_uint64(0)
+    self._check(self._L.flacb200_decode_batch_host(self._h, blob.ctypes.data, blob.size, len(so), so.ctypes.data, sl.ctypes.data,
+                                                   out_container_bytes, C.byref(rp) if rp else None, out.ctypes.data, out.nbytes,
+                                                   C.byref(tot), C.cast(infos, C.c_void_p)))
+    return int(tot.value), infos
 
 
 def _engine_decode_result(self):
@@ -312,6 +330,7 @@ def _engine_decode_kernel_times(self):
 
 Engine.decode_device = _engine_decode_device
 Engine.decode_host = _engine_decode_host
+Engine.decode_host_pipelined = _engine_decode_host_pipelined
 Engine.decode_result = _engine_decode_result
 Engine.decode_fetch = _engine_decode_fetch
 Engine.decode_kernel_times = _engine_decode_kernel_times

@@ -4,6 +4,7 @@
 // Two host synchronisations per batch (candidate count, decoded PCM size) because device buffers are sized from them.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -56,6 +57,13 @@ struct DecState {
     bool have = false;
     cudaEvent_t ev[5] = {nullptr};
     std::vector<DecStreamResult> h_res;
+    DecState* alt = nullptr;                // second state for flacb200_decode_batch_host's double buffering
+    // pipelined host path
+    Buf hblob;                              // device copy of the caller's blob
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    std::vector<cudaEvent_t> ev_h2d;
+    cudaEvent_t ev_pcm_free = nullptr, ev_post = nullptr;
+    bool pcm_busy = false;
 };
 
 void dec_free(void* p) {
@@ -63,19 +71,32 @@ void dec_free(void* p) {
     Buf* bufs[] = {&d->blob, &d->soff, &d->slen, &d->meta, &d->segs, &d->segcount, &d->segbase, &d->cands, &d->sizes, &d->slotoff, &d->samples,
                    &d->candfirst, &d->res, &d->ss32, &d->pcmoff, &d->pcm, &d->total};
     for (Buf* b : bufs) b->release();
+    d->hblob.release();
     for (auto& e : d->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : d->ev_h2d) if (e) cudaEventDestroy(e);
+    if (d->ev_pcm_free) cudaEventDestroy(d->ev_pcm_free);
+    if (d->ev_post) cudaEventDestroy(d->ev_post);
+    if (d->h2d) cudaStreamDestroy(d->h2d);
+    if (d->d2h) cudaStreamDestroy(d->d2h);
+    if (d->alt) dec_free(d->alt);
     delete d;
 }
 
-DecState* state(flacb200_ctx* ctx) {
+DecState* state(flacb200_ctx* ctx, int which = 0) {
     void** slot = fb_ctx_dec_slot(ctx, dec_free);
     if (!*slot) { DecState* d = new DecState(); for (auto& e : d->ev) cudaEventCreate(&e); *slot = d; }
-    return (DecState*)*slot;
+    DecState* d = (DecState*)*slot;
+    if (which == 0) return d;
+    if (!d->alt) { d->alt = new DecState(); for (auto& e : d->alt->ev) cudaEventCreate(&e); }     // second lane of the pipelined host path
+    return d->alt;
 }
 
 }  // namespace
 
 #define CKD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fb_ctx_fail(ctx, FLACB200_ERR_CUDA, #call, e_); } while (0)
+
+static int decode_core(flacb200_ctx* ctx, DecState* d, cudaStream_t st, const uint8_t* d_blob, int ns, const uint64_t* stream_off,
+                       const uint64_t* stream_len, uint32_t out_container_bytes, const flacb200_dec_raw_params* raw);
 
 extern "C" int flacb200_decode_batch(flacb200_ctx* ctx, const uint8_t* blob, int blob_is_device, uint64_t blob_bytes,
                                      uint32_t n_streams, const uint64_t* stream_off, const uint64_t* stream_len,
@@ -92,6 +113,20 @@ extern "C" int flacb200_decode_batch(flacb200_ctx* ctx, const uint8_t* blob, int
         if (stream_off[s] + stream_len[s] > blob_bytes) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "stream exceeds blob", cudaSuccess);
         if (stream_len[s] >= 0xFFFFFFF0ull) return fb_ctx_fail(ctx, FLACB200_ERR_UNSUPPORTED, "streams of 4 GiB or more are not supported", cudaSuccess);
     }
+    const uint8_t* d_blob = blob;
+    if (!blob_is_device && ns) {
+        CKD(d->blob.reserve(blob_bytes + 64));
+        CKD(cudaMemcpyAsync(d->blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, st));
+        CKD(cudaMemsetAsync((uint8_t*)d->blob.p + blob_bytes, 0, 16, st));
+        d_blob = (const uint8_t*)d->blob.p;
+    }
+    return decode_core(ctx, d, st, d_blob, ns, stream_off, stream_len, out_container_bytes, raw);
+}
+
+// One decode pass over streams whose bytes are already in HBM (d_blob + stream_off[s]).
+static int decode_core(flacb200_ctx* ctx, DecState* d, cudaStream_t st, const uint8_t* d_blob, int ns, const uint64_t* stream_off,
+                       const uint64_t* stream_len, uint32_t out_container_bytes, const flacb200_dec_raw_params* raw) {
+    d->have = false;
     // segments: every stream is cut into 4096-byte pieces scanned by one warp each
     d->h_segs.clear(); d->h_first_seg.assign(ns + 1, 0);
     for (int s = 0; s < ns; s++) {
@@ -107,13 +142,6 @@ extern "C" int flacb200_decode_batch(flacb200_ctx* ctx, const uint8_t* blob, int
     d->n_streams = ns; d->n_cands = 0; d->total_elems = 0;
     if (ns == 0) { d->have = true; d->out_bytes = out_container_bytes ? out_container_bytes : 2; return 0; }
 
-    const uint8_t* d_blob = blob;
-    if (!blob_is_device) {
-        CKD(d->blob.reserve(blob_bytes + 64));
-        CKD(cudaMemcpyAsync(d->blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, st));
-        CKD(cudaMemsetAsync((uint8_t*)d->blob.p + blob_bytes, 0, 16, st));
-        d_blob = (const uint8_t*)d->blob.p;
-    }
     CKD(d->soff.reserve(8 * (size_t)(ns + 1))); CKD(d->slen.reserve(8 * (size_t)(ns + 1)));
     CKD(d->meta.reserve(sizeof(DecStreamMeta) * (size_t)ns));
     CKD(d->segs.reserve(sizeof(DecSegment) * (size_t)(nsegs + 1)));
@@ -152,7 +180,8 @@ extern "C" int flacb200_decode_batch(flacb200_ctx* ctx, const uint8_t* blob, int
         h_base[nsegs] = (uint32_t)nc;
         std::vector<uint32_t> cf(ns + 1);
         for (int s = 0; s <= ns; s++) cf[s] = h_base[d->h_first_seg[s]];
-        CKD(cudaMemcpy(d->candfirst.p, cf.data(), 4 * (size_t)(ns + 1), cudaMemcpyHostToDevice));
+        CKD(cudaMemcpyAsync(d->candfirst.p, cf.data(), 4 * (size_t)(ns + 1), cudaMemcpyHostToDevice, st));
+        CKD(cudaStreamSynchronize(st));
     }
     CKD(cudaEventRecord(d->ev[1], st));
     uint64_t h_slots = 0;
@@ -232,6 +261,103 @@ extern "C" int flacb200_decode_fetch(flacb200_ctx* ctx, void* pcm, size_t pcm_ca
         }
     }
     if (frame_samples) { uint32_t k = 0; for (auto& c : hc) if (c.valid && k < frame_cap) frame_samples[k++] = c.blocksize; }
+    return 0;
+}
+
+// Host -> host decode in one call: the streams are cut into chunks; chunk c+1's bytes travel to the GPU while chunk c
+// decodes and chunk c-1's PCM travels back (two decode states alternate, so a chunk's PCM buffer is not reused before
+// its copy has left).  PCM lands in `pcm` in stream order, streams[s].pcm_off indexes it.
+extern "C" int flacb200_decode_batch_host(flacb200_ctx* ctx, const uint8_t* blob, uint64_t blob_bytes, uint32_t n_streams,
+                                          const uint64_t* stream_off, const uint64_t* stream_len, uint32_t out_container_bytes,
+                                          const flacb200_dec_raw_params* raw, void* pcm, size_t pcm_cap, uint64_t* total_elems,
+                                          flacb200_dec_stream_info* streams) {
+    if (!ctx) return FLACB200_ERR_NO_DEVICE;
+    if ((!blob && blob_bytes) || !pcm || (n_streams && (!stream_off || !stream_len))) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "null argument", cudaSuccess);
+    if (out_container_bytes != 2 && out_container_bytes != 4) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "out_container_bytes must be 2 or 4", cudaSuccess);
+    cudaSetDevice(fb_ctx_device(ctx));
+    const int ns = (int)n_streams;
+    if (total_elems) *total_elems = 0;
+    for (int s = 0; s < ns; s++) {
+        if (stream_off[s] + stream_len[s] > blob_bytes) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "stream exceeds blob", cudaSuccess);
+        if (stream_len[s] >= 0xFFFFFFF0ull) return fb_ctx_fail(ctx, FLACB200_ERR_UNSUPPORTED, "streams of 4 GiB or more are not supported", cudaSuccess);
+    }
+    if (ns == 0) return 0;
+    DecState* D[2] = {state(ctx, 0), state(ctx, 1)};
+    DecState* d0 = D[0];
+    cudaStream_t st = fb_ctx_stream(ctx);
+    if (!d0->h2d) { CKD(cudaStreamCreateWithFlags(&d0->h2d, cudaStreamNonBlocking)); CKD(cudaStreamCreateWithFlags(&d0->d2h, cudaStreamNonBlocking)); }
+    for (DecState* d : D) {
+        if (!d->ev_pcm_free) { CKD(cudaEventCreateWithFlags(&d->ev_pcm_free, cudaEventDisableTiming)); CKD(cudaEventCreateWithFlags(&d->ev_post, cudaEventDisableTiming)); }
+        d->pcm_busy = false; d->have = false;
+    }
+    // chunks of whole streams with about equal byte counts
+    // A chunk only pays off when it still fills the GPU: the frame kernel decodes one frame per thread and a launch
+    // cannot finish faster than one frame's serial decode (a few ms), so chunks hold >= ~200 MB of FLAC (~20 000 frames).
+    int nchunks = (int)(blob_bytes / (200ull << 20));
+    if (const char* ev = getenv("FLACB200_DEC_CHUNKS")) { const int v = atoi(ev); if (v > 0) nchunks = v; }
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 12) nchunks = 12;
+    if (nchunks > ns) nchunks = ns;
+    std::vector<int> cs(nchunks + 1, 0);
+    {
+        uint64_t tot = 0; for (int s = 0; s < ns; s++) tot += stream_len[s];
+        uint64_t acc = 0; int c = 1;
+        for (int s = 0; s < ns && c < nchunks; s++) { acc += stream_len[s]; if (acc * nchunks >= tot * c && s + 1 >= c) cs[c++] = s + 1; }
+        for (; c <= nchunks; c++) cs[c] = ns;
+    }
+    while ((int)d0->ev_h2d.size() < nchunks) { cudaEvent_t e; CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); d0->ev_h2d.push_back(e); }
+    CKD(d0->hblob.reserve(blob_bytes + 64));
+    uint8_t* d_blob = (uint8_t*)d0->hblob.p;
+    CKD(cudaMemsetAsync(d_blob + blob_bytes, 0, 16, d0->h2d));
+    bool monotonic = true;
+    for (int s = 1; s < ns; s++) if (stream_off[s] < stream_off[s - 1] + stream_len[s - 1]) { monotonic = false; break; }
+    for (int c = 0; c < nchunks; c++) {
+        const int s0 = cs[c], s1 = cs[c + 1];
+        if (s1 > s0) {
+            if (monotonic) {
+                const uint64_t b0 = stream_off[s0], b1 = stream_off[s1 - 1] + stream_len[s1 - 1];
+                CKD(cudaMemcpyAsync(d_blob + b0, blob + b0, b1 - b0, cudaMemcpyHostToDevice, d0->h2d));
+            } else {
+                for (int s = s0; s < s1; s++) CKD(cudaMemcpyAsync(d_blob + stream_off[s], blob + stream_off[s], stream_len[s], cudaMemcpyHostToDevice, d0->h2d));
+            }
+        }
+        CKD(cudaEventRecord(d0->ev_h2d[c], d0->h2d));
+    }
+    uint64_t elem_base = 0;
+    int status = 0;
+    for (int c = 0; c < nchunks; c++) {
+        const int s0 = cs[c], s1 = cs[c + 1];
+        if (s1 <= s0) continue;
+        DecState* d = D[c & 1];
+        CKD(cudaStreamWaitEvent(st, d0->ev_h2d[c], 0));
+        if (d->pcm_busy) { CKD(cudaStreamWaitEvent(st, d->ev_pcm_free, 0)); d->pcm_busy = false; }     // its previous PCM must have left
+        const int rc = decode_core(ctx, d, st, d_blob, s1 - s0, stream_off + s0, stream_len + s0, out_container_bytes, raw);
+        if (rc) { status = rc; break; }
+        CKD(cudaEventRecord(d->ev_post, st));
+        // per-stream results of the chunk (post may flag CRC errors: read them after it)
+        CKD(cudaMemcpyAsync(d->h_res.data(), d->res.p, sizeof(DecStreamResult) * (size_t)(s1 - s0), cudaMemcpyDeviceToHost, st));
+        const size_t bytes = (size_t)d->total_elems * out_container_bytes;
+        if ((elem_base + d->total_elems) * out_container_bytes > pcm_cap) { status = fb_ctx_fail(ctx, FLACB200_ERR_ARG, "pcm buffer too small", cudaSuccess); break; }
+        CKD(cudaStreamWaitEvent(d0->d2h, d->ev_post, 0));
+        if (bytes) CKD(cudaMemcpyAsync((uint8_t*)pcm + (size_t)elem_base * out_container_bytes, d->pcm.p, bytes, cudaMemcpyDeviceToHost, d0->d2h));
+        CKD(cudaEventRecord(d->ev_pcm_free, d0->d2h));
+        d->pcm_busy = true;
+        CKD(cudaStreamSynchronize(st));
+        if (streams) {
+            for (int s = s0; s < s1; s++) {
+                const DecStreamResult& h = d->h_res[s - s0];
+                flacb200_dec_stream_info& o = streams[s];
+                o.total_samples = h.total_samples; o.pcm_off = h.pcm_off + elem_base; o.consumed = h.consumed; o.n_frames = h.n_frames; o.status = h.status;
+                o.sample_rate = h.sample_rate; o.channels = h.channels; o.bits_per_sample = h.bps; o.max_blocksize = h.max_blocksize;
+            }
+        }
+        elem_base += d->total_elems;
+    }
+    CKD(cudaStreamSynchronize(d0->d2h));
+    CKD(cudaStreamSynchronize(d0->h2d));
+    for (DecState* d : D) d->pcm_busy = false;
+    if (status) return status;
+    if (total_elems) *total_elems = elem_base;
     return 0;
 }
 

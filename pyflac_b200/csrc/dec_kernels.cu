@@ -182,7 +182,8 @@ struct BitReader {
     const uint32_t* wend;               // first word past the stream (aligned up)
     const uint8_t* sbase;               // stream start (for bit positions)
     uint64_t acc; int n;                // n valid bits at the top of acc
-    uint32_t nextw;                     // word fetched one refill ahead (hides the load latency)
+    uint32_t next1, next2;              // RAW words fetched one and two refills ahead: the byte swap happens when a word is
+                                        // consumed, so nothing waits on a load until two refills (~6 symbols) after it was issued
     int over;                           // words consumed past the end of the stream
     __device__ __forceinline__ void init(const uint8_t* base, uint64_t start, uint64_t slen) {
         sbase = base;
@@ -197,18 +198,20 @@ struct BitReader {
         wp++;
         acc = ((uint64_t)w << 32) << skip;
         n = 32 - (int)skip;
-        nextw = 0;
-        if (wp < wend) nextw = __byte_perm(__ldg(wp), 0, 0x0123);
+        next1 = 0; next2 = 0;
+        if (wp < wend) next1 = __ldg(wp);
+        if (wp + 1 < wend) next2 = __ldg(wp + 1);
         fill();
     }
-    // invariant after fill(): n >= 32 (n <= 32 before => exactly one word is added)
+    // invariant after fill(): n >= 32 (n <= 32 before => exactly one word is added).  wp points at the word held in next1.
     __device__ __forceinline__ void fill() {
         if (n <= 32) {
-            const uint32_t w = nextw;
+            const uint32_t w = __byte_perm(next1, 0, 0x0123);
             if (wp >= wend) over++;
             wp++;
-            nextw = 0;
-            if (wp < wend) nextw = __byte_perm(__ldg(wp), 0, 0x0123);
+            next1 = next2;
+            next2 = 0;
+            if (wp + 1 < wend) next2 = __ldg(wp + 1);
             acc |= (uint64_t)w << (32 - n);
             n += 32;
         }

@@ -82,6 +82,31 @@ def test_encode_decode_roundtrip_full_size(eng):
         assert si.status == 0 and si.n_frames == 32 and np.array_equal(o, x)
 
 
+def test_decode_host_pipelined_matches_plain(eng, checkers, monkeypatch):
+    """flacb200_decode_batch_host (chunked H2D / decode / D2H pipeline) == the plain batch path, ragged streams,
+    mono + stereo, fewer streams than chunks, a corrupted stream in the middle"""
+    from pyflac_b200 import _native as nat
+    monkeypatch.setenv("FLACB200_DEC_CHUNKS", "5")           # force the multi-chunk pipeline on these small batches
+    for ch, n_streams in [(2, 40), (1, 5), (2, 1)]:
+        xs = [music_like(4096 * (1 + s % 5) + 37 * s, ch, 48000, 16, seed=90 + s) for s in range(n_streams)]
+        blobs, _ = nat.encode_streams(eng, xs, 48000, 16, 5, 4096)
+        blobs = [bytearray(b) for b in blobs]
+        if n_streams > 10:
+            blobs[7][len(blobs[7]) // 2] ^= 0x55                      # CRC mismatch somewhere inside stream 7
+        blob = np.frombuffer(b"".join(bytes(b) for b in blobs), np.uint8)
+        sl = np.array([len(b) for b in blobs], np.uint64)
+        so = np.concatenate([[0], np.cumsum(sl)[:-1]]).astype(np.uint64)
+        ref_out, ref_infos = nat.decode_streams(eng, [bytes(b) for b in blobs])
+        out = np.zeros(sum(x.size for x in xs) + 16, np.int16)
+        tot, infos = eng.decode_host_pipelined(blob, so, sl, out, 2)
+        for s in range(n_streams):
+            assert infos[s].status == ref_infos[s].status, s
+            assert infos[s].total_samples == ref_infos[s].total_samples and infos[s].n_frames == ref_infos[s].n_frames
+            got = out[int(infos[s].pcm_off): int(infos[s].pcm_off + infos[s].total_samples * ch)].reshape(-1, ch)
+            assert np.array_equal(got, ref_out[s].reshape(-1, ch)), s
+        assert tot == sum(int(i.total_samples) * ch for i in list(infos)[:n_streams])
+
+
 def test_full_size_config4_decode_4096_streams(eng):
     """BASELINE configs[3] shape: 4096 stereo s16 streams of 131072 samples -> int16 PCM (64 distinct, tiled)."""
     from pyflac_b200 import _native as nat
