@@ -91,46 +91,48 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 // used exactly when libFLAC proves it cannot overflow.  check_limit reproduces the _limit_residual rejection.
 //
 // Lane p walks its own contiguous samples; h[] is the predictor history, rotated statically: inside a group
-// of ORDER samples, sample u reads h[(u-1-j) mod ORDER] and then overwrites h[u] (the tap that just expired).
+// of C samples, sample u reads h[(u-1-j) mod C] and then overwrites h[u] (the tap that just expired).
+// C is the order CLASS (4, 8 or 12 taps; coefficients beyond the real order are zero): three code bodies instead of
+// thirteen keep the instruction working set of an SM -- whose warps run different orders at the same time -- inside
+// the instruction cache (the per-order version spent half its stall samples waiting for instruction fetch).
 // psum must be zeroed by the caller; partition totals arrive through shared atomics (<= 3 per lane).
-template <int ORDER, bool WIDE, bool PACKED>
-__device__ __noinline__ bool residual_partition_sums(SigView V, FrameGeo G, const int32_t* __restrict__ qs, int shift,
+template <int C, bool WIDE, bool PACKED>
+__device__ __noinline__ bool residual_partition_sums(SigView V, FrameGeo G, const int32_t* __restrict__ qs, int order, int shift,
                                                      int psize, bool check_limit, unsigned long long* psum, int lane) {
-    constexpr int O = ORDER > 0 ? ORDER : 1;
-    int32_t q[O];
+    int32_t q[C];
 #pragma unroll
-    for (int j = 0; j < ORDER; j++) q[j] = qs[j];
+    for (int j = 0; j < C; j++) q[j] = (j < order) ? qs[j] : 0;
     bool bad = false;
     const int blk_lo = lane * G.B0, blk_hi = min(G.N, blk_lo + G.B0);
-    int lo = max(blk_lo, ORDER);
+    int lo = max(blk_lo, order);
     const int32_t* rowp = V.base + lane * G.RS - blk_lo;      // rowp[i] is sample i for blk_lo <= i < blk_hi
     while (lo < blk_hi) {
         const int part = lo / psize;
         const int hi = min(blk_hi, (part + 1) * psize);
-        int32_t h[O];
+        int32_t h[C];
 #pragma unroll
-        for (int k = 0; k < ORDER; k++) h[k] = sig_word<PACKED>(V.base[pidx(G, lo - ORDER + k)], V);
+        for (int k = 0; k < C; k++) h[k] = sig_word<PACKED>(V.base[pidx(G, max(lo - C + k, 0))], V);    // taps before sample 0 carry zero coefficients
         unsigned long long acc = 0;
-        for (int g = lo; g < hi; g += O) {
+        for (int g = lo; g < hi; g += C) {
 #pragma unroll
-            for (int u = 0; u < O; u++) {
+            for (int u = 0; u < C; u++) {
                 if (g + u < hi) {
                     const int xv = sig_word<PACKED>(rowp[g + u], V);
                     long long r;
                     if (WIDE) {
                         long long s = 0;
 #pragma unroll
-                        for (int j = 0; j < ORDER; j++) s += (long long)q[j] * (long long)h[(u - 1 - j + 2 * O) % O];
+                        for (int j = 0; j < C; j++) s += (long long)q[j] * (long long)h[(u - 1 - j + 2 * C) % C];
                         r = (long long)xv - (s >> shift);
                         if (check_limit && (r <= (long long)INT32_MIN || r > (long long)INT32_MAX)) bad = true;
                     } else {
                         int s = 0;
 #pragma unroll
-                        for (int j = 0; j < ORDER; j++) s += q[j] * h[(u - 1 - j + 2 * O) % O];
+                        for (int j = 0; j < C; j++) s += q[j] * h[(u - 1 - j + 2 * C) % C];
                         r = (long long)(xv - (s >> shift));
                     }
                     acc += (unsigned long long)(r < 0 ? -r : r);
-                    if (ORDER > 0) h[u] = xv;
+                    h[u] = xv;
                 }
             }
         }
@@ -144,21 +146,9 @@ __device__ __noinline__ bool residual_partition_sums(SigView V, FrameGeo G, cons
 template <bool WIDE, bool PACKED>
 __device__ __forceinline__ bool residual_order(int order, const SigView& V, const FrameGeo& G, const int32_t* q, int shift,
                                                int psize, bool limit, unsigned long long* psum, int lane) {
-    switch (order) {
-        case 0: return residual_partition_sums<0, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        case 1: return residual_partition_sums<1, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        case 2: return residual_partition_sums<2, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        case 3: return residual_partition_sums<3, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        case 4: return residual_partition_sums<4, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        case 5: return residual_partition_sums<5, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        case 6: return residual_partition_sums<6, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        case 7: return residual_partition_sums<7, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        case 8: return residual_partition_sums<8, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        case 9: return residual_partition_sums<9, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        case 10: return residual_partition_sums<10, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        case 11: return residual_partition_sums<11, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-        default: return residual_partition_sums<12, WIDE, PACKED>(V, G, q, shift, psize, limit, psum, lane);
-    }
+    if (order <= 4) return residual_partition_sums<4, WIDE, PACKED>(V, G, q, order, shift, psize, limit, psum, lane);
+    if (order <= 8) return residual_partition_sums<8, WIDE, PACKED>(V, G, q, order, shift, psize, limit, psum, lane);
+    return residual_partition_sums<12, WIDE, PACKED>(V, G, q, order, shift, psize, limit, psum, lane);
 }
 
 template <bool PACKED>

@@ -52,12 +52,14 @@ __device__ __forceinline__ void put_bits(uint32_t* buf, uint32_t pos, uint32_t v
 // Residual arithmetic: r = x[i] - ((sum q_j x[i-1-j]) >> shift); fixed predictors are the same formula with
 // binomial coefficients and shift 0.  WIDE = 64-bit accumulate, chosen exactly as the analysis kernel does.
 template <int ORDER, bool WIDE>
-__device__ __forceinline__ uint32_t pack_rice_body(const SubframePlan& pl, const int32_t* __restrict__ qs, int shift,
-                                                   const int32_t* __restrict__ x, int N, uint32_t body, uint32_t* obuf,
-                                                   PackShared& S, int warp, int lane) {
-    int32_t q[ORDER > 0 ? ORDER : 1];
+__device__ __noinline__ uint32_t pack_rice_body(const SubframePlan& pl, const int32_t* __restrict__ qs, int order, int shift,
+                                                const int32_t* __restrict__ x, int N, uint32_t body, uint32_t* obuf,
+                                                PackShared& S, int warp, int lane) {
+    // ORDER is the order CLASS (4, 8 or 12 taps, coefficients beyond the real order are zero): three code bodies
+    // instead of thirteen keep the kernel inside the instruction cache
+    int32_t q[ORDER];
 #pragma unroll
-    for (int j = 0; j < ORDER; j++) q[j] = qs[j];
+    for (int j = 0; j < ORDER; j++) q[j] = (j < order) ? qs[j] : 0;
     const uint32_t plen = pl.rice2 ? 5u : 4u;
     const uint32_t psize = (uint32_t)N >> pl.part_order;
     const uint32_t magic = (uint32_t)((0x100000000ull + psize - 1u) / psize);   // i / psize == umulhi(i, magic) for i, psize < 2^16
@@ -70,17 +72,17 @@ __device__ __forceinline__ uint32_t pack_rice_body(const SubframePlan& pl, const
         for (int k = 0; k < kTileK; k++) {
             const int i = seg0 + k * 32 + lane;
             u[k] = 0xffffffffu;                                  // marks "no sample"
-            if (i >= ORDER && i < N) {
+            if (i >= order && i < N) {
                 int32_t r;
                 if (WIDE) {
                     long long sacc = 0;
 #pragma unroll
-                    for (int j = 0; j < ORDER; j++) sacc += (long long)q[j] * (long long)x[i - 1 - j];
+                    for (int j = 0; j < ORDER; j++) sacc += (long long)q[j] * (long long)x[max(i - 1 - j, 0)];
                     r = (int32_t)((long long)x[i] - (sacc >> shift));
                 } else {
                     int sacc = 0;
 #pragma unroll
-                    for (int j = 0; j < ORDER; j++) sacc += q[j] * x[i - 1 - j];
+                    for (int j = 0; j < ORDER; j++) sacc += q[j] * x[max(i - 1 - j, 0)];
                     r = x[i] - (sacc >> shift);
                 }
                 const uint32_t uu = ((uint32_t)r << 1) ^ (uint32_t)(r >> 31);
@@ -98,7 +100,7 @@ __device__ __forceinline__ uint32_t pack_rice_body(const SubframePlan& pl, const
 #pragma unroll
         for (int k = 0; k < kTileK; k++) {
             const int i = seg0 + k * 32 + lane;
-            const bool valid = (i >= ORDER && i < N);
+            const bool valid = (i >= order && i < N);
             uint32_t kk = 0, part = 0, len = 0;
             if (valid) {
                 part = __umulhi((uint32_t)i, magic);
@@ -111,7 +113,7 @@ __device__ __forceinline__ uint32_t pack_rice_body(const SubframePlan& pl, const
             if (valid) {
                 const uint32_t pos = wpos + (incl - len) + plen * (part + 1u);
                 put_bits(obuf, pos + (u[k] >> kk), (1u << kk) | (u[k] & ((1u << kk) - 1u)), kk + 1u);
-                if ((uint32_t)i == part * psize || i == ORDER) put_bits(obuf, pos - plen, kk, plen);   // first sample of its partition
+                if ((uint32_t)i == part * psize || i == order) put_bits(obuf, pos - plen, kk, plen);   // first sample of its partition
             }
             wpos += __shfl_sync(0xffffffffu, incl, 31);
         }
@@ -122,23 +124,11 @@ __device__ __forceinline__ uint32_t pack_rice_body(const SubframePlan& pl, const
 }
 
 template <bool WIDE>
-__device__ uint32_t pack_rice_dispatch(int order, const SubframePlan& pl, const int32_t* q, int shift, const int32_t* x, int N,
-                                       uint32_t body, uint32_t* obuf, PackShared& S, int warp, int lane) {
-    switch (order) {
-        case 0: return pack_rice_body<0, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        case 1: return pack_rice_body<1, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        case 2: return pack_rice_body<2, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        case 3: return pack_rice_body<3, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        case 4: return pack_rice_body<4, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        case 5: return pack_rice_body<5, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        case 6: return pack_rice_body<6, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        case 7: return pack_rice_body<7, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        case 8: return pack_rice_body<8, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        case 9: return pack_rice_body<9, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        case 10: return pack_rice_body<10, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        case 11: return pack_rice_body<11, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-        default: return pack_rice_body<12, WIDE>(pl, q, shift, x, N, body, obuf, S, warp, lane);
-    }
+__device__ __forceinline__ uint32_t pack_rice_dispatch(int order, const SubframePlan& pl, const int32_t* q, int shift, const int32_t* x, int N,
+                                                       uint32_t body, uint32_t* obuf, PackShared& S, int warp, int lane) {
+    if (order <= 4) return pack_rice_body<4, WIDE>(pl, q, order, shift, x, N, body, obuf, S, warp, lane);
+    if (order <= 8) return pack_rice_body<8, WIDE>(pl, q, order, shift, x, N, body, obuf, S, warp, lane);
+    return pack_rice_body<12, WIDE>(pl, q, order, shift, x, N, body, obuf, S, warp, lane);
 }
 
 template <typename PcmT>
@@ -249,13 +239,7 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
                 else blen = pack_rice_dispatch<true>((int)order, pl, pl.qlp, pl.shift, x, N, body, obuf, S, warp, lane);
             } else {
                 const int32_t cfix[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
-                switch (order) {
-                    case 0: blen = pack_rice_body<0, false>(pl, cfix[0], 0, x, N, body, obuf, S, warp, lane); break;
-                    case 1: blen = pack_rice_body<1, false>(pl, cfix[1], 0, x, N, body, obuf, S, warp, lane); break;
-                    case 2: blen = pack_rice_body<2, false>(pl, cfix[2], 0, x, N, body, obuf, S, warp, lane); break;
-                    case 3: blen = pack_rice_body<3, false>(pl, cfix[3], 0, x, N, body, obuf, S, warp, lane); break;
-                    default: blen = pack_rice_body<4, false>(pl, cfix[4], 0, x, N, body, obuf, S, warp, lane); break;
-                }
+                blen = pack_rice_body<4, false>(pl, cfix[order], (int)order, 0, x, N, body, obuf, S, warp, lane);
             }
             pos = body + blen;
         }
@@ -416,8 +400,11 @@ __device__ void md5_block(uint32_t h[4], const uint32_t w[16]) {
         0xf4292244,0x432aff97,0xab9423a7,0xfc93a039,0x655b59c3,0x8f0ccc92,0xffeff47d,0x85845dd1,
         0x6fa87e4f,0xfe2ce6e0,0xa3014314,0x4e0811a1,0xf7537e82,0xbd3af235,0x2ad7d2bb,0xeb86d391 };
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3];
-// critical path per step: LOP3 (f depends on the fresh b) -> IADD -> SHF -> IADD; a + K + w[g] is ready early
-#define FB_MD5_STEP(f, g, s, i) { const uint32_t akw = a + (K[i] + w[g]); const uint32_t t = akw + (f); a = d; d = c; c = b; b = b + rotl32(t, s); }
+// critical path per step: LOP3 (f depends on the fresh b) -> IADD3 -> LEA.HI (rotate + add).  K[i] + w[g] is formed by
+// an opaque add so that it stays OFF the chain (left to itself the compiler adds K after the 3-input add, a 4th
+// dependent instruction: 23 instead of ~15 cycles per step).
+#define FB_MD5_STEP(f, g, s, i) { uint32_t kw; asm volatile("add.u32 %0, %1, %2;" : "=r"(kw) : "r"(w[g]), "r"(K[i])); \
+                                  const uint32_t t = (a + kw) + (f); a = d; d = c; c = b; b = b + rotl32(t, s); }
 #pragma unroll
     for (int i = 0; i < 16; i++) { const int sh[4] = {7, 12, 17, 22}; FB_MD5_STEP((b & c) | (~b & d), i, sh[i & 3], i) }
 #pragma unroll
