@@ -112,6 +112,9 @@ __device__ __forceinline__ bool parse_header(const uint8_t* __restrict__ p, uint
 }
 
 // One warp per 4096-byte segment; pass 0 counts candidates, pass 1 writes them in position order.
+// The scan itself is an HBM stream: every lane loads 16 aligned bytes, a SIMD-in-register test marks positions that
+// hold 0xFF followed by 0xF8 / 0xF9, and only those (about one per 30 KiB of random data plus the real frame starts)
+// go through the header parser and its CRC-8.
 __global__ void __launch_bounds__(128)
 dec_sync_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, const uint64_t* __restrict__ stream_len,
                 const DecStreamMeta* __restrict__ meta, const DecSegment* __restrict__ segs, int n_segs, int pass,
@@ -125,23 +128,57 @@ dec_sync_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ s
     uint32_t count = 0;
     const uint32_t out0 = pass ? seg_base[seg] : 0u;
     if (m.status == kDecOk) {
-        for (uint32_t o = 0; o < kDecSegBytes; o += 32) {
-            const uint64_t pos = (uint64_t)sg.start + o + lane;
-            DecCand c; bool hit = false;
-            if (pos + 1 < slen && o + lane < sg.bytes && pos >= m.first_frame) {
-                if (sbase[pos] == 0xFF && (sbase[pos + 1] & 0xFE) == 0xF8) {
-                    hit = parse_header(sbase + pos, slen - pos, m, c);
-                    // frames of one stream keep channels / bps (cheap plausibility filter; the chain decides anyway)
-                    if (hit && (c.channels != m.channels || c.bps != m.bps) && m.channels) hit = false;
+        const uint8_t* seg_lo = sbase + sg.start;                                   // first byte of the segment
+        const uint8_t* seg_hi = seg_lo + sg.bytes;                                  // one past its last byte
+        const uint8_t* s_end = sbase + slen;
+        const uint8_t* a0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(seg_lo) & ~(uintptr_t)15);
+        for (const uint8_t* base = a0; base < seg_hi; base += 512) {
+            const uint8_t* p = base + 16 * lane;
+            uint32_t hits = 0;                                                      // bit k: candidate sync code at p + k
+            if (p < seg_hi && p + 16 > seg_lo) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+                const uint32_t nb = (p + 16 < s_end) ? (uint32_t)__ldg(p + 16) : 0u;   // first byte of the next chunk
+                const uint32_t w[5] = {v.x, v.y, v.z, v.w, nb};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t ff = __vcmpeq4(w[q], 0xFFFFFFFFu);                                   // 0xFF where the byte is 0xFF
+                    const uint32_t nx = __funnelshift_r(w[q], w[q + 1], 8);                             // the following bytes
+                    const uint32_t f8 = __vcmpeq4(nx & 0xFEFEFEFEu, 0xF8F8F8F8u);
+                    const uint32_t both = ff & f8;
+                    if (both) hits |= ((both & 1u) | ((both >> 7) & 2u) | ((both >> 14) & 4u) | ((both >> 21) & 8u)) << (4 * q);
+                }
+                // keep positions inside this segment, inside the stream's audio part, with a second byte present
+                for (uint32_t t = hits; t; t &= t - 1) {
+                    const int k = __ffs((int)t) - 1;
+                    const uint8_t* c = p + k;
+                    if (c < seg_lo || c >= seg_hi || c + 1 >= s_end || (uint64_t)(c - sbase) < m.first_frame) hits &= ~(1u << k);
                 }
             }
-            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-            if (pass && hit) {
-                c.stream = sg.stream; c.pos = (uint32_t)pos;
-                c.status = kDecPending; c.end_pos = 0; c.sample_slot = 0; c.valid = 0; c.sample_off = 0;
-                cands[out0 + count + __popc(mask & ((1u << lane) - 1u))] = c;
+            uint32_t lanes = __ballot_sync(0xffffffffu, hits != 0);
+            while (lanes) {                                                          // rare: lanes with hits, in position order
+                const int src = __ffs((int)lanes) - 1;
+                lanes &= lanes - 1;
+                uint32_t found = 0;
+                if (lane == src) {
+                    for (uint32_t t = hits; t; t &= t - 1) {
+                        const uint8_t* c = p + (__ffs((int)t) - 1);
+                        const uint64_t pos = (uint64_t)(c - sbase);
+                        DecCand cd;
+                        bool hit = parse_header(c, slen - pos, m, cd);
+                        // frames of one stream keep channels / bps (cheap plausibility filter; the chain decides anyway)
+                        if (hit && (cd.channels != m.channels || cd.bps != m.bps) && m.channels) hit = false;
+                        if (hit) {
+                            if (pass) {
+                                cd.stream = sg.stream; cd.pos = (uint32_t)pos;
+                                cd.status = kDecPending; cd.end_pos = 0; cd.sample_slot = 0; cd.valid = 0; cd.sample_off = 0;
+                                cands[out0 + count + found] = cd;
+                            }
+                            found++;
+                        }
+                    }
+                }
+                count += __shfl_sync(0xffffffffu, found, src);
             }
-            count += __popc(mask);
         }
     }
     if (!pass && lane == 0) seg_count[seg] = count;

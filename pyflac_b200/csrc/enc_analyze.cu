@@ -761,11 +761,11 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
                 if (ob < bb || (ob == bb && oi < bi)) { bb = ob; bi = oi; }
             }
             guess = (bb < 4294967295.0) ? bi : 1;
-            // guard band: a runner-up within 1e-9 relative of the winner could flip under a libm log that
+            // guard band: a runner-up within 1e-12 relative (several thousand ulps of the log) of the winner could flip under a libm log that
             // differs in the last ulp (DESIGN.md "log guard"); counted, never silently ignored
             const int ul_best = __shfl_sync(0xffffffffu, (int)ul, guess & 31);
             const bool amb = (lane >= 1 && lane <= max_this && lane != guess) && (ul || ul_best) &&
-                             fabs(bits - bb) <= 1e-9 * fabs(bb);
+                             fabs(bits - bb) <= 1e-12 * fabs(bb);
             if (__any_sync(0xffffffffu, amb) && lane == 0 && stats) atomicAdd(&stats->log_ambiguous, 1ull);
         }
         if (dg && step < kMaxApodSteps) { if (lane < max_this) dg->lpc_err[step][lane] = ws.lperr[lane]; if (lane == 0) dg->lpc_order[step] = guess; }
@@ -773,7 +773,7 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
         const int order = guess;
         bool ul2;
         const double rbps = expected_bits_per_sample(ws.lperr[order - 1], FB_DDIV(0.5, (double)(N - order)), &ul2);
-        if (ul2 && fabs(rbps - (double)sbps) <= 1e-9 * (double)sbps && lane == 0 && stats) atomicAdd(&stats->log_ambiguous, 1ull);
+        if (ul2 && fabs(rbps - (double)sbps) <= 1e-12 * (double)sbps && lane == 0 && stats) atomicAdd(&stats->log_ambiguous, 1ull);
         if (!(rbps >= (double)sbps)) {
             int prec = (int)P.qlp_precision;
             if (sbps <= 17) prec = min(prec, 32 - sbps - (int)ilog2_u32((uint32_t)order));
