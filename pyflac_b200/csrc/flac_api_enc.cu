@@ -37,7 +37,7 @@ const char *FLAC__VENDOR_STRING = "reference libFLAC 1.4.3 20230623";   // byte-
 
 namespace {
 
-enum { ST_OK = 0, ST_UNINITIALIZED = 1, ST_VERIFY_DECODER_ERROR = 3, ST_CLIENT_ERROR = 5, ST_IO_ERROR = 6, ST_FRAMING_ERROR = 7, ST_MEMORY_ALLOCATION_ERROR = 8 };
+enum { ST_OK = 0, ST_UNINITIALIZED = 1, ST_VERIFY_DECODER_ERROR = 3, ST_VERIFY_MISMATCH = 4, ST_CLIENT_ERROR = 5, ST_IO_ERROR = 6, ST_FRAMING_ERROR = 7, ST_MEMORY_ALLOCATION_ERROR = 8 };
 enum { INIT_OK = 0, INIT_ENCODER_ERROR = 1, INIT_UNSUPPORTED_CONTAINER = 2, INIT_INVALID_CALLBACKS = 3, INIT_ALREADY_INITIALIZED = 13 };
 
 // RFC 1321, incremental (host side of the handle API only)
@@ -112,6 +112,7 @@ struct EncImpl {
     std::vector<int32_t> pending;          // interleaved samples not yet framed
     uint32_t frame_number = 0;
     uint8_t last_ca = 0;                   // loose mid/side: channel assignment of the last frame delivered
+    uint64_t vstat_sample = 0; uint32_t vstat_channel = 0; int32_t vstat_expected = 0, vstat_got = 0;   // verify mismatch report
     uint64_t samples_written = 0, bytes_written = 0;
     uint32_t min_fs = 0, max_fs = 0, frames_written = 0;
     uint64_t streaminfo_offset = 0;        // byte position of the STREAMINFO block header as told by the tell callback
@@ -192,6 +193,27 @@ bool encode_pending(FLAC__StreamEncoder* e, uint64_t n) {
         size_t k = 0;
         for (size_t i = 0; i < vals; i++) { const uint32_t v = (uint32_t)m->pending[i]; for (uint32_t b = 0; b < bytes; b++) tmp[k++] = (uint8_t)(v >> (8 * b)); }
         m->md5.update(tmp.data(), tmp.size());
+    }
+    // up: verify_write_callback_ / FLAC__stream_encoder_set_verify (stream_encoder.h:781-801): every frame is decoded again
+    // (here: the whole batch through the GPU decoder, headerless mode) and compared with the input before it is delivered
+    if (m->verify && r.n_frames) {
+        flacb200_dec_raw_params rp; rp.sample_rate = m->sample_rate; rp.channels = m->channels; rp.bits_per_sample = m->bps;
+        const uint64_t boff = 0, blen = r.total_bytes;
+        std::vector<uint8_t> padded(m->arena.begin(), m->arena.begin() + r.total_bytes);
+        padded.resize(r.total_bytes + 16, 0);
+        std::vector<int32_t> back((size_t)n * m->channels);
+        flacb200_dec_stream_info di{};
+        if (flacb200_decode_batch(ctx, padded.data(), 0, blen, 1, &boff, &blen, 4, &rp) != 0 ||
+            flacb200_decode_fetch(ctx, back.data(), back.size() * 4, &di, nullptr, 0) != 0 || di.status != 0) { m->state = ST_VERIFY_DECODER_ERROR; return false; }
+        bool same = di.total_samples == n;
+        for (size_t i = 0; same && i < back.size(); i++) {
+            if (back[i] != m->pending[i]) {
+                same = false;
+                m->vstat_sample = m->samples_written + i / m->channels; m->vstat_channel = (uint32_t)(i % m->channels);
+                m->vstat_expected = m->pending[i]; m->vstat_got = back[i];
+            }
+        }
+        if (!same) { m->state = ST_VERIFY_MISMATCH; return false; }
     }
     if (loose && r.n_frames) {
         std::vector<uint8_t> ca(r.n_frames);
@@ -291,8 +313,11 @@ TUNING(rice_parameter_search_dist, uint32_t)
 
 int FLAC__stream_encoder_get_state(const FLAC__StreamEncoder* e) { return I(e) ? I(e)->state : ST_UNINITIALIZED; }
 const char* FLAC__stream_encoder_get_resolved_state_string(const FLAC__StreamEncoder* e) { return FLAC__StreamEncoderStateString[FLAC__stream_encoder_get_state(e)]; }
-void FLAC__stream_encoder_get_verify_decoder_error_stats(const FLAC__StreamEncoder*, FLAC__uint64* a, uint32_t* f, uint32_t* c, uint32_t* s, FLAC__int32* x, FLAC__int32* g) {
-    if (a) *a = 0; if (f) *f = 0; if (c) *c = 0; if (s) *s = 0; if (x) *x = 0; if (g) *g = 0;
+void FLAC__stream_encoder_get_verify_decoder_error_stats(const FLAC__StreamEncoder* e, FLAC__uint64* a, uint32_t* f, uint32_t* c, uint32_t* s, FLAC__int32* x, FLAC__int32* g) {
+    const EncImpl* m = I(e);
+    const uint32_t N = m && m->N ? m->N : 1u;
+    if (a) *a = m ? m->vstat_sample : 0; if (f) *f = m ? (uint32_t)(m->vstat_sample / N) : 0; if (c) *c = m ? m->vstat_channel : 0;
+    if (s) *s = m ? (uint32_t)(m->vstat_sample % N) : 0; if (x) *x = m ? m->vstat_expected : 0; if (g) *g = m ? m->vstat_got : 0;
 }
 FLAC__bool FLAC__stream_encoder_get_verify(const FLAC__StreamEncoder* e) { return I(e)->verify; }
 FLAC__bool FLAC__stream_encoder_get_streamable_subset(const FLAC__StreamEncoder* e) { return I(e)->streamable_subset; }

@@ -72,6 +72,16 @@ def test_stream_encoder_loose_mid_side_across_calls(ours, ref):
     assert _norm(a["log"]) == _norm(b["log"]) and a["file"] == b["file"]
 
 
+def test_stream_encoder_verify(ours, ref):
+    """verify=True: same bytes and callbacks as libFLAC's verifying encoder, state stays OK (decode-and-compare on the GPU)"""
+    from _flacapi import encode_session
+    for x, bps, sr in [(corpus_signal("mixed", 4096 * 3 + 11, 2, 16, seed=21), 16, 44100), (corpus_signal("wasted", 5000, 1, 24, seed=22), 24, 96000)]:
+        a = encode_session(ours, x, sr, bps, 5, 0, chunks=[3000] * 10, verify=True)
+        b = encode_session(ref, x, sr, bps, 5, 0, chunks=[3000] * 10, verify=True)
+        assert a["ok"] and a["finish"] == b["finish"] == 1
+        assert _norm(a["log"]) == _norm(b["log"]) and a["file"] == b["file"]
+
+
 def test_stream_encoder_init_errors(ours, ref):
     """reference tests/test_encoder.py:139-164,202-207"""
     from _flacapi import encode_session
