@@ -391,6 +391,46 @@ static uint32_t fixed_best_predictor(const int32_t *data, uint32_t len, int narr
     return 4;
 }
 
+/* up: fixed.c FLAC__fixed_compute_best_predictor_limit_residual (subframe_bps >= 28), AS THE SHIPPED x86-64 BINARY RUNS IT
+ * (its AVX2 build of the routine; verified with FLAC__stream_encoder_disable_instruction_set):
+ *   - sums and order choice agree with the C source for every block length that is 0 or 1 mod 4 (all standard
+ *     blocksizes); for lengths 2 or 3 mod 4 (only a short last block can have one) the AVX2 loop reads past the block
+ *     and the binary's choice depends on stale memory -- this restatement (and the GPU path) stays with the C sums;
+ *   - the C source stores 34.0 as the estimate of every order that does not take the lead, which makes an all-zero
+ *     block FIXED order 0; the AVX2 build gives every valid order the total_error_0 estimate, so an all-zero block is
+ *     CONSTANT.  The binary is what pyFLAC users run, so that is what is restated here.
+ * Unlike the plain variant the
+ * sums run over ALL samples (order k from sample k on), an order whose residual does not fit int32 anywhere
+ * (|r| > INT32_MAX) is invalid, the winner is the first strictly smallest valid total, and -- 1.4.3's
+ * CHECK_ORDER_IS_VALID macro -- the bits-per-sample estimate stored for an order that takes the lead is computed from
+ * total_error_0.  sig points at sample 0. */
+static uint32_t fixed_best_predictor_limit(const int32_t *sig, uint32_t N, uint64_t err_out[5], float rbps[5])
+{
+    uint64_t tot[5] = {0, 0, 0, 0, 0}, smallest = UINT64_MAX;
+    int valid[5] = {1, 1, 1, 1, 1};
+    uint32_t order = 0;
+    const double len = (double)(N - MAX_FIXED_ORDER);
+    for (uint32_t n = 0; n < N; n++) {
+        int64_t x0 = sig[n], x1 = n >= 1 ? sig[n - 1] : 0, x2 = n >= 2 ? sig[n - 2] : 0, x3 = n >= 3 ? sig[n - 3] : 0, x4 = n >= 4 ? sig[n - 4] : 0;
+        uint64_t e[5];
+        e[0] = (uint64_t)llabs(x0);
+        e[1] = n >= 1 ? (uint64_t)llabs(x0 - x1) : 0;
+        e[2] = n >= 2 ? (uint64_t)llabs(x0 - 2 * x1 + x2) : 0;
+        e[3] = n >= 3 ? (uint64_t)llabs(x0 - 3 * x1 + 3 * x2 - x3) : 0;
+        e[4] = n >= 4 ? (uint64_t)llabs(x0 - 4 * x1 + 6 * x2 - 4 * x3 + x4) : 0;
+        for (int k = 0; k < 5; k++) { tot[k] += e[k]; if (e[k] > (uint64_t)INT32_MAX) valid[k] = 0; }
+    }
+    for (int k = 0; k < 5; k++) {
+        if (valid[k] && tot[k] < smallest) { order = (uint32_t)k; smallest = tot[k]; }
+        /* pinned against the binary: every VALID order gets the estimate of total_error_0 (so [1] == 0.0, the
+         * constant-subframe trigger, happens exactly for an all-zero block: a non-zero constant block comes out as
+         * FIXED order 1), an invalid order gets 34.0 (>= any subframe_bps: "don't even try") */
+        rbps[k] = valid[k] ? (float)((tot[0] > 0) ? log(M_LN2 * (double)tot[0] / len) / M_LN2 : 0.0) : 34.0f;
+        err_out[k] = tot[k];
+    }
+    return order;
+}
+
 /* up: fixed.c FLAC__fixed_compute_residual. data points at sample `order`. */
 static void fixed_residual(const int32_t *data, uint32_t n, uint32_t order, int32_t *res)
 {
@@ -521,11 +561,15 @@ static int process_subframe(enc_t *e, const int32_t *sig, uint32_t sbps, uint32_
         uint64_t ferr[5];
         /* accumulator width: up: process_subframe_ "subframe_bps + ilog2(blocksize-4)+1 < 32" */
         const int narrow = sbps + ilog2_u32(N - MAX_FIXED_ORDER) + 1 < 32;
-        uint32_t forder = fixed_best_predictor(sig + MAX_FIXED_ORDER, N - MAX_FIXED_ORDER, narrow, ferr);
+        float rbps_hi[5] = {0, 0, 0, 0, 0};
+        const int hi = sbps >= 28;                                       /* up: process_subframe_ picks the _limit_residual variant */
+        uint32_t forder = hi ? fixed_best_predictor_limit(sig, N, ferr, rbps_hi)
+                             : fixed_best_predictor(sig + MAX_FIXED_ORDER, N - MAX_FIXED_ORDER, narrow, ferr);
         int constant = 0;
         if (tr) { memcpy(tr->fixed_err, ferr, sizeof ferr); tr->fixed_order = (int32_t)forder; }
-        /* fixed_residual_bits_per_sample[1] == 0.0  <=>  E1 == 0 (the log term cannot hit exactly 0 and still be constant) */
-        if (!disable_constant && ferr[1] == 0) {
+        /* fixed_residual_bits_per_sample[1] == 0.0  <=>  E1 == 0 (the log term cannot hit exactly 0 and still be constant);
+         * the _limit_residual variant yields 0.0 for order 1 exactly when total_error_0 == 0 (all-zero block) */
+        if (!disable_constant && (hi ? rbps_hi[1] == 0.0f : ferr[1] == 0)) {
             constant = 1;
             for (uint32_t i = 1; i < N; i++) if (sig[0] != sig[i]) { constant = 0; break; }
         }
@@ -536,7 +580,8 @@ static int process_subframe(enc_t *e, const int32_t *sig, uint32_t sbps, uint32_
         } else {
             /* ---- fixed (guess order only; "don't even try" test is dead for the guessed order) ---- */
             {
-                float fbits = (float)(ferr[forder] > 0 ? log(M_LN2 * (double)ferr[forder] / (double)(N - MAX_FIXED_ORDER)) / M_LN2 : 0.0);
+                float fbits = hi ? rbps_hi[forder]
+                                 : (float)(ferr[forder] > 0 ? log(M_LN2 * (double)ferr[forder] / (double)(N - MAX_FIXED_ORDER)) / M_LN2 : 0.0);
                 uint32_t fo = forder;
                 if (fo >= N) fo = N - 1;
                 if (!(fbits >= (float)sbps)) {
@@ -817,7 +862,9 @@ long fo_encode_stream(const fo_enc_cfg *cfg, const int32_t *pcm, uint64_t nsampl
     uint8_t *fbuf; size_t fcap;
 
     if (fo_encoder_init_status(cfg, 1, 0, 0) != 0) return -1;
-    if (cfg->bps > 24) return -3; /* >24-bit paths (33-bit side, _limit_residual fixed predictor) are not restated yet */
+    if (cfg->bps > 32) return -3;
+    /* the 33-bit side channel of 32-bit stereo with mid/side analysis is not restated yet */
+    if (cfg->bps == 32 && cfg->channels == 2 && LEVELS[cfg->level > 8 ? 8 : cfg->level].ms) return -3;
     memset(&e, 0, sizeof e);
     resolve_settings(cfg, s);
     {

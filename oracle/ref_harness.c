@@ -42,6 +42,7 @@ extern FLAC__bool FLAC__stream_encoder_set_channels(FLAC__StreamEncoder *, uint3
 extern FLAC__bool FLAC__stream_encoder_set_bits_per_sample(FLAC__StreamEncoder *, uint32_t);
 extern FLAC__bool FLAC__stream_encoder_set_sample_rate(FLAC__StreamEncoder *, uint32_t);
 extern FLAC__bool FLAC__stream_encoder_set_compression_level(FLAC__StreamEncoder *, uint32_t);
+extern FLAC__bool FLAC__stream_encoder_disable_instruction_set(FLAC__StreamEncoder *, uint32_t);   /* libFLAC's test hook: bit mask of SIMD levels to turn off */
 extern FLAC__bool FLAC__stream_encoder_set_blocksize(FLAC__StreamEncoder *, uint32_t);
 extern FLAC__bool FLAC__stream_encoder_set_limit_min_bitrate(FLAC__StreamEncoder *, FLAC__bool);
 extern FLAC__bool FLAC__stream_encoder_set_do_md5(FLAC__StreamEncoder *, FLAC__bool);
@@ -138,6 +139,7 @@ long ref_encode_stream(const ref_enc_cfg *cfg, const int32_t *pcm, uint64_t nsam
     FLAC__stream_encoder_set_bits_per_sample(e, cfg->bps);
     FLAC__stream_encoder_set_sample_rate(e, cfg->sample_rate);
     FLAC__stream_encoder_set_compression_level(e, cfg->level);
+    { const char *ev = getenv("REF_DISABLE_SIMD"); if (ev) FLAC__stream_encoder_disable_instruction_set(e, (uint32_t)strtoul(ev, 0, 0)); }
     FLAC__stream_encoder_set_blocksize(e, cfg->blocksize);
     FLAC__stream_encoder_set_streamable_subset(e, cfg->streamable_subset);
     FLAC__stream_encoder_set_limit_min_bitrate(e, cfg->limit_min_bitrate);

@@ -237,6 +237,35 @@ __device__ __noinline__ void fixed_error_sums(SigView V, FrameGeo G, int flush, 
     e[0] = warp_sum_u64(e0); e[1] = warp_sum_u64(e1); e[2] = warp_sum_u64(e2); e[3] = warp_sum_u64(e3); e[4] = warp_sum_u64(e4);
 }
 
+// up: fixed.c FLAC__fixed_compute_best_predictor_limit_residual (subframe_bps >= 28), as the shipped x86-64 binary runs
+// it (oracle/flac_oracle.c:fixed_best_predictor_limit documents the pinning): sums of |k-th difference| over ALL
+// samples (order k from sample k on) in 64-bit arithmetic, an order is invalid when any of its residuals exceeds
+// INT32_MAX in magnitude.  Returns totals in e[0..4] and a validity bit mask (every lane).  Plain layout only.
+__device__ __noinline__ uint32_t fixed_error_sums_limit(SigView V, FrameGeo G, int lane, unsigned long long* e) {
+    const int blk_lo = lane * G.B0, blk_hi = min(G.N, blk_lo + G.B0);
+    unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
+    uint32_t invalid = 0;
+    if (blk_lo < blk_hi) {
+        const int32_t* rowp = V.base + lane * G.RS - blk_lo;
+        auto at = [&](int i) { return i >= 0 ? (long long)V.base[pidx(G, i)] : 0ll; };
+        long long x1 = at(blk_lo - 1), x2 = at(blk_lo - 2), x3 = at(blk_lo - 3), x4 = at(blk_lo - 4);
+        for (int i = blk_lo; i < blk_hi; i++) {
+            const long long x0 = rowp[i];
+            const unsigned long long a0 = (unsigned long long)llabs(x0);
+            const unsigned long long a1 = i >= 1 ? (unsigned long long)llabs(x0 - x1) : 0ull;
+            const unsigned long long a2 = i >= 2 ? (unsigned long long)llabs(x0 - 2 * x1 + x2) : 0ull;
+            const unsigned long long a3 = i >= 3 ? (unsigned long long)llabs(x0 - 3 * x1 + 3 * x2 - x3) : 0ull;
+            const unsigned long long a4 = i >= 4 ? (unsigned long long)llabs(x0 - 4 * x1 + 6 * x2 - 4 * x3 + x4) : 0ull;
+            e0 += a0; e1 += a1; e2 += a2; e3 += a3; e4 += a4;
+            invalid |= (a0 > 0x7fffffffull ? 1u : 0u) | (a1 > 0x7fffffffull ? 2u : 0u) | (a2 > 0x7fffffffull ? 4u : 0u) |
+                       (a3 > 0x7fffffffull ? 8u : 0u) | (a4 > 0x7fffffffull ? 16u : 0u);
+            x4 = x3; x3 = x2; x2 = x1; x1 = x0;
+        }
+    }
+    e[0] = warp_sum_u64(e0); e[1] = warp_sum_u64(e1); e[2] = warp_sum_u64(e2); e[3] = warp_sum_u64(e3); e[4] = warp_sum_u64(e4);
+    return __reduce_or_sync(0xffffffffu, invalid);
+}
+
 template <bool PACKED>
 __device__ __forceinline__ void fixed_error_sums_rt(const SigView& V, const FrameGeo& G, int sbps, int lane, unsigned long long* e) {
     const int room = 32 - (sbps + 4);
@@ -613,7 +642,9 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
     };
     // up: process_subframe_ constant test + process_subframes_ limit_min_bitrate: when every earlier channel is
     // constant, the last channel (and mid/side after it) may not use a constant subframe
-    auto sig_const = [&](int s) { return N > 4 && S.sig_or[s] == S.sig_and[s]; };
+    // subframe_bps >= 28 (the _limit_residual predictor search): only an all-zero block comes out as CONSTANT there
+    // (oracle/flac_oracle.c:fixed_best_predictor_limit), a non-zero constant block becomes FIXED order 1
+    auto sig_const = [&](int s) { return N > 4 && (sig_sbps(s) >= 28 ? S.sig_or[s] == 0u : S.sig_or[s] == S.sig_and[s]); };
     auto sig_disable_const = [&](int s) {
         if (!(P.limit_min_bitrate && mode != 2 && s >= ch - 1)) return false;
         for (int c2 = 0; c2 < ch - 1; c2++) if (!sig_const(c2)) return false;
@@ -657,19 +688,28 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
                 } else {
                     const SigView V = sig_view(s);
                     unsigned long long e[5];
-                    fixed_error_sums_rt<PACKED>(V, G, sbps, lane, e);
-                    if ((uint32_t)sbps + ilog2_u32((uint32_t)N - 4u) + 1u < 32u) {   // libFLAC's 32-bit accumulators wrap
-#pragma unroll
-                        for (int k = 0; k < 5; k++) e[k] &= 0xffffffffull;
-                    }
                     int forder;
-                    {
+                    bool try_fixed = true;
+                    if (!PACKED && sbps >= 28) {
+                        const uint32_t invalid = fixed_error_sums_limit(V, G, lane, e);
+                        unsigned long long smallest = ~0ull;
+                        forder = 0;
+#pragma unroll
+                        for (int k = 0; k < 5; k++) if (!((invalid >> k) & 1u) && e[k] < smallest) { forder = k; smallest = e[k]; }
+                        try_fixed = ((invalid >> forder) & 1u) == 0u;      // no valid order: estimate 34.0 >= subframe_bps, "don't even try"
+                    } else {
+                        fixed_error_sums_rt<PACKED>(V, G, sbps, lane, e);
+                        if ((uint32_t)sbps + ilog2_u32((uint32_t)N - 4u) + 1u < 32u) {   // libFLAC's 32-bit accumulators wrap
+#pragma unroll
+                            for (int k = 0; k < 5; k++) e[k] &= 0xffffffffull;
+                        }
                         const unsigned long long m34 = min(e[3], e[4]), m234 = min(e[2], m34), m1234 = min(e[1], m234);
                         if (e[0] <= m1234) forder = 0; else if (e[1] <= m234) forder = 1; else if (e[2] <= m34) forder = 2; else if (e[3] <= e[4]) forder = 3; else forder = 4;
                     }
                     if (dg && lane == 0) { for (int k = 0; k < 5; k++) dg->fixed_err[k] = e[k]; dg->fixed_order = forder; dg->is_constant = constant; }
                     // fixed candidate at the guessed order (up: evaluate_fixed_subframe_)
                     int fo = forder; if (fo >= N) fo = N - 1;
+                    if (try_fixed) {
                     int omax = omax_frame;
                     while (omax > 0 && (N >> omax) <= fo) omax--;
                     const int nparts = 1 << omax, psize = N >> omax;
@@ -691,6 +731,7 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
                         if (lane + 32 < (1 << po)) pl.rice[lane + 32] = (uint8_t)k1;
                         const bool r2 = __any_sync(0xffffffffu, (lane < (1 << po) && k0 >= 15u) || (lane + 32 < (1 << po) && k1 >= 15u));
                         if (lane == 0) { pl.type = kFixed; pl.order = (uint8_t)fo; pl.part_order = (uint8_t)po; pl.rice2 = r2; pl.bits_est = est; pl.shift = 0; pl.precision = 0; }
+                    }
                     }
                     __syncwarp();
                 }

@@ -39,6 +39,14 @@ CASES = [
     ("music_s8_st_l5", "music", 4096, 2, 8, 22050, 5, 0),
     ("music_s20_st_l5", "music", 2304 + 17, 2, 20, 96000, 5, 2304),
     ("music_s16_bs100_l5", "music", 350, 2, 16, 12345, 5, 100),
+    # 32-bit (pyFLAC's int32 input): _limit_residual predictor search, no mid/side; lengths 0 or 1 mod 4 (see
+    # oracle/flac_oracle.c:fixed_best_predictor_limit for why other tails are not reproducible from the binary itself)
+    ("music_s32_mono_l5", "music", 4096 * 2 + 768, 1, 32, 44100, 5, 0),
+    ("mixed_s32_mono_l8", "mixed", 4096 + 401, 1, 32, 96000, 8, 0),
+    ("silence_s32_mono_l5", "silence", 4096 + 100, 1, 32, 48000, 5, 0),
+    ("wasted_s32_3ch_l5", "wasted", 4096 + 512, 3, 32, 48000, 5, 0),
+    ("music_s32_st_l3", "music", 4096 * 2, 2, 32, 48000, 3, 0),
+    ("mixed_s32_st_l0", "mixed", 1152 * 3 + 4, 2, 32, 48000, 0, 0),
 ]
 
 

@@ -82,6 +82,26 @@ def test_encode_decode_roundtrip_full_size(eng):
         assert si.status == 0 and si.n_frames == 32 and np.array_equal(o, x)
 
 
+def test_decode_32bit(eng, checkers):
+    """32-bit streams (mono / multi-channel / independent stereo): bit-exact PCM, incl. libFLAC-made streams"""
+    from pyflac_b200 import _native as nat
+    rng = np.random.default_rng(4)
+    n = 4096 + 400
+    m = music_like(n, 2, 48000, 24, seed=8).astype(np.int64)
+    xs = [np.clip(m * 180, -2**31, 2**31 - 1).astype(np.int32), rng.integers(-2**31, 2**31, (n, 2)).astype(np.int32),
+          np.zeros((n, 2), np.int32), (m * 256).astype(np.int32)]
+    blobs, _ = nat.encode_streams(eng, xs, 48000, 32, 3, 0)
+    out, infos = nat.decode_streams(eng, blobs)
+    for x, o, si in zip(xs, out, infos):
+        assert si.status == 0 and si.bits_per_sample == 32 and np.array_equal(o, x)
+    if checkers.ref_available():
+        mono = [x[:, :1].copy() for x in xs]
+        rb = [checkers.ref_encode(x, 48000, 32, 5, 0) for x in mono]
+        out, infos = nat.decode_streams(eng, rb)
+        for x, o, si in zip(mono, out, infos):
+            assert si.status == 0 and np.array_equal(o, x)
+
+
 def test_decode_host_pipelined_matches_plain(eng, checkers, monkeypatch):
     """flacb200_decode_batch_host (chunked H2D / decode / D2H pipeline) == the plain batch path, ragged streams,
     mono + stereo, fewer streams than chunks, a corrupted stream in the middle"""

@@ -70,6 +70,48 @@ def test_encode_loose_mid_side(eng, checkers):
     assert got[0] == checkers.oracle_encode(x24, 96000, 24, 4, 4096)
 
 
+def test_encode_32bit(eng, checkers):
+    """bits_per_sample = 32 (pyFLAC's int32 input, reference encoder.py:109): the _limit_residual fixed-predictor search
+    (orders whose residual leaves int32 are invalid; all-zero blocks are CONSTANT, other constant blocks FIXED order 1),
+    LPC with the int32 residual check, full-scale noise (VERBATIM), INT32_MIN samples, wasted bits that bring the
+    subframe below 28 bits.  Mono, 3 channels, and stereo at the levels without mid/side; lengths 0 or 1 mod 4."""
+    from pyflac_b200 import _native as nat
+    rng = np.random.default_rng(3)
+    n = 4096 * 2 + 300
+    m = music_like(n, 1, 48000, 24, seed=3).astype(np.int64)
+    def c32(a):
+        return np.clip(a, -2**31, 2**31 - 1).astype(np.int32)
+    spikes = m * 100
+    spikes[rng.integers(0, n, 5)] = -2**31
+    sig = {"zeros": np.zeros((n, 1), np.int64), "dc_odd": np.full((n, 1), 123456789), "dc_min": np.full((n, 1), -2**31),
+           "noise_full": rng.integers(-2**31, 2**31, (n, 1)), "music24_shl8": m * 256, "music_x200": m * 200 + rng.integers(-3, 4, (n, 1)),
+           "music_clip": m * 400, "walk": np.cumsum(rng.integers(-2**24, 2**24, (n, 1)), axis=0), "spikes": spikes,
+           "minmax": np.where(np.arange(n)[:, None] % 2 == 0, -2**31, 2**31 - 1), "lowbits": m // 64}
+    names = list(sig)
+    for level in (0, 2, 5, 8):
+        for bs in (0, 1000):
+            xs = [c32(sig[k]) for k in names]
+            got, out = nat.encode_streams(eng, xs, 48000, 32, level, bs)
+            for k, x, g in zip(names, xs, got):
+                assert g == checkers.oracle_encode(x, 48000, 32, level, bs), (k, level, bs)
+            assert out["log_guard_hits"] == 0
+    multi = [c32(np.concatenate([sig[k], np.roll(sig[k], 17, axis=0) // 2, np.roll(sig[k], 40, axis=0) // 3], axis=1)) for k in ("music_x200", "walk", "zeros")]
+    got, _ = nat.encode_streams(eng, multi, 44100, 32, 5, 0)
+    for x, g in zip(multi, got):
+        assert g == checkers.oracle_encode(x, 44100, 32, 5, 0)
+    stereo = [c32(np.concatenate([sig[k], np.roll(sig[k], 9, axis=0) // 2], axis=1)) for k in ("music_x200", "noise_full", "zeros", "dc_odd")]
+    for level in (0, 3):
+        got, _ = nat.encode_streams(eng, stereo, 48000, 32, level, 0)
+        for x, g in zip(stereo, got):
+            assert g == checkers.oracle_encode(x, 48000, 32, level, 0), level
+    if checkers.ref_available():
+        g, _ = nat.encode_streams(eng, [c32(sig["music_x200"])], 48000, 32, 5, 0)
+        assert g[0] == checkers.ref_encode(c32(sig["music_x200"]), 48000, 32, 5, 0)
+    # the 33-bit side channel is not built: 32-bit stereo at a mid/side level fails loudly instead of differing
+    with pytest.raises(Exception):
+        nat.encode_streams(eng, stereo, 48000, 32, 5, 0)
+
+
 def test_encode_limit_min_bitrate(eng, checkers):
     """FLAC__stream_encoder_set_limit_min_bitrate: a frame may not consist of constant subframes only
     (up: process_subframes_; ref: stream_encoder.h:1105-1115)"""

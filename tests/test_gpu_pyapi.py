@@ -93,22 +93,27 @@ def test_encoder_property_roundtrip():
 
 def test_file_encoder_and_decoder_roundtrip(checkers):
     import pyflac_b200 as pf
-    for bits, ch in [(16, 1), (16, 2), (32, 1)]:
-        x = music_like(4096 * 2 + 123, ch, 44100, 16, seed=bits + ch)
+    for bits, ch in [(16, 1), (16, 2), (32, 1), (32, 2)]:
+        x = music_like(4096 * 2 + 124, ch, 44100, 16, seed=bits + ch)
         xs = x if bits == 16 else (x.astype(np.int32) << 8)       # 32-bit container, 24 significant bits: wasted-bits path
         with tempfile.TemporaryDirectory() as d:
             wavp, flacp, outp = os.path.join(d, "a.wav"), os.path.join(d, "a.flac"), os.path.join(d, "b.wav")
             write_wav(wavp, xs, 44100, bits)
-            if bits == 32:
-                # 32 bits per sample is outside this build's range: must fail loudly, not silently differ
+            if bits == 32 and ch == 2:
+                # 32-bit stereo at a mid/side level needs the 33-bit side channel: must fail loudly, not silently differ
                 with pytest.raises(pf.EncoderInitException):
                     pf.FileEncoder(wavp, flacp).process()
+                data = pf.FileEncoder(wavp, flacp, compression_level=3).process()
+                assert data == open(flacp, "rb").read() == checkers.oracle_encode(xs, 44100, 32, 3, 0)
                 continue
             data = pf.FileEncoder(wavp, flacp, compression_level=5).process()
             assert data == open(flacp, "rb").read() == checkers.oracle_encode(xs, 44100, bits, 5, 0)
             pcm, sr = pf.FileDecoder(flacp, outp).process()
             assert sr == 44100 and pcm.dtype == np.float64 and pcm.shape == (len(x), ch)
-            assert np.array_equal(np.rint(pcm * 32768.0).astype(np.int16), x)
+            if bits == 16:
+                assert np.array_equal(np.rint(pcm * 32768.0).astype(np.int16), x)
+            else:       # the reference writes PCM_16 whatever the stream's depth (decoder.py:300-313): the high 16 bits survive
+                assert np.max(np.abs(pcm - xs.astype(np.float64) / 2147483648.0)) <= 2.0 ** -15
     with pytest.raises(pf.DecoderInitException):
         pf.FileDecoder("/nonexistent/file.flac")
 
