@@ -356,7 +356,7 @@ static uint32_t max_residual_bps(uint32_t sbps, const int32_t *q, uint32_t order
 /* up: lpc.c FLAC__lpc_compute_residual_from_qlp_coefficients[_wide|_limit_residual] (SV E9):
  * r[i] = x[i] - ((sum_j q[j]*x[i-1-j]) >> shift); 64-bit accumulate is exact for every variant that
  * libFLAC would pick; `limit` reproduces the _limit_residual rejection. data points at sample `order`. */
-static int lpc_residual(const int32_t *data, uint32_t n, const int32_t *q, uint32_t order, int shift, int limit, int32_t *res)
+static int lpc_residual(const int64_t *data, uint32_t n, const int32_t *q, uint32_t order, int shift, int limit, int32_t *res)
 {
     for (uint32_t i = 0; i < n; i++) {
         int64_t sum = 0;
@@ -372,7 +372,7 @@ static int lpc_residual(const int32_t *data, uint32_t n, const int32_t *q, uint3
 
 /* up: fixed.c FLAC__fixed_compute_best_predictor[_wide] (SV A.4).  data points at sample 4, len = N-4.
  * `narrow`: libFLAC used 32-bit accumulators (sums wrap mod 2^32) -- reproduced for exactness. */
-static uint32_t fixed_best_predictor(const int32_t *data, uint32_t len, int narrow, uint64_t err_out[5])
+static uint32_t fixed_best_predictor(const int64_t *data, uint32_t len, int narrow, uint64_t err_out[5])
 {
     uint64_t e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
     for (uint32_t i = 0; i < len; i++) {
@@ -404,7 +404,7 @@ static uint32_t fixed_best_predictor(const int32_t *data, uint32_t len, int narr
  * (|r| > INT32_MAX) is invalid, the winner is the first strictly smallest valid total, and -- 1.4.3's
  * CHECK_ORDER_IS_VALID macro -- the bits-per-sample estimate stored for an order that takes the lead is computed from
  * total_error_0.  sig points at sample 0. */
-static uint32_t fixed_best_predictor_limit(const int32_t *sig, uint32_t N, uint64_t err_out[5], float rbps[5])
+static uint32_t fixed_best_predictor_limit(const int64_t *sig, uint32_t N, int c_source, uint64_t err_out[5], float rbps[5])
 {
     uint64_t tot[5] = {0, 0, 0, 0, 0}, smallest = UINT64_MAX;
     int valid[5] = {1, 1, 1, 1, 1};
@@ -425,17 +425,20 @@ static uint32_t fixed_best_predictor_limit(const int32_t *sig, uint32_t N, uint6
         /* pinned against the binary: every VALID order gets the estimate of total_error_0 (so [1] == 0.0, the
          * constant-subframe trigger, happens exactly for an all-zero block: a non-zero constant block comes out as
          * FIXED order 1), an invalid order gets 34.0 (>= any subframe_bps: "don't even try") */
-        rbps[k] = valid[k] ? (float)((tot[0] > 0) ? log(M_LN2 * (double)tot[0] / len) / M_LN2 : 0.0) : 34.0f;
+        if (c_source)   /* C source (the 33-bit routine has no SIMD build): only an order that takes the lead gets the estimate */
+            rbps[k] = (smallest == tot[k] && order == (uint32_t)k && valid[k]) ? (float)((tot[0] > 0) ? log(M_LN2 * (double)tot[0] / len) / M_LN2 : 0.0) : 34.0f;
+        else
+            rbps[k] = valid[k] ? (float)((tot[0] > 0) ? log(M_LN2 * (double)tot[0] / len) / M_LN2 : 0.0) : 34.0f;
         err_out[k] = tot[k];
     }
     return order;
 }
 
 /* up: fixed.c FLAC__fixed_compute_residual. data points at sample `order`. */
-static void fixed_residual(const int32_t *data, uint32_t n, uint32_t order, int32_t *res)
+static void fixed_residual(const int64_t *data, uint32_t n, uint32_t order, int32_t *res)
 {
     for (uint32_t i = 0; i < n; i++) {
-        const int32_t *d = data + i;
+        const int64_t *d = data + i;
         int64_t r;
         switch (order) {
             case 0: r = d[0]; break;
@@ -543,7 +546,7 @@ static uint32_t add_sat(uint32_t est, uint32_t bits) { return bits < UINT32_MAX 
 
 /* up: stream_encoder.c process_subframe_ + evaluate_{verbatim,constant,fixed,lpc}_subframe_ + apply_apodization_
  * (SV A.4-A.9).  sig is modified only by the caller (wasted bits).  Returns the best residual workspace index. */
-static int process_subframe(enc_t *e, const int32_t *sig, uint32_t sbps, uint32_t wasted, int disable_constant,
+static int process_subframe(enc_t *e, const int64_t *sig, uint32_t sbps, uint32_t wasted, int disable_constant,
                             fo_subframe *best, int32_t **best_res, fo_signal_trace *tr)
 {
     const uint32_t N = e->N;
@@ -563,7 +566,7 @@ static int process_subframe(enc_t *e, const int32_t *sig, uint32_t sbps, uint32_
         const int narrow = sbps + ilog2_u32(N - MAX_FIXED_ORDER) + 1 < 32;
         float rbps_hi[5] = {0, 0, 0, 0, 0};
         const int hi = sbps >= 28;                                       /* up: process_subframe_ picks the _limit_residual variant */
-        uint32_t forder = hi ? fixed_best_predictor_limit(sig, N, ferr, rbps_hi)
+        uint32_t forder = hi ? fixed_best_predictor_limit(sig, N, 0, ferr, rbps_hi)   /* the binary treats the 33-bit side channel the same way (pinned) */
                              : fixed_best_predictor(sig + MAX_FIXED_ORDER, N - MAX_FIXED_ORDER, narrow, ferr);
         int constant = 0;
         if (tr) { memcpy(tr->fixed_err, ferr, sizeof ferr); tr->fixed_order = (int32_t)forder; }
@@ -681,9 +684,9 @@ static int process_subframe(enc_t *e, const int32_t *sig, uint32_t sbps, uint32_
 }
 
 /* up: stream_encoder.c get_wasted_bits_ (SV A.3) */
-static uint32_t wasted_bits(int32_t *sig, uint32_t n)
+static uint32_t wasted_bits(int64_t *sig, uint32_t n)
 {
-    uint32_t i, shift; int32_t x = 0;
+    uint32_t i, shift; int64_t x = 0;
     for (i = 0; i < n && !(x & 1); i++) x |= sig[i];
     if (x == 0) shift = 0;
     else for (shift = 0; !(x & 1); shift++) x >>= 1;
@@ -734,7 +737,7 @@ static void write_frame_header(bw_t *w, const settings_t *s, uint32_t N, uint32_
 }
 
 /* up: stream_encoder_framing.c FLAC__subframe_add_{constant,verbatim,fixed,lpc} + add_residual_partitioned_rice_ */
-static void write_subframe(bw_t *w, const fo_subframe *sf, const int32_t *sig, const int32_t *res, uint32_t N)
+static void write_subframe(bw_t *w, const fo_subframe *sf, const int64_t *sig, const int32_t *res, uint32_t N)
 {
     const uint32_t wflag = sf->wasted ? 1 : 0, sbps = (uint32_t)sf->sbps, order = (uint32_t)sf->order;
     switch (sf->type) {
@@ -767,7 +770,7 @@ static void write_subframe(bw_t *w, const fo_subframe *sf, const int32_t *sig, c
 }
 
 /* up: stream_encoder.c process_subframes_ (SV A.3, A.9, E2) + process_frame_ tail (zero pad, CRC-16) */
-static int encode_frame(enc_t *e, int32_t *sigs[], uint32_t frame_number, bw_t *w, fo_frame_trace *tr)
+static int encode_frame(enc_t *e, int64_t *sigs[], uint32_t frame_number, bw_t *w, fo_frame_trace *tr)
 {
     const settings_t *s = &e->s;
     const uint32_t N = e->N, ch = s->channels;
@@ -776,7 +779,7 @@ static int encode_frame(enc_t *e, int32_t *sigs[], uint32_t frame_number, bw_t *
     int32_t *resbuf[FO_MAX_CHANNELS + 2];
     uint32_t sbps[FO_MAX_CHANNELS + 2], wst[FO_MAX_CHANNELS + 2];
     int do_indep, do_ms, ca = 0, all_const = 1, disable_const = 0;
-    int32_t *mid = sigs[ch], *side = sigs[ch + 1];
+    int64_t *mid = sigs[ch], *side = sigs[ch + 1];
 
     if (s->do_ms) {
         if (s->loose) {
@@ -787,7 +790,11 @@ static int encode_frame(enc_t *e, int32_t *sigs[], uint32_t frame_number, bw_t *
 
     if (do_ms) for (uint32_t i = 0; i < N; i++) { side[i] = sigs[0][i] - sigs[1][i]; mid[i] = (sigs[0][i] + sigs[1][i]) >> 1; }
     if (do_indep) for (uint32_t c = 0; c < ch; c++) { uint32_t wb = wasted_bits(sigs[c], N); if (wb > s->bps) wb = s->bps; wst[c] = wb; sbps[c] = s->bps - wb; }
-    if (do_ms) for (uint32_t c = 0; c < 2; c++) { uint32_t wb = wasted_bits(sigs[ch + c], N); if (wb > s->bps) wb = s->bps; wst[ch + c] = wb; sbps[ch + c] = s->bps - wb + (c ? 1 : 0); }
+    if (do_ms) for (uint32_t c = 0; c < 2; c++) { uint32_t wb = wasted_bits(sigs[ch + c], N);
+        /* up: get_wasted_bits_wide_ (33-bit side of 32-bit input): an all-zero side reports ONE wasted bit, which moves it
+         * onto the 32-bit paths (pinned: the binary writes CONSTANT, wasted = 1, 32-bit zero) */
+        if (c == 1 && s->bps == 32 && wb == 0) { int allz = 1; for (uint32_t i = 0; i < N; i++) if (sigs[ch + 1][i]) { allz = 0; break; } if (allz) wb = 1; }
+        if (wb > s->bps) wb = s->bps; wst[ch + c] = wb; sbps[ch + c] = s->bps - wb + (c ? 1 : 0); }
 
     /* every signal gets its own residual buffer so the winner survives the next call */
     for (uint32_t c = 0; c < ch + 2; c++) resbuf[c] = 0;
@@ -858,18 +865,16 @@ long fo_encode_stream(const fo_enc_cfg *cfg, const int32_t *pcm, uint64_t nsampl
     md5_t md5;
     size_t pos = 0;
     uint32_t nframes = 0, min_fs = 0, max_fs = 0, frame_number = 0, cur_window_N = 0;
-    int32_t *sigs[FO_MAX_CHANNELS + 2];
+    int64_t *sigs[FO_MAX_CHANNELS + 2];
     uint8_t *fbuf; size_t fcap;
 
     if (fo_encoder_init_status(cfg, 1, 0, 0) != 0) return -1;
     if (cfg->bps > 32) return -3;
-    /* the 33-bit side channel of 32-bit stereo with mid/side analysis is not restated yet */
-    if (cfg->bps == 32 && cfg->channels == 2 && LEVELS[cfg->level > 8 ? 8 : cfg->level].ms) return -3;
     memset(&e, 0, sizeof e);
     resolve_settings(cfg, s);
     {
         const uint32_t B = s->blocksize;
-        for (uint32_t c = 0; c < s->channels + 2; c++) sigs[c] = (int32_t *)malloc(sizeof(int32_t) * (B + 8));
+        for (uint32_t c = 0; c < s->channels + 2; c++) sigs[c] = (int64_t *)malloc(sizeof(int64_t) * (B + 8));
         e.window = (float *)malloc(sizeof(float) * B); e.windowed = (float *)malloc(sizeof(float) * (B + 8));
         e.res[0] = (int32_t *)malloc(sizeof(int32_t) * (B + 8)); e.res[1] = (int32_t *)malloc(sizeof(int32_t) * (B + 8));
         fcap = (size_t)B * (s->channels) * 5 + 1024; fbuf = (uint8_t *)malloc(fcap);
