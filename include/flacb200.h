@@ -45,7 +45,7 @@ enum {
 typedef struct {
     uint32_t sample_rate;
     uint32_t channels;
-    uint32_t bits_per_sample;     /* 4..32; 32-bit stereo only at levels without mid/side (0, 3) in this build */
+    uint32_t bits_per_sample;     /* 4..32 */
     uint32_t compression_level;   /* 0..8 */
     uint32_t blocksize;           /* 0 = libFLAC default (1152 for levels 0-2, else 4096) */
     uint32_t container_bytes;     /* PCM element size in memory: 2 (int16, bps<=16) or 4 (int32) */

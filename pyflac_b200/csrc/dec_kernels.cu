@@ -207,7 +207,8 @@ dec_scan_u32_kernel(const uint32_t* __restrict__ in, int n, uint32_t* __restrict
 
 __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, uint32_t* __restrict__ sizes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) sizes[i] = cands[i].blocksize * cands[i].channels;
+    // 32-bit stereo: a side subframe may hold 33-bit samples; they are kept as (sample >> 1) plus a bitmap of the dropped bits
+    if (i < n) sizes[i] = cands[i].blocksize * cands[i].channels + ((cands[i].bps == 32 && cands[i].channels == 2) ? (cands[i].blocksize + 31) / 32 : 0u);
 }
 
 // ------------------------------------------------------------------ frame decode: one thread per candidate ----
@@ -309,18 +310,76 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
     int status = kDecOk;
     for (uint32_t chn = 0; chn < c.channels && status == kDecOk; chn++) {
         int32_t* o = out + (size_t)chn * N;
-        uint32_t bps = c.bps + (((c.ca == 1 && chn == 1) || (c.ca == 2 && chn == 0) || (c.ca == 3 && chn == 1)) ? 1u : 0u);
+        const bool is_side = (c.ca == 1 && chn == 1) || (c.ca == 2 && chn == 0) || (c.ca == 3 && chn == 1);
+        uint32_t bps = c.bps + (is_side ? 1u : 0u);
+        // the side channel of a 32-bit stream spans 33 bits even when its subframe drops wasted bits: its plane always holds
+        // sample >> 1 and the bitmap behind the planes the low bits (zero when there are wasted bits)
+        const bool side33 = is_side && c.bps == 32;
         const uint32_t hdr = br.get(8);
         if (hdr & 0x80) { status = kDecBadFrame; break; }
         uint32_t wasted = 0;
         if (hdr & 1) { wasted = br.unary() + 1; if (wasted >= bps) { status = kDecBadFrame; break; } bps -= wasted; }
+        const uint32_t wsh = (side33 && wasted) ? wasted - 1u : wasted;
+        if (side33 && bps <= 32) { uint32_t* bm = reinterpret_cast<uint32_t*>(out + (size_t)c.channels * N); for (uint32_t w2 = 0; w2 < (N + 31u) / 32u; w2++) bm[w2] = 0u; }
         const uint32_t type = (hdr >> 1) & 0x3f;
-        if (bps > 32) { status = kDecUnsupported; break; }                     // 33-bit side channel of 32-bit streams: not built yet
+        if (bps > 33) { status = kDecBadFrame; break; }
+        if (bps == 33) {
+            // ---- 33-bit side channel of a 32-bit stereo stream (rare, generic code): 64-bit history in local memory; the plane
+            // receives sample >> 1 and a bitmap behind the planes the dropped low bits (dec_post_kernel puts them back) ----
+            uint32_t* bitmap = reinterpret_cast<uint32_t*>(out + (size_t)c.channels * N);
+            uint32_t word = 0;
+            auto emit = [&](uint32_t i, long long v) {
+                o[i] = (int32_t)(v >> 1);
+                word |= (uint32_t)(v & 1ll) << (i & 31u);
+                if ((i & 31u) == 31u || i + 1 == N) { bitmap[i >> 5] = word; word = 0; }
+            };
+            auto get33 = [&]() -> long long { const uint32_t hi = br.get(1); const uint32_t lo = br.get(32); return (long long)lo - (hi ? 0x100000000ll : 0ll); };
+            if (type == 0) { const long long v = get33(); for (uint32_t i = 0; i < N; i++) emit(i, v); }
+            else if (type == 1) { for (uint32_t i = 0; i < N; i++) emit(i, get33()); }
+            else {
+                uint32_t order; int shift = 0; bool lpc;
+                if (type >= 8 && type <= 12) { order = type - 8; lpc = false; }
+                else if (type >= 32) { order = type - 31; lpc = true; }
+                else { status = kDecBadFrame; break; }
+                if (order > N) { status = kDecBadFrame; break; }
+                long long hh[32]; int qq[32];
+                for (uint32_t i = 0; i < order; i++) { const long long v = get33(); hh[i & 31u] = v; emit(i, v); }
+                if (lpc) {
+                    const uint32_t prec = br.get(4) + 1; if (prec == 16) { status = kDecBadFrame; break; }
+                    shift = br.get_signed(5); if (shift < 0) { status = kDecBadFrame; break; }
+                    for (uint32_t j = 0; j < order; j++) qq[j] = br.get_signed(prec);
+                } else {
+                    const int cf[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+                    for (uint32_t j = 0; j < order; j++) qq[j] = cf[order][j];
+                }
+                const uint32_t method = br.get(2);
+                if (method > 1) { status = kDecBadFrame; break; }
+                const uint32_t po = br.get(4), plen = method ? 5u : 4u, pesc = method ? 31u : 15u;
+                if ((N >> po) < order || (po > 0 && (N & ((1u << po) - 1)))) { status = kDecBadFrame; break; }
+                uint32_t left = 0, k = 0, raw = 0;
+                bool first = true;
+                for (uint32_t i = order; i < N; i++) {
+                    if (left == 0) { left = (N >> po) - (first ? order : 0u); first = false; k = br.get(plen); raw = (k == pesc) ? br.get(5) : 0u; }
+                    left--;
+                    int32_t r;
+                    if (k == pesc) r = br.get_signed(raw);
+                    else { const uint32_t qv = br.unary(); const uint32_t u = (qv << k) | br.get(k); r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
+                    long long sacc = 0;
+                    for (uint32_t j = 0; j < order; j++) sacc += (long long)qq[j] * hh[(i - 1 - j) & 31u];
+                    const long long v = (long long)r + (sacc >> shift);
+                    hh[i & 31u] = v;
+                    emit(i, v);
+                    if (br.overrun()) break;
+                }
+            }
+            if (br.overrun()) status = kDecIncomplete;
+            continue;
+        }
         if (type == 0) {                                                        // CONSTANT
-            const int32_t v = br.get_signed(bps) << wasted;
+            const int32_t v = br.get_signed(bps) << wsh;
             for (uint32_t i = 0; i < N; i++) o[i] = v;
         } else if (type == 1) {                                                 // VERBATIM
-            for (uint32_t i = 0; i < N; i++) o[i] = br.get_signed(bps) << wasted;
+            for (uint32_t i = 0; i < N; i++) o[i] = br.get_signed(bps) << wsh;
         } else {
             uint32_t order; int shift = 0; bool lpc;
             if (type >= 8 && type <= 12) { order = type - 8; lpc = false; }
@@ -334,7 +393,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
             const bool fast = order <= (uint32_t)kDecFastOrder;
             for (uint32_t i = 0; i < order; i++) {
                 const int32_t v = br.get_signed(bps);
-                o[i] = v << wasted;
+                o[i] = v << wsh;
                 if (fast) {
 #pragma unroll
                     for (int j = kDecFastOrder - 1; j > 0; j--) h[j] = h[j - 1];
@@ -410,7 +469,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
                     }
                     sh.hist[i & 31][t] = v;
                 }
-                o[i] = v << wasted;
+                o[i] = v << wsh;
                 if (br.overrun()) break;
             }
         }
@@ -500,10 +559,20 @@ dec_post_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ s
     if (c.ca == 0) {
         for (uint32_t e = tid; e < N * ch; e += 256) { const uint32_t i = e / ch, k = e - i * ch; out[e] = (OutT)in[(size_t)k * N + i]; }
     } else {
+        const bool side33 = c.bps == 32;             // side plane = side >> 1, low bits in the bitmap behind the planes (dec_frame_kernel)
+        const uint32_t* bitmap = reinterpret_cast<const uint32_t*>(in + (size_t)2 * N);
         for (uint32_t i = tid; i < N; i += 256) {
             const int32_t a = in[i], b = in[N + i];
             int32_t l, r;
-            if (c.ca == 1) { l = a; r = a - b; }
+            if (side33) {
+                // modulo-2^32 arithmetic is exact because the results fit 32 bits.  side = 2*sh + lsb:
+                //   left/side: R = L - side;  side/right: L = side + R;  mid/side: L = mid + sh + lsb, R = mid - sh
+                const uint32_t lsb = (bitmap[i >> 5] >> (i & 31u)) & 1u;
+                if (c.ca == 1) { l = a; r = (int32_t)((uint32_t)a - (((uint32_t)b << 1) | lsb)); }
+                else if (c.ca == 2) { r = b; l = (int32_t)((((uint32_t)a << 1) | lsb) + (uint32_t)b); }
+                else { l = (int32_t)((uint32_t)a + (uint32_t)b + lsb); r = (int32_t)((uint32_t)a - (uint32_t)b); }
+            }
+            else if (c.ca == 1) { l = a; r = a - b; }
             else if (c.ca == 2) { l = a + b; r = b; }
             else { const int32_t m2 = (int32_t)(((uint32_t)a << 1) | ((uint32_t)b & 1u)); l = (m2 + b) >> 1; r = (m2 - b) >> 1; }
             out[2 * i] = (OutT)l; out[2 * i + 1] = (OutT)r;

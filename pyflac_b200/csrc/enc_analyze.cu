@@ -25,6 +25,7 @@
 //
 // Exactness: integer work is exact; floating point follows fb_math.cuh (unfused, RN).  No tensor cores:
 // this is integer / bit-serial work, not a dense contraction.
+#include <type_traits>
 #include "fb_common.cuh"
 #include "fb_math.cuh"
 
@@ -47,7 +48,14 @@ enum SigKind : int { kLo16 = 0, kHi16 = 1, kMid16 = 2, kSide16 = 3, kPlain = 4 }
 struct SigView {
     const int32_t* base;     // packed: the frame's words; plain: the signal's own row block (wasted bits already removed)
     int ca, cb, sh;
+    // 33-bit side channel of 32-bit stereo (no wasted bits): derived from the left (base) and right (base2) rows,
+    // value = (left << shl) - (right << shr) in 64-bit arithmetic (the rows hold the channels without THEIR wasted bits)
+    const int32_t* base2;
+    int shl, shr, s33;
 };
+__device__ __forceinline__ long long sig_word64(const SigView& V, int p) {
+    return V.s33 ? ((long long)V.base[p] << V.shl) - ((long long)V.base2[p] << V.shr) : (long long)V.base[p];
+}
 
 struct FrameGeo {
     int N, B0, RS, pad;      // samples, samples per row, row stride in words, RS - B0
@@ -96,9 +104,10 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 // thirteen keep the instruction working set of an SM -- whose warps run different orders at the same time -- inside
 // the instruction cache (the per-order version spent half its stall samples waiting for instruction fetch).
 // psum must be zeroed by the caller; partition totals arrive through shared atomics (<= 3 per lane).
-template <int C, bool WIDE, bool PACKED>
+template <int C, bool WIDE, bool PACKED, bool S33 = false>
 __device__ __noinline__ bool residual_partition_sums(SigView V, FrameGeo G, const int32_t* __restrict__ qs, int order, int shift,
                                                      int psize, bool check_limit, unsigned long long* psum, int lane) {
+    using HistT = typename std::conditional<S33, long long, int32_t>::type;      // S33: 33-bit samples (always WIDE, plain layout)
     int32_t q[C];
 #pragma unroll
     for (int j = 0; j < C; j++) q[j] = (j < order) ? qs[j] : 0;
@@ -109,15 +118,20 @@ __device__ __noinline__ bool residual_partition_sums(SigView V, FrameGeo G, cons
     while (lo < blk_hi) {
         const int part = lo / psize;
         const int hi = min(blk_hi, (part + 1) * psize);
-        int32_t h[C];
+        HistT h[C];
 #pragma unroll
-        for (int k = 0; k < C; k++) h[k] = sig_word<PACKED>(V.base[pidx(G, max(lo - C + k, 0))], V);    // taps before sample 0 carry zero coefficients
+        for (int k = 0; k < C; k++) {       // taps before sample 0 carry zero coefficients
+            if (S33) h[k] = (HistT)sig_word64(V, pidx(G, max(lo - C + k, 0)));
+            else h[k] = (HistT)sig_word<PACKED>(V.base[pidx(G, max(lo - C + k, 0))], V);
+        }
         unsigned long long acc = 0;
         for (int g = lo; g < hi; g += C) {
 #pragma unroll
             for (int u = 0; u < C; u++) {
                 if (g + u < hi) {
-                    const int xv = sig_word<PACKED>(rowp[g + u], V);
+                    HistT xv;
+                    if (S33) xv = (HistT)sig_word64(V, lane * G.RS - blk_lo + g + u);
+                    else xv = (HistT)sig_word<PACKED>(rowp[g + u], V);
                     long long r;
                     if (WIDE) {
                         long long s = 0;
@@ -128,8 +142,8 @@ __device__ __noinline__ bool residual_partition_sums(SigView V, FrameGeo G, cons
                     } else {
                         int s = 0;
 #pragma unroll
-                        for (int j = 0; j < C; j++) s += q[j] * h[(u - 1 - j + 2 * C) % C];
-                        r = (long long)(xv - (s >> shift));
+                        for (int j = 0; j < C; j++) s += q[j] * (int)h[(u - 1 - j + 2 * C) % C];
+                        r = (long long)((int)xv - (s >> shift));
                     }
                     acc += (unsigned long long)(r < 0 ? -r : r);
                     h[u] = xv;
@@ -156,6 +170,11 @@ __device__ __forceinline__ bool residual_dispatch(bool wide, int order, const Si
                                                   int shift, int psize, int nparts, bool limit, unsigned long long* psum, int lane) {
     for (int p = lane; p < nparts; p += 32) psum[p] = 0ull;
     __syncwarp();
+    if (!PACKED && V.s33) {         // 33-bit side channel: 64-bit samples, always the wide accumulator
+        if (order <= 4) return residual_partition_sums<4, true, false, true>(V, G, q, order, shift, psize, limit, psum, lane);
+        if (order <= 8) return residual_partition_sums<8, true, false, true>(V, G, q, order, shift, psize, limit, psum, lane);
+        return residual_partition_sums<12, true, false, true>(V, G, q, order, shift, psize, limit, psum, lane);
+    }
     return wide ? residual_order<true, PACKED>(order, V, G, q, shift, psize, limit, psum, lane)
                 : residual_order<false, PACKED>(order, V, G, q, shift, psize, limit, psum, lane);
 }
@@ -246,11 +265,10 @@ __device__ __noinline__ uint32_t fixed_error_sums_limit(SigView V, FrameGeo G, i
     unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
     uint32_t invalid = 0;
     if (blk_lo < blk_hi) {
-        const int32_t* rowp = V.base + lane * G.RS - blk_lo;
-        auto at = [&](int i) { return i >= 0 ? (long long)V.base[pidx(G, i)] : 0ll; };
+        auto at = [&](int i) { return i >= 0 ? sig_word64(V, pidx(G, i)) : 0ll; };
         long long x1 = at(blk_lo - 1), x2 = at(blk_lo - 2), x3 = at(blk_lo - 3), x4 = at(blk_lo - 4);
         for (int i = blk_lo; i < blk_hi; i++) {
-            const long long x0 = rowp[i];
+            const long long x0 = sig_word64(V, lane * G.RS - blk_lo + i);
             const unsigned long long a0 = (unsigned long long)llabs(x0);
             const unsigned long long a1 = i >= 1 ? (unsigned long long)llabs(x0 - x1) : 0ull;
             const unsigned long long a2 = i >= 2 ? (unsigned long long)llabs(x0 - 2 * x1 + x2) : 0ull;
@@ -283,7 +301,12 @@ __device__ __forceinline__ const FrameBits* frame_bits(const unsigned char* work
 __device__ __forceinline__ double* frame_ac(unsigned char* work, size_t stride, int f) {
     return reinterpret_cast<double*>(work + (size_t)f * stride + sizeof(FrameBits));
 }
-__device__ __forceinline__ int wasted_from_or(uint32_t o, int bps) { const int w = o ? (__ffs((int)o) - 1) : 0; return w > bps ? bps : w; }
+// side33: the signal is the 33-bit side channel of 32-bit stereo (up: get_wasted_bits_wide_): an all-zero side reports ONE
+// wasted bit, which moves it onto the 32-bit paths (pinned against the binary, oracle/flac_oracle.c:encode_frame)
+__device__ __forceinline__ int wasted_from_or(uint32_t o, int bps, bool side33 = false) {
+    const int w = o ? (__ffs((int)o) - 1) : (side33 ? 1 : 0);
+    return w > bps ? bps : w;
+}
 
 // up: process_subframes_ + get_wasted_bits_: OR of all samples gives the wasted bits, OR == AND means
 // every sample is equal (constant subframe).  One warp per frame.
@@ -322,9 +345,9 @@ frame_bits_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ fr
             for (int i = lane; i < N; i += 32) {
                 int v;
                 if (s < ch) v = (int)__ldg(base + (uint64_t)i * ch + s);
-                else {
-                    const int l = (int)__ldg(base + (uint64_t)i * ch), r = (int)__ldg(base + (uint64_t)i * ch + 1);
-                    v = (s == ch) ? ((l + r) >> 1) : (l - r);
+                else {      // 64-bit: the sum / difference of two 32-bit samples needs 33 bits (only the low 32 matter for OR / AND)
+                    const long long l = (long long)__ldg(base + (uint64_t)i * ch), r = (long long)__ldg(base + (uint64_t)i * ch + 1);
+                    v = (s == ch) ? (int)((l + r) >> 1) : (int)(l - r);
                 }
                 o |= (uint32_t)v; a &= (uint32_t)v;
             }
@@ -365,7 +388,7 @@ __device__ __forceinline__ float ac_fetch(const AcJob& J, const float* __restric
     if (!in) return 0.0f;
     const float wv = __ldg(windows + J.woff + (i < J.part ? i : J.N - 2 * J.part + i));
     const int ca = (int)(signed char)(J.sel >> 16), cb = (int)(signed char)(J.sel >> 24);
-    int v;
+    int v = 0;
     if (PACKED) {
         const PcmT* b = reinterpret_cast<const PcmT*>(J.base);
         int wd;
@@ -374,11 +397,13 @@ __device__ __forceinline__ float ac_fetch(const AcJob& J, const float* __restric
         const int lo = (int)(short)wd, hi = wd >> 16;
         v = (lo * ca + hi * cb) >> J.sh;
     } else {
+        // up: FLAC__lpc_window_data[_wide]: 64-bit so that mid / side of 32-bit input (33 bits) convert exactly like libFLAC's
+        // (float)int64; values that fit int32 give the same float as (float)int32
         const PcmT* b = reinterpret_cast<const PcmT*>(J.base) + (size_t)i * ch;
-        const int x0 = (int)__ldg(b + (J.sel & 0xff));
-        v = x0 * ca;
-        if (cb) v += (int)__ldg(b + ((J.sel >> 8) & 0xff)) * cb;
-        v >>= J.sh;
+        long long v64 = (long long)__ldg(b + (J.sel & 0xff)) * ca;
+        if (cb) v64 += (long long)__ldg(b + ((J.sel >> 8) & 0xff)) * cb;
+        v64 >>= J.sh;
+        return FB_FMUL(__ll2float_rn(v64), wv);
     }
     return FB_FMUL(__int2float_rn(v), wv);
 }
@@ -452,7 +477,7 @@ autoc_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames,
             const int N = (int)fd.blocksize;
             if (N > 4 && !(b > 1 && N / b <= 32)) {
                 const FrameBits* fb = frame_bits(work, work_stride, f);
-                const int wst = wasted_from_or(fb->or_[s], (int)P.bps);
+                const int wst = wasted_from_or(fb->or_[s], (int)P.bps, P.bps == 32 && P.do_mid_side && s == ch + 1);
                 const int off = (k * N) / b;
                 J.base = pcm + fd.pcm_off + (size_t)off * ch;
                 int c0, c1, ca, cb, sh = wst;
@@ -613,18 +638,19 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
                 xall[pidx(G, i)] = wd;
             }
         } else {
+            const bool need_lr = P.bps == 32 && P.do_mid_side;       // the 33-bit side channel is read through the left / right rows
             for (int s = 0; s < nsig; s++) {
-                if (!sig_active(s)) continue;
+                if (!sig_active(s) && !(need_lr && s < ch)) continue;
                 int32_t* x = xall + (size_t)s * sig_words;
-                const int wst = wasted_from_or(frame_bits(work, work_stride, (int)blockIdx.x)->or_[s], (int)P.bps);   // rows hold the signal with wasted bits removed
+                const int wst = wasted_from_or(frame_bits(work, work_stride, (int)blockIdx.x)->or_[s], (int)P.bps, P.bps == 32 && P.do_mid_side && s == ch + 1);   // rows hold the signal with wasted bits removed
                 for (int i = tid; i < N; i += kAnThreads) {
                     int v;
-                    if (s < ch) v = (int)__ldg(base + (uint64_t)i * ch + s);
-                    else {
-                        const int l = (int)__ldg(base + (uint64_t)i * ch), r = (int)__ldg(base + (uint64_t)i * ch + 1);
-                        v = (s == ch) ? ((l + r) >> 1) : (l - r);
+                    if (s < ch) v = (int)__ldg(base + (uint64_t)i * ch + s) >> wst;
+                    else {      // 64-bit: 32-bit input needs 33 bits here; a side channel that keeps all 33 is read through L / R instead
+                        const long long l = (long long)__ldg(base + (uint64_t)i * ch), r = (long long)__ldg(base + (uint64_t)i * ch + 1);
+                        v = (s == ch) ? (int)(((l + r) >> 1) >> wst) : (int)((l - r) >> wst);
                     }
-                    x[pidx(G, i)] = v >> wst;
+                    x[pidx(G, i)] = v;
                 }
             }
         }
@@ -632,12 +658,18 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
     __syncthreads();
 
     // per-signal facts every thread can derive on its own
-    auto sig_wasted = [&](int s) { return wasted_from_or(S.sig_or[s], (int)P.bps); };
+    auto sig_wasted = [&](int s) { return wasted_from_or(S.sig_or[s], (int)P.bps, P.bps == 32 && P.do_mid_side && s == ch + 1); };
     auto sig_sbps = [&](int s) { return (int)P.bps - sig_wasted(s) + ((P.do_mid_side && s == ch + 1) ? 1 : 0); };
     auto sig_view = [&](int s) {
         SigView V;
+        V.base2 = nullptr; V.shl = 0; V.shr = 0; V.s33 = 0;
         if (PACKED) { V.base = xall; V.ca = (s != 1); V.cb = (s == 0) ? 0 : (s == 3 ? -1 : 1); V.sh = sig_wasted(s) + (s == 2 ? 1 : 0); }
-        else { V.base = xall + (size_t)s * sig_words; V.ca = 1; V.cb = 0; V.sh = 0; }
+        else {
+            V.base = xall + (size_t)s * sig_words; V.ca = 1; V.cb = 0; V.sh = 0;
+            if (P.bps == 32 && P.do_mid_side && s == ch + 1 && sig_wasted(s) == 0) {      // 33-bit side: read through the left / right rows
+                V.base = xall; V.base2 = xall + (size_t)sig_words; V.shl = sig_wasted(0); V.shr = sig_wasted(1); V.s33 = 1;
+            }
+        }
         return V;
     };
     // up: process_subframe_ constant test + process_subframes_ limit_min_bitrate: when every earlier channel is

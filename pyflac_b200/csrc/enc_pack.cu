@@ -41,6 +41,12 @@ __device__ __forceinline__ void put_bits(uint32_t* buf, uint32_t pos, uint32_t v
     }
 }
 
+// up to 33 bits (the side channel of 32-bit stereo): top bit, then the low 32
+__device__ __forceinline__ void put_bits64(uint32_t* buf, uint32_t pos, long long v, uint32_t n) {
+    if (n > 32) { put_bits(buf, pos, (uint32_t)((unsigned long long)v >> 32), n - 32); put_bits(buf, pos + n - 32, (uint32_t)v, 32); }
+    else put_bits(buf, pos, (uint32_t)v, n);
+}
+
 // Rice-coded body of one subframe (up: add_residual_partitioned_rice_ + FLAC__bitwriter_write_rice_signed_block).
 // The whole CTA works on one subframe at a time, tile by tile: thread (warp w, lane l) owns samples
 //   i = t0 + w*512 + k*32 + l,  k = 0..15
@@ -51,10 +57,15 @@ __device__ __forceinline__ void put_bits(uint32_t* buf, uint32_t pos, uint32_t v
 // (a partition's parameter field sits right before its first sample's code).  Returns the body length in bits.
 // Residual arithmetic: r = x[i] - ((sum q_j x[i-1-j]) >> shift); fixed predictors are the same formula with
 // binomial coefficients and shift 0.  WIDE = 64-bit accumulate, chosen exactly as the analysis kernel does.
-template <int ORDER, bool WIDE>
+// S33: 33-bit samples (side channel of 32-bit stereo): x[] holds sample >> 1, lsb[] the dropped bits (always WIDE).
+template <int ORDER, bool WIDE, bool S33 = false>
 __device__ __noinline__ uint32_t pack_rice_body(const SubframePlan& pl, const int32_t* __restrict__ qs, int order, int shift,
-                                                const int32_t* __restrict__ x, int N, uint32_t body, uint32_t* obuf,
+                                                const int32_t* __restrict__ x, const uint32_t* __restrict__ lsb, int N, uint32_t body, uint32_t* obuf,
                                                 PackShared& S, int warp, int lane) {
+    auto X = [&](int i) -> long long {
+        if (S33) return ((long long)x[i] << 1) | (long long)((lsb[i >> 5] >> (i & 31)) & 1u);
+        return (long long)x[i];
+    };
     // ORDER is the order CLASS (4, 8 or 12 taps, coefficients beyond the real order are zero): three code bodies
     // instead of thirteen keep the kernel inside the instruction cache
     int32_t q[ORDER];
@@ -77,8 +88,8 @@ __device__ __noinline__ uint32_t pack_rice_body(const SubframePlan& pl, const in
                 if (WIDE) {
                     long long sacc = 0;
 #pragma unroll
-                    for (int j = 0; j < ORDER; j++) sacc += (long long)q[j] * (long long)x[max(i - 1 - j, 0)];
-                    r = (int32_t)((long long)x[i] - (sacc >> shift));
+                    for (int j = 0; j < ORDER; j++) sacc += (long long)q[j] * X(max(i - 1 - j, 0));
+                    r = (int32_t)(X(i) - (sacc >> shift));
                 } else {
                     int sacc = 0;
 #pragma unroll
@@ -124,11 +135,16 @@ __device__ __noinline__ uint32_t pack_rice_body(const SubframePlan& pl, const in
 }
 
 template <bool WIDE>
-__device__ __forceinline__ uint32_t pack_rice_dispatch(int order, const SubframePlan& pl, const int32_t* q, int shift, const int32_t* x, int N,
-                                                       uint32_t body, uint32_t* obuf, PackShared& S, int warp, int lane) {
-    if (order <= 4) return pack_rice_body<4, WIDE>(pl, q, order, shift, x, N, body, obuf, S, warp, lane);
-    if (order <= 8) return pack_rice_body<8, WIDE>(pl, q, order, shift, x, N, body, obuf, S, warp, lane);
-    return pack_rice_body<12, WIDE>(pl, q, order, shift, x, N, body, obuf, S, warp, lane);
+__device__ __forceinline__ uint32_t pack_rice_dispatch(int order, const SubframePlan& pl, const int32_t* q, int shift, const int32_t* x,
+                                                       const uint32_t* lsb, bool s33, int N, uint32_t body, uint32_t* obuf, PackShared& S, int warp, int lane) {
+    if (s33) {
+        if (order <= 4) return pack_rice_body<4, true, true>(pl, q, order, shift, x, lsb, N, body, obuf, S, warp, lane);
+        if (order <= 8) return pack_rice_body<8, true, true>(pl, q, order, shift, x, lsb, N, body, obuf, S, warp, lane);
+        return pack_rice_body<12, true, true>(pl, q, order, shift, x, lsb, N, body, obuf, S, warp, lane);
+    }
+    if (order <= 4) return pack_rice_body<4, WIDE>(pl, q, order, shift, x, lsb, N, body, obuf, S, warp, lane);
+    if (order <= 8) return pack_rice_body<8, WIDE>(pl, q, order, shift, x, lsb, N, body, obuf, S, warp, lane);
+    return pack_rice_body<12, WIDE>(pl, q, order, shift, x, lsb, N, body, obuf, S, warp, lane);
 }
 
 template <typename PcmT>
@@ -145,6 +161,7 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
     int32_t* xall = reinterpret_cast<int32_t*>(smem_raw);
     uint32_t* obuf = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ch * P.smem_stride * 4);
     PackShared& S = *reinterpret_cast<PackShared*>(smem_raw + (size_t)ch * P.smem_stride * 4 + (size_t)obuf_words * 4);
+    uint32_t* lsb = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ch * P.smem_stride * 4 + (size_t)obuf_words * 4 + ((sizeof(PackShared) + 15) / 16) * 16);   // 33-bit side: dropped low bits
 
     // ---- zero the frame image, CRC table, coded-signal map, frame header ----
     for (uint32_t i = tid; i < obuf_words; i += kPackThreads) obuf[i] = 0u;
@@ -178,14 +195,24 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
         for (int c = 0; c < ch; c++) {
             const int si = S.sigidx[c], wasted = S.plan[c].wasted;
             int32_t* x = xall + (size_t)c * P.smem_stride;
-            for (int i = tid; i < N; i += kPackThreads) {
-                int v;
-                if (si < ch) v = (int)__ldg(base + (uint64_t)i * ch + si);
-                else {
-                    const int l = (int)__ldg(base + (uint64_t)i * ch), r = (int)__ldg(base + (uint64_t)i * ch + 1);
-                    v = (si == ch) ? ((l + r) >> 1) : (l - r);
+            const bool s33 = S.plan[c].sbps > 32;          // side channel of 32-bit stereo without wasted bits: x = sample >> 1, lsb = dropped bits
+            for (int i0 = 0; i0 < N; i0 += kPackThreads) {
+                const int i = i0 + tid;
+                long long v = 0;
+                if (i < N) {
+                    if (si < ch) v = (long long)__ldg(base + (uint64_t)i * ch + si);
+                    else {      // 64-bit: mid / side of 32-bit input need 33 bits
+                        const long long l = (long long)__ldg(base + (uint64_t)i * ch), r = (long long)__ldg(base + (uint64_t)i * ch + 1);
+                        v = (si == ch) ? ((l + r) >> 1) : (l - r);
+                    }
+                    v >>= wasted;
                 }
-                x[i] = v >> wasted;
+                if (s33) {
+                    const uint32_t word = __ballot_sync(0xffffffffu, (v & 1ll) != 0);
+                    if (lane == 0 && i < N) lsb[i >> 5] = word;
+                    v >>= 1;
+                }
+                if (i < N) x[i] = (int32_t)v;
             }
         }
     }
@@ -198,6 +225,8 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
         const SubframePlan& pl = S.plan[c];
         const int32_t* x = xall + (size_t)c * P.smem_stride;
         const uint32_t sbps = pl.sbps, order = pl.order, wf = pl.wasted ? 1u : 0u;
+        const bool s33 = sbps > 32;
+        auto X = [&](int i) -> long long { return s33 ? (((long long)x[i] << 1) | (long long)((lsb[i >> 5] >> (i & 31)) & 1u)) : (long long)x[i]; };
         const uint32_t after_hdr = pos + 8u + pl.wasted;
         if (warp == 0) {   // subframe header, warm-up, predictor description: one lane per field
             if (lane == 0) {
@@ -210,10 +239,10 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
                 }
                 put_bits(obuf, pos, tb | wf, 8);
                 if (pl.wasted) put_bits(obuf, pos + 8u, 1u, pl.wasted);        // unary: wasted-1 zeros, then 1
-                if (pl.type == kConstant) put_bits(obuf, after_hdr, (uint32_t)x[0], sbps);
+                if (pl.type == kConstant) put_bits64(obuf, after_hdr, X(0), sbps);
             }
             if (pl.type == kFixed || pl.type == kLpc) {
-                if ((uint32_t)lane < order) put_bits(obuf, after_hdr + (uint32_t)lane * sbps, (uint32_t)x[lane], sbps);
+                if ((uint32_t)lane < order) put_bits64(obuf, after_hdr + (uint32_t)lane * sbps, X(lane), sbps);
                 uint32_t p2 = after_hdr + order * sbps;
                 if (pl.type == kLpc) {
                     if (lane == 12) put_bits(obuf, p2, (((uint32_t)pl.precision - 1u) << 5) | ((uint32_t)pl.shift & 31u), 9);
@@ -225,7 +254,7 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
         }
         if (pl.type == kConstant) pos = after_hdr + sbps;
         else if (pl.type == kVerbatim) {
-            for (int i = tid; i < N; i += kPackThreads) put_bits(obuf, after_hdr + (uint32_t)i * sbps, (uint32_t)x[i], sbps);
+            for (int i = tid; i < N; i += kPackThreads) put_bits64(obuf, after_hdr + (uint32_t)i * sbps, X(i), sbps);
             pos = after_hdr + (uint32_t)N * sbps;
         } else {
             uint32_t body = after_hdr + order * sbps + 6u, blen;
@@ -235,11 +264,12 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
                 for (uint32_t j = 0; j < order; j++) asum += abs(pl.qlp[j]);
                 if (asum == 0) asum = 1;
                 // same accumulator-width rule as the analysis kernel (up: FLAC__lpc_max_prediction_before_shift_bps)
-                if ((int)sbps + (int)silog2((int64_t)asum) <= 32) blen = pack_rice_dispatch<false>((int)order, pl, pl.qlp, pl.shift, x, N, body, obuf, S, warp, lane);
-                else blen = pack_rice_dispatch<true>((int)order, pl, pl.qlp, pl.shift, x, N, body, obuf, S, warp, lane);
+                if ((int)sbps + (int)silog2((int64_t)asum) <= 32) blen = pack_rice_dispatch<false>((int)order, pl, pl.qlp, pl.shift, x, lsb, s33, N, body, obuf, S, warp, lane);
+                else blen = pack_rice_dispatch<true>((int)order, pl, pl.qlp, pl.shift, x, lsb, s33, N, body, obuf, S, warp, lane);
             } else {
                 const int32_t cfix[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
-                blen = pack_rice_body<4, false>(pl, cfix[order], (int)order, 0, x, N, body, obuf, S, warp, lane);
+                if (s33) blen = pack_rice_body<4, true, true>(pl, cfix[order], (int)order, 0, x, lsb, N, body, obuf, S, warp, lane);
+                else blen = pack_rice_body<4, false>(pl, cfix[order], (int)order, 0, x, lsb, N, body, obuf, S, warp, lane);
             }
             pos = body + blen;
         }
@@ -266,7 +296,7 @@ void launch_pack(const void* pcm, const FrameDesc* frames, const EncParams& P, i
                  const uint8_t* frame_ca, uint8_t* scratch, uint32_t scratch_stride, uint32_t* frame_len,
                  cudaStream_t stream) {
     const uint32_t obuf_words = scratch_stride / 4 + 4;
-    const size_t smem = (size_t)P.channels * P.smem_stride * 4 + (size_t)obuf_words * 4 + sizeof(PackShared) + 16;
+    const size_t smem = (size_t)P.channels * P.smem_stride * 4 + (size_t)obuf_words * 4 + ((sizeof(PackShared) + 15) / 16) * 16 + ((size_t)P.blocksize + 31) / 32 * 4 + 16;
     if (P.container_bytes == 2) {
         cudaFuncSetAttribute(pack_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         pack_kernel<int16_t><<<n_frames, kPackThreads, smem, stream>>>((const int16_t*)pcm, frames, P, plans, frame_ca, scratch, scratch_stride, frame_len, obuf_words);
@@ -277,7 +307,7 @@ void launch_pack(const void* pcm, const FrameDesc* frames, const EncParams& P, i
 }
 
 size_t pack_smem_bytes(const EncParams& P, uint32_t scratch_stride) {
-    return (size_t)P.channels * P.smem_stride * 4 + (size_t)(scratch_stride / 4 + 4) * 4 + sizeof(PackShared) + 16;
+    return (size_t)P.channels * P.smem_stride * 4 + (size_t)(scratch_stride / 4 + 4) * 4 + ((sizeof(PackShared) + 15) / 16) * 16 + ((size_t)P.blocksize + 31) / 32 * 4 + 16;
 }
 
 // ------------------------------------------------------------------ layout: scan, compaction, stream prologue ----

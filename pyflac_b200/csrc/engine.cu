@@ -175,7 +175,6 @@ static int resolve_params(flacb200_ctx* ctx, const flacb200_enc_config& c, EncPa
     }
     P.limit_min_bitrate = c.limit_min_bitrate ? 1u : 0u;
     // limits of this build (DESIGN.md "limits")
-    if (c.bits_per_sample == 32 && P.do_mid_side) return fail(ctx, FLACB200_ERR_UNSUPPORTED, "32-bit stereo with mid/side analysis (33-bit side channel) not built yet: use compression level 0 or 3");
     if (c.container_bytes != 2 && c.container_bytes != 4) return fail(ctx, FLACB200_ERR_ARG, "container_bytes must be 2 or 4");
     if (c.container_bytes == 2 && c.bits_per_sample > 16) return fail(ctx, FLACB200_ERR_ARG, "int16 container needs bits_per_sample <= 16");
     P.smem_stride = ((P.blocksize + 3) / 4) * 4;

@@ -239,8 +239,7 @@ int init_common(FLAC__StreamEncoder* e) {
     const uint32_t lvl = m->level > 8 ? 8 : m->level;
     m->N = m->blocksize ? m->blocksize : (kMaxLpc[lvl] == 0 ? 1152u : 4096u);
     // limits of this build fail loudly here instead of producing a different stream (DESIGN.md "limits")
-    static const int kMs[9] = {0, 1, 1, 0, 1, 1, 1, 1, 1};
-    if (m->custom_tuning || (m->bps == 32 && m->channels == 2 && kMs[lvl])) { m->state = ST_FRAMING_ERROR; return INIT_ENCODER_ERROR; }   // 33-bit side channel: not built
+    if (m->custom_tuning) { m->state = ST_FRAMING_ERROR; return INIT_ENCODER_ERROR; }
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (!shared_ctx()) { m->state = ST_MEMORY_ALLOCATION_ERROR; return INIT_ENCODER_ERROR; }   // no CUDA device: no CPU fallback

@@ -47,6 +47,10 @@ CASES = [
     ("wasted_s32_3ch_l5", "wasted", 4096 + 512, 3, 32, 48000, 5, 0),
     ("music_s32_st_l3", "music", 4096 * 2, 2, 32, 48000, 3, 0),
     ("mixed_s32_st_l0", "mixed", 1152 * 3 + 4, 2, 32, 48000, 0, 0),
+    # 32-bit stereo with mid/side analysis: 33-bit side channel
+    ("music_s32_st_l5", "music", 4096 * 2 + 768, 2, 32, 48000, 5, 0),
+    ("mixed_s32_st_l8", "mixed", 4096 + 400, 2, 32, 48000, 8, 0),
+    ("lr_uncorr_s32_st_l2", "lr_uncorr", 1152 * 2 + 4, 2, 32, 44100, 2, 0),
 ]
 
 

@@ -94,11 +94,21 @@ def test_decode_32bit(eng, checkers):
     out, infos = nat.decode_streams(eng, blobs)
     for x, o, si in zip(xs, out, infos):
         assert si.status == 0 and si.bits_per_sample == 32 and np.array_equal(o, x)
+    # mid/side levels: the side channel has 33 bits (all four channel assignments, with and without wasted bits)
+    L = m[:, 0] * 200
+    pairs = [(L, L.copy()), (L, -L + rng.integers(-3, 4, n)), (L, -L), (L, L + rng.integers(-1000, 1000, n)), (L, m[:, 1] * 180),
+             (rng.integers(-2**31, 2**31, n), rng.integers(-2**31, 2**31, n)), (np.full(n, 2**31 - 1), np.full(n, -2**31)), (L * 2, -L * 2 + 4)]
+    ys = [np.clip(np.stack([a, b], axis=1), -2**31, 2**31 - 1).astype(np.int32) for a, b in pairs]
+    for level in (2, 5, 8):
+        blobs = [checkers.oracle_encode(y, 48000, 32, level, 0) for y in ys]
+        out, infos = nat.decode_streams(eng, blobs)
+        for y, o, si in zip(ys, out, infos):
+            assert si.status == 0 and np.array_equal(o, y), level
     if checkers.ref_available():
         mono = [x[:, :1].copy() for x in xs]
-        rb = [checkers.ref_encode(x, 48000, 32, 5, 0) for x in mono]
+        rb = [checkers.ref_encode(x, 48000, 32, 5, 0) for x in mono] + [checkers.ref_encode(y, 48000, 32, 5, 0) for y in ys]
         out, infos = nat.decode_streams(eng, rb)
-        for x, o, si in zip(mono, out, infos):
+        for x, o, si in zip(mono + ys, out, infos):
             assert si.status == 0 and np.array_equal(o, x)
 
 

@@ -107,9 +107,25 @@ def test_encode_32bit(eng, checkers):
     if checkers.ref_available():
         g, _ = nat.encode_streams(eng, [c32(sig["music_x200"])], 48000, 32, 5, 0)
         assert g[0] == checkers.ref_encode(c32(sig["music_x200"]), 48000, 32, 5, 0)
-    # the 33-bit side channel is not built: 32-bit stereo at a mid/side level fails loudly instead of differing
-    with pytest.raises(Exception):
-        nat.encode_streams(eng, stereo, 48000, 32, 5, 0)
+    # 32-bit stereo with mid/side analysis: the side channel has 33 bits (64-bit predictor / residual arithmetic, 33-bit
+    # warm-up and verbatim samples; an all-zero side reports one wasted bit, get_wasted_bits_wide_)
+    L = m[:, 0] * 200
+    R0 = np.roll(m[:, 0], 5) * 150
+    pairs = {"same": (L, L.copy()), "anti_noisy": (L, -L + rng.integers(-3, 4, n)), "anti": (L, -L), "anti_odd": (L, (-L) // 2 * 2 + 1),
+             "noise": (rng.integers(-2**31, 2**31, n), rng.integers(-2**31, 2**31, n)), "neg_m1": (sig["noise_full"][:, 0], -sig["noise_full"][:, 0] - 1),
+             "near": (L, L + rng.integers(-1000, 1000, n)), "rails": (np.full(n, 2**31 - 1), np.full(n, -2**31)), "indep": (L, R0),
+             "sparse": (np.where(rng.random(n) < 0.001, 2**31 - 1, 0), np.where(rng.random(n) < 0.001, -2**31, 0))}
+    xs = [c32(np.stack([a, b], axis=1)) for a, b in pairs.values()]
+    for level in (1, 2, 4, 5, 8):
+        for bs in (0, 1152):
+            got, out = nat.encode_streams(eng, xs, 48000, 32, level, bs)
+            for k, x, g in zip(pairs, xs, got):
+                assert g == checkers.oracle_encode(x, 48000, 32, level, bs), (k, level, bs)
+            assert out["log_guard_hits"] == 0
+    if checkers.ref_available():
+        got, _ = nat.encode_streams(eng, xs, 48000, 32, 5, 0)
+        for k, x, g in zip(pairs, xs, got):
+            assert g == checkers.ref_encode(x, 48000, 32, 5, 0), k
 
 
 def test_encode_limit_min_bitrate(eng, checkers):
