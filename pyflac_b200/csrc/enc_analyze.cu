@@ -415,34 +415,51 @@ struct AcSource {            // packed layout: what the nsig jobs of one (frame,
     uint32_t shpack;         // right shift of signal s in byte s (wasted bits; +1 for mid)
 };
 
+// What a lane holds for the next chunk while the chains of the current one run: raw loads only (packed layout: one word
+// and one window value per source), so nothing waits for HBM/L2 until ac_finish() turns them into windowed floats AFTER
+// the chains.  Other layouts: the finished floats (their fetch is per job).
+struct AcRaw { int wd[2]; float wv[2]; float dv[kAcJobsMax]; };
+
 template <typename PcmT, bool PACKED>
-__device__ __forceinline__ void ac_fetch_all(float (&dv)[kAcJobsMax], const AcSource (&src)[2], const AcJob* __restrict__ jobs,
-                                             int jobs_per_warp, int nsig, const float* __restrict__ windows, int ch, int i) {
+__device__ __forceinline__ void ac_load(AcRaw& R, const AcSource (&src)[2], const AcJob* __restrict__ jobs,
+                                        int jobs_per_warp, const float* __restrict__ windows, int ch, int i) {
     if (PACKED) {
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            float wv = 0.0f; int lo = 0, hi = 0;
+            R.wv[u] = 0.0f; R.wd[u] = 0;
             if (i < src[u].len && i < 2 * src[u].part) {
-                wv = __ldg(windows + (i < src[u].part ? src[u].wofs : src[u].wtail) + i);
-                int wd;
-                if ((reinterpret_cast<uintptr_t>(src[u].base) & 3u) == 0) wd = __ldg(reinterpret_cast<const int*>(src[u].base) + i);
-                else wd = (int)((uint32_t)(uint16_t)__ldg(src[u].base + 2 * i) | ((uint32_t)(uint16_t)__ldg(src[u].base + 2 * i + 1) << 16));
-                lo = (int)(short)wd; hi = wd >> 16;
+                R.wv[u] = __ldg(windows + (i < src[u].part ? src[u].wofs : src[u].wtail) + i);
+                if ((reinterpret_cast<uintptr_t>(src[u].base) & 3u) == 0) R.wd[u] = __ldg(reinterpret_cast<const int*>(src[u].base) + i);
+                else R.wd[u] = (int)((uint32_t)(uint16_t)__ldg(src[u].base + 2 * i) | ((uint32_t)(uint16_t)__ldg(src[u].base + 2 * i + 1) << 16));
             }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < kAcJobsMax; q++) R.dv[q] = (q < jobs_per_warp) ? ac_fetch<PcmT, PACKED>(jobs[q], windows, ch, i) : 0.0f;
+    }
+}
+
+template <bool PACKED>
+__device__ __forceinline__ void ac_finish(float (&dv)[kAcJobsMax], const AcRaw& R, const AcSource (&src)[2], int nsig) {
+    if (PACKED) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int lo = (int)(short)R.wd[u], hi = R.wd[u] >> 16;
+            const float wv = R.wv[u];
             const uint32_t sp = src[u].shpack;
             dv[4 * u + 0] = FB_FMUL(__int2float_rn(lo >> (sp & 0xff)), wv);
             dv[4 * u + 1] = FB_FMUL(__int2float_rn(hi >> ((sp >> 8) & 0xff)), wv);
             if (nsig > 2) {
                 dv[4 * u + 2] = FB_FMUL(__int2float_rn((lo + hi) >> ((sp >> 16) & 0xff)), wv);
                 dv[4 * u + 3] = FB_FMUL(__int2float_rn((lo - hi) >> (sp >> 24)), wv);
-            } else {        // two signals per source: jobs 0,1 | 2,3 (sources beyond the second stay empty)
+            } else {        // two signals per source: jobs 0,1 | 2,3
                 dv[4 * u + 2] = 0.0f; dv[4 * u + 3] = 0.0f;
             }
         }
         if (nsig == 2) { dv[2] = dv[4]; dv[3] = dv[5]; dv[4] = dv[5] = 0.0f; }
     } else {
 #pragma unroll
-        for (int q = 0; q < kAcJobsMax; q++) dv[q] = (q < jobs_per_warp) ? ac_fetch<PcmT, PACKED>(jobs[q], windows, ch, i) : 0.0f;
+        for (int q = 0; q < kAcJobsMax; q++) dv[q] = R.dv[q];
     }
 }
 
@@ -512,7 +529,9 @@ autoc_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames,
         }
     }
     float dv[kAcJobsMax];
-    ac_fetch_all<PcmT, PACKED>(dv, src, jobs, jobs_per_warp, nsig, windows, ch, lane);
+    AcRaw raw;
+    ac_load<PcmT, PACKED>(raw, src, jobs, jobs_per_warp, windows, ch, lane);
+    ac_finish<PACKED>(dv, raw, src, nsig);
 #pragma unroll
     for (int q = 0; q < kAcJobsMax; q++) if (q < jobs_per_warp) ring[q * kAcRing + 16 + lane] = (double)dv[q];
     __syncwarp();
@@ -526,7 +545,7 @@ autoc_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames,
     const int nchunks = (maxlen + 31) >> 5;
     for (int c = 0; c < nchunks; c++) {
         const int slot = c & 1;
-        ac_fetch_all<PcmT, PACKED>(dv, src, jobs, jobs_per_warp, nsig, windows, ch, (c + 1) * 32 + lane);
+        ac_load<PcmT, PACKED>(raw, src, jobs, jobs_per_warp, windows, ch, (c + 1) * 32 + lane);     // in flight while the chains run
         if (active) {
             const double* curp = jobring + 16 + slot * 32;
             const double* lagp = curp - lag0;
@@ -540,6 +559,7 @@ autoc_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames,
             }
         }
         __syncwarp();
+        ac_finish<PACKED>(dv, raw, src, nsig);
 #pragma unroll
         for (int q = 0; q < kAcJobsMax; q++) {
             if (q < jobs_per_warp) {

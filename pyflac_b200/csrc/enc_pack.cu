@@ -148,7 +148,7 @@ __device__ __forceinline__ uint32_t pack_rice_dispatch(int order, const Subframe
 }
 
 template <typename PcmT>
-__global__ void __launch_bounds__(kPackThreads)
+__global__ void __launch_bounds__(kPackThreads, 4)
 pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, EncParams P,
             const SubframePlan* __restrict__ plans, const uint8_t* __restrict__ frame_ca,
             uint8_t* __restrict__ scratch, uint32_t scratch_stride, uint32_t* __restrict__ frame_len, uint32_t obuf_words) {
@@ -192,27 +192,41 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
     // ---- rebuild the coded signals (wasted bits removed) ----
     {
         const PcmT* base = pcm + fd.pcm_off;
-        for (int c = 0; c < ch; c++) {
-            const int si = S.sigidx[c], wasted = S.plan[c].wasted;
-            int32_t* x = xall + (size_t)c * P.smem_stride;
-            const bool s33 = S.plan[c].sbps > 32;          // side channel of 32-bit stereo without wasted bits: x = sample >> 1, lsb = dropped bits
-            for (int i0 = 0; i0 < N; i0 += kPackThreads) {
-                const int i = i0 + tid;
-                long long v = 0;
-                if (i < N) {
-                    if (si < ch) v = (long long)__ldg(base + (uint64_t)i * ch + si);
-                    else {      // 64-bit: mid / side of 32-bit input need 33 bits
-                        const long long l = (long long)__ldg(base + (uint64_t)i * ch), r = (long long)__ldg(base + (uint64_t)i * ch + 1);
-                        v = (si == ch) ? ((l + r) >> 1) : (l - r);
+        if (ch == 2) {
+            // stereo: one pass, both channels of a sample loaded once (one 32-bit word for an aligned int16 container); four
+            // samples per thread are in flight before the first one is used
+            const int si0 = S.sigidx[0], si1 = S.sigidx[1], w0 = S.plan[0].wasted, w1 = S.plan[1].wasted;
+            const bool s33_0 = S.plan[0].sbps > 32, s33_1 = S.plan[1].sbps > 32;
+            const bool word_ok = sizeof(PcmT) == 2 && ((reinterpret_cast<uintptr_t>(base) & 3u) == 0);
+            int32_t* x0 = xall; int32_t* x1 = xall + P.smem_stride;
+            for (int i0 = 0; i0 < N; i0 += 4 * kPackThreads) {
+                long long l[4], r[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * kPackThreads + tid;
+                    l[u] = 0; r[u] = 0;
+                    if (i < N) {
+                        if (word_ok) { const int wd = __ldg(reinterpret_cast<const int*>(base) + i); l[u] = (long long)(short)wd; r[u] = (long long)(wd >> 16); }
+                        else { l[u] = (long long)__ldg(base + 2 * (uint64_t)i); r[u] = (long long)__ldg(base + 2 * (uint64_t)i + 1); }
                     }
-                    v >>= wasted;
                 }
-                if (s33) {
-                    const uint32_t word = __ballot_sync(0xffffffffu, (v & 1ll) != 0);
-                    if (lane == 0 && i < N) lsb[i >> 5] = word;
-                    v >>= 1;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * kPackThreads + tid;
+                    if (i0 + u * kPackThreads >= N) break;                      // uniform: whole CTA past the end
+                    const long long m = (l[u] + r[u]) >> 1, sd = l[u] - r[u];  // 64-bit: 32-bit input needs 33 bits here
+                    long long v0 = (si0 == 0 ? l[u] : si0 == 1 ? r[u] : si0 == 2 ? m : sd) >> w0;
+                    long long v1 = (si1 == 0 ? l[u] : si1 == 1 ? r[u] : si1 == 2 ? m : sd) >> w1;
+                    if (s33_0) { const uint32_t word = __ballot_sync(0xffffffffu, (v0 & 1ll) != 0); if (lane == 0 && i < N) lsb[i >> 5] = word; v0 >>= 1; }
+                    if (s33_1) { const uint32_t word = __ballot_sync(0xffffffffu, (v1 & 1ll) != 0); if (lane == 0 && i < N) lsb[i >> 5] = word; v1 >>= 1; }
+                    if (i < N) { x0[i] = (int32_t)v0; x1[i] = (int32_t)v1; }
                 }
-                if (i < N) x[i] = (int32_t)v;
+            }
+        } else {
+            for (int c = 0; c < ch; c++) {
+                const int si = S.sigidx[c], wasted = S.plan[c].wasted;
+                int32_t* x = xall + (size_t)c * P.smem_stride;
+                for (int i = tid; i < N; i += kPackThreads) x[i] = (int)__ldg(base + (uint64_t)i * ch + si) >> wasted;
             }
         }
     }
