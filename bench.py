@@ -273,6 +273,53 @@ def main():
     if world > 1:
         dist.barrier()
 
+    # ---------------- scatter / gather over NCCL (PCM born on rank 0's GPU) ----------------
+    sg = None
+    if world > 1:
+        try:
+            from pyflac_b200.dist import scatter_streams, gather_packed
+
+            class _DevMem:      # zero-copy torch view of the engine's device arena (CUDA array interface)
+                def __init__(self, ptr, nbytes):
+                    self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+            elems = N_SAMPLES * CHANNELS
+            # setup (untimed): the root collects every rank's streams so that all PCM starts on one GPU
+            mine = d_pcm.view(N_STREAMS, elems).view(torch.uint8)           # NCCL moves bytes, not int16
+            parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+            dist.gather(mine, gather_list=parts, dst=0)
+            full = torch.cat(parts, 0).view(torch.int16) if rank == 0 else None
+            del parts
+
+            def step_sg():
+                blk, (lo, hi) = scatter_streams(full, world * N_STREAMS, elems, torch.int16, dev)
+                k = hi - lo
+                off = (np.arange(k, dtype=np.uint64) * np.uint64(elems))
+                eng.encode_device(cfg, blk.data_ptr(), blk.numel(), off, np.full(k, N_SAMPLES, np.uint64))
+                r = eng.result()                                    # waits for this batch (incl. its MD5): the bytes must be final
+                arena = torch.as_tensor(_DevMem(r.d_arena, int(r.total_bytes)), device=dev)
+                bufs, sizes = gather_packed(arena, int(r.total_bytes), dev)
+                return sizes
+            for _ in range(2):
+                sizes = step_sg()
+            torch.cuda.synchronize(); dist.barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nsg = max(2, args.steps // 4)
+            g0.record()
+            for _ in range(nsg):
+                sizes = step_sg()
+            g1.record()
+            torch.cuda.synchronize(); dist.barrier()
+            tsg = torch.tensor([g0.elapsed_time(g1) / nsg], dtype=torch.float64, device=dev)
+            dist.all_reduce(tsg, op=dist.ReduceOp.MAX)
+            sg = {"value": world * total_samples / (float(tsg[0]) * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": float(tsg[0]),
+                  "scatter_bytes_per_step": (world - 1) * pcm_bytes, "gather_bytes_per_step": int(sum(sizes[1:])),
+                  "what": "all PCM resident on rank 0's GPU -> NCCL scatter of stream blocks -> encode on every rank -> NCCL gather of the packed bytes to rank 0"}
+            del full
+        except Exception as ex:                                   # never lose the main line to the optional mode
+            sg = {"error": repr(ex)[:300]}
+        torch.cuda.set_stream(work_stream)
+        eng.set_stream(work_stream.cuda_stream)
+
     # ---------------- decode (second half of the metric): the streams just encoded, device-resident and host->host ----------------
     arena_np = h_arena.numpy()
     total_flac = int(tot.value)
@@ -354,6 +401,7 @@ def main():
                                     "achieved": (out_bytes + pcm_bytes) / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9,
                                     "peak": peak, "unit": "GB/s",
                                     "frac": (out_bytes + pcm_bytes) / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9 / peak}},
+            "scatter_gather": sg,
             "frames_per_step": n_frames * world, "compressed_bytes_per_step": out_bytes, "ratio": out_bytes / pcm_bytes,
             "log_guard_hits": guard_hits,
         }

@@ -90,6 +90,46 @@ def test_rank_reductions_gloo_world2():
         os.unlink(path)
 
 
+_WORKER_SG = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from pyflac_b200.dist import scatter_streams, gather_packed, shard_range
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+n, e = 7, 50                                            # 7 streams over 2 ranks: blocks of 4 and 3
+full = torch.arange(n * e, dtype=torch.int16).reshape(n, e) if r == 0 else None
+blk, (lo, hi) = scatter_streams(full, n, e, torch.int16, "cpu")
+ok = bool((blk == torch.arange(n * e, dtype=torch.int16).reshape(n, e)[lo:hi]).all()) and (lo, hi) == shard_range(n, r, w)
+payload = (blk.reshape(-1).to(torch.int32) % 251).to(torch.uint8)[: 100 + 37 * r]      # "packed bytes", different length per rank
+bufs, sizes = gather_packed(torch.cat([payload, torch.zeros(64, dtype=torch.uint8)]), payload.numel(), "cpu")
+if r == 0:
+    exp1 = (torch.arange(n * e, dtype=torch.int16).reshape(n, e)[4:7].reshape(-1).to(torch.int32) % 251).to(torch.uint8)[:137]
+    ok = ok and sizes == [100, 137] and bool((bufs[0] == payload).all()) and bool((bufs[1] == exp1).all())
+flag = torch.tensor([1.0 if ok else 0.0]); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if r == 0:
+    print("RESULT", float(flag))
+dist.destroy_process_group()
+'''
+
+
+def test_scatter_gather_gloo_world2():
+    """pyflac_b200.dist.scatter_streams / gather_packed (the NCCL scatter of PCM born on one GPU and the gather of the
+    packed bytes, SURVEY 8(e)) on the gloo backend with uneven blocks and ragged payloads"""
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(_WORKER_SG)
+        path = f.name
+    try:
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                              "--master-port", "29578", path, ROOT], capture_output=True, text=True, timeout=240, env=env)
+        line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
+        assert line, out.stdout + out.stderr
+        assert float(line[0].split()[1]) == 1.0
+    finally:
+        os.unlink(path)
+
+
 def test_package_surface_matches_reference_names():
     import pyflac_b200 as pf
     for name in ["StreamEncoder", "FileEncoder", "EncoderState", "EncoderInitException", "EncoderProcessException",
