@@ -147,7 +147,8 @@ __device__ __forceinline__ uint32_t pack_rice_dispatch(int order, const Subframe
     return pack_rice_body<12, WIDE>(pl, q, order, shift, x, lsb, N, body, obuf, S, warp, lane);
 }
 
-template <typename PcmT>
+// B32: 32-bit input (its side channel can need 33 bits); every other depth compiles without that machinery.
+template <typename PcmT, bool B32>
 __global__ void __launch_bounds__(kPackThreads, 4)
 pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, EncParams P,
             const SubframePlan* __restrict__ plans, const uint8_t* __restrict__ frame_ca,
@@ -196,7 +197,7 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
             // stereo: one pass, both channels of a sample loaded once (one 32-bit word for an aligned int16 container); four
             // samples per thread are in flight before the first one is used
             const int si0 = S.sigidx[0], si1 = S.sigidx[1], w0 = S.plan[0].wasted, w1 = S.plan[1].wasted;
-            const bool s33_0 = S.plan[0].sbps > 32, s33_1 = S.plan[1].sbps > 32;
+            const bool s33_0 = B32 && S.plan[0].sbps > 32, s33_1 = B32 && S.plan[1].sbps > 32;
             const bool word_ok = sizeof(PcmT) == 2 && ((reinterpret_cast<uintptr_t>(base) & 3u) == 0);
             int32_t* x0 = xall; int32_t* x1 = xall + P.smem_stride;
             for (int i0 = 0; i0 < N; i0 += 4 * kPackThreads) {
@@ -239,7 +240,7 @@ pack_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, 
         const SubframePlan& pl = S.plan[c];
         const int32_t* x = xall + (size_t)c * P.smem_stride;
         const uint32_t sbps = pl.sbps, order = pl.order, wf = pl.wasted ? 1u : 0u;
-        const bool s33 = sbps > 32;
+        const bool s33 = B32 && sbps > 32;
         auto X = [&](int i) -> long long { return s33 ? (((long long)x[i] << 1) | (long long)((lsb[i >> 5] >> (i & 31)) & 1u)) : (long long)x[i]; };
         const uint32_t after_hdr = pos + 8u + pl.wasted;
         if (warp == 0) {   // subframe header, warm-up, predictor description: one lane per field
@@ -312,11 +313,14 @@ void launch_pack(const void* pcm, const FrameDesc* frames, const EncParams& P, i
     const uint32_t obuf_words = scratch_stride / 4 + 4;
     const size_t smem = (size_t)P.channels * P.smem_stride * 4 + (size_t)obuf_words * 4 + ((sizeof(PackShared) + 15) / 16) * 16 + ((size_t)P.blocksize + 31) / 32 * 4 + 16;
     if (P.container_bytes == 2) {
-        cudaFuncSetAttribute(pack_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        pack_kernel<int16_t><<<n_frames, kPackThreads, smem, stream>>>((const int16_t*)pcm, frames, P, plans, frame_ca, scratch, scratch_stride, frame_len, obuf_words);
+        cudaFuncSetAttribute(pack_kernel<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        pack_kernel<int16_t, false><<<n_frames, kPackThreads, smem, stream>>>((const int16_t*)pcm, frames, P, plans, frame_ca, scratch, scratch_stride, frame_len, obuf_words);
+    } else if (P.bps < 32) {
+        cudaFuncSetAttribute(pack_kernel<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        pack_kernel<int32_t, false><<<n_frames, kPackThreads, smem, stream>>>((const int32_t*)pcm, frames, P, plans, frame_ca, scratch, scratch_stride, frame_len, obuf_words);
     } else {
-        cudaFuncSetAttribute(pack_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        pack_kernel<int32_t><<<n_frames, kPackThreads, smem, stream>>>((const int32_t*)pcm, frames, P, plans, frame_ca, scratch, scratch_stride, frame_len, obuf_words);
+        cudaFuncSetAttribute(pack_kernel<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        pack_kernel<int32_t, true><<<n_frames, kPackThreads, smem, stream>>>((const int32_t*)pcm, frames, P, plans, frame_ca, scratch, scratch_stride, frame_len, obuf_words);
     }
 }
 
