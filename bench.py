@@ -69,6 +69,18 @@ def make_pcm(rank, n_streams=N_STREAMS):
     return out
 
 
+def make_pcm_short(rank, n_streams, n_samples):
+    """Synthetic PCM for the decode leg (BASELINE configs[3] shape): 32 distinct music-like streams per rank, tiled with a
+    circular shift + gain like make_pcm."""
+    from pyflac_b200.synth import music_like
+    base = [music_like(n_samples, CHANNELS, SAMPLE_RATE, BPS, seed=5000 + 1000 * rank + s) for s in range(32)]
+    out = np.empty((n_streams, n_samples, CHANNELS), np.int16)
+    for s in range(n_streams):
+        b, k = base[s % 32], s // 32
+        out[s] = b if k == 0 else (np.roll(b, 104729 * k % n_samples, axis=0).astype(np.int32) * (256 - k) // 256).astype(np.int16)
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -320,48 +332,77 @@ def main():
         torch.cuda.set_stream(work_stream)
         eng.set_stream(work_stream.cuda_stream)
 
-    # ---------------- decode (second half of the metric): the streams just encoded, device-resident and host->host ----------------
+    # ---------------- decode (second half of the metric), device-resident and host->host ----------------
+    def decode_leg(blob_np, s_off, s_len, n_elems, expect, steps):
+        """blob_np: pinned uint8 array (+16 bytes of padding); returns (device ms/step, e2e ms/step, kernel ms, ok)."""
+        nbytes = int(blob_np.size - 16)
+        d_flac = torch.from_numpy(blob_np).to(dev)
+        for _ in range(2):
+            eng.decode_device(d_flac.data_ptr(), nbytes, s_off, s_len, 2)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        dv0, dv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dv0.record()
+        for _ in range(steps):
+            eng.decode_device(d_flac.data_ptr(), nbytes, s_off, s_len, 2)
+        dv1.record()
+        torch.cuda.synchronize()
+        dev_ms = dv0.elapsed_time(dv1) / steps
+        kt = eng.decode_kernel_times()
+        ok = int(eng.decode_result().total_elems) == n_elems
+        del d_flac
+        h_out = torch.empty(n_elems, dtype=torch.int16).pin_memory()
+        infos_d = [None]
+
+        def step_e2e():
+            infos_d[0] = eng.decode_host_pipelined(blob_np, s_off, s_len, h_out.numpy(), 2)[1]
+        step_e2e()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        d0 = time.perf_counter()
+        for _ in range(steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - d0) * 1e3 / steps
+        ok = ok and bool(np.array_equal(h_out.numpy(), expect.reshape(-1))) and all(infos_d[0][s].status == 0 for s in range(len(s_off)))
+        del h_out
+        return dev_ms, e2e_ms, kt, ok
+
+    # (a) round trip: the 256 streams the encode step just produced
     arena_np = h_arena.numpy()
     total_flac = int(tot.value)
-    d_flac = torch.from_numpy(arena_np[:total_flac + 16].copy()).to(dev)
     s_off = np.array([infos[s].byte_off for s in range(N_STREAMS)], np.uint64)
     s_len = np.array([infos[s].byte_len for s in range(N_STREAMS)], np.uint64)
-    for _ in range(2):
-        eng.decode_device(d_flac.data_ptr(), total_flac, s_off, s_len, 2)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    dv0, dv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dv0.record()
-    for _ in range(args.steps):
-        eng.decode_device(d_flac.data_ptr(), total_flac, s_off, s_len, 2)
-    dv1.record()
-    torch.cuda.synchronize()
-    dec_ms = dv0.elapsed_time(dv1)
-    dec_kt = eng.decode_kernel_times()
-    dres = eng.decode_result()
-    dec_ok = int(dres.total_elems) == total_samples
-    h_out = torch.empty(total_samples, dtype=torch.int16).pin_memory()
-    dinfos = [None] * N_STREAMS
+    rt_dev_ms, rt_e2e_ms, rt_kt, rt_ok = decode_leg(arena_np[:total_flac + 16], s_off, s_len, total_samples, pcm, args.steps)
 
-    def step_dec_e2e():
-        tot_e, dinf = eng.decode_host_pipelined(arena_np[:total_flac + 16], s_off, s_len, h_out.numpy(), 2)
-        dinfos[:] = dinf[:N_STREAMS]
-    step_dec_e2e()
-    torch.cuda.synchronize()
-    d0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_dec_e2e()
-    torch.cuda.synchronize()
-    dec_e2e_s = time.perf_counter() - d0
-    dec_ok = dec_ok and bool(np.array_equal(h_out.numpy(), pcm.reshape(-1))) and all(dinfos[s].status == 0 for s in range(N_STREAMS))
-    del d_flac
+    # (b) BASELINE configs[3]: 4096 parallel .flac streams (131 072 stereo samples each, level 5) -> int16 PCM
+    D_STREAMS, D_SAMPLES = 4096, 131072
+    pcm4 = make_pcm_short(rank, D_STREAMS, D_SAMPLES)
+    d4 = torch.from_numpy(pcm4.reshape(-1)).to(dev)
+    off4 = np.arange(D_STREAMS, dtype=np.uint64) * np.uint64(D_SAMPLES * CHANNELS)
+    eng.encode_device(cfg, d4.data_ptr(), d4.numel(), off4, np.full(D_STREAMS, D_SAMPLES, np.uint64))
+    enc4 = eng.fetch()
+    del d4
+    total4 = int(enc4["total_bytes"])
+    h_blob4 = torch.empty(total4 + 16, dtype=torch.uint8).pin_memory()
+    h_blob4.numpy()[:total4] = enc4["arena"][:total4]
+    h_blob4.numpy()[total4:] = 0
+    s_off4 = np.array([si.byte_off for si in enc4["streams"]], np.uint64)
+    s_len4 = np.array([si.byte_len for si in enc4["streams"]], np.uint64)
+    del enc4
+    dsteps = max(3, args.steps // 4)
+    dec_ms_step, dec_e2e_ms_step, dec_kt, dec_ok = decode_leg(h_blob4.numpy(), s_off4, s_len4, pcm4.size, pcm4, dsteps)
+    dec_total_samples = pcm4.size
+    dec_bytes = total4 + pcm4.nbytes
+    dec_ms, dec_e2e_s = dec_ms_step, dec_e2e_ms_step / 1e3
 
     # ---------------- reduce over ranks ----------------
-    t = torch.tensor([ms_total, e2e_s * 1e3, dec_ms, dec_e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s * 1e3, dec_ms, dec_e2e_s * 1e3, rt_dev_ms, rt_e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max, e2e_ms_max, dec_ms_max, dec_e2e_ms_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    ms_total_max, e2e_ms_max, dec_ms_max, dec_e2e_ms_max, rt_dev_max, rt_e2e_max = (float(t[i]) for i in range(6))
 
     if rank == 0:
         ms_per_step = ms_total_max / args.steps
@@ -392,15 +433,22 @@ def main():
                              "frac": pcm_bytes / (max(kt_acc.get("md5", 0.0), 1e-6) * 1e-3) / 1e9 / peak,
                              "algorithmic_bytes_per_launch": pcm_bytes},
             "decode": {"metric": "decode_msamples_per_s", "unit": UNIT,
-                       "value": world * total_samples / (dec_ms_max / args.steps * 1e-3) / 1e6,
-                       "e2e_value": world * total_samples / (dec_e2e_ms_max / args.steps * 1e-3) / 1e6,
-                       "ms_per_step": dec_ms_max / args.steps, "e2e_ms_per_step": dec_e2e_ms_max / args.steps,
-                       "workload": "the 256 streams produced by the encode step (libFLAC-identical bytes) -> int16 PCM",
+                       "value": world * dec_total_samples / (dec_ms_max * 1e-3) / 1e6,
+                       "e2e_value": world * dec_total_samples / (dec_e2e_ms_max * 1e-3) / 1e6,
+                       "ms_per_step": dec_ms_max, "e2e_ms_per_step": dec_e2e_ms_max, "steps": dsteps,
+                       "workload": "StreamDecoder: 4096 parallel .flac streams (131072 stereo int16 samples each, level 5) -> int16 PCM (BASELINE configs[3]) per GPU",
+                       "h2d_bytes_per_step": total4, "d2h_bytes_per_step": int(pcm4.nbytes),
                        "pcm_identical_to_input": bool(dec_ok), "kernel_ms": dec_kt,
                        "roofline": {"bound": "hbm", "kernel": "dec_frame_kernel",
-                                    "achieved": (out_bytes + pcm_bytes) / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9,
+                                    "achieved": dec_bytes / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9,
                                     "peak": peak, "unit": "GB/s",
-                                    "frac": (out_bytes + pcm_bytes) / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9 / peak}},
+                                    "frac": dec_bytes / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9 / peak,
+                                    "algorithmic_bytes_per_launch": dec_bytes}},
+            "decode_roundtrip_256": {"value": world * total_samples / (rt_dev_max * 1e-3) / 1e6, "e2e_value": world * total_samples / (rt_e2e_max * 1e-3) / 1e6,
+                                     "unit": UNIT, "ms_per_step": rt_dev_max, "e2e_ms_per_step": rt_e2e_max, "kernel_ms": rt_kt,
+                                     "workload": "the 256 streams produced by the encode step (libFLAC-identical bytes) -> int16 PCM; a launch cannot "
+                                                 "finish faster than one frame's serial decode, so this small batch is latency bound",
+                                     "pcm_identical_to_input": bool(rt_ok)},
             "scatter_gather": sg,
             "frames_per_step": n_frames * world, "compressed_bytes_per_step": out_bytes, "ratio": out_bytes / pcm_bytes,
             "log_guard_hits": guard_hits,
@@ -421,8 +469,8 @@ def main():
                 sweep[t] = (n_sample if t > 1 else 8) * N_SAMPLES * CHANNELS / best / 1e6
             tbest = max(sweep, key=sweep.get)
             import _checkers as ck
-            ddt = min(ck.ref_decode_mt(arena_np[:total_flac + 16], s_off, s_len, tbest)[0] for _ in range(2))
-            cpu_decode = total_samples / ddt / 1e6
+            ddt = min(ck.ref_decode_mt(h_blob4.numpy(), s_off4, s_len4, tbest)[0] for _ in range(2))
+            cpu_decode = dec_total_samples / ddt / 1e6
             line["cpu_baseline"] = {"value": sweep[tbest], "unit": UNIT, "cores": tbest, "kind": "reference",
                                     "sample": f"all {n_sample} streams of the step (8 for the 1-thread point), one FLAC__StreamEncoder per pthread, "
                                               f"libFLAC 1.4.3 from oracle/_ref; best of thread sweep",

@@ -291,9 +291,11 @@ extern "C" int flacb200_decode_batch_host(flacb200_ctx* ctx, const uint8_t* blob
         d->pcm_busy = false; d->have = false;
     }
     // chunks of whole streams with about equal byte counts
-    // A chunk only pays off when it still fills the GPU: the frame kernel decodes one frame per thread and a launch
-    // cannot finish faster than one frame's serial decode (a few ms), so chunks hold >= ~200 MB of FLAC (~20 000 frames).
-    int nchunks = (int)(blob_bytes / (200ull << 20));
+    // One chunk by default.  Measured on B200: the decode pipeline of a chunk issues small H2D / D2H copies (segment tables,
+    // candidate counts, per-stream results) that queue on the same copy engines BEHIND the big blob / PCM transfers of the
+    // neighbouring chunks, so chunks serialise instead of overlapping (6 chunks: 97 ms, 1 chunk: 84 ms for 1.26 GB in /
+    // 2.15 GB out); and a launch cannot finish faster than one frame's serial decode.  FLACB200_DEC_CHUNKS overrides.
+    int nchunks = 1;
     if (const char* ev = getenv("FLACB200_DEC_CHUNKS")) { const int v = atoi(ev); if (v > 0) nchunks = v; }
     if (nchunks < 1) nchunks = 1;
     if (nchunks > 12) nchunks = 12;

@@ -216,40 +216,47 @@ __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, u
 // 32-bit load that tops the 64-bit window up to >= 32 valid bits), so the 32 lanes of a warp -- each decoding its
 // own frame -- stay converged: a byte-wise refill loop entered by every lane at a different symbol would serialise.
 struct BitReader {
-    const uint32_t* __restrict__ wp;    // next aligned word to fetch
+    const uint32_t* __restrict__ wp;    // next aligned word to consume
     const uint32_t* wend;               // first word past the stream (aligned up)
     const uint8_t* sbase;               // stream start (for bit positions)
+    const uint8_t* send;                // one past the stream's last byte
     uint64_t acc; int n;                // n valid bits at the top of acc
-    uint32_t next1, next2;              // RAW words fetched one and two refills ahead: the byte swap happens when a word is
-                                        // consumed, so nothing waits on a load until two refills (~6 symbols) after it was issued
+    uint4 cur, nxt;                     // RAW 16-byte chunks: the one holding *wp and the one after it.  A chunk is fetched
+                                        // a whole chunk (about 12 symbols) before its first word is needed and the byte swap
+                                        // happens at consumption, so the lanes -- each streaming its own frame -- rarely wait
     int over;                           // words consumed past the end of the stream
+    __device__ __forceinline__ uint4 load_chunk(const uint4* c) const {
+        return (reinterpret_cast<const uint8_t*>(c) < send) ? __ldg(c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    // raw word at wp (zero past the end), then advance; rotates the chunks when the last word of `cur` goes
+    __device__ __forceinline__ uint32_t take() {
+        const uint32_t idx = (uint32_t)(reinterpret_cast<uintptr_t>(wp) >> 2) & 3u;
+        uint32_t raw = idx == 0u ? cur.x : (idx == 1u ? cur.y : (idx == 2u ? cur.z : cur.w));
+        if (wp >= wend) { raw = 0u; over++; }
+        wp++;
+        if (idx == 3u) { cur = nxt; nxt = load_chunk(reinterpret_cast<const uint4*>(wp) + 1); }
+        return raw;
+    }
     __device__ __forceinline__ void init(const uint8_t* base, uint64_t start, uint64_t slen) {
-        sbase = base;
+        sbase = base; send = base + slen;
         const uint8_t* p = base + start;
         const uintptr_t a = (uintptr_t)p;
         wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-        wend = reinterpret_cast<const uint32_t*>(((uintptr_t)(base + slen) + 3) & ~(uintptr_t)3);
+        wend = reinterpret_cast<const uint32_t*>(((uintptr_t)send + 3) & ~(uintptr_t)3);
         over = 0;
+        const uint4* c0 = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+        cur = load_chunk(c0); nxt = load_chunk(c0 + 1);
         const uint32_t skip = (uint32_t)(a & 3) * 8u;
-        uint32_t w = 0;
-        if (wp < wend) w = __byte_perm(__ldg(wp), 0, 0x0123);
-        wp++;
+        const uint32_t w = __byte_perm(take(), 0, 0x0123);
+        over = 0;                                                        // the first word is never "past the end" bookkeeping
         acc = ((uint64_t)w << 32) << skip;
         n = 32 - (int)skip;
-        next1 = 0; next2 = 0;
-        if (wp < wend) next1 = __ldg(wp);
-        if (wp + 1 < wend) next2 = __ldg(wp + 1);
         fill();
     }
-    // invariant after fill(): n >= 32 (n <= 32 before => exactly one word is added).  wp points at the word held in next1.
+    // invariant after fill(): n >= 32 (n <= 32 before => exactly one word is added)
     __device__ __forceinline__ void fill() {
         if (n <= 32) {
-            const uint32_t w = __byte_perm(next1, 0, 0x0123);
-            if (wp >= wend) over++;
-            wp++;
-            next1 = next2;
-            next2 = 0;
-            if (wp + 1 < wend) next2 = __ldg(wp + 1);
+            const uint32_t w = __byte_perm(take(), 0, 0x0123);
             acc |= (uint64_t)w << (32 - n);
             n += 32;
         }
