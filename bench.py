@@ -44,6 +44,10 @@ METRIC = "encode_msamples_per_s_level5"
 UNIT = "MSamples/s"
 
 
+# DRAM bytes per launch on the bench batch, from the committed ncu --set full capture (profiles/r01c_ncu_encode_kernels.txt)
+NCU_TRAFFIC_BYTES = {"autoc": 504219904 + 19234304, "analyze": 511988480 + 18227200, "pack": 501509120 + 264538624}
+
+
 def workload_config():
     return {"workload": "StreamEncoder: 256 parallel 48kHz stereo int16 streams x 10 s, blocksize=4096, level=5 (BASELINE configs[1]) per GPU",
             "n_streams_per_gpu": N_STREAMS, "samples_per_stream": N_SAMPLES, "channels": CHANNELS,
@@ -425,7 +429,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "profiles/r01c_ncu_encode_kernels.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch on this batch)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": kt_acc},
             "roofline_md5": {"bound": "hbm", "kernel": "md5_kernel (side stream, overlapped with the next batches)",
