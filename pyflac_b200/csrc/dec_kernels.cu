@@ -216,36 +216,37 @@ __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, u
 // 32-bit load that tops the 64-bit window up to >= 32 valid bits), so the 32 lanes of a warp -- each decoding its
 // own frame -- stay converged: a byte-wise refill loop entered by every lane at a different symbol would serialise.
 struct BitReader {
-    const uint32_t* __restrict__ wp;    // next aligned word to consume
-    const uint32_t* wend;               // first word past the stream (aligned up)
-    const uint8_t* sbase;               // stream start (for bit positions)
-    const uint8_t* send;                // one past the stream's last byte
+    const uint4* c16;                   // 16-byte aligned address at or below the first byte read
+    uint32_t wi;                        // next word to consume, counted from c16 (32-bit bookkeeping: no pointer compares in the loop)
+    uint32_t wend;                      // first word index past the stream (aligned up)
+    uint32_t nchunk;                    // chunks that may be loaded (those that start before the stream's end)
+    int64_t  off0;                      // byte offset of c16 relative to the stream start (for bit positions)
     uint64_t acc; int n;                // n valid bits at the top of acc
-    uint4 cur, nxt;                     // RAW 16-byte chunks: the one holding *wp and the one after it.  A chunk is fetched
+    uint4 cur, nxt;                     // RAW 16-byte chunks: the one holding word wi and the one after it.  A chunk is fetched
                                         // a whole chunk (about 12 symbols) before its first word is needed and the byte swap
                                         // happens at consumption, so the lanes -- each streaming its own frame -- rarely wait
     int over;                           // words consumed past the end of the stream
-    __device__ __forceinline__ uint4 load_chunk(const uint4* c) const {
-        return (reinterpret_cast<const uint8_t*>(c) < send) ? __ldg(c) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    // raw word at wp (zero past the end), then advance; rotates the chunks when the last word of `cur` goes
+    __device__ __forceinline__ uint4 load_chunk(uint32_t ci) const { return ci < nchunk ? __ldg(c16 + ci) : make_uint4(0u, 0u, 0u, 0u); }
+    // raw word wi (zero past the end), then advance; rotates the chunks when the last word of `cur` goes
     __device__ __forceinline__ uint32_t take() {
-        const uint32_t idx = (uint32_t)(reinterpret_cast<uintptr_t>(wp) >> 2) & 3u;
+        const uint32_t idx = wi & 3u;
         uint32_t raw = idx == 0u ? cur.x : (idx == 1u ? cur.y : (idx == 2u ? cur.z : cur.w));
-        if (wp >= wend) { raw = 0u; over++; }
-        wp++;
-        if (idx == 3u) { cur = nxt; nxt = load_chunk(reinterpret_cast<const uint4*>(wp) + 1); }
+        if (wi >= wend) { raw = 0u; over++; }
+        wi++;
+        if (idx == 3u) { cur = nxt; nxt = load_chunk((wi >> 2) + 1u); }
         return raw;
     }
     __device__ __forceinline__ void init(const uint8_t* base, uint64_t start, uint64_t slen) {
-        sbase = base; send = base + slen;
         const uint8_t* p = base + start;
-        const uintptr_t a = (uintptr_t)p;
-        wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-        wend = reinterpret_cast<const uint32_t*>(((uintptr_t)send + 3) & ~(uintptr_t)3);
+        const uintptr_t a = (uintptr_t)p, a16 = a & ~(uintptr_t)15;
+        c16 = reinterpret_cast<const uint4*>(a16);
+        off0 = (int64_t)a16 - (int64_t)(uintptr_t)base;
+        const uint64_t end_rel = (uint64_t)((int64_t)slen - off0);      // stream end relative to c16 (bytes)
+        wend = (uint32_t)((end_rel + 3u) >> 2);
+        nchunk = (uint32_t)((end_rel + 15u) >> 4);
+        wi = (uint32_t)((a - a16) >> 2);
         over = 0;
-        const uint4* c0 = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
-        cur = load_chunk(c0); nxt = load_chunk(c0 + 1);
+        cur = load_chunk(0u); nxt = load_chunk(1u);
         const uint32_t skip = (uint32_t)(a & 3) * 8u;
         const uint32_t w = __byte_perm(take(), 0, 0x0123);
         over = 0;                                                        // the first word is never "past the end" bookkeeping
@@ -290,7 +291,7 @@ struct BitReader {
         return q;
     }
     // bit offset (from the stream start) of the next unread bit
-    __device__ __forceinline__ uint64_t bit_position() const { return (uint64_t)((const uint8_t*)wp - sbase) * 8ull - (uint64_t)n; }
+    __device__ __forceinline__ uint64_t bit_position() const { return (uint64_t)((int64_t)wi * 4 + off0) * 8ull - (uint64_t)n; }
 };
 
 
@@ -444,8 +445,20 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
                 int32_t r;
                 if (k == pesc) r = br.get_signed(raw);
                 else {
-                    const uint32_t qv = br.unary();
-                    const uint32_t u = (qv << k) | br.get(k);
+                    // common case: the whole code (unary zeros, stop bit, k low bits) lies in the 32 valid bits at the top of the
+                    // window -- one refill check and one extraction per sample; anything longer takes the generic path
+                    br.fill();
+                    const uint32_t hi32 = (uint32_t)(br.acc >> 32);
+                    const uint32_t z = (uint32_t)__clz((int)hi32);
+                    uint32_t u;
+                    if (hi32 != 0u && z + 1u + k <= 32u) {
+                        const uint32_t rem = k ? ((uint32_t)((br.acc << (z + 1u)) >> 32) >> (32u - k)) : 0u;
+                        u = (z << k) | rem;
+                        br.acc <<= (z + 1u + k); br.n -= (int)(z + 1u + k);
+                    } else {
+                        const uint32_t qv = br.unary();
+                        u = (qv << k) | br.get(k);
+                    }
                     r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1u);
                 }
                 int32_t v;
