@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <functional>
 #include <vector>
 
 #include "../../include/flacb200.h"
@@ -28,6 +29,8 @@ void launch_dec_frames(const uint8_t*, const uint64_t*, const uint64_t*, DecCand
 void launch_dec_chain(DecCand*, const uint32_t*, const DecStreamMeta*, const uint64_t*, int, DecStreamResult*, uint32_t*, cudaStream_t);
 void launch_dec_assign(DecStreamResult*, const uint64_t*, int, cudaStream_t);
 void launch_dec_post(const uint8_t*, const uint64_t*, DecCand*, int, const uint64_t*, const int32_t*, DecStreamResult*, void*, int, cudaStream_t);
+void launch_dec_cand_first(const uint32_t*, const uint32_t*, int, int, const uint64_t*, uint32_t*, cudaStream_t);
+void launch_dec_mirror(const void*, void*, size_t, cudaStream_t);
 }
 using namespace fb;
 
@@ -48,7 +51,11 @@ struct Buf {
 };
 
 struct DecState {
-    Buf blob, soff, slen, meta, segs, segcount, segbase, cands, sizes, slotoff, samples, candfirst, res, ss32, pcmoff, pcm, total;
+    Buf blob, soff, slen, meta, segs, segcount, segbase, cands, sizes, slotoff, samples, candfirst, res, ss32, pcmoff, pcm, total, firstseg;
+    // readbacks go through mapped pinned memory written by tiny kernels: a D2H memcpy would queue on the copy engine behind
+    // the bulk PCM transfer of the previous chunk (flacb200_decode_batch_host)
+    uint64_t* m_total = nullptr;            // [0] scan total
+    unsigned char* m_res = nullptr; size_t m_res_cap = 0;
     std::vector<DecSegment> h_segs;
     std::vector<uint32_t> h_first_seg;      // first segment of each stream (+1 sentinel)
     int n_streams = 0, n_cands = 0;
@@ -69,7 +76,9 @@ struct DecState {
 void dec_free(void* p) {
     DecState* d = (DecState*)p;
     Buf* bufs[] = {&d->blob, &d->soff, &d->slen, &d->meta, &d->segs, &d->segcount, &d->segbase, &d->cands, &d->sizes, &d->slotoff, &d->samples,
-                   &d->candfirst, &d->res, &d->ss32, &d->pcmoff, &d->pcm, &d->total};
+                   &d->candfirst, &d->res, &d->ss32, &d->pcmoff, &d->pcm, &d->total, &d->firstseg};
+    if (d->m_total) cudaFreeHost(d->m_total);
+    if (d->m_res) cudaFreeHost(d->m_res);
     for (Buf* b : bufs) b->release();
     d->hblob.release();
     for (auto& e : d->ev) if (e) cudaEventDestroy(e);
@@ -96,7 +105,8 @@ DecState* state(flacb200_ctx* ctx, int which = 0) {
 #define CKD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fb_ctx_fail(ctx, FLACB200_ERR_CUDA, #call, e_); } while (0)
 
 static int decode_core(flacb200_ctx* ctx, DecState* d, cudaStream_t st, const uint8_t* d_blob, int ns, const uint64_t* stream_off,
-                       const uint64_t* stream_len, uint32_t out_container_bytes, const flacb200_dec_raw_params* raw);
+                       const uint64_t* stream_len, uint32_t out_container_bytes, const flacb200_dec_raw_params* raw,
+                       const std::function<int()>* after_uploads = nullptr);
 
 extern "C" int flacb200_decode_batch(flacb200_ctx* ctx, const uint8_t* blob, int blob_is_device, uint64_t blob_bytes,
                                      uint32_t n_streams, const uint64_t* stream_off, const uint64_t* stream_len,
@@ -125,7 +135,8 @@ extern "C" int flacb200_decode_batch(flacb200_ctx* ctx, const uint8_t* blob, int
 
 // One decode pass over streams whose bytes are already in HBM (d_blob + stream_off[s]).
 static int decode_core(flacb200_ctx* ctx, DecState* d, cudaStream_t st, const uint8_t* d_blob, int ns, const uint64_t* stream_off,
-                       const uint64_t* stream_len, uint32_t out_container_bytes, const flacb200_dec_raw_params* raw) {
+                       const uint64_t* stream_len, uint32_t out_container_bytes, const flacb200_dec_raw_params* raw,
+                       const std::function<int()>* after_uploads) {
     d->have = false;
     // segments: every stream is cut into 4096-byte pieces scanned by one warp each
     d->h_segs.clear(); d->h_first_seg.assign(ns + 1, 0);
@@ -149,9 +160,21 @@ static int decode_core(flacb200_ctx* ctx, DecState* d, cudaStream_t st, const ui
     CKD(d->candfirst.reserve(4 * (size_t)(ns + 2)));
     CKD(d->res.reserve(sizeof(DecStreamResult) * (size_t)ns)); CKD(d->ss32.reserve(4 * (size_t)(ns + 1)));
     CKD(d->pcmoff.reserve(8 * (size_t)(ns + 1))); CKD(d->total.reserve(64));
+    if (!d->m_total) CKD(cudaHostAlloc((void**)&d->m_total, 64, cudaHostAllocMapped));
+    if (d->m_res_cap < sizeof(DecStreamResult) * (size_t)ns) {
+        if (d->m_res) cudaFreeHost(d->m_res);
+        d->m_res = nullptr; d->m_res_cap = 0;
+        const size_t want = sizeof(DecStreamResult) * (size_t)ns * 2 + 256;
+        CKD(cudaHostAlloc((void**)&d->m_res, want, cudaHostAllocMapped));
+        d->m_res_cap = want;
+    }
+    CKD(d->firstseg.reserve(4 * (size_t)(ns + 2)));
+    CKD(cudaMemcpyAsync(d->firstseg.p, d->h_first_seg.data(), 4 * (size_t)(ns + 1), cudaMemcpyHostToDevice, st));
     CKD(cudaMemcpyAsync(d->soff.p, stream_off, 8 * (size_t)ns, cudaMemcpyHostToDevice, st));
     CKD(cudaMemcpyAsync(d->slen.p, stream_len, 8 * (size_t)ns, cudaMemcpyHostToDevice, st));
     if (nsegs) CKD(cudaMemcpyAsync(d->segs.p, d->h_segs.data(), sizeof(DecSegment) * (size_t)nsegs, cudaMemcpyHostToDevice, st));
+    // the last H2D copies of this pass are in the queue: the pipelined host path now submits the next chunk's bytes
+    if (after_uploads) { const int rcu = (*after_uploads)(); if (rcu) return rcu; }
 
     DecStreamMeta rawp; memset(&rawp, 0, sizeof rawp);
     if (raw) { rawp.sample_rate = raw->sample_rate; rawp.channels = raw->channels; rawp.bps = raw->bits_per_sample; }
@@ -162,8 +185,9 @@ static int decode_core(flacb200_ctx* ctx, DecState* d, cudaStream_t st, const ui
         launch_dec_sync(d_blob, (const uint64_t*)d->soff.p, (const uint64_t*)d->slen.p, (const DecStreamMeta*)d->meta.p, (const DecSegment*)d->segs.p, nsegs, 0,
                         (uint32_t*)d->segcount.p, nullptr, nullptr, st);
         launch_dec_scan((const uint32_t*)d->segcount.p, nsegs, (uint32_t*)d->segbase.p, nullptr, (uint64_t*)d->total.p, st);
-        CKD(cudaMemcpyAsync(&h_total, d->total.p, 8, cudaMemcpyDeviceToHost, st));
+        launch_dec_mirror(d->total.p, d->m_total, 8, st);
         CKD(cudaStreamSynchronize(st));                                  // sync #1: number of candidates
+        h_total = d->m_total[0];
     }
     const int nc = (int)h_total;
     d->n_cands = nc;
@@ -172,24 +196,16 @@ static int decode_core(flacb200_ctx* ctx, DecState* d, cudaStream_t st, const ui
     if (nsegs && nc)
         launch_dec_sync(d_blob, (const uint64_t*)d->soff.p, (const uint64_t*)d->slen.p, (const DecStreamMeta*)d->meta.p, (const DecSegment*)d->segs.p, nsegs, 1,
                         (uint32_t*)d->segcount.p, (const uint32_t*)d->segbase.p, (DecCand*)d->cands.p, st);
-    // first candidate of each stream = scan value at the stream's first segment (+ sentinel = nc)
-    {
-        std::vector<uint32_t> h_base((size_t)nsegs + 1, 0);
-        if (nsegs) CKD(cudaMemcpyAsync(h_base.data(), d->segbase.p, 4 * (size_t)nsegs, cudaMemcpyDeviceToHost, st));
-        CKD(cudaStreamSynchronize(st));
-        h_base[nsegs] = (uint32_t)nc;
-        std::vector<uint32_t> cf(ns + 1);
-        for (int s = 0; s <= ns; s++) cf[s] = h_base[d->h_first_seg[s]];
-        CKD(cudaMemcpyAsync(d->candfirst.p, cf.data(), 4 * (size_t)(ns + 1), cudaMemcpyHostToDevice, st));
-        CKD(cudaStreamSynchronize(st));
-    }
+    // first candidate of each stream = scan value at the stream's first segment (+ sentinel = nc), computed on the device
+    launch_dec_cand_first((const uint32_t*)d->segbase.p, (const uint32_t*)d->firstseg.p, ns, nsegs, (const uint64_t*)d->total.p, (uint32_t*)d->candfirst.p, st);
     CKD(cudaEventRecord(d->ev[1], st));
     uint64_t h_slots = 0;
     if (nc) {
         launch_dec_cand_size((const DecCand*)d->cands.p, nc, (uint32_t*)d->sizes.p, st);
         launch_dec_scan((const uint32_t*)d->sizes.p, nc, nullptr, (uint64_t*)d->slotoff.p, (uint64_t*)d->total.p, st);
-        CKD(cudaMemcpyAsync(&h_slots, d->total.p, 8, cudaMemcpyDeviceToHost, st));
+        launch_dec_mirror(d->total.p, d->m_total, 8, st);
         CKD(cudaStreamSynchronize(st));                                  // sync #2: scratch size for candidate samples
+        h_slots = d->m_total[0];
         CKD(d->samples.reserve(4 * (size_t)(h_slots + 16)));
         launch_dec_frames(d_blob, (const uint64_t*)d->soff.p, (const uint64_t*)d->slen.p, (DecCand*)d->cands.p, nc, (const uint64_t*)d->slotoff.p, (int32_t*)d->samples.p, st);
     }
@@ -200,9 +216,11 @@ static int decode_core(flacb200_ctx* ctx, DecState* d, cudaStream_t st, const ui
     launch_dec_assign((DecStreamResult*)d->res.p, (const uint64_t*)d->pcmoff.p, ns, st);
     d->h_res.resize(ns);
     uint64_t h_elems = 0;
-    CKD(cudaMemcpyAsync(&h_elems, d->total.p, 8, cudaMemcpyDeviceToHost, st));
-    CKD(cudaMemcpyAsync(d->h_res.data(), d->res.p, sizeof(DecStreamResult) * (size_t)ns, cudaMemcpyDeviceToHost, st));
+    launch_dec_mirror(d->total.p, d->m_total, 8, st);
+    launch_dec_mirror(d->res.p, d->m_res, sizeof(DecStreamResult) * (size_t)ns, st);
     CKD(cudaStreamSynchronize(st));                                      // sync #3: PCM size
+    h_elems = d->m_total[0];
+    memcpy(d->h_res.data(), d->m_res, sizeof(DecStreamResult) * (size_t)ns);
     uint32_t ob = out_container_bytes;
     if (ob == 0) { ob = 2; for (int s = 0; s < ns; s++) if (d->h_res[s].bps > 16) ob = 4; }
     for (int s = 0; s < ns; s++) if (ob == 2 && d->h_res[s].bps > 16 && d->h_res[s].n_frames) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "int16 output requested for a >16-bit stream", cudaSuccess);
@@ -291,11 +309,10 @@ extern "C" int flacb200_decode_batch_host(flacb200_ctx* ctx, const uint8_t* blob
         d->pcm_busy = false; d->have = false;
     }
     // chunks of whole streams with about equal byte counts
-    // One chunk by default.  Measured on B200: the decode pipeline of a chunk issues small H2D / D2H copies (segment tables,
-    // candidate counts, per-stream results) that queue on the same copy engines BEHIND the big blob / PCM transfers of the
-    // neighbouring chunks, so chunks serialise instead of overlapping (6 chunks: 97 ms, 1 chunk: 84 ms for 1.26 GB in /
-    // 2.15 GB out); and a launch cannot finish faster than one frame's serial decode.  FLACB200_DEC_CHUNKS overrides.
-    int nchunks = 1;
+    // Chunks must still fill the GPU (the frame kernel decodes one frame per thread and a launch cannot finish faster than
+    // one frame's serial decode, a few ms): one chunk per ~300 MB of FLAC.  All table uploads of a chunk are submitted before
+    // the next chunk's bytes and every readback goes through mapped memory, so the bulk copies never delay the small ones.
+    int nchunks = (int)(blob_bytes / (300ull << 20));
     if (const char* ev = getenv("FLACB200_DEC_CHUNKS")) { const int v = atoi(ev); if (v > 0) nchunks = v; }
     if (nchunks < 1) nchunks = 1;
     if (nchunks > 12) nchunks = 12;
@@ -313,7 +330,9 @@ extern "C" int flacb200_decode_batch_host(flacb200_ctx* ctx, const uint8_t* blob
     CKD(cudaMemsetAsync(d_blob + blob_bytes, 0, 16, d0->h2d));
     bool monotonic = true;
     for (int s = 1; s < ns; s++) if (stream_off[s] < stream_off[s - 1] + stream_len[s - 1]) { monotonic = false; break; }
-    for (int c = 0; c < nchunks; c++) {
+    // blob chunk c+1 is enqueued right before chunk c is decoded: the copy engine runs in submission order, so chunk c's
+    // small table uploads (issued inside decode_core) only wait for transfers they need anyway
+    auto enqueue_blob = [&](int c) -> int {
         const int s0 = cs[c], s1 = cs[c + 1];
         if (s1 > s0) {
             if (monotonic) {
@@ -324,7 +343,9 @@ extern "C" int flacb200_decode_batch_host(flacb200_ctx* ctx, const uint8_t* blob
             }
         }
         CKD(cudaEventRecord(d0->ev_h2d[c], d0->h2d));
-    }
+        return 0;
+    };
+    { const int rc0 = enqueue_blob(0); if (rc0) return rc0; }
     uint64_t elem_base = 0;
     int status = 0;
     for (int c = 0; c < nchunks; c++) {
@@ -332,12 +353,13 @@ extern "C" int flacb200_decode_batch_host(flacb200_ctx* ctx, const uint8_t* blob
         if (s1 <= s0) continue;
         DecState* d = D[c & 1];
         CKD(cudaStreamWaitEvent(st, d0->ev_h2d[c], 0));
+        const std::function<int()> next_blob = [&]() -> int { return (c + 1 < nchunks) ? enqueue_blob(c + 1) : 0; };
         if (d->pcm_busy) { CKD(cudaStreamWaitEvent(st, d->ev_pcm_free, 0)); d->pcm_busy = false; }     // its previous PCM must have left
-        const int rc = decode_core(ctx, d, st, d_blob, s1 - s0, stream_off + s0, stream_len + s0, out_container_bytes, raw);
+        const int rc = decode_core(ctx, d, st, d_blob, s1 - s0, stream_off + s0, stream_len + s0, out_container_bytes, raw, &next_blob);
         if (rc) { status = rc; break; }
         CKD(cudaEventRecord(d->ev_post, st));
         // per-stream results of the chunk (post may flag CRC errors: read them after it)
-        CKD(cudaMemcpyAsync(d->h_res.data(), d->res.p, sizeof(DecStreamResult) * (size_t)(s1 - s0), cudaMemcpyDeviceToHost, st));
+        launch_dec_mirror(d->res.p, d->m_res, sizeof(DecStreamResult) * (size_t)(s1 - s0), st);
         const size_t bytes = (size_t)d->total_elems * out_container_bytes;
         if ((elem_base + d->total_elems) * out_container_bytes > pcm_cap) { status = fb_ctx_fail(ctx, FLACB200_ERR_ARG, "pcm buffer too small", cudaSuccess); break; }
         CKD(cudaStreamWaitEvent(d0->d2h, d->ev_post, 0));
@@ -345,6 +367,7 @@ extern "C" int flacb200_decode_batch_host(flacb200_ctx* ctx, const uint8_t* blob
         CKD(cudaEventRecord(d->ev_pcm_free, d0->d2h));
         d->pcm_busy = true;
         CKD(cudaStreamSynchronize(st));
+        memcpy(d->h_res.data(), d->m_res, sizeof(DecStreamResult) * (size_t)(s1 - s0));
         if (streams) {
             for (int s = s0; s < s1; s++) {
                 const DecStreamResult& h = d->h_res[s - s0];

@@ -600,6 +600,20 @@ dec_post_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ s
     }
 }
 
+// first candidate of every stream = scan value at the stream's first segment (sentinel: all candidates)
+__global__ void dec_cand_first_kernel(const uint32_t* __restrict__ seg_base, const uint32_t* __restrict__ first_seg, int n_streams, int n_segs,
+                                      const uint64_t* __restrict__ total, uint32_t* __restrict__ cand_first) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_streams) return;
+    const uint32_t fs = first_seg[s];
+    cand_first[s] = (s < n_streams && (int)fs < n_segs) ? seg_base[fs] : (uint32_t)*total;
+}
+// copy a few words to mapped host memory (readbacks that must not queue behind bulk D2H copies on the copy engine)
+__global__ void dec_mirror_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int n_words) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_words) dst[i] = src[i];
+}
+
 // ------------------------------------------------------------------ launchers ----
 void launch_dec_meta(const uint8_t* blob, const uint64_t* soff, const uint64_t* slen, int ns, int raw, const DecStreamMeta& rawp, DecStreamMeta* meta, cudaStream_t st) {
     dec_meta_kernel<<<(ns + 127) / 128, 128, 0, st>>>(blob, soff, slen, ns, raw, rawp, meta);
@@ -622,6 +636,13 @@ void launch_dec_chain(DecCand* cands, const uint32_t* cand_first, const DecStrea
 }
 void launch_dec_assign(DecStreamResult* res, const uint64_t* pcm_off, int ns, cudaStream_t st) {
     dec_assign_kernel<<<(ns + 127) / 128, 128, 0, st>>>(res, pcm_off, ns);
+}
+void launch_dec_cand_first(const uint32_t* seg_base, const uint32_t* first_seg, int ns, int nsegs, const uint64_t* total, uint32_t* cand_first, cudaStream_t st) {
+    dec_cand_first_kernel<<<(ns + 1 + 127) / 128, 128, 0, st>>>(seg_base, first_seg, ns, nsegs, total, cand_first);
+}
+void launch_dec_mirror(const void* src, void* dst, size_t bytes, cudaStream_t st) {
+    const int n = (int)((bytes + 3) / 4);
+    if (n) dec_mirror_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, n);
 }
 void launch_dec_post(const uint8_t* blob, const uint64_t* soff, DecCand* cands, int n, const uint64_t* slot_off, const int32_t* samples, DecStreamResult* res,
                      void* pcm_out, int out_bytes, cudaStream_t st) {

@@ -625,7 +625,7 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
 
     // ---- shared memory carve-up (sizes mirrored by analyze_smem_bytes) ----
     const int sig_words = (int)P.an_stride;                                // words per staged signal (or per packed frame)
-    const int n_steps = (int)P.ac_gsz;                                     // apodization steps per signal
+    const int n_steps = (int)P.apod_steps;                                     // apodization steps per signal
     const int nwin = (int)(P.apod_parts * (P.apod_parts + 1) / 2);
     int32_t* xall = reinterpret_cast<int32_t*>(smem_raw);
     unsigned char* cur = smem_raw + (size_t)(PACKED ? 1 : nsig) * sig_words * 4;
@@ -1006,11 +1006,10 @@ int launch_analyze(const void* pcm, const FrameDesc* frames, const float* window
     return 1 + (P.max_lpc_order > 0 ? 1 : 0) + (P.loose_frames ? 2 : 1);
 }
 
-// Shared-memory plan of the analysis kernel; fills P.ac_gsz (apodization steps per signal) and P.an_stride (staged
+// Shared-memory plan of the analysis kernel; fills P.apod_steps (apodization steps per signal) and P.an_stride (staged
 // words per signal).  Called by the host before launching.
 void analyze_layout(EncParams& P) {
-    P.pool_bytes = 0;
-    P.ac_gsz = apod_steps(P);
+    P.apod_steps = apod_steps(P);
     // 32 rows of ceil(N/32) samples with an odd row stride
     const uint32_t b0 = (P.blocksize + 31) / 32, rs = b0 | 1u;
     P.an_stride = ((32u * rs + 3u) / 4u) * 4u;
@@ -1020,7 +1019,7 @@ size_t analyze_smem_bytes(const EncParams& P) {
     const size_t nsig = P.n_signals;
     return (size_t)(packed_layout(P) ? 1 : nsig) * P.an_stride * 4 + (size_t)kAnWarps * sizeof(WarpScratch) +
            (size_t)kAnWarps * 2 * kMaxParts * 8 + nsig * sizeof(SubframePlan) +
-           nsig * P.ac_gsz * sizeof(SubframePlan) + sizeof(AnShared) + 64;
+           nsig * P.apod_steps * sizeof(SubframePlan) + sizeof(AnShared) + 64;
 }
 
 }  // namespace fb

@@ -33,8 +33,8 @@ struct EncParams {
     uint32_t container_bytes;    // 2 = int16 samples in HBM, 4 = int32
     uint32_t n_signals;          // channels (+2 when do_mid_side)
     uint32_t smem_stride;        // int32 words reserved per signal in shared memory (>= max blocksize, multiple of 4)
-    uint32_t pool_bytes;         // analysis kernel: partition-sum area aliased with the autocorrelation rings
-    uint32_t ac_gsz;             // analysis kernel: (signal, window) jobs packed per warp in the autocorrelation phase
+    uint32_t apod_steps;         // analysis kernel: LPC candidates per signal = steps of libFLAC's apodization walk (1, 3 or 9)
+    uint32_t reserved0;
     uint32_t an_stride;          // analysis kernel: int32 words staged per signal (32 padded rows)
     uint32_t loose_frames;       // loose mid/side (levels 1, 4 on stereo): a full L/R/M/S decision every this many frames; 0 = off
     uint32_t limit_min_bitrate;  // up: process_subframes_ -- never emit a frame made of constant subframes only
