@@ -463,8 +463,11 @@ __device__ __forceinline__ void ac_finish(float (&dv)[kAcJobsMax], const AcRaw& 
     }
 }
 
+#ifndef FB_AC_MIN_CTAS
+#define FB_AC_MIN_CTAS 6      // measured: 85 registers (no spills) at 24 warps/SM beats 64 registers at 32 warps/SM by ~6 %
+#endif
 template <typename PcmT, bool PACKED>
-__global__ void __launch_bounds__(kAcThreads, 8)
+__global__ void __launch_bounds__(kAcThreads, FB_AC_MIN_CTAS)
 autoc_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, int n_frames, const float* __restrict__ windows,
              EncParams P, unsigned char* __restrict__ work, size_t work_stride, int lanes_per_job, int jobs_per_warp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -594,8 +597,11 @@ struct AnShared {
     int32_t  fixed_q[kAnWarps][4];                   // binomial coefficients of the fixed candidate a warp is evaluating
 };
 
+#ifndef FB_AN_MIN_CTAS
+#define FB_AN_MIN_CTAS 8
+#endif
 template <typename PcmT, bool PACKED>
-__global__ void __launch_bounds__(kAnThreads, PACKED ? 8 : 3)
+__global__ void __launch_bounds__(kAnThreads, PACKED ? FB_AN_MIN_CTAS : 3)
 analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, const float* __restrict__ windows,
                EncParams P, SubframePlan* __restrict__ plans, uint8_t* __restrict__ frame_ca,
                SignalDebug* __restrict__ dbg, EncStats* __restrict__ stats, int pass,
