@@ -48,6 +48,7 @@ enum SigKind : int { kLo16 = 0, kHi16 = 1, kMid16 = 2, kSide16 = 3, kPlain = 4 }
 struct SigView {
     const int32_t* base;     // packed: the frame's words; plain: the signal's own row block (wasted bits already removed)
     int ca, cb, sh;
+    int cab;                 // packed: (ca & 0xff) | (cb & 0xff) << 8 for the dot-product instruction
     // 33-bit side channel of 32-bit stereo (no wasted bits): derived from the left (base) and right (base2) rows,
     // value = (left << shl) - (right << shr) in 64-bit arithmetic (the rows hold the channels without THEIR wasted bits)
     const int32_t* base2;
@@ -69,8 +70,8 @@ __device__ __forceinline__ int pidx(const FrameGeo& G, int i) {
 template <bool PACKED>
 __device__ __forceinline__ int sig_word(int w, const SigView& V) {
     if constexpr (PACKED) {
-        const int lo = (int)(short)w, hi = w >> 16;
-        return (lo * V.ca + hi * V.cb) >> V.sh;
+        // one IDP.2A: (low half) * ca + (high half) * cb, the two int16 halves of w against the two int8 coefficients
+        return __dp2a_lo(w, V.cab, 0) >> V.sh;
     } else {
         return w;
     }
@@ -688,8 +689,8 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
     auto sig_sbps = [&](int s) { return (int)P.bps - sig_wasted(s) + ((P.do_mid_side && s == ch + 1) ? 1 : 0); };
     auto sig_view = [&](int s) {
         SigView V;
-        V.base2 = nullptr; V.shl = 0; V.shr = 0; V.s33 = 0;
-        if (PACKED) { V.base = xall; V.ca = (s != 1); V.cb = (s == 0) ? 0 : (s == 3 ? -1 : 1); V.sh = sig_wasted(s) + (s == 2 ? 1 : 0); }
+        V.base2 = nullptr; V.shl = 0; V.shr = 0; V.s33 = 0; V.cab = 1;
+        if (PACKED) { V.base = xall; V.ca = (s != 1); V.cb = (s == 0) ? 0 : (s == 3 ? -1 : 1); V.sh = sig_wasted(s) + (s == 2 ? 1 : 0); V.cab = (V.ca & 0xff) | ((V.cb & 0xff) << 8); }
         else {
             V.base = xall + (size_t)s * sig_words; V.ca = 1; V.cb = 0; V.sh = 0;
             if (P.bps == 32 && P.do_mid_side && s == ch + 1 && sig_wasted(s) == 0) {      // 33-bit side: read through the left / right rows
