@@ -95,6 +95,36 @@ def test_oracle_vs_reference_binary_edges(checkers):
 
 
 @needs_ref
+def test_oracle_vs_reference_binary_32bit(checkers):
+    """32-bit input: the _limit_residual predictor search as the shipped binary runs it (all-zero block CONSTANT, other
+    constant blocks FIXED order 1, invalid orders when a residual leaves int32) and the 33-bit side channel of stereo
+    (all-zero side reports one wasted bit).  Lengths 0 or 1 mod 4."""
+    if not checkers.ref_available():
+        pytest.skip("oracle/_ref not present")
+    from pyflac_b200.synth import music_like
+    rng = np.random.default_rng(12)
+    n = 4096 + 400
+    m = music_like(n, 2, 48000, 24, seed=6).astype(np.int64)
+    L, R = m[:, 0] * 200, m[:, 1] * 180
+    spikes = L.copy(); spikes[rng.integers(0, n, 4)] = -2**31
+    mono = {"zeros": np.zeros(n, np.int64), "dc_odd": np.full(n, 7654321), "dc_min": np.full(n, -2**31), "music": L, "shl8": m[:, 0] * 256,
+            "noise": rng.integers(-2**31, 2**31, n), "spikes": spikes, "minmax": np.where(np.arange(n) % 2 == 0, -2**31, 2**31 - 1)}
+    def c32(a):
+        return np.clip(a, -2**31, 2**31 - 1).astype(np.int32)
+    for name, v in mono.items():
+        x = c32(v)[:, None]
+        for level in (0, 5, 8):
+            assert checkers.oracle_encode(x, 48000, 32, level, 0) == checkers.ref_encode(x, 48000, 32, level, 0), (name, level)
+    stereo = {"same": (L, L), "anti": (L, -L), "anti_noisy": (L, -L + rng.integers(-3, 4, n)), "indep": (L, R), "rails": (np.full(n, 2**31 - 1), np.full(n, -2**31)),
+              "noise": (rng.integers(-2**31, 2**31, n), rng.integers(-2**31, 2**31, n)), "near": (L, L + rng.integers(-500, 500, n))}
+    for name, (a, b) in stereo.items():
+        x = c32(np.stack([a, b], axis=1))
+        for level in (1, 3, 5, 8):
+            assert checkers.oracle_encode(x, 44100, 32, level, 1152 if level == 1 else 0) == checkers.ref_encode(x, 44100, 32, level, 1152 if level == 1 else 0), (name, level)
+        dec, _ = checkers.oracle_decode(checkers.ref_encode(x, 44100, 32, 5, 0))
+        assert np.array_equal(dec, x)
+
+
 def test_init_status_matches_reference(checkers):
     """Init validation order (reference tests/test_encoder.py:139-164,202-207)."""
     import ctypes as C
