@@ -44,8 +44,8 @@ METRIC = "encode_msamples_per_s_level5"
 UNIT = "MSamples/s"
 
 
-# DRAM bytes per launch on the bench batch, from the committed ncu --set full capture (profiles/r01c_ncu_encode_kernels.txt)
-NCU_TRAFFIC_BYTES = {"autoc": 504219904 + 19234304, "analyze": 511988480 + 18227200, "pack": 501509120 + 264538624}
+# DRAM bytes per launch on the bench batch, from the committed ncu --set full capture (profiles/r01d_ncu_encode_kernels.txt)
+NCU_TRAFFIC_BYTES = {"autoc": 499152384 + 13786880, "analyze": 512133120 + 18882560, "pack": 502199552 + 264583168}
 
 
 def workload_config():
@@ -429,7 +429,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "profiles/r01c_ncu_encode_kernels.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch on this batch)",
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "profiles/r01d_ncu_encode_kernels.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch on this batch)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": kt_acc},

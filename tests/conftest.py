@@ -34,3 +34,23 @@ def load_golden(case):
     with open(os.path.join(g, case["name"] + ".flac"), "rb") as f:
         flac = f.read()
     return x, flac
+
+
+def fixture_cases():
+    """pyFLAC's own tests/data/*.flac (imported by tests/golden/make_fixtures.py)."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "fixtures", "fixtures.json")) as f:
+        return json.load(f)["cases"]
+
+
+def fixture_path(name):
+    return os.path.join(ROOT, "tests", "golden", "fixtures", name)
+
+
+def pcm_md5(x, bps):
+    """MD5 the way STREAMINFO defines it: interleaved little-endian samples of (bps+7)/8 bytes."""
+    import hashlib
+    import numpy as np
+    w = (bps + 7) // 8
+    raw = np.ascontiguousarray(np.asarray(x).astype("<i4")).view(np.uint8).reshape(-1, 4)
+    return hashlib.md5(np.ascontiguousarray(raw[:, :w]).tobytes()).hexdigest()

@@ -146,6 +146,23 @@ def test_init_status_matches_reference(checkers):
             assert (got == 0) == (r >= 0), (p, subset, got, r)
 
 
+def test_oracle_on_imported_reference_fixtures(checkers):
+    """The committed copies of pyFLAC's tests/data/*.flac (tests/golden/fixtures): the oracle's decode hashes to the
+    STREAMINFO MD5 == MD5 of the matching .wav, and its level-5 encode of that PCM is the file the bundled libFLAC wrote."""
+    from conftest import fixture_cases, fixture_path, pcm_md5
+    for c in fixture_cases():
+        data = open(fixture_path(c["name"] + ".flac"), "rb").read()
+        assert len(data) == c["flac_bytes"] and data[26:42].hex() == c["streaminfo_md5"]
+        pcm, info = checkers.oracle_decode(data)
+        assert pcm.shape == (c["samples"], c["channels"]) and info["bps"] == c["bps"] and info["sample_rate"] == c["sample_rate"]
+        assert pcm_md5(pcm, c["bps"]) == c["streaminfo_md5"] == c["pcm_md5"]
+        if c["level5"]:
+            assert c["wav_md5"] == c["pcm_md5"]
+            want = open(fixture_path(c["level5"]["file"]), "rb").read()
+            x = pcm.astype(np.int16 if c["bps"] <= 16 else np.int32)
+            assert checkers.oracle_encode(x, c["sample_rate"], c["bps"], 5, 0) == want, c["name"]
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/tests/data"), reason="reference fixtures not present")
 def test_oracle_decodes_reference_fixtures(checkers):
     """tests/data/{mono,stereo,surround,32bit}.flac <-> .wav pairs: STREAMINFO MD5 == MD5 of decoded PCM."""
