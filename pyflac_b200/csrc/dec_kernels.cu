@@ -125,59 +125,82 @@ dec_sync_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ s
     const DecStreamMeta m = meta[sg.stream];
     const uint8_t* sbase = blob + stream_off[sg.stream];
     const uint64_t slen = stream_len[sg.stream];
+    if (pass && seg_count[seg] == 0u) return;                                       // nothing to write for this segment
     uint32_t count = 0;
     const uint32_t out0 = pass ? seg_base[seg] : 0u;
     if (m.status == kDecOk) {
         const uint8_t* seg_lo = sbase + sg.start;                                   // first byte of the segment
-        const uint8_t* seg_hi = seg_lo + sg.bytes;                                  // one past its last byte
-        const uint8_t* s_end = sbase + slen;
         const uint8_t* a0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(seg_lo) & ~(uintptr_t)15);
-        for (const uint8_t* base = a0; base < seg_hi; base += 512) {
-            const uint8_t* p = base + 16 * lane;
-            uint32_t hits = 0;                                                      // bit k: candidate sync code at p + k
-            if (p < seg_hi && p + 16 > seg_lo) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-                const uint32_t nb = (p + 16 < s_end) ? (uint32_t)__ldg(p + 16) : 0u;   // first byte of the next chunk
-                const uint32_t w[5] = {v.x, v.y, v.z, v.w, nb};
+        // 32-bit offsets relative to seg_lo keep the per-row bookkeeping short (the scan is instruction bound, not HBM bound)
+        const int nbytes = (int)sg.bytes;                                           // segment = [0, nbytes)
+        const uint64_t end64 = slen - sg.start;
+        const int end_rel = end64 > 0x7fffffffull ? 0x7fffffff : (int)end64;        // stream end
+        const uint64_t first64 = m.first_frame > sg.start ? m.first_frame - sg.start : 0ull;
+        const int first_rel = first64 > 0x7fffffffull ? 0x7fffffff : (int)first64;
+        const int row0 = (int)(a0 - seg_lo) + 16 * lane;                            // this lane's chunk in row 0 (-15 .. 496)
+        // four 512-byte rows per trip, all loads issued before any is looked at
+        for (int rb = 0; rb + row0 - 16 * lane < nbytes; rb += 2048) {
+            uint4 v[4]; uint32_t nb31[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int rel = row0 + rb + 512 * u;
+                // a chunk is needed when it overlaps the segment or supplies the byte after the segment's last one
+                const bool need = rel + 16 > 0 && rel < nbytes + 16 && rel < end_rel;
+                v[u] = need ? __ldg(reinterpret_cast<const uint4*>(seg_lo + rel)) : make_uint4(0u, 0u, 0u, 0u);
+                nb31[u] = (lane == 31 && rel < nbytes && rel + 16 < end_rel) ? (uint32_t)__ldg(seg_lo + rel + 16) : 0u;   // first byte of the next row
+            }
+            uint32_t hits[4];                                                       // bit k: 0xFF then 0xF8/0xF9 at byte k of the chunk
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                uint32_t nb = __shfl_down_sync(0xffffffffu, v[u].x & 0xffu, 1);      // first byte of the next lane's chunk
+                if (lane == 31) nb = nb31[u];
+                const uint32_t w[5] = {v[u].x, v[u].y, v[u].z, v[u].w, nb};
+                uint32_t h = 0;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const uint32_t ff = __vcmpeq4(w[q], 0xFFFFFFFFu);                                   // 0xFF where the byte is 0xFF
                     const uint32_t nx = __funnelshift_r(w[q], w[q + 1], 8);                             // the following bytes
-                    const uint32_t f8 = __vcmpeq4(nx & 0xFEFEFEFEu, 0xF8F8F8F8u);
-                    const uint32_t both = ff & f8;
-                    if (both) hits |= ((both & 1u) | ((both >> 7) & 2u) | ((both >> 14) & 4u) | ((both >> 21) & 8u)) << (4 * q);
+                    const uint32_t both = ff & __vcmpeq4(nx & 0xFEFEFEFEu, 0xF8F8F8F8u);
+                    if (both) h |= ((both & 1u) | ((both >> 7) & 2u) | ((both >> 14) & 4u) | ((both >> 21) & 8u)) << (4 * q);
                 }
-                // keep positions inside this segment, inside the stream's audio part, with a second byte present
-                for (uint32_t t = hits; t; t &= t - 1) {
-                    const int k = __ffs((int)t) - 1;
-                    const uint8_t* c = p + k;
-                    if (c < seg_lo || c >= seg_hi || c + 1 >= s_end || (uint64_t)(c - sbase) < m.first_frame) hits &= ~(1u << k);
-                }
+                hits[u] = h;
             }
-            uint32_t lanes = __ballot_sync(0xffffffffu, hits != 0);
-            while (lanes) {                                                          // rare: lanes with hits, in position order
-                const int src = __ffs((int)lanes) - 1;
-                lanes &= lanes - 1;
-                uint32_t found = 0;
-                if (lane == src) {
-                    for (uint32_t t = hits; t; t &= t - 1) {
-                        const uint8_t* c = p + (__ffs((int)t) - 1);
-                        const uint64_t pos = (uint64_t)(c - sbase);
-                        DecCand cd;
-                        bool hit = parse_header(c, slen - pos, m, cd);
-                        // frames of one stream keep channels / bps (cheap plausibility filter; the chain decides anyway)
-                        if (hit && (cd.channels != m.channels || cd.bps != m.bps) && m.channels) hit = false;
-                        if (hit) {
-                            if (pass) {
-                                cd.stream = sg.stream; cd.pos = (uint32_t)pos;
-                                cd.status = kDecPending; cd.end_pos = 0; cd.sample_slot = 0; cd.valid = 0; cd.sample_off = 0;
-                                cands[out0 + count + found] = cd;
+            if (!__any_sync(0xffffffffu, (hits[0] | hits[1] | hits[2] | hits[3]) != 0u)) continue;
+            // rare (about one row in 60 on random data, plus the real frame starts): rows, lanes and bits in position order
+#pragma unroll 1
+            for (int u = 0; u < 4; u++) {
+                uint32_t hu = u == 0 ? hits[0] : (u == 1 ? hits[1] : (u == 2 ? hits[2] : hits[3]));
+                const int rel = row0 + rb + 512 * u;
+                // keep positions inside this segment, inside the stream's audio part, with a second byte present
+                for (uint32_t t = hu; t; t &= t - 1) {
+                    const int k = __ffs((int)t) - 1, cr = rel + k;
+                    if (cr < 0 || cr >= nbytes || cr + 1 >= end_rel || cr < first_rel) hu &= ~(1u << k);
+                }
+                uint32_t lanes = __ballot_sync(0xffffffffu, hu != 0);
+                while (lanes) {
+                    const int src = __ffs((int)lanes) - 1;
+                    lanes &= lanes - 1;
+                    uint32_t found = 0;
+                    if (lane == src) {
+                        for (uint32_t t = hu; t; t &= t - 1) {
+                            const uint8_t* c = seg_lo + rel + (__ffs((int)t) - 1);
+                            const uint64_t pos = (uint64_t)(c - sbase);
+                            DecCand cd;
+                            bool hit = parse_header(c, slen - pos, m, cd);
+                            // frames of one stream keep channels / bps (cheap plausibility filter; the chain decides anyway)
+                            if (hit && (cd.channels != m.channels || cd.bps != m.bps) && m.channels) hit = false;
+                            if (hit) {
+                                if (pass) {
+                                    cd.stream = sg.stream; cd.pos = (uint32_t)pos;
+                                    cd.status = kDecPending; cd.end_pos = 0; cd.sample_slot = 0; cd.valid = 0; cd.sample_off = 0;
+                                    cands[out0 + count + found] = cd;
+                                }
+                                found++;
                             }
-                            found++;
                         }
                     }
+                    count += __shfl_sync(0xffffffffu, found, src);
                 }
-                count += __shfl_sync(0xffffffffu, found, src);
             }
         }
     }
@@ -208,30 +231,30 @@ dec_scan_u32_kernel(const uint32_t* __restrict__ in, int n, uint32_t* __restrict
 __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, uint32_t* __restrict__ sizes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     // 32-bit stereo: a side subframe may hold 33-bit samples; they are kept as (sample >> 1) plus a bitmap of the dropped bits
-    if (i < n) sizes[i] = cands[i].blocksize * cands[i].channels + ((cands[i].bps == 32 && cands[i].channels == 2) ? (cands[i].blocksize + 31) / 32 : 0u);
+    // slots are padded to four elements so that every frame's planes start 16-byte aligned (dec_frame_kernel stores int4)
+    if (i < n) sizes[i] = (cands[i].blocksize * cands[i].channels + ((cands[i].bps == 32 && cands[i].channels == 2) ? (cands[i].blocksize + 31) / 32 : 0u) + 3u) & ~3u;
 }
 
 // ------------------------------------------------------------------ frame decode: one thread per candidate ----
-// MSB-first bit reader over global memory.  The refill is word-granular and branch-free (one predicated aligned
-// 32-bit load that tops the 64-bit window up to >= 32 valid bits), so the 32 lanes of a warp -- each decoding its
-// own frame -- stay converged: a byte-wise refill loop entered by every lane at a different symbol would serialise.
+// MSB-first bit reader over global memory.  The window is 64 bits in two registers (ahi:alo, n valid bits from the top);
+// a refill adds one 32-bit word whenever n <= 32 and is branch-free apart from the chunk rotation, so the 32 lanes of a
+// warp -- each decoding its own frame -- stay converged: a byte-wise refill loop entered by every lane at a different
+// symbol would serialise.  Raw 16-byte chunks are fetched a whole chunk (about 12 symbols) before their first word is
+// needed and byte-swapped at consumption, so a lane rarely waits for memory.
 struct BitReader {
     const uint4* c16;                   // 16-byte aligned address at or below the first byte read
     uint32_t wi;                        // next word to consume, counted from c16 (32-bit bookkeeping: no pointer compares in the loop)
     uint32_t wend;                      // first word index past the stream (aligned up)
-    uint32_t nchunk;                    // chunks that may be loaded (those that start before the stream's end)
+    uint32_t nchunk;                    // chunks that may be loaded (those that start before the stream's end); later ones read as zero
     int64_t  off0;                      // byte offset of c16 relative to the stream start (for bit positions)
-    uint64_t acc; int n;                // n valid bits at the top of acc
-    uint4 cur, nxt;                     // RAW 16-byte chunks: the one holding word wi and the one after it.  A chunk is fetched
-                                        // a whole chunk (about 12 symbols) before its first word is needed and the byte swap
-                                        // happens at consumption, so the lanes -- each streaming its own frame -- rarely wait
-    int over;                           // words consumed past the end of the stream
+    uint32_t ahi, alo; int n;           // n valid bits at the top of ahi:alo, zeros below
+    uint4 cur, nxt;                     // the chunk holding word wi and the one after it
     __device__ __forceinline__ uint4 load_chunk(uint32_t ci) const { return ci < nchunk ? __ldg(c16 + ci) : make_uint4(0u, 0u, 0u, 0u); }
-    // raw word wi (zero past the end), then advance; rotates the chunks when the last word of `cur` goes
+    // raw word wi, then advance; rotates the chunks when the last word of `cur` goes
     __device__ __forceinline__ uint32_t take() {
         const uint32_t idx = wi & 3u;
-        uint32_t raw = idx == 0u ? cur.x : (idx == 1u ? cur.y : (idx == 2u ? cur.z : cur.w));
-        if (wi >= wend) { raw = 0u; over++; }
+        const uint32_t t0 = (idx & 1u) ? cur.y : cur.x, t1 = (idx & 1u) ? cur.w : cur.z;
+        const uint32_t raw = (idx & 2u) ? t1 : t0;
         wi++;
         if (idx == 3u) { cur = nxt; nxt = load_chunk((wi >> 2) + 1u); }
         return raw;
@@ -245,29 +268,32 @@ struct BitReader {
         wend = (uint32_t)((end_rel + 3u) >> 2);
         nchunk = (uint32_t)((end_rel + 15u) >> 4);
         wi = (uint32_t)((a - a16) >> 2);
-        over = 0;
         cur = load_chunk(0u); nxt = load_chunk(1u);
         const uint32_t skip = (uint32_t)(a & 3) * 8u;
-        const uint32_t w = __byte_perm(take(), 0, 0x0123);
-        over = 0;                                                        // the first word is never "past the end" bookkeeping
-        acc = ((uint64_t)w << 32) << skip;
+        ahi = __byte_perm(take(), 0, 0x0123) << skip; alo = 0u;
         n = 32 - (int)skip;
         fill();
     }
-    // invariant after fill(): n >= 32 (n <= 32 before => exactly one word is added)
+    // invariant after fill(): n >= 32.  Before it n <= 32 means every valid bit sits in ahi and alo is zero.
     __device__ __forceinline__ void fill() {
         if (n <= 32) {
             const uint32_t w = __byte_perm(take(), 0, 0x0123);
-            acc |= (uint64_t)w << (32 - n);
+            ahi |= __funnelshift_rc(w, 0u, (uint32_t)n);                // w >> n, 0 when n == 32
+            alo = __funnelshift_lc(0u, w, (uint32_t)(32 - n));          // w << (32 - n), 0 when n == 0
             n += 32;
         }
     }
-    __device__ __forceinline__ bool overrun() const { return over > 2; }
+    __device__ __forceinline__ void consume(uint32_t len) {             // len <= 32
+        ahi = __funnelshift_lc(alo, ahi, len);
+        alo = __funnelshift_lc(0u, alo, len);
+        n -= (int)len;
+    }
+    // words taken beyond the end of the stream (two may sit unread in the window of a frame that ends with the stream)
+    __device__ __forceinline__ bool overrun() const { return wi > wend + 2u; }
     __device__ __forceinline__ uint32_t get(uint32_t k) {          // k <= 32
         fill();
-        if (k == 0) return 0u;
-        const uint32_t v = (uint32_t)(acc >> (64 - k));
-        acc <<= k; n -= (int)k;
+        const uint32_t v = __funnelshift_rc(ahi, 0u, 32u - k);      // ahi >> (32 - k), 0 when k == 0
+        consume(k);
         return v;
     }
     __device__ __forceinline__ int32_t get_signed(uint32_t k) {
@@ -278,43 +304,79 @@ struct BitReader {
     __device__ __forceinline__ uint32_t unary() {
         fill();
         uint32_t q = 0;
-        uint32_t hi = (uint32_t)(acc >> 32);
-        while (hi == 0) {                                          // rare: more than 31 zeros in a row
-            q += 32; acc <<= 32; n -= 32;
+        while (ahi == 0u) {                                        // rare: more than 31 zeros in a row
+            q += 32; consume(32);
             fill();
-            hi = (uint32_t)(acc >> 32);
-            if (over > 2 || q > (1u << 26)) { over = 3; return q; }
+            if (overrun() || q > (1u << 26)) { wi = wend + 3u; return q; }
         }
-        const int z = __clz((int)hi);
-        q += (uint32_t)z;
-        acc <<= (z + 1); n -= (z + 1);
+        const uint32_t z = (uint32_t)__clz((int)ahi);
+        q += z;
+        consume(z + 1u);
         return q;
+    }
+    // one Rice code with parameter k (< 31): when the unary zeros, the stop bit and the k low bits all lie in the 32 valid
+    // bits at the top of the window this is one refill check and one extraction; anything longer takes the generic path
+    __device__ __forceinline__ int32_t rice(uint32_t k) {
+        fill();
+        const uint32_t z = (uint32_t)__clz((int)ahi);              // 32 when ahi == 0
+        uint32_t u;
+        if (z + 1u + k <= 32u) {
+            const uint32_t t = __funnelshift_lc(alo, ahi, z + 1u); // the bits after the stop bit
+            u = (z << k) | __funnelshift_rc(t, 0u, 32u - k);
+            consume(z + 1u + k);
+        } else {
+            const uint32_t qv = unary();
+            u = (qv << k) | get(k);
+        }
+        return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u);
     }
     // bit offset (from the stream start) of the next unread bit
     __device__ __forceinline__ uint64_t bit_position() const { return (uint64_t)((int64_t)wi * 4 + off0) * 8ull - (uint64_t)n; }
 };
 
-
-// per-thread history ring and coefficients live in shared memory, [index][thread] so lanes hit distinct banks
-template <int THREADS>
-struct DecShared { int32_t hist[32][THREADS]; int32_t q[32][THREADS]; };
-
 constexpr int kDecFrameThreads = 64;
+#ifndef FB_DEC_MIN_CTAS
+#define FB_DEC_MIN_CTAS 16     // 64 registers (a few spilled words) at 32 warps/SM: measured 5.0 ms for 131 072 frames against 6.8 ms at 12 CTAs / 78 registers
+#endif
 
-constexpr int kDecFastOrder = 12;      // predictor orders up to this use the register shift-register path
+constexpr int kDecFastOrder = 12;      // predictor orders up to this keep history and coefficients in registers
 
-__global__ void __launch_bounds__(kDecFrameThreads)
+// four samples of the prediction recurrence with TAPS taps (ref: FLAC__lpc_restore_signal / _wide, lpc.c; the 32-bit
+// accumulate is exact whenever libFLAC picks it, so WIDE only has to be set when it would pick the 64-bit one)
+template <int TAPS, bool WIDE>
+__device__ __forceinline__ void restore4(int32_t (&h)[kDecFastOrder], const int32_t (&q)[kDecFastOrder], const int32_t (&r)[4], int shift, int4& v4) {
+    int32_t v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        if (WIDE) {
+            long long s = 0;
+#pragma unroll
+            for (int j = 0; j < TAPS; j++) s += (long long)q[j] * (long long)h[j];
+            v[u] = (int32_t)((long long)r[u] + (s >> shift));
+        } else {
+            int s = 0;
+#pragma unroll
+            for (int j = 0; j < TAPS; j++) s += q[j] * h[j];
+            v[u] = r[u] + (s >> shift);
+        }
+#pragma unroll
+        for (int j = TAPS - 1; j > 0; j--) h[j] = h[j - 1];
+        h[0] = v[u];
+    }
+    v4 = make_int4(v[0], v[1], v[2], v[3]);
+}
+
+__global__ void __launch_bounds__(kDecFrameThreads, FB_DEC_MIN_CTAS)
 dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, const uint64_t* __restrict__ stream_len,
                  DecCand* __restrict__ cands, int n_cands, const uint64_t* __restrict__ slot_off, int32_t* __restrict__ samples) {
-    __shared__ DecShared<kDecFrameThreads> sh;
-    const int t = threadIdx.x, ci = blockIdx.x * kDecFrameThreads + t;
+    const int ci = blockIdx.x * kDecFrameThreads + threadIdx.x;
     if (ci >= n_cands) return;
     DecCand c = cands[ci];
     const uint8_t* sbase = blob + stream_off[c.stream];
     const uint64_t slen = stream_len[c.stream];
     BitReader br; br.init(sbase, (uint64_t)c.pos + c.hdr_bytes, slen);
     const uint32_t N = c.blocksize;
-    int32_t* out = samples + slot_off[ci];
+    int32_t* out = samples + slot_off[ci];                                  // 16-byte aligned (dec_cand_size_kernel pads the slots)
     int status = kDecOk;
     for (uint32_t chn = 0; chn < c.channels && status == kDecOk; chn++) {
         int32_t* o = out + (size_t)chn * N;
@@ -331,27 +393,45 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
         if (side33 && bps <= 32) { uint32_t* bm = reinterpret_cast<uint32_t*>(out + (size_t)c.channels * N); for (uint32_t w2 = 0; w2 < (N + 31u) / 32u; w2++) bm[w2] = 0u; }
         const uint32_t type = (hdr >> 1) & 0x3f;
         if (bps > 33) { status = kDecBadFrame; break; }
-        if (bps == 33) {
-            // ---- 33-bit side channel of a 32-bit stereo stream (rare, generic code): 64-bit history in local memory; the plane
-            // receives sample >> 1 and a bitmap behind the planes the dropped low bits (dec_post_kernel puts them back) ----
+        if (type == 0 && bps <= 32) {                                           // CONSTANT
+            const int32_t v = br.get_signed(bps) << wsh;
+            for (uint32_t i = 0; i < N; i++) o[i] = v;
+            if (br.overrun()) status = kDecIncomplete;
+            continue;
+        }
+        if (type == 1 && bps <= 32) {                                           // VERBATIM
+            for (uint32_t i = 0; i < N; i++) o[i] = br.get_signed(bps) << wsh;
+            if (br.overrun()) status = kDecIncomplete;
+            continue;
+        }
+        uint32_t order = 0; bool lpc = false;
+        if (type >= 8 && type <= 12) order = type - 8;
+        else if (type >= 32) { order = type - 31; lpc = true; }
+        else if (type >= 2) { status = kDecBadFrame; break; }
+        if (order > N) { status = kDecBadFrame; break; }
+        if (bps == 33 || order > (uint32_t)kDecFastOrder) {
+            // ---- rare, generic code: the 33-bit side channel of a 32-bit stereo stream (the plane receives sample >> 1 and a
+            // bitmap behind the planes the dropped low bits; dec_post_kernel puts them back) and predictor orders above
+            // kDecFastOrder.  64-bit history and accumulate in local memory. ----
+            const bool w33 = bps == 33;
             uint32_t* bitmap = reinterpret_cast<uint32_t*>(out + (size_t)c.channels * N);
             uint32_t word = 0;
             auto emit = [&](uint32_t i, long long v) {
+                if (!w33) { o[i] = (int32_t)v << wsh; return; }
                 o[i] = (int32_t)(v >> 1);
                 word |= (uint32_t)(v & 1ll) << (i & 31u);
                 if ((i & 31u) == 31u || i + 1 == N) { bitmap[i >> 5] = word; word = 0; }
             };
-            auto get33 = [&]() -> long long { const uint32_t hi = br.get(1); const uint32_t lo = br.get(32); return (long long)lo - (hi ? 0x100000000ll : 0ll); };
-            if (type == 0) { const long long v = get33(); for (uint32_t i = 0; i < N; i++) emit(i, v); }
-            else if (type == 1) { for (uint32_t i = 0; i < N; i++) emit(i, get33()); }
+            auto getw = [&]() -> long long {
+                if (!w33) return (long long)br.get_signed(bps);
+                const uint32_t hi = br.get(1); const uint32_t lo = br.get(32); return (long long)lo - (hi ? 0x100000000ll : 0ll);
+            };
+            if (type == 0) { const long long v = getw(); for (uint32_t i = 0; i < N; i++) emit(i, v); }
+            else if (type == 1) { for (uint32_t i = 0; i < N; i++) emit(i, getw()); }
             else {
-                uint32_t order; int shift = 0; bool lpc;
-                if (type >= 8 && type <= 12) { order = type - 8; lpc = false; }
-                else if (type >= 32) { order = type - 31; lpc = true; }
-                else { status = kDecBadFrame; break; }
-                if (order > N) { status = kDecBadFrame; break; }
+                int shift = 0;
                 long long hh[32]; int qq[32];
-                for (uint32_t i = 0; i < order; i++) { const long long v = get33(); hh[i & 31u] = v; emit(i, v); }
+                for (uint32_t i = 0; i < order; i++) { const long long v = getw(); hh[i & 31u] = v; emit(i, v); }
                 if (lpc) {
                     const uint32_t prec = br.get(4) + 1; if (prec == 16) { status = kDecBadFrame; break; }
                     shift = br.get_signed(5); if (shift < 0) { status = kDecBadFrame; break; }
@@ -367,11 +447,9 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
                 uint32_t left = 0, k = 0, raw = 0;
                 bool first = true;
                 for (uint32_t i = order; i < N; i++) {
-                    if (left == 0) { left = (N >> po) - (first ? order : 0u); first = false; k = br.get(plen); raw = (k == pesc) ? br.get(5) : 0u; }
+                    while (left == 0) { left = (N >> po) - (first ? order : 0u); first = false; k = br.get(plen); raw = (k == pesc) ? br.get(5) : 0u; }
                     left--;
-                    int32_t r;
-                    if (k == pesc) r = br.get_signed(raw);
-                    else { const uint32_t qv = br.unary(); const uint32_t u = (qv << k) | br.get(k); r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
+                    const int32_t r = (k == pesc) ? br.get_signed(raw) : br.rice(k);
                     long long sacc = 0;
                     for (uint32_t j = 0; j < order; j++) sacc += (long long)qq[j] * hh[(i - 1 - j) & 31u];
                     const long long v = (long long)r + (sacc >> shift);
@@ -383,113 +461,88 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
             if (br.overrun()) status = kDecIncomplete;
             continue;
         }
-        if (type == 0) {                                                        // CONSTANT
-            const int32_t v = br.get_signed(bps) << wsh;
-            for (uint32_t i = 0; i < N; i++) o[i] = v;
-        } else if (type == 1) {                                                 // VERBATIM
-            for (uint32_t i = 0; i < N; i++) o[i] = br.get_signed(bps) << wsh;
+        // ---- FIXED / LPC up to kDecFastOrder taps: history (newest first: h[j] = sample i-1-j) and coefficients in registers ----
+        int32_t h[kDecFastOrder], q[kDecFastOrder];
+#pragma unroll
+        for (int j = 0; j < kDecFastOrder; j++) { h[j] = 0; q[j] = 0; }
+        for (uint32_t i = 0; i < order; i++) {
+            const int32_t v = br.get_signed(bps);
+            o[i] = v << wsh;
+#pragma unroll
+            for (int j = kDecFastOrder - 1; j > 0; j--) h[j] = h[j - 1];
+            h[0] = v;
+        }
+        int shift = 0;
+        uint32_t prec = 0;
+        if (lpc) {
+            prec = br.get(4) + 1; if (prec == 16) { status = kDecBadFrame; break; }
+            shift = br.get_signed(5); if (shift < 0) { status = kDecBadFrame; break; }
+            for (uint32_t j = 0; j < order; j++) {
+                const int32_t cv = br.get_signed(prec);
+#pragma unroll
+                for (int jj = 0; jj < kDecFastOrder; jj++) if ((uint32_t)jj == j) q[jj] = cv;
+            }
         } else {
-            uint32_t order; int shift = 0; bool lpc;
-            if (type >= 8 && type <= 12) { order = type - 8; lpc = false; }
-            else if (type >= 32) { order = type - 31; lpc = true; }
-            else { status = kDecBadFrame; break; }
-            if (order > N) { status = kDecBadFrame; break; }
-            // warm-up samples: newest first in h[] (h[j] = sample i-1-j); orders above kDecFastOrder use the shared ring
-            int32_t h[kDecFastOrder], q[kDecFastOrder];
+            const int32_t cf[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
 #pragma unroll
-            for (int j = 0; j < kDecFastOrder; j++) { h[j] = 0; q[j] = 0; }
-            const bool fast = order <= (uint32_t)kDecFastOrder;
-            for (uint32_t i = 0; i < order; i++) {
-                const int32_t v = br.get_signed(bps);
-                o[i] = v << wsh;
-                if (fast) {
+            for (int jj = 0; jj < 4; jj++) q[jj] = cf[order][jj];
+        }
+        // ref: lpc.c FLAC__lpc_restore_signal vs _wide: 32-bit accumulate is exact iff bps + precision + ilog2(order) <= 32
+        const bool wide = lpc ? (bps + prec + ilog2_u32(order ? order : 1) > 32) : (bps + order > 31);
+        // residual: method, partition order, then per partition a parameter and its symbols
+        const uint32_t method = br.get(2);
+        if (method > 1) { status = kDecBadFrame; break; }
+        const uint32_t po = br.get(4), plen = method ? 5u : 4u, pesc = method ? 31u : 15u;
+        const uint32_t psize = N >> po;
+        if (psize < order || (po > 0 && (N & ((1u << po) - 1)))) { status = kDecBadFrame; break; }
+        uint32_t left = 0, k = 0, raw = 0;
+        bool first = true;
+        // Blocks and partitions whose lengths are multiples of four (every stream libFLAC writes apart from a short last
+        // block) run four samples per iteration: history rotates by register renaming, one 16-byte store per four
+        // samples, one partition test per four.  Scalar iterations lead up to the first multiple of four; everything
+        // else is scalar throughout.  Lanes of a warp keep their own counters, so mixed orders stay converged.
+        const bool quads = ((N | psize) & 3u) == 0u;
+        const uint32_t scalar_end = quads ? min(N, (order + 3u) & ~3u) : N;
+        uint32_t i = order;
+        for (; i < scalar_end; i++) {
+            while (left == 0) { left = psize - (first ? order : 0u); first = false; k = br.get(plen); raw = (k == pesc) ? br.get(5) : 0u; }
+            left--;
+            const int32_t r = (k == pesc) ? br.get_signed(raw) : br.rice(k);
+            long long s = 0;
 #pragma unroll
-                    for (int j = kDecFastOrder - 1; j > 0; j--) h[j] = h[j - 1];
-                    h[0] = v;
-                } else sh.hist[i & 31][t] = v;
-            }
-            uint32_t prec = 0;
-            if (lpc) {
-                prec = br.get(4) + 1; if (prec == 16) { status = kDecBadFrame; break; }
-                shift = br.get_signed(5); if (shift < 0) { status = kDecBadFrame; break; }
-                for (uint32_t j = 0; j < order; j++) {
-                    const int32_t cv = br.get_signed(prec);
-                    if (fast) {
+            for (int j = 0; j < kDecFastOrder; j++) s += (long long)q[j] * (long long)h[j];
+            const int32_t v = wide ? (int32_t)((long long)r + (s >> shift)) : r + ((int32_t)s >> shift);
 #pragma unroll
-                        for (int jj = 0; jj < kDecFastOrder; jj++) if ((uint32_t)jj == j) q[jj] = cv;
-                    } else sh.q[j][t] = cv;
-                }
-            } else {
-                const int32_t cf[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+            for (int j = kDecFastOrder - 1; j > 0; j--) h[j] = h[j - 1];
+            h[0] = v;
+            o[i] = v << wsh;
+            if (br.overrun()) break;
+        }
+        if (quads && !br.overrun()) {
+            const int cls = order <= 4u ? 0 : (order <= 8u ? 1 : 2);
+            for (; i < N; i += 4) {
+                while (left == 0) { left = psize - (first ? order : 0u); first = false; k = br.get(plen); raw = (k == pesc) ? br.get(5) : 0u; }
+                left -= 4;
+                int32_t r[4];
+                if (k == pesc) {
 #pragma unroll
-                for (int jj = 0; jj < 4; jj++) q[jj] = cf[order][jj];
-            }
-            // up: lpc.c FLAC__lpc_restore_signal vs _wide: 32-bit accumulate is exact iff bps + precision + ilog2(order) <= 32
-            const bool wide = lpc ? (bps + prec + ilog2_u32(order ? order : 1) > 32) : (bps + order > 31);
-            // residual: method, partition order, then per partition a parameter and its symbols (one flat loop over samples
-            // with a per-lane "symbols left in this partition" counter keeps lanes with different partition orders converged)
-            const uint32_t method = br.get(2);
-            if (method > 1) { status = kDecBadFrame; break; }
-            const uint32_t po = br.get(4), plen = method ? 5u : 4u, pesc = method ? 31u : 15u;
-            if ((N >> po) < order || (po > 0 && (N & ((1u << po) - 1)))) { status = kDecBadFrame; break; }
-            uint32_t left = 0, k = 0, raw = 0;
-            bool first = true;
-            for (uint32_t i = order; i < N; i++) {
-                if (left == 0) {
-                    left = (N >> po) - (first ? order : 0u);
-                    first = false;
-                    k = br.get(plen);
-                    raw = (k == pesc) ? br.get(5) : 0u;
-                }
-                left--;
-                int32_t r;
-                if (k == pesc) r = br.get_signed(raw);
-                else {
-                    // common case: the whole code (unary zeros, stop bit, k low bits) lies in the 32 valid bits at the top of the
-                    // window -- one refill check and one extraction per sample; anything longer takes the generic path
-                    br.fill();
-                    const uint32_t hi32 = (uint32_t)(br.acc >> 32);
-                    const uint32_t z = (uint32_t)__clz((int)hi32);
-                    uint32_t u;
-                    if (hi32 != 0u && z + 1u + k <= 32u) {
-                        const uint32_t rem = k ? ((uint32_t)((br.acc << (z + 1u)) >> 32) >> (32u - k)) : 0u;
-                        u = (z << k) | rem;
-                        br.acc <<= (z + 1u + k); br.n -= (int)(z + 1u + k);
-                    } else {
-                        const uint32_t qv = br.unary();
-                        u = (qv << k) | br.get(k);
-                    }
-                    r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1u);
-                }
-                int32_t v;
-                if (fast) {
-                    if (wide) {
-                        long long s = 0;
-#pragma unroll
-                        for (int j = 0; j < kDecFastOrder; j++) s += (long long)q[j] * (long long)h[j];
-                        v = (int32_t)((long long)r + (s >> shift));
-                    } else {
-                        int s = 0;
-#pragma unroll
-                        for (int j = 0; j < kDecFastOrder; j++) s += q[j] * h[j];
-                        v = r + (s >> shift);
-                    }
-#pragma unroll
-                    for (int j = kDecFastOrder - 1; j > 0; j--) h[j] = h[j - 1];
-                    h[0] = v;
+                    for (int u = 0; u < 4; u++) r[u] = br.get_signed(raw);
                 } else {
-                    if (wide) {
-                        long long s = 0;
-                        for (uint32_t j = 0; j < order; j++) s += (long long)sh.q[j][t] * (long long)sh.hist[(i - 1 - j) & 31][t];
-                        v = (int32_t)((long long)r + (s >> shift));
-                    } else {
-                        int s = 0;
-                        for (uint32_t j = 0; j < order; j++) s += sh.q[j][t] * sh.hist[(i - 1 - j) & 31][t];
-                        v = r + (s >> shift);
-                    }
-                    sh.hist[i & 31][t] = v;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) r[u] = br.rice(k);
                 }
-                o[i] = v << wsh;
+                int4 v4;
+                if (!wide) {
+                    if (cls == 0) restore4<4, false>(h, q, r, shift, v4);
+                    else if (cls == 1) restore4<8, false>(h, q, r, shift, v4);
+                    else restore4<12, false>(h, q, r, shift, v4);
+                } else {
+                    if (cls == 0) restore4<4, true>(h, q, r, shift, v4);
+                    else if (cls == 1) restore4<8, true>(h, q, r, shift, v4);
+                    else restore4<12, true>(h, q, r, shift, v4);
+                }
+                v4.x <<= wsh; v4.y <<= wsh; v4.z <<= wsh; v4.w <<= wsh;
+                *reinterpret_cast<int4*>(o + i) = v4;
                 if (br.overrun()) break;
             }
         }
@@ -547,39 +600,104 @@ __global__ void dec_assign_kernel(DecStreamResult* __restrict__ res, const uint6
 // ------------------------------------------------------------------ post: one CTA per chained frame ----
 // CRC-16 of the frame bytes (chunked, combined in GF(2)[x]/P like the encoder), undo channel decorrelation
 // (ref: format.h:388-393), narrow to the caller's container, interleave [sample][channel], coalesced stores.
+// undo one inter-channel decorrelation (ref: format.h:388-393); a = plane 0, b = plane 1
+__device__ __forceinline__ void undo_stereo(int ca, int32_t a, int32_t b, int32_t& l, int32_t& r) {
+    if (ca == 1) { l = a; r = a - b; }
+    else if (ca == 2) { l = a + b; r = b; }
+    else { const int32_t m2 = (int32_t)(((uint32_t)a << 1) | ((uint32_t)b & 1u)); l = (m2 + b) >> 1; r = (m2 - b) >> 1; }
+}
+
 template <typename OutT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 dec_post_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, DecCand* __restrict__ cands,
                 const uint64_t* __restrict__ slot_off, const int32_t* __restrict__ samples, DecStreamResult* __restrict__ res,
                 OutT* __restrict__ pcm_out) {
-    __shared__ uint16_t crc_tab[256];
+    __shared__ __align__(16) uint16_t crc_tabs[4][256];
     __shared__ uint32_t crc_warp[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const DecCand c = cands[blockIdx.x];
     if (!c.valid) return;
-    {
-        uint16_t v = (uint16_t)(tid << 8);
+    reinterpret_cast<uint2*>(&crc_tabs[0][0])[tid] = reinterpret_cast<const uint2*>(&g_crc16_slice.t[0][0])[tid];
+    const uint32_t N = c.blocksize, ch = c.channels;
+    const int32_t* in = samples + slot_off[blockIdx.x];                     // 16-byte aligned (padded slots)
+    OutT* out = pcm_out + res[c.stream].pcm_off + c.sample_off * ch;
+    // Stereo frames whose planes can be read four samples at a time: the first 1024 sample quads of both planes are
+    // requested BEFORE the CRC so that their latency hides behind it.
+    const bool side33 = c.bps == 32;                 // side plane = side >> 1, low bits in the bitmap behind the planes (dec_frame_kernel)
+    const bool quads = c.ca != 0 && !side33 && (N & 3u) == 0u;
+    const uint32_t nq = N >> 2;
+    const int4* pa = reinterpret_cast<const int4*>(in);
+    const int4* pb = reinterpret_cast<const int4*>(in + N);
+    int4 A[4], B[4];
+    if (quads) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) v = (uint16_t)((v & 0x8000) ? ((v << 1) ^ 0x8005) : (v << 1));
-        crc_tab[tid] = v;
+        for (int u = 0; u < 4; u++) {
+            const uint32_t qi = (uint32_t)tid + 256u * (uint32_t)u;
+            if (qi < nq) { A[u] = __ldcs(pa + qi); B[u] = __ldcs(pb + qi); }
+        }
     }
     __syncthreads();
     const uint8_t* fb = blob + stream_off[c.stream] + c.pos;
     const uint32_t nb = c.end_pos - c.pos - 2u;
     {
-        const uint16_t c2 = cta_crc16<256>([&](uint32_t j) { return __ldg(fb + j); }, nb, crc_tab, crc_warp, tid);
+        const uint32_t mis = (uint32_t)((uintptr_t)fb & 3u);
+        const uint32_t* fw = reinterpret_cast<const uint32_t*>(fb - mis);   // aligned words; byte j of the frame is byte j + mis of fw
+        const uint16_t c2 = cta_crc16_words<256>([&](uint32_t j) {
+            const uint32_t o = j + mis;
+            return __funnelshift_r(__ldg(fw + (o >> 2)), __ldg(fw + (o >> 2) + 1), (o & 3u) * 8u);
+        }, nb, crc_tabs, crc_warp, tid);
         if (tid == 0) {
             const uint16_t stored = (uint16_t)((uint16_t)fb[nb] << 8 | fb[nb + 1]);
             if (c2 != stored) { res[c.stream].status = kDecCrcMismatch; cands[blockIdx.x].status = kDecCrcMismatch; }
         }
     }
-    const uint32_t N = c.blocksize, ch = c.channels;
-    const int32_t* in = samples + slot_off[blockIdx.x];
-    OutT* out = pcm_out + res[c.stream].pcm_off + c.sample_off * ch;
     if (c.ca == 0) {
         for (uint32_t e = tid; e < N * ch; e += 256) { const uint32_t i = e / ch, k = e - i * ch; out[e] = (OutT)in[(size_t)k * N + i]; }
+    } else if (quads) {
+        const bool al16 = ((uintptr_t)out & 15u) == 0u, alpair = ((uintptr_t)out & (2u * sizeof(OutT) - 1u)) == 0u;
+        for (uint32_t q0 = 0; q0 < nq; q0 += 1024u) {
+            if (q0) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t qi = q0 + (uint32_t)tid + 256u * (uint32_t)u;
+                    if (qi < nq) { A[u] = __ldcs(pa + qi); B[u] = __ldcs(pb + qi); }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t qi = q0 + (uint32_t)tid + 256u * (uint32_t)u;
+                if (qi >= nq) continue;
+                int32_t l[4], r[4];
+                undo_stereo(c.ca, A[u].x, B[u].x, l[0], r[0]); undo_stereo(c.ca, A[u].y, B[u].y, l[1], r[1]);
+                undo_stereo(c.ca, A[u].z, B[u].z, l[2], r[2]); undo_stereo(c.ca, A[u].w, B[u].w, l[3], r[3]);
+                OutT* po = out + (size_t)qi * 8u;
+                if (sizeof(OutT) == 2) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) w[k] = ((uint32_t)l[k] & 0xffffu) | ((uint32_t)r[k] << 16);
+                    if (al16) __stcs(reinterpret_cast<uint4*>(po), make_uint4(w[0], w[1], w[2], w[3]));
+                    else if (alpair) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) reinterpret_cast<uint32_t*>(po)[k] = w[k];
+                    } else {                                                   // a batch that mixes channel counts can leave a stream 2-byte aligned
+#pragma unroll
+                        for (int k = 0; k < 4; k++) { po[2 * k] = (OutT)l[k]; po[2 * k + 1] = (OutT)r[k]; }
+                    }
+                } else {
+                    if (al16) {
+                        __stcs(reinterpret_cast<int4*>(po), make_int4(l[0], r[0], l[1], r[1]));
+                        __stcs(reinterpret_cast<int4*>(po) + 1, make_int4(l[2], r[2], l[3], r[3]));
+                    } else if (alpair) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) reinterpret_cast<int2*>(po)[k] = make_int2(l[k], r[k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) { po[2 * k] = (OutT)l[k]; po[2 * k + 1] = (OutT)r[k]; }
+                    }
+                }
+            }
+        }
     } else {
-        const bool side33 = c.bps == 32;             // side plane = side >> 1, low bits in the bitmap behind the planes (dec_frame_kernel)
         const uint32_t* bitmap = reinterpret_cast<const uint32_t*>(in + (size_t)2 * N);
         for (uint32_t i = tid; i < N; i += 256) {
             const int32_t a = in[i], b = in[N + i];
@@ -591,10 +709,7 @@ dec_post_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ s
                 if (c.ca == 1) { l = a; r = (int32_t)((uint32_t)a - (((uint32_t)b << 1) | lsb)); }
                 else if (c.ca == 2) { r = b; l = (int32_t)((((uint32_t)a << 1) | lsb) + (uint32_t)b); }
                 else { l = (int32_t)((uint32_t)a + (uint32_t)b + lsb); r = (int32_t)((uint32_t)a - (uint32_t)b); }
-            }
-            else if (c.ca == 1) { l = a; r = a - b; }
-            else if (c.ca == 2) { l = a + b; r = b; }
-            else { const int32_t m2 = (int32_t)(((uint32_t)a << 1) | ((uint32_t)b & 1u)); l = (m2 + b) >> 1; r = (m2 - b) >> 1; }
+            } else undo_stereo(c.ca, a, b, l, r);
             out[2 * i] = (OutT)l; out[2 * i + 1] = (OutT)r;
         }
     }

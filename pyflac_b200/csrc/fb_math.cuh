@@ -208,6 +208,57 @@ constexpr CrcPosTable make_crc_pos_table() {
 }
 static __device__ const CrcPosTable g_crc_pos = make_crc_pos_table();
 
+// Slice-by-4 tables for the same CRC: t[0] is the plain byte table, t[k][x] = CRC of byte x followed by k zero bytes, so
+// one 32-bit step is four INDEPENDENT lookups instead of four dependent ones.  Built at compile time.
+struct __align__(16) Crc16Slice { uint16_t t[4][256]; };
+constexpr Crc16Slice make_crc16_slice() {
+    Crc16Slice s{};
+    for (int x = 0; x < 256; x++) {
+        uint16_t v = (uint16_t)(x << 8);
+        for (int i = 0; i < 8; i++) v = (uint16_t)((v & 0x8000) ? ((v << 1) ^ 0x8005) : (v << 1));
+        s.t[0][x] = v;
+    }
+    for (int k = 1; k < 4; k++)
+        for (int x = 0; x < 256; x++) s.t[k][x] = (uint16_t)((s.t[k - 1][x] << 8) ^ s.t[0][s.t[k - 1][x] >> 8]);
+    return s;
+}
+static __device__ const Crc16Slice g_crc16_slice = make_crc16_slice();
+
+// As cta_crc16 below, for input that can be fetched four bytes at a time: word_at(j) returns bytes j..j+3 (byte j in the
+// low bits; j is arbitrary, reading up to 3 bytes past nb must be harmless); tabs = the four tables in shared memory.
+template <int THREADS, typename WordAt>
+__device__ __forceinline__ uint16_t cta_crc16_words(WordAt word_at, uint32_t nb, const uint16_t (*tabs)[256], uint32_t* warp_x, int tid) {
+    const uint32_t nchunks = (nb + 63u) >> 6;
+    uint32_t acc = 0;
+    for (uint32_t j = (uint32_t)tid; j < nchunks; j += THREADS) {          // j counts chunks from the end of the frame
+        const uint32_t end = nb - (j << 6);
+        uint32_t crc = 0;
+        if (end >= 64u) {
+            const uint32_t beg = end - 64u;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint32_t w = word_at(beg + 4u * (uint32_t)i);
+                crc = (uint32_t)tabs[3][(crc >> 8) ^ (w & 0xffu)] ^ tabs[2][(crc & 0xffu) ^ ((w >> 8) & 0xffu)] ^ tabs[1][(w >> 16) & 0xffu] ^ tabs[0][w >> 24];
+            }
+        } else {
+            for (uint32_t b = 0; b < end; b++) crc = ((crc << 8) & 0xffffu) ^ tabs[0][(crc >> 8) ^ (word_at(b) & 0xffu)];
+        }
+        uint16_t c16 = (uint16_t)crc;
+        if (j) c16 = crc16_mulmod(c16, g_crc_pos.lo[j & 255u]);
+        if (j >> 8) c16 = crc16_mulmod(c16, g_crc_pos.hi[(j >> 8) & 15u]);
+        acc ^= c16;
+    }
+    acc = __reduce_xor_sync(0xffffffffu, acc);
+    if ((tid & 31) == 0) warp_x[tid >> 5] = acc;
+    __syncthreads();
+    uint32_t r = 0;
+    if (tid < 32) {
+        r = (tid < THREADS / 32) ? warp_x[tid] : 0u;
+        r = __reduce_xor_sync(0xffffffffu, r);
+    }
+    return (uint16_t)r;
+}
+
 // CRC-16 (poly 0x8005, init 0) of nb bytes by a whole CTA of THREADS threads.  byte_at(j) returns byte j;
 // crc_tab is the 256-entry byte table in shared memory; warp_x is THREADS/32 words of shared scratch.
 // The result is valid on warp 0 (all lanes) after the call; contains one __syncthreads().
