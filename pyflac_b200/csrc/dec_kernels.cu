@@ -158,10 +158,12 @@ dec_sync_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ s
                 uint32_t h = 0;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const uint32_t ff = __vcmpeq4(w[q], 0xFFFFFFFFu);                                   // 0xFF where the byte is 0xFF
                     const uint32_t nx = __funnelshift_r(w[q], w[q + 1], 8);                             // the following bytes
-                    const uint32_t both = ff & __vcmpeq4(nx & 0xFEFEFEFEu, 0xF8F8F8F8u);
-                    if (both) h |= ((both & 1u) | ((both >> 7) & 2u) | ((both >> 14) & 4u) | ((both >> 21) & 8u)) << (4 * q);
+                    // a byte of c is zero exactly where this byte is 0xFF and the next one 0xF8 / 0xF9; exact zero-byte test
+                    // (7-bit adds cannot carry across bytes), 0x80 in every matching byte
+                    const uint32_t c = ~w[q] | ((nx & 0xFEFEFEFEu) ^ 0xF8F8F8F8u);
+                    const uint32_t both = ~((((c & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | c) | 0x7F7F7F7Fu);
+                    if (both) h |= (((both >> 7) & 1u) | ((both >> 14) & 2u) | ((both >> 21) & 4u) | ((both >> 28) & 8u)) << (4 * q);
                 }
                 hits[u] = h;
             }
@@ -239,8 +241,13 @@ __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, u
 // MSB-first bit reader over global memory.  The window is 64 bits in two registers (ahi:alo, n valid bits from the top);
 // a refill adds one 32-bit word whenever n <= 32 and is branch-free apart from the chunk rotation, so the 32 lanes of a
 // warp -- each decoding its own frame -- stay converged: a byte-wise refill loop entered by every lane at a different
-// symbol would serialise.  Raw 16-byte chunks are fetched a whole chunk (about 12 symbols) before their first word is
-// needed and byte-swapped at consumption, so a lane rarely waits for memory.
+// symbol would serialise.
+constexpr int kDecFrameThreads = 64;
+#ifndef FB_DEC_RING
+#define FB_DEC_RING 4
+#endif
+constexpr int kDecRing = FB_DEC_RING;  // 16-byte chunks per thread in the shared-memory ring (power of two); kDecRing - 2 chunks are in flight
+
 struct BitReader {
     const uint4* c16;                   // 16-byte aligned address at or below the first byte read
     uint32_t wi;                        // next word to consume, counted from c16 (32-bit bookkeeping: no pointer compares in the loop)
@@ -248,18 +255,30 @@ struct BitReader {
     uint32_t nchunk;                    // chunks that may be loaded (those that start before the stream's end); later ones read as zero
     int64_t  off0;                      // byte offset of c16 relative to the stream start (for bit positions)
     uint32_t ahi, alo; int n;           // n valid bits at the top of ahi:alo, zeros below
-    uint4 cur, nxt;                     // the chunk holding word wi and the one after it
-    __device__ __forceinline__ uint4 load_chunk(uint32_t ci) const { return ci < nchunk ? __ldg(c16 + ci) : make_uint4(0u, 0u, 0u, 0u); }
-    // raw word wi, then advance; rotates the chunks when the last word of `cur` goes
+    uint32_t ring;                      // shared-memory address of this thread's slot 0; slot s is kDecFrameThreads * 16 * s further
+    // The bytes travel global -> shared with cp.async, two chunks (about 20 symbols) ahead of their use, and are read
+    // back one word at a time.  Loads into registers would not do: the 32 lanes of a warp reach their chunk boundaries
+    // at different symbols but share one register scoreboard, so every lane's refill would wait for the load another
+    // lane issued an iteration earlier (measured: 62 % of all stall samples).  cp.async has no destination register.
+    __device__ __forceinline__ void request(uint32_t ci) const {
+        const uint32_t dst = ring + (ci & (uint32_t)(kDecRing - 1)) * (uint32_t)(kDecFrameThreads * 16);
+        const bool in = ci < nchunk;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(c16 + (in ? ci : 0u)), "r"(in ? 16u : 0u) : "memory");   // size 0: zero fill
+    }
+    // raw word wi, then advance; at a chunk boundary ask for the chunk after next and make sure the new one has landed
     __device__ __forceinline__ uint32_t take() {
-        const uint32_t idx = wi & 3u;
-        const uint32_t t0 = (idx & 1u) ? cur.y : cur.x, t1 = (idx & 1u) ? cur.w : cur.z;
-        const uint32_t raw = (idx & 2u) ? t1 : t0;
+        uint32_t raw;
+        const uint32_t src = ring + ((wi >> 2) & (uint32_t)(kDecRing - 1)) * (uint32_t)(kDecFrameThreads * 16) + (wi & 3u) * 4u;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(src) : "memory");
         wi++;
-        if (idx == 3u) { cur = nxt; nxt = load_chunk((wi >> 2) + 1u); }
+        if ((wi & 3u) == 0u) {
+            request((wi >> 2) + (uint32_t)(kDecRing - 2));
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" :: "n"(kDecRing - 2) : "memory");
+        }
         return raw;
     }
-    __device__ __forceinline__ void init(const uint8_t* base, uint64_t start, uint64_t slen) {
+    __device__ __forceinline__ void init(const uint8_t* base, uint64_t start, uint64_t slen, uint32_t ring_addr) {
         const uint8_t* p = base + start;
         const uintptr_t a = (uintptr_t)p, a16 = a & ~(uintptr_t)15;
         c16 = reinterpret_cast<const uint4*>(a16);
@@ -268,7 +287,10 @@ struct BitReader {
         wend = (uint32_t)((end_rel + 3u) >> 2);
         nchunk = (uint32_t)((end_rel + 15u) >> 4);
         wi = (uint32_t)((a - a16) >> 2);
-        cur = load_chunk(0u); nxt = load_chunk(1u);
+        ring = ring_addr;
+#pragma unroll
+        for (int i = 0; i < kDecRing - 1; i++) { request((uint32_t)i); asm volatile("cp.async.commit_group;" ::: "memory"); }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         const uint32_t skip = (uint32_t)(a & 3) * 8u;
         ahi = __byte_perm(take(), 0, 0x0123) << skip; alo = 0u;
         n = 32 - (int)skip;
@@ -334,7 +356,6 @@ struct BitReader {
     __device__ __forceinline__ uint64_t bit_position() const { return (uint64_t)((int64_t)wi * 4 + off0) * 8ull - (uint64_t)n; }
 };
 
-constexpr int kDecFrameThreads = 64;
 #ifndef FB_DEC_MIN_CTAS
 #define FB_DEC_MIN_CTAS 16     // 64 registers (a few spilled words) at 32 warps/SM: measured 5.0 ms for 131 072 frames against 6.8 ms at 12 CTAs / 78 registers
 #endif
@@ -369,12 +390,13 @@ __device__ __forceinline__ void restore4(int32_t (&h)[kDecFastOrder], const int3
 __global__ void __launch_bounds__(kDecFrameThreads, FB_DEC_MIN_CTAS)
 dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, const uint64_t* __restrict__ stream_len,
                  DecCand* __restrict__ cands, int n_cands, const uint64_t* __restrict__ slot_off, int32_t* __restrict__ samples) {
+    __shared__ uint4 ring_buf[kDecRing][kDecFrameThreads];
     const int ci = blockIdx.x * kDecFrameThreads + threadIdx.x;
     if (ci >= n_cands) return;
     DecCand c = cands[ci];
     const uint8_t* sbase = blob + stream_off[c.stream];
     const uint64_t slen = stream_len[c.stream];
-    BitReader br; br.init(sbase, (uint64_t)c.pos + c.hdr_bytes, slen);
+    BitReader br; br.init(sbase, (uint64_t)c.pos + c.hdr_bytes, slen, (uint32_t)__cvta_generic_to_shared(&ring_buf[0][threadIdx.x]));
     const uint32_t N = c.blocksize;
     int32_t* out = samples + slot_off[ci];                                  // 16-byte aligned (dec_cand_size_kernel pads the slots)
     int status = kDecOk;
@@ -519,8 +541,11 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
             if (br.overrun()) break;
         }
         if (quads && !br.overrun()) {
-            const int cls = order <= 4u ? 0 : (order <= 8u ? 1 : 2);
+            const int cls_own = order <= 4u ? 0 : (order <= 8u ? 1 : 2);
             for (; i < N; i += 4) {
+                // the lanes that are here together all take the widest class any of them needs (surplus taps multiply zero
+                // coefficients): one body per warp and iteration instead of up to three run one after the other
+                const int cls = (int)__reduce_max_sync(__activemask(), (unsigned)cls_own);
                 while (left == 0) { left = psize - (first ? order : 0u); first = false; k = br.get(plen); raw = (k == pesc) ? br.get(5) : 0u; }
                 left -= 4;
                 int32_t r[4];

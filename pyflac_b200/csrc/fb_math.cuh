@@ -224,7 +224,7 @@ constexpr Crc16Slice make_crc16_slice() {
 }
 static __device__ const Crc16Slice g_crc16_slice = make_crc16_slice();
 
-// As cta_crc16 below, for input that can be fetched four bytes at a time: word_at(j) returns bytes j..j+3 (byte j in the
+// As cta_crc16 below (but without a CTA-wide wait: only warp 0 blocks), for input that can be fetched four bytes at a time: word_at(j) returns bytes j..j+3 (byte j in the
 // low bits; j is arbitrary, reading up to 3 bytes past nb must be harmless); tabs = the four tables in shared memory.
 template <int THREADS, typename WordAt>
 __device__ __forceinline__ uint16_t cta_crc16_words(WordAt word_at, uint32_t nb, const uint16_t (*tabs)[256], uint32_t* warp_x, int tid) {
@@ -250,11 +250,15 @@ __device__ __forceinline__ uint16_t cta_crc16_words(WordAt word_at, uint32_t nb,
     }
     acc = __reduce_xor_sync(0xffffffffu, acc);
     if ((tid & 31) == 0) warp_x[tid >> 5] = acc;
-    __syncthreads();
+    // only warp 0 needs the partial results: the other warps signal and go on with their next job (named barrier 1)
     uint32_t r = 0;
     if (tid < 32) {
+        asm volatile("bar.sync 1, %0;" :: "n"(THREADS) : "memory");
         r = (tid < THREADS / 32) ? warp_x[tid] : 0u;
         r = __reduce_xor_sync(0xffffffffu, r);
+    } else {
+        __threadfence_block();
+        asm volatile("bar.arrive 1, %0;" :: "n"(THREADS) : "memory");
     }
     return (uint16_t)r;
 }
