@@ -209,25 +209,47 @@ dec_sync_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ s
     if (!pass && lane == 0) seg_count[seg] = count;
 }
 
-// Generic single-CTA exclusive scan of uint32 -> uint64 (counts are small; n up to a few million)
+// Generic single-CTA exclusive scan of uint32 -> uint32 / uint64 (n up to a few million; 64-bit sums throughout: the
+// per-stream element counts can approach 2^32).  Tiles of 4096 elements: coalesced loads (the next tile is requested
+// before the current one is scanned), per-thread prefix of 4, warp shuffles, one pass over the data.
 __global__ void __launch_bounds__(1024)
 dec_scan_u32_kernel(const uint32_t* __restrict__ in, int n, uint32_t* __restrict__ out32, uint64_t* __restrict__ out64, uint64_t* __restrict__ total) {
-    __shared__ unsigned long long part[1024];
-    const int tid = threadIdx.x, per = (n + 1023) / 1024;
-    const int lo = min(n, tid * per), hi = min(n, lo + per);
-    unsigned long long s = 0;
-    for (int i = lo; i < hi; i++) s += in[i];
-    part[tid] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const unsigned long long v = (tid >= o) ? part[tid - o] : 0ull;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
+    typedef unsigned long long u64;
+    __shared__ u64 warp_tot[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u64 carry = 0;
+    auto load4 = [&](int base, uint32_t (&v)[4]) {
+        const int i0 = base + 4 * tid;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (i0 + k < n) ? in[i0 + k] : 0u;
+    };
+    uint32_t cur[4], nxt[4];
+    load4(0, cur);
+    int par = 0;
+    for (int base = 0; base < n; base += 4096, par ^= 1) {
+        load4(base + 4096, nxt);
+        const u64 s1 = (u64)cur[0] + cur[1], s2 = s1 + cur[2], s3 = s2 + cur[3];
+        u64 inc = s3;                                                        // inclusive scan of the threads' sums within the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) warp_tot[par][warp] = inc;
+        __syncthreads();                                                     // (the other parity's totals are free again by now)
+        const u64 wt = warp_tot[par][lane];
+        u64 winc = wt;                                                       // every warp scans the 32 warp totals itself
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        const u64 warp_excl = __shfl_sync(0xffffffffu, winc - wt, warp);
+        const u64 tile_total = __shfl_sync(0xffffffffu, winc, 31);
+        const u64 e0 = carry + warp_excl + (inc - s3);
+        const int i0 = base + 4 * tid;
+        const u64 e[4] = {e0, e0 + cur[0], e0 + s1, e0 + s2};
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i0 + k < n) { if (out32) out32[i0 + k] = (uint32_t)e[k]; if (out64) out64[i0 + k] = e[k]; }
+        carry += tile_total;
+#pragma unroll
+        for (int k = 0; k < 4; k++) cur[k] = nxt[k];
     }
-    unsigned long long run = part[tid] - s;
-    for (int i = lo; i < hi; i++) { if (out32) out32[i] = (uint32_t)run; if (out64) out64[i] = run; run += in[i]; }
-    if (tid == 1023 && total) *total = part[1023];
+    if (tid == 0 && total) *total = carry;
 }
 
 __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, uint32_t* __restrict__ sizes) {
