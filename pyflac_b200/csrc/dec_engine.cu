@@ -310,9 +310,10 @@ extern "C" int flacb200_decode_batch_host(flacb200_ctx* ctx, const uint8_t* blob
     }
     // chunks of whole streams with about equal byte counts
     // Chunks must still fill the GPU (the frame kernel decodes one frame per thread and a launch cannot finish faster than
-    // one frame's serial decode, a few ms): one chunk per ~300 MB of FLAC.  All table uploads of a chunk are submitted before
+    // one frame's serial decode, about 2 ms): one chunk per ~200 MB of FLAC (measured on 1.26 GB: 1/2/4/6/8 chunks take
+    // 72/68/57.5/55/56 ms).  All table uploads of a chunk are submitted before
     // the next chunk's bytes and every readback goes through mapped memory, so the bulk copies never delay the small ones.
-    int nchunks = (int)(blob_bytes / (300ull << 20));
+    int nchunks = (int)(blob_bytes / (200ull << 20));
     if (const char* ev = getenv("FLACB200_DEC_CHUNKS")) { const int v = atoi(ev); if (v > 0) nchunks = v; }
     if (nchunks < 1) nchunks = 1;
     if (nchunks > 12) nchunks = 12;
