@@ -46,6 +46,11 @@ extern FLAC__bool FLAC__stream_encoder_disable_instruction_set(FLAC__StreamEncod
 extern FLAC__bool FLAC__stream_encoder_set_blocksize(FLAC__StreamEncoder *, uint32_t);
 extern FLAC__bool FLAC__stream_encoder_set_limit_min_bitrate(FLAC__StreamEncoder *, FLAC__bool);
 extern FLAC__bool FLAC__stream_encoder_set_do_md5(FLAC__StreamEncoder *, FLAC__bool);
+extern FLAC__bool FLAC__stream_encoder_set_max_lpc_order(FLAC__StreamEncoder *, uint32_t);
+extern FLAC__bool FLAC__stream_encoder_set_qlp_coeff_precision(FLAC__StreamEncoder *, uint32_t);
+extern FLAC__bool FLAC__stream_encoder_set_do_exhaustive_model_search(FLAC__StreamEncoder *, FLAC__bool);
+extern FLAC__bool FLAC__stream_encoder_set_min_residual_partition_order(FLAC__StreamEncoder *, uint32_t);
+extern FLAC__bool FLAC__stream_encoder_set_max_residual_partition_order(FLAC__StreamEncoder *, uint32_t);
 extern int FLAC__stream_encoder_init_stream(FLAC__StreamEncoder *, enc_write_cb, enc_seek_cb, enc_tell_cb, enc_meta_cb, void *);
 extern FLAC__bool FLAC__stream_encoder_process_interleaved(FLAC__StreamEncoder *, const int32_t *, uint32_t);
 extern FLAC__bool FLAC__stream_encoder_finish(FLAC__StreamEncoder *);
@@ -140,6 +145,14 @@ long ref_encode_stream(const ref_enc_cfg *cfg, const int32_t *pcm, uint64_t nsam
     FLAC__stream_encoder_set_sample_rate(e, cfg->sample_rate);
     FLAC__stream_encoder_set_compression_level(e, cfg->level);
     { const char *ev = getenv("REF_DISABLE_SIMD"); if (ev) FLAC__stream_encoder_disable_instruction_set(e, (uint32_t)strtoul(ev, 0, 0)); }
+    /* tuning away from the presets (stream_encoder.h:993-1115): only used to make DECODE fixtures whose subframes the
+     * presets never produce (orders above 12, partition orders above 6, exhaustive order search) */
+    { const char *ev;
+      if ((ev = getenv("REF_MAX_LPC_ORDER"))) FLAC__stream_encoder_set_max_lpc_order(e, (uint32_t)atoi(ev));
+      if ((ev = getenv("REF_QLP_PRECISION"))) FLAC__stream_encoder_set_qlp_coeff_precision(e, (uint32_t)atoi(ev));
+      if ((ev = getenv("REF_EXHAUSTIVE"))) FLAC__stream_encoder_set_do_exhaustive_model_search(e, atoi(ev));
+      if ((ev = getenv("REF_MIN_PART_ORDER"))) FLAC__stream_encoder_set_min_residual_partition_order(e, (uint32_t)atoi(ev));
+      if ((ev = getenv("REF_MAX_PART_ORDER"))) FLAC__stream_encoder_set_max_residual_partition_order(e, (uint32_t)atoi(ev)); }
     FLAC__stream_encoder_set_blocksize(e, cfg->blocksize);
     FLAC__stream_encoder_set_streamable_subset(e, cfg->streamable_subset);
     FLAC__stream_encoder_set_limit_min_bitrate(e, cfg->limit_min_bitrate);

@@ -54,3 +54,14 @@ def pcm_md5(x, bps):
     w = (bps + 7) // 8
     raw = np.ascontiguousarray(np.asarray(x).astype("<i4")).view(np.uint8).reshape(-1, 4)
     return hashlib.md5(np.ascontiguousarray(raw[:, :w]).tobytes()).hexdigest()
+
+
+def foreign_cases():
+    """decode fixtures the presets never produce (tests/golden/make_foreign.py): tuned libFLAC output and hand-written streams"""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "foreign", "foreign.json")) as f:
+        return json.load(f)["cases"]
+
+
+def foreign_path(name):
+    return os.path.join(ROOT, "tests", "golden", "foreign", name)

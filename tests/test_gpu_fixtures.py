@@ -8,7 +8,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from conftest import fixture_cases, fixture_path, pcm_md5
+from conftest import fixture_cases, fixture_path, foreign_cases, foreign_path, pcm_md5
 
 pytestmark = pytest.mark.gpu
 FIX = fixture_cases()
@@ -112,3 +112,30 @@ def test_file_encoder_on_fixture_audio(checkers):
             _write_wav(wavp, x, c["sample_rate"], c["bps"])
             data = pf.FileEncoder(wavp, flacp, compression_level=5).process()
             assert data == _blob(c["level5"]["file"]) == open(flacp, "rb").read(), c["name"]
+
+
+def test_batch_decode_foreign_streams(eng, checkers):
+    """streams the presets never produce (tests/golden/foreign): predictor orders up to 32 (the decoder's generic path),
+    partition order 8, partitions of 9 samples, 16-sample blocks, escape-coded partitions with 0..22 raw bits, 5-bit Rice
+    parameters, CONSTANT / VERBATIM / FIXED side by side, wasted bits, every channel assignment"""
+    from pyflac_b200 import _native as nat
+    cases = foreign_cases()
+    blobs = {c["name"]: open(foreign_path(c["name"] + ".flac"), "rb").read() for c in cases}
+    for grp in ([c for c in cases if c["bps"] <= 16], [c for c in cases if c["bps"] > 16]):
+        out, infos = nat.decode_streams(eng, [blobs[c["name"]] for c in grp])
+        for c, o, si in zip(grp, out, infos):
+            assert si.status == 0, (c["name"], nat.DEC_STATUS.get(si.status))
+            assert o.shape == (c["samples"], c["channels"]) and si.bits_per_sample == c["bps"]
+            assert pcm_md5(o, c["bps"]) == c["pcm_md5"], c["name"]
+            want, _ = checkers.oracle_decode(blobs[c["name"]])
+            assert np.array_equal(o.astype(np.int64), want.astype(np.int64)), c["name"]
+    # and one of them through the drop-in stream decoder, fed in small pieces
+    import pyflac_b200 as pf
+    c = next(c for c in cases if c["name"] == "crafted_method1_s16_st_bs4096")
+    got = []
+    dec = pf.StreamDecoder(write_callback=lambda a, sr, ch, n: got.append(a.copy()))
+    data = blobs[c["name"]]
+    for i in range(0, len(data), 3000):
+        dec.process(data[i:i + 3000])
+    dec.finish()
+    assert pcm_md5(np.concatenate(got), 16) == c["pcm_md5"]

@@ -163,6 +163,21 @@ def test_oracle_on_imported_reference_fixtures(checkers):
             assert checkers.oracle_encode(x, c["sample_rate"], c["bps"], 5, 0) == want, c["name"]
 
 
+def test_oracle_decodes_foreign_streams(checkers):
+    """tests/golden/foreign: predictor orders up to 32, partition order 8, 9-sample partitions, 16-sample blocks (libFLAC with
+    tuned settings) and hand-written streams with escape partitions / 5-bit Rice parameters -- each was accepted by the
+    bundled libFLAC decoder when it was made; the oracle must hash to the STREAMINFO MD5 and, when the binary is here, equal it."""
+    from conftest import foreign_cases, foreign_path, pcm_md5
+    for c in foreign_cases():
+        data = open(foreign_path(c["name"] + ".flac"), "rb").read()
+        pcm, info = checkers.oracle_decode(data)
+        assert pcm.shape == (c["samples"], c["channels"]) and info["bps"] == c["bps"]
+        assert pcm_md5(pcm, c["bps"]) == c["pcm_md5"] == data[26:42].hex(), c["name"]
+        if checkers.ref_available():
+            ref, rinfo = checkers.ref_decode(data)
+            assert rinfo["errors"] == 0 and np.array_equal(ref, pcm), c["name"]
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/tests/data"), reason="reference fixtures not present")
 def test_oracle_decodes_reference_fixtures(checkers):
     """tests/data/{mono,stereo,surround,32bit}.flac <-> .wav pairs: STREAMINFO MD5 == MD5 of decoded PCM."""
