@@ -1,7 +1,7 @@
 """GPU parity diagnostic: encode the golden cases (and optional extra corpus) on the GPU and, for every
 mismatch against libFLAC's bytes, locate the first diverging decision by comparing the kernel's
 analysis trace with the oracle's trace.  Test tooling (uses oracle/); run on the GPU box:
-    python tools/diag_encode.py [--extra]
+    python tests/diag_encode.py [--extra]
 """
 import json
 import os
