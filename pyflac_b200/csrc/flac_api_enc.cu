@@ -290,8 +290,13 @@ SETTER(sample_rate, uint32_t, sample_rate)
 SETTER(blocksize, uint32_t, blocksize)
 SETTER(streamable_subset, FLAC__bool, streamable_subset)
 SETTER(limit_min_bitrate, FLAC__bool, limit_min_bitrate)
-SETTER(total_samples_estimate, FLAC__uint64, total_samples_estimate)
 #undef SETTER
+// STREAMINFO holds total_samples in 36 bits; libFLAC clamps the estimate on the way in (ref: format.h:536 FLAC__STREAM_METADATA_STREAMINFO_TOTAL_SAMPLES_LEN)
+FLAC__bool FLAC__stream_encoder_set_total_samples_estimate(FLAC__StreamEncoder* e, FLAC__uint64 v) {
+    EncImpl* m = I(e); if (!m || m->state != ST_UNINITIALIZED) return 0;
+    const FLAC__uint64 lim = (1ull << 36) - 1;
+    m->total_samples_estimate = v < lim ? v : lim; return 1;
+}
 FLAC__bool FLAC__stream_encoder_set_compression_level(FLAC__StreamEncoder* e, uint32_t v) {
     EncImpl* m = I(e); if (!m || m->state != ST_UNINITIALIZED) return 0;
     m->level = v > 8 ? 8 : v; m->custom_tuning = false; return 1;

@@ -1,0 +1,137 @@
+"""CPU tests of the drop-in layer's CONTROL surface (no GPU needed: nothing is initialised): the FLAC__stream_encoder_* /
+FLAC__stream_decoder_* setters, getters, defaults, preset table and string tables of libflacb200.so compared call by call
+with the reference's libFLAC 1.4.3 (oracle/_ref) -- the part of the boundary pyFLAC's properties read
+(pyflac/encoder.py:141-231, pyflac/decoder.py:108; stream_encoder.h:803-864 for the presets)."""
+import ctypes as C
+import os
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def libs(checkers):
+    if not checkers.ref_available():
+        pytest.skip("oracle/_ref not present")
+    from pyflac_b200 import _native
+    ours = C.CDLL(_native.LIB_PATH)
+    ref = C.CDLL(os.path.join(checkers.ORACLE_DIR, "_ref", "libFLAC-12.1.0.so"))
+    for L in (ours, ref):
+        L.FLAC__stream_encoder_new.restype = C.c_void_p
+        L.FLAC__stream_decoder_new.restype = C.c_void_p
+        L.FLAC__stream_encoder_get_resolved_state_string.restype = C.c_char_p
+        L.FLAC__stream_decoder_get_resolved_state_string.restype = C.c_char_p
+    return ours, ref
+
+
+ENC_GETTERS = ["state", "verify", "streamable_subset", "channels", "bits_per_sample", "sample_rate", "blocksize", "do_mid_side_stereo",
+               "loose_mid_side_stereo", "max_lpc_order", "qlp_coeff_precision", "do_qlp_coeff_prec_search", "do_escape_coding",
+               "do_exhaustive_model_search", "min_residual_partition_order", "max_residual_partition_order",
+               "rice_parameter_search_dist", "limit_min_bitrate"]
+
+
+def _enc_snapshot(L, e):
+    out = {}
+    for g in ENC_GETTERS:
+        f = getattr(L, "FLAC__stream_encoder_get_" + g)
+        f.argtypes = [C.c_void_p]
+        f.restype = C.c_uint32
+        out[g] = f(e)
+    f = L.FLAC__stream_encoder_get_total_samples_estimate
+    f.argtypes = [C.c_void_p]
+    f.restype = C.c_uint64
+    out["total_samples_estimate"] = f(e)
+    L.FLAC__stream_encoder_get_resolved_state_string.argtypes = [C.c_void_p]
+    out["state_string"] = L.FLAC__stream_encoder_get_resolved_state_string(e)
+    return out
+
+
+def _set(L, e, name, v):
+    f = getattr(L, "FLAC__stream_encoder_set_" + name)
+    f.argtypes = [C.c_void_p, C.c_uint64 if name == "total_samples_estimate" else C.c_uint32]
+    f.restype = C.c_int
+    return f(e, v)
+
+
+def test_encoder_defaults_and_presets_match_libflac(libs):
+    ours, ref = libs
+    snaps = []
+    for L in libs:
+        L.FLAC__stream_encoder_delete.argtypes = [C.c_void_p]
+        e = L.FLAC__stream_encoder_new()
+        s = [("new", _enc_snapshot(L, e))]
+        for level in list(range(9)) + [12, 5]:                      # 12: above the table (libFLAC clamps to 8)
+            r = _set(L, e, "compression_level", level)
+            s.append((f"level {level}", r, _enc_snapshot(L, e)))
+        L.FLAC__stream_encoder_delete(e)
+        snaps.append(s)
+    assert snaps[0] == snaps[1]
+
+
+def test_encoder_setters_round_trip_like_libflac(libs):
+    """the setters pyFLAC uses (pyflac/encoder.py:145-231) plus blocksize / sample-rate extremes: same return values and the same
+    values read back -- libFLAC stores what it is given and validates at init (stream_encoder.h:1471-1532)"""
+    script = [("channels", 2), ("channels", 0), ("channels", 9), ("bits_per_sample", 16), ("bits_per_sample", 33), ("bits_per_sample", 3),
+              ("sample_rate", 48000), ("sample_rate", 0), ("sample_rate", 1048576), ("blocksize", 4096), ("blocksize", 15), ("blocksize", 65536),
+              ("verify", 1), ("verify", 0), ("streamable_subset", 0), ("limit_min_bitrate", 1), ("total_samples_estimate", 123456789012),
+              ("compression_level", 3), ("blocksize", 0)]
+    snaps = []
+    for L in libs:
+        e = L.FLAC__stream_encoder_new()
+        s = []
+        for name, v in script:
+            s.append((name, v, _set(L, e, name, v), _enc_snapshot(L, e)))
+        L.FLAC__stream_encoder_delete(e)
+        snaps.append(s)
+    for a, b in zip(*snaps):
+        assert a == b
+
+
+def test_uninitialised_calls_behave_like_libflac(libs):
+    """process / finish on a handle that was never initialised, and the decoder's defaults"""
+    res = []
+    for L in libs:
+        e = L.FLAC__stream_encoder_new()
+        L.FLAC__stream_encoder_finish.argtypes = [C.c_void_p]
+        L.FLAC__stream_encoder_finish.restype = C.c_int
+        r = [L.FLAC__stream_encoder_finish(e), _enc_snapshot(L, e)["state"]]
+        L.FLAC__stream_encoder_delete(e)
+        d = L.FLAC__stream_decoder_new()
+        for g in ["state", "md5_checking", "channels", "bits_per_sample", "sample_rate", "blocksize"]:
+            f = getattr(L, "FLAC__stream_decoder_get_" + g)
+            f.argtypes = [C.c_void_p]
+            f.restype = C.c_uint32
+            r.append((g, f(d)))
+        L.FLAC__stream_decoder_get_resolved_state_string.argtypes = [C.c_void_p]
+        r.append(L.FLAC__stream_decoder_get_resolved_state_string(d))
+        for name in ["finish", "flush", "reset", "process_single", "process_until_end_of_stream"]:
+            f = getattr(L, "FLAC__stream_decoder_" + name)
+            f.argtypes = [C.c_void_p]
+            f.restype = C.c_int
+            r.append((name, f(d)))
+        f = L.FLAC__stream_decoder_set_md5_checking
+        f.argtypes = [C.c_void_p, C.c_int]
+        f.restype = C.c_int
+        r.append(("set_md5_checking", f(d, 1), L.FLAC__stream_decoder_get_md5_checking(d)))
+        L.FLAC__stream_decoder_delete.argtypes = [C.c_void_p]
+        L.FLAC__stream_decoder_delete(d)
+        res.append(r)
+    assert res[0] == res[1]
+
+
+def test_string_tables_match_libflac(libs):
+    tables = {"FLAC__StreamEncoderStateString": 9, "FLAC__StreamEncoderInitStatusString": 14, "FLAC__StreamDecoderStateString": 10,
+              "FLAC__StreamDecoderInitStatusString": 6, "FLAC__StreamDecoderErrorStatusString": 5,
+              "FLAC__StreamEncoderWriteStatusString": 2, "FLAC__StreamDecoderWriteStatusString": 2}
+    for sym, n in tables.items():
+        got = []
+        for L in libs:
+            try:
+                arr = (C.c_char_p * n).in_dll(L, sym)
+            except ValueError:
+                got.append(None)
+                continue
+            got.append([arr[i] for i in range(n)])
+        if got[0] is None:                                    # not every table is part of pyFLAC's cdef; the ones it reads must be there
+            assert sym in ("FLAC__StreamEncoderWriteStatusString", "FLAC__StreamDecoderWriteStatusString"), sym
+            continue
+        assert got[0] == got[1], sym
