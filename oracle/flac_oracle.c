@@ -184,6 +184,8 @@ int fo_encoder_init_status(const fo_enc_cfg *c, int has_write, int has_seek, int
         if (!(c->bps == 8 || c->bps == 12 || c->bps == 16 || c->bps == 20 || c->bps == 24 || c->bps == 32)) return 11; /* NOT_STREAMABLE */
         if (c->sample_rate <= 48000 && (bs > 4608 || maxlpc > 12)) return 11;
         if (bs > 16384) return 11;
+        /* up: FLAC__format_sample_rate_is_subset: above 16 bits the frame header can only carry multiples of 10 Hz */
+        if (c->sample_rate >= (1u << 16) && c->sample_rate % 10u != 0u) return 11;
     }
     return 0;
 }
@@ -794,7 +796,8 @@ static int encode_frame(enc_t *e, int64_t *sigs[], uint32_t frame_number, bw_t *
         /* up: get_wasted_bits_wide_ (33-bit side of 32-bit input): an all-zero side reports ONE wasted bit, which moves it
          * onto the 32-bit paths (pinned: the binary writes CONSTANT, wasted = 1, 32-bit zero) */
         if (c == 1 && s->bps == 32 && wb == 0) { int allz = 1; for (uint32_t i = 0; i < N; i++) if (sigs[ch + 1][i]) { allz = 0; break; } if (allz) wb = 1; }
-        if (wb > s->bps) wb = s->bps; wst[ch + c] = wb; sbps[ch + c] = s->bps - wb + (c ? 1 : 0); }
+        if (wb > s->bps) wb = s->bps;
+        wst[ch + c] = wb; sbps[ch + c] = s->bps - wb + (c ? 1 : 0); }
 
     /* every signal gets its own residual buffer so the winner survives the next call */
     for (uint32_t c = 0; c < ch + 2; c++) resbuf[c] = 0;

@@ -142,6 +142,8 @@ extern "C" int flacb200_enc_validate(const flacb200_enc_config* c) {
         if (!(b == 8 || b == 12 || b == 16 || b == 20 || b == 24 || b == 32)) return 11;
         if (c->sample_rate <= 48000 && (bs > 4608 || maxlpc > 12)) return 11;
         if (bs > 16384) return 11;
+        // a subset frame header must be able to carry the rate: above 16 bits only multiples of 10 Hz can (format.h:  FLAC__format_sample_rate_is_subset)
+        if (c->sample_rate >= (1u << 16) && c->sample_rate % 10u != 0u) return 11;
     }
     return 0;
 }

@@ -135,3 +135,30 @@ def test_string_tables_match_libflac(libs):
             assert sym in ("FLAC__StreamEncoderWriteStatusString", "FLAC__StreamDecoderWriteStatusString"), sym
             continue
         assert got[0] == got[1], sym
+
+
+def test_init_validation_matches_libflac_without_a_device(libs):
+    """init_stream validates the settings before it touches the GPU, in libFLAC's order: every rejected
+    configuration returns libFLAC's status; an accepted one returns OK -- or ENCODER_ERROR here, where there is no device"""
+    import itertools
+    import numpy as np
+    import _flacapi as fa
+    ours, ref = libs
+    x = np.zeros((4, 2), np.int16)
+    grid = itertools.product([0, 1, 8000, 48000, 96000, 655350, 655351, 1048575], [3, 4, 8, 16, 24, 32, 33], [0, 15, 16, 1152, 4608, 4609, 16384, 16385, 65535],
+                             [0, 5, 8], [True, False])
+    n_bad = 0
+    for sr, bps, bs, level, subset in grid:
+        kw = dict(sample_rate=sr, bps=bps, level=level, blocksize=bs, streamable_subset=subset, init_only=True)
+        a = fa.encode_session(ours, x, **kw)["init_status"]
+        b = fa.encode_session(ref, x, **kw)["init_status"]
+        if b == 0:
+            assert a in (0, 1), (kw, a, b)
+        else:
+            n_bad += 1
+            assert a == b, (kw, a, b)
+    assert n_bad > 100
+    for ch in (0, 1, 8, 9):                                                 # channel count; missing write callback
+        xc = np.zeros((4, max(ch, 1)), np.int16)
+        a, b = [fa.encode_session(L, xc, 48000, 16, init_only=True)["init_status"] if ch else None for L in (ours, ref)]
+        assert (a == b) or (b == 0 and a == 1), (ch, a, b)
