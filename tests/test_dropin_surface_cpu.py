@@ -162,3 +162,41 @@ def test_init_validation_matches_libflac_without_a_device(libs):
         xc = np.zeros((4, max(ch, 1)), np.int16)
         a, b = [fa.encode_session(L, xc, 48000, 16, init_only=True)["init_status"] if ch else None for L in (ours, ref)]
         assert (a == b) or (b == 0 and a == 1), (ch, a, b)
+
+
+def test_init_callback_and_file_errors_match_libflac(libs):
+    """missing callbacks, seek without tell, files that cannot be opened: same init status and same state afterwards
+    (reference tests: tests/test_decoder.py:107-111 `test_process_invalid_file`, tests/test_encoder.py:233-252)"""
+    import _flacapi as fa
+    res = []
+    for L in libs:
+        r = []
+        L.FLAC__stream_decoder_init_stream.argtypes = [C.c_void_p] * 10
+        L.FLAC__stream_decoder_init_stream.restype = C.c_int
+        L.FLAC__stream_decoder_init_file.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.FLAC__stream_decoder_init_file.restype = C.c_int
+        L.FLAC__stream_decoder_get_state.argtypes = [C.c_void_p]
+        L.FLAC__stream_decoder_delete.argtypes = [C.c_void_p]
+        rd, wr, er = fa.DEC_READ_CB(lambda *a: 0), fa.DEC_WRITE_CB(lambda *a: 0), fa.DEC_ERROR_CB(lambda *a: None)
+        p = lambda f: C.cast(f, C.c_void_p)                                  # noqa: E731
+        d = L.FLAC__stream_decoder_new()
+        r.append(L.FLAC__stream_decoder_init_stream(d, None, None, None, None, None, p(wr), None, p(er), None))      # no read callback
+        r.append(L.FLAC__stream_decoder_init_stream(d, p(rd), None, None, None, None, None, None, p(er), None))      # no write callback
+        r.append(L.FLAC__stream_decoder_init_stream(d, p(rd), None, None, None, None, p(wr), None, None, None))      # no error callback
+        r.append(L.FLAC__stream_decoder_init_stream(d, p(rd), p(rd), None, None, None, p(wr), None, p(er), None))    # seek without tell/length/eof
+        r.append(L.FLAC__stream_decoder_init_file(d, b"/nonexistent/dir/x.flac", p(wr), None, p(er), None))
+        r.append(L.FLAC__stream_decoder_init_file(d, b"/nonexistent/dir/x.flac", None, None, p(er), None))
+        r.append(L.FLAC__stream_decoder_get_state(d))
+        L.FLAC__stream_decoder_delete(d)
+        fa._proto(L)
+        L.FLAC__stream_encoder_init_stream.argtypes = [C.c_void_p] * 6
+        w, s, t = fa.WRITE_CB(lambda *a: 0), fa.SEEK_CB(lambda *a: 0), fa.TELL_CB(lambda *a: 0)
+        e = L.FLAC__stream_encoder_new()
+        r.append(L.FLAC__stream_encoder_init_stream(e, None, None, None, None, None))                                 # no write callback
+        r.append(L.FLAC__stream_encoder_init_stream(e, p(w), p(s), None, None, None))                                 # seek without tell
+        r.append(L.FLAC__stream_encoder_get_state(e))
+        r.append(L.FLAC__stream_encoder_init_file(e, b"/nonexistent/dir/x.flac", None, None))
+        r.append(L.FLAC__stream_encoder_get_state(e))
+        L.FLAC__stream_encoder_delete(e)
+        res.append(r)
+    assert res[0] == res[1], res
