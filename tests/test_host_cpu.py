@@ -139,3 +139,34 @@ def test_package_surface_matches_reference_names():
     assert str(pf.DecoderState.UNINITIALIZED) == "FLAC__STREAM_DECODER_UNINITIALIZED"
     assert str(pf.EncoderInitException(3)) == "FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_CALLBACKS"
     assert str(pf.DecoderInitException(4)) == "FLAC__STREAM_DECODER_INIT_STATUS_ERROR_OPENING_FILE"
+
+
+def test_encoder_and_decoder_properties_without_a_device():
+    """reference tests/test_encoder.py:32-93 and tests/test_decoder.py:37-40: property setters / getters and the state of a
+    handle that was never initialised need no GPU; initialising one without a device fails loudly (no CPU fallback)"""
+    import numpy as np
+    import pytest
+    import pyflac_b200 as pf
+    from pyflac_b200.encoder import _Encoder
+    from pyflac_b200.decoder import _Decoder
+    e = _Encoder()
+    assert e._limit_min_bitrate is False or e._limit_min_bitrate == 0
+    for name, val in [("_verify", True), ("_channels", 2), ("_bits_per_sample", 24), ("_sample_rate", 48000), ("_blocksize", 128),
+                      ("_streamable_subset", False), ("_limit_min_bitrate", True)]:
+        setattr(e, name, val)
+        assert getattr(e, name) == val
+    e._compression_level = 8
+    assert e.state == pf.EncoderState.UNINITIALIZED and str(e.state) == "FLAC__STREAM_ENCODER_UNINITIALIZED"
+    with pytest.raises(TypeError):
+        e.process([1, 2, 3, 4])
+    d = _Decoder()
+    assert d.state == pf.DecoderState.UNINITIALIZED and str(d.state) == "FLAC__STREAM_DECODER_UNINITIALIZED"
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        has_gpu = False
+    if not has_gpu:
+        with pytest.raises(pf.EncoderInitException) as ei:
+            pf.StreamEncoder(48000, lambda *a: None).process(np.zeros((4096, 2), np.int16))
+        assert "ENCODER_ERROR" in str(ei.value)
