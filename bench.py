@@ -45,6 +45,7 @@ UNIT = "MSamples/s"
 
 
 # DRAM bytes per launch on the bench batch, from the committed ncu --set full capture (profiles/r01d_ncu_encode_kernels.txt)
+NCU_TRAFFIC_BYTES_DEC_FRAME = 2211892000 + 4882201000     # dec_frame_kernel on the 4096-stream decode leg (profiles/r01e_ncu_decode_kernels_4096_streams.txt)
 NCU_TRAFFIC_BYTES = {"autoc": 499152384 + 13786880, "analyze": 512133120 + 18882560, "pack": 502199552 + 264583168}
 
 
@@ -448,6 +449,7 @@ def main():
                                     "achieved": dec_bytes / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9,
                                     "peak": peak, "unit": "GB/s",
                                     "frac": dec_bytes / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9 / peak,
+                                    "traffic": NCU_TRAFFIC_BYTES_DEC_FRAME, "traffic_source": "profiles/r01e_ncu_decode_kernels_4096_streams.txt (int32 planar scratch: 2 x the int16 PCM the path finally writes)",
                                     "algorithmic_bytes_per_launch": dec_bytes}},
             "decode_roundtrip_256": {"value": world * total_samples / (rt_dev_max * 1e-3) / 1e6, "e2e_value": world * total_samples / (rt_e2e_max * 1e-3) / 1e6,
                                      "unit": UNIT, "ms_per_step": rt_dev_max, "e2e_ms_per_step": rt_e2e_max, "kernel_ms": rt_kt,
