@@ -45,8 +45,9 @@ UNIT = "MSamples/s"
 
 
 # DRAM bytes per launch on the bench batch, from the committed ncu --set full capture (profiles/r01d_ncu_encode_kernels.txt)
-NCU_TRAFFIC_BYTES_DEC_FRAME = 2211892000 + 4882201000     # dec_frame_kernel on the 4096-stream decode leg (profiles/r01e_ncu_decode_kernels_4096_streams.txt)
 NCU_TRAFFIC_BYTES = {"autoc": 499152384 + 13786880, "analyze": 512133120 + 18882560, "pack": 502199552 + 264583168}
+# dec_frame_kernel on the 4096-stream decode leg (profiles/r01e_ncu_decode_kernels_4096_streams.txt)
+NCU_TRAFFIC_BYTES_DEC_FRAME = 2211892000 + 4882201000
 
 
 def workload_config():
