@@ -11,7 +11,8 @@ def main():
     p.add_argument("-o", "--output-file", type=Path)
     p.add_argument("-c", "--compression-level", type=int, choices=range(9), default=5)
     p.add_argument("-b", "--block-size", type=int, default=0)
-    p.add_argument("-v", "--verify", action="store_true")
+    # as in the reference: verification is ON unless -v is given (pyflac/__main__.py:31)
+    p.add_argument("-v", "--verify", action="store_false", default=True)
     a = p.parse_args()
     with open(a.input_file, "rb") as f:
         magic = f.read(4)
@@ -22,7 +23,7 @@ def main():
         out = a.output_file or a.input_file.with_suffix(".wav")
         FileDecoder(a.input_file, out).process()
     else:
-        raise SystemExit("input must be a WAV or FLAC file")
+        raise ValueError("Please provide either a WAV or a FLAC file")
     print(out)
 
 
