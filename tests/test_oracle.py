@@ -95,6 +95,29 @@ def test_oracle_vs_reference_binary_edges(checkers):
 
 
 @needs_ref
+def test_oracle_vs_reference_binary_random_settings(checkers):
+    """seeded random walk over depth / channels / level / blocksize / length / signal kind / flags: the restatement and the
+    bundled binary must agree byte for byte (encode) and the oracle must decode the binary's bytes back to the input"""
+    rng = np.random.default_rng(20240607)
+    for it in range(48):
+        bps = int(rng.choice([4, 8, 12, 13, 16, 16, 16, 20, 24, 24]))
+        ch = int(rng.choice([1, 1, 2, 2, 2, 3, 5, 8]))
+        level = int(rng.integers(0, 9))
+        bs = int(rng.choice([0, 0, 16, 64, 192, 255, 256, 1000, 1152, 2048, 4096, 4608]))
+        n = int(rng.choice([1, 7, 100, 1153, 3000, 4096, 4097, 9000, 12288]))
+        kind = str(rng.choice(CORPUS_KINDS))
+        lmb = bool(rng.integers(0, 2))
+        sr = int(rng.choice([8000, 22050, 44100, 48000]))
+        subset = bps in (8, 12, 16, 20, 24)
+        x = corpus_signal(kind, n, ch, bps, seed=1000 + it, sample_rate=sr)
+        a = checkers.oracle_encode(x, sr, bps, level, bs, limit_min_bitrate=lmb, streamable_subset=subset)
+        b = checkers.ref_encode(x, sr, bps, level, bs, limit_min_bitrate=lmb, streamable_subset=subset)
+        assert a == b, (it, bps, ch, level, bs, n, kind, lmb, sr)
+        dec, info = checkers.oracle_decode(b)
+        assert info["bps"] == bps and np.array_equal(dec.reshape(n, ch), np.asarray(x).reshape(n, ch)), (it, "decode")
+
+
+@needs_ref
 def test_oracle_vs_reference_binary_32bit(checkers):
     """32-bit input: the _limit_residual predictor search as the shipped binary runs it (all-zero block CONSTANT, other
     constant blocks FIXED order 1, invalid orders when a residual leaves int32) and the 33-bit side channel of stereo
