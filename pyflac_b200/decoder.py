@@ -79,6 +79,10 @@ class _Decoder:
     def state(self) -> DecoderState:
         return DecoderState(self._lib.FLAC__stream_decoder_get_state(self._decoder))
 
+    def process(self):
+        """Overridden by the stream / file decoders (reference pyflac/decoder.py:110-111)."""
+        raise NotImplementedError
+
     # ---- trampolines shared by all decoder flavours
     def _on_write(self, _dec, frame, buffers, _cd):
         try:

@@ -192,3 +192,44 @@ def test_wav_reader_on_reference_wavs_when_present():
         assert hashlib.md5(np.ascontiguousarray(x).tobytes()).hexdigest() == c["wav_md5"], c["name"]
         y, sr2 = wav.read_float64(os.path.join(src, c["name"] + ".wav"))
         assert sr2 == sr and y.dtype == np.float64 and y.shape == x.shape and float(np.max(np.abs(y))) <= 1.0
+
+
+def test_public_signatures_match_reference_source_when_present():
+    """constructor and method signatures (names, order, defaults) of the five public classes, read from the reference's
+    source with `ast` (the reference package itself cannot be imported here: its cffi modules are not built)"""
+    import ast
+    import inspect
+    import pytest
+    import pyflac_b200 as pf
+    files = {"/root/reference/pyflac/encoder.py": ["StreamEncoder", "FileEncoder"],
+             "/root/reference/pyflac/decoder.py": ["StreamDecoder", "FileDecoder", "OneShotDecoder"]}
+    if not all(os.path.exists(f) for f in files):
+        pytest.skip("reference source not present")
+    for path, classes in files.items():
+        tree = ast.parse(open(path).read())
+        for node in tree.body:
+            if not (isinstance(node, ast.ClassDef) and node.name in classes):
+                continue
+            ours = getattr(pf, node.name)
+            for fn in node.body:
+                if not isinstance(fn, ast.FunctionDef) or (fn.name.startswith("_") and fn.name != "__init__"):
+                    continue
+                assert hasattr(ours, fn.name), (node.name, fn.name)
+                sig = inspect.signature(getattr(ours, fn.name))
+                ref_names = [a.arg for a in fn.args.args]
+                assert list(sig.parameters)[:len(ref_names)] == ref_names, (node.name, fn.name, list(sig.parameters), ref_names)
+                n_def = len(fn.args.defaults)
+                for a, d in zip(fn.args.args[len(fn.args.args) - n_def:], fn.args.defaults):
+                    want = ast.literal_eval(d)
+                    assert sig.parameters[a.arg].default == want, (node.name, fn.name, a.arg)
+    # the private base classes carry the properties pyFLAC's own tests poke (tests/test_encoder.py:32-93)
+    from pyflac_b200.encoder import _Encoder
+    from pyflac_b200.decoder import _Decoder
+    for path, cls, ours in [("/root/reference/pyflac/encoder.py", "_Encoder", _Encoder), ("/root/reference/pyflac/decoder.py", "_Decoder", _Decoder)]:
+        node = next(n for n in ast.parse(open(path).read()).body if isinstance(n, ast.ClassDef) and n.name == cls)
+        for fn in node.body:
+            if isinstance(fn, ast.FunctionDef) and not fn.name.startswith("__"):
+                assert hasattr(ours, fn.name), (cls, fn.name)
+                is_prop = any(isinstance(d, ast.Name) and d.id == "property" for d in fn.decorator_list)
+                if is_prop:
+                    assert isinstance(inspect.getattr_static(ours, fn.name), property), (cls, fn.name)
