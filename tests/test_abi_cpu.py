@@ -135,3 +135,30 @@ def test_crc16_chunk_combination(fbmath):
         e >>= 1
     assert crc(np.concatenate([a, b])) == (fbmath.t_crc16_mulmod(crc(a), xp) ^ crc(b))
     assert crc(b"123456789") == 0xFEE8
+
+
+def test_host_multibuffer_md5_matches_hashlib():
+    """the host->host encode path hashes the caller's PCM with 16-lane AVX-512 / 8-lane AVX2 / scalar MD5 (csrc/md5_mb.h,
+    md5_host.h): every path this CPU has against hashlib, ragged lengths incl. 0, 55, 56, 63, 64, 65 and multi-block"""
+    import hashlib
+    d = os.path.join(ROOT, "tests", "cpu_shim")
+    so = os.path.join(d, "libmd5_host_shim.so")
+    subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", so, os.path.join(d, "md5_host_shim.cpp")], check=True)
+    L = C.CDLL(so)
+    L.t_md5_group.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    widest = L.t_md5_lanes()
+    rng = np.random.default_rng(5)
+    lens_sets = [[0, 1, 55, 56, 57, 63, 64, 65, 119, 120, 128, 1000, 4096, 4097, 100000, 7],
+                 [1920000 // 8] * 16, [64 * 50] * 5 + [64 * 50 + 3] * 3, [200, 100, 300]]
+    for lens in lens_sets:
+        for n in sorted({len(lens), min(len(lens), 8), 1}):
+            ls = np.array(lens[:n], np.uint64)
+            off = np.concatenate([[0], np.cumsum(ls)[:-1]]).astype(np.uint64)
+            blob = rng.integers(0, 256, int(ls.sum()) + 64, dtype=np.uint8)
+            want = b"".join(hashlib.md5(blob[int(o):int(o + l)].tobytes()).digest() for o, l in zip(off, ls))
+            for lanes in (16, 8, 1):
+                if lanes > widest or (lanes == 8 and n > 8):
+                    continue
+                got = np.zeros(16 * n, np.uint8)
+                assert L.t_md5_group(blob.ctypes.data, off.ctypes.data, ls.ctypes.data, n, lanes, got.ctypes.data) == 0
+                assert got.tobytes() == want, (lens[:n], lanes)
