@@ -175,6 +175,11 @@ int  flacb200_kernel_times(flacb200_ctx *ctx, float *ms);
 /* Wall-clock breakdown (ms since entry) of the last flacb200_encode_batch_host call:
  * ms[1] work enqueued, ms[2] all chunks' kernels finished, ms[3] D2H finished, ms[4] host MD5 joined, ms[5] return. */
 int  flacb200_host_path_times(flacb200_ctx *ctx, double *ms);
+/* Tuning knobs of the two host -> host calls, read from the environment at call time (defaults are measured on a
+ * B200 / PCIe 5 host and normally right):
+ *   FLACB200_CHUNKS       pieces the PCM of flacb200_encode_batch_host is cut into for the H2D / kernel / D2H pipeline (default 12)
+ *   FLACB200_MD5_THREADS  host threads hashing the caller's PCM meanwhile (default: calibrated so they finish with the H2D copy)
+ *   FLACB200_DEC_CHUNKS   groups of streams flacb200_decode_batch_host pipelines (default: one per 200 MB of FLAC, at most 12) */
 /* Kernel launches issued by this ctx so far (bench.py's gpu_launches). */
 uint64_t flacb200_launch_count(const flacb200_ctx *ctx);
 
