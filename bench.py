@@ -458,7 +458,9 @@ def main():
                                                  "finish faster than one frame's serial decode, so this small batch is latency bound",
                                      "pcm_identical_to_input": bool(rt_ok)},
             "scatter_gather": sg,
-            "frames_per_step": n_frames * world, "compressed_bytes_per_step": out_bytes, "ratio": out_bytes / pcm_bytes,
+            "frames_per_step": n_frames * world, "frames_per_s": n_frames * world / (ms_per_step * 1e-3),
+            "x_realtime": value * 1e6 / (SAMPLE_RATE * CHANNELS), "x_realtime_e2e": e2e_val * 1e6 / (SAMPLE_RATE * CHANNELS),
+            "compressed_bytes_per_step": out_bytes, "ratio": out_bytes / pcm_bytes,
             "log_guard_hits": guard_hits,
         }
         if not args.no_cpu_baseline:
