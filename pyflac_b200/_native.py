@@ -70,9 +70,12 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
-        _build.build()
+    from . import build as _build
+    if _build.needs_build():
+        # sources newer than the library (or no library): rebuild when nvcc is here; a snapshot shipped to a box
+        # without nvcc keeps the library it came with
+        if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")) or not os.path.exists(LIB_PATH):
+            _build.build()
     L = C.CDLL(LIB_PATH)
     L.flacb200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     L.flacb200_destroy.argtypes = [C.c_void_p]
@@ -336,13 +339,19 @@ Engine.decode_fetch = _engine_decode_fetch
 Engine.decode_kernel_times = _engine_decode_kernel_times
 
 
-def decode_streams(engine, blobs, out_container_bytes=0):
-    """Convenience: decode a list of .flac byte strings -> list of (n, ch) arrays + infos."""
+def decode_streams(engine, blobs, out_container_bytes=0, check=False):
+    """Convenience: decode a list of .flac byte strings -> list of (n, ch) arrays + infos.
+    check=True raises NativeError when any stream ends with a non-zero status (truncated, CRC mismatch, ...);
+    otherwise the caller reads infos[s].status (DEC_STATUS)."""
     sizes = np.array([len(b) for b in blobs], np.uint64)
     offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64) if len(blobs) else np.zeros(0, np.uint64)
     blob = np.frombuffer(b"".join(blobs) + bytes(16), np.uint8)
     engine.decode_host(blob, offs, sizes, out_container_bytes)
     pcm, infos, _ = engine.decode_fetch()
+    if check:
+        bad = [(s, int(si.status)) for s, si in enumerate(infos) if si.status != 0]
+        if bad:
+            raise NativeError(6, "decode failed for streams " + ", ".join(f"{s}: {DEC_STATUS.get(st, st)}" for s, st in bad[:8]))
     out = []
     for si in infos:
         ch = max(int(si.channels), 1)

@@ -627,6 +627,9 @@ __global__ void dec_chain_kernel(DecCand* __restrict__ cands, const uint32_t* __
             const int st = cands[i].status;
             if (st != kDecOk) { r.status = st; break; }
             if (r.n_frames == 0) { r.sample_rate = cands[i].sample_rate; r.channels = cands[i].channels; r.bps = cands[i].bps; }
+            // the PCM layout scans 32-bit element counts per stream: a stream that would decode to 2^32 elements or more (a few MB
+            // of CONSTANT frames can) stops here with an error instead of wrapping the count
+            if ((r.total_samples + cands[i].blocksize) * (uint64_t)(r.channels ? r.channels : 1) > 0xFFFFFFF0ull) { r.status = kDecUnsupported; break; }
             cands[i].valid = 1; cands[i].sample_off = r.total_samples;
             r.total_samples += cands[i].blocksize; r.n_frames++;
             if (cands[i].blocksize > r.max_blocksize) r.max_blocksize = cands[i].blocksize;

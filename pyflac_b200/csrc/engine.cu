@@ -475,6 +475,9 @@ extern "C" int flacb200_encode_batch(flacb200_ctx* ctx, const flacb200_enc_confi
     const void* d_pcm = pcm;
     if (!pcm_is_device) {
         const size_t bytes = (size_t)pcm_elems * cfg->container_bytes;
+        // the MD5 of an earlier host-PCM batch may still be reading the staging buffer on its side stream
+        { int wrc = wait_all_sets(ctx, ctx->stream); if (wrc) return wrc; }
+        if (bytes + 64 > ctx->d_pcm.cap) for (auto& S : ctx->sets) if (S.busy) { CK(cudaStreamSynchronize(S.side)); S.busy = false; }   // about to free it
         CK(ctx->d_pcm.reserve(bytes + 64));
         CK(cudaMemcpyAsync(ctx->d_pcm.p, pcm, bytes, cudaMemcpyHostToDevice, ctx->stream));
         d_pcm = ctx->d_pcm.p;

@@ -280,7 +280,10 @@ int FLAC__stream_decoder_init_FILE(FLAC__StreamDecoder* d, FILE* f, FLAC__Stream
     if (m->state != DS_UNINITIALIZED) return DI_ALREADY_INITIALIZED;
     if (!f || !w || !ecb) return DI_INVALID_CALLBACKS;
     m->read_cb = nullptr; m->write_cb = w; m->error_cb = ecb; m->meta_cb = mcb; m->client = client; m->file = f;
-    return init_common(d);
+    const int rc = init_common(d);
+    // a failed init leaves the FILE with the caller (init_file closes the one it opened): finish()/delete must not close it again
+    if (rc != DI_OK) { m->file = nullptr; m->state = DS_UNINITIALIZED; }
+    return rc;
 }
 int FLAC__stream_decoder_init_file(FLAC__StreamDecoder* d, const char* filename, FLAC__StreamDecoderWriteCallback w, FLAC__StreamDecoderMetadataCallback mcb,
                                    FLAC__StreamDecoderErrorCallback ecb, void* client) {

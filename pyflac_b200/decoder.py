@@ -232,7 +232,14 @@ class OneShotDecoder(_Decoder):
 
 
 # ---------------------------------------------------------------------------- additive batch front-end
-def decode_batch(blobs: Sequence[bytes], device: int = 0):
-    """Decode many .flac byte strings in one GPU batch -> (list of (n, channels) int16/int32 arrays, list of info)."""
+def decode_batch(blobs: Sequence[bytes], device: int = 0, strict: bool = True):
+    """Decode many .flac byte strings in one GPU batch -> (list of (n, channels) int16/int32 arrays, list of info).
+    strict (default): a stream that ends with an error (truncated, CRC mismatch, not FLAC ...) raises
+    DecoderProcessException instead of coming back short; strict=False returns what decoded and info[s].status."""
     from .encoder import _engine
-    return _native.decode_streams(_engine(device), list(blobs))
+    out, infos = _native.decode_streams(_engine(device), list(blobs))
+    if strict:
+        bad = [(s, int(si.status)) for s, si in enumerate(infos) if si.status != 0]
+        if bad:
+            raise DecoderProcessException("; ".join(f"stream {s}: {_native.DEC_STATUS.get(st, st)}" for s, st in bad[:8]))
+    return out, infos

@@ -13,6 +13,31 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+_HAVE_GPU = None
+
+
+def have_gpu():
+    """True when libflacb200 can create an engine on device 0 (asked once per session)."""
+    global _HAVE_GPU
+    if _HAVE_GPU is None:
+        try:
+            from pyflac_b200 import _native as nat
+            nat.Engine(0).close()
+            _HAVE_GPU = True
+        except Exception:
+            _HAVE_GPU = False
+    return _HAVE_GPU
+
+
+def pytest_collection_modifyitems(config, items):
+    # GPU-marked tests skip (not error) on a host without a CUDA device
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if gpu_items and not have_gpu():
+        skip = pytest.mark.skip(reason="no CUDA device (libflacb200 has no CPU fallback)")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def checkers():
     """Build the test-only checker libraries once per session."""

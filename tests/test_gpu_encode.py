@@ -178,6 +178,32 @@ def test_encode_multichannel_and_depths(eng, checkers):
             assert got[0] == checkers.oracle_encode(x, 96000, bps, 5, 0), (bps, kind)
 
 
+def test_encode_low_bit_depths(eng, checkers):
+    """bits_per_sample 4..7 (libFLAC's lower limit is 4; none is in the streamable subset): qlp precision max(5, 2 + bps/2),
+    every level family, mono / stereo (mid/side: the side channel has bps + 1 bits) / 3 channels, odd and default blocksizes."""
+    from pyflac_b200 import _native as nat
+    rng = np.random.default_rng(11)
+    for bps in (4, 5, 6, 7):
+        lo, hi = -(1 << (bps - 1)), (1 << (bps - 1)) - 1
+        n = 4096 + 1152 + 77
+        t = np.arange(n)
+        for ch in (1, 2, 3):
+            tone = np.stack([np.round((hi - 1) * 0.8 * np.sin(2 * np.pi * (220 + 30 * c) * t / 48000.0 + c)) for c in range(ch)], axis=1)
+            xs = [np.clip(tone + rng.integers(-1, 2, (n, ch)), lo, hi).astype(np.int16),
+                  rng.integers(lo, hi + 1, (n, ch)).astype(np.int16),                         # full-scale noise -> VERBATIM
+                  np.full((n, ch), lo, np.int16),                                             # most negative value, constant
+                  (np.clip(tone, lo, hi).astype(np.int16) >> 1) << 1]                         # one wasted bit
+            for level, bs in [(0, 0), (2, 0), (5, 0), (8, 1000), (4, 576)]:
+                got, out = nat.encode_streams(eng, xs, 48000, bps, level, bs, streamable_subset=False)
+                for i, (x, g) in enumerate(zip(xs, got)):
+                    assert g == checkers.oracle_encode(x, 48000, bps, level, bs, streamable_subset=False), (bps, ch, level, bs, i)
+                assert out["log_guard_hits"] == 0
+        if checkers.ref_available():
+            x = np.clip(np.round(hi * 0.7 * np.sin(t / 9.0))[:, None] + rng.integers(-1, 2, (n, 2)), lo, hi).astype(np.int16)
+            got, _ = nat.encode_streams(eng, [x], 44100, bps, 5, 0, streamable_subset=False)
+            assert got[0] == checkers.ref_encode(x, 44100, bps, 5, 0, streamable_subset=False), bps
+
+
 def test_encode_sample_rates_and_frame_numbers(eng, checkers):
     from pyflac_b200 import _native as nat
     for sr in [8000, 12345, 50001, 65535, 96000, 176400, 655350]:
@@ -224,12 +250,20 @@ def test_full_size_properties(eng, checkers):
     fo, fl = out["frame_off"], out["frame_len"]
     assert np.all(fo[1:] >= fo[:-1] + fl[:-1])                      # frames laid out in order without overlap
     assert np.all(arena[fo.astype(np.int64)] == 0xFF)               # every frame starts with the sync code
-    for s in (0, 17, 255):                                          # encode -> decode round trip + byte equality
-        si = out["streams"][s]
-        blob = arena[int(si.byte_off): int(si.byte_off + si.byte_len)].tobytes()
-        dec, info = checkers.oracle_decode(blob)                    # validates every CRC-8/CRC-16 and the MD5
+    blobs = [arena[int(si.byte_off): int(si.byte_off + si.byte_len)].tobytes() for si in out["streams"]]
+    # byte equality of EVERY stream (all 256 are distinct): against the reference binary when it travelled to this box
+    # (pthreads, seconds), else against the oracle port
+    if checkers.ref_available():
+        _, _, ref_blobs = checkers.ref_encode_mt(pcm, 48000, 16, 5, 4096, min(32, os.cpu_count() or 8), keep_bytes=True)
+        for s in range(256):
+            assert blobs[s] == ref_blobs[s].tobytes(), s
+    else:
+        for s in range(256):
+            assert blobs[s] == checkers.oracle_encode(pcm[s], 48000, 16, 5, 4096), s
+    for s in (0, 17, 255):                                          # encode -> oracle decode round trip + the oracle port's bytes
+        dec, info = checkers.oracle_decode(blobs[s])                # validates every CRC-8/CRC-16 and the MD5
         assert np.array_equal(dec, pcm[s].astype(np.int32))
-        assert blob == checkers.oracle_encode(pcm[s], 48000, 16, 5, 4096)
+        assert blobs[s] == checkers.oracle_encode(pcm[s], 48000, 16, 5, 4096)
 
 
 def test_full_size_config3_24bit_mono_level8(eng, checkers):
@@ -248,13 +282,14 @@ def test_full_size_config3_24bit_mono_level8(eng, checkers):
     assert len(out["frame_len"]) == n_streams * 64
     arena = out["arena"]
     blobs = [arena[int(si.byte_off): int(si.byte_off + si.byte_len)] for si in out["streams"]]
-    for s in range(64):                                                   # the 64 tiles of each distinct stream are identical
-        for k in range(1, 64, 21):
-            assert np.array_equal(blobs[s], blobs[s + 64 * k])
-    for s in (0, 31, 63):
+    for s in range(64):                                                   # all 64 tiles of each distinct stream are identical
+        for k in range(1, 64):
+            assert np.array_equal(blobs[s], blobs[s + 64 * k]), (s, k)
+    for s in range(64):                                                   # every distinct stream byte for byte against the oracle
         b = blobs[s].tobytes()
-        assert b == checkers.oracle_encode(uniq[s], 192000, 24, 8, 4096)
-        dec, info = checkers.oracle_decode(b)
+        assert b == checkers.oracle_encode(uniq[s], 192000, 24, 8, 4096), s
+    for s in (0, 31, 63):
+        dec, info = checkers.oracle_decode(blobs[s].tobytes())
         assert info["bps"] == 24 and np.array_equal(dec, uniq[s].astype(np.int32))
     import hashlib
     for s in (5, 4095):

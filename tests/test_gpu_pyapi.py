@@ -152,3 +152,50 @@ def test_batch_frontend(checkers):
     x24 = [music_like(9000, 1, 192000, 24, seed=7)]
     blobs, _ = pf.encode_batch(x24, 192000, compression_level=8, blocksize=4096, bits_per_sample=24)
     assert blobs[0] == checkers.oracle_encode(x24[0], 192000, 24, 8, 4096)
+
+
+def test_config_c1_file_encoder_10s_stereo(checkers, tmp_path):
+    """BASELINE configs[0], the exact shape: one 10 s 48 kHz stereo int16 WAV through FileEncoder at level 5, default
+    blocksize (117 frames of 4096 + one of 768).  The file must equal libFLAC's byte for byte."""
+    import pyflac_b200 as pf
+    x = music_like(480000, 2, 48000, 16, seed=2024)
+    wav, flac = str(tmp_path / "c1.wav"), str(tmp_path / "c1.flac")
+    write_wav(wav, x, 48000, 16)
+    data = pf.FileEncoder(wav, flac, compression_level=5).process()
+    want = checkers.ref_encode(x, 48000, 16, 5, 0, seekable=True) if checkers.ref_available() else checkers.oracle_encode(x, 48000, 16, 5, 0)
+    assert data == want and open(flac, "rb").read() == want
+    assert data == checkers.oracle_encode(x, 48000, 16, 5, 0)
+    dec, info = checkers.oracle_decode(data)
+    assert np.array_equal(dec, x.astype(np.int32))
+    out_wav = str(tmp_path / "c1_back.wav")
+    y, sr = pf.FileDecoder(flac, out_wav).process()
+    assert sr == 48000 and y.shape == x.shape and np.array_equal(np.round(y * 32768.0).astype(np.int32), x.astype(np.int32))
+
+
+def test_cli_round_trip(checkers, tmp_path):
+    """`python -m pyflac_b200 in.wav -o out.flac` then `... out.flac -o back.wav` (reference pyflac/__main__.py:20-57):
+    the .flac equals libFLAC's for the same level / blocksize, the WAV that comes back holds the same samples; a file
+    that is neither RIFF nor fLaC is refused."""
+    import subprocess
+    import sys
+    from pyflac_b200 import wav as pwav
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    x = music_like(4096 * 4 + 321, 2, 44100, 16, seed=77)
+    wav, flac, back = str(tmp_path / "a.wav"), str(tmp_path / "a.flac"), str(tmp_path / "b.wav")
+    write_wav(wav, x, 44100, 16)
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-m", "pyflac_b200", wav, "-o", flac, "-c", "8", "-b", "1152"], capture_output=True, text=True, env=env, cwd=root)
+    assert r.returncode == 0, r.stderr
+    assert open(flac, "rb").read() == checkers.oracle_encode(x, 44100, 16, 8, 1152)
+    r = subprocess.run([sys.executable, "-m", "pyflac_b200", flac, "-o", back], capture_output=True, text=True, env=env, cwd=root)
+    assert r.returncode == 0, r.stderr
+    y, sr = pwav.read_pcm(back)
+    assert sr == 44100 and np.array_equal(y, x)
+    # default output name: input with the suffix swapped
+    r = subprocess.run([sys.executable, "-m", "pyflac_b200", wav], capture_output=True, text=True, env=env, cwd=root)
+    assert r.returncode == 0 and os.path.exists(str(tmp_path / "a.flac"))
+    assert open(str(tmp_path / "a.flac"), "rb").read() == checkers.oracle_encode(x, 44100, 16, 5, 0)
+    junk = str(tmp_path / "junk.bin")
+    open(junk, "wb").write(b"not audio at all")
+    r = subprocess.run([sys.executable, "-m", "pyflac_b200", junk], capture_output=True, text=True, env=env, cwd=root)
+    assert r.returncode != 0 and "WAV or a FLAC" in r.stderr

@@ -196,7 +196,8 @@ def test_wav_reader_on_reference_wavs_when_present():
 
 def test_public_signatures_match_reference_source_when_present():
     """constructor and method signatures (names, order, defaults) of the five public classes, read from the reference's
-    source with `ast` (the reference package itself cannot be imported here: its cffi modules are not built)"""
+    source with `ast` (no GPU here; on the GPU box tests/test_gpu_reference_suite.py builds the reference's cffi modules against
+    libflacb200.so and runs its unmodified test-suite)"""
     import ast
     import inspect
     import pytest
