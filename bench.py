@@ -19,6 +19,11 @@ One *step* = one pass of the whole encode path over the batch.  1 sample = 1 cha
 
 Multi-GPU: streams are independent, so ranks shard them with no data-path collective (weak scaling: every
 rank encodes its own 256 streams); torch.distributed is used for the barrier and the max-over-ranks time.
+
+Extra legs in the same JSON line (--quick skips them): `config_c5_shape` = BASELINE configs[4]'s per-GPU shard (4096 x 131072
+stereo int16, level 5) on every rank (at --gpus 8 that is the 32768 streams of configs[4]); `config_c2` = BASELINE configs[2]
+(4096 x 262144 mono 24-bit, 192 kHz, level 8) at --gpus 1; `decode_*` top-level keys = BASELINE configs[3].
+Every rank byte-compares a sample of ITS OWN output with libFLAC in the same run (`cpu_baseline.ranks_checked`).
 """
 import argparse
 import json
@@ -44,10 +49,17 @@ METRIC = "encode_msamples_per_s_level5"
 UNIT = "MSamples/s"
 
 
-# DRAM bytes per launch on the bench batch, from the committed ncu --set full capture (profiles/r01d_ncu_encode_kernels.txt)
-NCU_TRAFFIC_BYTES = {"autoc": 499152384 + 13786880, "analyze": 512133120 + 18882560, "pack": 502199552 + 264583168}
-# dec_frame_kernel on the 4096-stream decode leg (profiles/r01e_ncu_decode_kernels_4096_streams.txt)
-NCU_TRAFFIC_BYTES_DEC_FRAME = 2211892000 + 4882201000
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` on the bench batch, from the ncu --set full
+    capture of THIS round's code (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when
+    the file has no entry for the kernel (a stale constant would be worse than no number)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            t = json.load(f)
+        e = t["kernels"].get(kernel)
+        return (int(e["dram_read_bytes"]) + int(e["dram_write_bytes"]), t.get("source", "profiles/r02_traffic.json")) if e else (None, None)
+    except Exception:
+        return None, None
 
 
 def workload_config():
@@ -84,6 +96,18 @@ def make_pcm_short(rank, n_streams, n_samples):
     for s in range(n_streams):
         b, k = base[s % 32], s // 32
         out[s] = b if k == 0 else (np.roll(b, 104729 * k % n_samples, axis=0).astype(np.int32) * (256 - k) // 256).astype(np.int16)
+    return out
+
+
+def make_pcm_c2(rank, n_streams, n_samples):
+    """BASELINE configs[2]: mono 24-bit (int32 container) 192 kHz; 32 distinct music-like bases per rank, every stream a
+    different circular shift + gain of one of them."""
+    from pyflac_b200.synth import music_like
+    base = [music_like(n_samples, 1, 192000, 24, seed=9000 + 1000 * rank + s)[:, 0] for s in range(32)]
+    out = np.empty((n_streams, n_samples), np.int32)
+    for s in range(n_streams):
+        b, k = base[s % 32], s // 32
+        out[s] = b if k == 0 else (np.roll(b, (15485863 * k) % n_samples).astype(np.int64) * (1024 - k) // 1024).astype(np.int32)
     return out
 
 
@@ -146,13 +170,14 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_reference_run(pcm, n_threads, keep_bytes=False):
+def cpu_reference_run(pcm, n_threads, keep_bytes=False, sample_rate=SAMPLE_RATE, bps=BPS, level=LEVEL):
     """libFLAC 1.4.3 (the binary pyFLAC bundles) over pthreads -- test/bench infrastructure from oracle/_ref."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    if os.path.join(ROOT, "tests") not in sys.path:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _checkers as ck
     if not ck.ref_available():
         ck.build_checkers()
-    return ck.ref_encode_mt(pcm, SAMPLE_RATE, BPS, LEVEL, BLOCKSIZE, n_threads, keep_bytes=keep_bytes)
+    return ck.ref_encode_mt(pcm, sample_rate, bps, level, BLOCKSIZE, n_threads, keep_bytes=keep_bytes)
 
 
 def run_reference(args, rank, world):
@@ -189,6 +214,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline encode only (profiling runs): no decode / config legs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -291,9 +317,28 @@ def main():
     if world > 1:
         dist.barrier()
 
+    # ---------------- every rank checks ITS OWN bytes against libFLAC, same run ----------------
+    # (rank 0 additionally compares all of its 256 streams further down; here: a sample of >= 8 streams per rank, so that at
+    #  N GPUs the whole job's output is covered, not just rank 0's)
+    ranks_checked, ranks_equal = 0, True
+    if not args.no_cpu_baseline:
+        sel = sorted(set(int(v) for v in np.linspace(0, N_STREAMS - 1, 8)) | {(37 * rank + 5) % N_STREAMS})
+        arena_chk = h_arena.numpy()
+        _, _, ref_blobs = cpu_reference_run(np.ascontiguousarray(pcm[sel]), min(len(sel), max(1, host_threads() // max(world, 1))), keep_bytes=True)
+        mine_ok = all(bytes(arena_chk[int(infos[s].byte_off): int(infos[s].byte_off + infos[s].byte_len)]) == ref_blobs[k].tobytes()
+                      for k, s in enumerate(sel))
+        del ref_blobs
+        chk = torch.tensor([1.0 if mine_ok else 0.0, 1.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            mn = chk[:1].clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            sm = chk[1:].clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ranks_equal, ranks_checked = bool(mn[0] > 0.5), int(round(float(sm[0])))
+        else:
+            ranks_equal, ranks_checked = bool(mine_ok), 1
+
     # ---------------- scatter / gather over NCCL (PCM born on rank 0's GPU) ----------------
     sg = None
-    if world > 1:
+    if world > 1 and not args.quick:
         try:
             from pyflac_b200.dist import scatter_streams, gather_packed
 
@@ -313,9 +358,14 @@ def main():
                 k = hi - lo
                 off = (np.arange(k, dtype=np.uint64) * np.uint64(elems))
                 eng.encode_device(cfg, blk.data_ptr(), blk.numel(), off, np.full(k, N_SAMPLES, np.uint64))
-                r = eng.result()                                    # waits for this batch (incl. its MD5): the bytes must be final
+                # frames never depend on the MD5 (a serial chain, ~20 ms for 10 s streams): gather the packed bytes as soon as
+                # the frames are final and send the 16-byte digests after them
+                r = eng.result(wait_md5=False)
                 arena = torch.as_tensor(_DevMem(r.d_arena, int(r.total_bytes)), device=dev)
                 bufs, sizes = gather_packed(arena, int(r.total_bytes), dev)
+                dig = torch.from_numpy(eng.fetch_md5()).to(dev)                    # waits for this batch's MD5 chain
+                alld = [torch.empty_like(dig) for _ in range(world)] if rank == 0 else None
+                dist.gather(dig, gather_list=alld, dst=0)
                 return sizes
             for _ in range(2):
                 sizes = step_sg()
@@ -331,7 +381,8 @@ def main():
             dist.all_reduce(tsg, op=dist.ReduceOp.MAX)
             sg = {"value": world * total_samples / (float(tsg[0]) * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": float(tsg[0]),
                   "scatter_bytes_per_step": (world - 1) * pcm_bytes, "gather_bytes_per_step": int(sum(sizes[1:])),
-                  "what": "all PCM resident on rank 0's GPU -> NCCL scatter of stream blocks -> encode on every rank -> NCCL gather of the packed bytes to rank 0"}
+                  "what": "all PCM resident on rank 0's GPU -> NCCL scatter of stream blocks -> encode on every rank -> NCCL gather of the packed "
+                          "bytes to rank 0, MD5 digests (16 B per stream) gathered after the frames"}
             del full
         except Exception as ex:                                   # never lose the main line to the optional mode
             sg = {"error": repr(ex)[:300]}
@@ -376,39 +427,132 @@ def main():
         del h_out
         return dev_ms, e2e_ms, kt, ok
 
-    # (a) round trip: the 256 streams the encode step just produced
-    arena_np = h_arena.numpy()
-    total_flac = int(tot.value)
-    s_off = np.array([infos[s].byte_off for s in range(N_STREAMS)], np.uint64)
-    s_len = np.array([infos[s].byte_len for s in range(N_STREAMS)], np.uint64)
-    rt_dev_ms, rt_e2e_ms, rt_kt, rt_ok = decode_leg(arena_np[:total_flac + 16], s_off, s_len, total_samples, pcm, args.steps)
+    def encode_leg(cfg_x, pcm_np, n_streams, n_samples, channels, steps, with_e2e):
+        """One extra encode workload on this rank: device-resident ms/step (CUDA events) and, optionally, host->host ms/step."""
+        flat = pcm_np.reshape(-1)
+        h_x = torch.from_numpy(flat).pin_memory() if with_e2e else None
+        d_x = (h_x if with_e2e else torch.from_numpy(flat)).to(dev)
+        off_x = np.arange(n_streams, dtype=np.uint64) * np.uint64(n_samples * channels)
+        smp_x = np.full(n_streams, n_samples, np.uint64)
+        for _ in range(2):
+            eng.encode_device(cfg_x, d_x.data_ptr(), d_x.numel(), off_x, smp_x)
+        torch.cuda.synchronize()
+        r = eng.result()
+        if world > 1:
+            dist.barrier()
+        l0 = eng.launch_count
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(steps):
+            eng.encode_device(cfg_x, d_x.data_ptr(), d_x.numel(), off_x, smp_x)
+        eng.join()
+        a1.record()
+        torch.cuda.synchronize()
+        out = {"ms_dev": a0.elapsed_time(a1) / steps, "kernel_ms": eng.kernel_times(), "out_bytes": int(r.total_bytes), "n_frames": int(r.n_frames),
+               "launches_per_step": (eng.launch_count - l0) // steps, "guard_hits": int(r.log_guard_hits), "d_pcm": d_x, "off": off_x, "smp": smp_x, "ms_e2e": None}
+        if with_e2e:
+            cap = flat.nbytes + (64 << 20)
+            h_ar = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            foff = np.zeros(out["n_frames"], np.uint64); flen = np.zeros(out["n_frames"], np.uint32)
+            inf = (nat.StreamInfo * n_streams)()
+            totx = C.c_uint64(0)
 
-    # (b) BASELINE configs[3]: 4096 parallel .flac streams (131 072 stereo samples each, level 5) -> int16 PCM
-    D_STREAMS, D_SAMPLES = 4096, 131072
-    pcm4 = make_pcm_short(rank, D_STREAMS, D_SAMPLES)
-    d4 = torch.from_numpy(pcm4.reshape(-1)).to(dev)
-    off4 = np.arange(D_STREAMS, dtype=np.uint64) * np.uint64(D_SAMPLES * CHANNELS)
-    eng.encode_device(cfg, d4.data_ptr(), d4.numel(), off4, np.full(D_STREAMS, D_SAMPLES, np.uint64))
-    enc4 = eng.fetch()
-    del d4
-    total4 = int(enc4["total_bytes"])
-    h_blob4 = torch.empty(total4 + 16, dtype=torch.uint8).pin_memory()
-    h_blob4.numpy()[:total4] = enc4["arena"][:total4]
-    h_blob4.numpy()[total4:] = 0
-    s_off4 = np.array([si.byte_off for si in enc4["streams"]], np.uint64)
-    s_len4 = np.array([si.byte_len for si in enc4["streams"]], np.uint64)
-    del enc4
-    dsteps = max(3, args.steps // 4)
-    dec_ms_step, dec_e2e_ms_step, dec_kt, dec_ok = decode_leg(h_blob4.numpy(), s_off4, s_len4, pcm4.size, pcm4, dsteps)
-    dec_total_samples = pcm4.size
-    dec_bytes = total4 + pcm4.nbytes
-    dec_ms, dec_e2e_s = dec_ms_step, dec_e2e_ms_step / 1e3
+            def st():
+                rc = L.flacb200_encode_batch_host(eng._h, C.byref(cfg_x), h_x.data_ptr(), h_x.numel(), n_streams, off_x.ctypes.data, smp_x.ctypes.data,
+                                                  h_ar.data_ptr(), cap, C.byref(totx), foff.ctypes.data, flen.ctypes.data, C.cast(inf, C.c_void_p))
+                if rc != 0:
+                    raise RuntimeError(L.flacb200_last_error(eng._h).decode())
+            st()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                st()
+            torch.cuda.synchronize()
+            out["ms_e2e"] = (time.perf_counter() - t0) * 1e3 / steps
+            out["e2e_d2h_bytes"] = int(totx.value) + out["n_frames"] * 12 + n_streams * 56
+            del h_ar
+        return out
+
+    extra_t = [0.0] * 10          # times to max-reduce: dec dev, dec e2e, rt dev, rt e2e, c5 dev, c5 e2e, c2 dev
+    dec = rt = c5 = c2 = None
+    if not args.quick:
+        # (a) round trip: the 256 streams the encode step just produced
+        arena_np = h_arena.numpy()
+        total_flac = int(tot.value)
+        s_off = np.array([infos[s].byte_off for s in range(N_STREAMS)], np.uint64)
+        s_len = np.array([infos[s].byte_len for s in range(N_STREAMS)], np.uint64)
+        rt_dev_ms, rt_e2e_ms, rt_kt, rt_ok = decode_leg(arena_np[:total_flac + 16], s_off, s_len, total_samples, pcm, args.steps)
+        rt = {"kt": rt_kt, "ok": rt_ok}
+        extra_t[2], extra_t[3] = rt_dev_ms, rt_e2e_ms
+
+        # (b) BASELINE configs[4]'s per-GPU shard: 4096 streams x 131072 stereo int16, level 5 (at --gpus 8: 32768 streams)
+        D_STREAMS, D_SAMPLES = 4096, 131072
+        pcm4 = make_pcm_short(rank, D_STREAMS, D_SAMPLES)
+        xsteps = max(3, args.steps // 4)
+        c5 = encode_leg(cfg, pcm4, D_STREAMS, D_SAMPLES, CHANNELS, xsteps, with_e2e=True)
+        extra_t[4], extra_t[5] = c5["ms_dev"], c5["ms_e2e"]
+
+        # (c) BASELINE configs[3]: those 4096 .flac streams -> int16 PCM
+        eng.encode_device(cfg, c5["d_pcm"].data_ptr(), c5["d_pcm"].numel(), c5["off"], c5["smp"])
+        enc4 = eng.fetch()
+        c5.pop("d_pcm")
+        total4 = int(enc4["total_bytes"])
+        h_blob4 = torch.empty(total4 + 16, dtype=torch.uint8).pin_memory()
+        h_blob4.numpy()[:total4] = enc4["arena"][:total4]
+        h_blob4.numpy()[total4:] = 0
+        s_off4 = np.array([si.byte_off for si in enc4["streams"]], np.uint64)
+        s_len4 = np.array([si.byte_len for si in enc4["streams"]], np.uint64)
+        del enc4
+        dsteps = max(3, args.steps // 4)
+        dec_ms_step, dec_e2e_ms_step, dec_kt, dec_ok = decode_leg(h_blob4.numpy(), s_off4, s_len4, pcm4.size, pcm4, dsteps)
+        dec = {"kt": dec_kt, "ok": dec_ok, "samples": pcm4.size, "bytes": total4 + pcm4.nbytes, "flac_bytes": total4, "pcm_bytes": int(pcm4.nbytes), "steps": dsteps}
+        extra_t[0], extra_t[1] = dec_ms_step, dec_e2e_ms_step
+        c5_cpu = None
+        if rank == 0 and not args.no_cpu_baseline:
+            import _checkers as ck
+            thr = host_threads()
+            ddt = min(ck.ref_decode_mt(h_blob4.numpy(), s_off4, s_len4, thr)[0] for _ in range(2))
+            dec["cpu_value"], dec["cpu_cores"] = pcm4.size / ddt / 1e6, thr
+            # libFLAC on a bounded sample of the c5 shape (512 of the 4096 streams) + byte equality of those streams
+            nsm = 512
+            dtc, _, blobs = cpu_reference_run(pcm4[:nsm], thr, keep_bytes=True)
+            eng.encode_host(cfg, pcm4[:nsm].reshape(-1), np.arange(nsm, dtype=np.uint64) * np.uint64(D_SAMPLES * CHANNELS), np.full(nsm, D_SAMPLES, np.uint64))
+            o5 = eng.fetch()
+            eq5 = all(o5["arena"][int(si.byte_off): int(si.byte_off + si.byte_len)].tobytes() == blobs[k].tobytes() for k, si in enumerate(o5["streams"]))
+            c5_cpu = {"value": nsm * D_SAMPLES * CHANNELS / dtc / 1e6, "unit": UNIT, "cores": thr, "kind": "reference",
+                      "sample": f"{nsm} of the 4096 streams, one FLAC__StreamEncoder per pthread", "bytes_identical_to_gpu": bool(eq5)}
+            del blobs, o5
+        del h_blob4, pcm4
+
+        # (d) BASELINE configs[2]: 4096 streams x 262144 mono 24-bit (int32 container), 192 kHz, level 8 -- 1 GPU only
+        if world == 1:
+            C2_STREAMS, C2_SAMPLES = 4096, 262144
+            pcm2 = make_pcm_c2(rank, C2_STREAMS, C2_SAMPLES)
+            cfg2 = nat.Engine.make_config(192000, 1, 24, 8, BLOCKSIZE, container_bytes=4)
+            c2 = encode_leg(cfg2, pcm2, C2_STREAMS, C2_SAMPLES, 1, 3, with_e2e=False)
+            c2.pop("d_pcm")
+            c2["pcm_bytes"], c2["samples"] = int(pcm2.nbytes), int(pcm2.size)
+            extra_t[6] = c2["ms_dev"]
+            if not args.no_cpu_baseline:
+                thr = host_threads()
+                nsm = 256
+                dtc, _, blobs = cpu_reference_run(pcm2[:nsm, :, None], thr, keep_bytes=True, sample_rate=192000, bps=24, level=8)
+                eng.encode_host(cfg2, pcm2[:nsm].reshape(-1), np.arange(nsm, dtype=np.uint64) * np.uint64(C2_SAMPLES), np.full(nsm, C2_SAMPLES, np.uint64))
+                o2 = eng.fetch()
+                eq2 = all(o2["arena"][int(si.byte_off): int(si.byte_off + si.byte_len)].tobytes() == blobs[k].tobytes() for k, si in enumerate(o2["streams"]))
+                c2["cpu"] = {"value": nsm * C2_SAMPLES / dtc / 1e6, "unit": UNIT, "cores": thr, "kind": "reference",
+                             "sample": f"{nsm} of the 4096 streams, libFLAC 1.4.3 with set_bits_per_sample(24), level 8", "bytes_identical_to_gpu": bool(eq2)}
+                del blobs, o2
+            del pcm2
 
     # ---------------- reduce over ranks ----------------
-    t = torch.tensor([ms_total, e2e_s * 1e3, dec_ms, dec_e2e_s * 1e3, rt_dev_ms, rt_e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s * 1e3] + extra_t, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max, e2e_ms_max, dec_ms_max, dec_e2e_ms_max, rt_dev_max, rt_e2e_max = (float(t[i]) for i in range(6))
+    ms_total_max, e2e_ms_max = float(t[0]), float(t[1])
+    xt = [float(v) for v in t[2:]]
 
     if rank == 0:
         ms_per_step = ms_total_max / args.steps
@@ -417,9 +561,12 @@ def main():
         peak, peak_src = hbm_peak()
         # dominant kernel = the longest one on the encode stream (the step's critical path).  md5_kernel runs on a side
         # stream under the next batches (a 256-thread serial chain, pure latency) and is listed in kernel_ms / roofline_md5.
-        dom = max(("autoc", "analyze", "pack"), key=lambda k: kt_acc.get(k, 0.0))
+        dom = max([k for k in ("fused", "autoc", "analyze", "pack") if k in kt_acc], key=lambda k: kt_acc.get(k, 0.0))
         alg_bytes = pcm_bytes + out_bytes
         achieved = alg_bytes / (kt_acc[dom] * 1e-3) / 1e9
+        dom_kernel = "fused_encode_kernel" if dom == "fused" else dom + "_kernel"
+        traffic, traffic_src = ncu_traffic(dom_kernel)
+        dec_traffic, dec_traffic_src = ncu_traffic("dec_frame_kernel")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -430,63 +577,99 @@ def main():
                     "last_call_breakdown_ms": host_path_ms},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "profiles/r01d_ncu_encode_kernels.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch on this batch)",
+            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
+                         "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                          "kernel_ms": kt_acc},
             "roofline_md5": {"bound": "hbm", "kernel": "md5_kernel (side stream, overlapped with the next batches)",
                              "achieved": pcm_bytes / (max(kt_acc.get("md5", 0.0), 1e-6) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": pcm_bytes / (max(kt_acc.get("md5", 0.0), 1e-6) * 1e-3) / 1e9 / peak,
                              "algorithmic_bytes_per_launch": pcm_bytes},
-            "decode": {"metric": "decode_msamples_per_s", "unit": UNIT,
-                       "value": world * dec_total_samples / (dec_ms_max * 1e-3) / 1e6,
-                       "e2e_value": world * dec_total_samples / (dec_e2e_ms_max * 1e-3) / 1e6,
-                       "ms_per_step": dec_ms_max, "e2e_ms_per_step": dec_e2e_ms_max, "steps": dsteps,
-                       "workload": "StreamDecoder: 4096 parallel .flac streams (131072 stereo int16 samples each, level 5) -> int16 PCM (BASELINE configs[3]) per GPU",
-                       "h2d_bytes_per_step": total4, "d2h_bytes_per_step": int(pcm4.nbytes),
-                       "pcm_identical_to_input": bool(dec_ok), "kernel_ms": dec_kt,
-                       "roofline": {"bound": "hbm", "kernel": "dec_frame_kernel",
-                                    "achieved": dec_bytes / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9,
-                                    "peak": peak, "unit": "GB/s",
-                                    "frac": dec_bytes / (max(dec_kt.get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9 / peak,
-                                    "traffic": NCU_TRAFFIC_BYTES_DEC_FRAME, "traffic_source": "profiles/r01e_ncu_decode_kernels_4096_streams.txt (int32 planar scratch: 2 x the int16 PCM the path finally writes)",
-                                    "algorithmic_bytes_per_launch": dec_bytes}},
-            "decode_roundtrip_256": {"value": world * total_samples / (rt_dev_max * 1e-3) / 1e6, "e2e_value": world * total_samples / (rt_e2e_max * 1e-3) / 1e6,
-                                     "unit": UNIT, "ms_per_step": rt_dev_max, "e2e_ms_per_step": rt_e2e_max, "kernel_ms": rt_kt,
-                                     "workload": "the 256 streams produced by the encode step (libFLAC-identical bytes) -> int16 PCM; a launch cannot "
-                                                 "finish faster than one frame's serial decode, so this small batch is latency bound",
-                                     "pcm_identical_to_input": bool(rt_ok)},
             "scatter_gather": sg,
             "frames_per_step": n_frames * world, "frames_per_s": n_frames * world / (ms_per_step * 1e-3),
             "x_realtime": value * 1e6 / (SAMPLE_RATE * CHANNELS), "x_realtime_e2e": e2e_val * 1e6 / (SAMPLE_RATE * CHANNELS),
             "compressed_bytes_per_step": out_bytes, "ratio": out_bytes / pcm_bytes,
             "log_guard_hits": guard_hits,
         }
+        if dec is not None:
+            dec_ms_max, dec_e2e_ms_max, rt_dev_max, rt_e2e_max, c5_dev_max, c5_e2e_max, c2_dev_max = xt[0], xt[1], xt[2], xt[3], xt[4], xt[5], xt[6]
+            dval = world * dec["samples"] / (dec_ms_max * 1e-3) / 1e6
+            dval_e2e = world * dec["samples"] / (dec_e2e_ms_max * 1e-3) / 1e6
+            # BASELINE configs[3] lifted to the top level (second half of the metric)
+            line["decode_metric"] = "decode_msamples_per_s"
+            line["decode_value"] = dval
+            line["decode_e2e_value"] = dval_e2e
+            line["decode_ms_per_step"] = dec_ms_max
+            line["decode"] = {"metric": "decode_msamples_per_s", "unit": UNIT, "value": dval, "e2e_value": dval_e2e,
+                              "ms_per_step": dec_ms_max, "e2e_ms_per_step": dec_e2e_ms_max, "steps": dec["steps"],
+                              "workload": "StreamDecoder: 4096 parallel .flac streams (131072 stereo int16 samples each, level 5) -> int16 PCM (BASELINE configs[3]) per GPU",
+                              "h2d_bytes_per_step": dec["flac_bytes"], "d2h_bytes_per_step": dec["pcm_bytes"],
+                              "pcm_identical_to_input": bool(dec["ok"]), "kernel_ms": dec["kt"],
+                              "cpu_baseline": ({"value": dec["cpu_value"], "unit": UNIT, "cores": dec["cpu_cores"], "kind": "reference",
+                                                "sample": "all 4096 streams, one FLAC__StreamDecoder per pthread"} if "cpu_value" in dec else None),
+                              "roofline": {"bound": "hbm", "kernel": "dec_frame_kernel",
+                                           "achieved": dec["bytes"] / (max(dec["kt"].get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9,
+                                           "peak": peak, "unit": "GB/s",
+                                           "frac": dec["bytes"] / (max(dec["kt"].get("frame_decode", 0.0), 1e-6) * 1e-3) / 1e9 / peak,
+                                           "step_frac": dec["bytes"] / (dec_ms_max * 1e-3) / 1e9 / peak,
+                                           "traffic": dec_traffic, "traffic_source": dec_traffic_src,
+                                           "algorithmic_bytes_per_launch": dec["bytes"]}}
+            line["decode_roundtrip_256"] = {"value": world * total_samples / (rt_dev_max * 1e-3) / 1e6, "e2e_value": world * total_samples / (rt_e2e_max * 1e-3) / 1e6,
+                                            "unit": UNIT, "ms_per_step": rt_dev_max, "e2e_ms_per_step": rt_e2e_max, "kernel_ms": rt["kt"],
+                                            "workload": "the 256 streams produced by the encode step (libFLAC-identical bytes) -> int16 PCM; a launch cannot "
+                                                        "finish faster than one frame's serial decode, so this small batch is latency bound",
+                                            "pcm_identical_to_input": bool(rt["ok"])}
+            c5_samples = 4096 * 131072 * CHANNELS
+            c5_alg = c5_samples * 2 + c5["out_bytes"]
+            c5k = c5["kernel_ms"]
+            c5dom = max([k for k in ("fused", "autoc", "analyze", "pack") if k in c5k], key=lambda k: c5k.get(k, 0.0))
+            line["config_c5_shape"] = {
+                "workload": f"BASELINE configs[4]: {4096 * world} streams x 131072 stereo int16 samples, level 5, blocksize 4096 ({4096} per GPU, {world} GPU(s))",
+                "metric": METRIC, "unit": UNIT, "value": world * c5_samples / (c5_dev_max * 1e-3) / 1e6, "ms_per_step": c5_dev_max,
+                "e2e": {"value": world * c5_samples / (c5_e2e_max * 1e-3) / 1e6, "ms_per_step": c5_e2e_max, "h2d_bytes_per_step": c5_samples * 2,
+                        "d2h_bytes_per_step": c5.get("e2e_d2h_bytes")},
+                "n_streams_total": 4096 * world, "frames_per_step": c5["n_frames"] * world, "gpu_launches_per_step": c5["launches_per_step"],
+                "roofline": {"bound": "hbm", "kernel": ("fused_encode_kernel" if c5dom == "fused" else c5dom + "_kernel"),
+                             "achieved": c5_alg / (c5k[c5dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": c5_alg / (c5k[c5dom] * 1e-3) / 1e9 / peak,
+                             "algorithmic_bytes_per_launch": c5_alg, "kernel_ms": c5k, "traffic": None},
+                "cpu_baseline": c5_cpu, "log_guard_hits": c5["guard_hits"]}
+            if c2 is not None:
+                c2_alg = c2["pcm_bytes"] + c2["out_bytes"]
+                c2k = c2["kernel_ms"]
+                c2dom = max([k for k in ("fused", "autoc", "analyze", "pack") if k in c2k], key=lambda k: c2k.get(k, 0.0))
+                line["config_c2"] = {
+                    "workload": "BASELINE configs[2]: StreamEncoder, 4096 streams x 262144 mono 24-bit samples (int32 container), 192 kHz, level 8, blocksize 4096, 1 GPU",
+                    "metric": "encode_msamples_per_s_level8_24bit", "unit": UNIT, "value": c2["samples"] / (c2_dev_max * 1e-3) / 1e6, "ms_per_step": c2_dev_max,
+                    "frames_per_step": c2["n_frames"], "gpu_launches_per_step": c2["launches_per_step"], "ratio": c2["out_bytes"] / c2["pcm_bytes"],
+                    "roofline": {"bound": "hbm", "kernel": c2dom + "_kernel", "achieved": c2_alg / (c2k[c2dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": c2_alg / (c2k[c2dom] * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": c2_alg, "kernel_ms": c2k, "traffic": None},
+                    "cpu_baseline": c2.get("cpu"), "log_guard_hits": c2["guard_hits"]}
         if not args.no_cpu_baseline:
             threads = host_threads()
             n_sample = N_STREAMS
             _, _, blobs = cpu_reference_run(pcm[:n_sample], threads, keep_bytes=True)
-            # same-run byte equality of every stream against the GPU output of the last e2e step
+            # same-run byte equality of every stream of rank 0 against the GPU output of the last e2e step
             arena = h_arena.numpy()
             equal = all(bytes(arena[int(infos[s].byte_off): int(infos[s].byte_off + infos[s].byte_len)]) == blobs[s].tobytes()
                         for s in range(n_sample))
             del blobs
-            # libFLAC does not scale to every hardware thread on a shared box: report the best of a thread sweep
-            sweep = {}
-            for t in sorted({1, max(1, threads // 4), max(1, threads // 2), threads}):
-                best = min(cpu_reference_run(pcm[:n_sample] if t > 1 else pcm[:8], t)[0] for _ in range(2))
-                sweep[t] = (n_sample if t > 1 else 8) * N_SAMPLES * CHANNELS / best / 1e6
-            tbest = max(sweep, key=sweep.get)
-            import _checkers as ck
-            ddt = min(ck.ref_decode_mt(h_blob4.numpy(), s_off4, s_len4, tbest)[0] for _ in range(2))
-            cpu_decode = dec_total_samples / ddt / 1e6
-            line["cpu_baseline"] = {"value": sweep[tbest], "unit": UNIT, "cores": tbest, "kind": "reference",
-                                    "sample": f"all {n_sample} streams of the step (8 for the 1-thread point), one FLAC__StreamEncoder per pthread, "
-                                              f"libFLAC 1.4.3 from oracle/_ref; best of thread sweep",
-                                    "thread_sweep_msamples_per_s": {str(k): v for k, v in sweep.items()},
-                                    "host_threads": threads, "bytes_identical_to_gpu": bool(equal),
-                                    "decode_value": cpu_decode, "decode_cores": tbest}
+            # same procedure as --impl reference: pick the thread count libFLAC scales best with, then average timed runs
+            cand = sorted({max(1, threads // 4), max(1, threads // 2), threads})
+            probe = {tt: cpu_reference_run(pcm[:n_sample], tt)[0] for tt in cand}
+            tbest = min(probe, key=probe.get)
+            dts = [cpu_reference_run(pcm[:n_sample], tbest)[0] for _ in range(3)]
+            one = min(cpu_reference_run(pcm[:8], 1)[0] for _ in range(2))
+            line["cpu_baseline"] = {"value": n_sample * N_SAMPLES * CHANNELS / float(np.mean(dts)) / 1e6, "unit": UNIT, "cores": tbest, "kind": "reference",
+                                    "sample": f"all {n_sample} streams of the step, one FLAC__StreamEncoder per pthread, "
+                                              f"libFLAC 1.4.3 from oracle/_ref; thread count picked by a probe of {cand}, mean of 3 runs",
+                                    "one_thread_value": 8 * N_SAMPLES * CHANNELS / one / 1e6,
+                                    "host_threads": threads, "bytes_identical_to_gpu": bool(equal and ranks_equal),
+                                    "ranks_checked": ranks_checked,
+                                    "streams_checked": f"rank 0: all {n_sample}; every rank: 9 of its own {N_STREAMS}"}
+            if dec is not None and "cpu_value" in dec:
+                line["cpu_baseline"]["decode_value"], line["cpu_baseline"]["decode_cores"] = dec["cpu_value"], dec["cpu_cores"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -111,6 +111,14 @@ int  flacb200_encode_set_prev_assignment(flacb200_ctx *ctx, const uint8_t *prev_
 int  flacb200_encode_fetch_assignments(flacb200_ctx *ctx, uint8_t *frame_ca, size_t cap);
 /* Synchronises, then reports sizes and device pointers. */
 int  flacb200_encode_result(flacb200_ctx *ctx, flacb200_enc_result *res);
+/* The MD5 of a stream is one serial chain over all of its samples and ends long after the frames of a batch are final
+ * (about 20 ms for 10 s of stereo audio, whatever the batch size).  flacb200_encode_result_frames returns as soon as the
+ * frames, the index and the stream prologues are final; the 16 MD5 bytes of every STREAMINFO (arena offset byte_off + 26)
+ * are still zero then -- exactly what libFLAC writes before its seek-back at finish() (stream_encoder.h:1744-1770).
+ * flacb200_encode_fetch_md5 waits for the chain, returns the digests (16 bytes per stream) and by then the arena and the
+ * per-stream info hold them too. */
+int  flacb200_encode_result_frames(flacb200_ctx *ctx, flacb200_enc_result *res);
+int  flacb200_encode_fetch_md5(flacb200_ctx *ctx, uint8_t *digests, size_t cap);
 /* Copy results to host memory (any pointer may be NULL). arena_cap in bytes. */
 int  flacb200_encode_fetch(flacb200_ctx *ctx, uint8_t *arena, size_t arena_cap,
                            uint64_t *frame_off, uint32_t *frame_len, uint32_t *frame_samples,
@@ -168,8 +176,10 @@ int  flacb200_decode_batch_host(flacb200_ctx *ctx, const uint8_t *blob, uint64_t
 int  flacb200_decode_kernel_times(flacb200_ctx *ctx, float *ms);
 
 /* Per-kernel device times of the last batch, measured with CUDA events on the launching streams:
- * ms[0..8] = analysis (all three kernels), pack, scan, compact, finalize(+MD5 join), md5 (side stream), then the
- * analysis split into its kernels: frame_bits (OR/AND), autoc (autocorrelation), analyze (decisions). */
+ * ms[0..9] = analysis (all three kernels), pack, scan, compact, finalize(+MD5 join), md5 (side stream), then the
+ * analysis split into its kernels: frame_bits (OR/AND), autoc (autocorrelation), analyze (decisions); ms[9] = 1 when
+ * the batch ran the fused kernel (16-bit stereo: one launch from PCM to frame bytes, csrc/enc_fused.cu): ms[0] is
+ * that kernel, ms[1] and ms[6..8] are zero. */
 int  flacb200_set_profiling(flacb200_ctx *ctx, int on);
 int  flacb200_kernel_times(flacb200_ctx *ctx, float *ms);
 /* Wall-clock breakdown (ms since entry) of the last flacb200_encode_batch_host call:

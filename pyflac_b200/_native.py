@@ -88,6 +88,8 @@ def lib():
     L.flacb200_encode_batch.argtypes = [C.c_void_p, C.POINTER(EncConfig), C.c_void_p, C.c_int, C.c_uint64, C.c_uint32,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
     L.flacb200_encode_result.argtypes = [C.c_void_p, C.POINTER(EncResult)]
+    L.flacb200_encode_result_frames.argtypes = [C.c_void_p, C.POINTER(EncResult)]
+    L.flacb200_encode_fetch_md5.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.flacb200_encode_set_prev_assignment.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.flacb200_encode_fetch_assignments.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.flacb200_encode_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -148,9 +150,12 @@ class Engine:
     def kernel_times(self):
         """Device ms of the last batch: analysis (its three kernels together), pack, scan, compact, finalize, md5, then
         the analysis split: frame_bits, autoc, analyze."""
-        ms = np.zeros(9, np.float32)
+        ms = np.zeros(10, np.float32)
         self._check(self._L.flacb200_kernel_times(self._h, ms.ctypes.data))
-        return dict(zip(["analysis", "pack", "scan", "compact", "finalize", "md5", "frame_bits", "autoc", "analyze"], [float(v) for v in ms]))
+        d = dict(zip(["analysis", "pack", "scan", "compact", "finalize", "md5", "frame_bits", "autoc", "analyze"], [float(v) for v in ms[:9]]))
+        if ms[9] > 0:       # the fused kernel ran: one launch from PCM to frame bytes
+            d = {"fused": d["analysis"], "scan": d["scan"], "compact": d["compact"], "finalize": d["finalize"], "md5": d["md5"]}
+        return d
 
     @property
     def launch_count(self):
@@ -183,10 +188,23 @@ class Engine:
         self._check(self._L.flacb200_encode_batch(self._h, C.byref(cfg), pcm.ctypes.data, 0, pcm.size, len(so),
                                                   so.ctypes.data, ss.ctypes.data, ff.ctypes.data if ff is not None else None))
 
-    def result(self):
+    def result(self, wait_md5=True):
+        """Sizes + device pointers of the last batch.  wait_md5=False returns once the frames, index and prologues are final
+        (the MD5 fields of STREAMINFO still zero); fetch_md5() then waits for the digests."""
         r = EncResult()
-        self._check(self._L.flacb200_encode_result(self._h, C.byref(r)))
+        fn = self._L.flacb200_encode_result if wait_md5 else self._L.flacb200_encode_result_frames
+        self._check(fn(self._h, C.byref(r)))
+        self._last_n_streams = int(r.n_streams)
         return r
+
+    def fetch_md5(self):
+        """(n_streams, 16) uint8: the STREAMINFO MD5 of every stream of the last batch (waits for the MD5 chain)."""
+        n = getattr(self, "_last_n_streams", None)
+        if n is None:
+            n = int(self.result(wait_md5=False).n_streams)
+        out = np.zeros((max(n, 1), 16), np.uint8)
+        self._check(self._L.flacb200_encode_fetch_md5(self._h, out.ctypes.data, out.nbytes))
+        return out[:n]
 
     def fetch(self):
         """-> dict(arena=uint8 array, frame_off, frame_len, frame_samples, frame_stream, streams=[StreamInfo])"""

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libflacb200.so")
-SOURCES = ["engine.cu", "enc_analyze.cu", "enc_pack.cu", "flac_api_enc.cu", "dec_kernels.cu", "dec_engine.cu", "flac_api_dec.cu"]
+SOURCES = ["engine.cu", "enc_analyze.cu", "enc_pack.cu", "enc_fused.cu", "flac_api_enc.cu", "dec_kernels.cu", "dec_engine.cu", "flac_api_dec.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

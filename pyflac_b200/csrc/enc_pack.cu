@@ -10,6 +10,7 @@
 //     bitwriter.c FLAC__bitwriter_write_rice_signed_block (ref: format.h:209-475).
 #include "fb_common.cuh"
 #include "fb_math.cuh"
+#include "enc_dev.cuh"
 
 namespace fb {
 
@@ -28,24 +29,6 @@ struct PackShared {
     uint8_t  hdr[16];
     uint32_t hdr_len, x1;
 };
-
-__device__ __forceinline__ void put_bits(uint32_t* buf, uint32_t pos, uint32_t val, uint32_t n) {
-    if (n == 0) return;
-    if (n < 32) val &= (1u << n) - 1u;
-    const uint32_t w = pos >> 5, o = pos & 31;
-    if (o + n <= 32) atomicOr(&buf[w], val << (32 - o - n));
-    else {
-        const uint32_t r = o + n - 32;
-        atomicOr(&buf[w], val >> r);
-        atomicOr(&buf[w + 1], val << (32 - r));
-    }
-}
-
-// up to 33 bits (the side channel of 32-bit stereo): top bit, then the low 32
-__device__ __forceinline__ void put_bits64(uint32_t* buf, uint32_t pos, long long v, uint32_t n) {
-    if (n > 32) { put_bits(buf, pos, (uint32_t)((unsigned long long)v >> 32), n - 32); put_bits(buf, pos + n - 32, (uint32_t)v, 32); }
-    else put_bits(buf, pos, (uint32_t)v, n);
-}
 
 // Rice-coded body of one subframe (up: add_residual_partitioned_rice_ + FLAC__bitwriter_write_rice_signed_block).
 // The whole CTA works on one subframe at a time, tile by tile: thread (warp w, lane l) owns samples
@@ -529,6 +512,23 @@ void launch_md5(const void* pcm, uint32_t container_bytes, const uint64_t* strea
     const int threads = 32, blocks = (n_streams + threads - 1) / threads;
     if (container_bytes == 2) md5_kernel<int16_t><<<blocks, threads, 0, stream>>>((const int16_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
     else md5_kernel<int32_t><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
+}
+
+// The MD5 chain of a batch ends long after its frames are final: the digests are patched into the finished stream
+// images (STREAMINFO bytes 26..41 of each stream) and the per-stream info by this kernel on the batch's side stream.
+__global__ void md5_patch_kernel(const uint8_t* __restrict__ md5, const uint32_t* __restrict__ stream_nframes, int n_streams,
+                                 uint32_t write_prologue, uint8_t* __restrict__ arena, StreamInfoOut* __restrict__ info) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    for (int i = 0; i < 16; i++) info[s].md5[i] = md5[(size_t)s * 16 + i];
+    if (write_prologue && stream_nframes[s]) {
+        uint8_t* p = arena + info[s].byte_off + 26;
+        for (int i = 0; i < 16; i++) p[i] = md5[(size_t)s * 16 + i];
+    }
+}
+void launch_md5_patch(const uint8_t* md5, const uint32_t* stream_nframes, int n_streams, uint32_t write_prologue, uint8_t* arena,
+                      StreamInfoOut* info, cudaStream_t stream) {
+    md5_patch_kernel<<<(n_streams + 127) / 128, 128, 0, stream>>>(md5, stream_nframes, n_streams, write_prologue, arena, info);
 }
 
 void launch_layout(const uint32_t* frame_len, const FrameDesc* frames, int n_frames, uint32_t prologue_bytes, uint64_t base,

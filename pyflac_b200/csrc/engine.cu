@@ -31,11 +31,14 @@ void analyze_layout(EncParams&);
 void launch_pack(const void*, const FrameDesc*, const EncParams&, int, const SubframePlan*, const uint8_t*, uint8_t*,
                  uint32_t, uint32_t*, cudaStream_t);
 size_t pack_smem_bytes(const EncParams&, uint32_t);
+bool fused_eligible(const EncParams&, uint32_t, int);
+void launch_fused(const void*, const FrameDesc*, const float*, const EncParams&, int, uint8_t*, EncStats*, uint8_t*, uint32_t, uint32_t*, cudaStream_t);
 void launch_md5(const void*, uint32_t, const uint64_t*, const uint64_t*, int, uint32_t, uint32_t, uint8_t*, cudaStream_t);
 void launch_layout(const uint32_t*, const FrameDesc*, int, uint32_t, uint64_t, uint64_t*, uint64_t*, cudaStream_t);
 void launch_compact(const uint8_t*, uint32_t, const uint32_t*, const uint64_t*, uint8_t*, int, cudaStream_t);
 void launch_finalize(const uint32_t*, const uint64_t*, const uint32_t*, const uint32_t*, const uint64_t*, const uint8_t*,
                      int, const EncParams&, uint32_t, uint8_t*, StreamInfoOut*, cudaStream_t);
+void launch_md5_patch(const uint8_t*, const uint32_t*, int, uint32_t, uint8_t*, StreamInfoOut*, cudaStream_t);
 }  // namespace fb
 
 using namespace fb;
@@ -71,6 +74,7 @@ struct flacb200_ctx {
     int n_frames = 0, n_streams = 0;
     uint32_t scratch_stride = 0;
     bool have_batch = false, debug = false;
+    bool use_fused = false;                // this batch runs enc_fused.cu (16-bit stereo, one kernel per frame from PCM to bytes)
     std::vector<FrameDesc> h_frames;
     std::vector<uint32_t> h_stream_first, h_stream_nframes;
     std::vector<uint64_t> h_stream_off, h_stream_samples;
@@ -302,6 +306,7 @@ extern "C" int flacb200_kernel_times(flacb200_ctx* ctx, float* ms) {
     CK(cudaEventElapsedTime(&ms[6], ctx->ev_k[0], ctx->ev_k[8]));
     CK(cudaEventElapsedTime(&ms[7], ctx->ev_k[8], ctx->ev_k[9]));
     CK(cudaEventElapsedTime(&ms[8], ctx->ev_k[9], ctx->ev_k[1]));
+    ms[9] = ctx->use_fused ? 1.0f : 0.0f;        // 1: ms[0] is the fused kernel (enc_fused.cu), ms[1] and ms[6..8] are zero
     return 0;
 }
 extern "C" uint64_t flacb200_launch_count(const flacb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -363,8 +368,9 @@ static int plan_batch(flacb200_ctx* ctx, const flacb200_enc_config& cfg, uint32_
     ctx->scratch_stride = max_frame_bytes(P);
     ctx->debug = cfg.debug_trace != 0;
 
+    ctx->use_fused = !ctx->debug && !getenv("FLACB200_NO_FUSED") && fused_eligible(P, ctx->scratch_stride, ctx->max_smem_optin);
     const size_t sa = analyze_smem_bytes(P), sp = pack_smem_bytes(P, ctx->scratch_stride);
-    if ((int)sa > ctx->max_smem_optin || (int)sp > ctx->max_smem_optin)
+    if (!ctx->use_fused && ((int)sa > ctx->max_smem_optin || (int)sp > ctx->max_smem_optin))
         return fail(ctx, FLACB200_ERR_UNSUPPORTED, "blocksize x channels exceeds the shared-memory frame tile of this build");
 
     const int nf = ctx->n_frames;
@@ -433,27 +439,41 @@ static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
         ctx->launches++;
     }
     if (prof) CK(cudaEventRecord(ctx->ev_k[0], st));
-    const int n_an = launch_analyze(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, (SubframePlan*)ctx->d_plans.p,
-                                    (uint8_t*)ctx->d_ca.p, ctx->debug ? (SignalDebug*)ctx->d_debug.p : nullptr, (EncStats*)S.stats.p,
-                                    analyze_smem_bytes(P), ctx->d_work.p, st, prof ? &ctx->ev_k[8] : nullptr);
-    if (prof) CK(cudaEventRecord(ctx->ev_k[1], st));
-    launch_pack(d_pcm, (const FrameDesc*)ctx->d_frames.p, P, nf, (const SubframePlan*)ctx->d_plans.p, (const uint8_t*)ctx->d_ca.p,
-                (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)S.flen.p, st);
+    int n_an;
+    if (ctx->use_fused) {
+        // one kernel from PCM to frame bytes (enc_fused.cu); the split events collapse onto its end
+        launch_fused(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, (uint8_t*)ctx->d_ca.p, (EncStats*)S.stats.p,
+                     (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)S.flen.p, st);
+        if (prof) { CK(cudaEventRecord(ctx->ev_k[8], st)); CK(cudaEventRecord(ctx->ev_k[9], st)); CK(cudaEventRecord(ctx->ev_k[1], st)); }
+        n_an = 0;
+    } else {
+        n_an = launch_analyze(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, (SubframePlan*)ctx->d_plans.p,
+                              (uint8_t*)ctx->d_ca.p, ctx->debug ? (SignalDebug*)ctx->d_debug.p : nullptr, (EncStats*)S.stats.p,
+                              analyze_smem_bytes(P), ctx->d_work.p, st, prof ? &ctx->ev_k[8] : nullptr);
+        if (prof) CK(cudaEventRecord(ctx->ev_k[1], st));
+        launch_pack(d_pcm, (const FrameDesc*)ctx->d_frames.p, P, nf, (const SubframePlan*)ctx->d_plans.p, (const uint8_t*)ctx->d_ca.p,
+                    (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)S.flen.p, st);
+    }
     if (prof) CK(cudaEventRecord(ctx->ev_k[2], st));
     const uint32_t pro = ctx->cfg.write_prologue ? (uint32_t)kStreamPrologueBytes : 0u;
     launch_layout((const uint32_t*)S.flen.p, (const FrameDesc*)ctx->d_frames.p, nf, pro, 0ull, (uint64_t*)S.foff.p, (uint64_t*)S.total.p, st);
     if (prof) CK(cudaEventRecord(ctx->ev_k[3], st));
     launch_compact((const uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (const uint32_t*)S.flen.p, (const uint64_t*)S.foff.p, (uint8_t*)S.arena.p, nf, st);
     if (prof) CK(cudaEventRecord(ctx->ev_k[4], st));
-    // finalize (STREAMINFO with MD5) follows the MD5 on the set's side stream; the main stream moves on to the next batch
-    cudaStream_t fs = md5 ? S.side : st;
-    if (md5) { CK(cudaEventRecord(S.ev_main, st)); CK(cudaStreamWaitEvent(S.side, S.ev_main, 0)); }
+    // finalize (stream prologues, per-stream info; MD5 fields zero) closes the batch on the main stream: from here on the
+    // frames and the index are final.  The MD5 chain -- serial per stream, longer than everything else for long streams --
+    // keeps running on the set's side stream and patches its 16 bytes per stream into place when it is done; the main
+    // stream moves on to the next batch (flacb200_encode_result_frames / flacb200_encode_fetch_md5 expose the two moments).
     launch_finalize((const uint32_t*)S.flen.p, (const uint64_t*)S.foff.p, (const uint32_t*)ctx->d_sfirst.p, (const uint32_t*)ctx->d_snframes.p,
-                    (const uint64_t*)ctx->d_ssamples.p, md5 ? (const uint8_t*)S.md5.p : nullptr, ns, P, pro ? 1u : 0u, (uint8_t*)S.arena.p,
-                    (StreamInfoOut*)S.sinfo.p, fs);
-    if (prof) CK(cudaEventRecord(ctx->ev_k[5], fs));
-    if (md5) { CK(cudaEventRecord(S.ev_free, S.side)); S.busy = true; }
-    ctx->launches += 4 + n_an;
+                    (const uint64_t*)ctx->d_ssamples.p, nullptr, ns, P, pro ? 1u : 0u, (uint8_t*)S.arena.p, (StreamInfoOut*)S.sinfo.p, st);
+    if (prof) CK(cudaEventRecord(ctx->ev_k[5], st));
+    if (md5) {
+        CK(cudaEventRecord(S.ev_main, st)); CK(cudaStreamWaitEvent(S.side, S.ev_main, 0));
+        launch_md5_patch((const uint8_t*)S.md5.p, (const uint32_t*)ctx->d_snframes.p, ns, pro ? 1u : 0u, (uint8_t*)S.arena.p, (StreamInfoOut*)S.sinfo.p, S.side);
+        CK(cudaEventRecord(S.ev_free, S.side)); S.busy = true;
+        ctx->launches++;
+    }
+    ctx->launches += (ctx->use_fused ? 4 : 4 + n_an);        // fused | analysis kernels + pack, then scan, compact, finalize
     CK(cudaGetLastError());
     return 0;
 }
@@ -505,7 +525,22 @@ extern "C" int flacb200_encode_fetch_assignments(flacb200_ctx* ctx, uint8_t* fra
     return 0;
 }
 
-extern "C" int flacb200_encode_result(flacb200_ctx* ctx, flacb200_enc_result* res) {
+static int encode_result_impl(flacb200_ctx* ctx, flacb200_enc_result* res, bool wait_md5);
+extern "C" int flacb200_encode_result(flacb200_ctx* ctx, flacb200_enc_result* res) { return encode_result_impl(ctx, res, true); }
+extern "C" int flacb200_encode_result_frames(flacb200_ctx* ctx, flacb200_enc_result* res) { return encode_result_impl(ctx, res, false); }
+extern "C" int flacb200_encode_fetch_md5(flacb200_ctx* ctx, uint8_t* digests, size_t cap) {
+    if (!ctx || !digests) return FLACB200_ERR_ARG;
+    if (!ctx->have_batch) return fail(ctx, FLACB200_ERR_ARG, "no batch");
+    if (cap < (size_t)ctx->n_streams * 16) return fail(ctx, FLACB200_ERR_ARG, "digest buffer too small");
+    cudaSetDevice(ctx->device);
+    if (!ctx->cfg.do_md5) { memset(digests, 0, (size_t)ctx->n_streams * 16); return 0; }
+    cudaStream_t side = ctx->set().side;
+    if (ctx->n_streams && ctx->n_frames) CK(cudaMemcpyAsync(digests, ctx->set().md5.p, (size_t)ctx->n_streams * 16, cudaMemcpyDeviceToHost, side));
+    else memset(digests, 0, (size_t)ctx->n_streams * 16);
+    CK(cudaStreamSynchronize(side));
+    return 0;
+}
+static int encode_result_impl(flacb200_ctx* ctx, flacb200_enc_result* res, bool wait_md5) {
     if (!ctx || !res) return FLACB200_ERR_ARG;
     if (!ctx->have_batch) return fail(ctx, FLACB200_ERR_ARG, "no batch");
     cudaSetDevice(ctx->device);
@@ -513,7 +548,7 @@ extern "C" int flacb200_encode_result(flacb200_ctx* ctx, flacb200_enc_result* re
     CK(cudaMemcpyAsync(&total, ctx->set().total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&stt, ctx->set().stats.p, sizeof stt, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->set().busy) CK(cudaStreamSynchronize(ctx->set().side));     // MD5 + STREAMINFO of this batch live on the set's side stream
+    if (wait_md5 && ctx->set().busy) CK(cudaStreamSynchronize(ctx->set().side));     // the MD5 of this batch lives on the set's side stream
     res->total_bytes = total; res->n_frames = (uint32_t)ctx->n_frames; res->n_streams = (uint32_t)ctx->n_streams;
     res->log_guard_hits = stt.log_ambiguous;
     res->d_arena = (const uint8_t*)ctx->set().arena.p; res->d_frame_off = (const uint64_t*)ctx->set().foff.p; res->d_frame_len = (const uint32_t*)ctx->set().flen.p;
@@ -694,12 +729,19 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         dev_base[c + 1] = dev_base[c] + (((uint64_t)cnf * ctx->scratch_stride + (uint64_t)cns * kStreamPrologueBytes + 255) / 256) * 256;
         CKJ(cudaStreamWaitEvent(st, ctx->ev_h2d[c], 0));
         if (cnf > 0) {
-            const int n_an = launch_analyze(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf,
+            int n_an = 0;
+            if (ctx->use_fused) {
+                launch_fused(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf, (uint8_t*)ctx->d_ca.p + f0,
+                             (EncStats*)ctx->set().stats.p, (uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride,
+                             (uint32_t*)ctx->set().flen.p + f0, st);
+            } else {
+            n_an = launch_analyze(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf,
                                             (SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals, (uint8_t*)ctx->d_ca.p + f0, nullptr, (EncStats*)ctx->set().stats.p,
                                             analyze_smem_bytes(P), (uint8_t*)ctx->d_work.p + (size_t)f0 * analyze_work_stride(P), st, nullptr);
             launch_pack(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, P, cnf, (const SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals,
                         (const uint8_t*)ctx->d_ca.p + f0, (uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride,
                         (uint32_t*)ctx->set().flen.p + f0, st);
+            }
             launch_layout((const uint32_t*)ctx->set().flen.p + f0, (const FrameDesc*)ctx->d_frames.p + f0, cnf, pro, dev_base[c],
                           (uint64_t*)ctx->set().foff.p + f0, (uint64_t*)ctx->d_totals.p + c, st);
             launch_compact((const uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride, (const uint32_t*)ctx->set().flen.p + f0,
@@ -707,7 +749,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
             launch_finalize((const uint32_t*)ctx->set().flen.p, (const uint64_t*)ctx->set().foff.p, (const uint32_t*)ctx->d_sfirst.p + s0,
                             (const uint32_t*)ctx->d_snframes.p + s0, (const uint64_t*)ctx->d_ssamples.p + s0, nullptr, cns, P, pro ? 1u : 0u,
                             (uint8_t*)ctx->set().arena.p, (StreamInfoOut*)ctx->set().sinfo.p + s0, st);
-            ctx->launches += 4 + n_an;
+            ctx->launches += ctx->use_fused ? 4 : 4 + n_an;
         } else {
             CKJ(cudaMemsetAsync((uint64_t*)ctx->d_totals.p + c, 0, 8, st));
         }

@@ -215,6 +215,59 @@ def test_encode_sample_rates_and_frame_numbers(eng, checkers):
     assert got[0] == checkers.oracle_encode(x, 48000, 16, 0, 16)
 
 
+def test_result_frames_then_md5(eng, checkers):
+    """flacb200_encode_result_frames / flacb200_encode_fetch_md5: the frames of a batch are final (and fetchable) before
+    its MD5 chain ends; the digests arrive later and are patched into the stream images.  Everything but the 16 MD5 bytes
+    must already equal libFLAC's output at the first moment, everything at the second."""
+    from pyflac_b200 import _native as nat
+    xs = [music_like(4096 * 40 + 123 * s, 2, 48000, 16, seed=300 + s) for s in range(24)]
+    flat = np.concatenate([x.reshape(-1) for x in xs])
+    sizes = np.array([x.size for x in xs], np.uint64)
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+    cfg = nat.Engine.make_config(48000, 2, 16, 5, 0)
+    eng.encode_host(cfg, flat, offs, sizes // 2)
+    r = eng.result(wait_md5=False)
+    assert r.n_streams == 24 and r.total_bytes > 0
+    dig = eng.fetch_md5()
+    out = eng.fetch()
+    for s, x in enumerate(xs):
+        si = out["streams"][s]
+        blob = out["arena"][int(si.byte_off): int(si.byte_off + si.byte_len)].tobytes()
+        assert blob == checkers.oracle_encode(x, 48000, 16, 5, 0), s
+        assert bytes(dig[s]) == hashlib.md5(x.tobytes()).digest() == bytes(si.md5) == blob[26:42]
+    # do_md5 = 0: digests are zero, as libFLAC's set_do_md5(false)
+    cfg0 = nat.Engine.make_config(48000, 2, 16, 5, 0, do_md5=False)
+    eng.encode_host(cfg0, flat, offs, sizes // 2)
+    eng.result(wait_md5=False)
+    assert not eng.fetch_md5().any()
+    out0 = eng.fetch()
+    si = out0["streams"][3]
+    assert bytes(out0["arena"][int(si.byte_off) + 26: int(si.byte_off) + 42]) == bytes(16)
+
+
+def test_fused_and_multi_kernel_paths_agree(checkers, monkeypatch):
+    """16-bit stereo runs the fused kernel (csrc/enc_fused.cu), FLACB200_NO_FUSED=1 the multi-kernel path the other layouts
+    use: same bytes from both, for aligned and unaligned frame bases (the fused kernel stages with TMA only when the frame
+    starts on a 16-byte boundary), odd blocksizes and every level without loose mid/side."""
+    from pyflac_b200 import _native as nat
+    xs = [corpus_signal(kind, 4096 * 2 + 1000 + 3 * i, 2, 16, seed=40 + i) for i, kind in enumerate(CORPUS_KINDS)]
+    xs += [music_like(n, 2, 48000, 16, seed=n) for n in (1, 3, 17, 4097, 4096 * 3)]
+    for level, bs in [(0, 0), (2, 0), (3, 0), (5, 0), (5, 1000), (6, 0), (8, 0), (8, 1152), (7, 4608), (5, 16)]:
+        monkeypatch.delenv("FLACB200_NO_FUSED", raising=False)
+        e1 = nat.Engine(0)
+        a, oa = nat.encode_streams(e1, xs, 44100, 16, level, bs)
+        launches_fused = e1.launch_count
+        e1.close()
+        monkeypatch.setenv("FLACB200_NO_FUSED", "1")
+        e2 = nat.Engine(0)
+        b, ob = nat.encode_streams(e2, xs, 44100, 16, level, bs)
+        assert e2.launch_count > launches_fused            # the other path really ran
+        e2.close()
+        assert a == b, (level, bs)
+        assert oa["log_guard_hits"] == 0 and ob["log_guard_hits"] == 0
+    monkeypatch.delenv("FLACB200_NO_FUSED", raising=False)
+
+
 def test_encode_vs_reference_binary_live(eng, checkers):
     """same-run comparison with the reference binary itself when oracle/_ref travelled to this box"""
     if not checkers.ref_available():
