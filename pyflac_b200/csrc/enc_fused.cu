@@ -30,6 +30,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <algorithm>
+#include <vector>
+#include <stdio.h>
+#include <stdlib.h>
 #include "fb_common.cuh"
 #include "fb_math.cuh"
 #include "enc_dev.cuh"
@@ -39,7 +42,10 @@ namespace fb {
 constexpr int kFuThreads = 256;
 constexpr int kFuWarps = kFuThreads / 32;
 constexpr int kFuSig = 4;                  // L, R, mid, side
-constexpr int kFuRing = 82;                // doubles per autocorrelation job: 16 mirror + 2 slots of 32 (+2 against bank aliasing)
+constexpr int kWinSlots = 16;              // 32-float slots of the window-value ring (cp.async destination)
+constexpr int kWinAhead = 8;               // chunks a window value is requested ahead of its use
+constexpr int kFuSlots = 4;                // 32-sample slots in the autocorrelation ring (power of two)
+constexpr int kFuRing = 16 + 32 * kFuSlots + 2;   // doubles per autocorrelation job: 16 mirror + the slots (+2: jobs land in different banks)
 constexpr int kFuRun = 16;                 // consecutive samples a lane codes in the pack phase
 constexpr int kFuChunk = 32 * kFuRun;      // samples a warp codes per round
 
@@ -48,7 +54,7 @@ constexpr int kFuChunk = 32 * kFuRun;      // samples a warp codes per round
 struct FuLayout {
     uint32_t tile_words;
     uint32_t ovl_off, ovl_bytes;
-    uint32_t ring_off, acstore_off, ws_off, psum_off, fixsum_off, baseplan_off, stepplan_off;   // inside ovl
+    uint32_t ring_off, wring_off, acstore_off, ws_off, psum_off, fixsum_off, baseplan_off, stepplan_off;   // inside ovl
     uint32_t shared_off, crctab_off, total_bytes;
     uint32_t obuf_words, n_win, n_steps, pad;
 };
@@ -60,6 +66,7 @@ struct FuShared {
     uint32_t step_bits[kFuSig][kMaxSteps];
     int      need_list[kFuSig];
     int      nneed, queue_a, queue_b, ca;
+    int      ac_warp, pad2;                // the warp that runs the first autocorrelation item (rotates per SM, see g_fu_ticket)
     SubframePlan plan[2];                  // the two coded subframes
     int32_t  sigidx[2];
     uint32_t segtot[kFuWarps];
@@ -110,80 +117,151 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 // up: lpc.c FLAC__lpc_window_data[_partial] + FLAC__lpc_compute_autocorrelation.
 // One item = one window (depth b, position k) of the frame, nsig jobs (signals) that share the sample word and the
 // window value.  Lane = (job, lag pair): chains of lags 2q and 2q+1, each strictly sequential in i (fma of two exact
-// float products == libFLAC's mul + add).  Per job a ring of two 32-sample slots of doubles with a 16-entry mirror of
-// slot 1's tail in front of slot 0, so "i - lag" is a plain negative offset.  The raw word and window value of chunk
-// c+1 are requested before the chains of chunk c run and are converted after them.
+// float products == libFLAC's mul + add).  Per job a ring of four 32-sample slots of doubles with a 16-entry mirror of
+// the last slot's tail in front of slot 0, so "i - lag" is a plain negative offset.  Window values arrive through a
+// cp.async ring eight chunks ahead; chunk c+1 is converted before the chains of chunk c run.
+// ROLE 0: one warp converts and runs the chains (levels with many windows).  ROLE 1 / 2: a pair of warps -- the chain warp
+// (1) only runs the DFMA chains, its partner (2) windows and converts one chunk ahead into the ring; they meet once per
+// 32-sample chunk at a named barrier (bar_id, 64 threads).  A warp issues in order, so a lone warp pays the conversion's
+// dependent steps (shared load -> int -> float -> multiply -> double -> store, ~150 cycles) in front of every chunk's
+// 260 cycles of chain latency; the pair hides them (measured: 1050 -> ~300 cycles per chunk).
+template <int ROLE>
 __device__ __noinline__ void fu_autoc_item(const int32_t* __restrict__ tile, const FuGeo G, const float* __restrict__ win_tab,
                                            int b, int k, int nsig, int lags, const uint32_t* __restrict__ sig_or, int bps,
-                                           double* __restrict__ ring, double* __restrict__ acstore, int n_win, int lane) {
+                                           double* __restrict__ ring, float* __restrict__ wring, double* __restrict__ acstore, int n_win,
+                                           int lane, int bar_id) {
     const int N = G.N;
     const int len = N / b, part = (b == 1) ? N : N / b / 2, off = (k * N) / b;
     const int wtail = N - 2 * part;                   // window index = i (i < part) or wtail + i (part <= i < 2*part)
     const int LJ = (lags + 1) >> 1;                   // lanes per job
-    int shp[kFuSig];
-#pragma unroll
-    for (int s = 0; s < kFuSig; s++) shp[s] = (s < nsig) ? wasted_from_or(sig_or[s], bps) + (s == 2 ? 1 : 0) : 0;
-    for (int idx = lane; idx < nsig * 16; idx += 32) ring[(idx >> 4) * kFuRing + (idx & 15)] = 0.0;
-
-    int raw_w; float raw_wv;
-    auto request = [&](int i) {
-        raw_w = 0; raw_wv = 0.0f;
-        if (i < len && i < 2 * part) {
-            raw_wv = __ldg(win_tab + (i < part ? i : wtail + i));
-            raw_w = tile[tix(G, off + i)];
-        }
-    };
-    auto convert = [&](int slot) {
-        const int lo = (int)(short)raw_w, hi = raw_w >> 16;
-        float dv[kFuSig];
-        dv[0] = FB_FMUL(__int2float_rn(lo >> shp[0]), raw_wv);
-        dv[1] = FB_FMUL(__int2float_rn(hi >> shp[1]), raw_wv);
-        dv[2] = FB_FMUL(__int2float_rn((lo + hi) >> shp[2]), raw_wv);
-        dv[3] = FB_FMUL(__int2float_rn((lo - hi) >> shp[3]), raw_wv);
-#pragma unroll
-        for (int s = 0; s < kFuSig; s++) {
-            if (s < nsig) {
-                const double d = (double)dv[s];
-                ring[s * kFuRing + 16 + slot * 32 + lane] = d;
-                if (slot == 1 && lane >= 16) ring[s * kFuRing + lane - 16] = d;      // slot 1's tail mirrored in front of slot 0
-            }
-        }
-    };
-    request(lane);
-    convert(0);
-    __syncwarp();
-
-    const int jb = lane / LJ, qd = lane - jb * LJ;
-    const bool active = jb < nsig;
-    const int lag0 = 2 * qd;
-    const double* jobring = ring + (active ? jb : 0) * kFuRing;
-    double a0 = 0.0, a1 = 0.0, p1 = 0.0;
     const int nchunks = (len + 31) >> 5;
-    for (int c = 0; c < nchunks; c++) {
-        const int slot = c & 1;
-        request((c + 1) * 32 + lane);
-        if (active) {
-            const double* curp = jobring + 16 + slot * 32;
-            const double* lagp = curp - lag0;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory"); };
+
+    if (ROLE != 1) {
+        int shp[kFuSig];
 #pragma unroll
-            for (int s = 0; s < 32; s += 2) {
-                const double2 c2 = *reinterpret_cast<const double2*>(curp + s);
-                const double2 l2 = *reinterpret_cast<const double2*>(lagp + s);
-                a0 = fma(c2.x, l2.x, a0); a1 = fma(c2.x, p1, a1);
-                a0 = fma(c2.y, l2.y, a0); a1 = fma(c2.y, l2.x, a1);
-                p1 = l2.y;
+        for (int s = 0; s < kFuSig; s++) shp[s] = (s < nsig) ? wasted_from_or(sig_or[s], bps) + (s == 2 ? 1 : 0) : 0;
+        for (int idx = lane; idx < nsig * 16; idx += 32) ring[(idx >> 4) * kFuRing + (idx & 15)] = 0.0;
+        // The window table lives in global memory (16 KiB per blocksize, shared by every frame; the SM's L1 is mostly carved
+        // into shared memory here, so a read is an L2 round trip of several hundred cycles).  Its values travel straight into
+        // a small shared ring with cp.async -- no destination register, so nothing waits on them -- kWinAhead chunks ahead
+        // of their use; samples outside the window read as zero (src-size 0 zero-fills).
+        const uint32_t wr_base = smem_u32(wring) + (uint32_t)lane * 4u;
+        auto request = [&](int c) {
+            const int i = c * 32 + lane;
+            const bool in = (i < len && i < 2 * part);
+            const float* src = win_tab + (in ? (i < part ? i : wtail + i) : 0);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(wr_base + (uint32_t)(c & (kWinSlots - 1)) * 128u), "l"(src), "r"(in ? 4u : 0u) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto convert = [&](int c) {
+            const int slot = c & (kFuSlots - 1);
+            const int i = c * 32 + lane;
+            float rwv;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rwv) : "r"(wr_base + (uint32_t)(c & (kWinSlots - 1)) * 128u) : "memory");
+            const int rw = (i < len && i < 2 * part) ? tile[tix(G, off + i)] : 0;
+            const int lo = (int)(short)rw, hi = rw >> 16;
+            float dv[kFuSig];
+            dv[0] = FB_FMUL(__int2float_rn(lo >> shp[0]), rwv);
+            dv[1] = FB_FMUL(__int2float_rn(hi >> shp[1]), rwv);
+            dv[2] = FB_FMUL(__int2float_rn((lo + hi) >> shp[2]), rwv);
+            dv[3] = FB_FMUL(__int2float_rn((lo - hi) >> shp[3]), rwv);
+#pragma unroll
+            for (int s = 0; s < kFuSig; s++) {
+                if (s < nsig) {
+                    const double d = (double)dv[s];
+                    ring[s * kFuRing + 16 + slot * 32 + lane] = d;
+                    if (slot == kFuSlots - 1 && lane >= 16) ring[s * kFuRing + lane - 16] = d;      // the last slot's tail mirrored in front of slot 0
+                }
             }
+        };
+#pragma unroll 1
+        for (int c = 0; c < kWinAhead; c++) request(c);
+        asm volatile("cp.async.wait_group %0;" :: "n"(kWinAhead - 1) : "memory");       // chunk 0 has landed
+        convert(0);
+        if (ROLE == 2) {
+            // converter of a pair: chunk c+1 is ready before the chain warp passes barrier c.  While the chains of chunk c
+            // read slot c (and the tail of slot c-1, the mirror only when slot == 0) this warp fills slot c+2.
+            request(kWinAhead);
+            asm volatile("cp.async.wait_group %0;" :: "n"(kWinAhead - 1) : "memory");
+            convert(1);
+#pragma unroll 1
+            for (int c = 0; c < nchunks; c++) {
+                pair_sync();
+                request(c + 1 + kWinAhead);
+                asm volatile("cp.async.wait_group %0;" :: "n"(kWinAhead - 1) : "memory");
+                convert(c + 2);
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            return;
         }
         __syncwarp();
-        convert(slot ^ 1);
+        // ROLE 0 continues below with the chains, converting chunk c+1 in front of the chains of chunk c
+        const int jb = lane / LJ, qd = lane - jb * LJ;
+        const bool active = jb < nsig;
+        const int lag0 = 2 * qd;
+        const double* jobring = ring + (active ? jb : 0) * kFuRing;
+        double a0 = 0.0, a1 = 0.0, p1 = 0.0;
+#pragma unroll 1
+        for (int c = 0; c < nchunks; c++) {
+            const int slot = c & (kFuSlots - 1);
+            request(c + kWinAhead);
+            asm volatile("cp.async.wait_group %0;" :: "n"(kWinAhead - 1) : "memory");   // chunk c+1's window values have landed
+            convert(c + 1);
+            if (active) {
+                const double* curp = jobring + 16 + slot * 32;
+                const double* lagp = curp - lag0;
+#pragma unroll
+                for (int s = 0; s < 32; s += 2) {
+                    const double2 c2 = *reinterpret_cast<const double2*>(curp + s);
+                    const double2 l2 = *reinterpret_cast<const double2*>(lagp + s);
+                    a0 = fma(c2.x, l2.x, a0); a1 = fma(c2.x, p1, a1);
+                    a0 = fma(c2.y, l2.y, a0); a1 = fma(c2.y, l2.x, a1);
+                    p1 = l2.y;
+                }
+            }
+            __syncwarp();
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (active) {
+            double* dst = acstore + ((size_t)jb * n_win + (b - 1) * b / 2 + k) * kAcStoreStride + lag0;
+            dst[0] = a0;
+            if (lag0 + 1 < kAcStoreStride) dst[1] = a1;
+        }
+        __syncwarp();
+        return;
+    }
+    // ---- ROLE 1: the chain warp of a pair ----
+    {
+        const int jb = lane / LJ, qd = lane - jb * LJ;
+        const bool active = jb < nsig;
+        const int lag0 = 2 * qd;
+        const double* jobring = ring + (active ? jb : 0) * kFuRing;
+        double a0 = 0.0, a1 = 0.0, p1 = 0.0;
+#pragma unroll 1
+        for (int c = 0; c < nchunks; c++) {
+            const int slot = c & (kFuSlots - 1);
+            pair_sync();                                                   // chunk c (and c+1) converted
+            if (active) {
+                const double* curp = jobring + 16 + slot * 32;
+                const double* lagp = curp - lag0;
+#pragma unroll
+                for (int s = 0; s < 32; s += 2) {
+                    const double2 c2 = *reinterpret_cast<const double2*>(curp + s);
+                    const double2 l2 = *reinterpret_cast<const double2*>(lagp + s);
+                    a0 = fma(c2.x, l2.x, a0); a1 = fma(c2.x, p1, a1);
+                    a0 = fma(c2.y, l2.y, a0); a1 = fma(c2.y, l2.x, a1);
+                    p1 = l2.y;
+                }
+            }
+        }
+        if (active) {
+            double* dst = acstore + ((size_t)jb * n_win + (b - 1) * b / 2 + k) * kAcStoreStride + lag0;
+            dst[0] = a0;
+            if (lag0 + 1 < kAcStoreStride) dst[1] = a1;
+        }
         __syncwarp();
     }
-    if (active) {
-        double* dst = acstore + ((size_t)jb * n_win + (b - 1) * b / 2 + k) * kAcStoreStride + lag0;
-        dst[0] = a0;
-        if (lag0 + 1 < kAcStoreStride) dst[1] = a1;
-    }
-    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------ fixed predictors
@@ -369,32 +447,88 @@ __device__ __forceinline__ bool fu_lpc_psums(const int32_t* tile, const FuGeo& G
 }
 
 // ------------------------------------------------------------------------------------------------ pack
-// A lane's bits form one contiguous run: they are assembled in a register and leave word by word.  Words strictly
-// inside the run belong to this lane alone (plain store into the zeroed image); the first and the last word may be
-// shared with the neighbouring runs / header fields (atomicOr).
-struct BitRun {
-    uint32_t* buf; uint32_t first_w, cw, cv;
-    __device__ __forceinline__ void init(uint32_t* b, uint32_t pos) { buf = b; cw = first_w = pos >> 5; cv = 0u; }
-    __device__ __forceinline__ void flush() {
-        if (cv) { if (cw == first_w) atomicOr(&buf[cw], cv); else buf[cw] = cv; }
-        cv = 0u;
-    }
-    // val < 2^n, 1 <= n <= 32
-    __device__ __forceinline__ void put(uint32_t pos, uint32_t val, uint32_t n) {
-        const uint32_t w = pos >> 5, o = pos & 31u;
-        if (w != cw) { flush(); cw = w; }
-        if (o + n <= 32u) cv |= val << (32u - o - n);
-        else { const uint32_t r = o + n - 32u; cv |= val >> r; flush(); cw = w + 1u; cv = val << (32u - r); }
-    }
-    __device__ __forceinline__ void finish() { if (cv) atomicOr(&buf[cw], cv); cv = 0u; }
-};
+// i / psize through the precomputed reciprocal; magic 0 marks one-sample partitions (the 32-bit reciprocal of 1 does not exist)
+__device__ __forceinline__ uint32_t pdiv(uint32_t i, uint32_t magic) { return magic ? __umulhi(i, magic) : i; }
+
+// val < 2^n, 1 <= n <= 32
+__device__ __forceinline__ void put_code(uint32_t* buf, uint32_t pos, uint32_t val, uint32_t n) {
+    const uint32_t w = pos >> 5, o = pos & 31u;
+    if (o + n <= 32u) atomicOr(&buf[w], val << (32u - o - n));
+    else { const uint32_t r = o + n - 32u; atomicOr(&buf[w], val >> r); atomicOr(&buf[w + 1u], val << (32u - r)); }
+}
 
 // Rice-coded body of one subframe (up: add_residual_partitioned_rice_ + FLAC__bitwriter_write_rice_signed_block).
-// Round r: warp w codes samples [(r * 8 + w) * 512, +512), lane l the 16 consecutive samples at + 16 l.  Pass 1 computes
-// each residual once (kept zig-zag folded in registers) and the lane's bit count (codes + the parameter field of every
-// partition that starts inside the run); an exclusive warp scan and the eight warp totals (one CTA barrier per round)
-// give the lane's absolute bit position; pass 2 writes the run.  Returns the body length in bits.
+// Round r: warp w codes samples [(r * 8 + w) * 512, +512), lane l the 16 consecutive samples at + 16 l, four at a time
+// (one 16-byte shared load; the predictor history slides through registers).  Pass 1 counts the lane's bits (codes + the
+// parameter field of every partition that starts inside its run); an exclusive warp scan and the eight warp totals (one
+// CTA barrier per round) give the lane's absolute bit position; pass 2 computes the residuals again and ORs the codes
+// into the zeroed image: neighbouring lanes are ~160 bits apart, so the shared atomics rarely meet in one word.  The
+// residuals are computed twice instead of parked in registers: the loops stay rolled and small (this phase was
+// instruction-fetch bound when it was unrolled over the run).  Returns the body length in bits.
 // C = order class, WIDE = 64-bit accumulate (chosen exactly as the analysis does).
+template <int C, bool WIDE, bool EMIT>
+__device__ __forceinline__ uint32_t fu_pack_run(const SubframePlan& pl, const int32_t (&q)[C], int order, int shift, const int32_t* __restrict__ tile,
+                                                const FuGeo& G, const Sig& sg, int i0, uint32_t plen, uint32_t psize, uint32_t pmagic, bool runpart,
+                                                uint32_t pos, uint32_t* __restrict__ obuf) {
+    const int N = G.N;
+    int32_t xw[C];                                     // the C samples before the current quad
+#pragma unroll
+    for (int v = 0; v < C / 4; v++) {
+        const int idx = i0 - C + 4 * v;
+        int4 w = make_int4(0, 0, 0, 0);
+        if (idx >= 0) w = *reinterpret_cast<const int4*>(tile + tix(G, idx));
+        xw[4 * v + 0] = sv(w.x, sg); xw[4 * v + 1] = sv(w.y, sg); xw[4 * v + 2] = sv(w.z, sg); xw[4 * v + 3] = sv(w.w, sg);
+    }
+    const uint32_t part0 = pdiv((uint32_t)i0, pmagic);
+    uint32_t kk = pl.rice[part0];
+    uint32_t bits = 0;
+#pragma unroll 1
+    for (int ib = i0; ib < i0 + kFuRun && ib < N; ib += 4) {
+        const int4 w = *reinterpret_cast<const int4*>(tile + tix(G, ib));
+        int32_t xq[4];
+        xq[0] = sv(w.x, sg); xq[1] = sv(w.y, sg); xq[2] = sv(w.z, sg); xq[3] = sv(w.w, sg);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int i = ib + t;
+            int32_t r;
+            if (WIDE) {
+                long long s = 0;
+#pragma unroll
+                for (int j = 0; j < C; j++) s += (long long)q[j] * (long long)((t - 1 - j >= 0) ? xq[(t - 1 - j) & 3] : xw[(C + t - 1 - j) % C]);
+                r = (int32_t)((long long)xq[t] - (s >> shift));
+            } else {
+                int s = 0;
+#pragma unroll
+                for (int j = 0; j < C; j++) s += q[j] * ((t - 1 - j >= 0) ? xq[(t - 1 - j) & 3] : xw[(C + t - 1 - j) % C]);
+                r = xq[t] - (s >> shift);
+            }
+            const uint32_t uu = ((uint32_t)r << 1) ^ (uint32_t)(r >> 31);
+            bool head;
+            if (runpart) head = (i == i0 && (uint32_t)i0 == part0 * psize && i0 >= order) || (i == order);
+            else {
+                const uint32_t part = pdiv((uint32_t)i, pmagic);
+                kk = pl.rice[part];
+                head = (i == order) || ((uint32_t)i == part * psize && i > order);
+            }
+            if (i >= order && i < N) {
+                if (EMIT) {
+                    if (head) { put_code(obuf, pos, kk, plen); pos += plen; }
+                    pos += uu >> kk;                                                 // unary zeros: the image is already zero
+                    put_code(obuf, pos, (1u << kk) | (uu & ((1u << kk) - 1u)), kk + 1u);
+                    pos += kk + 1u;
+                } else {
+                    bits += (uu >> kk) + 1u + kk + (head ? plen : 0u);
+                }
+            }
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < C - 4; k2++) xw[k2] = xw[k2 + 4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++) xw[C - 4 + k2] = xq[k2];
+    }
+    return bits;
+}
+
 template <int C, bool WIDE>
 __device__ __noinline__ uint32_t fu_pack_body(const SubframePlan& pl, const int32_t* __restrict__ qs, int order, int shift,
                                               const int32_t* __restrict__ tile, const FuGeo G, const Sig sg, uint32_t body,
@@ -405,61 +539,13 @@ __device__ __noinline__ uint32_t fu_pack_body(const SubframePlan& pl, const int3
     for (int j = 0; j < C; j++) q[j] = (j < order) ? qs[j] : 0;
     const uint32_t plen = pl.rice2 ? 5u : 4u;
     const uint32_t psize = (uint32_t)N >> pl.part_order;
-    const uint32_t pmagic = (uint32_t)((0x100000000ull + psize - 1u) / psize);   // i / psize == umulhi(i, pmagic) for i, psize < 2^16
+    const uint32_t pmagic = psize > 1u ? (uint32_t)((0x100000000ull + psize - 1u) / psize) : 0u;   // i / psize == umulhi(i, pmagic) for i, psize < 2^16 (psize 1: pdiv)
     const bool runpart = (psize % (uint32_t)kFuRun) == 0u;                        // a run never straddles a partition boundary
     uint32_t done_bits = 0;
     for (int r0 = 0; r0 < N; r0 += kFuWarps * kFuChunk) {
         const int i0 = r0 + warp * kFuChunk + lane * kFuRun;
-        uint32_t u[kFuRun];
-        uint32_t kks = 0;                          // runpart: the run's Rice parameter; else unused
         uint32_t mybits = 0;
-        uint32_t heads = 0;                        // bit t: sample i0 + t starts a partition
-        if (i0 < N) {
-            int32_t x[C + kFuRun];                 // x[C + t] = sample i0 + t, x[0..C) = the C samples before the run
-#pragma unroll
-            for (int v = 0; v < (C + kFuRun) / 4; v++) {
-                const int idx = i0 - C + 4 * v;
-                int4 w = make_int4(0, 0, 0, 0);
-                if (idx >= 0 && idx < N) w = *reinterpret_cast<const int4*>(tile + tix(G, idx));
-                x[4 * v + 0] = sv(w.x, sg); x[4 * v + 1] = sv(w.y, sg); x[4 * v + 2] = sv(w.z, sg); x[4 * v + 3] = sv(w.w, sg);
-            }
-            uint32_t part0 = __umulhi((uint32_t)i0, pmagic);
-            if (runpart) kks = pl.rice[part0];
-#pragma unroll
-            for (int t = 0; t < kFuRun; t++) {
-                const int i = i0 + t;
-                int32_t r;
-                if (WIDE) {
-                    long long s = 0;
-#pragma unroll
-                    for (int j = 0; j < C; j++) s += (long long)q[j] * (long long)x[C + t - 1 - j];
-                    r = (int32_t)((long long)x[C + t] - (s >> shift));
-                } else {
-                    int s = 0;
-#pragma unroll
-                    for (int j = 0; j < C; j++) s += q[j] * x[C + t - 1 - j];
-                    r = x[C + t] - (s >> shift);
-                }
-                const uint32_t uu = ((uint32_t)r << 1) ^ (uint32_t)(r >> 31);
-                const bool valid = (i >= order) && (i < N);
-                uint32_t kk = kks;
-                bool head;
-                if (runpart) head = (t == 0 && (uint32_t)i0 == part0 * psize && i0 >= order) || (i == order);
-                else {
-                    const uint32_t part = __umulhi((uint32_t)i, pmagic);
-                    kk = pl.rice[part];
-                    head = (i == order) || ((uint32_t)i == part * psize && i > order);
-                }
-                u[t] = valid ? uu : 0xffffffffu;
-                if (valid) {
-                    mybits += (uu >> kk) + 1u + kk + (head ? plen : 0u);
-                    if (head) heads |= 1u << t;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int t = 0; t < kFuRun; t++) u[t] = 0xffffffffu;
-        }
+        if (i0 < N) mybits = fu_pack_run<C, WIDE, false>(pl, q, order, shift, tile, G, sg, i0, plen, psize, pmagic, runpart, 0u, obuf);
         // exclusive scan of the lanes' bit counts; warp totals through shared memory
         uint32_t incl = mybits;
 #pragma unroll
@@ -469,22 +555,7 @@ __device__ __noinline__ uint32_t fu_pack_body(const SubframePlan& pl, const int3
         uint32_t pos = body + done_bits + (incl - mybits), round_bits = 0;
 #pragma unroll
         for (int w2 = 0; w2 < kFuWarps; w2++) { const uint32_t t2 = S.segtot[w2]; if (w2 < warp) pos += t2; round_bits += t2; }
-        if (mybits) {
-            BitRun br; br.init(obuf, pos);
-            uint32_t part = __umulhi((uint32_t)i0, pmagic);
-            uint32_t kk = pl.rice[part];
-#pragma unroll
-            for (int t = 0; t < kFuRun; t++) {
-                if (u[t] != 0xffffffffu) {
-                    if (!runpart) { part = __umulhi((uint32_t)(i0 + t), pmagic); kk = pl.rice[part]; }
-                    if ((heads >> t) & 1u) { br.put(pos, kk, plen); pos += plen; }
-                    pos += u[t] >> kk;                                              // unary zeros: the image is already zero
-                    br.put(pos, (1u << kk) | (u[t] & ((1u << kk) - 1u)), kk + 1u);
-                    pos += kk + 1u;
-                }
-            }
-            br.finish();
-        }
+        if (mybits) fu_pack_run<C, WIDE, true>(pl, q, order, shift, tile, G, sg, i0, plen, psize, pmagic, runpart, pos, obuf);
         done_bits += round_bits;
         __syncthreads();                              // segtot is reused by the next round / subframe
     }
@@ -500,15 +571,25 @@ __device__ __forceinline__ uint32_t fu_pack_dispatch(int order, const SubframePl
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+// The autocorrelation warp of a CTA keeps one SM sub-partition's FP64 pipe busy (a warp-wide DFMA occupies it for two
+// cycles whatever the number of active lanes).  If the four resident CTAs all gave that job to the same warp index, their
+// chains would share ONE sub-partition's pipe (measured: 27 cycles per step instead of the 8.1-cycle DFMA latency).  A
+// ticket per SM rotates the warp index, so co-resident CTAs land on different sub-partitions.
+__device__ unsigned int g_fu_ticket[256];
+
 #ifndef FB_FU_MIN_CTAS
 #define FB_FU_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(kFuThreads, FB_FU_MIN_CTAS)
 fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict__ frames, const float* __restrict__ windows,
                     EncParams P, FuLayout L, uint8_t* __restrict__ frame_ca, EncStats* __restrict__ stats,
-                    uint8_t* __restrict__ scratch, uint32_t scratch_stride, uint32_t* __restrict__ frame_len) {
+                    uint8_t* __restrict__ scratch, uint32_t scratch_stride, uint32_t* __restrict__ frame_len,
+                    unsigned long long* __restrict__ tl) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // optional per-CTA timeline (FLACB200_FU_TIMELINE=<file>; tools/fu_timeline.py): clock64 at the phase boundaries
+#define FU_MARK(k) do { if (tl && tid == 0) tl[(size_t)blockIdx.x * 16 + (k)] = (unsigned long long)clock64(); } while (0)
+    FU_MARK(0);
     const int nsig = (int)P.n_signals;                    // 2 or 4
     const FrameDesc fd = frames[blockIdx.x];
     const int N = (int)fd.blocksize;
@@ -524,6 +605,7 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
     int32_t* tile = reinterpret_cast<int32_t*>(smem_raw);
     unsigned char* ovl = smem_raw + L.ovl_off;
     double* ring_all = reinterpret_cast<double*>(ovl + L.ring_off);
+    float* wring_all = reinterpret_cast<float*>(ovl + L.wring_off);
     double* acstore = reinterpret_cast<double*>(ovl + L.acstore_off);
     WarpScratch* wsall = reinterpret_cast<WarpScratch*>(ovl + L.ws_off);
     unsigned long long* psum_all = reinterpret_cast<unsigned long long*>(ovl + L.psum_off);
@@ -540,7 +622,13 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
     // =================== stage: the frame crosses HBM once ===================
     const int16_t* base = pcm + fd.pcm_off;
     const bool use_tma = ((reinterpret_cast<uintptr_t>(base) & 15u) == 0u);
-    if (tid == 0) { mbar_init(&S.mbar, 1); S.queue_a = 0; S.queue_b = 0; S.nneed = 0; S.ca = 0; }
+    if (tid == 0) {
+        mbar_init(&S.mbar, 1); S.queue_a = 0; S.queue_b = 0; S.nneed = 0; S.ca = 0;
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        S.ac_warp = (int)(atomicAdd(&g_fu_ticket[smid & 255u], 1u) & (unsigned)(kFuWarps - 1));
+        if (tl) tl[(size_t)blockIdx.x * 16 + 11] = smid;
+    }
     if (tid < kFuSig) { S.sig_or[tid] = 0u; S.sig_and[tid] = 0xffffffffu; S.best_bits[tid] = 0u; }
     for (int i = tid; i < kFuSig * kMaxSteps; i += kFuThreads) (&S.step_bits[0][0])[i] = 0xffffffffu;
     reinterpret_cast<uint2*>(&crc_tabs[0][0])[tid] = reinterpret_cast<const uint2*>(&g_crc16_slice.t[0][0])[tid];   // 256 threads x 8 bytes = the four tables
@@ -558,8 +646,8 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
             if (bytes) tma_load_1d(dst, src, bytes, &S.mbar);
             // the last words of a row whose length is not a multiple of four; zero up to the next quad
             for (int w = (int)(bytes >> 2); w < ((n_r + 3) & ~3); w++) dst[w] = (w < n_r) ? __ldg(src + w) : 0;
+            mbar_wait(&S.mbar, 0);          // the other warps wait at the CTA barrier below without spending issue slots
         }
-        mbar_wait(&S.mbar, 0);
     } else {
         const bool al4 = ((reinterpret_cast<uintptr_t>(base) & 3u) == 0u);
         const int Nq = (N + 3) & ~3;
@@ -573,6 +661,7 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
         }
     }
     __syncthreads();
+    FU_MARK(1);
 
     // =================== OR / AND of every signal (up: get_wasted_bits_) ===================
     {
@@ -601,6 +690,7 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
         }
     }
     __syncthreads();
+    FU_MARK(2);
 
     const int bps = (int)P.bps, ch = 2;
     auto sig_wasted = [&](int s) { return wasted_from_or(S.sig_or[s], bps); };
@@ -623,24 +713,41 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
     }
     __syncthreads();
     const int nneed = S.nneed;
+    FU_MARK(3);
 
     // =================== queue A: autocorrelation items first (long, latency bound), then the fixed analyses ===================
     const int n_ac = (max_lpc > 0 && nneed > 0) ? nwin : 0;
+    {
+        // autocorrelation item t (window t = depth b, position k) belongs to warp (ac_warp + t) mod 8: at most six windows.
+        // Up to three windows (levels 3-7) get a second warp each, (ac_warp + t + 4) mod 8, that converts for the chain warp.
+        const int wrel = (warp - S.ac_warp) & (kFuWarps - 1);
+        const bool paired = n_ac * 2 + 2 <= kFuWarps;
+        const int t = paired ? (wrel & 3) : wrel;
+        const bool mine = paired ? (wrel < 4 ? wrel < n_ac : (wrel - 4) < n_ac) : wrel < n_ac;
+        if (mine) {
+            int b = 1, k = t;
+            while (k >= b) { k -= b; b++; }
+            if (!(b > 1 && N / b <= 32)) {                                   // libFLAC skips windows this short
+                const bool mark = tl && lane == 0 && wrel == 0;
+                if (mark) { tl[(size_t)blockIdx.x * 16 + 12] = (unsigned long long)clock64(); tl[(size_t)blockIdx.x * 16 + 14] = (unsigned long long)warp; }
+                double* rg = ring_all + (size_t)t * kFuSig * kFuRing;
+                float* wr = wring_all + (size_t)t * kWinSlots * 32;
+                const float* wt = windows + fd.window_off;
+                const int lags = (int)P.max_lpc_order + 1;
+                if (!paired) fu_autoc_item<0>(tile, G, wt, b, k, nsig, lags, S.sig_or, bps, rg, wr, acstore, nwin, lane, 0);
+                else if (wrel < 4) fu_autoc_item<1>(tile, G, wt, b, k, nsig, lags, S.sig_or, bps, rg, wr, acstore, nwin, lane, 2 + t);
+                else fu_autoc_item<2>(tile, G, wt, b, k, nsig, lags, S.sig_or, bps, rg, wr, acstore, nwin, lane, 2 + t);
+                if (mark) tl[(size_t)blockIdx.x * 16 + 13] = (unsigned long long)clock64();
+            }
+        }
+    }
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(&S.queue_a, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_ac + nsig) break;
-        if (t < n_ac) {
-            int b = 1, k = t;
-            while (k >= b) { k -= b; b++; }                                  // window t = (depth b, position k)
-            if (b > 1 && N / b <= 32) continue;                              // libFLAC skips windows this short
-            fu_autoc_item(tile, G, windows + fd.window_off, b, k, nsig, (int)P.max_lpc_order + 1, S.sig_or, bps,
-                          ring_all + (size_t)t * kFuSig * kFuRing, acstore, nwin, lane);
-            continue;
-        }
+        if (t >= nsig) break;
         // ---- fixed analysis of signal s: verbatim baseline, constant, or the guessed fixed order (rows E3, E10, E11) ----
-        const int s = t - n_ac;
+        const int s = t;
         SubframePlan& pl = base_plan[s];
         reinterpret_cast<uint32_t*>(&pl)[lane] = 0u;
         __syncwarp();
@@ -673,19 +780,21 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
                 while (omax > 0 && (N >> omax) <= fo) omax--;
                 const int nparts = 1 << omax, psize = N >> omax, ratio = nparts0 >> omax;
                 const bool narrow = (uint32_t)sbps + 4u < 32u - ilog2_u32((uint32_t)psize);
-                // partition sums of the chosen order: the pass above covers samples 4..N-1, partition 0 also owns fo..3
+                // partition sums of the chosen order: the pass above covers samples 4..N-1; samples fo..3 are added here, each to
+                // the partition it lies in (all in partition 0 unless the partitions are shorter than four samples)
+                if (lane == 0) {
+                    for (int i = fo; i < 4; i++) {
+                        const int x0 = sv(tile[tix(G, i)], sg);
+                        const int xa = i >= 1 ? sv(tile[tix(G, i - 1)], sg) : 0, xb = i >= 2 ? sv(tile[tix(G, i - 2)], sg) : 0, xc = i >= 3 ? sv(tile[tix(G, i - 3)], sg) : 0;
+                        int d;
+                        if (fo == 0) d = x0; else if (fo == 1) d = x0 - xa; else if (fo == 2) d = x0 - 2 * xa + xb; else d = x0 - 3 * xa + 3 * xb - xc;
+                        fixsum[fo * kMaxParts + i / psize0] += (unsigned long long)(uint32_t)abs(d);
+                    }
+                }
+                __syncwarp();
                 for (int p = lane; p < nparts; p += 32) {
                     unsigned long long v = 0;
                     for (int j = 0; j < ratio; j++) v += fixsum[fo * kMaxParts + p * ratio + j];
-                    if (p == 0) {
-                        for (int i = fo; i < 4; i++) {
-                            const int x0 = sv(tile[tix(G, i)], sg);
-                            const int xa = i >= 1 ? sv(tile[tix(G, i - 1)], sg) : 0, xb = i >= 2 ? sv(tile[tix(G, i - 2)], sg) : 0, xc = i >= 3 ? sv(tile[tix(G, i - 3)], sg) : 0;
-                            int d;
-                            if (fo == 0) d = x0; else if (fo == 1) d = x0 - xa; else if (fo == 2) d = x0 - 2 * xa + xb; else d = x0 - 3 * xa + 3 * xb - xc;
-                            v += (unsigned long long)(uint32_t)abs(d);
-                        }
-                    }
                     psum[p] = v;
                 }
                 __syncwarp();
@@ -706,6 +815,7 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
         __syncwarp();
     }
     __syncthreads();
+    FU_MARK(4);
 
     // =================== queue B: one LPC candidate per (signal, apodization step) ===================
     // up: apply_apodization_ + evaluate_lpc_subframe_.  Step list of set_next_subdivide_tukey:
@@ -819,6 +929,7 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
         }
     }
     __syncthreads();
+    FU_MARK(5);
 
     // =================== selection: candidates in libFLAC's order, replace only on strict <; channel assignment ===================
     if (warp == 0) {
@@ -851,8 +962,10 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
     __syncthreads();
 
     // =================== pack (row E12): the analysis scratch becomes the frame image ===================
+    FU_MARK(6);
     for (uint32_t i = tid; i < L.obuf_words; i += kFuThreads) obuf[i] = 0u;
     __syncthreads();
+    FU_MARK(7);
     if (tid < (int)S.hdr_len) put_bits(obuf, (uint32_t)tid * 8u, S.hdr[tid], 8);
     uint32_t pos = S.hdr_len * 8u;
     for (int c = 0; c < ch; c++) {
@@ -909,6 +1022,7 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
     __syncthreads();
 
     // =================== CRC-16 over the byte-padded frame, append, store ===================
+    FU_MARK(8);
     const uint32_t nb = (pos + 7u) >> 3;
     {
         const uint16_t c2 = cta_crc16_words<kFuThreads>([&](uint32_t j) {
@@ -918,12 +1032,15 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
         if (tid == 0) put_bits(obuf, nb * 8u, c2, 16);
     }
     __syncthreads();
+    FU_MARK(9);
     {
         const uint32_t total = nb + 2u;
         uint32_t* dst = reinterpret_cast<uint32_t*>(scratch + (size_t)blockIdx.x * scratch_stride);
         for (uint32_t wd = tid; wd < (total + 3u) / 4u; wd += kFuThreads) dst[wd] = __byte_perm(obuf[wd], 0u, 0x0123);
         if (tid == 0) frame_len[blockIdx.x] = total;
     }
+    FU_MARK(10);
+#undef FU_MARK
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -944,6 +1061,7 @@ static FuLayout fused_layout(const EncParams& P, uint32_t scratch_stride) {
     L.ovl_off = up(L.tile_words * 4u, 128u);
     uint32_t o = 0;
     L.ring_off = o;      o += up((P.max_lpc_order ? L.n_win : 0u) * kFuSig * kFuRing * 8u, 16u);
+    L.wring_off = o;     o += (P.max_lpc_order ? L.n_win : 0u) * kWinSlots * 32u * 4u;
     L.acstore_off = o;   o += up(kFuSig * L.n_win * kAcStoreStride * 8u, 16u);
     L.ws_off = o;        o += up(kFuWarps * (uint32_t)sizeof(WarpScratch), 16u);
     L.psum_off = o;      o += kFuWarps * 2u * kMaxParts * 8u;
@@ -970,8 +1088,20 @@ void launch_fused(const void* pcm, const FrameDesc* frames, const float* windows
                   EncStats* stats, uint8_t* scratch, uint32_t scratch_stride, uint32_t* frame_len, cudaStream_t stream) {
     const FuLayout L = fused_layout(P, scratch_stride);
     cudaFuncSetAttribute(fused_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes);
+    // debugging aid: FLACB200_FU_TIMELINE=<file> dumps 16 clock64 marks per CTA of every launch (synchronous; tools/fu_timeline.py)
+    unsigned long long* tl = nullptr;
+    const char* tl_path = getenv("FLACB200_FU_TIMELINE");
+    if (tl_path && cudaMalloc(&tl, (size_t)n_frames * 16 * 8) != cudaSuccess) tl = nullptr;
+    if (tl) cudaMemsetAsync(tl, 0, (size_t)n_frames * 16 * 8, stream);
     fused_encode_kernel<<<(unsigned)n_frames, kFuThreads, L.total_bytes, stream>>>((const int16_t*)pcm, frames, windows, P, L, frame_ca, stats,
-                                                                                  scratch, scratch_stride, frame_len);
+                                                                                  scratch, scratch_stride, frame_len, tl);
+    if (tl) {
+        std::vector<unsigned long long> h((size_t)n_frames * 16);
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h.data(), tl, h.size() * 8, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(tl_path, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+        cudaFree(tl);
+    }
 }
 
 }  // namespace fb

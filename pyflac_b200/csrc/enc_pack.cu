@@ -56,7 +56,8 @@ __device__ __noinline__ uint32_t pack_rice_body(const SubframePlan& pl, const in
     for (int j = 0; j < ORDER; j++) q[j] = (j < order) ? qs[j] : 0;
     const uint32_t plen = pl.rice2 ? 5u : 4u;
     const uint32_t psize = (uint32_t)N >> pl.part_order;
-    const uint32_t magic = (uint32_t)((0x100000000ull + psize - 1u) / psize);   // i / psize == umulhi(i, magic) for i, psize < 2^16
+    const uint32_t magic = psize > 1u ? (uint32_t)((0x100000000ull + psize - 1u) / psize) : 0u;   // i / psize == umulhi(i, magic) for i, psize < 2^16; 0 = one-sample partitions
+    auto pdiv = [&](uint32_t i) { return magic ? __umulhi(i, magic) : i; };
     uint32_t done_bits = 0;                                                      // code bits of all previous tiles
     for (int t0 = 0; t0 < N; t0 += kTileSamples) {
         uint32_t u[kTileK];
@@ -80,7 +81,7 @@ __device__ __noinline__ uint32_t pack_rice_body(const SubframePlan& pl, const in
                     r = x[i] - (sacc >> shift);
                 }
                 const uint32_t uu = ((uint32_t)r << 1) ^ (uint32_t)(r >> 31);
-                const uint32_t kk = pl.rice[__umulhi((uint32_t)i, magic)];
+                const uint32_t kk = pl.rice[pdiv((uint32_t)i)];
                 u[k] = uu;
                 mybits += (uu >> kk) + 1u + kk;
             }
@@ -97,7 +98,7 @@ __device__ __noinline__ uint32_t pack_rice_body(const SubframePlan& pl, const in
             const bool valid = (i >= order && i < N);
             uint32_t kk = 0, part = 0, len = 0;
             if (valid) {
-                part = __umulhi((uint32_t)i, magic);
+                part = pdiv((uint32_t)i);
                 kk = pl.rice[part];
                 len = (u[k] >> kk) + 1u + kk;
             }
