@@ -564,7 +564,7 @@ def main():
         dom = max([k for k in ("fused", "autoc", "analyze", "pack") if k in kt_acc], key=lambda k: kt_acc.get(k, 0.0))
         alg_bytes = pcm_bytes + out_bytes
         achieved = alg_bytes / (kt_acc[dom] * 1e-3) / 1e9
-        dom_kernel = "fused_encode_kernel" if dom == "fused" else dom + "_kernel"
+        dom_kernel = ("fused_" if kt_acc.get("path") == "tma" and dom != "autoc" else "") + dom + "_kernel"
         traffic, traffic_src = ncu_traffic(dom_kernel)
         dec_traffic, dec_traffic_src = ncu_traffic("dec_frame_kernel")
         line = {
@@ -631,7 +631,7 @@ def main():
                 "e2e": {"value": world * c5_samples / (c5_e2e_max * 1e-3) / 1e6, "ms_per_step": c5_e2e_max, "h2d_bytes_per_step": c5_samples * 2,
                         "d2h_bytes_per_step": c5.get("e2e_d2h_bytes")},
                 "n_streams_total": 4096 * world, "frames_per_step": c5["n_frames"] * world, "gpu_launches_per_step": c5["launches_per_step"],
-                "roofline": {"bound": "hbm", "kernel": ("fused_encode_kernel" if c5dom == "fused" else c5dom + "_kernel"),
+                "roofline": {"bound": "hbm", "kernel": ("fused_" if c5k.get("path") == "tma" and c5dom != "autoc" else "") + c5dom + "_kernel",
                              "achieved": c5_alg / (c5k[c5dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": c5_alg / (c5k[c5dom] * 1e-3) / 1e9 / peak,
                              "algorithmic_bytes_per_launch": c5_alg, "kernel_ms": c5k, "traffic": None},
                 "cpu_baseline": c5_cpu, "log_guard_hits": c5["guard_hits"]}

@@ -178,8 +178,8 @@ int  flacb200_decode_kernel_times(flacb200_ctx *ctx, float *ms);
 /* Per-kernel device times of the last batch, measured with CUDA events on the launching streams:
  * ms[0..9] = analysis (all three kernels), pack, scan, compact, finalize(+MD5 join), md5 (side stream), then the
  * analysis split into its kernels: frame_bits (OR/AND), autoc (autocorrelation), analyze (decisions); ms[9] = 1 when
- * the batch ran the fused kernel (16-bit stereo: one launch from PCM to frame bytes, csrc/enc_fused.cu): ms[0] is
- * that kernel, ms[1] and ms[6..8] are zero. */
+ * the batch ran the fused path (16-bit stereo, csrc/enc_fused.cu): ms[7] is its autocorrelation kernel, ms[8] its
+ * persistent worker kernel (TMA-staged frame tile -> frame bytes), ms[1] and ms[6] are zero. */
 int  flacb200_set_profiling(flacb200_ctx *ctx, int on);
 int  flacb200_kernel_times(flacb200_ctx *ctx, float *ms);
 /* Wall-clock breakdown (ms since entry) of the last flacb200_encode_batch_host call:

@@ -153,8 +153,9 @@ class Engine:
         ms = np.zeros(10, np.float32)
         self._check(self._L.flacb200_kernel_times(self._h, ms.ctypes.data))
         d = dict(zip(["analysis", "pack", "scan", "compact", "finalize", "md5", "frame_bits", "autoc", "analyze"], [float(v) for v in ms[:9]]))
-        if ms[9] > 0:       # the fused kernel ran: one launch from PCM to frame bytes
-            d = {"fused": d["analysis"], "scan": d["scan"], "compact": d["compact"], "finalize": d["finalize"], "md5": d["md5"]}
+        if ms[9] > 0:       # the TMA-staged kernels of csrc/enc_fused.cu ran (16-bit stereo): there is no OR/AND pass
+            d.pop("frame_bits")
+            d["path"] = "tma"
         return d
 
     @property

@@ -401,7 +401,7 @@ __device__ __forceinline__ void ac_finish(float (&dv)[kAcJobsMax], const AcRaw& 
 template <typename PcmT, bool PACKED>
 __global__ void __launch_bounds__(kAcThreads, FB_AC_MIN_CTAS)
 autoc_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, int n_frames, const float* __restrict__ windows,
-             EncParams P, unsigned char* __restrict__ work, size_t work_stride, int lanes_per_job, int jobs_per_warp) {
+             EncParams P, unsigned char* __restrict__ work, size_t work_stride, int lanes_per_job, int jobs_per_warp, int unshifted) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nsig = (int)P.n_signals, ch = (int)P.channels;
@@ -429,7 +429,8 @@ autoc_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames,
             const int N = (int)fd.blocksize;
             if (N > 4 && !(b > 1 && N / b <= 32)) {
                 const FrameBits* fb = frame_bits(work, work_stride, f);
-                const int wst = wasted_from_or(fb->or_[s], (int)P.bps, P.bps == 32 && P.do_mid_side && s == ch + 1);
+                // un-shifted mode (enc_fused.cu): the wasted bits are not known yet; the consumer rescales by the exact factor 4^-wasted
+                const int wst = unshifted ? 0 : wasted_from_or(fb->or_[s], (int)P.bps, P.bps == 32 && P.do_mid_side && s == ch + 1);
                 const int off = (k * N) / b;
                 J.base = pcm + fd.pcm_off + (size_t)off * ch;
                 int c0, c1, ca, cb, sh = wst;
@@ -922,7 +923,7 @@ static void launch_all(const PcmT* pcm, const FrameDesc* frames, const float* wi
         for (uint32_t b = 1; b <= P.apod_parts; b++) warps += ((long long)n_frames * P.n_signals * b + jpw - 1) / jpw;
         const size_t ac_smem = (size_t)(kAcThreads / 32) * kAcJobsMax * (kAcRing * 8 + sizeof(AcJob));
         const unsigned blocks = (unsigned)((warps + kAcThreads / 32 - 1) / (kAcThreads / 32));
-        autoc_kernel<PcmT, PACKED><<<blocks, kAcThreads, ac_smem, stream>>>(pcm, frames, n_frames, windows, P, work, stride, lpj, jpw);
+        autoc_kernel<PcmT, PACKED><<<blocks, kAcThreads, ac_smem, stream>>>(pcm, frames, n_frames, windows, P, work, stride, lpj, jpw, 0);
     }
     if (ev) cudaEventRecord(ev[1], stream);
     cudaFuncSetAttribute(analyze_kernel<PcmT, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
@@ -930,6 +931,22 @@ static void launch_all(const PcmT* pcm, const FrameDesc* frames, const float* wi
     for (int pass = 0; pass < (P.loose_frames ? 2 : 1); pass++)
         analyze_kernel<PcmT, PACKED><<<(unsigned)n_frames, kAnThreads, smem_bytes, stream>>>(pcm, frames, windows, P, plans, frame_ca, dbg, stats,
                                                                                             pass, work, stride);
+}
+
+// The autocorrelation kernel alone, on the un-shifted signals of 16-bit stereo frames (first kernel of the enc_fused.cu path:
+// it needs no OR/AND pass in front of it).  Same work records as launch_analyze.
+void launch_autoc_unshifted(const void* pcm, const FrameDesc* frames, const float* windows, const EncParams& P, int n_frames, void* work, cudaStream_t stream) {
+    if (P.max_lpc_order == 0 || n_frames == 0) return;
+    const size_t stride = analyze_work_stride(P);
+    const int lags = (int)P.max_lpc_order + 1, lpj = (lags + 3) / 4;
+    int jpw = (32 / lpj) < kAcJobsMax ? (32 / lpj) : kAcJobsMax;
+    if (jpw > 2 * (int)P.n_signals) jpw = 2 * (int)P.n_signals;
+    jpw = jpw / (int)P.n_signals * (int)P.n_signals;
+    long long warps = 0;
+    for (uint32_t b = 1; b <= P.apod_parts; b++) warps += ((long long)n_frames * P.n_signals * b + jpw - 1) / jpw;
+    const size_t ac_smem = (size_t)(kAcThreads / 32) * kAcJobsMax * (kAcRing * 8 + sizeof(AcJob));
+    const unsigned blocks = (unsigned)((warps + kAcThreads / 32 - 1) / (kAcThreads / 32));
+    autoc_kernel<int16_t, true><<<blocks, kAcThreads, ac_smem, stream>>>((const int16_t*)pcm, frames, n_frames, windows, P, (unsigned char*)work, stride, lpj, jpw, 1);
 }
 
 // host-visible launcher (called from engine.cu); `work` = n_frames * analyze_work_stride(P) bytes of device scratch.

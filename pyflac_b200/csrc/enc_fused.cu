@@ -41,12 +41,10 @@ namespace fb {
 
 constexpr int kFuThreads = 256;
 constexpr int kFuWarps = kFuThreads / 32;
+constexpr int kFuAnThreads = 128;          // analysis kernel: four warps, one work item each
+constexpr int kFuAnWarps = kFuAnThreads / 32;
 constexpr int kFuSig = 4;                  // L, R, mid, side
-constexpr int kWinSlots = 16;              // 32-float slots of the window-value ring (cp.async destination)
-constexpr int kWinAhead = 8;               // chunks a window value is requested ahead of its use
-constexpr int kFuSlots = 4;                // 32-sample slots in the autocorrelation ring (power of two)
-constexpr int kFuRing = 16 + 32 * kFuSlots + 2;   // doubles per autocorrelation job: 16 mirror + the slots (+2: jobs land in different banks)
-constexpr int kFuRun = 16;                 // consecutive samples a lane codes in the pack phase
+constexpr int kFuRun = 20;                 // consecutive samples a lane codes in the pack phase (five 16-byte quads: lanes 80 bytes apart, conflict free)
 constexpr int kFuChunk = 32 * kFuRun;      // samples a warp codes per round
 
 // Shared-memory plan, computed on the host (fused_layout) and passed by value.  The `ovl` region is used twice:
@@ -54,7 +52,8 @@ constexpr int kFuChunk = 32 * kFuRun;      // samples a warp codes per round
 struct FuLayout {
     uint32_t tile_words;
     uint32_t ovl_off, ovl_bytes;
-    uint32_t ring_off, wring_off, acstore_off, ws_off, psum_off, fixsum_off, baseplan_off, stepplan_off;   // inside ovl
+    uint32_t acstore_off, ws_off, psum_off, fixsum_off, baseplan_off, stepplan_off;   // inside ovl
+    uint32_t pk_obuf_off, pk_shared_off, pk_crctab_off, pk_total_bytes;   // pack kernel: tile | image | FuShared | CRC tables
     uint32_t shared_off, crctab_off, total_bytes;
     uint32_t obuf_words, n_win, n_steps, pad;
 };
@@ -66,7 +65,7 @@ struct FuShared {
     uint32_t step_bits[kFuSig][kMaxSteps];
     int      need_list[kFuSig];
     int      nneed, queue_a, queue_b, ca;
-    int      ac_warp, pad2;                // the warp that runs the first autocorrelation item (rotates per SM, see g_fu_ticket)
+    int      frame, pad2;                  // the frame this CTA encodes (its ticket)
     SubframePlan plan[2];                  // the two coded subframes
     int32_t  sigidx[2];
     uint32_t segtot[kFuWarps];
@@ -113,157 +112,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------ autocorrelation
-// up: lpc.c FLAC__lpc_window_data[_partial] + FLAC__lpc_compute_autocorrelation.
-// One item = one window (depth b, position k) of the frame, nsig jobs (signals) that share the sample word and the
-// window value.  Lane = (job, lag pair): chains of lags 2q and 2q+1, each strictly sequential in i (fma of two exact
-// float products == libFLAC's mul + add).  Per job a ring of four 32-sample slots of doubles with a 16-entry mirror of
-// the last slot's tail in front of slot 0, so "i - lag" is a plain negative offset.  Window values arrive through a
-// cp.async ring eight chunks ahead; chunk c+1 is converted before the chains of chunk c run.
-// ROLE 0: one warp converts and runs the chains (levels with many windows).  ROLE 1 / 2: a pair of warps -- the chain warp
-// (1) only runs the DFMA chains, its partner (2) windows and converts one chunk ahead into the ring; they meet once per
-// 32-sample chunk at a named barrier (bar_id, 64 threads).  A warp issues in order, so a lone warp pays the conversion's
-// dependent steps (shared load -> int -> float -> multiply -> double -> store, ~150 cycles) in front of every chunk's
-// 260 cycles of chain latency; the pair hides them (measured: 1050 -> ~300 cycles per chunk).
-template <int ROLE>
-__device__ __noinline__ void fu_autoc_item(const int32_t* __restrict__ tile, const FuGeo G, const float* __restrict__ win_tab,
-                                           int b, int k, int nsig, int lags, const uint32_t* __restrict__ sig_or, int bps,
-                                           double* __restrict__ ring, float* __restrict__ wring, double* __restrict__ acstore, int n_win,
-                                           int lane, int bar_id) {
-    const int N = G.N;
-    const int len = N / b, part = (b == 1) ? N : N / b / 2, off = (k * N) / b;
-    const int wtail = N - 2 * part;                   // window index = i (i < part) or wtail + i (part <= i < 2*part)
-    const int LJ = (lags + 1) >> 1;                   // lanes per job
-    const int nchunks = (len + 31) >> 5;
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory"); };
-
-    if (ROLE != 1) {
-        int shp[kFuSig];
-#pragma unroll
-        for (int s = 0; s < kFuSig; s++) shp[s] = (s < nsig) ? wasted_from_or(sig_or[s], bps) + (s == 2 ? 1 : 0) : 0;
-        for (int idx = lane; idx < nsig * 16; idx += 32) ring[(idx >> 4) * kFuRing + (idx & 15)] = 0.0;
-        // The window table lives in global memory (16 KiB per blocksize, shared by every frame; the SM's L1 is mostly carved
-        // into shared memory here, so a read is an L2 round trip of several hundred cycles).  Its values travel straight into
-        // a small shared ring with cp.async -- no destination register, so nothing waits on them -- kWinAhead chunks ahead
-        // of their use; samples outside the window read as zero (src-size 0 zero-fills).
-        const uint32_t wr_base = smem_u32(wring) + (uint32_t)lane * 4u;
-        auto request = [&](int c) {
-            const int i = c * 32 + lane;
-            const bool in = (i < len && i < 2 * part);
-            const float* src = win_tab + (in ? (i < part ? i : wtail + i) : 0);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(wr_base + (uint32_t)(c & (kWinSlots - 1)) * 128u), "l"(src), "r"(in ? 4u : 0u) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        auto convert = [&](int c) {
-            const int slot = c & (kFuSlots - 1);
-            const int i = c * 32 + lane;
-            float rwv;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rwv) : "r"(wr_base + (uint32_t)(c & (kWinSlots - 1)) * 128u) : "memory");
-            const int rw = (i < len && i < 2 * part) ? tile[tix(G, off + i)] : 0;
-            const int lo = (int)(short)rw, hi = rw >> 16;
-            float dv[kFuSig];
-            dv[0] = FB_FMUL(__int2float_rn(lo >> shp[0]), rwv);
-            dv[1] = FB_FMUL(__int2float_rn(hi >> shp[1]), rwv);
-            dv[2] = FB_FMUL(__int2float_rn((lo + hi) >> shp[2]), rwv);
-            dv[3] = FB_FMUL(__int2float_rn((lo - hi) >> shp[3]), rwv);
-#pragma unroll
-            for (int s = 0; s < kFuSig; s++) {
-                if (s < nsig) {
-                    const double d = (double)dv[s];
-                    ring[s * kFuRing + 16 + slot * 32 + lane] = d;
-                    if (slot == kFuSlots - 1 && lane >= 16) ring[s * kFuRing + lane - 16] = d;      // the last slot's tail mirrored in front of slot 0
-                }
-            }
-        };
-#pragma unroll 1
-        for (int c = 0; c < kWinAhead; c++) request(c);
-        asm volatile("cp.async.wait_group %0;" :: "n"(kWinAhead - 1) : "memory");       // chunk 0 has landed
-        convert(0);
-        if (ROLE == 2) {
-            // converter of a pair: chunk c+1 is ready before the chain warp passes barrier c.  While the chains of chunk c
-            // read slot c (and the tail of slot c-1, the mirror only when slot == 0) this warp fills slot c+2.
-            request(kWinAhead);
-            asm volatile("cp.async.wait_group %0;" :: "n"(kWinAhead - 1) : "memory");
-            convert(1);
-#pragma unroll 1
-            for (int c = 0; c < nchunks; c++) {
-                pair_sync();
-                request(c + 1 + kWinAhead);
-                asm volatile("cp.async.wait_group %0;" :: "n"(kWinAhead - 1) : "memory");
-                convert(c + 2);
-            }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            return;
-        }
-        __syncwarp();
-        // ROLE 0 continues below with the chains, converting chunk c+1 in front of the chains of chunk c
-        const int jb = lane / LJ, qd = lane - jb * LJ;
-        const bool active = jb < nsig;
-        const int lag0 = 2 * qd;
-        const double* jobring = ring + (active ? jb : 0) * kFuRing;
-        double a0 = 0.0, a1 = 0.0, p1 = 0.0;
-#pragma unroll 1
-        for (int c = 0; c < nchunks; c++) {
-            const int slot = c & (kFuSlots - 1);
-            request(c + kWinAhead);
-            asm volatile("cp.async.wait_group %0;" :: "n"(kWinAhead - 1) : "memory");   // chunk c+1's window values have landed
-            convert(c + 1);
-            if (active) {
-                const double* curp = jobring + 16 + slot * 32;
-                const double* lagp = curp - lag0;
-#pragma unroll
-                for (int s = 0; s < 32; s += 2) {
-                    const double2 c2 = *reinterpret_cast<const double2*>(curp + s);
-                    const double2 l2 = *reinterpret_cast<const double2*>(lagp + s);
-                    a0 = fma(c2.x, l2.x, a0); a1 = fma(c2.x, p1, a1);
-                    a0 = fma(c2.y, l2.y, a0); a1 = fma(c2.y, l2.x, a1);
-                    p1 = l2.y;
-                }
-            }
-            __syncwarp();
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (active) {
-            double* dst = acstore + ((size_t)jb * n_win + (b - 1) * b / 2 + k) * kAcStoreStride + lag0;
-            dst[0] = a0;
-            if (lag0 + 1 < kAcStoreStride) dst[1] = a1;
-        }
-        __syncwarp();
-        return;
-    }
-    // ---- ROLE 1: the chain warp of a pair ----
-    {
-        const int jb = lane / LJ, qd = lane - jb * LJ;
-        const bool active = jb < nsig;
-        const int lag0 = 2 * qd;
-        const double* jobring = ring + (active ? jb : 0) * kFuRing;
-        double a0 = 0.0, a1 = 0.0, p1 = 0.0;
-#pragma unroll 1
-        for (int c = 0; c < nchunks; c++) {
-            const int slot = c & (kFuSlots - 1);
-            pair_sync();                                                   // chunk c (and c+1) converted
-            if (active) {
-                const double* curp = jobring + 16 + slot * 32;
-                const double* lagp = curp - lag0;
-#pragma unroll
-                for (int s = 0; s < 32; s += 2) {
-                    const double2 c2 = *reinterpret_cast<const double2*>(curp + s);
-                    const double2 l2 = *reinterpret_cast<const double2*>(lagp + s);
-                    a0 = fma(c2.x, l2.x, a0); a1 = fma(c2.x, p1, a1);
-                    a0 = fma(c2.y, l2.y, a0); a1 = fma(c2.y, l2.x, a1);
-                    p1 = l2.y;
-                }
-            }
-        }
-        if (active) {
-            double* dst = acstore + ((size_t)jb * n_win + (b - 1) * b / 2 + k) * kAcStoreStride + lag0;
-            dst[0] = a0;
-            if (lag0 + 1 < kAcStoreStride) dst[1] = a1;
-        }
-        __syncwarp();
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ fixed predictors
 // up: fixed.c FLAC__fixed_compute_best_predictor[_wide] and, in the same pass, what
 // precompute_partition_info_sums_ would compute from the order-k fixed residual: |k-th difference| IS that residual.
@@ -272,7 +120,7 @@ __device__ __noinline__ void fu_autoc_item(const int32_t* __restrict__ tile, con
 // to partition 0).  Returns the five totals in e[] (every lane).
 template <bool VEC>
 __device__ __noinline__ void fu_fixed_sums(const int32_t* __restrict__ tile, const FuGeo G, const Sig sg, int psize,
-                                           unsigned long long* __restrict__ fixsum, int lane, unsigned long long* e) {
+                                           unsigned long long* __restrict__ fixsum, int fstride, int lane, unsigned long long* e) {
     const int blk_lo = lane * G.B0w, blk_hi = min(G.N, blk_lo + G.B0w);
     unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
     int lo = max(blk_lo, 4);
@@ -298,11 +146,11 @@ __device__ __noinline__ void fu_fixed_sums(const int32_t* __restrict__ tile, con
                 for (int i = lo; i < hi; i++) FU_FIXED_STEP(rowp[i])
             }
 #undef FU_FIXED_STEP
-            atomicAdd(&fixsum[0 * kMaxParts + part], (unsigned long long)s0);
-            atomicAdd(&fixsum[1 * kMaxParts + part], (unsigned long long)s1);
-            atomicAdd(&fixsum[2 * kMaxParts + part], (unsigned long long)s2);
-            atomicAdd(&fixsum[3 * kMaxParts + part], (unsigned long long)s3);
-            atomicAdd(&fixsum[4 * kMaxParts + part], (unsigned long long)s4);
+            atomicAdd(&fixsum[0 * fstride + part], (unsigned long long)s0);
+            atomicAdd(&fixsum[1 * fstride + part], (unsigned long long)s1);
+            atomicAdd(&fixsum[2 * fstride + part], (unsigned long long)s2);
+            atomicAdd(&fixsum[3 * fstride + part], (unsigned long long)s3);
+            atomicAdd(&fixsum[4 * fstride + part], (unsigned long long)s4);
             e0 += s0; e1 += s1; e2 += s2; e3 += s3; e4 += s4;
             lo = hi;
         }
@@ -458,17 +306,17 @@ __device__ __forceinline__ void put_code(uint32_t* buf, uint32_t pos, uint32_t v
 }
 
 // Rice-coded body of one subframe (up: add_residual_partitioned_rice_ + FLAC__bitwriter_write_rice_signed_block).
-// Round r: warp w codes samples [(r * 8 + w) * 512, +512), lane l the 16 consecutive samples at + 16 l, four at a time
+// Round r: warp w codes samples [(r * 8 + w) * 640, +640), lane l the 20 consecutive samples at + 20 l, four at a time
 // (one 16-byte shared load; the predictor history slides through registers).  Pass 1 counts the lane's bits (codes + the
 // parameter field of every partition that starts inside its run); an exclusive warp scan and the eight warp totals (one
 // CTA barrier per round) give the lane's absolute bit position; pass 2 computes the residuals again and ORs the codes
-// into the zeroed image: neighbouring lanes are ~160 bits apart, so the shared atomics rarely meet in one word.  The
+// into the zeroed image: neighbouring lanes are ~200 bits apart, so the shared atomics rarely meet in one word.  The
 // residuals are computed twice instead of parked in registers: the loops stay rolled and small (this phase was
 // instruction-fetch bound when it was unrolled over the run).  Returns the body length in bits.
 // C = order class, WIDE = 64-bit accumulate (chosen exactly as the analysis does).
 template <int C, bool WIDE, bool EMIT>
 __device__ __forceinline__ uint32_t fu_pack_run(const SubframePlan& pl, const int32_t (&q)[C], int order, int shift, const int32_t* __restrict__ tile,
-                                                const FuGeo& G, const Sig& sg, int i0, uint32_t plen, uint32_t psize, uint32_t pmagic, bool runpart,
+                                                const FuGeo& G, const Sig& sg, int i0, uint32_t plen, uint32_t psize, uint32_t pmagic, bool quadpart,
                                                 uint32_t pos, uint32_t* __restrict__ obuf) {
     const int N = G.N;
     int32_t xw[C];                                     // the C samples before the current quad
@@ -479,14 +327,19 @@ __device__ __forceinline__ uint32_t fu_pack_run(const SubframePlan& pl, const in
         if (idx >= 0) w = *reinterpret_cast<const int4*>(tile + tix(G, idx));
         xw[4 * v + 0] = sv(w.x, sg); xw[4 * v + 1] = sv(w.y, sg); xw[4 * v + 2] = sv(w.z, sg); xw[4 * v + 3] = sv(w.w, sg);
     }
-    const uint32_t part0 = pdiv((uint32_t)i0, pmagic);
-    uint32_t kk = pl.rice[part0];
+    uint32_t kk = 0;
     uint32_t bits = 0;
 #pragma unroll 1
     for (int ib = i0; ib < i0 + kFuRun && ib < N; ib += 4) {
         const int4 w = *reinterpret_cast<const int4*>(tile + tix(G, ib));
         int32_t xq[4];
         xq[0] = sv(w.x, sg); xq[1] = sv(w.y, sg); xq[2] = sv(w.z, sg); xq[3] = sv(w.w, sg);
+        bool qhead = false;                            // quadpart: a partition can only start at the first sample of a quad
+        if (quadpart) {
+            const uint32_t part = pdiv((uint32_t)ib, pmagic);
+            kk = pl.rice[part];
+            qhead = ((uint32_t)ib == part * psize) && ib > order;
+        }
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             const int i = ib + t;
@@ -504,7 +357,7 @@ __device__ __forceinline__ uint32_t fu_pack_run(const SubframePlan& pl, const in
             }
             const uint32_t uu = ((uint32_t)r << 1) ^ (uint32_t)(r >> 31);
             bool head;
-            if (runpart) head = (i == i0 && (uint32_t)i0 == part0 * psize && i0 >= order) || (i == order);
+            if (quadpart) head = (t == 0 && qhead) || (i == order);
             else {
                 const uint32_t part = pdiv((uint32_t)i, pmagic);
                 kk = pl.rice[part];
@@ -540,12 +393,12 @@ __device__ __noinline__ uint32_t fu_pack_body(const SubframePlan& pl, const int3
     const uint32_t plen = pl.rice2 ? 5u : 4u;
     const uint32_t psize = (uint32_t)N >> pl.part_order;
     const uint32_t pmagic = psize > 1u ? (uint32_t)((0x100000000ull + psize - 1u) / psize) : 0u;   // i / psize == umulhi(i, pmagic) for i, psize < 2^16 (psize 1: pdiv)
-    const bool runpart = (psize % (uint32_t)kFuRun) == 0u;                        // a run never straddles a partition boundary
+    const bool quadpart = (psize & 3u) == 0u;                                      // a 4-sample quad never straddles a partition boundary
     uint32_t done_bits = 0;
     for (int r0 = 0; r0 < N; r0 += kFuWarps * kFuChunk) {
         const int i0 = r0 + warp * kFuChunk + lane * kFuRun;
         uint32_t mybits = 0;
-        if (i0 < N) mybits = fu_pack_run<C, WIDE, false>(pl, q, order, shift, tile, G, sg, i0, plen, psize, pmagic, runpart, 0u, obuf);
+        if (i0 < N) mybits = fu_pack_run<C, WIDE, false>(pl, q, order, shift, tile, G, sg, i0, plen, psize, pmagic, quadpart, 0u, obuf);
         // exclusive scan of the lanes' bit counts; warp totals through shared memory
         uint32_t incl = mybits;
 #pragma unroll
@@ -555,7 +408,7 @@ __device__ __noinline__ uint32_t fu_pack_body(const SubframePlan& pl, const int3
         uint32_t pos = body + done_bits + (incl - mybits), round_bits = 0;
 #pragma unroll
         for (int w2 = 0; w2 < kFuWarps; w2++) { const uint32_t t2 = S.segtot[w2]; if (w2 < warp) pos += t2; round_bits += t2; }
-        if (mybits) fu_pack_run<C, WIDE, true>(pl, q, order, shift, tile, G, sg, i0, plen, psize, pmagic, runpart, pos, obuf);
+        if (mybits) fu_pack_run<C, WIDE, true>(pl, q, order, shift, tile, G, sg, i0, plen, psize, pmagic, quadpart, pos, obuf);
         done_bits += round_bits;
         __syncthreads();                              // segtot is reused by the next round / subframe
     }
@@ -570,88 +423,35 @@ __device__ __forceinline__ uint32_t fu_pack_dispatch(int order, const SubframePl
     return fu_pack_body<12, WIDE>(pl, q, order, shift, tile, G, sg, body, obuf, S, warp, lane);
 }
 
-// ------------------------------------------------------------------------------------------------ the kernel
-// The autocorrelation warp of a CTA keeps one SM sub-partition's FP64 pipe busy (a warp-wide DFMA occupies it for two
-// cycles whatever the number of active lanes).  If the four resident CTAs all gave that job to the same warp index, their
-// chains would share ONE sub-partition's pipe (measured: 27 cycles per step instead of the 8.1-cycle DFMA latency).  A
-// ticket per SM rotates the warp index, so co-resident CTAs land on different sub-partitions.
-__device__ unsigned int g_fu_ticket[256];
-
-#ifndef FB_FU_MIN_CTAS
-#define FB_FU_MIN_CTAS 4
-#endif
-__global__ void __launch_bounds__(kFuThreads, FB_FU_MIN_CTAS)
-fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict__ frames, const float* __restrict__ windows,
-                    EncParams P, FuLayout L, uint8_t* __restrict__ frame_ca, EncStats* __restrict__ stats,
-                    uint8_t* __restrict__ scratch, uint32_t scratch_stride, uint32_t* __restrict__ frame_len,
-                    unsigned long long* __restrict__ tl) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // optional per-CTA timeline (FLACB200_FU_TIMELINE=<file>; tools/fu_timeline.py): clock64 at the phase boundaries
-#define FU_MARK(k) do { if (tl && tid == 0) tl[(size_t)blockIdx.x * 16 + (k)] = (unsigned long long)clock64(); } while (0)
-    FU_MARK(0);
-    const int nsig = (int)P.n_signals;                    // 2 or 4
-    const FrameDesc fd = frames[blockIdx.x];
-    const int N = (int)fd.blocksize;
-
-    FuGeo G;
-    G.N = N;
-    G.B0w = (((N + 31) >> 5) + 3) & ~3;
-    if (G.B0w < 4) G.B0w = 4;
-    G.gap = ((G.B0w >> 2) & 1) ? 0 : 4;
-    G.RS = G.B0w + G.gap;
-    G.magic = (uint32_t)((0x100000000ull + (uint32_t)G.B0w - 1ull) / (uint32_t)G.B0w);
-
-    int32_t* tile = reinterpret_cast<int32_t*>(smem_raw);
-    unsigned char* ovl = smem_raw + L.ovl_off;
-    double* ring_all = reinterpret_cast<double*>(ovl + L.ring_off);
-    float* wring_all = reinterpret_cast<float*>(ovl + L.wring_off);
-    double* acstore = reinterpret_cast<double*>(ovl + L.acstore_off);
-    WarpScratch* wsall = reinterpret_cast<WarpScratch*>(ovl + L.ws_off);
-    unsigned long long* psum_all = reinterpret_cast<unsigned long long*>(ovl + L.psum_off);
-    unsigned long long* fixsum_all = reinterpret_cast<unsigned long long*>(ovl + L.fixsum_off);
-    SubframePlan* base_plan = reinterpret_cast<SubframePlan*>(ovl + L.baseplan_off);
-    SubframePlan* step_plan = reinterpret_cast<SubframePlan*>(ovl + L.stepplan_off);
-    uint32_t* obuf = reinterpret_cast<uint32_t*>(ovl);
-    FuShared& S = *reinterpret_cast<FuShared*>(smem_raw + L.shared_off);
-    uint16_t (*crc_tabs)[256] = reinterpret_cast<uint16_t (*)[256]>(smem_raw + L.crctab_off);
-    unsigned long long* psum = psum_all + (size_t)warp * 2 * kMaxParts;
-    WarpScratch& ws = wsall[warp];
-    const int n_steps = (int)L.n_steps, nwin = (int)L.n_win;
-
-    // =================== stage: the frame crosses HBM once ===================
-    const int16_t* base = pcm + fd.pcm_off;
+// ------------------------------------------------------------------------------------------------ staging (both kernels)
+// The frame crosses the SM boundary once per kernel: warp 0 issues one cp.async.bulk (TMA, SASS UBLKCP) per tile row, whole
+// 16-byte units, completion counted in bytes on an mbarrier; frames that do not start on a 16-byte boundary are staged
+// with plain loads.  Ends with a CTA barrier: the tile is complete for every thread.
+template <int NT>
+__device__ __forceinline__ void fu_stage(const int16_t* __restrict__ base, int N, const FuGeo& G, int32_t* __restrict__ tile,
+                                         unsigned long long* mbar, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
     const bool use_tma = ((reinterpret_cast<uintptr_t>(base) & 15u) == 0u);
-    if (tid == 0) {
-        mbar_init(&S.mbar, 1); S.queue_a = 0; S.queue_b = 0; S.nneed = 0; S.ca = 0;
-        unsigned int smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        S.ac_warp = (int)(atomicAdd(&g_fu_ticket[smid & 255u], 1u) & (unsigned)(kFuWarps - 1));
-        if (tl) tl[(size_t)blockIdx.x * 16 + 11] = smid;
-    }
-    if (tid < kFuSig) { S.sig_or[tid] = 0u; S.sig_and[tid] = 0xffffffffu; S.best_bits[tid] = 0u; }
-    for (int i = tid; i < kFuSig * kMaxSteps; i += kFuThreads) (&S.step_bits[0][0])[i] = 0xffffffffu;
-    reinterpret_cast<uint2*>(&crc_tabs[0][0])[tid] = reinterpret_cast<const uint2*>(&g_crc16_slice.t[0][0])[tid];   // 256 threads x 8 bytes = the four tables
+    if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     if (use_tma) {
         if (warp == 0) {
-            // one bulk copy per tile row (row r = samples [r*B0w, (r+1)*B0w)), whole 16-byte units; completion in bytes on the mbarrier
-            const int n_r = max(0, min(G.B0w, N - lane * G.B0w));
+            const int n_r = max(0, min(G.B0w, N - lane * G.B0w));            // row r = samples [r*B0w, (r+1)*B0w)
             const uint32_t bytes = (uint32_t)(n_r * 4) & ~15u;
             const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
-            if (lane == 0) mbar_expect_tx(&S.mbar, total);
+            if (lane == 0) mbar_expect_tx(mbar, total);
             __syncwarp();
             int32_t* dst = tile + lane * G.RS;
             const int32_t* src = reinterpret_cast<const int32_t*>(base) + lane * G.B0w;
-            if (bytes) tma_load_1d(dst, src, bytes, &S.mbar);
+            if (bytes) tma_load_1d(dst, src, bytes, mbar);
             // the last words of a row whose length is not a multiple of four; zero up to the next quad
             for (int w = (int)(bytes >> 2); w < ((n_r + 3) & ~3); w++) dst[w] = (w < n_r) ? __ldg(src + w) : 0;
-            mbar_wait(&S.mbar, 0);          // the other warps wait at the CTA barrier below without spending issue slots
+            mbar_wait(mbar, 0);             // the other warps wait at the barrier below without spending issue slots
         }
     } else {
         const bool al4 = ((reinterpret_cast<uintptr_t>(base) & 3u) == 0u);
         const int Nq = (N + 3) & ~3;
-        for (int i = tid; i < Nq; i += kFuThreads) {
+        for (int i = tid; i < Nq; i += NT) {
             int wd = 0;
             if (i < N) {
                 if (al4) wd = __ldg(reinterpret_cast<const int*>(base) + i);
@@ -661,22 +461,72 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
         }
     }
     __syncthreads();
-    FU_MARK(1);
+}
+
+__device__ __forceinline__ FuGeo fu_geo(int N) {
+    FuGeo G;
+    G.N = N;
+    G.B0w = (((N + 31) >> 5) + 3) & ~3;
+    if (G.B0w < 4) G.B0w = 4;
+    G.gap = ((G.B0w >> 2) & 1) ? 0 : 4;
+    G.RS = G.B0w + G.gap;
+    G.magic = (uint32_t)((0x100000000ull + (uint32_t)G.B0w - 1ull) / (uint32_t)G.B0w);
+    return G;
+}
+
+// ------------------------------------------------------------------------------------------------ analysis kernel
+// One CTA of four warps per frame (rows E2-E11): stage, OR/AND, then one warp per work item -- the fixed analysis of a
+// signal, then one LPC candidate per (signal, apodization step) -- and the choice.  Everything the pack kernel needs
+// leaves as two 128-byte plans + the channel assignment.  Seven CTAs per SM: the kernel is issue / latency bound and
+// lives on the number of warps that have work at the same time, so every warp of a CTA always has an item.
+#ifndef FB_FU_AN_CTAS
+#define FB_FU_AN_CTAS 7
+#endif
+__global__ void __launch_bounds__(kFuAnThreads, FB_FU_AN_CTAS)
+fused_analyze_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict__ frames, EncParams P, FuLayout L,
+                     const double* __restrict__ g_ac, size_t ac_frame_stride, SubframePlan* __restrict__ plans, uint8_t* __restrict__ frame_ca,
+                     EncStats* __restrict__ stats) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x;
+    FuShared& S = *reinterpret_cast<FuShared*>(smem_raw + L.shared_off);
+    const int nsig = (int)P.n_signals;                    // 2 or 4
+    const int n_steps = (int)L.n_steps, nwin = (int)L.n_win;
+    const FrameDesc fd = frames[f];
+    const int N = (int)fd.blocksize;
+    const FuGeo G = fu_geo(N);
+    int32_t* tile = reinterpret_cast<int32_t*>(smem_raw);
+    unsigned char* ovl = smem_raw + L.ovl_off;
+    double* acstore = reinterpret_cast<double*>(ovl + L.acstore_off);
+    WarpScratch* wsall = reinterpret_cast<WarpScratch*>(ovl + L.ws_off);
+    unsigned long long* psum_all = reinterpret_cast<unsigned long long*>(ovl + L.psum_off);
+    unsigned long long* fixsum_all = reinterpret_cast<unsigned long long*>(ovl + L.fixsum_off);
+    SubframePlan* base_plan = reinterpret_cast<SubframePlan*>(ovl + L.baseplan_off);
+    SubframePlan* step_plan = reinterpret_cast<SubframePlan*>(ovl + L.stepplan_off);
+    unsigned long long* psum = psum_all + (size_t)warp * 2 * kMaxParts;
+    WarpScratch& ws = wsall[warp];
+
+    if (tid == 0) { S.queue_a = 0; S.queue_b = 0; S.nneed = 0; S.ca = 0; }
+    if (tid < kFuSig) { S.sig_or[tid] = 0u; S.sig_and[tid] = 0xffffffffu; S.best_bits[tid] = 0u; }
+    for (int i = tid; i < kFuSig * kMaxSteps; i += kFuAnThreads) (&S.step_bits[0][0])[i] = 0xffffffffu;
+    fu_stage<kFuAnThreads>(pcm + fd.pcm_off, N, G, tile, &S.mbar, tid);
 
     // =================== OR / AND of every signal (up: get_wasted_bits_) ===================
     {
         uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0, a0 = ~0u, a1 = ~0u, a2 = ~0u, a3 = ~0u;
-        const int row = tid >> 3, sub = tid & 7;
-        const int row_lo = row * G.B0w;
-        for (int c = 4 * sub; c < G.B0w && row_lo + c < N; c += 32) {
-            const int4 w = *reinterpret_cast<const int4*>(tile + row * G.RS + c);
-            const int xw[4] = {w.x, w.y, w.z, w.w};
+        for (int rs = tid; rs < 256; rs += kFuAnThreads) {               // (row, 8 threads per row)
+            const int row = rs >> 3, sub = rs & 7;
+            const int row_lo = row * G.B0w;
+            for (int c = 4 * sub; c < G.B0w && row_lo + c < N; c += 32) {
+                const int4 w = *reinterpret_cast<const int4*>(tile + row * G.RS + c);
+                const int xw[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                if (row_lo + c + t < N) {
-                    const int lo = (int)(short)xw[t], hi = xw[t] >> 16, m = (lo + hi) >> 1, sd = lo - hi;
-                    o0 |= (uint32_t)lo; o1 |= (uint32_t)hi; o2 |= (uint32_t)m; o3 |= (uint32_t)sd;
-                    a0 &= (uint32_t)lo; a1 &= (uint32_t)hi; a2 &= (uint32_t)m; a3 &= (uint32_t)sd;
+                for (int t = 0; t < 4; t++) {
+                    if (row_lo + c + t < N) {
+                        const int lo = (int)(short)xw[t], hi = xw[t] >> 16, m = (lo + hi) >> 1, sd = lo - hi;
+                        o0 |= (uint32_t)lo; o1 |= (uint32_t)hi; o2 |= (uint32_t)m; o3 |= (uint32_t)sd;
+                        a0 &= (uint32_t)lo; a1 &= (uint32_t)hi; a2 &= (uint32_t)m; a3 &= (uint32_t)sd;
+                    }
                 }
             }
         }
@@ -690,7 +540,6 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
         }
     }
     __syncthreads();
-    FU_MARK(2);
 
     const int bps = (int)P.bps, ch = 2;
     auto sig_wasted = [&](int s) { return wasted_from_or(S.sig_or[s], bps); };
@@ -713,34 +562,9 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
     }
     __syncthreads();
     const int nneed = S.nneed;
-    FU_MARK(3);
 
-    // =================== queue A: autocorrelation items first (long, latency bound), then the fixed analyses ===================
-    const int n_ac = (max_lpc > 0 && nneed > 0) ? nwin : 0;
-    {
-        // autocorrelation item t (window t = depth b, position k) belongs to warp (ac_warp + t) mod 8: at most six windows.
-        // Up to three windows (levels 3-7) get a second warp each, (ac_warp + t + 4) mod 8, that converts for the chain warp.
-        const int wrel = (warp - S.ac_warp) & (kFuWarps - 1);
-        const bool paired = n_ac * 2 + 2 <= kFuWarps;
-        const int t = paired ? (wrel & 3) : wrel;
-        const bool mine = paired ? (wrel < 4 ? wrel < n_ac : (wrel - 4) < n_ac) : wrel < n_ac;
-        if (mine) {
-            int b = 1, k = t;
-            while (k >= b) { k -= b; b++; }
-            if (!(b > 1 && N / b <= 32)) {                                   // libFLAC skips windows this short
-                const bool mark = tl && lane == 0 && wrel == 0;
-                if (mark) { tl[(size_t)blockIdx.x * 16 + 12] = (unsigned long long)clock64(); tl[(size_t)blockIdx.x * 16 + 14] = (unsigned long long)warp; }
-                double* rg = ring_all + (size_t)t * kFuSig * kFuRing;
-                float* wr = wring_all + (size_t)t * kWinSlots * 32;
-                const float* wt = windows + fd.window_off;
-                const int lags = (int)P.max_lpc_order + 1;
-                if (!paired) fu_autoc_item<0>(tile, G, wt, b, k, nsig, lags, S.sig_or, bps, rg, wr, acstore, nwin, lane, 0);
-                else if (wrel < 4) fu_autoc_item<1>(tile, G, wt, b, k, nsig, lags, S.sig_or, bps, rg, wr, acstore, nwin, lane, 2 + t);
-                else fu_autoc_item<2>(tile, G, wt, b, k, nsig, lags, S.sig_or, bps, rg, wr, acstore, nwin, lane, 2 + t);
-                if (mark) tl[(size_t)blockIdx.x * 16 + 13] = (unsigned long long)clock64();
-            }
-        }
-    }
+    // =================== queue A: the fixed analyses (the autocorrelation arrives from the chain warp of an earlier CTA) ===================
+    const bool want_lpc = (max_lpc > 0 && nneed > 0);
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(&S.queue_a, 1);
@@ -760,13 +584,14 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
                 if (bits < best_bits) { best_bits = bits; if (lane == 0) { pl.type = kConstant; pl.bits_est = bits; } }
             } else {
                 const Sig sg = make_sig(s, wasted);
-                unsigned long long* fixsum = fixsum_all + (size_t)s * 5 * kMaxParts;
+                const int fstride = 1 << (int)P.max_part_order;                          // >= the frame's partitions
+                unsigned long long* fixsum = fixsum_all + (size_t)s * 5 * fstride;
                 const int nparts0 = 1 << omax_frame, psize0 = N >> omax_frame;
-                for (int i = lane; i < 5 * kMaxParts; i += 32) fixsum[i] = 0ull;
+                for (int i = lane; i < 5 * fstride; i += 32) fixsum[i] = 0ull;
                 __syncwarp();
                 unsigned long long e[5];
-                if ((psize0 & 3) == 0) fu_fixed_sums<true>(tile, G, sg, psize0, fixsum, lane, e);
-                else fu_fixed_sums<false>(tile, G, sg, psize0, fixsum, lane, e);
+                if ((psize0 & 3) == 0) fu_fixed_sums<true>(tile, G, sg, psize0, fixsum, fstride, lane, e);
+                else fu_fixed_sums<false>(tile, G, sg, psize0, fixsum, fstride, lane, e);
                 __syncwarp();
                 if ((uint32_t)sbps + ilog2_u32((uint32_t)N - 4u) + 1u < 32u) {                 // libFLAC's 32-bit accumulators wrap
 #pragma unroll
@@ -788,13 +613,13 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
                         const int xa = i >= 1 ? sv(tile[tix(G, i - 1)], sg) : 0, xb = i >= 2 ? sv(tile[tix(G, i - 2)], sg) : 0, xc = i >= 3 ? sv(tile[tix(G, i - 3)], sg) : 0;
                         int d;
                         if (fo == 0) d = x0; else if (fo == 1) d = x0 - xa; else if (fo == 2) d = x0 - 2 * xa + xb; else d = x0 - 3 * xa + 3 * xb - xc;
-                        fixsum[fo * kMaxParts + i / psize0] += (unsigned long long)(uint32_t)abs(d);
+                        fixsum[fo * fstride + i / psize0] += (unsigned long long)(uint32_t)abs(d);
                     }
                 }
                 __syncwarp();
                 for (int p = lane; p < nparts; p += 32) {
                     unsigned long long v = 0;
-                    for (int j = 0; j < ratio; j++) v += fixsum[fo * kMaxParts + p * ratio + j];
+                    for (int j = 0; j < ratio; j++) v += fixsum[fo * fstride + p * ratio + j];
                     psum[p] = v;
                 }
                 __syncwarp();
@@ -815,7 +640,17 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
         __syncwarp();
     }
     __syncthreads();
-    FU_MARK(4);
+
+    // =================== the frame's autocorrelations (fused_autoc_kernel, earlier on the stream) ===================
+    if (want_lpc) {
+        // into shared memory, scaled by 4^-wasted: the chain kernel windowed the un-shifted signal (exact power-of-two scaling)
+        for (int i = tid; i < nsig * nwin * kAcStoreStride; i += kFuAnThreads) {
+            const int s = i / (nwin * kAcStoreStride);
+            const int w2 = 2 * sig_wasted(s);
+            acstore[i] = __dmul_rn(__ldcg(reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(g_ac) + (size_t)f * ac_frame_stride) + i), __longlong_as_double((long long)(1023 - w2) << 52));
+        }
+        __syncthreads();
+    }
 
     // =================== queue B: one LPC candidate per (signal, apodization step) ===================
     // up: apply_apodization_ + evaluate_lpc_subframe_.  Step list of set_next_subdivide_tukey:
@@ -929,7 +764,6 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
         }
     }
     __syncthreads();
-    FU_MARK(5);
 
     // =================== selection: candidates in libFLAC's order, replace only on strict <; channel assignment ===================
     if (warp == 0) {
@@ -951,21 +785,53 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
         const int pick0 = __shfl_sync(0xffffffffu, pick, si0), pick1 = __shfl_sync(0xffffffffu, pick, si1);
         const uint32_t* src0 = reinterpret_cast<const uint32_t*>(pick0 < 0 ? &base_plan[si0] : &step_plan[(size_t)si0 * n_steps + pick0]);
         const uint32_t* src1 = reinterpret_cast<const uint32_t*>(pick1 < 0 ? &base_plan[si1] : &step_plan[(size_t)si1 * n_steps + pick1]);
-        reinterpret_cast<uint32_t*>(&S.plan[0])[lane] = src0[lane];       // 128 bytes = 32 words
-        reinterpret_cast<uint32_t*>(&S.plan[1])[lane] = src1[lane];
+        // the two coded subframes' plans (128 bytes each) are all the pack kernel needs besides the PCM
+        uint32_t* dst = reinterpret_cast<uint32_t*>(plans + (size_t)f * 2);
+        dst[lane] = src0[lane];
+        dst[32 + lane] = src1[lane];
+        if (lane == 0) frame_ca[f] = (uint8_t)ca;
+    }
+
+}
+
+// ------------------------------------------------------------------------------------------------ pack kernel
+// One CTA of eight warps per frame (row E12): stage the frame again (TMA), code the two chosen subframes into a zeroed
+// frame image in shared memory, CRC-16, store.
+#ifndef FB_FU_PK_CTAS
+#define FB_FU_PK_CTAS 4
+#endif
+__global__ void __launch_bounds__(kFuThreads, FB_FU_PK_CTAS)
+fused_pack_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict__ frames, EncParams P, FuLayout L,
+                  const SubframePlan* __restrict__ plans, const uint8_t* __restrict__ frame_ca,
+                  uint8_t* __restrict__ scratch, uint32_t scratch_stride, uint32_t* __restrict__ frame_len) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x;
+    const int ch = 2;
+    const FrameDesc fd = frames[f];
+    const int N = (int)fd.blocksize;
+    const FuGeo G = fu_geo(N);
+    int32_t* tile = reinterpret_cast<int32_t*>(smem_raw);
+    uint32_t* obuf = reinterpret_cast<uint32_t*>(smem_raw + L.pk_obuf_off);
+    FuShared& S = *reinterpret_cast<FuShared*>(smem_raw + L.pk_shared_off);
+    uint16_t (*crc_tabs)[256] = reinterpret_cast<uint16_t (*)[256]>(smem_raw + L.pk_crctab_off);
+
+    reinterpret_cast<uint2*>(&crc_tabs[0][0])[tid] = reinterpret_cast<const uint2*>(&g_crc16_slice.t[0][0])[tid];   // 256 threads x 8 bytes = the four tables
+    if (warp == 0) {
+        const int ca = (int)frame_ca[f];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(plans + (size_t)f * 2);
+        reinterpret_cast<uint32_t*>(&S.plan[0])[lane] = src[lane];           // 2 x 128 bytes
+        reinterpret_cast<uint32_t*>(&S.plan[1])[lane] = src[32 + lane];
         if (lane == 0) {
-            S.sigidx[0] = si0; S.sigidx[1] = si1; S.ca = ca;
-            frame_ca[blockIdx.x] = (uint8_t)ca;
+            S.sigidx[0] = (ca == 2) ? 3 : (ca == 3 ? 2 : 0); S.sigidx[1] = (ca == 0 || ca == 2) ? 1 : 3; S.ca = ca;
             S.hdr_len = (uint32_t)build_frame_header(S.hdr, P.channels, P.bps, P.sample_rate, (uint32_t)N, fd.frame_number, ca);
         }
     }
-    __syncthreads();
+    fu_stage<kFuThreads>(pcm + fd.pcm_off, N, G, tile, &S.mbar, tid);
 
     // =================== pack (row E12): the analysis scratch becomes the frame image ===================
-    FU_MARK(6);
     for (uint32_t i = tid; i < L.obuf_words; i += kFuThreads) obuf[i] = 0u;
     __syncthreads();
-    FU_MARK(7);
     if (tid < (int)S.hdr_len) put_bits(obuf, (uint32_t)tid * 8u, S.hdr[tid], 8);
     uint32_t pos = S.hdr_len * 8u;
     for (int c = 0; c < ch; c++) {
@@ -1022,7 +888,6 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
     __syncthreads();
 
     // =================== CRC-16 over the byte-padded frame, append, store ===================
-    FU_MARK(8);
     const uint32_t nb = (pos + 7u) >> 3;
     {
         const uint16_t c2 = cta_crc16_words<kFuThreads>([&](uint32_t j) {
@@ -1032,15 +897,12 @@ fused_encode_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict
         if (tid == 0) put_bits(obuf, nb * 8u, c2, 16);
     }
     __syncthreads();
-    FU_MARK(9);
     {
         const uint32_t total = nb + 2u;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(scratch + (size_t)blockIdx.x * scratch_stride);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(scratch + (size_t)f * scratch_stride);
         for (uint32_t wd = tid; wd < (total + 3u) / 4u; wd += kFuThreads) dst[wd] = __byte_perm(obuf[wd], 0u, 0x0123);
-        if (tid == 0) frame_len[blockIdx.x] = total;
+        if (tid == 0) frame_len[f] = total;
     }
-    FU_MARK(10);
-#undef FU_MARK
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1058,50 +920,49 @@ static FuLayout fused_layout(const EncParams& P, uint32_t scratch_stride) {
     L.n_steps = fu_apod_steps(P);
     L.obuf_words = scratch_stride / 4u + 4u;
     auto up = [](uint32_t v, uint32_t a) { return (v + a - 1u) / a * a; };
+    // analysis kernel: tile | scratch | FuShared
     L.ovl_off = up(L.tile_words * 4u, 128u);
     uint32_t o = 0;
-    L.ring_off = o;      o += up((P.max_lpc_order ? L.n_win : 0u) * kFuSig * kFuRing * 8u, 16u);
-    L.wring_off = o;     o += (P.max_lpc_order ? L.n_win : 0u) * kWinSlots * 32u * 4u;
     L.acstore_off = o;   o += up(kFuSig * L.n_win * kAcStoreStride * 8u, 16u);
-    L.ws_off = o;        o += up(kFuWarps * (uint32_t)sizeof(WarpScratch), 16u);
-    L.psum_off = o;      o += kFuWarps * 2u * kMaxParts * 8u;
-    L.fixsum_off = o;    o += kFuSig * 5u * kMaxParts * 8u;
+    L.ws_off = o;        o += up(kFuAnWarps * (uint32_t)sizeof(WarpScratch), 16u);
+    L.psum_off = o;      o += kFuAnWarps * 2u * kMaxParts * 8u;
+    L.fixsum_off = o;    o += kFuSig * 5u * (1u << P.max_part_order) * 8u;
     L.baseplan_off = o;  o += kFuSig * (uint32_t)sizeof(SubframePlan);
     L.stepplan_off = o;  o += kFuSig * std::max(1u, L.n_steps) * (uint32_t)sizeof(SubframePlan);
-    L.ovl_bytes = up(std::max(o, L.obuf_words * 4u + 16u), 128u);
+    L.ovl_bytes = up(o, 128u);
     L.shared_off = L.ovl_off + L.ovl_bytes;
-    L.crctab_off = up(L.shared_off + (uint32_t)sizeof(FuShared), 16u);
-    L.total_bytes = L.crctab_off + 4u * 256u * 2u;
+    L.crctab_off = 0;
+    L.total_bytes = up(L.shared_off + (uint32_t)sizeof(FuShared), 16u);
+    // pack kernel: tile | frame image | FuShared | CRC tables
+    L.pk_obuf_off = up(L.tile_words * 4u, 128u);
+    L.pk_shared_off = L.pk_obuf_off + up(L.obuf_words * 4u + 16u, 128u);
+    L.pk_crctab_off = up(L.pk_shared_off + (uint32_t)sizeof(FuShared), 16u);
+    L.pk_total_bytes = L.pk_crctab_off + 4u * 256u * 2u;
     return L;
 }
 
-// Can this batch take the fused kernel?  16-bit stereo in an int16 container, no loose mid/side (its followers wait for
-// a decision made in another frame), tile + scratch small enough for at least two CTAs per SM.
+// Can this batch take the TMA-staged kernels of this file?  16-bit stereo in an int16 container, no loose mid/side (its
+// followers wait for a decision made in another frame), tiles small enough for at least two CTAs per SM.
 bool fused_eligible(const EncParams& P, uint32_t scratch_stride, int max_smem_optin) {
     if (!(P.container_bytes == 2 && P.channels == 2) || P.loose_frames) return false;
     if (P.max_lpc_order > kMaxOrder) return false;
     const FuLayout L = fused_layout(P, scratch_stride);
-    return (int)L.total_bytes <= max_smem_optin && L.total_bytes <= 110u * 1024u;
+    const uint32_t m = std::max(L.total_bytes, L.pk_total_bytes);
+    return (int)m <= max_smem_optin && m <= 110u * 1024u;
 }
 
-void launch_fused(const void* pcm, const FrameDesc* frames, const float* windows, const EncParams& P, int n_frames, uint8_t* frame_ca,
-                  EncStats* stats, uint8_t* scratch, uint32_t scratch_stride, uint32_t* frame_len, cudaStream_t stream) {
+// ac = the autocorrelations autoc_kernel (enc_analyze.cu, un-shifted mode) left in the per-frame work records:
+// frame f's [signal][window][kAcStoreStride] doubles start at ac + f * ac_frame_stride bytes.  plans: 2 per frame.
+void launch_fused(const void* pcm, const FrameDesc* frames, const EncParams& P, int n_frames, const void* ac, size_t ac_frame_stride,
+                  SubframePlan* plans, uint8_t* frame_ca, EncStats* stats, uint8_t* scratch, uint32_t scratch_stride, uint32_t* frame_len,
+                  cudaStream_t stream, cudaEvent_t ev_after_analyze) {
     const FuLayout L = fused_layout(P, scratch_stride);
-    cudaFuncSetAttribute(fused_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes);
-    // debugging aid: FLACB200_FU_TIMELINE=<file> dumps 16 clock64 marks per CTA of every launch (synchronous; tools/fu_timeline.py)
-    unsigned long long* tl = nullptr;
-    const char* tl_path = getenv("FLACB200_FU_TIMELINE");
-    if (tl_path && cudaMalloc(&tl, (size_t)n_frames * 16 * 8) != cudaSuccess) tl = nullptr;
-    if (tl) cudaMemsetAsync(tl, 0, (size_t)n_frames * 16 * 8, stream);
-    fused_encode_kernel<<<(unsigned)n_frames, kFuThreads, L.total_bytes, stream>>>((const int16_t*)pcm, frames, windows, P, L, frame_ca, stats,
-                                                                                  scratch, scratch_stride, frame_len, tl);
-    if (tl) {
-        std::vector<unsigned long long> h((size_t)n_frames * 16);
-        cudaStreamSynchronize(stream);
-        cudaMemcpy(h.data(), tl, h.size() * 8, cudaMemcpyDeviceToHost);
-        if (FILE* f = fopen(tl_path, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
-        cudaFree(tl);
-    }
+    cudaFuncSetAttribute(fused_analyze_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes);
+    fused_analyze_kernel<<<(unsigned)n_frames, kFuAnThreads, L.total_bytes, stream>>>((const int16_t*)pcm, frames, P, L, (const double*)ac, ac_frame_stride,
+                                                                                    plans, frame_ca, stats);
+    if (ev_after_analyze) cudaEventRecord(ev_after_analyze, stream);
+    cudaFuncSetAttribute(fused_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.pk_total_bytes);
+    fused_pack_kernel<<<(unsigned)n_frames, kFuThreads, L.pk_total_bytes, stream>>>((const int16_t*)pcm, frames, P, L, plans, frame_ca, scratch, scratch_stride, frame_len);
 }
 
 }  // namespace fb

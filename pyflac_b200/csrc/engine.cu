@@ -32,7 +32,9 @@ void launch_pack(const void*, const FrameDesc*, const EncParams&, int, const Sub
                  uint32_t, uint32_t*, cudaStream_t);
 size_t pack_smem_bytes(const EncParams&, uint32_t);
 bool fused_eligible(const EncParams&, uint32_t, int);
-void launch_fused(const void*, const FrameDesc*, const float*, const EncParams&, int, uint8_t*, EncStats*, uint8_t*, uint32_t, uint32_t*, cudaStream_t);
+void launch_autoc_unshifted(const void*, const FrameDesc*, const float*, const EncParams&, int, void*, cudaStream_t);
+void launch_fused(const void*, const FrameDesc*, const EncParams&, int, const void*, size_t, SubframePlan*, uint8_t*, EncStats*, uint8_t*, uint32_t,
+                  uint32_t*, cudaStream_t, cudaEvent_t);
 void launch_md5(const void*, uint32_t, const uint64_t*, const uint64_t*, int, uint32_t, uint32_t, uint8_t*, cudaStream_t);
 void launch_layout(const uint32_t*, const FrameDesc*, int, uint32_t, uint64_t, uint64_t*, uint64_t*, cudaStream_t);
 void launch_compact(const uint8_t*, uint32_t, const uint32_t*, const uint64_t*, uint8_t*, int, cudaStream_t);
@@ -306,7 +308,7 @@ extern "C" int flacb200_kernel_times(flacb200_ctx* ctx, float* ms) {
     CK(cudaEventElapsedTime(&ms[6], ctx->ev_k[0], ctx->ev_k[8]));
     CK(cudaEventElapsedTime(&ms[7], ctx->ev_k[8], ctx->ev_k[9]));
     CK(cudaEventElapsedTime(&ms[8], ctx->ev_k[9], ctx->ev_k[1]));
-    ms[9] = ctx->use_fused ? 1.0f : 0.0f;        // 1: ms[0] is the fused kernel (enc_fused.cu), ms[1] and ms[6..8] are zero
+    ms[9] = ctx->use_fused ? 1.0f : 0.0f;        // 1: the TMA-staged kernels of enc_fused.cu ran: ms[7] autocorrelation, ms[8] analysis, ms[1] pack; ms[6] (OR/AND pass) is zero
     return 0;
 }
 extern "C" uint64_t flacb200_launch_count(const flacb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -442,10 +444,14 @@ static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
     int n_an;
     if (ctx->use_fused) {
         // one kernel from PCM to frame bytes (enc_fused.cu); the split events collapse onto its end
-        launch_fused(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, (uint8_t*)ctx->d_ca.p, (EncStats*)S.stats.p,
-                     (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)S.flen.p, st);
-        if (prof) { CK(cudaEventRecord(ctx->ev_k[8], st)); CK(cudaEventRecord(ctx->ev_k[9], st)); CK(cudaEventRecord(ctx->ev_k[1], st)); }
-        n_an = 0;
+        // enc_fused.cu path: autocorrelation (un-shifted, no OR/AND pass needed) -> TMA-staged analysis -> TMA-staged pack
+        if (prof) CK(cudaEventRecord(ctx->ev_k[8], st));
+        launch_autoc_unshifted(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, ctx->d_work.p, st);
+        if (prof) CK(cudaEventRecord(ctx->ev_k[9], st));
+        launch_fused(d_pcm, (const FrameDesc*)ctx->d_frames.p, P, nf, (const uint8_t*)ctx->d_work.p + 64, analyze_work_stride(P), (SubframePlan*)ctx->d_plans.p,
+                     (uint8_t*)ctx->d_ca.p, (EncStats*)S.stats.p, (uint8_t*)ctx->d_scratch.p, ctx->scratch_stride, (uint32_t*)S.flen.p, st,
+                     prof ? ctx->ev_k[1] : nullptr);
+        n_an = (P.max_lpc_order > 0 ? 1 : 0) + 1;
     } else {
         n_an = launch_analyze(d_pcm, (const FrameDesc*)ctx->d_frames.p, (const float*)ctx->d_windows.p, P, nf, (SubframePlan*)ctx->d_plans.p,
                               (uint8_t*)ctx->d_ca.p, ctx->debug ? (SignalDebug*)ctx->d_debug.p : nullptr, (EncStats*)S.stats.p,
@@ -473,7 +479,7 @@ static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
         CK(cudaEventRecord(S.ev_free, S.side)); S.busy = true;
         ctx->launches++;
     }
-    ctx->launches += (ctx->use_fused ? 4 : 4 + n_an);        // fused | analysis kernels + pack, then scan, compact, finalize
+    ctx->launches += 4 + n_an;        // analysis kernels, pack, scan, compact, finalize
     CK(cudaGetLastError());
     return 0;
 }
@@ -731,9 +737,12 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         if (cnf > 0) {
             int n_an = 0;
             if (ctx->use_fused) {
-                launch_fused(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf, (uint8_t*)ctx->d_ca.p + f0,
-                             (EncStats*)ctx->set().stats.p, (uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride,
-                             (uint32_t*)ctx->set().flen.p + f0, st);
+                launch_autoc_unshifted(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf,
+                                       (uint8_t*)ctx->d_work.p + (size_t)f0 * analyze_work_stride(P), st);
+                launch_fused(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, P, cnf, (const uint8_t*)ctx->d_work.p + (size_t)f0 * analyze_work_stride(P) + 64,
+                             analyze_work_stride(P), (SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals, (uint8_t*)ctx->d_ca.p + f0, (EncStats*)ctx->set().stats.p,
+                             (uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride, (uint32_t*)ctx->set().flen.p + f0, st, nullptr);
+                n_an = (P.max_lpc_order > 0 ? 1 : 0) + 1;
             } else {
             n_an = launch_analyze(ctx->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf,
                                             (SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals, (uint8_t*)ctx->d_ca.p + f0, nullptr, (EncStats*)ctx->set().stats.p,
@@ -749,7 +758,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
             launch_finalize((const uint32_t*)ctx->set().flen.p, (const uint64_t*)ctx->set().foff.p, (const uint32_t*)ctx->d_sfirst.p + s0,
                             (const uint32_t*)ctx->d_snframes.p + s0, (const uint64_t*)ctx->d_ssamples.p + s0, nullptr, cns, P, pro ? 1u : 0u,
                             (uint8_t*)ctx->set().arena.p, (StreamInfoOut*)ctx->set().sinfo.p + s0, st);
-            ctx->launches += ctx->use_fused ? 4 : 4 + n_an;
+            ctx->launches += 4 + n_an;
         } else {
             CKJ(cudaMemsetAsync((uint64_t*)ctx->d_totals.p + c, 0, 8, st));
         }

@@ -6,13 +6,11 @@ import numpy as np
 
 a = np.fromfile(sys.argv[1], np.uint64).reshape(-1, 16).astype(np.int64)
 a = a[a[:, 10] > 0]
-names = ["stage (TMA)", "OR/AND", "need list", "queue A (autoc || fixed)", "queue B (LPC)", "select", "zero image", "pack", "CRC", "store"]
+names = ["stage (TMA)", "OR/AND", "need list", "queue A (fixed)", "queue B (LPC)", "select", "zero image", "pack", "CRC", "store"]
 tot = a[:, 10] - a[:, 0]
 print(f"{len(a)} CTAs; CTA lifetime median {np.median(tot):.0f} cycles (p10 {np.percentile(tot, 10):.0f}, p90 {np.percentile(tot, 90):.0f})")
 for k, n in enumerate(names):
     d = a[:, k + 1] - a[:, k]
     print(f"  {n:28s} median {np.median(d):8.0f}  p90 {np.percentile(d, 90):8.0f}  ({100 * np.median(d) / np.median(tot):4.1f}%)")
-ac = a[:, 13] - a[:, 12]
-ok = a[:, 12] > 0
-print(f"  autocorrelation warp alone   median {np.median(ac[ok]):8.0f}  p90 {np.percentile(ac[ok], 90):8.0f}")
-print("  autoc warp index histogram:", np.bincount(a[ok, 14].astype(int), minlength=8).tolist())
+span = a[:, 10].max() - a[:, 0].min()
+print(f"  worker kernel span {span} cycles")
