@@ -143,11 +143,24 @@ typedef struct {
     uint64_t pcm_off;             /* ELEMENT offset of the stream's first sample in the output */
     uint64_t consumed;            /* bytes covered by metadata + successfully chained frames */
     uint32_t n_frames;
-    int32_t  status;              /* 0 ok; 2 not FLAC, 3 bad metadata, 4 bad frame, 5 incomplete frame, 6 lost sync, 7 CRC-16 mismatch, 8 unsupported */
+    int32_t  status;              /* 0 ok, else the FIRST problem met: 2 not FLAC, 3 bad metadata, 4 bad frame, 5 incomplete frame, 6 lost sync,
+                                     7 CRC-16 mismatch, 8 unsupported, 9 reserved values.  Decoding goes on behind a damaged frame the way
+                                     libFLAC 1.4.3's does (stream_decoder.h:1440-1460): the frame is dropped, the search resumes, and when a
+                                     later frame's number shows that frames are missing they stand as silence in the PCM. */
     uint32_t sample_rate, channels, bits_per_sample, max_blocksize;
+    uint32_t n_events;            /* error-callback events libFLAC would have fired; the first 16 are logged below */
+    uint32_t gap_samples;         /* samples of silence inserted for missing frames */
+    uint32_t ev_frame[16];        /* good frames delivered before event k */
+    uint8_t  ev_status[16];       /* FLAC__StreamDecoderErrorStatus of event k (0 LOST_SYNC, 1 BAD_HEADER, 2 FRAME_CRC_MISMATCH, 3 UNPARSEABLE_STREAM) */
+    uint64_t next_sample;         /* stream position behind the last delivered frame, by the frame headers: hand it to the next headerless batch */
+    uint32_t last_blocksize, have_last;
 } flacb200_dec_stream_info;
 
-typedef struct { uint32_t sample_rate, channels, bits_per_sample; } flacb200_dec_raw_params;
+/* flags bit 0: more input may follow (streaming): errors behind the last good frame are not reported yet;
+ * bit 1: frames of this stream were delivered by an earlier batch: next_sample / last_blocksize (from that batch's
+ * flacb200_dec_stream_info) let the decoder see frames missing across the batch boundary.  fixed_blocksize: STREAMINFO's
+ * blocksize when min == max, else 0. */
+typedef struct { uint32_t sample_rate, channels, bits_per_sample, flags; uint64_t next_sample; uint32_t last_blocksize, fixed_blocksize; } flacb200_dec_raw_params;
 
 typedef struct {
     uint64_t total_elems;         /* PCM elements (samples x channels) produced over all streams */
@@ -165,6 +178,9 @@ int  flacb200_decode_result(flacb200_ctx *ctx, flacb200_dec_result *res);
  * cap entries) receives the blocksize of every decoded frame in stream order. */
 int  flacb200_decode_fetch(flacb200_ctx *ctx, void *pcm, size_t pcm_cap, flacb200_dec_stream_info *streams,
                            uint32_t *frame_samples, uint32_t frame_cap);
+/* Sample offset (within its stream's PCM, inserted silence included) of every delivered frame, in the order of
+ * flacb200_decode_fetch's frame_samples. */
+int  flacb200_decode_fetch_frame_offsets(flacb200_ctx *ctx, uint64_t *frame_sample_off, uint32_t frame_cap);
 /* One-call host -> host decode used for end-to-end work: chunks of streams are pipelined (H2D of the next chunk,
  * kernels of the current one, D2H of the previous one run concurrently).  out_container_bytes must be 2 or 4.
  * PCM lands in `pcm` in stream order; streams[s].pcm_off (elements) indexes it; *total_elems = elements written. */
@@ -190,6 +206,10 @@ int  flacb200_host_path_times(flacb200_ctx *ctx, double *ms);
  *   FLACB200_CHUNKS       pieces the PCM of flacb200_encode_batch_host is cut into for the H2D / kernel / D2H pipeline (default 12)
  *   FLACB200_MD5_THREADS  host threads hashing the caller's PCM meanwhile (default: calibrated so they finish with the H2D copy)
  *   FLACB200_DEC_CHUNKS   groups of streams flacb200_decode_batch_host pipelines (default: one per 200 MB of FLAC, at most 12) */
+/* Drop-in layer (flacb200_flac_api.h): concurrent FLAC__stream_encoder_process_interleaved() calls of different handles are
+ * coalesced into shared GPU batches by a per-device dispatcher; this reports how many batches / jobs it has run.  Handles
+ * choose their device from FLACB200_DEVICE=<index> or round-robin over FLACB200_DEVICES=<i,j,...> (default 0). */
+int  flacb200_dispatch_stats(int device, uint64_t *batches, uint64_t *jobs);
 /* Kernel launches issued by this ctx so far (bench.py's gpu_launches). */
 uint64_t flacb200_launch_count(const flacb200_ctx *ctx);
 

@@ -259,7 +259,8 @@ def encode_streams(engine, streams, sample_rate, bits_per_sample, compression_le
 class DecStreamInfo(C.Structure):
     _fields_ = [("total_samples", C.c_uint64), ("pcm_off", C.c_uint64), ("consumed", C.c_uint64), ("n_frames", C.c_uint32),
                 ("status", C.c_int32), ("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32),
-                ("max_blocksize", C.c_uint32)]
+                ("max_blocksize", C.c_uint32), ("n_events", C.c_uint32), ("gap_samples", C.c_uint32), ("ev_frame", C.c_uint32 * 16),
+                ("ev_status", C.c_uint8 * 16), ("next_sample", C.c_uint64), ("last_blocksize", C.c_uint32), ("have_last", C.c_uint32)]
 
 
 class DecResult(C.Structure):
@@ -268,11 +269,12 @@ class DecResult(C.Structure):
 
 
 class DecRawParams(C.Structure):
-    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32)]
+    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32), ("flags", C.c_uint32),
+                ("next_sample", C.c_uint64), ("last_blocksize", C.c_uint32), ("fixed_blocksize", C.c_uint32)]
 
 
 DEC_STATUS = {0: "ok", 2: "not FLAC", 3: "bad metadata", 4: "bad frame", 5: "incomplete frame", 6: "lost sync",
-              7: "CRC-16 mismatch", 8: "unsupported"}
+              7: "CRC-16 mismatch", 8: "unsupported", 9: "reserved values"}
 
 
 def _dec_proto(L):

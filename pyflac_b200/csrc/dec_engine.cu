@@ -26,7 +26,8 @@ void launch_dec_sync(const uint8_t*, const uint64_t*, const uint64_t*, const Dec
 void launch_dec_scan(const uint32_t*, int, uint32_t*, uint64_t*, uint64_t*, cudaStream_t);
 void launch_dec_cand_size(const DecCand*, int, uint32_t*, cudaStream_t);
 void launch_dec_frames(const uint8_t*, const uint64_t*, const uint64_t*, DecCand*, int, const uint64_t*, int32_t*, cudaStream_t);
-void launch_dec_chain(DecCand*, const uint32_t*, const DecStreamMeta*, const uint64_t*, int, DecStreamResult*, uint32_t*, cudaStream_t);
+void launch_dec_chain(DecCand*, const uint32_t*, const DecStreamMeta*, const uint64_t*, int, int, DecStreamResult*, uint32_t*, unsigned int*, cudaStream_t);
+void launch_dec_crc(const uint8_t*, const uint64_t*, DecCand*, int, cudaStream_t);
 void launch_dec_assign(DecStreamResult*, const uint64_t*, int, cudaStream_t);
 void launch_dec_post(const uint8_t*, const uint64_t*, DecCand*, int, const uint64_t*, const int32_t*, DecStreamResult*, void*, int, cudaStream_t);
 void launch_dec_cand_first(const uint32_t*, const uint32_t*, int, int, const uint64_t*, uint32_t*, cudaStream_t);
@@ -177,7 +178,11 @@ static int decode_core(flacb200_ctx* ctx, DecState* d, cudaStream_t st, const ui
     if (after_uploads) { const int rcu = (*after_uploads)(); if (rcu) return rcu; }
 
     DecStreamMeta rawp; memset(&rawp, 0, sizeof rawp);
-    if (raw) { rawp.sample_rate = raw->sample_rate; rawp.channels = raw->channels; rawp.bps = raw->bits_per_sample; }
+    if (raw) {
+        rawp.sample_rate = raw->sample_rate; rawp.channels = raw->channels; rawp.bps = raw->bits_per_sample;
+        rawp.min_blocksize = rawp.max_blocksize = raw->fixed_blocksize;
+        rawp.have_last = (raw->flags & 2u) ? 1u : 0u; rawp.last_blocksize = raw->last_blocksize; rawp.next_sample = raw->next_sample;
+    }
     CKD(cudaEventRecord(d->ev[0], st));
     launch_dec_meta(d_blob, (const uint64_t*)d->soff.p, (const uint64_t*)d->slen.p, ns, raw ? 1 : 0, rawp, (DecStreamMeta*)d->meta.p, st);
     uint64_t h_total = 0;
@@ -209,29 +214,35 @@ static int decode_core(flacb200_ctx* ctx, DecState* d, cudaStream_t st, const ui
         CKD(d->samples.reserve(4 * (size_t)(h_slots + 16)));
         launch_dec_frames(d_blob, (const uint64_t*)d->soff.p, (const uint64_t*)d->slen.p, (DecCand*)d->cands.p, nc, (const uint64_t*)d->slotoff.p, (int32_t*)d->samples.p, st);
     }
+    if (nc) launch_dec_crc(d_blob, (const uint64_t*)d->soff.p, (DecCand*)d->cands.p, nc, st);
     CKD(cudaEventRecord(d->ev[2], st));
-    launch_dec_chain((DecCand*)d->cands.p, (const uint32_t*)d->candfirst.p, (const DecStreamMeta*)d->meta.p, (const uint64_t*)d->slen.p, ns,
-                     (DecStreamResult*)d->res.p, (uint32_t*)d->ss32.p, st);
+    // total (8 bytes) is followed by the "some stream has silence to fill" flag
+    CKD(cudaMemsetAsync((uint8_t*)d->total.p + 8, 0, 8, st));
+    const int eof = (raw && (raw->flags & 1u)) ? 0 : 1;         // raw bit 0: more input may follow (streaming callers)
+    launch_dec_chain((DecCand*)d->cands.p, (const uint32_t*)d->candfirst.p, (const DecStreamMeta*)d->meta.p, (const uint64_t*)d->slen.p, ns, eof,
+                     (DecStreamResult*)d->res.p, (uint32_t*)d->ss32.p, (unsigned int*)((uint8_t*)d->total.p + 8), st);
     launch_dec_scan((const uint32_t*)d->ss32.p, ns, nullptr, (uint64_t*)d->pcmoff.p, (uint64_t*)d->total.p, st);
     launch_dec_assign((DecStreamResult*)d->res.p, (const uint64_t*)d->pcmoff.p, ns, st);
     d->h_res.resize(ns);
     uint64_t h_elems = 0;
-    launch_dec_mirror(d->total.p, d->m_total, 8, st);
+    launch_dec_mirror(d->total.p, d->m_total, 16, st);
     launch_dec_mirror(d->res.p, d->m_res, sizeof(DecStreamResult) * (size_t)ns, st);
     CKD(cudaStreamSynchronize(st));                                      // sync #3: PCM size
     h_elems = d->m_total[0];
+    const bool any_gap = d->m_total[1] != 0;
     memcpy(d->h_res.data(), d->m_res, sizeof(DecStreamResult) * (size_t)ns);
     uint32_t ob = out_container_bytes;
     if (ob == 0) { ob = 2; for (int s = 0; s < ns; s++) if (d->h_res[s].bps > 16) ob = 4; }
     for (int s = 0; s < ns; s++) if (ob == 2 && d->h_res[s].bps > 16 && d->h_res[s].n_frames) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "int16 output requested for a >16-bit stream", cudaSuccess);
     d->out_bytes = ob; d->total_elems = h_elems;
     CKD(d->pcm.reserve((size_t)h_elems * ob + 64));
+    if (any_gap) CKD(cudaMemsetAsync(d->pcm.p, 0, (size_t)h_elems * ob, st));     // missing frames stand as silence (rare: corrupted input)
     CKD(cudaEventRecord(d->ev[3], st));
     launch_dec_post(d_blob, (const uint64_t*)d->soff.p, (DecCand*)d->cands.p, nc, (const uint64_t*)d->slotoff.p, (const int32_t*)d->samples.p,
                     (DecStreamResult*)d->res.p, d->pcm.p, (int)ob, st);
     CKD(cudaEventRecord(d->ev[4], st));
     CKD(cudaGetLastError());
-    fb_ctx_add_launches(ctx, 11);
+    fb_ctx_add_launches(ctx, 12);
     d->have = true;
     return 0;
 }
@@ -276,9 +287,26 @@ extern "C" int flacb200_decode_fetch(flacb200_ctx* ctx, void* pcm, size_t pcm_ca
             flacb200_dec_stream_info& o = streams[s];
             o.total_samples = h.total_samples; o.pcm_off = h.pcm_off; o.consumed = h.consumed; o.n_frames = h.n_frames; o.status = h.status;
             o.sample_rate = h.sample_rate; o.channels = h.channels; o.bits_per_sample = h.bps; o.max_blocksize = h.max_blocksize;
+            o.n_events = h.n_events; o.gap_samples = h.gap_samples; o.next_sample = h.next_sample; o.last_blocksize = h.last_blocksize; o.have_last = h.have_last;
+            for (int k = 0; k < kDecMaxEvents; k++) { o.ev_frame[k] = h.ev_frame[k]; o.ev_status[k] = h.ev_status[k]; }
         }
     }
     if (frame_samples) { uint32_t k = 0; for (auto& c : hc) if (c.valid && k < frame_cap) frame_samples[k++] = c.blocksize; }
+    return 0;
+}
+
+// sample offset (within its stream's PCM, silence included) of every delivered frame, in the order of flacb200_decode_fetch's frame_samples
+extern "C" int flacb200_decode_fetch_frame_offsets(flacb200_ctx* ctx, uint64_t* frame_sample_off, uint32_t frame_cap) {
+    if (!ctx || !frame_sample_off) return FLACB200_ERR_ARG;
+    DecState* d = state(ctx);
+    if (!d->have) return fb_ctx_fail(ctx, FLACB200_ERR_ARG, "no decode batch", cudaSuccess);
+    cudaSetDevice(fb_ctx_device(ctx));
+    cudaStream_t st = fb_ctx_stream(ctx);
+    std::vector<DecCand> hc(d->n_cands);
+    if (d->n_cands) CKD(cudaMemcpyAsync(hc.data(), d->cands.p, sizeof(DecCand) * (size_t)d->n_cands, cudaMemcpyDeviceToHost, st));
+    CKD(cudaStreamSynchronize(st));
+    uint32_t k = 0;
+    for (auto& c : hc) if (c.valid && k < frame_cap) frame_sample_off[k++] = c.sample_off;
     return 0;
 }
 
@@ -375,6 +403,8 @@ extern "C" int flacb200_decode_batch_host(flacb200_ctx* ctx, const uint8_t* blob
                 flacb200_dec_stream_info& o = streams[s];
                 o.total_samples = h.total_samples; o.pcm_off = h.pcm_off + elem_base; o.consumed = h.consumed; o.n_frames = h.n_frames; o.status = h.status;
                 o.sample_rate = h.sample_rate; o.channels = h.channels; o.bits_per_sample = h.bps; o.max_blocksize = h.max_blocksize;
+                o.n_events = h.n_events; o.gap_samples = h.gap_samples; o.next_sample = h.next_sample; o.last_blocksize = h.last_blocksize; o.have_last = h.have_last;
+                for (int k = 0; k < kDecMaxEvents; k++) { o.ev_frame[k] = h.ev_frame[k]; o.ev_status[k] = h.ev_status[k]; }
             }
         }
         elem_base += d->total_elems;

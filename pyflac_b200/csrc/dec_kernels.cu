@@ -26,6 +26,7 @@ __global__ void dec_meta_kernel(const uint8_t* __restrict__ blob, const uint64_t
     DecStreamMeta m;
     if (raw_frames) { m = raw_params; m.first_frame = 0; m.status = kDecOk; meta[s] = m; return; }
     m.first_frame = 0; m.sample_rate = 0; m.channels = 0; m.bps = 0; m.min_blocksize = 0; m.max_blocksize = 0; m.total_samples = 0; m.status = kDecOk;
+    m.have_last = 0; m.last_blocksize = 0; m.next_sample = 0;
     for (int i = 0; i < 16; i++) m.md5[i] = 0;
     const uint8_t* p = blob + stream_off[s];
     const uint64_t len = stream_len[s];
@@ -432,7 +433,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
         const uint32_t hdr = br.get(8);
         if (hdr & 0x80) { status = kDecBadFrame; break; }
         uint32_t wasted = 0;
-        if (hdr & 1) { wasted = br.unary() + 1; if (wasted >= bps) { status = kDecBadFrame; break; } bps -= wasted; }
+        if (hdr & 1) { wasted = br.unary() + 1; if (br.overrun()) { status = kDecIncomplete; break; } if (wasted >= bps) { status = kDecBadFrame; break; } bps -= wasted; }
         const uint32_t wsh = (side33 && wasted) ? wasted - 1u : wasted;
         if (side33 && bps <= 32) { uint32_t* bm = reinterpret_cast<uint32_t*>(out + (size_t)c.channels * N); for (uint32_t w2 = 0; w2 < (N + 31u) / 32u; w2++) bm[w2] = 0u; }
         const uint32_t type = (hdr >> 1) & 0x3f;
@@ -451,7 +452,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
         uint32_t order = 0; bool lpc = false;
         if (type >= 8 && type <= 12) order = type - 8;
         else if (type >= 32) { order = type - 31; lpc = true; }
-        else if (type >= 2) { status = kDecBadFrame; break; }
+        else if (type >= 2) { status = kDecUnparseable; break; }            // reserved subframe types
         if (order > N) { status = kDecBadFrame; break; }
         if (bps == 33 || order > (uint32_t)kDecFastOrder) {
             // ---- rare, generic code: the 33-bit side channel of a 32-bit stereo stream (the plane receives sample >> 1 and a
@@ -485,7 +486,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
                     for (uint32_t j = 0; j < order; j++) qq[j] = cf[order][j];
                 }
                 const uint32_t method = br.get(2);
-                if (method > 1) { status = kDecBadFrame; break; }
+                if (method > 1) { status = kDecUnparseable; break; }
                 const uint32_t po = br.get(4), plen = method ? 5u : 4u, pesc = method ? 31u : 15u;
                 if ((N >> po) < order || (po > 0 && (N & ((1u << po) - 1)))) { status = kDecBadFrame; break; }
                 uint32_t left = 0, k = 0, raw = 0;
@@ -535,7 +536,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
         const bool wide = lpc ? (bps + prec + ilog2_u32(order ? order : 1) > 32) : (bps + order > 31);
         // residual: method, partition order, then per partition a parameter and its symbols
         const uint32_t method = br.get(2);
-        if (method > 1) { status = kDecBadFrame; break; }
+        if (method > 1) { status = kDecUnparseable; break; }                  // reserved residual coding methods
         const uint32_t po = br.get(4), plen = method ? 5u : 4u, pesc = method ? 31u : 15u;
         const uint32_t psize = N >> po;
         if (psize < order || (po > 0 && (N & ((1u << po) - 1)))) { status = kDecBadFrame; break; }
@@ -605,41 +606,142 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
         if (endbyte + 2 > slen) status = kDecIncomplete;
         c.end_pos = (uint32_t)(endbyte + 2);
     }
+    if (status != kDecOk) {                         // where the parse stopped: the resynchronisation scan goes on from here
+        const uint64_t stop = (br.bit_position() + 7ull) >> 3;
+        c.end_pos = (uint32_t)(stop < slen ? stop : slen);
+    }
     cands[ci].status = status;
     cands[ci].end_pos = c.end_pos;
 }
 
+// ------------------------------------------------------------------ CRC-16 of every decodable candidate: one warp each ----
+// (ref: format.h:467-475.)  Runs before the chain walk so that the walk can treat a frame with a bad checksum exactly as
+// libFLAC does: report it, drop it and search on from just behind its sync code.
+__global__ void __launch_bounds__(128)
+dec_crc_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, DecCand* __restrict__ cands, int n_cands) {
+    __shared__ __align__(16) uint16_t tabs[4][256];
+    for (int i = threadIdx.x; i < 256; i += 128) reinterpret_cast<uint2*>(&tabs[0][0])[i] = reinterpret_cast<const uint2*>(&g_crc16_slice.t[0][0])[i];
+    __syncthreads();
+    const int ci = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (ci >= n_cands) return;
+    const DecCand c = cands[ci];
+    if (c.status != kDecOk) return;
+    const uint8_t* fb = blob + stream_off[c.stream] + c.pos;
+    const uint32_t nb = c.end_pos - c.pos - 2u;
+    const uint32_t mis = (uint32_t)((uintptr_t)fb & 3u);
+    const uint32_t* fw = reinterpret_cast<const uint32_t*>(fb - mis);       // aligned words; byte j of the frame is byte j + mis of fw
+    auto word_at = [&](uint32_t j) { const uint32_t o = j + mis; return __funnelshift_r(__ldg(fw + (o >> 2)), __ldg(fw + (o >> 2) + 1), (o & 3u) * 8u); };
+    const uint32_t nchunks = (nb + 63u) >> 6;
+    uint32_t acc = 0;
+    for (uint32_t j = (uint32_t)lane; j < nchunks; j += 32) {               // 64-byte chunks counted from the end of the frame
+        const uint32_t end = nb - (j << 6);
+        uint32_t crc = 0;
+        if (end >= 64u) {
+            const uint32_t beg = end - 64u;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint32_t w = word_at(beg + 4u * (uint32_t)i);
+                crc = (uint32_t)tabs[3][(crc >> 8) ^ (w & 0xffu)] ^ tabs[2][(crc & 0xffu) ^ ((w >> 8) & 0xffu)] ^ tabs[1][(w >> 16) & 0xffu] ^ tabs[0][w >> 24];
+            }
+        } else {
+            for (uint32_t b = 0; b < end; b++) crc = ((crc << 8) & 0xffffu) ^ tabs[0][(crc >> 8) ^ (word_at(b) & 0xffu)];
+        }
+        uint16_t c16 = (uint16_t)crc;
+        if (j) c16 = crc16_mulmod(c16, g_crc_pos.lo[j & 255u]);
+        if (j >> 8) c16 = crc16_mulmod(c16, g_crc_pos.hi[(j >> 8) & 15u]);
+        acc ^= c16;
+    }
+    acc = __reduce_xor_sync(0xffffffffu, acc);
+    if (lane == 0) {
+        const uint16_t stored = (uint16_t)((uint16_t)fb[nb] << 8 | fb[nb + 1]);
+        if ((uint16_t)acc != stored) cands[ci].status = kDecCrcMismatch;
+    }
+}
+
 // ------------------------------------------------------------------ chain walk: one thread per stream ----
+// The sequential part of libFLAC's stream_decoder.c (frame_sync_ / read_frame_) over the candidate table, incl. what
+// 1.4.3 does when something is wrong (pinned against the reference binary, tests/test_gpu_decode.py::test_decode_error_
+// recovery_matches_libflac):
+//  * bytes that are not a frame where one should start: LOST_SYNC once, the search goes on to the next candidate;
+//  * a frame whose CRC-16 does not match: FRAME_CRC_MISMATCH, the frame is dropped and the search resumes two bytes
+//    behind its sync code (so LOST_SYNC follows while the scan runs through the frame's body);
+//  * a frame that cannot be parsed: UNPARSEABLE_STREAM (reserved values) or LOST_SYNC, the search resumes where the parse stopped;
+//  * a good frame whose number says that frames are missing in front of it (and something was decoded before): the gap is
+//    filled with silence in units of the previous frame's blocksize; missing frames at the very start or end are not filled.
+// Errors behind the last good frame are reported only when no more input can follow (eof): a streaming caller sees them
+// once, when the next good frame or the end of the stream closes the gap.
 __global__ void dec_chain_kernel(DecCand* __restrict__ cands, const uint32_t* __restrict__ cand_first, const DecStreamMeta* __restrict__ meta,
-                                 const uint64_t* __restrict__ stream_len, int n_streams, DecStreamResult* __restrict__ res, uint32_t* __restrict__ stream_samples32) {
+                                 const uint64_t* __restrict__ stream_len, int n_streams, int eof, DecStreamResult* __restrict__ res,
+                                 uint32_t* __restrict__ stream_samples32, unsigned int* __restrict__ any_gap) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_streams) return;
-    DecStreamResult r; r.total_samples = 0; r.n_frames = 0; r.status = meta[s].status; r.consumed = meta[s].first_frame; r.max_blocksize = 0; r.pcm_off = 0;
-    r.sample_rate = meta[s].sample_rate; r.channels = meta[s].channels; r.bps = meta[s].bps;
+    DecStreamResult r;
+    r.total_samples = 0; r.n_frames = 0; r.status = meta[s].status; r.consumed = meta[s].first_frame; r.max_blocksize = 0; r.pcm_off = 0;
+    r.sample_rate = meta[s].sample_rate; r.channels = meta[s].channels; r.bps = meta[s].bps; r.n_events = 0; r.gap_samples = 0;
+    r.next_sample = meta[s].next_sample; r.last_blocksize = meta[s].last_blocksize; r.have_last = meta[s].have_last;
+    for (int k = 0; k < kDecMaxEvents; k++) { r.ev_frame[k] = 0; r.ev_status[k] = 0; }
     if (r.status == kDecOk) {
         uint64_t expect = meta[s].first_frame;
         uint32_t i = cand_first[s];
         const uint32_t iend = cand_first[s + 1];
         const uint64_t slen = stream_len[s];
+        // events since the last good frame (committed when the next good frame or the end of input closes the gap)
+        uint8_t pend[kDecMaxEvents]; uint32_t npend = 0; int pend_first = kDecOk;
+        auto push = [&](int flac_status, int own_status) { if (npend < (uint32_t)kDecMaxEvents) pend[npend] = (uint8_t)flac_status; npend++; if (pend_first == kDecOk) pend_first = own_status; };
+        auto commit = [&]() {
+            for (uint32_t k = 0; k < npend; k++) { if (r.n_events < (uint32_t)kDecMaxEvents && k < (uint32_t)kDecMaxEvents) { r.ev_frame[r.n_events] = r.n_frames; r.ev_status[r.n_events] = pend[k]; } r.n_events++; }
+            if (r.status == kDecOk) r.status = pend_first;
+            npend = 0; pend_first = kDecOk;
+        };
+        bool have_last = meta[s].have_last != 0, in_gap = false, incomplete_tail = false;
+        uint64_t next_sample = meta[s].next_sample;      // first sample behind the last delivered frame, by the frame headers' numbering
+        uint32_t last_bs = meta[s].last_blocksize, fixed_bs = meta[s].max_blocksize && meta[s].min_blocksize == meta[s].max_blocksize ? meta[s].max_blocksize : 0u;
         while (expect < slen) {
             while (i < iend && cands[i].pos < expect) i++;
-            if (i >= iend || cands[i].pos != expect) { r.status = kDecLostSync; break; }
-            const int st = cands[i].status;
-            if (st != kDecOk) { r.status = st; break; }
-            if (r.n_frames == 0) { r.sample_rate = cands[i].sample_rate; r.channels = cands[i].channels; r.bps = cands[i].bps; }
-            // the PCM layout scans 32-bit element counts per stream: a stream that would decode to 2^32 elements or more (a few MB
-            // of CONSTANT frames can) stops here with an error instead of wrapping the count
-            if ((r.total_samples + cands[i].blocksize) * (uint64_t)(r.channels ? r.channels : 1) > 0xFFFFFFF0ull) { r.status = kDecUnsupported; break; }
-            cands[i].valid = 1; cands[i].sample_off = r.total_samples;
-            r.total_samples += cands[i].blocksize; r.n_frames++;
-            if (cands[i].blocksize > r.max_blocksize) r.max_blocksize = cands[i].blocksize;
-            expect = cands[i].end_pos;
-            r.consumed = expect;
-            i++;
+            if (i >= iend) break;
+            if (cands[i].pos != expect && !in_gap) { push(0, kDecLostSync); in_gap = true; }             // LOST_SYNC, once per search
+            const DecCand c = cands[i];
+            if (c.status == kDecOk) {
+                if (r.n_frames == 0) { r.sample_rate = c.sample_rate; r.channels = c.channels; r.bps = c.bps; }
+                if (fixed_bs == 0 && !c.variable) fixed_bs = c.blocksize;                                   // up: fixed_block_size falls back to the first frame's
+                const uint64_t start = c.variable ? c.number : c.number * (uint64_t)fixed_bs;
+                uint64_t gap = (have_last && start > next_sample) ? start - next_sample : 0ull;
+                if (gap > (1ull << 28)) gap = 0;                                                           // a corrupt number, not a hole in the stream
+                const uint64_t chn = (uint64_t)(r.channels ? r.channels : 1);
+                if ((r.total_samples + gap + c.blocksize) * chn > 0xFFFFFFF0ull) { if (r.status == kDecOk) r.status = kDecUnsupported; break; }
+                commit();
+                in_gap = false;
+                r.total_samples += gap; r.gap_samples += (uint32_t)gap;
+                cands[i].valid = 1; cands[i].sample_off = r.total_samples;
+                r.total_samples += c.blocksize; r.n_frames++;
+                if (c.blocksize > r.max_blocksize) r.max_blocksize = c.blocksize;
+                have_last = true; next_sample = start + c.blocksize; last_bs = c.blocksize;
+                expect = c.end_pos;
+                r.consumed = expect;
+                i++;
+            } else if (c.status == kDecIncomplete) {
+                incomplete_tail = true;                                     // the frame runs past the input: wait for more, or lost at the end
+                break;
+            } else {
+                if (c.status == kDecCrcMismatch) { push(2, kDecCrcMismatch); expect = (uint64_t)c.pos + 2; }
+                else { push(c.status == kDecUnparseable ? 3 : 0, c.status); expect = c.end_pos > c.pos + 2 ? c.end_pos : (uint64_t)c.pos + 2; }
+                in_gap = false;                                             // the next search reports its own LOST_SYNC
+                i++;
+            }
+        }
+        r.next_sample = next_sample; r.last_blocksize = last_bs; r.have_last = have_last ? 1u : 0u;
+        if (eof) {
+            // nothing follows: what is left behind the last good frame is lost
+            if (r.consumed < slen && !in_gap && (incomplete_tail || expect < slen || npend == 0)) push(0, incomplete_tail ? kDecIncomplete : kDecLostSync);
+            if (r.consumed < slen || npend) commit();
+            if (r.consumed < slen && r.status == kDecOk) r.status = kDecLostSync;
+        } else if (r.status == kDecOk && r.consumed < slen) {
+            r.status = incomplete_tail ? kDecIncomplete : kDecLostSync;    // informational for streaming callers: bytes are still pending
         }
     }
+    if (r.gap_samples) atomicOr(any_gap, 1u);
     res[s] = r;
-    stream_samples32[s] = (uint32_t)(r.total_samples * (r.channels ? r.channels : 1));   // elements; streams < 2^32 elements
+    stream_samples32[s] = (uint32_t)(r.total_samples * (r.channels ? r.channels : 1));   // elements; < 2^32 (checked above)
 }
 
 __global__ void dec_assign_kernel(DecStreamResult* __restrict__ res, const uint64_t* __restrict__ pcm_off, int n_streams) {
@@ -648,7 +750,7 @@ __global__ void dec_assign_kernel(DecStreamResult* __restrict__ res, const uint6
 }
 
 // ------------------------------------------------------------------ post: one CTA per chained frame ----
-// CRC-16 of the frame bytes (chunked, combined in GF(2)[x]/P like the encoder), undo channel decorrelation
+// (CRC-16 is checked per candidate by dec_crc_kernel before the chain walk.)  Undo channel decorrelation
 // (ref: format.h:388-393), narrow to the caller's container, interleave [sample][channel], coalesced stores.
 // undo one inter-channel decorrelation (ref: format.h:388-393); a = plane 0, b = plane 1
 __device__ __forceinline__ void undo_stereo(int ca, int32_t a, int32_t b, int32_t& l, int32_t& r) {
@@ -662,17 +764,13 @@ __global__ void __launch_bounds__(256, 4)
 dec_post_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, DecCand* __restrict__ cands,
                 const uint64_t* __restrict__ slot_off, const int32_t* __restrict__ samples, DecStreamResult* __restrict__ res,
                 OutT* __restrict__ pcm_out) {
-    __shared__ __align__(16) uint16_t crc_tabs[4][256];
-    __shared__ uint32_t crc_warp[8];
     const int tid = threadIdx.x;
     const DecCand c = cands[blockIdx.x];
     if (!c.valid) return;
-    reinterpret_cast<uint2*>(&crc_tabs[0][0])[tid] = reinterpret_cast<const uint2*>(&g_crc16_slice.t[0][0])[tid];
     const uint32_t N = c.blocksize, ch = c.channels;
     const int32_t* in = samples + slot_off[blockIdx.x];                     // 16-byte aligned (padded slots)
     OutT* out = pcm_out + res[c.stream].pcm_off + c.sample_off * ch;
-    // Stereo frames whose planes can be read four samples at a time: the first 1024 sample quads of both planes are
-    // requested BEFORE the CRC so that their latency hides behind it.
+    // Stereo frames whose planes can be read four samples at a time: the first 1024 sample quads of both planes are requested up front.
     const bool side33 = c.bps == 32;                 // side plane = side >> 1, low bits in the bitmap behind the planes (dec_frame_kernel)
     const bool quads = c.ca != 0 && !side33 && (N & 3u) == 0u;
     const uint32_t nq = N >> 2;
@@ -684,21 +782,6 @@ dec_post_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ s
         for (int u = 0; u < 4; u++) {
             const uint32_t qi = (uint32_t)tid + 256u * (uint32_t)u;
             if (qi < nq) { A[u] = __ldcs(pa + qi); B[u] = __ldcs(pb + qi); }
-        }
-    }
-    __syncthreads();
-    const uint8_t* fb = blob + stream_off[c.stream] + c.pos;
-    const uint32_t nb = c.end_pos - c.pos - 2u;
-    {
-        const uint32_t mis = (uint32_t)((uintptr_t)fb & 3u);
-        const uint32_t* fw = reinterpret_cast<const uint32_t*>(fb - mis);   // aligned words; byte j of the frame is byte j + mis of fw
-        const uint16_t c2 = cta_crc16_words<256>([&](uint32_t j) {
-            const uint32_t o = j + mis;
-            return __funnelshift_r(__ldg(fw + (o >> 2)), __ldg(fw + (o >> 2) + 1), (o & 3u) * 8u);
-        }, nb, crc_tabs, crc_warp, tid);
-        if (tid == 0) {
-            const uint16_t stored = (uint16_t)((uint16_t)fb[nb] << 8 | fb[nb + 1]);
-            if (c2 != stored) { res[c.stream].status = kDecCrcMismatch; cands[blockIdx.x].status = kDecCrcMismatch; }
         }
     }
     if (c.ca == 0) {
@@ -796,8 +879,12 @@ void launch_dec_cand_size(const DecCand* cands, int n, uint32_t* sizes, cudaStre
 void launch_dec_frames(const uint8_t* blob, const uint64_t* soff, const uint64_t* slen, DecCand* cands, int n, const uint64_t* slot_off, int32_t* samples, cudaStream_t st) {
     if (n) dec_frame_kernel<<<(n + kDecFrameThreads - 1) / kDecFrameThreads, kDecFrameThreads, 0, st>>>(blob, soff, slen, cands, n, slot_off, samples);
 }
-void launch_dec_chain(DecCand* cands, const uint32_t* cand_first, const DecStreamMeta* meta, const uint64_t* slen, int ns, DecStreamResult* res, uint32_t* ss32, cudaStream_t st) {
-    dec_chain_kernel<<<(ns + 127) / 128, 128, 0, st>>>(cands, cand_first, meta, slen, ns, res, ss32);
+void launch_dec_chain(DecCand* cands, const uint32_t* cand_first, const DecStreamMeta* meta, const uint64_t* slen, int ns, int eof, DecStreamResult* res,
+                      uint32_t* ss32, unsigned int* any_gap, cudaStream_t st) {
+    dec_chain_kernel<<<(ns + 127) / 128, 128, 0, st>>>(cands, cand_first, meta, slen, ns, eof, res, ss32, any_gap);
+}
+void launch_dec_crc(const uint8_t* blob, const uint64_t* soff, DecCand* cands, int n, cudaStream_t st) {
+    if (n) dec_crc_kernel<<<(n + 3) / 4, 128, 0, st>>>(blob, soff, cands, n);
 }
 void launch_dec_assign(DecStreamResult* res, const uint64_t* pcm_off, int ns, cudaStream_t st) {
     dec_assign_kernel<<<(ns + 127) / 128, 128, 0, st>>>(res, pcm_off, ns);

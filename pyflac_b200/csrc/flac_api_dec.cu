@@ -40,15 +40,23 @@ enum { DS_SEARCH_FOR_METADATA = 0, DS_READ_METADATA = 1, DS_SEARCH_FOR_FRAME_SYN
 enum { DI_OK = 0, DI_UNSUPPORTED_CONTAINER = 1, DI_INVALID_CALLBACKS = 2, DI_MEMORY_ALLOCATION_ERROR = 3, DI_ERROR_OPENING_FILE = 4, DI_ALREADY_INITIALIZED = 5 };
 enum { ERR_LOST_SYNC = 0, ERR_BAD_HEADER = 1, ERR_FRAME_CRC_MISMATCH = 2, ERR_UNPARSEABLE_STREAM = 3, ERR_BAD_METADATA = 4 };
 
+// one engine context per CUDA device for the decoder handles; the device comes from FLACB200_DEVICE (default 0).
+// The mutex covers GPU work only: callbacks are fired after it is released.
 std::mutex g_dec_mu;
-flacb200_ctx* g_dec_ctx = nullptr;
-int g_dec_rc = -1;
+flacb200_ctx* g_dec_ctx[64] = {nullptr};
+int g_dec_rc[64];
+bool g_dec_init = false;
 flacb200_ctx* dec_ctx() {
-    if (g_dec_rc == -1) g_dec_rc = flacb200_create(&g_dec_ctx, 0);
-    return g_dec_rc == 0 ? g_dec_ctx : nullptr;
+    int dev = 0;
+    if (const char* l = getenv("FLACB200_DEVICE")) dev = atoi(l);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!g_dec_init) { for (int& r : g_dec_rc) r = -1; g_dec_init = true; }
+    if (g_dec_rc[dev] == -1) g_dec_rc[dev] = flacb200_create(&g_dec_ctx[dev], dev);
+    return g_dec_rc[dev] == 0 ? g_dec_ctx[dev] : nullptr;
 }
 
-struct PendingFrame { uint32_t blocksize; std::vector<int32_t> planar; };   // [channel][sample]
+// what the next callback delivers: a decoded frame, a frame of silence standing in for a missing one, or an error status
+struct PendingFrame { uint32_t blocksize; std::vector<int32_t> planar; int error = -1; };   // planar = [channel][sample]; error >= 0: FLAC__StreamDecoderErrorStatus
 
 struct DecImpl {
     int state = DS_UNINITIALIZED;
@@ -61,6 +69,8 @@ struct DecImpl {
     bool eof = false, metadata_done = false;
     uint32_t sample_rate = 0, channels = 0, bps = 0, blocksize = 0;
     uint64_t total_samples = 0, frame_index = 0, bytes_consumed = 0;
+    uint32_t min_blocksize = 0;
+    bool have_last = false; uint64_t next_sample = 0; uint32_t last_blocksize = 0;     // stream position behind the last delivered frame
     std::deque<PendingFrame> ready;       // decoded frames not yet delivered
     FLAC__Frame frame;                    // callback payload (header filled per frame)
 };
@@ -104,7 +114,7 @@ int parse_metadata(FLAC__StreamDecoder* d) {
         if (pos + 4 + len > m->in.size()) return m->eof ? -1 : 0;
         if (type == 0 && len >= 34) {
             const uint8_t* q = p + 4;
-            m->blocksize = (uint32_t)q[2] << 8 | q[3];
+            m->blocksize = (uint32_t)q[2] << 8 | q[3]; m->min_blocksize = (uint32_t)q[0] << 8 | q[1];
             m->sample_rate = (uint32_t)q[10] << 12 | (uint32_t)q[11] << 4 | (q[12] >> 4);
             m->channels = ((q[12] >> 1) & 7) + 1;
             m->bps = (((uint32_t)q[12] & 1) << 4 | (q[13] >> 4)) + 1;
@@ -132,48 +142,65 @@ int parse_metadata(FLAC__StreamDecoder* d) {
     return 1;
 }
 
-// decode every complete frame currently buffered (one GPU batch); returns false on fatal error
+// decode every complete frame currently buffered (one GPU batch); returns false on fatal error.  What libFLAC 1.4.3
+// does around damaged input is reproduced from the engine's per-stream event log (dec_kernels.cu:dec_chain_kernel): error
+// callbacks in their place between the frames, a frame with a bad CRC never delivered, missing frames delivered as silence.
 bool decode_buffered(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
     if (m->in.empty()) return true;
-    std::lock_guard<std::mutex> lk(g_dec_mu);
-    flacb200_ctx* ctx = dec_ctx();
-    if (!ctx) { m->state = DS_MEMORY_ALLOCATION_ERROR; return false; }
-    flacb200_dec_raw_params raw{m->sample_rate, m->channels, m->bps};
-    const uint64_t off = 0, len = m->in.size();
-    if (flacb200_decode_batch(ctx, m->in.data(), 0, len, 1, &off, &len, 4, &raw) != 0) { report(d, ERR_UNPARSEABLE_STREAM); m->state = DS_ABORTED; return false; }
-    flacb200_dec_result r;
-    if (flacb200_decode_result(ctx, &r) != 0) { m->state = DS_ABORTED; return false; }
-    std::vector<int32_t> pcm((size_t)r.total_elems + 1);
-    std::vector<uint32_t> fs(r.n_frames + 1);
+    std::vector<int32_t> pcm; std::vector<uint32_t> fs; std::vector<uint64_t> fo;
     flacb200_dec_stream_info si;
-    if (flacb200_decode_fetch(ctx, pcm.data(), pcm.size() * 4, &si, fs.data(), r.n_frames) != 0) { m->state = DS_ABORTED; return false; }
-    // queue frames (planar int32 per channel, as libFLAC hands them to the write callback)
-    size_t base = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_dec_mu);                      // GPU work only; callbacks fire after the lock is gone
+        flacb200_ctx* ctx = dec_ctx();
+        if (!ctx) { m->state = DS_MEMORY_ALLOCATION_ERROR; return false; }
+        flacb200_dec_raw_params raw; memset(&raw, 0, sizeof raw);
+        raw.sample_rate = m->sample_rate; raw.channels = m->channels; raw.bits_per_sample = m->bps;
+        raw.flags = (m->eof ? 0u : 1u) | (m->have_last ? 2u : 0u);
+        raw.next_sample = m->next_sample; raw.last_blocksize = m->last_blocksize;
+        raw.fixed_blocksize = (m->min_blocksize == m->blocksize) ? m->blocksize : 0u;
+        const uint64_t off = 0, len = m->in.size();
+        if (flacb200_decode_batch(ctx, m->in.data(), 0, len, 1, &off, &len, 4, &raw) != 0) { report(d, ERR_UNPARSEABLE_STREAM); m->state = DS_ABORTED; return false; }
+        flacb200_dec_result r;
+        if (flacb200_decode_result(ctx, &r) != 0) { m->state = DS_ABORTED; return false; }
+        pcm.resize((size_t)r.total_elems + 1); fs.resize(r.n_frames + 1); fo.resize(r.n_frames + 1);
+        if (flacb200_decode_fetch(ctx, pcm.data(), pcm.size() * 4, &si, fs.data(), r.n_frames) != 0 ||
+            flacb200_decode_fetch_frame_offsets(ctx, fo.data(), r.n_frames) != 0) { m->state = DS_ABORTED; return false; }
+    }
     const uint32_t ch = si.channels ? si.channels : m->channels;
+    auto queue_error = [&](int status) { PendingFrame pf; pf.blocksize = 0; pf.error = status; m->ready.push_back(std::move(pf)); };
+    auto queue_events = [&](uint32_t before_frame) {
+        for (uint32_t k = 0; k < si.n_events && k < 16; k++) if (si.ev_frame[k] == before_frame) queue_error(si.ev_status[k]);
+    };
+    uint64_t at = 0;                                                   // sample position within this batch's PCM
+    uint32_t silence_bs = m->last_blocksize;
     for (uint32_t f = 0; f < si.n_frames; f++) {
+        queue_events(f);
+        // frames missing in front of this one stand as silence, in units of the previous frame's blocksize
+        for (uint64_t gap = fo[f] - at; gap > 0;) {
+            const uint32_t n = (uint32_t)((silence_bs && gap > silence_bs) ? silence_bs : gap);
+            PendingFrame pf; pf.blocksize = n; pf.planar.assign((size_t)n * ch, 0);
+            m->ready.push_back(std::move(pf));
+            gap -= n; at += n;
+        }
         PendingFrame pf; pf.blocksize = fs[f]; pf.planar.resize((size_t)fs[f] * ch);
-        for (uint32_t i = 0; i < fs[f]; i++) for (uint32_t c = 0; c < ch; c++) pf.planar[(size_t)c * fs[f] + i] = pcm[base + (size_t)i * ch + c];
-        base += (size_t)fs[f] * ch;
+        const int32_t* src = pcm.data() + (size_t)fo[f] * ch;
+        for (uint32_t i = 0; i < fs[f]; i++) for (uint32_t c = 0; c < ch; c++) pf.planar[(size_t)c * fs[f] + i] = src[(size_t)i * ch + c];
         m->ready.push_back(std::move(pf));
+        at = fo[f] + fs[f]; silence_bs = fs[f];
     }
+    queue_events(si.n_frames);
+    for (uint32_t k = 16; k < si.n_events; k++) queue_error(ERR_LOST_SYNC);       // beyond the log: reported, kind unknown
     if (si.n_frames) { m->channels = ch; if (si.sample_rate) m->sample_rate = si.sample_rate; if (si.bits_per_sample) m->bps = si.bits_per_sample; }
-    const size_t consumed = (size_t)si.consumed;
-    // what stopped the chain?
-    if (si.status == 7) report(d, ERR_FRAME_CRC_MISMATCH);
-    else if (si.status == 4) report(d, ERR_BAD_HEADER);
-    else if (si.status == 8) report(d, ERR_UNPARSEABLE_STREAM);
-    else if (si.status == 6 || si.status == 5) {
-        // no frame where one should start / frame cut short: fine while more input may come, LOST_SYNC at end of stream
-        if (m->eof && consumed < m->in.size()) report(d, ERR_LOST_SYNC);
+    m->have_last = si.have_last != 0; m->next_sample = si.next_sample; m->last_blocksize = si.last_blocksize;
+    if (si.status == 8) { queue_error(ERR_UNPARSEABLE_STREAM); }                  // a stream this build cannot represent
+    size_t drop = (size_t)si.consumed;
+    if (m->eof || si.status == 8) drop = m->in.size();
+    else if (si.n_frames == 0 && m->in.size() > (1u << 20)) {
+        // a megabyte without a single frame: report the lost sync and keep only what a sync code could straddle
+        queue_error(ERR_LOST_SYNC);
+        drop = m->in.size() - 16;
     }
-    size_t drop = consumed;
-    if (si.status == 7 || si.status == 4 || si.status == 8) drop = m->in.size();      // unrecoverable here: discard the slice
-    else if (si.status == 6 && !m->eof && consumed < m->in.size()) {
-        // garbage where a frame should start: skip to the last few bytes (a sync code may straddle the slice end)
-        if (si.n_frames == 0 && m->in.size() > 65536) { report(d, ERR_LOST_SYNC); drop = m->in.size() - 16; }
-    }
-    if (m->eof && (si.status == 6 || si.status == 5)) drop = m->in.size();
     m->in.erase(m->in.begin(), m->in.begin() + (long)drop);
     m->bytes_consumed += drop;
     return true;
@@ -183,6 +210,12 @@ bool decode_buffered(FLAC__StreamDecoder* d) {
 bool deliver_one(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
     PendingFrame& pf = m->ready.front();
+    if (pf.error >= 0) {                                                // an error event in its place between the frames
+        const int status = pf.error;
+        m->ready.pop_front();
+        report(d, status);
+        return m->state != DS_ABORTED;
+    }
     const int32_t* planes[8] = {nullptr};
     for (uint32_t c = 0; c < m->channels && c < 8; c++) planes[c] = pf.planar.data() + (size_t)c * pf.blocksize;
     memset(&m->frame.header, 0, sizeof m->frame.header);
@@ -257,7 +290,8 @@ FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder* d
 static int init_common(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
     m->in.clear(); m->eof = false; m->metadata_done = false; m->ready.clear(); m->frame_index = 0; m->bytes_consumed = 0;
-    m->sample_rate = m->channels = m->bps = m->blocksize = 0; m->total_samples = 0;
+    m->sample_rate = m->channels = m->bps = m->blocksize = 0; m->total_samples = 0; m->min_blocksize = 0;
+    m->have_last = false; m->next_sample = 0; m->last_blocksize = 0;
     {
         std::lock_guard<std::mutex> lk(g_dec_mu);
         if (!dec_ctx()) { m->state = DS_MEMORY_ALLOCATION_ERROR; return DI_MEMORY_ALLOCATION_ERROR; }     // no CUDA device: fail loudly, no CPU fallback

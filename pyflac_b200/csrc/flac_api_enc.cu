@@ -10,6 +10,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <vector>
 
@@ -86,13 +90,167 @@ struct Md5 {
     }
 };
 
-// one engine context per process for the handle API, created on first use
-std::mutex g_mu;
-flacb200_ctx* g_ctx = nullptr;
-int g_ctx_rc = -1;
-flacb200_ctx* shared_ctx() {
-    if (g_ctx_rc == -1) g_ctx_rc = flacb200_create(&g_ctx, 0);
-    return g_ctx_rc == 0 ? g_ctx : nullptr;
+// ------------------------------------------------------------------------------------------------ dispatcher
+// pyFLAC runs one FLAC__StreamEncoder per stream and, for many streams, one thread per encoder
+// (/root/reference/pyflac/encoder.py:293-330; libFLAC handles are independent).  A GPU wants the opposite:
+// many streams per launch.  The dispatcher sits between the two: every process_interleaved() / finish() that has whole
+// frames to encode submits a job and blocks; the first submitter becomes the leader, waits a short gather window for the
+// other handles that are in flight, encodes ALL compatible jobs (same settings) in ONE flacb200_encode_batch call and hands
+// every job its own frames.  Each caller then fires its write callbacks on its own thread, outside any lock -- a callback
+// may use another encoder.  One dispatcher (and one engine context) per CUDA device; handles pick a device from
+// FLACB200_DEVICE (one index) or round-robin over FLACB200_DEVICES (comma separated list).
+struct EncJob {
+    // in
+    flacb200_enc_config cfg; const int32_t* pcm; uint64_t n; uint32_t ffn; uint8_t prev_ca; bool loose, verify;
+    // out
+    std::vector<uint8_t> bytes; std::vector<uint32_t> flen, fsmp; uint8_t last_ca = 0;
+    int rc = 0;                 // 0 ok, 1 engine error, 2 verify decoder error, 3 verify mismatch
+    uint64_t v_sample = 0; uint32_t v_channel = 0; int32_t v_expected = 0, v_got = 0;
+    bool done = false;
+};
+
+struct Dispatcher {
+    std::mutex mu; std::condition_variable cv;
+    std::deque<EncJob*> q;
+    bool running = false;
+    int device = 0; flacb200_ctx* ctx = nullptr; int ctx_rc = -1;
+    std::atomic<int> active{0};                 // initialised encoder handles on this device
+    // leader-only scratch (pinned)
+    void* h_pcm = nullptr; size_t h_pcm_cap = 0;
+    std::vector<uint8_t> arena; std::vector<uint64_t> foff; std::vector<uint32_t> flen, fsmp, fstream; std::vector<uint8_t> ca;
+    uint64_t batches = 0, jobs = 0;
+    int gather_us = 400;                        // adaptive: halves whenever a window closes with a single job, back to 400 when a batch had company
+
+    flacb200_ctx* context() {
+        if (ctx_rc == -1) ctx_rc = flacb200_create(&ctx, device);
+        return ctx_rc == 0 ? ctx : nullptr;
+    }
+    static bool same_key(const flacb200_enc_config& a, const flacb200_enc_config& b) { return memcmp(&a, &b, sizeof a) == 0; }
+
+    void run(std::vector<EncJob*>& B);
+    void submit(EncJob* job) {
+        std::unique_lock<std::mutex> lk(mu);
+        q.push_back(job);
+        cv.notify_all();
+        while (!job->done) {
+            if (running) { cv.wait(lk); continue; }
+            running = true;                                   // this thread leads one batch
+            const int others = active.load();
+            if (others > 1 && gather_us > 0 && !getenv("FLACB200_NO_GATHER")) {
+                // gather window: the other handles of this device are probably about to submit too (while a batch runs,
+                // later submissions queue up and form the next batch by themselves; the window only helps the first one)
+                const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(gather_us);
+                while ((int)q.size() < others && cv.wait_until(lk, deadline) != std::cv_status::timeout) {}
+            }
+            std::vector<EncJob*> B;
+            const flacb200_enc_config key = q.front()->cfg;
+            for (auto it = q.begin(); it != q.end();) { if (same_key((*it)->cfg, key) && (*it)->loose == q.front()->loose) { B.push_back(*it); it = q.erase(it); } else ++it; }
+            lk.unlock();
+            run(B);
+            lk.lock();
+            for (EncJob* j : B) j->done = true;
+            batches++; jobs += B.size();
+            gather_us = (B.size() > 1 || !q.empty()) ? 400 : gather_us / 2;
+            running = false;
+            cv.notify_all();
+        }
+    }
+};
+
+void Dispatcher::run(std::vector<EncJob*>& B) {
+    auto fail_all = [&](int rc) { for (EncJob* j : B) j->rc = rc; };
+    flacb200_ctx* c = context();
+    if (!c) { fail_all(1); return; }
+    cudaSetDevice(device);
+    flacb200_enc_config cfg = B[0]->cfg;
+    const uint32_t ch = cfg.channels;
+    const bool narrow = cfg.bits_per_sample <= 16;            // int16 container: half the H2D bytes, and 16-bit stereo takes the TMA-staged kernels
+    cfg.container_bytes = narrow ? 2u : 4u;
+    const size_t ns = B.size();
+    std::vector<uint64_t> off(ns), cnt(ns); std::vector<uint32_t> ffn(ns); std::vector<uint8_t> prev(ns);
+    uint64_t elems = 0;
+    for (size_t s = 0; s < ns; s++) { off[s] = elems; cnt[s] = B[s]->n; ffn[s] = B[s]->ffn; prev[s] = B[s]->prev_ca; elems += B[s]->n * ch; }
+    const size_t bytes = (size_t)elems * cfg.container_bytes;
+    if (bytes > h_pcm_cap) {
+        if (h_pcm) cudaFreeHost(h_pcm);
+        h_pcm = nullptr; h_pcm_cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        if (cudaHostAlloc(&h_pcm, want, cudaHostAllocDefault) != cudaSuccess) { fail_all(1); return; }
+        h_pcm_cap = want;
+    }
+    for (size_t s = 0; s < ns; s++) {
+        const size_t n = (size_t)B[s]->n * ch;
+        if (narrow) { int16_t* d = (int16_t*)h_pcm + off[s]; const int32_t* x = B[s]->pcm; for (size_t i = 0; i < n; i++) d[i] = (int16_t)x[i]; }
+        else memcpy((int32_t*)h_pcm + off[s], B[s]->pcm, n * 4);
+    }
+    if (B[0]->loose && flacb200_encode_set_prev_assignment(c, prev.data(), (uint32_t)ns) != 0) { fail_all(1); return; }
+    if (flacb200_encode_batch(c, &cfg, h_pcm, 0, elems, (uint32_t)ns, off.data(), cnt.data(), ffn.data()) != 0) { fail_all(1); return; }
+    flacb200_enc_result r;
+    if (flacb200_encode_result(c, &r) != 0) { fail_all(1); return; }
+    arena.resize(r.total_bytes ? r.total_bytes : 1); foff.resize(r.n_frames); flen.resize(r.n_frames); fsmp.resize(r.n_frames); fstream.resize(r.n_frames);
+    if (flacb200_encode_fetch(c, arena.data(), arena.size(), foff.data(), flen.data(), fsmp.data(), fstream.data(), nullptr) != 0) { fail_all(1); return; }
+    if (B[0]->loose && r.n_frames) { ca.resize(r.n_frames); if (flacb200_encode_fetch_assignments(c, ca.data(), ca.size()) != 0) { fail_all(1); return; } }
+    // frames are ordered by stream: hand every job its own
+    uint32_t f = 0;
+    for (size_t s = 0; s < ns; s++) {
+        EncJob* j = B[s];
+        j->flen.clear(); j->fsmp.clear(); j->bytes.clear();
+        const uint32_t f0 = f;
+        while (f < r.n_frames && fstream[f] == s) f++;
+        if (f > f0) {
+            const uint64_t b0 = foff[f0], b1 = foff[f - 1] + flen[f - 1];
+            j->bytes.assign(arena.begin() + (long)b0, arena.begin() + (long)b1);
+            j->flen.assign(flen.begin() + f0, flen.begin() + f); j->fsmp.assign(fsmp.begin() + f0, fsmp.begin() + f);
+            if (B[0]->loose) j->last_ca = ca[f - 1];
+        }
+    }
+    // up: verify_write_callback_ / FLAC__stream_encoder_set_verify (stream_encoder.h:781-801): every frame is decoded again (here:
+    // all verifying jobs of the batch in one GPU decode, headerless mode) and compared with the input before it is delivered
+    std::vector<EncJob*> V;
+    for (EncJob* j : B) if (j->verify && !j->flen.empty()) V.push_back(j);
+    if (!V.empty()) {
+        std::vector<uint8_t> blob; std::vector<uint64_t> boff(V.size()), blen(V.size());
+        for (size_t v = 0; v < V.size(); v++) { boff[v] = blob.size(); blen[v] = V[v]->bytes.size(); blob.insert(blob.end(), V[v]->bytes.begin(), V[v]->bytes.end()); }
+        blob.resize(blob.size() + 16, 0);
+        flacb200_dec_raw_params rp; memset(&rp, 0, sizeof rp); rp.sample_rate = cfg.sample_rate; rp.channels = ch; rp.bits_per_sample = cfg.bits_per_sample; rp.fixed_blocksize = cfg.blocksize;
+        std::vector<flacb200_dec_stream_info> di(V.size());
+        uint64_t tot = 0; for (EncJob* j : V) tot += j->n * ch;
+        std::vector<int32_t> back((size_t)tot + 1);
+        if (flacb200_decode_batch(c, blob.data(), 0, blob.size() - 16, (uint32_t)V.size(), boff.data(), blen.data(), 4, &rp) != 0 ||
+            flacb200_decode_fetch(c, back.data(), back.size() * 4, di.data(), nullptr, 0) != 0) { for (EncJob* j : V) j->rc = 2; return; }
+        for (size_t v = 0; v < V.size(); v++) {
+            EncJob* j = V[v];
+            if (di[v].status != 0) { j->rc = 2; continue; }
+            const int32_t* got = back.data() + di[v].pcm_off;
+            bool same = di[v].total_samples == j->n;
+            const size_t n = (size_t)j->n * ch;
+            for (size_t i = 0; same && i < n; i++)
+                if (got[i] != j->pcm[i]) { same = false; j->v_sample = i / ch; j->v_channel = (uint32_t)(i % ch); j->v_expected = j->pcm[i]; j->v_got = got[i]; }
+            if (!same) j->rc = 3;
+        }
+    }
+}
+
+std::mutex g_disp_mu;
+std::vector<Dispatcher*> g_disp;               // index = CUDA device
+std::atomic<unsigned> g_rr{0};
+
+// device for a new handle: FLACB200_DEVICE=<i>, or round robin over FLACB200_DEVICES=<i,j,...>; default 0
+int pick_device() {
+    if (const char* l = getenv("FLACB200_DEVICES")) {
+        std::vector<int> d; const char* p = l;
+        while (*p) { char* e; const long v = strtol(p, &e, 10); if (e == p) break; d.push_back((int)v); p = (*e == ',') ? e + 1 : e; }
+        if (!d.empty()) return d[g_rr.fetch_add(1) % d.size()];
+    }
+    if (const char* l = getenv("FLACB200_DEVICE")) return atoi(l);
+    return 0;
+}
+Dispatcher* dispatcher(int device) {
+    std::lock_guard<std::mutex> lk(g_disp_mu);
+    if (device < 0) device = 0;
+    if ((size_t)device >= g_disp.size()) g_disp.resize((size_t)device + 1, nullptr);
+    if (!g_disp[device]) { g_disp[device] = new Dispatcher(); g_disp[device]->device = device; }
+    return g_disp[device];
 }
 
 struct EncImpl {
@@ -110,6 +268,7 @@ struct EncImpl {
     FILE* file = nullptr; bool own_file = false;
     uint32_t N = 0;                        // resolved blocksize
     std::vector<int32_t> pending;          // interleaved samples not yet framed
+    Dispatcher* disp = nullptr; bool counted = false;      // this handle's device queue; counted in disp->active while initialised
     uint32_t frame_number = 0;
     uint8_t last_ca = 0;                   // loose mid/side: channel assignment of the last frame delivered
     uint64_t vstat_sample = 0; uint32_t vstat_channel = 0; int32_t vstat_expected = 0, vstat_got = 0;   // verify mismatch report
@@ -165,63 +324,43 @@ bool deliver(FLAC__StreamEncoder* e, const uint8_t* buf, size_t bytes, uint32_t 
     return true;
 }
 
-// encode `n` pending inter-channel samples (whole frames, or everything at finish) in one GPU batch
+// encode `n` pending inter-channel samples (whole frames, or everything at finish): one job for the device's dispatcher,
+// which batches it with whatever the other handles have submitted; then MD5 and callbacks on this thread, no lock held
 bool encode_pending(FLAC__StreamEncoder* e, uint64_t n) {
     EncImpl* m = I(e);
     if (n == 0) return true;
-    std::lock_guard<std::mutex> lk(g_mu);
-    flacb200_ctx* ctx = shared_ctx();
-    if (!ctx) { m->state = ST_MEMORY_ALLOCATION_ERROR; return false; }
-    flacb200_enc_config cfg{};
-    cfg.sample_rate = m->sample_rate; cfg.channels = m->channels; cfg.bits_per_sample = m->bps;
-    cfg.compression_level = m->level; cfg.blocksize = m->N; cfg.container_bytes = 4;
-    cfg.write_prologue = 0; cfg.do_md5 = 0; cfg.streamable_subset = 0; cfg.debug_trace = 0;
-    cfg.limit_min_bitrate = m->limit_min_bitrate ? 1u : 0u;
-    const uint64_t off = 0, cnt = n; const uint32_t ffn = m->frame_number;
-    const bool loose = (m->level == 1 || m->level == 4) && m->channels == 2;
-    if (loose && flacb200_encode_set_prev_assignment(ctx, &m->last_ca, 1) != 0) { m->state = ST_FRAMING_ERROR; return false; }
-    if (flacb200_encode_batch(ctx, &cfg, m->pending.data(), 0, n * m->channels, 1, &off, &cnt, &ffn) != 0) { m->state = ST_FRAMING_ERROR; return false; }
-    flacb200_enc_result r;
-    if (flacb200_encode_result(ctx, &r) != 0) { m->state = ST_FRAMING_ERROR; return false; }
-    m->arena.resize(r.total_bytes ? r.total_bytes : 1); m->foff.resize(r.n_frames); m->flen.resize(r.n_frames); m->fsmp.resize(r.n_frames);
-    if (flacb200_encode_fetch(ctx, m->arena.data(), m->arena.size(), m->foff.data(), m->flen.data(), m->fsmp.data(), nullptr, nullptr) != 0) { m->state = ST_FRAMING_ERROR; return false; }
+    if (!m->disp) { m->state = ST_MEMORY_ALLOCATION_ERROR; return false; }
+    EncJob job;
+    memset(&job.cfg, 0, sizeof job.cfg);
+    job.cfg.sample_rate = m->sample_rate; job.cfg.channels = m->channels; job.cfg.bits_per_sample = m->bps;
+    job.cfg.compression_level = m->level; job.cfg.blocksize = m->N; job.cfg.container_bytes = 4;
+    job.cfg.write_prologue = 0; job.cfg.do_md5 = 0; job.cfg.streamable_subset = 0; job.cfg.debug_trace = 0;
+    job.cfg.limit_min_bitrate = m->limit_min_bitrate ? 1u : 0u;
+    job.pcm = m->pending.data(); job.n = n; job.ffn = m->frame_number; job.prev_ca = m->last_ca;
+    job.loose = (m->level == 1 || m->level == 4) && m->channels == 2;
+    job.verify = m->verify != 0;
+    m->disp->submit(&job);
+    if (job.rc == 1) { m->state = ST_FRAMING_ERROR; return false; }
     // MD5 over (bps+7)/8 little-endian bytes per sample, interleaved (up: md5.c FLAC__MD5Accumulate)
     {
         const uint32_t bytes = (m->bps + 7) / 8;
         const size_t vals = (size_t)n * m->channels;
         std::vector<uint8_t> tmp(vals * bytes);
         size_t k = 0;
-        for (size_t i = 0; i < vals; i++) { const uint32_t v = (uint32_t)m->pending[i]; for (uint32_t b = 0; b < bytes; b++) tmp[k++] = (uint8_t)(v >> (8 * b)); }
+        if (bytes == 2) for (size_t i = 0; i < vals; i++) { const uint32_t v = (uint32_t)m->pending[i]; tmp[k++] = (uint8_t)v; tmp[k++] = (uint8_t)(v >> 8); }
+        else for (size_t i = 0; i < vals; i++) { const uint32_t v = (uint32_t)m->pending[i]; for (uint32_t b = 0; b < bytes; b++) tmp[k++] = (uint8_t)(v >> (8 * b)); }
         m->md5.update(tmp.data(), tmp.size());
     }
-    // up: verify_write_callback_ / FLAC__stream_encoder_set_verify (stream_encoder.h:781-801): every frame is decoded again
-    // (here: the whole batch through the GPU decoder, headerless mode) and compared with the input before it is delivered
-    if (m->verify && r.n_frames) {
-        flacb200_dec_raw_params rp; rp.sample_rate = m->sample_rate; rp.channels = m->channels; rp.bits_per_sample = m->bps;
-        const uint64_t boff = 0, blen = r.total_bytes;
-        std::vector<uint8_t> padded(m->arena.begin(), m->arena.begin() + r.total_bytes);
-        padded.resize(r.total_bytes + 16, 0);
-        std::vector<int32_t> back((size_t)n * m->channels);
-        flacb200_dec_stream_info di{};
-        if (flacb200_decode_batch(ctx, padded.data(), 0, blen, 1, &boff, &blen, 4, &rp) != 0 ||
-            flacb200_decode_fetch(ctx, back.data(), back.size() * 4, &di, nullptr, 0) != 0 || di.status != 0) { m->state = ST_VERIFY_DECODER_ERROR; return false; }
-        bool same = di.total_samples == n;
-        for (size_t i = 0; same && i < back.size(); i++) {
-            if (back[i] != m->pending[i]) {
-                same = false;
-                m->vstat_sample = m->samples_written + i / m->channels; m->vstat_channel = (uint32_t)(i % m->channels);
-                m->vstat_expected = m->pending[i]; m->vstat_got = back[i];
-            }
-        }
-        if (!same) { m->state = ST_VERIFY_MISMATCH; return false; }
+    if (job.rc == 2) { m->state = ST_VERIFY_DECODER_ERROR; return false; }
+    if (job.rc == 3) {
+        m->vstat_sample = m->samples_written + job.v_sample; m->vstat_channel = job.v_channel; m->vstat_expected = job.v_expected; m->vstat_got = job.v_got;
+        m->state = ST_VERIFY_MISMATCH; return false;
     }
-    if (loose && r.n_frames) {
-        std::vector<uint8_t> ca(r.n_frames);
-        if (flacb200_encode_fetch_assignments(ctx, ca.data(), ca.size()) != 0) { m->state = ST_FRAMING_ERROR; return false; }
-        m->last_ca = ca.back();
-    }
-    for (uint32_t f = 0; f < r.n_frames; f++) {
-        if (!deliver(e, m->arena.data() + m->foff[f], m->flen[f], m->fsmp[f], m->frame_number)) return false;
+    if (job.loose && !job.flen.empty()) m->last_ca = job.last_ca;
+    size_t at = 0;
+    for (size_t f = 0; f < job.flen.size(); f++) {
+        if (!deliver(e, job.bytes.data() + at, job.flen[f], job.fsmp[f], m->frame_number)) return false;
+        at += job.flen[f];
         m->frame_number++;
     }
     m->pending.erase(m->pending.begin(), m->pending.begin() + (size_t)n * m->channels);
@@ -241,8 +380,11 @@ int init_common(FLAC__StreamEncoder* e) {
     // limits of this build fail loudly here instead of producing a different stream (DESIGN.md "limits")
     if (m->custom_tuning) { m->state = ST_FRAMING_ERROR; return INIT_ENCODER_ERROR; }
     {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (!shared_ctx()) { m->state = ST_MEMORY_ALLOCATION_ERROR; return INIT_ENCODER_ERROR; }   // no CUDA device: no CPU fallback
+        Dispatcher* d = dispatcher(pick_device());
+        std::lock_guard<std::mutex> lk(d->mu);
+        if (!d->context()) { m->state = ST_MEMORY_ALLOCATION_ERROR; return INIT_ENCODER_ERROR; }   // no CUDA device: no CPU fallback
+        m->disp = d;
+        if (!m->counted) { d->active.fetch_add(1); m->counted = true; }
     }
     m->pending.clear(); m->frame_number = 0; m->last_ca = 0; m->samples_written = 0; m->bytes_written = 0; m->min_fs = m->max_fs = 0; m->frames_written = 0; m->streaminfo_offset = 0;
     m->md5.init();
@@ -269,6 +411,15 @@ int init_common(FLAC__StreamEncoder* e) {
 }  // namespace
 
 extern "C" {
+
+// batches / jobs the encoder dispatcher of `device` has run so far (tests: cross-object batching really happens)
+int flacb200_dispatch_stats(int device, uint64_t* batches, uint64_t* jobs) {
+    Dispatcher* d = dispatcher(device);
+    std::lock_guard<std::mutex> lk(d->mu);
+    if (batches) *batches = d->batches;
+    if (jobs) *jobs = d->jobs;
+    return 0;
+}
 
 FLAC__StreamEncoder* FLAC__stream_encoder_new(void) {
     Handle* h = new Handle();
@@ -434,6 +585,7 @@ FLAC__bool FLAC__stream_encoder_finish(FLAC__StreamEncoder* e) {
     if (m->file && m->own_file) { if (m->file != stdout) fclose(m->file); }
     m->file = nullptr;
     m->pending.clear();
+    if (m->counted && m->disp) { m->disp->active.fetch_sub(1); m->counted = false; }
     reset_settings(m);                                         // stream_encoder.h:225-227: back to defaults
     m->state = ST_UNINITIALIZED;
     return ok ? 1 : 0;

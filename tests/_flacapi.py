@@ -140,7 +140,7 @@ def decode_session(L, data, read_chunk=8192):
                                                    DEC_WRITE_CB, C.c_void_p, DEC_ERROR_CB, C.c_void_p]
     L.FLAC__stream_decoder_init_stream.restype = C.c_int
     pos = [0]
-    blocks, frames, errors = [], [], []
+    blocks, frames, errors, events = [], [], [], []       # events: ('w', blocksize) / ('e', status) in callback order
 
     def r(dec, buf, pbytes, cd):
         want = min(pbytes[0], read_chunk)
@@ -161,15 +161,17 @@ def decode_session(L, data, read_chunk=8192):
         for c in range(h.channels):
             blk[:, c] = np.ctypeslib.as_array(buffers[c], shape=(h.blocksize,))
         blocks.append(blk)
+        events.append(('w', int(h.blocksize)))
         return 0
 
     def e(dec, status, cd):
         errors.append(status)
+        events.append(('e', int(status)))
 
     rcb, wcb, ecb = DEC_READ_CB(r), DEC_WRITE_CB(w), DEC_ERROR_CB(e)
     d = L.FLAC__stream_decoder_new()
     st = L.FLAC__stream_decoder_init_stream(d, rcb, None, None, None, None, wcb, None, ecb, None)
-    res = dict(init_status=st, frames=frames, errors=errors)
+    res = dict(init_status=st, frames=frames, errors=errors, events=events)
     if st == 0:
         res["ok"] = bool(L.FLAC__stream_decoder_process_until_end_of_stream(d))
         res["state"] = L.FLAC__stream_decoder_get_state(d)

@@ -1,4 +1,5 @@
 """GPU decode parity tests (pytest -m gpu): CUDA decode path through the C ABI vs the oracle / golden PCM."""
+import os
 import numpy as np
 import pytest
 
@@ -70,6 +71,77 @@ def test_decode_errors_are_reported(eng, checkers):
     assert infos[1].status != 0
     assert infos[2].status != 0 and infos[2].n_frames >= 1 and np.array_equal(out[2], x[: out[2].shape[0]])
     assert infos[3].status == 2
+
+
+def test_decode_error_recovery_matches_libflac(eng, checkers):
+    """Damaged streams through the drop-in StreamDecoder API of BOTH libraries (same ctypes driver, tests/_flacapi.py): the
+    error-callback sequence, its place between the write callbacks, the PCM (a frame with a bad CRC is never delivered,
+    missing frames come as silence of the previous blocksize, nothing is filled at the very start or end) and the final state
+    must equal libFLAC 1.4.3's (/root/reference/pyflac/include/FLAC/stream_decoder.h:431-448,1440-1460 document the
+    contract; the binary is the judge).  Read sizes of 8192 (libFLAC's own), 1000 and 1 MiB exercise the state carried from
+    one buffered slice to the next."""
+    import ctypes as C
+    from _flacapi import decode_session
+    from pyflac_b200 import _native as nat
+    if not checkers.ref_available():
+        pytest.skip("oracle/_ref not present")
+    ours = nat.lib()
+    ref = C.CDLL(os.path.join(os.path.dirname(checkers.REF_SO), "libFLAC-12.1.0.so"))
+    x = music_like(4096 * 8 + 321, 2, 44100, 16, seed=8)
+    data, off, ln, _ = checkers.ref_encode(x, 44100, 16, 5, 0, with_index=True)
+    off = [int(o) for o in off]
+    y = music_like(1152 * 6 + 100, 1, 48000, 16, seed=3)
+    data2, off2, _, _ = checkers.ref_encode(y, 48000, 16, 0, 0, with_index=True)
+
+    def flip(d, *positions):
+        b = bytearray(d)
+        for p in positions:
+            b[p] ^= 1
+        return bytes(b)
+    cases = {
+        "clean": data,
+        "payload bit in frame 2": flip(data, off[2] + 100),
+        "frames 2,3": flip(data, off[2] + 100, off[3] + 100),
+        "frames 2,3,4": flip(data, off[2] + 100, off[3] + 100, off[4] + 100),
+        "crc byte of frame 2": flip(data, off[3] - 1),
+        "frame 2 removed": data[:off[2]] + data[off[3]:],
+        "frames 2-4 removed": data[:off[2]] + data[off[5]:],
+        "frames 0,1 removed": data[:off[0]] + data[off[2]:],
+        "frame 1 repeated after frame 2": data[:off[3]] + data[off[1]:off[2]] + data[off[3]:],
+        "last full frame": flip(data, off[7] + 100),
+        "frames 6,7 then the short one": flip(data, off[6] + 100, off[7] + 100),
+        "frames 7,8 (the end)": flip(data, off[7] + 100, off[8] + 10),
+        "final short frame": flip(data, off[8] + 20),
+        "first frame": flip(data, off[0] + 50),
+        "frames 0 and 3": flip(data, off[0] + 50, off[3] + 60),
+        "199 junk bytes before frame 3": data[:off[3]] + bytes(range(1, 200)) + data[off[3]:],
+        "truncated inside frame 2": data[:off[2] + 300],
+        "truncated after frame 0": data[:off[1]],
+        "one byte short": data[:-1],
+        "trailing zeros": data + bytes(1000),
+        "trailing junk": data + b"ID3 junk" * 50,
+        "mono 1152 level 0, frames 1,2": flip(data2, int(off2[1]) + 50, int(off2[2]) + 50),
+    }
+    for name, blob in cases.items():
+        b = decode_session(ref, blob, 8192)
+        for chunk in (8192, 1000, 1 << 20):
+            a = decode_session(ours, blob, chunk)
+            assert a["events"] == b["events"], (name, chunk, a["events"], b["events"])
+            assert np.array_equal(a["pcm"], b["pcm"]), (name, chunk)
+            assert a["ok"] == b["ok"] and a["state"] == b["state"], (name, chunk)
+    # a flipped high bit usually derails the parse (reserved values, runaway unary codes): the kinds and count of errors then
+    # depend on false sync codes inside the damaged frame; what must hold is what was delivered
+    for k in (300, 1000, 5000):
+        b2 = bytearray(data); b2[off[2] + k] ^= 0x80
+        a, b = decode_session(ours, bytes(b2)), decode_session(ref, bytes(b2))
+        assert a["errors"] and np.array_equal(a["pcm"], b["pcm"]), k
+    # the batch ABI sees the same PCM, the first problem as status and the event log
+    out, infos = nat.decode_streams(eng, [cases["payload bit in frame 2"], cases["frame 2 removed"], cases["clean"]])
+    want = decode_session(ref, cases["payload bit in frame 2"])
+    assert infos[0].status == 7 and np.array_equal(out[0], want["pcm"]) and infos[0].gap_samples == 4096
+    assert [int(v) for v in infos[0].ev_status[:infos[0].n_events]] == [2, 0] and [int(v) for v in infos[0].ev_frame[:2]] == [2, 2]
+    assert infos[1].status == 0 and infos[1].gap_samples == 4096 and infos[1].n_events == 0 and out[1].shape[0] == len(x)
+    assert infos[2].status == 0 and infos[2].n_events == 0 and np.array_equal(out[2], x)
 
 
 def test_encode_decode_roundtrip_full_size(eng):

@@ -117,3 +117,88 @@ def test_stream_decoder_garbage_reports_error(ours):
     junk = np.random.default_rng(1).integers(0, 256, 100000).astype(np.uint8).tobytes()
     a = decode_session(ours, junk)
     assert a["errors"] and a["pcm"].shape[0] == 0
+
+
+def test_many_stream_encoders_on_threads_share_gpu_batches(checkers):
+    """BASELINE configs[1] the way pyFLAC users reach it: 256 StreamEncoder objects, one thread each
+    (/root/reference/pyflac/encoder.py:293-330).  The per-device dispatcher coalesces their concurrent process() calls into
+    shared GPU batches; every stream must still equal libFLAC's bytes, and the threaded run must beat the same 256 encoders
+    run one after the other (one-stream batches) by a wide margin."""
+    import ctypes as C
+    import threading
+    import time
+    import pyflac_b200 as pf
+    from pyflac_b200 import _native as nat
+    from pyflac_b200.synth import music_like
+    n_enc, n = 256, 4096 * 24 + 500
+    xs = [music_like(n, 2, 48000, 16, seed=7000 + s) for s in range(n_enc)]
+    want = [checkers.oracle_encode(x, 48000, 16, 5, 0, seekable=False) for x in xs[:8]]
+
+    def run(threaded):
+        outs = [bytearray() for _ in range(n_enc)]
+        encs = [pf.StreamEncoder(48000, (lambda b, nb, ns, fr, o=outs[s]: o.extend(b)), compression_level=5) for s in range(n_enc)]
+
+        def work(s):
+            for i in range(0, n, 4096 * 8):               # three process() calls per stream, then finish()
+                encs[s].process(xs[s][i:i + 4096 * 8])
+            assert encs[s].finish() is True
+        t0 = time.perf_counter()
+        if threaded:
+            th = [threading.Thread(target=work, args=(s,)) for s in range(n_enc)]
+            [t.start() for t in th]
+            [t.join(120) for t in th]
+            assert not any(t.is_alive() for t in th)
+        else:
+            for s in range(n_enc):
+                work(s)
+        return time.perf_counter() - t0, outs
+
+    L = nat.lib()
+    L.flacb200_dispatch_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    b0, j0, b1, j1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    run(True)                                               # warm-up: contexts, pinned buffers, kernels
+    L.flacb200_dispatch_stats(0, C.byref(b0), C.byref(j0))
+    t_thr, outs = run(True)
+    L.flacb200_dispatch_stats(0, C.byref(b1), C.byref(j1))
+    t_seq, outs_seq = run(False)
+    for s in range(8):
+        assert bytes(outs[s]) == want[s] == bytes(outs_seq[s]), s
+    for s in range(n_enc):
+        assert outs[s] == outs_seq[s], s
+    jobs, batches = j1.value - j0.value, b1.value - b0.value
+    assert jobs >= n_enc * 4
+    print(f"\n256 StreamEncoders: threaded {t_thr * 1e3:.1f} ms ({batches} GPU batches for {jobs} jobs), one after the other {t_seq * 1e3:.1f} ms")
+    assert batches * 4 <= jobs                             # at least four handles per batch on average
+    assert t_thr * 3 < t_seq
+
+
+def test_write_callback_may_drive_another_encoder(checkers):
+    """Callbacks run outside every library lock (libFLAC handles are independent): a write callback that
+    feeds a second encoder must not deadlock."""
+    import threading
+    import pyflac_b200 as pf
+    from pyflac_b200.synth import music_like
+    x = music_like(4096 * 6 + 11, 2, 44100, 16, seed=11)
+    y = music_like(4096 * 2, 1, 44100, 16, seed=12)
+    inner_out, outer_out, fed = bytearray(), bytearray(), [0]
+    inner = pf.StreamEncoder(44100, lambda b, nb, ns, fr: inner_out.extend(b), compression_level=3)
+
+    def outer_cb(b, nb, ns, fr):
+        outer_out.extend(b)
+        if ns and fed[0] < len(y):                          # every audio frame of the outer stream feeds the inner encoder
+            inner.process(y[fed[0]:fed[0] + 2048])
+            fed[0] += 2048
+    outer = pf.StreamEncoder(44100, outer_cb, compression_level=5)
+    done = []
+
+    def work():
+        outer.process(x)
+        outer.finish()
+        inner.finish()
+        done.append(True)
+    t = threading.Thread(target=work, daemon=True)
+    t.start()
+    t.join(60)
+    assert done, "deadlock: a write callback could not use another encoder"
+    assert bytes(outer_out) == checkers.oracle_encode(x, 44100, 16, 5, 0, seekable=False)
+    assert bytes(inner_out) == checkers.oracle_encode(y[:fed[0]], 44100, 16, 3, 0, seekable=False)
