@@ -449,6 +449,11 @@ __device__ void md5_block(uint32_t h[4], const uint32_t w[16]) {
     h[0] += a; h[1] += b; h[2] += c; h[3] += d;
 }
 
+__device__ __forceinline__ void md5_block4(uint32_t h[4], const uint4& n0, const uint4& n1, const uint4& n2, const uint4& n3) {
+    const uint32_t w[16] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, n3.z, n3.w};
+    md5_block(h, w);
+}
+
 // Generic feeder: packs (bps+7)/8 little-endian bytes of each sample into 32-bit words, one sample at a time.
 struct Md5Feeder {
     uint32_t h[4]; uint32_t w[16]; uint64_t acc; uint32_t accbits, widx;
@@ -476,34 +481,96 @@ struct Md5Feeder {
     }
 };
 
-// One thread per stream.  Fast path (the container bytes ARE the hashed bytes: int16 container with 16-bit
-// samples, int32 with 32-bit): 64-byte blocks are fetched with four 16-byte loads and the next block is
-// prefetched while the current one is hashed, so the serial MD5 chain (about 16 dependent-issue cycles per
-// step, 64 steps per block) is the only thing on the critical path.
-template <typename PcmT>
-__global__ void md5_kernel(const PcmT* __restrict__ pcm, const uint64_t* __restrict__ stream_pcm_off,
+// One thread per stream, one warp (32 streams) per CTA.  Fast paths: the container bytes ARE the hashed bytes (int16
+// container with 16-bit samples, int32 with 32-bit), or 24-bit samples in an int32 container (three of every four bytes,
+// gathered with one PRMT per hashed word).  The chain's static schedule is 12 cycles per step (LEA.HI -> LOP3 -> IADD3),
+// 768 cycles per 64-byte block -- about one DRAM round trip, and the instructions that feed it sit in the same in-order
+// issue stream, so: the bytes travel global -> shared with cp.async in 256-byte pieces per stream (half a warp copies one
+// stream's piece: whole 128-byte lines instead of 32 scattered 16-byte sectors per request), kMd5Ring pieces deep, from
+// register-resident source addresses (three instructions per copy); each lane reads its own row back 16 bytes at a time
+// (row stride 272 bytes: the eight lanes of an LDS.128 phase fall in distinct banks).  Measured on the bench batch
+// (256 streams of 1.92 MB): 21.1 ms with per-lane loads one block ahead -> 15.6 ms.
+constexpr int kMd5Piece = 256, kMd5Row = kMd5Piece + 16, kMd5Ring = 4;
+template <typename PcmT, bool K24>
+__global__ void __launch_bounds__(32) md5_kernel(const PcmT* __restrict__ pcm, const uint64_t* __restrict__ stream_pcm_off,
                            const uint64_t* __restrict__ stream_samples, int n_streams, uint32_t channels, uint32_t bps,
                            uint8_t* __restrict__ digest_out) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_streams) return;
+    __shared__ __align__(16) uint8_t ring[kMd5Ring][32][kMd5Row];
+    const int lane = threadIdx.x, s = blockIdx.x * 32 + lane;
+    const bool live = s < n_streams;
     const uint32_t bytes_per = (bps + 7) / 8;
-    const PcmT* p = pcm + stream_pcm_off[s];
-    const uint64_t nvals = stream_samples[s] * channels;
+    const PcmT* p = pcm + (live ? stream_pcm_off[s] : 0ull);
+    const uint64_t nvals = live ? stream_samples[s] * channels : 0ull;
     Md5Feeder f; f.init();
-    uint64_t i = 0;
-    if (bytes_per == sizeof(PcmT) && (((uintptr_t)p) & 15u) == 0) {
-        const uint64_t nblocks = (nvals * sizeof(PcmT)) / 64;
-        const uint4* p4 = reinterpret_cast<const uint4*>(p);
-        uint4 n0, n1, n2, n3;
-        if (nblocks) { n0 = __ldg(p4); n1 = __ldg(p4 + 1); n2 = __ldg(p4 + 2); n3 = __ldg(p4 + 3); }
-        for (uint64_t b = 0; b < nblocks; b++) {
-            uint32_t w[16] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, n3.z, n3.w};
-            if (b + 1 < nblocks) { const uint4* q4 = p4 + 4 * (b + 1); n0 = __ldg(q4); n1 = __ldg(q4 + 1); n2 = __ldg(q4 + 2); n3 = __ldg(q4 + 3); }
-            md5_block(f.h, w);
-        }
-        i = nblocks * (64 / sizeof(PcmT));
+    const bool fast = live && bytes_per == (K24 ? 3u : (uint32_t)sizeof(PcmT)) && (((uintptr_t)p) & 15u) == 0;
+    const uint64_t np_own = fast ? (nvals * sizeof(PcmT)) / kMd5Piece : 0ull;     // whole pieces of this lane's stream
+    uint64_t np_max = np_own, np_all = np_own;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const uint64_t v = __shfl_xor_sync(0xffffffffu, np_max, o), u = __shfl_xor_sync(0xffffffffu, np_all, o);
+        np_max = v > np_max ? v : np_max; np_all = u < np_all ? u : np_all;
     }
-    for (; i < nvals; i++) f.push((uint32_t)(int)__ldg(p + i), bytes_per);
+    if (np_max) {                                                          // warp-uniform
+        const int half = lane >> 4, l16 = lane & 15;
+        // Copy duty of a lane: 16 bytes of the piece of streams 2j + half, j = 0..15.  Pieces that every stream of the warp
+        // has (q < np_all) are requested with no per-stream test.
+        uint64_t src[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) src[j] = __shfl_sync(0xffffffffu, (uint64_t)(uintptr_t)p, 2 * j + half) + (uint64_t)l16 * 16;
+        auto request = [&](uint64_t q) {
+            const int slot = (int)(q % kMd5Ring);
+            const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(&ring[slot][half][l16 * 16]);
+            if (q < np_all) {
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst0 + (uint32_t)(2 * j * kMd5Row)), "l"(src[j] + q * kMd5Piece) : "memory");
+            } else if (q < np_max) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint64_t np = __shfl_sync(0xffffffffu, np_own, 2 * j + half);
+                    if (q < np)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst0 + (uint32_t)(2 * j * kMd5Row)), "l"(src[j] + q * kMd5Piece) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");            // requests past the end commit empty groups
+        };
+        for (int q = 0; q < kMd5Ring - 1; q++) request((uint64_t)q);
+        for (uint64_t q = 0; q < np_max; q++) {
+            asm volatile("cp.async.wait_group %0;" :: "n"(kMd5Ring - 2) : "memory");
+            __syncwarp();
+            const uint4* row = reinterpret_cast<const uint4*>(&ring[q % kMd5Ring][lane][0]);
+            if (q < np_own) {                                              // uniform while q < np_all
+                if (K24) {
+                    // 64 samples = 192 hashed bytes = three blocks; four samples (one 16-byte read) give three words
+                    uint32_t w[48];
+#pragma unroll
+                    for (int g = 0; g < 16; g++) {
+                        const uint4 x = row[g];
+                        w[3 * g] = __byte_perm(x.x, x.y, 0x4210); w[3 * g + 1] = __byte_perm(x.y, x.z, 0x5421); w[3 * g + 2] = __byte_perm(x.z, x.w, 0x6542);
+                    }
+                    md5_block(f.h, w); md5_block(f.h, w + 16); md5_block(f.h, w + 32);
+                } else {
+                    // four blocks; the words of the next block are read while this one is hashed, two blocks per trip so that the
+                    // two register sets alternate without moves
+                    uint4 a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3];
+#pragma unroll 1
+                    for (int k = 0; k < 4; k += 2) {
+                        const uint4 b0 = row[4 * k + 4], b1 = row[4 * k + 5], b2 = row[4 * k + 6], b3 = row[4 * k + 7];
+                        md5_block4(f.h, a0, a1, a2, a3);
+                        const int kn = (k + 2) & 3;
+                        a0 = row[4 * kn]; a1 = row[4 * kn + 1]; a2 = row[4 * kn + 2]; a3 = row[4 * kn + 3];
+                        md5_block4(f.h, b0, b1, b2, b3);
+                    }
+                }
+            }
+            __syncwarp();                                                  // every lane is done with the slot the next request refills
+            request(q + kMd5Ring - 1);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    if (!live) return;
+    // what the pieces did not cover (everything, for other container / sample-size pairs) goes through the generic feeder
+    for (uint64_t i = np_own * (kMd5Piece / sizeof(PcmT)); i < nvals; i++) f.push((uint32_t)(int)__ldg(p + i), bytes_per);
     f.finish(nvals * bytes_per, digest_out + (size_t)s * 16);
 }
 
@@ -511,8 +578,9 @@ void launch_md5(const void* pcm, uint32_t container_bytes, const uint64_t* strea
                 int n_streams, uint32_t channels, uint32_t bps, uint8_t* digest_out, cudaStream_t stream) {
     // one warp per CTA: the chains are latency-bound, spreading them over SMs costs nothing
     const int threads = 32, blocks = (n_streams + threads - 1) / threads;
-    if (container_bytes == 2) md5_kernel<int16_t><<<blocks, threads, 0, stream>>>((const int16_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
-    else md5_kernel<int32_t><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
+    if (container_bytes == 2) md5_kernel<int16_t, false><<<blocks, threads, 0, stream>>>((const int16_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
+    else if ((bps + 7) / 8 == 3) md5_kernel<int32_t, true><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
+    else md5_kernel<int32_t, false><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
 }
 
 // The MD5 chain of a batch ends long after its frames are final: the digests are patched into the finished stream

@@ -349,3 +349,29 @@ def test_full_size_config3_24bit_mono_level8(eng, checkers):
         x = uniq[s % 64].astype("<i4").tobytes()
         le24 = b"".join(x[i:i + 3] for i in range(0, len(x), 4))
         assert bytes(out["streams"][s].md5) == hashlib.md5(le24).digest()
+
+
+@pytest.mark.parametrize("bps,ch", [(16, 2), (24, 1), (24, 2), (32, 2), (8, 1), (12, 2), (20, 1)])
+def test_md5_ragged_batch(eng, bps, ch):
+    """md5_kernel: 40 streams of one batch with lengths around every boundary of its staging (0 whole 256-byte pieces, one,
+    many; tails of 0..63 bytes; more than a warp of streams), odd element offsets that break the 16-byte alignment of some
+    streams, each sample size in its container.  The digest must be MD5 of the samples as little-endian (bps+7)/8-byte values."""
+    from pyflac_b200 import _native as nat
+    rng = np.random.default_rng(bps * 10 + ch)
+    dt = np.int16 if bps <= 16 else np.int32
+    lens = [1, 2, 15, 16, 21, 22, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 1000, 4096, 4097, 5000, 8192, 12345,
+            20000, 3, 64, 640, 6400, 30001, 17, 170, 1700, 17000, 99, 999, 9999, 4095, 8191, 16383]
+    xs = [rng.integers(-(1 << (bps - 1)), 1 << (bps - 1), size=(n, ch), dtype=np.int64).astype(dt) for n in lens]
+    pad = [0, 1, 3, 0, 5, 0, 0, 7] * 5                           # elements of slack before each stream: some starts are misaligned
+    parts, offs, pos = [], [], 0
+    for x, g in zip(xs, pad):
+        parts.append(np.zeros(g, dt)); pos += g
+        offs.append(pos); parts.append(x.reshape(-1)); pos += x.size
+    flat = np.concatenate(parts)
+    cfg = nat.Engine.make_config(48000, ch, bps, 2, 0)
+    eng.encode_host(cfg, flat, np.array(offs, np.uint64), np.array(lens, np.uint64))
+    out = eng.fetch()
+    nb = (bps + 7) // 8
+    for s, x in enumerate(xs):
+        le = x.reshape(-1).astype("<i4").view(np.uint8).reshape(-1, 4)[:, :nb].tobytes()
+        assert bytes(out["streams"][s].md5) == hashlib.md5(le).digest(), (s, lens[s])

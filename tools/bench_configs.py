@@ -39,7 +39,7 @@ def run_encode(name, base, n_streams, sr, bps, level, bs, ch):
     dt_s = (time.perf_counter() - t0) / steps
     res = eng.result()
     print(name, f"{pcm.size / dt_s / 1e6:.0f} MSamples/s", f"{dt_s * 1e3:.2f} ms/step", "ratio %.3f" % (res.total_bytes / pcm.nbytes * (dt().itemsize * 8 / bps)),
-          {k: round(v, 3) for k, v in eng.kernel_times().items()}, "guard", res.log_guard_hits)
+          {k: (round(v, 3) if isinstance(v, float) else v) for k, v in eng.kernel_times().items()}, "guard", res.log_guard_hits)
     return pcm
 
 
