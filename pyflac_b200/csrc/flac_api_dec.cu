@@ -11,12 +11,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <deque>
 #include <mutex>
 #include <vector>
 
 #include "../../include/flacb200.h"
 #include "../../include/flacb200_flac_api.h"
+#include "md5_host.h"
 
 extern "C" {
 // values read from the reference binary (pyflac/decoder.py:46,60,546)
@@ -36,7 +38,7 @@ const char *const FLAC__StreamDecoderErrorStatusString[] = {
 namespace {
 
 enum { DS_SEARCH_FOR_METADATA = 0, DS_READ_METADATA = 1, DS_SEARCH_FOR_FRAME_SYNC = 2, DS_READ_FRAME = 3, DS_END_OF_STREAM = 4,
-       DS_ABORTED = 7, DS_MEMORY_ALLOCATION_ERROR = 8, DS_UNINITIALIZED = 9 };
+       DS_SEEK_ERROR = 6, DS_ABORTED = 7, DS_MEMORY_ALLOCATION_ERROR = 8, DS_UNINITIALIZED = 9 };
 enum { DI_OK = 0, DI_UNSUPPORTED_CONTAINER = 1, DI_INVALID_CALLBACKS = 2, DI_MEMORY_ALLOCATION_ERROR = 3, DI_ERROR_OPENING_FILE = 4, DI_ALREADY_INITIALIZED = 5 };
 enum { ERR_LOST_SYNC = 0, ERR_BAD_HEADER = 1, ERR_FRAME_CRC_MISMATCH = 2, ERR_UNPARSEABLE_STREAM = 3, ERR_BAD_METADATA = 4 };
 
@@ -56,14 +58,20 @@ flacb200_ctx* dec_ctx() {
 }
 
 // what the next callback delivers: a decoded frame, a frame of silence standing in for a missing one, or an error status
-struct PendingFrame { uint32_t blocksize; std::vector<int32_t> planar; int error = -1; };   // planar = [channel][sample]; error >= 0: FLAC__StreamDecoderErrorStatus
+struct PendingFrame { uint32_t blocksize; std::vector<int32_t> planar; int error = -1; uint64_t first_sample = 0; };   // planar = [channel][sample]; error >= 0: FLAC__StreamDecoderErrorStatus
 
 struct DecImpl {
     int state = DS_UNINITIALIZED;
     FLAC__bool md5_checking = 0;
     FLAC__StreamDecoderReadCallback read_cb = nullptr; FLAC__StreamDecoderWriteCallback write_cb = nullptr;
     FLAC__StreamDecoderErrorCallback error_cb = nullptr; FLAC__StreamDecoderMetadataCallback meta_cb = nullptr;
+    FLAC__StreamDecoderSeekCallback seek_cb = nullptr; FLAC__StreamDecoderTellCallback tell_cb = nullptr;
+    FLAC__StreamDecoderLengthCallback length_cb = nullptr; FLAC__StreamDecoderEofCallback eof_cb = nullptr;
     void* client = nullptr;
+    uint32_t meta_calls_pending = 0;      // libFLAC's process_single reads ONE metadata block per call: calls still owed for the blocks parsed at once
+    uint64_t first_frame_offset = 0;      // byte offset of the first audio frame (behind the metadata blocks)
+    // MD5 of the delivered samples against STREAMINFO's (stream_decoder.h: set_md5_checking; off once a seek or flush happened)
+    bool md5_active = false; fb::Md5 md5; uint8_t stored_md5[16] = {0}; std::vector<int32_t> md5_tmp;
     FILE* file = nullptr;
     std::vector<uint8_t> in;              // bytes not yet consumed
     bool eof = false, metadata_done = false;
@@ -105,7 +113,7 @@ int parse_metadata(FLAC__StreamDecoder* d) {
         report(d, ERR_LOST_SYNC);
         return -1;
     }
-    size_t pos = 4; bool last = false, have_si = false;
+    size_t pos = 4; bool last = false, have_si = false; uint32_t nblocks = 0;
     while (!last) {
         if (pos + 4 > m->in.size()) return m->eof ? -1 : 0;
         const uint8_t* p = m->in.data() + pos;
@@ -120,6 +128,8 @@ int parse_metadata(FLAC__StreamDecoder* d) {
             m->bps = (((uint32_t)q[12] & 1) << 4 | (q[13] >> 4)) + 1;
             m->total_samples = ((uint64_t)(q[13] & 0xF) << 32) | (uint64_t)q[14] << 24 | (uint64_t)q[15] << 16 | (uint64_t)q[16] << 8 | q[17];
             have_si = true;
+            memcpy(m->stored_md5, q + 18, 16);
+            { bool any = false; for (int i = 0; i < 16; i++) any |= q[18 + i] != 0; if (!any) m->md5_active = false; }   // an unset MD5 is not checked
             if (m->meta_cb) {
                 FLAC__StreamMetadata md; memset(&md, 0, sizeof md);
                 md.type = 0; md.is_last = last; md.length = len;
@@ -132,13 +142,15 @@ int parse_metadata(FLAC__StreamDecoder* d) {
                 m->meta_cb(d, &md, m->client);
             }
         }
-        pos += 4 + len;
+        pos += 4 + len; nblocks++;
     }
     if (!have_si) { report(d, ERR_BAD_METADATA); return -1; }
     m->in.erase(m->in.begin(), m->in.begin() + (long)pos);
     m->bytes_consumed += pos;
+    m->first_frame_offset = m->bytes_consumed;
     m->metadata_done = true;
-    m->state = DS_SEARCH_FOR_FRAME_SYNC;
+    m->meta_calls_pending = nblocks - 1;
+    m->state = m->meta_calls_pending ? DS_READ_METADATA : DS_SEARCH_FOR_FRAME_SYNC;
     return 1;
 }
 
@@ -174,16 +186,19 @@ bool decode_buffered(FLAC__StreamDecoder* d) {
     };
     uint64_t at = 0;                                                   // sample position within this batch's PCM
     uint32_t silence_bs = m->last_blocksize;
+    // stream position of this batch's first PCM sample, from the position behind its last frame (frame headers)
+    const uint64_t extent = si.n_frames ? fo[si.n_frames - 1] + fs[si.n_frames - 1] : 0;
+    const uint64_t base = si.next_sample >= extent ? si.next_sample - extent : 0;
     for (uint32_t f = 0; f < si.n_frames; f++) {
         queue_events(f);
         // frames missing in front of this one stand as silence, in units of the previous frame's blocksize
         for (uint64_t gap = fo[f] - at; gap > 0;) {
             const uint32_t n = (uint32_t)((silence_bs && gap > silence_bs) ? silence_bs : gap);
-            PendingFrame pf; pf.blocksize = n; pf.planar.assign((size_t)n * ch, 0);
+            PendingFrame pf; pf.blocksize = n; pf.planar.assign((size_t)n * ch, 0); pf.first_sample = base + at;
             m->ready.push_back(std::move(pf));
             gap -= n; at += n;
         }
-        PendingFrame pf; pf.blocksize = fs[f]; pf.planar.resize((size_t)fs[f] * ch);
+        PendingFrame pf; pf.blocksize = fs[f]; pf.planar.resize((size_t)fs[f] * ch); pf.first_sample = base + fo[f];
         const int32_t* src = pcm.data() + (size_t)fo[f] * ch;
         for (uint32_t i = 0; i < fs[f]; i++) for (uint32_t c = 0; c < ch; c++) pf.planar[(size_t)c * fs[f] + i] = src[(size_t)i * ch + c];
         m->ready.push_back(std::move(pf));
@@ -220,8 +235,14 @@ bool deliver_one(FLAC__StreamDecoder* d) {
     for (uint32_t c = 0; c < m->channels && c < 8; c++) planes[c] = pf.planar.data() + (size_t)c * pf.blocksize;
     memset(&m->frame.header, 0, sizeof m->frame.header);
     m->frame.header.blocksize = pf.blocksize; m->frame.header.sample_rate = m->sample_rate; m->frame.header.channels = m->channels;
-    m->frame.header.channel_assignment = 0; m->frame.header.bits_per_sample = m->bps; m->frame.header.number_type = 0;
-    m->frame.header.number.frame_number = (uint32_t)m->frame_index;
+    // libFLAC hands every frame over with its sample number, whatever the header carried (stream_decoder.c read_frame_header_)
+    m->frame.header.channel_assignment = 0; m->frame.header.bits_per_sample = m->bps; m->frame.header.number_type = 1;
+    m->frame.header.number.sample_number = pf.first_sample;
+    if (m->md5_active) {
+        m->md5_tmp.resize((size_t)pf.blocksize * m->channels);
+        for (uint32_t c = 0; c < m->channels; c++) for (uint32_t i = 0; i < pf.blocksize; i++) m->md5_tmp[(size_t)i * m->channels + c] = planes[c][i];
+        m->md5.update_samples(m->md5_tmp.data(), m->md5_tmp.size(), 4, (m->bps + 7) / 8);
+    }
     m->state = DS_READ_FRAME;
     const int st = m->write_cb(d, &m->frame, planes, m->client);
     m->frame_index++;
@@ -237,6 +258,11 @@ int step(FLAC__StreamDecoder* d, bool until_end) {
     const size_t kSlice = until_end ? (1u << 20) : (1u << 16);
     for (;;) {
         if (m->state == DS_ABORTED || m->state == DS_END_OF_STREAM) return m->state == DS_ABORTED ? -1 : 0;
+        if (m->meta_calls_pending) {                                     // one process_single per metadata block, as libFLAC
+            if (until_end) m->meta_calls_pending = 0; else m->meta_calls_pending--;
+            if (!m->meta_calls_pending) m->state = DS_SEARCH_FOR_FRAME_SYNC;
+            if (!until_end) return 1;
+        }
         if (!m->ready.empty()) return deliver_one(d) ? 1 : -1;
         if (!m->metadata_done) {
             const int r = parse_metadata(d);
@@ -285,13 +311,15 @@ int FLAC__stream_decoder_get_channel_assignment(const FLAC__StreamDecoder*) { re
 uint32_t FLAC__stream_decoder_get_bits_per_sample(const FLAC__StreamDecoder* d) { return D(d)->bps; }
 uint32_t FLAC__stream_decoder_get_sample_rate(const FLAC__StreamDecoder* d) { return D(d)->sample_rate; }
 uint32_t FLAC__stream_decoder_get_blocksize(const FLAC__StreamDecoder* d) { return D(d)->blocksize; }
-FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder* d, FLAC__uint64* p) { if (!p) return 0; *p = D(d)->bytes_consumed; return 1; }
+// stream_decoder.h:1083-1099: needs a tell callback (FILE input always has one)
+FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder* d, FLAC__uint64* p) { const DecImpl* m = D(d); if (!p || (!m->file && !m->tell_cb)) return 0; *p = m->bytes_consumed; return 1; }
 
 static int init_common(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
     m->in.clear(); m->eof = false; m->metadata_done = false; m->ready.clear(); m->frame_index = 0; m->bytes_consumed = 0;
     m->sample_rate = m->channels = m->bps = m->blocksize = 0; m->total_samples = 0; m->min_blocksize = 0;
-    m->have_last = false; m->next_sample = 0; m->last_blocksize = 0;
+    m->have_last = false; m->next_sample = 0; m->last_blocksize = 0; m->first_frame_offset = 0; m->meta_calls_pending = 0;
+    m->md5_active = m->md5_checking != 0; m->md5.init(); memset(m->stored_md5, 0, 16);
     {
         std::lock_guard<std::mutex> lk(g_dec_mu);
         if (!dec_ctx()) { m->state = DS_MEMORY_ALLOCATION_ERROR; return DI_MEMORY_ALLOCATION_ERROR; }     // no CUDA device: fail loudly, no CPU fallback
@@ -306,6 +334,7 @@ int FLAC__stream_decoder_init_stream(FLAC__StreamDecoder* d, FLAC__StreamDecoder
     if (m->state != DS_UNINITIALIZED) return DI_ALREADY_INITIALIZED;
     if (!r || !w || !ecb || (s && (!t || !l || !e))) return DI_INVALID_CALLBACKS;
     m->read_cb = r; m->write_cb = w; m->error_cb = ecb; m->meta_cb = mcb; m->client = client; m->file = nullptr;
+    m->seek_cb = s; m->tell_cb = t; m->length_cb = l; m->eof_cb = e;
     return init_common(d);
 }
 int FLAC__stream_decoder_init_FILE(FLAC__StreamDecoder* d, FILE* f, FLAC__StreamDecoderWriteCallback w, FLAC__StreamDecoderMetadataCallback mcb,
@@ -314,6 +343,7 @@ int FLAC__stream_decoder_init_FILE(FLAC__StreamDecoder* d, FILE* f, FLAC__Stream
     if (m->state != DS_UNINITIALIZED) return DI_ALREADY_INITIALIZED;
     if (!f || !w || !ecb) return DI_INVALID_CALLBACKS;
     m->read_cb = nullptr; m->write_cb = w; m->error_cb = ecb; m->meta_cb = mcb; m->client = client; m->file = f;
+    m->seek_cb = nullptr; m->tell_cb = nullptr; m->length_cb = nullptr; m->eof_cb = nullptr;
     const int rc = init_common(d);
     // a failed init leaves the FILE with the caller (init_file closes the one it opened): finish()/delete must not close it again
     if (rc != DI_OK) { m->file = nullptr; m->state = DS_UNINITIALIZED; }
@@ -339,15 +369,48 @@ int FLAC__stream_decoder_init_ogg_file(FLAC__StreamDecoder*, const char*, FLAC__
 FLAC__bool FLAC__stream_decoder_finish(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
     if (m->state == DS_UNINITIALIZED) return 1;
+    // stream_decoder.h:1145-1150: false when MD5 checking is on and the MD5 of what was delivered differs from STREAMINFO's
+    bool md5_failed = false;
+    if (m->md5_active) { uint8_t got[16]; m->md5.final(got); md5_failed = memcmp(got, m->stored_md5, 16) != 0; }
     if (m->file && m->file != stdin) fclose(m->file);
     m->file = nullptr; m->in.clear(); m->ready.clear();
     m->read_cb = nullptr; m->write_cb = nullptr; m->error_cb = nullptr; m->meta_cb = nullptr; m->client = nullptr;   // stream_decoder.h: finish resets the callbacks too
-    m->md5_checking = 0;
+    m->seek_cb = nullptr; m->tell_cb = nullptr; m->length_cb = nullptr; m->eof_cb = nullptr;
+    m->md5_checking = 0; m->md5_active = false;
     m->state = DS_UNINITIALIZED;
+    return md5_failed ? 0 : 1;
+}
+static bool input_seek(FLAC__StreamDecoder* d, uint64_t off) {
+    DecImpl* m = D(d);
+    if (m->file) return m->file != stdin && fseeko(m->file, (off_t)off, SEEK_SET) == 0;
+    return m->seek_cb && m->seek_cb(d, off, m->client) == 0;
+}
+static bool input_length(FLAC__StreamDecoder* d, uint64_t* len) {
+    DecImpl* m = D(d);
+    if (m->file) { struct stat st; if (m->file == stdin || fstat(fileno(m->file), &st) != 0 || st.st_size <= 0) return false; *len = (uint64_t)st.st_size; return true; }
+    return m->length_cb && m->length_cb(d, len, m->client) == 0;
+}
+// stream_decoder.h:1370-1400: flush drops the buffered input and turns MD5 checking off
+FLAC__bool FLAC__stream_decoder_flush(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    if (m->state == DS_UNINITIALIZED) return 0;
+    m->in.clear(); m->ready.clear(); m->md5_active = false; m->have_last = false; m->meta_calls_pending = 0;
+    m->state = DS_SEARCH_FOR_FRAME_SYNC;
     return 1;
 }
-FLAC__bool FLAC__stream_decoder_flush(FLAC__StreamDecoder* d) { DecImpl* m = D(d); if (m->state == DS_UNINITIALIZED) return 0; m->in.clear(); m->ready.clear(); m->state = DS_SEARCH_FOR_FRAME_SYNC; return 1; }
-FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) { DecImpl* m = D(d); if (m->state == DS_UNINITIALIZED) return 0; m->in.clear(); m->ready.clear(); m->metadata_done = false; m->eof = false; m->state = DS_SEARCH_FOR_METADATA; return 1; }
+// stream_decoder.h:1402-1437: reset = flush + back to the start of a seekable input (stdin cannot rewind: false), metadata is
+// read again and MD5 checking starts over
+FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    if (m->state == DS_UNINITIALIZED) return 0;
+    FLAC__stream_decoder_flush(d);
+    if (m->file) { if (m->file == stdin) return 0; if (fseeko(m->file, 0, SEEK_SET) != 0) return 0; }
+    else if (m->seek_cb && m->seek_cb(d, 0, m->client) == 1) return 0;          // seekable and the seek fails: reset fails
+    m->metadata_done = false; m->eof = false; m->frame_index = 0; m->bytes_consumed = 0; m->next_sample = 0; m->last_blocksize = 0;
+    m->md5_active = m->md5_checking != 0; m->md5.init();
+    m->state = DS_SEARCH_FOR_METADATA;
+    return 1;
+}
 
 FLAC__bool FLAC__stream_decoder_process_single(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
@@ -359,6 +422,7 @@ FLAC__bool FLAC__stream_decoder_process_until_end_of_metadata(FLAC__StreamDecode
     DecImpl* m = D(d);
     if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED) return 0;
     while (!m->metadata_done && m->state != DS_END_OF_STREAM) if (step(d, false) < 0) return 0;
+    if (m->meta_calls_pending) { m->meta_calls_pending = 0; m->state = DS_SEARCH_FOR_FRAME_SYNC; }
     return 1;
 }
 FLAC__bool FLAC__stream_decoder_process_until_end_of_stream(FLAC__StreamDecoder* d) {
@@ -379,6 +443,71 @@ FLAC__bool FLAC__stream_decoder_skip_single_frame(FLAC__StreamDecoder* d) {
     m->write_cb = keep;
     return r >= 0;
 }
-FLAC__bool FLAC__stream_decoder_seek_absolute(FLAC__StreamDecoder*, FLAC__uint64) { return 0; }   // seeking is out of scope
+// stream_decoder.h:1519-1538 (builder/decoder.py:475).  libFLAC bisects the byte range with single-frame reads; here each probe
+// reads a window of the input at an estimated byte position and decodes every frame inside it in one GPU batch (headerless mode
+// finds the first frame whose header CRC and frame CRC hold, and the frame headers give the stream position), so one or two probes
+// decide.  As in libFLAC the frame that holds the target sample is delivered through the write callback before the call returns,
+// cut to start at the target; the following process_* calls continue behind it.  Errors met while probing are not reported
+// (libFLAC: is_seeking), MD5 checking is off afterwards, and a failed search leaves the decoder in SEEK_ERROR until flush / reset.
+FLAC__bool FLAC__stream_decoder_seek_absolute(FLAC__StreamDecoder* d, FLAC__uint64 sample) {
+    DecImpl* m = D(d);
+    if (m->state != DS_SEARCH_FOR_METADATA && m->state != DS_READ_METADATA && m->state != DS_SEARCH_FOR_FRAME_SYNC &&
+        m->state != DS_READ_FRAME && m->state != DS_END_OF_STREAM) return 0;
+    if (m->file ? m->file == stdin : !(m->seek_cb && m->tell_cb && m->length_cb && m->eof_cb)) return 0;   // not seekable
+    if (m->total_samples > 0 && sample >= m->total_samples) return 0;
+    m->md5_active = false;
+    uint64_t length = 0;
+    if (!input_length(d, &length)) return 0;
+    if (!m->metadata_done) {
+        if (!FLAC__stream_decoder_process_until_end_of_metadata(d) || !m->metadata_done) return 0;
+        if (m->total_samples > 0 && sample >= m->total_samples) return 0;
+    }
+    m->meta_calls_pending = 0;
+    uint64_t lo = m->first_frame_offset, hi = length;                  // the target frame starts in [lo, hi)
+    uint64_t lo_s = 0, hi_s = m->total_samples;                        // stream positions at those bytes (hi_s == 0: unknown)
+    size_t window = 1u << 18;
+    for (int iter = 0; iter < 64 && lo < hi; iter++) {
+        uint64_t pos = lo;
+        if (hi - lo > window) {
+            if (hi_s > lo_s && sample >= lo_s && iter < 6) {           // proportional guess, a quarter window early
+                const uint64_t g = lo + (uint64_t)((long double)(sample - lo_s) / (long double)(hi_s - lo_s) * (long double)(hi - lo));
+                pos = g > lo + window / 4 ? g - window / 4 : lo;
+            } else pos = lo + (hi - lo) / 2;
+            if (pos >= hi) pos = hi - 1;
+        }
+        if (!input_seek(d, pos)) break;
+        m->in.clear(); m->ready.clear(); m->eof = false; m->have_last = false; m->next_sample = 0; m->last_blocksize = 0;
+        m->bytes_consumed = pos;
+        while (!m->eof && m->in.size() < window) if (!pull(d, window - m->in.size())) return 0;
+        const bool hit_end = m->eof;
+        if (!decode_buffered(d)) return 0;
+        uint64_t first_s = 0, end_s = 0; bool any = false;
+        for (const PendingFrame& pf : m->ready) if (pf.error < 0) { if (!any) first_s = pf.first_sample; any = true; end_s = pf.first_sample + pf.blocksize; }
+        if (!any) {                                                    // no whole frame inside the window
+            if (!hit_end && window < (64u << 20)) { window *= 4; continue; }
+            if (pos == lo) break;
+            hi = pos; continue;
+        }
+        if (sample < first_s) { if (pos == lo) break; hi = pos; hi_s = first_s; continue; }      // pos == lo: the target was never coded (missing frames)
+        if (sample >= end_s) { if (hit_end) break; lo = m->bytes_consumed; lo_s = end_s; continue; }
+        while (!m->ready.empty()) {
+            PendingFrame& pf = m->ready.front();
+            if (pf.error < 0 && sample < pf.first_sample + pf.blocksize) break;
+            m->ready.pop_front();
+        }
+        PendingFrame& pf = m->ready.front();
+        const uint32_t delta = (uint32_t)(sample - pf.first_sample);
+        if (delta) {
+            const uint32_t n = pf.blocksize - delta;
+            std::vector<int32_t> cut((size_t)n * m->channels);
+            for (uint32_t c = 0; c < m->channels; c++) memcpy(&cut[(size_t)c * n], &pf.planar[(size_t)c * pf.blocksize + delta], (size_t)n * 4);
+            pf.planar.swap(cut); pf.blocksize = n; pf.first_sample = sample;
+        }
+        return deliver_one(d) ? 1 : 0;
+    }
+    m->in.clear(); m->ready.clear();
+    m->state = DS_SEEK_ERROR;
+    return 0;
+}
 
 }  // extern "C"

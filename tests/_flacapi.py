@@ -179,3 +179,101 @@ def decode_session(L, data, read_chunk=8192):
     L.FLAC__stream_decoder_delete(d)
     res["pcm"] = np.concatenate(blocks) if blocks else np.zeros((0, 1), np.int32)
     return res
+
+
+DEC_SEEK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
+DEC_TELL_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p)
+DEC_LENGTH_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p)
+DEC_EOF_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+
+
+def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, path=None):
+    """A StreamDecoder session driven by a script, over seekable callbacks (or a file when `path` is given).
+    ops: ('seek', sample) | ('single', n) | ('end',) | ('flush',) | ('reset',) | ('meta',).
+    Returns dict(events=[...], finish=bool): events are ('w', number_type, sample_number, blocksize, crc32 of the samples),
+    ('e', status) and ('ret', op, return value, decoder state) in the order they happened."""
+    import zlib
+    for n, at, rt in [("new", [], C.c_void_p), ("delete", [C.c_void_p], None), ("finish", [C.c_void_p], C.c_int),
+                      ("get_state", [C.c_void_p], C.c_int), ("process_until_end_of_stream", [C.c_void_p], C.c_int),
+                      ("process_until_end_of_metadata", [C.c_void_p], C.c_int), ("process_single", [C.c_void_p], C.c_int),
+                      ("flush", [C.c_void_p], C.c_int), ("reset", [C.c_void_p], C.c_int),
+                      ("seek_absolute", [C.c_void_p, C.c_uint64], C.c_int), ("set_md5_checking", [C.c_void_p, C.c_int], C.c_int),
+                      ("get_total_samples", [C.c_void_p], C.c_uint64)]:
+        f = getattr(L, "FLAC__stream_decoder_" + n)
+        f.argtypes, f.restype = at, rt
+    L.FLAC__stream_decoder_init_stream.argtypes = [C.c_void_p, DEC_READ_CB, DEC_SEEK_CB, DEC_TELL_CB, DEC_LENGTH_CB, DEC_EOF_CB,
+                                                   DEC_WRITE_CB, C.c_void_p, DEC_ERROR_CB, C.c_void_p]
+    L.FLAC__stream_decoder_init_stream.restype = C.c_int
+    L.FLAC__stream_decoder_init_file.argtypes = [C.c_void_p, C.c_char_p, DEC_WRITE_CB, C.c_void_p, DEC_ERROR_CB, C.c_void_p]
+    L.FLAC__stream_decoder_init_file.restype = C.c_int
+    pos = [0]
+    events = []
+
+    def r(dec, buf, pbytes, cd):
+        k = min(pbytes[0], len(data) - pos[0])
+        if k == 0:
+            pbytes[0] = 0
+            return 1
+        C.memmove(buf, data[pos[0]:pos[0] + k], k)
+        pos[0] += k
+        pbytes[0] = k
+        return 0
+
+    def sk(dec, off, cd):
+        pos[0] = min(int(off), len(data))
+        return 0
+
+    def tl(dec, poff, cd):
+        poff[0] = pos[0]
+        return 0
+
+    def ln(dec, plen, cd):
+        plen[0] = len(data)
+        return 0
+
+    def ef(dec, cd):
+        return int(pos[0] >= len(data))
+
+    def w(dec, frame, buffers, cd):
+        h = C.cast(frame, C.POINTER(FrameHeaderView)).contents
+        crc = 0
+        for c in range(h.channels):
+            crc = zlib.crc32(np.ctypeslib.as_array(buffers[c], shape=(h.blocksize,)).tobytes(), crc)
+        events.append(('w', int(h.number_type), int(h.number), int(h.blocksize), crc))
+        return 0
+
+    def e(dec, status, cd):
+        events.append(('e', int(status)))
+
+    cbs = (DEC_READ_CB(r), DEC_SEEK_CB(sk), DEC_TELL_CB(tl), DEC_LENGTH_CB(ln), DEC_EOF_CB(ef), DEC_WRITE_CB(w), DEC_ERROR_CB(e))
+    null = lambda T: C.cast(None, T)  # noqa: E731
+    d = L.FLAC__stream_decoder_new()
+    L.FLAC__stream_decoder_set_md5_checking(d, int(md5_checking))
+    if path is not None:
+        st = L.FLAC__stream_decoder_init_file(d, path.encode(), cbs[5], None, cbs[6], None)
+    elif seekable:
+        st = L.FLAC__stream_decoder_init_stream(d, cbs[0], cbs[1], cbs[2], cbs[3], cbs[4], cbs[5], None, cbs[6], None)
+    else:
+        st = L.FLAC__stream_decoder_init_stream(d, cbs[0], null(DEC_SEEK_CB), null(DEC_TELL_CB), null(DEC_LENGTH_CB), null(DEC_EOF_CB),
+                                                cbs[5], None, cbs[6], None)
+    res = dict(init_status=st, events=events)
+    if st == 0:
+        for op in ops:
+            if op[0] == 'seek':
+                rv = L.FLAC__stream_decoder_seek_absolute(d, op[1])
+            elif op[0] == 'single':
+                rv = 1
+                for _ in range(op[1]):
+                    rv = L.FLAC__stream_decoder_process_single(d)
+            elif op[0] == 'end':
+                rv = L.FLAC__stream_decoder_process_until_end_of_stream(d)
+            elif op[0] == 'meta':
+                rv = L.FLAC__stream_decoder_process_until_end_of_metadata(d)
+            elif op[0] == 'flush':
+                rv = L.FLAC__stream_decoder_flush(d)
+            elif op[0] == 'reset':
+                rv = L.FLAC__stream_decoder_reset(d)
+            events.append(('ret', op[0], int(rv), int(L.FLAC__stream_decoder_get_state(d))))
+        res["finish"] = bool(L.FLAC__stream_decoder_finish(d))
+    L.FLAC__stream_decoder_delete(d)
+    return res

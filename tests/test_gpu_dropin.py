@@ -202,3 +202,75 @@ def test_write_callback_may_drive_another_encoder(checkers):
     assert done, "deadlock: a write callback could not use another encoder"
     assert bytes(outer_out) == checkers.oracle_encode(x, 44100, 16, 5, 0, seekable=False)
     assert bytes(inner_out) == checkers.oracle_encode(y[:fed[0]], 44100, 16, 3, 0, seekable=False)
+
+
+def _flac_for_seek(checkers, n=4096 * 30 + 1234, ch=2, bps=16, bs=0, level=5, seed=9):
+    x = music_like(n, ch, 48000, bps, seed=seed)
+    return x, checkers.oracle_encode(x, 48000, bps, level, bs)
+
+
+@pytest.mark.parametrize("via", ["callbacks", "file"])
+def test_decoder_seek_matches_libflac(ours, ref, checkers, tmp_path, via):
+    """FLAC__stream_decoder_seek_absolute (builder/decoder.py:475): the frame holding the target is delivered inside the call, cut to
+    start at the target, with its sample number; the next process_* calls continue behind it; targets at frame starts, inside
+    frames, in the short last frame, backwards, after END_OF_STREAM; out-of-range targets fail without touching the state."""
+    from _flacapi import scripted_decode_session
+    x, flac = _flac_for_seek(checkers)
+    n = len(x)
+    ops = [('seek', 4096 * 7 + 5), ('single', 3), ('seek', 0), ('single', 1), ('seek', 4096 * 29), ('single', 1), ('seek', n - 1), ('end',),
+           ('seek', 4096 * 3 - 1), ('single', 2), ('seek', n), ('seek', n + 1000), ('seek', 4096 * 12), ('end',), ('seek', 17), ('single', 1)]
+    path = None
+    if via == "file":
+        path = str(tmp_path / "seek.flac")
+        with open(path, "wb") as f:
+            f.write(flac)
+    a = scripted_decode_session(ours, flac, ops, path=path)
+    b = scripted_decode_session(ref, flac, ops, path=path)
+    assert a["init_status"] == b["init_status"] == 0
+    assert a["events"] == b["events"]
+    assert a["finish"] == b["finish"]
+
+
+def test_decoder_seek_variable_shapes(ours, ref, checkers):
+    """seeking in streams whose frames carry frame numbers with a small blocksize (many frames per probe window), 24-bit mono, and a
+    stream of several MB (more than one probe)"""
+    from _flacapi import scripted_decode_session
+    for (n, ch, bps, bs, level) in [(50000, 1, 16, 192, 2), (4096 * 9 + 3, 1, 24, 4096, 8), (48000 * 40, 2, 16, 4096, 0)]:
+        x, flac = _flac_for_seek(checkers, n, ch, bps, bs, level, seed=n % 97)
+        rng = np.random.default_rng(n)
+        ops = []
+        for t in rng.integers(0, n, size=12):
+            ops += [('seek', int(t)), ('single', 2)]
+        ops += [('seek', n - 1), ('end',)]
+        a = scripted_decode_session(ours, flac, ops)
+        b = scripted_decode_session(ref, flac, ops)
+        assert a["events"] == b["events"], (n, ch, bps, bs)
+
+
+def test_decoder_seek_needs_seekable_input(ours, ref, checkers):
+    from _flacapi import scripted_decode_session
+    x, flac = _flac_for_seek(checkers, 20000)
+    ops = [('seek', 5000), ('single', 2), ('end',)]
+    a = scripted_decode_session(ours, flac, ops, seekable=False)
+    b = scripted_decode_session(ref, flac, ops, seekable=False)
+    assert a["events"] == b["events"] and a["events"][0][:3] == ('ret', 'seek', 0)
+
+
+def test_decoder_md5_checking_matches_libflac(ours, ref, checkers):
+    """set_md5_checking (builder/decoder.py:391): finish() is false when the MD5 of the delivered samples differs from STREAMINFO's --
+    a wrong stored digest, or a decode that stopped early; a zero digest is not checked; seek and flush switch the check off."""
+    from _flacapi import scripted_decode_session
+    x, flac = _flac_for_seek(checkers, 4096 * 5 + 77)
+    bad = bytearray(flac); bad[26] ^= 0x55; bad = bytes(bad)
+    zero = bytearray(flac); zero[26:42] = bytes(16); zero = bytes(zero)
+    cases = [(flac, [('end',)], True), (bad, [('end',)], True), (zero, [('end',)], True), (flac, [('meta',), ('single', 2)], True),
+             (bad, [('end',)], False), (bad, [('seek', 100), ('end',)], True), (bad, [('single', 3), ('flush',), ('end',)], True),
+             (flac, [('single', 3), ('reset',), ('end',)], True), (bad, [('single', 3), ('reset',), ('end',)], True)]
+    for i, (data, ops, chk) in enumerate(cases):
+        a = scripted_decode_session(ours, data, ops, md5_checking=chk)
+        b = scripted_decode_session(ref, data, ops, md5_checking=chk)
+        assert a["finish"] == b["finish"], i
+        if ('flush',) not in ops:       # what survives a mid-stream flush depends on how much input each decoder had buffered ahead
+            assert a["events"] == b["events"], i
+    assert scripted_decode_session(ours, bad, [('end',)], md5_checking=True)["finish"] is False
+    assert scripted_decode_session(ours, flac, [('end',)], md5_checking=True)["finish"] is True
