@@ -311,9 +311,10 @@ def main():
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - e0
-    hp = (C.c_double * 6)()
-    L.flacb200_host_path_times(eng._h, hp)
-    host_path_ms = {"md5_workers_done": hp[0], "enqueued": hp[1], "kernels_done": hp[2], "d2h_done": hp[3], "md5_joined": hp[4], "total": hp[5]}
+    hp = (C.c_double * 10)()
+    L.flacb200_host_path_info(eng._h, hp, 10)
+    host_path_ms = {"md5_workers_done": hp[0], "enqueued": hp[1], "kernels_done": hp[2], "d2h_done": hp[3], "md5_joined": hp[4], "total": hp[5],
+                    "gpu_md5_done": hp[6], "streams_hashed_on_gpu": int(hp[7]), "host_md5_threads": int(hp[8]), "chunks": int(hp[9])}
     if world > 1:
         dist.barrier()
 

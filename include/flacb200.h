@@ -201,10 +201,18 @@ int  flacb200_kernel_times(flacb200_ctx *ctx, float *ms);
 /* Wall-clock breakdown (ms since entry) of the last flacb200_encode_batch_host call:
  * ms[1] work enqueued, ms[2] all chunks' kernels finished, ms[3] D2H finished, ms[4] host MD5 joined, ms[5] return. */
 int  flacb200_host_path_times(flacb200_ctx *ctx, double *ms);
+/* The same plus how the MD5 work of that call was placed: v[6] ms when the digests hashed on the GPU had reached the host
+ * (0: none were), v[7] streams hashed on the GPU, v[8] host MD5 threads, v[9] chunks; n = entries of v to fill (<= 10).
+ * Host threads hash the caller's buffer while the GPU encodes; their number is this rank's share of the CPUs the process may
+ * run on (sched_getaffinity / LOCAL_WORLD_SIZE).  When they cannot finish by the time the transfer does, the streams of the
+ * first chunks are hashed by md5_kernel as their bytes land in HBM, and the split follows the measured finish times. */
+int  flacb200_host_path_info(flacb200_ctx *ctx, double *v, int n);
 /* Tuning knobs of the two host -> host calls, read from the environment at call time (defaults are measured on a
  * B200 / PCIe 5 host and normally right):
  *   FLACB200_CHUNKS       pieces the PCM of flacb200_encode_batch_host is cut into for the H2D / kernel / D2H pipeline (default 12)
- *   FLACB200_MD5_THREADS  host threads hashing the caller's PCM meanwhile (default: calibrated so they finish with the H2D copy)
+ *   FLACB200_MD5_THREADS  host threads hashing the caller's PCM meanwhile (default: calibrated so they finish with the H2D copy,
+ *                         at most this rank's share of the host: affinity mask / FLACB200_LOCAL_RANKS or LOCAL_WORLD_SIZE)
+ *   FLACB200_MD5_GPU_CHUNKS  leading chunks whose streams md5_kernel hashes instead of the host (default: balanced automatically)
  *   FLACB200_DEC_CHUNKS   groups of streams flacb200_decode_batch_host pipelines (default: one per 200 MB of FLAC, at most 12) */
 /* Drop-in layer (flacb200_flac_api.h): concurrent FLAC__stream_encoder_process_interleaved() calls of different handles are
  * coalesced into shared GPU batches by a per-device dispatcher; this reports how many batches / jobs it has run.  Handles

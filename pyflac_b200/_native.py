@@ -98,6 +98,7 @@ def lib():
     L.flacb200_encode_batch_host.argtypes = [C.c_void_p, C.POINTER(EncConfig), C.c_void_p, C.c_uint64, C.c_uint32,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64),
                                              C.c_void_p, C.c_void_p, C.c_void_p]
+    L.flacb200_host_path_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.flacb200_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.flacb200_kernel_times.argtypes = [C.c_void_p, C.c_void_p]
     L.flacb200_launch_count.restype = C.c_uint64
@@ -222,6 +223,37 @@ class Engine:
         return dict(arena=arena[:int(r.total_bytes)], frame_off=off[:nf], frame_len=ln[:nf], frame_samples=smp[:nf],
                     frame_stream=stm[:nf], streams=[infos[i] for i in range(ns)], log_guard_hits=int(r.log_guard_hits),
                     total_bytes=int(r.total_bytes))
+
+    def encode_host_to_host(self, cfg, pcm, stream_off, stream_samples, arena_cap=None):
+        """flacb200_encode_batch_host: PCM in host memory -> complete .flac images in host memory, one synchronous call
+        (chunked H2D / kernels / D2H pipeline, MD5 on host threads and/or the GPU).  Returns the dict of fetch() plus
+        path_info (flacb200_host_path_info)."""
+        pcm = np.ascontiguousarray(pcm)
+        so = np.ascontiguousarray(stream_off, np.uint64)
+        ss = np.ascontiguousarray(stream_samples, np.uint64)
+        ns = len(so)
+        nf = int(sum((int(n) + self._blocksize_of(cfg) - 1) // self._blocksize_of(cfg) for n in ss))
+        cap = int(arena_cap or (pcm.nbytes * 2 + nf * 64 + ns * 256 + (1 << 20)))
+        arena = np.empty(cap, np.uint8)
+        off = np.zeros(max(nf, 1), np.uint64)
+        ln = np.zeros(max(nf, 1), np.uint32)
+        infos = (StreamInfo * max(ns, 1))()
+        tot = C.c_uint64(0)
+        self._check(self._L.flacb200_encode_batch_host(self._h, C.byref(cfg), pcm.ctypes.data, pcm.size, ns, so.ctypes.data, ss.ctypes.data,
+                                                       arena.ctypes.data, cap, C.byref(tot), off.ctypes.data, ln.ctypes.data,
+                                                       C.cast(infos, C.c_void_p)))
+        v = np.zeros(10, np.float64)
+        self._check(self._L.flacb200_host_path_info(self._h, v.ctypes.data, 10))
+        return dict(arena=arena[:tot.value], frame_off=off[:nf], frame_len=ln[:nf], streams=[infos[i] for i in range(ns)],
+                    total_bytes=int(tot.value),
+                    path_info=dict(host_md5_done_ms=v[0], kernels_done_ms=v[2], d2h_done_ms=v[3], total_ms=v[5], gpu_md5_done_ms=v[6],
+                                   streams_hashed_on_gpu=int(v[7]), host_md5_threads=int(v[8]), chunks=int(v[9])))
+
+    @staticmethod
+    def _blocksize_of(cfg):
+        if cfg.blocksize:
+            return int(cfg.blocksize)
+        return 1152 if cfg.compression_level < 3 else 4096
 
     def fetch_trace(self, n_signals, want_debug=True):
         r = self.result()

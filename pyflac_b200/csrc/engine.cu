@@ -9,10 +9,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sched.h>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <thread>
 #include <string>
 #include <vector>
@@ -60,6 +64,46 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Host threads of one ctx for the MD5 of host-resident PCM: created once, parked on a condition variable between calls
+// (a fresh std::thread per call and worker cost 0.3-0.5 ms of the 12 ms host path and more on an oversubscribed host).
+struct HostPool {
+    std::vector<std::thread> threads;
+    std::mutex mu; std::condition_variable cv_go, cv_done;
+    std::function<void()> job; uint64_t gen = 0; int want = 0, running = 0; bool stop = false;
+    void start(int n, std::function<void()> fn) {
+        std::unique_lock<std::mutex> lk(mu);
+        while ((int)threads.size() < n) threads.emplace_back([this, idx = (int)threads.size()] { loop(idx); });
+        job = std::move(fn); want = n; running = n; gen++;
+        cv_go.notify_all();
+    }
+    void wait() { std::unique_lock<std::mutex> lk(mu); cv_done.wait(lk, [this] { return running == 0; }); }
+    void loop(int idx) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<void()> fn;
+            { std::unique_lock<std::mutex> lk(mu); cv_go.wait(lk, [&] { return stop || (gen != seen && idx < want); }); if (stop) return; seen = gen; fn = job; }
+            fn();
+            { std::unique_lock<std::mutex> lk(mu); if (--running == 0) cv_done.notify_all(); }
+        }
+    }
+    ~HostPool() { { std::unique_lock<std::mutex> lk(mu); stop = true; cv_go.notify_all(); } for (auto& t : threads) t.join(); }
+};
+
+// Hardware threads this process may use, shared fairly with the other ranks of the node: the affinity mask (a cgroup cpuset
+// shows up there; std::thread::hardware_concurrency() reports the whole machine) divided by LOCAL_WORLD_SIZE (torchrun).
+static unsigned host_thread_budget() {
+    unsigned n = 0;
+    cpu_set_t set; CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0) n = (unsigned)CPU_COUNT(&set);
+    if (n == 0) n = std::thread::hardware_concurrency();
+    if (n == 0) n = 8;
+    unsigned ranks = 1;
+    if (const char* ev = getenv("FLACB200_LOCAL_RANKS")) { const int v = atoi(ev); if (v > 0) ranks = (unsigned)v; }
+    else if (const char* ev2 = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(ev2); if (v > 0) ranks = (unsigned)v; }
+    n /= ranks;
+    return n < 1 ? 1 : n;
+}
+
 struct flacb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr, md5_stream = nullptr;
@@ -96,7 +140,14 @@ struct flacb200_ctx {
     uint64_t* h_totals = nullptr;          // pinned: per-chunk arena byte counts
     DevBuf d_totals;
     uint64_t e2e_last_bytes = 0;
-    double e2e_ms[6] = {0};               // last host call: plan, enqueue, kernels drained, d2h done, md5 join, total
+    double e2e_ms[10] = {0};              // last host call: host md5 done, enqueue, kernels drained, d2h done, md5 join, total, GPU md5 done, streams hashed on the GPU, host md5 threads, chunks
+    HostPool pool;
+    cudaEvent_t ev_md5 = nullptr, ev_d2h = nullptr;      // blocking-sync events: the calling thread sleeps instead of spinning on a core the MD5 workers need
+    uint8_t* h_digests = nullptr; size_t h_digests_cap = 0;   // pinned: digests of the streams hashed on the GPU
+    std::atomic<uint64_t> gpu_md5_done_us{0};
+    std::chrono::steady_clock::time_point t_call;
+    int md5_gpu_chunks = -1;              // chunks (from the front of the batch) whose streams the GPU hashes; -1: not decided yet
+    uint64_t md5_split_key = 0;           // batch shape the split was tuned for
 
     DevBuf d_pcm, d_frames, d_windows, d_plans, d_ca, d_scratch, d_work;
     DevBuf d_sfirst, d_snframes, d_soff, d_ssamples, d_debug;
@@ -237,7 +288,9 @@ extern "C" int flacb200_create(flacb200_ctx** out, int device) {
     cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
     for (auto& e : ctx->ev_h2d) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    for (auto& e : ctx->ev_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& e : ctx->ev_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync);
+    cudaEventCreateWithFlags(&ctx->ev_md5, cudaEventDisableTiming | cudaEventBlockingSync);
+    cudaEventCreateWithFlags(&ctx->ev_d2h, cudaEventDisableTiming | cudaEventBlockingSync);
     cudaHostAlloc((void**)&ctx->h_totals, sizeof(uint64_t) * flacb200_ctx::kMaxChunks, cudaHostAllocDefault);
     ctx->stream = ctx->own_stream;
     *out = ctx;
@@ -266,6 +319,9 @@ extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
     cudaStreamDestroy(ctx->h2d_stream); cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->dec && ctx->dec_free) ctx->dec_free(ctx->dec);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+    if (ctx->h_digests) cudaFreeHost(ctx->h_digests);
+    if (ctx->ev_md5) cudaEventDestroy(ctx->ev_md5);
+    if (ctx->ev_d2h) cudaEventDestroy(ctx->ev_d2h);
     ctx->d_totals.release();
     cudaStreamDestroy(ctx->own_stream); cudaStreamDestroy(ctx->md5_stream);
     delete ctx;
@@ -292,6 +348,7 @@ void fb_ctx_add_launches(flacb200_ctx* c, uint64_t n) { c->launches += n; }
 extern "C" int flacb200_join(flacb200_ctx* ctx) { if (!ctx) return FLACB200_ERR_ARG; cudaSetDevice(ctx->device); return wait_all_sets(ctx, ctx->stream); }
 
 extern "C" int flacb200_host_path_times(flacb200_ctx* ctx, double* ms) { if (!ctx || !ms) return FLACB200_ERR_ARG; for (int i = 0; i < 6; i++) ms[i] = ctx->e2e_ms[i]; return 0; }
+extern "C" int flacb200_host_path_info(flacb200_ctx* ctx, double* v, int n) { if (!ctx || !v || n < 0) return FLACB200_ERR_ARG; for (int i = 0; i < n && i < 10; i++) v[i] = ctx->e2e_ms[i]; return 0; }
 
 extern "C" int flacb200_set_profiling(flacb200_ctx* ctx, int on) { if (!ctx) return FLACB200_ERR_ARG; ctx->profiling = on != 0; return 0; }
 // ms[0..8] = analysis (3 kernels), pack, layout(scan), compact, finalize (incl. waiting for MD5), md5 (side stream),
@@ -648,38 +705,71 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     const auto t_start = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     std::atomic<uint64_t> md5_done_us{0};
-    // ---- host MD5 workers (one serial chain per stream) ----
+    // ---- MD5 (one serial chain per stream): host threads hash the caller's buffer while the GPU encodes; when the host cannot
+    // finish by the time the transfer does (few cores per rank), the streams of the first chunks -- the ones that reach HBM
+    // first -- are hashed by md5_kernel on a side stream instead, and the split is re-balanced from the measured finish times ----
     const bool want_md5 = cfg->do_md5 != 0;
     std::vector<uint8_t> digests((size_t)ns * 16, 0);
-    std::vector<std::thread> workers;
     std::atomic<int> next_stream{0};
+    bool pool_running = false;
+    int gpu_chunks = 0, g_streams = 0;
+    unsigned nt = 0;
+    std::atomic<uint64_t>& gpu_md5_done_us = ctx->gpu_md5_done_us;  // stamped by a host function on the MD5 stream
+    ctx->t_call = t_start;
+    const uint32_t bytes_per = (P.bps + 7) / 8, chn = P.channels;
+    const bool raw_bytes = (bytes_per == cont);                    // the container bytes are the hashed bytes
+    const int G = fb::md5_mb16_available() ? 16 : 8;               // streams per SIMD pass (AVX-512 / AVX2)
+    // Hashing competes with the H2D DMA for host memory bandwidth (measured: 8+ threads finish the MD5s in 6 ms but
+    // stretch the 491 MB copy from 11 to 13.5 ms), so use just enough threads to finish when the transfer does:
+    // threads = (bytes / calibrated per-thread rate) / (bytes / ~42 GB/s PCIe), within this rank's share of the host.
+    static const double gbps_per_thread = [] {
+        std::vector<uint8_t> buf(16u << 16, 0x5a);
+        const uint8_t* d[16]; size_t l[16]; uint8_t dig[16][16];
+        for (int i = 0; i < 16; i++) { d[i] = buf.data() + ((size_t)i << 16); l[i] = 1u << 16; }
+        fb::md5_group16(d, l, 16, dig);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < 4; r++) fb::md5_group16(d, l, 16, dig);
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return sec > 0 ? 4.0 * buf.size() / sec / 1e9 : 4.0;
+    }();
+    const double total_mb = (double)pcm_elems * cont / 1e6, t_h2d_ms = total_mb / 44.0;
     if (want_md5) {
-        unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 8;
-        // the calling thread only enqueues copies and waits, so every hardware thread can hash; groups of 16 streams
-        // (AVX-512) or 8 (AVX2) per SIMD pass
-        const int G = fb::md5_mb16_available() ? 16 : 8;
-        // Hashing competes with the H2D DMA for host memory bandwidth (measured: 8+ threads finish the MD5s in 6 ms but
-        // stretch the 491 MB copy from 11 to 13.5 ms), so use just enough threads to finish when the transfer does:
-        // threads = (bytes / calibrated per-thread rate) / (bytes / ~42 GB/s PCIe), at most all cores but one.
-        static const double gbps_per_thread = [] {
-            std::vector<uint8_t> buf(16u << 16, 0x5a);
-            const uint8_t* d[16]; size_t l[16]; uint8_t dig[16][16];
-            for (int i = 0; i < 16; i++) { d[i] = buf.data() + ((size_t)i << 16); l[i] = 1u << 16; }
-            fb::md5_group16(d, l, 16, dig);
-            const auto t0 = std::chrono::steady_clock::now();
-            for (int r = 0; r < 4; r++) fb::md5_group16(d, l, 16, dig);
-            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            return sec > 0 ? 4.0 * buf.size() / sec / 1e9 : 4.0;
-        }();
+        const unsigned budget = host_thread_budget();
+        const unsigned max_workers = budget > 2 ? budget - 1 : budget;      // the calling thread sleeps in blocking waits most of the time
         unsigned want = (unsigned)(42.0 / gbps_per_thread + 0.5);
         if (want < 1) want = 1;
-        if (want > (hw > 2 ? hw - 1 : hw)) want = hw > 2 ? hw - 1 : hw;
+        if (want > max_workers) want = max_workers;
         if (const char* ev = getenv("FLACB200_MD5_THREADS")) { const int v = atoi(ev); if (v > 0) want = (unsigned)v; }
-        const unsigned nt = std::min<unsigned>(std::min<unsigned>(want, 64u), (unsigned)((ns + G - 1) / G));
-        const uint32_t bytes_per = (P.bps + 7) / 8, chn = P.channels;
-        const bool raw_bytes = (bytes_per == cont);          // the container bytes are the hashed bytes
-        for (unsigned t = 0; t < nt; t++)
-            workers.emplace_back([&, bytes_per, chn, raw_bytes, G]() {
+        nt = std::min<unsigned>(std::min<unsigned>(want, 64u), (unsigned)((ns + G - 1) / G));
+        const bool gpu_fast = raw_bytes || (bytes_per == 3 && cont == 4);   // md5_kernel's staged paths
+        uint64_t max_stream_bytes = 0;
+        for (int s = 0; s < ns; s++) max_stream_bytes = std::max<uint64_t>(max_stream_bytes, stream_samples[s] * chn * bytes_per);
+        const double host_all_ms = total_mb / ((double)nt * gbps_per_thread);   // MB / (GB/s) = ms
+        const double gpu_chain_ms = (double)max_stream_bytes * 8.3e-6;      // measured: 15.9 ms per 1.92 MB stream, whatever the stream count
+        const uint64_t key = (uint64_t)ns * 1000003ull ^ (uint64_t)pcm_elems * 31ull ^ ((uint64_t)nt << 48) ^ ((uint64_t)P.bps << 56) ^ (uint64_t)nchunks;
+        if (ctx->md5_split_key != key || ctx->md5_gpu_chunks < 0) {
+            int best = 0; double best_t = host_all_ms;
+            if (gpu_fast && host_all_ms > t_h2d_ms * 1.1)
+                for (int g = 1; g <= nchunks; g++) {
+                    const double fr = (double)cs[g] / (double)ns;
+                    const double t = std::max(fr * t_h2d_ms + gpu_chain_ms, (1.0 - fr) * host_all_ms);
+                    if (t < best_t - 0.2) { best_t = t; best = g; }
+                }
+            ctx->md5_gpu_chunks = best; ctx->md5_split_key = key;
+        }
+        gpu_chunks = gpu_fast ? std::min(ctx->md5_gpu_chunks, nchunks) : 0;
+        if (const char* ev = getenv("FLACB200_MD5_GPU_CHUNKS")) { const int v = atoi(ev); if (v >= 0 && gpu_fast) gpu_chunks = std::min(v, nchunks); }
+        g_streams = cs[gpu_chunks];
+        next_stream.store(g_streams);
+        if (g_streams > 0 && (size_t)g_streams * 16 > ctx->h_digests_cap) {
+            if (ctx->h_digests) cudaFreeHost(ctx->h_digests);
+            ctx->h_digests = nullptr; ctx->h_digests_cap = 0;
+            CK(cudaHostAlloc((void**)&ctx->h_digests, (size_t)ns * 16 + 64, cudaHostAllocDefault));
+            ctx->h_digests_cap = (size_t)ns * 16 + 64;
+        }
+        gpu_md5_done_us.store(0);
+        if (g_streams < ns) {
+            ctx->pool.start((int)nt, [&, bytes_per, chn, raw_bytes, G]() {
                 for (;;) {
                     const int g = next_stream.fetch_add(G);
                     if (g >= ns) {
@@ -702,8 +792,10 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
                     }
                 }
             });
+            pool_running = true;
+        }
     }
-    auto join_workers = [&]() { for (auto& w : workers) if (w.joinable()) w.join(); };
+    auto join_workers = [&]() { if (pool_running) { ctx->pool.wait(); pool_running = false; } };
 
     // ---- enqueue: H2D per chunk, then kernels per chunk ----
     auto bail = [&](int code) { join_workers(); return code; };
@@ -734,6 +826,12 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         const int cnf = f1 - f0, cns = s1 - s0;
         dev_base[c + 1] = dev_base[c] + (((uint64_t)cnf * ctx->scratch_stride + (uint64_t)cns * kStreamPrologueBytes + 255) / 256) * 256;
         CKJ(cudaStreamWaitEvent(st, ctx->ev_h2d[c], 0));
+        if (c < gpu_chunks && cns > 0) {                              // this chunk's digests come from the GPU, as soon as its bytes are there
+            CKJ(cudaStreamWaitEvent(ctx->md5_stream, ctx->ev_h2d[c], 0));
+            launch_md5(ctx->d_pcm.p, cont, (const uint64_t*)ctx->d_soff.p + s0, (const uint64_t*)ctx->d_ssamples.p + s0, cns, P.channels, P.bps,
+                       (uint8_t*)ctx->set().md5.p + (size_t)s0 * 16, ctx->md5_stream);
+            ctx->launches++;
+        }
         if (cnf > 0) {
             int n_an = 0;
             if (ctx->use_fused) {
@@ -766,6 +864,15 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         CKJ(cudaEventRecord(ctx->ev_done[c], st));
     }
     if (dev_base[nchunks] > ctx->set().arena.cap) return bail(fail(ctx, FLACB200_ERR_CUDA, "device arena too small"));
+    if (g_streams > 0) {
+        CKJ(cudaMemcpyAsync(ctx->h_digests, ctx->set().md5.p, (size_t)g_streams * 16, cudaMemcpyDeviceToHost, ctx->md5_stream));
+        CKJ(cudaLaunchHostFunc(ctx->md5_stream, [](void* p) {
+            flacb200_ctx* c = (flacb200_ctx*)p;
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c->t_call).count();
+            c->gpu_md5_done_us.store((uint64_t)(ms * 1000.0));
+        }, ctx));
+        CKJ(cudaEventRecord(ctx->ev_md5, ctx->md5_stream));
+    }
 
     ctx->e2e_ms[1] = since();
     // ---- drain: as each chunk finishes, copy exactly its bytes to the next free spot of the host arena ----
@@ -787,13 +894,39 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     flacb200_stream_info* info_host = streams;
     if (!info_host) { tmp_info.resize(ns); info_host = tmp_info.data(); }
     CKJ(cudaMemcpyAsync(info_host, ctx->set().sinfo.p, sizeof(StreamInfoOut) * ns, cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    CKJ(cudaStreamSynchronize(ctx->d2h_stream));
+    CKJ(cudaEventRecord(ctx->ev_d2h, ctx->d2h_stream));
+    CKJ(cudaEventSynchronize(ctx->ev_d2h));
     CKJ(cudaGetLastError());
-#undef CKJ
     ctx->e2e_ms[3] = since();
     join_workers();
+    if (g_streams > 0) {
+        CKJ(cudaEventSynchronize(ctx->ev_md5));
+        memcpy(digests.data(), ctx->h_digests, (size_t)g_streams * 16);
+    }
+#undef CKJ
     ctx->e2e_ms[4] = since();
     ctx->e2e_ms[0] = (double)md5_done_us.load() / 1000.0;       // when the last MD5 worker ran out of streams
+    ctx->e2e_ms[6] = (double)gpu_md5_done_us.load() / 1000.0;   // when the GPU's digests had reached the host
+    ctx->e2e_ms[7] = (double)g_streams; ctx->e2e_ms[8] = (double)nt; ctx->e2e_ms[9] = (double)nchunks;
+    if (want_md5 && !getenv("FLACB200_MD5_GPU_CHUNKS")) {
+        // re-balance for the next call of this shape: move one chunk across when the measured finish times say it pays
+        const double t_host = ctx->e2e_ms[0], t_gpu = ctx->e2e_ms[6], t_rest = ctx->e2e_ms[3];
+        const double now_max = std::max(std::max(t_host, t_gpu), t_rest);
+        const bool gpu_fast = raw_bytes || (bytes_per == 3 && cont == 4);
+        const double step = t_h2d_ms / nchunks;
+        if (gpu_fast && gpu_chunks < nchunks && g_streams < ns && t_host >= now_max - 1e-9) {
+            const double rem = (double)(nchunks - gpu_chunks);
+            const double new_host = t_host * (rem - 1.0) / rem;
+            uint64_t msb = 0; for (int s = 0; s < ns; s++) msb = std::max<uint64_t>(msb, stream_samples[s] * chn * bytes_per);
+            const double new_gpu = (gpu_chunks > 0 ? t_gpu : (double)msb * 8.3e-6) + step;
+            if (std::max(std::max(new_host, new_gpu), t_rest) < now_max - 0.3) ctx->md5_gpu_chunks = gpu_chunks + 1;
+        } else if (gpu_chunks > 0 && t_gpu >= now_max - 1e-9) {
+            const double rem = (double)(nchunks - gpu_chunks);
+            const double new_host = rem > 0 ? t_host * (rem + 1.0) / rem : total_mb / ((double)nt * gbps_per_thread) / nchunks;
+            const double new_gpu = gpu_chunks > 1 ? t_gpu - step : 0.0;
+            if (std::max(std::max(new_host, new_gpu), t_rest) < now_max - 0.3) ctx->md5_gpu_chunks = gpu_chunks - 1;
+        }
+    }
     // device-arena offsets -> host-arena offsets; MD5 digests into STREAMINFO
     for (int c = 0; c < nchunks; c++) {
         const int s0 = cs[c], s1 = cs[c + 1];

@@ -375,3 +375,40 @@ def test_md5_ragged_batch(eng, bps, ch):
     for s, x in enumerate(xs):
         le = x.reshape(-1).astype("<i4").view(np.uint8).reshape(-1, 4)[:, :nb].tobytes()
         assert bytes(out["streams"][s].md5) == hashlib.md5(le).digest(), (s, lens[s])
+
+
+@pytest.mark.parametrize("bps", [16, 24])
+def test_host_path_md5_placement(eng, checkers, monkeypatch, bps):
+    """flacb200_encode_batch_host: whoever hashes a stream -- host threads, md5_kernel as the chunk lands in HBM, or both -- the
+    images (frames, index, STREAMINFO with its MD5) equal the reference's.  The split is forced through the environment knobs."""
+    from pyflac_b200 import _native as nat
+    ch = 2 if bps == 16 else 1
+    xs = [music_like(4096 * 3 + 517 * s, ch, 48000, bps, seed=700 + s) for s in range(30)]
+    dt = np.int16 if bps == 16 else np.int32
+    flat = np.concatenate([x.reshape(-1) for x in xs]).astype(dt)
+    sizes = np.array([x.size for x in xs], np.uint64)
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+    cfg = nat.Engine.make_config(48000, ch, bps, 5, 4096)
+    want = [checkers.oracle_encode(x, 48000, bps, 5, 4096) for x in xs]
+    for gpu_chunks, threads in [("0", "1"), ("0", "3"), ("5", "2"), ("12", "1"), (None, None)]:
+        for k, v in (("FLACB200_MD5_GPU_CHUNKS", gpu_chunks), ("FLACB200_MD5_THREADS", threads)):
+            if v is None:
+                monkeypatch.delenv(k, raising=False)
+            else:
+                monkeypatch.setenv(k, v)
+        for rep in range(2):
+            out = eng.encode_host_to_host(cfg, flat, offs, sizes // ch)
+            pi = out["path_info"]
+            if gpu_chunks == "0":
+                assert pi["streams_hashed_on_gpu"] == 0
+            if gpu_chunks == "12":
+                assert pi["streams_hashed_on_gpu"] == 30 and pi["gpu_md5_done_ms"] > 0
+            if gpu_chunks == "5":
+                assert 0 < pi["streams_hashed_on_gpu"] < 30
+            for s, x in enumerate(xs):
+                si = out["streams"][s]
+                blob = out["arena"][int(si.byte_off): int(si.byte_off + si.byte_len)].tobytes()
+                assert blob == want[s], (gpu_chunks, threads, s)
+                nb = (bps + 7) // 8
+                le = x.reshape(-1).astype("<i4").view(np.uint8).reshape(-1, 4)[:, :nb].tobytes()
+                assert bytes(si.md5) == hashlib.md5(le).digest()
