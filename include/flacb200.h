@@ -132,6 +132,17 @@ int  flacb200_encode_batch_host(flacb200_ctx *ctx, const flacb200_enc_config *cf
                                 uint32_t n_streams, const uint64_t *stream_off, const uint64_t *stream_samples,
                                 uint8_t *arena, size_t arena_cap, uint64_t *total_bytes,
                                 uint64_t *frame_off, uint32_t *frame_len, flacb200_stream_info *streams);
+/* The same work without waiting: submit returns once the batch is enqueued (H2D chunks, kernels, MD5 on the GPU's side stream)
+ * and hands out a ticket; up to 3 batches may be in flight, so the PCIe link stays busy in both directions and no call waits
+ * for a serial MD5 chain.  collect blocks until that batch's images, index and STREAMINFO digests are in the host buffers given
+ * to submit (they and pcm_host must stay valid until then) and returns the byte count.  Tickets are collected in submission
+ * order; batches in flight share one stream layout (a different layout needs the earlier ones collected first). */
+int  flacb200_encode_host_submit(flacb200_ctx *ctx, const flacb200_enc_config *cfg,
+                                 const void *pcm_host, uint64_t pcm_elems,
+                                 uint32_t n_streams, const uint64_t *stream_off, const uint64_t *stream_samples,
+                                 uint8_t *arena, size_t arena_cap, uint64_t *frame_off, uint32_t *frame_len,
+                                 flacb200_stream_info *streams, int *ticket);
+int  flacb200_encode_host_collect(flacb200_ctx *ctx, int ticket, uint64_t *total_bytes);
 /* ------------------------------------------------------------------ batch decode ----
  * n_streams independent FLAC byte strings (stream s = stream_len[s] bytes at byte offset stream_off[s] of `blob`).
  * Output: interleaved PCM [sample][channel] per stream, back to back in stream order, in `out_container_bytes`

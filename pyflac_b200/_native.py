@@ -99,6 +99,9 @@ def lib():
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64),
                                              C.c_void_p, C.c_void_p, C.c_void_p]
     L.flacb200_host_path_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.flacb200_encode_host_submit.argtypes = [C.c_void_p, C.POINTER(EncConfig), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    L.flacb200_encode_host_collect.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
     L.flacb200_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.flacb200_kernel_times.argtypes = [C.c_void_p, C.c_void_p]
     L.flacb200_launch_count.restype = C.c_uint64
@@ -224,7 +227,7 @@ class Engine:
                     frame_stream=stm[:nf], streams=[infos[i] for i in range(ns)], log_guard_hits=int(r.log_guard_hits),
                     total_bytes=int(r.total_bytes))
 
-    def encode_host_to_host(self, cfg, pcm, stream_off, stream_samples, arena_cap=None):
+    def encode_host_to_host(self, cfg, pcm, stream_off, stream_samples, arena_cap=None, arena=None):
         """flacb200_encode_batch_host: PCM in host memory -> complete .flac images in host memory, one synchronous call
         (chunked H2D / kernels / D2H pipeline, MD5 on host threads and/or the GPU).  Returns the dict of fetch() plus
         path_info (flacb200_host_path_info)."""
@@ -234,7 +237,10 @@ class Engine:
         ns = len(so)
         nf = int(sum((int(n) + self._blocksize_of(cfg) - 1) // self._blocksize_of(cfg) for n in ss))
         cap = int(arena_cap or (pcm.nbytes * 2 + nf * 64 + ns * 256 + (1 << 20)))
-        arena = np.empty(cap, np.uint8)
+        if arena is None:
+            arena = np.empty(cap, np.uint8)
+        else:
+            cap = arena.size                                       # caller's buffer (e.g. pinned memory)
         off = np.zeros(max(nf, 1), np.uint64)
         ln = np.zeros(max(nf, 1), np.uint32)
         infos = (StreamInfo * max(ns, 1))()
@@ -248,6 +254,33 @@ class Engine:
                     total_bytes=int(tot.value),
                     path_info=dict(host_md5_done_ms=v[0], kernels_done_ms=v[2], d2h_done_ms=v[3], total_ms=v[5], gpu_md5_done_ms=v[6],
                                    streams_hashed_on_gpu=int(v[7]), host_md5_threads=int(v[8]), chunks=int(v[9])))
+
+    def submit_host(self, cfg, pcm, stream_off, stream_samples, arena_cap=None):
+        """flacb200_encode_host_submit: enqueue one host -> host batch and return a ticket (up to 3 in flight)."""
+        pcm = np.ascontiguousarray(pcm)
+        so = np.ascontiguousarray(stream_off, np.uint64)
+        ss = np.ascontiguousarray(stream_samples, np.uint64)
+        ns = len(so)
+        nf = int(sum((int(n) + self._blocksize_of(cfg) - 1) // self._blocksize_of(cfg) for n in ss))
+        cap = int(arena_cap or (pcm.nbytes * 2 + nf * 64 + ns * 256 + (1 << 20)))
+        job = dict(pcm=pcm, so=so, ss=ss, arena=np.empty(cap, np.uint8), off=np.zeros(max(nf, 1), np.uint64), ln=np.zeros(max(nf, 1), np.uint32),
+                   infos=(StreamInfo * max(ns, 1))(), nf=nf, ns=ns)
+        t = C.c_int(-1)
+        self._check(self._L.flacb200_encode_host_submit(self._h, C.byref(cfg), pcm.ctypes.data, pcm.size, ns, so.ctypes.data, ss.ctypes.data,
+                                                        job["arena"].ctypes.data, cap, job["off"].ctypes.data, job["ln"].ctypes.data,
+                                                        C.cast(job["infos"], C.c_void_p), C.byref(t)))
+        if not hasattr(self, "_jobs"):
+            self._jobs = {}
+        self._jobs[t.value] = job
+        return t.value
+
+    def collect_host(self, ticket):
+        """flacb200_encode_host_collect: wait for a submitted batch; returns the dict of encode_host_to_host (without path_info)."""
+        job = self._jobs.pop(ticket)
+        tot = C.c_uint64(0)
+        self._check(self._L.flacb200_encode_host_collect(self._h, ticket, C.byref(tot)))
+        return dict(arena=job["arena"][:tot.value], frame_off=job["off"][:job["nf"]], frame_len=job["ln"][:job["nf"]],
+                    streams=[job["infos"][i] for i in range(job["ns"])], total_bytes=int(tot.value))
 
     @staticmethod
     def _blocksize_of(cfg):

@@ -491,20 +491,35 @@ struct Md5Feeder {
 // (row stride 272 bytes: the eight lanes of an LDS.128 phase fall in distinct banks).  Measured on the bench batch
 // (256 streams of 1.92 MB): 21.1 ms with per-lane loads one block ahead -> 15.6 ms.
 constexpr int kMd5Piece = 256, kMd5Row = kMd5Piece + 16, kMd5Ring = 4;
+// Host -> host path: the kernel is launched before the PCM has arrived; the copy stream sets flag c when chunk c (streams
+// cs[c] .. cs[c+1]-1) is in HBM.  The warp waits for the chunk of its last stream (chunks land in order), so every chain starts
+// the moment its bytes are there and all chains of a batch run side by side in ONE launch.
+__device__ __noinline__ void md5_wait_for_chunk(const Md5Gate& gate, int n_streams) {
+    const int last = min((int)blockIdx.x * 32 + 31, n_streams - 1);
+    int c = 0;
+    while (c + 1 < gate.nchunks && last >= gate.cs[c + 1]) c++;
+    // every lane polls (one broadcast load per try): a single polling lane left the warp split behind the wait -- lane 0 and
+    // lanes 1..31 then ran the whole hash as two passes, 2x the time -- whatever __syncwarp() followed
+    const volatile uint32_t* f = gate.flags + c;
+    while (__any_sync(0xffffffffu, *f == 0u)) __nanosleep(500);
+    __threadfence();
+}
 template <typename PcmT, bool K24>
 __global__ void __launch_bounds__(32) md5_kernel(const PcmT* __restrict__ pcm, const uint64_t* __restrict__ stream_pcm_off,
                            const uint64_t* __restrict__ stream_samples, int n_streams, uint32_t channels, uint32_t bps,
-                           uint8_t* __restrict__ digest_out) {
+                           uint8_t* __restrict__ digest_out, Md5Gate gate) {
     __shared__ __align__(16) uint8_t ring[kMd5Ring][32][kMd5Row];
     const int lane = threadIdx.x, s = blockIdx.x * 32 + lane;
     const bool live = s < n_streams;
+    if (gate.flags) md5_wait_for_chunk(gate, n_streams);               // host -> host path: launched ahead of its input
     const uint32_t bytes_per = (bps + 7) / 8;
-    const PcmT* p = pcm + (live ? stream_pcm_off[s] : 0ull);
+    // lanes past the last stream mirror the warp's first stream for the copies (valid addresses, nothing hashed)
+    const PcmT* p = pcm + stream_pcm_off[live ? s : blockIdx.x * 32];
     const uint64_t nvals = live ? stream_samples[s] * channels : 0ull;
     Md5Feeder f; f.init();
     const bool fast = live && bytes_per == (K24 ? 3u : (uint32_t)sizeof(PcmT)) && (((uintptr_t)p) & 15u) == 0;
     const uint64_t np_own = fast ? (nvals * sizeof(PcmT)) / kMd5Piece : 0ull;     // whole pieces of this lane's stream
-    uint64_t np_max = np_own, np_all = np_own;
+    uint64_t np_max = np_own, np_all = live ? np_own : ~0ull;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         const uint64_t v = __shfl_xor_sync(0xffffffffu, np_max, o), u = __shfl_xor_sync(0xffffffffu, np_all, o);
@@ -574,13 +589,18 @@ __global__ void __launch_bounds__(32) md5_kernel(const PcmT* __restrict__ pcm, c
     f.finish(nvals * bytes_per, digest_out + (size_t)s * 16);
 }
 
-void launch_md5(const void* pcm, uint32_t container_bytes, const uint64_t* stream_pcm_off, const uint64_t* stream_samples,
-                int n_streams, uint32_t channels, uint32_t bps, uint8_t* digest_out, cudaStream_t stream) {
+void launch_md5_gated(const void* pcm, uint32_t container_bytes, const uint64_t* stream_pcm_off, const uint64_t* stream_samples,
+                      int n_streams, uint32_t channels, uint32_t bps, uint8_t* digest_out, const Md5Gate& gate, cudaStream_t stream) {
     // one warp per CTA: the chains are latency-bound, spreading them over SMs costs nothing
     const int threads = 32, blocks = (n_streams + threads - 1) / threads;
-    if (container_bytes == 2) md5_kernel<int16_t, false><<<blocks, threads, 0, stream>>>((const int16_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
-    else if ((bps + 7) / 8 == 3) md5_kernel<int32_t, true><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
-    else md5_kernel<int32_t, false><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out);
+    if (container_bytes == 2) md5_kernel<int16_t, false><<<blocks, threads, 0, stream>>>((const int16_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out, gate);
+    else if ((bps + 7) / 8 == 3) md5_kernel<int32_t, true><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out, gate);
+    else md5_kernel<int32_t, false><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out, gate);
+}
+void launch_md5(const void* pcm, uint32_t container_bytes, const uint64_t* stream_pcm_off, const uint64_t* stream_samples,
+                int n_streams, uint32_t channels, uint32_t bps, uint8_t* digest_out, cudaStream_t stream) {
+    Md5Gate none; none.flags = nullptr; none.nchunks = 0;
+    launch_md5_gated(pcm, container_bytes, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out, none, stream);
 }
 
 // The MD5 chain of a batch ends long after its frames are final: the digests are patched into the finished stream

@@ -40,6 +40,7 @@ void launch_autoc_unshifted(const void*, const FrameDesc*, const float*, const E
 void launch_fused(const void*, const FrameDesc*, const EncParams&, int, const void*, size_t, SubframePlan*, uint8_t*, EncStats*, uint8_t*, uint32_t,
                   uint32_t*, cudaStream_t, cudaEvent_t);
 void launch_md5(const void*, uint32_t, const uint64_t*, const uint64_t*, int, uint32_t, uint32_t, uint8_t*, cudaStream_t);
+void launch_md5_gated(const void*, uint32_t, const uint64_t*, const uint64_t*, int, uint32_t, uint32_t, uint8_t*, const Md5Gate&, cudaStream_t);
 void launch_layout(const uint32_t*, const FrameDesc*, int, uint32_t, uint64_t, uint64_t*, uint64_t*, cudaStream_t);
 void launch_compact(const uint8_t*, uint32_t, const uint32_t*, const uint64_t*, uint8_t*, int, cudaStream_t);
 void launch_finalize(const uint32_t*, const uint64_t*, const uint32_t*, const uint32_t*, const uint64_t*, const uint8_t*,
@@ -146,10 +147,14 @@ struct flacb200_ctx {
     uint8_t* h_digests = nullptr; size_t h_digests_cap = 0;   // pinned: digests of the streams hashed on the GPU
     std::atomic<uint64_t> gpu_md5_done_us{0};
     std::chrono::steady_clock::time_point t_call;
+    struct HostJob;                       // one in-flight flacb200_encode_host_submit (defined below)
+    static constexpr int kJobs = 3;
+    HostJob* jobs[kJobs] = {nullptr};
+    int next_job = 0;
     int md5_gpu_chunks = -1;              // chunks (from the front of the batch) whose streams the GPU hashes; -1: not decided yet
     uint64_t md5_split_key = 0;           // batch shape the split was tuned for
 
-    DevBuf d_pcm, d_frames, d_windows, d_plans, d_ca, d_scratch, d_work;
+    DevBuf d_pcm, d_frames, d_windows, d_plans, d_ca, d_scratch, d_work, d_flags;
     DevBuf d_sfirst, d_snframes, d_soff, d_ssamples, d_debug;
 
     // Output buffers exist three times and rotate per batch: the MD5 of a batch (a serial chain per stream, longer
@@ -168,6 +173,8 @@ struct flacb200_ctx {
 };
 
 static int wait_all_sets(flacb200_ctx* ctx, cudaStream_t st);
+void fb_ctx_free_jobs(flacb200_ctx* ctx);
+bool fb_ctx_jobs_in_flight(flacb200_ctx* ctx);
 static int fail(flacb200_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
     char buf[512];
     if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
@@ -301,7 +308,7 @@ extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_pcm, &ctx->d_frames, &ctx->d_windows, &ctx->d_plans, &ctx->d_ca, &ctx->d_scratch, &ctx->d_work, &ctx->d_sfirst, &ctx->d_snframes,
+    DevBuf* bufs[] = {&ctx->d_flags, &ctx->d_pcm, &ctx->d_frames, &ctx->d_windows, &ctx->d_plans, &ctx->d_ca, &ctx->d_scratch, &ctx->d_work, &ctx->d_sfirst, &ctx->d_snframes,
                       &ctx->d_soff, &ctx->d_ssamples, &ctx->d_debug};
     for (DevBuf* b : bufs) b->release();
     for (auto& S : ctx->sets) {
@@ -317,6 +324,7 @@ extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
     for (auto& e : ctx->ev_h2d) cudaEventDestroy(e);
     for (auto& e : ctx->ev_done) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->h2d_stream); cudaStreamDestroy(ctx->d2h_stream);
+    fb_ctx_free_jobs(ctx);
     if (ctx->dec && ctx->dec_free) ctx->dec_free(ctx->dec);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     if (ctx->h_digests) cudaFreeHost(ctx->h_digests);
@@ -669,6 +677,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     if (!ctx) return FLACB200_ERR_NO_DEVICE;
     if (!cfg || !pcm_host || !arena || (n_streams && (!stream_off || !stream_samples))) return fail(ctx, FLACB200_ERR_ARG, "null argument");
     cudaSetDevice(ctx->device);
+    if (fb_ctx_jobs_in_flight(ctx)) return fail(ctx, FLACB200_ERR_ARG, "collect the submitted batches before a synchronous host call");
     for (uint32_t s = 0; s < n_streams; s++)
         if (stream_off[s] + stream_samples[s] * cfg->channels > pcm_elems) return fail(ctx, FLACB200_ERR_ARG, "stream exceeds pcm buffer");
     if (ctx->prev_ca_pending || !same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr)) {
@@ -804,6 +813,19 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     CKJ(cudaMemsetAsync(ctx->set().stats.p, 0, sizeof(EncStats), st));
     bool monotonic = true;
     for (int s = 1; s < ns; s++) if (stream_off[s] < stream_off[s - 1] + stream_samples[s - 1] * P.channels) { monotonic = false; break; }
+    if (g_streams > 0) {
+        // ONE md5_kernel launch for all GPU-hashed streams, ahead of the data: its warps wait for the arrival flag of their chunk
+        // (set on the copy stream behind each chunk), so the chains start as their bytes land and run side by side
+        CKJ(ctx->d_flags.reserve(sizeof(uint32_t) * flacb200_ctx::kMaxChunks));
+        CKJ(cudaMemsetAsync(ctx->d_flags.p, 0, sizeof(uint32_t) * flacb200_ctx::kMaxChunks, ctx->h2d_stream));
+        CKJ(cudaEventRecord(ctx->ev_fork, ctx->h2d_stream));
+        CKJ(cudaStreamWaitEvent(ctx->md5_stream, ctx->ev_fork, 0));
+        Md5Gate gate; gate.flags = (const uint32_t*)ctx->d_flags.p; gate.nchunks = gpu_chunks;
+        for (int c = 0; c <= nchunks && c < 17; c++) gate.cs[c] = cs[c];
+        launch_md5_gated(ctx->d_pcm.p, cont, (const uint64_t*)ctx->d_soff.p, (const uint64_t*)ctx->d_ssamples.p, g_streams, P.channels, P.bps,
+                         (uint8_t*)ctx->set().md5.p, gate, ctx->md5_stream);
+        ctx->launches++;
+    }
     for (int c = 0; c < nchunks; c++) {
         const int s0 = cs[c], s1 = cs[c + 1];
         if (s1 > s0) {
@@ -816,6 +838,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
                                         stream_samples[s] * P.channels * cont, cudaMemcpyHostToDevice, ctx->h2d_stream));
             }
         }
+        if (c < gpu_chunks) CKJ(cudaMemsetAsync((uint32_t*)ctx->d_flags.p + c, 0xff, sizeof(uint32_t), ctx->h2d_stream));
         CKJ(cudaEventRecord(ctx->ev_h2d[c], ctx->h2d_stream));
     }
     const uint32_t pro = cfg->write_prologue ? (uint32_t)kStreamPrologueBytes : 0u;
@@ -826,12 +849,6 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         const int cnf = f1 - f0, cns = s1 - s0;
         dev_base[c + 1] = dev_base[c] + (((uint64_t)cnf * ctx->scratch_stride + (uint64_t)cns * kStreamPrologueBytes + 255) / 256) * 256;
         CKJ(cudaStreamWaitEvent(st, ctx->ev_h2d[c], 0));
-        if (c < gpu_chunks && cns > 0) {                              // this chunk's digests come from the GPU, as soon as its bytes are there
-            CKJ(cudaStreamWaitEvent(ctx->md5_stream, ctx->ev_h2d[c], 0));
-            launch_md5(ctx->d_pcm.p, cont, (const uint64_t*)ctx->d_soff.p + s0, (const uint64_t*)ctx->d_ssamples.p + s0, cns, P.channels, P.bps,
-                       (uint8_t*)ctx->set().md5.p + (size_t)s0 * 16, ctx->md5_stream);
-            ctx->launches++;
-        }
         if (cnf > 0) {
             int n_an = 0;
             if (ctx->use_fused) {
@@ -944,5 +961,270 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     ctx->e2e_last_bytes = host_base[nchunks];
     ctx->e2e_ms[5] = since();
     if (total_bytes) *total_bytes = host_base[nchunks];
+    return 0;
+}
+
+// ---------------------------------------------------------------- pipelined host -> host encode ----
+// flacb200_encode_host_submit / _collect: the same work as flacb200_encode_batch_host, but the call returns once everything is
+// enqueued and up to kJobs batches are in flight, so a caller with a queue of batches (a library of files) keeps the PCIe link
+// busy in both directions all the time and nothing waits for a serial MD5 chain: the digests come from md5_kernel, chunk by chunk
+// as the bytes land in HBM, on a side stream that overlaps the following batches (the host threads -- and the second read of the PCM
+// from host memory, which is what limits many ranks on one host -- are not needed).  Each job owns a PCM staging buffer, an
+// output set, its events and a drain thread that sleeps in blocking waits and issues each chunk's D2H copy when its size is known.
+struct flacb200_ctx::HostJob {
+    bool active = false;
+    int rc = 0; std::string err;
+    DevBuf d_pcm, d_totals, d_flags;
+    cudaEvent_t ev_h2d[kMaxChunks] = {nullptr}, ev_done[kMaxChunks] = {nullptr}, ev_md5 = nullptr, ev_d2h = nullptr, ev_flags = nullptr;
+    uint64_t* h_totals = nullptr; uint8_t* h_digests = nullptr; size_t h_digests_cap = 0;
+    int set_idx = 0, nchunks = 0, nf = 0, ns = 0;
+    bool want_md5 = false, gpu_md5 = false; uint32_t pro = 0;
+    std::vector<int> cs; std::vector<uint64_t> dev_base;
+    std::vector<uint32_t> stream_first;
+    const void* pcm_host = nullptr; uint32_t cont = 0, chn = 0, bytes_per = 0;
+    std::vector<uint64_t> s_off, s_smp;
+    uint8_t* arena = nullptr; size_t arena_cap = 0; uint64_t* frame_off = nullptr; uint32_t* frame_len = nullptr; flacb200_stream_info* streams = nullptr;
+    uint64_t total = 0;
+    std::thread drain;
+    void init() {
+        for (auto& e : ev_h2d) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        for (auto& e : ev_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync);
+        cudaEventCreateWithFlags(&ev_md5, cudaEventDisableTiming | cudaEventBlockingSync);
+        cudaEventCreateWithFlags(&ev_d2h, cudaEventDisableTiming | cudaEventBlockingSync);
+        cudaEventCreateWithFlags(&ev_flags, cudaEventDisableTiming);
+        cudaHostAlloc((void**)&h_totals, sizeof(uint64_t) * kMaxChunks, cudaHostAllocDefault);
+    }
+    void destroy() {
+        if (drain.joinable()) drain.join();
+        for (auto& e : ev_h2d) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_done) if (e) cudaEventDestroy(e);
+        if (ev_md5) cudaEventDestroy(ev_md5);
+        if (ev_d2h) cudaEventDestroy(ev_d2h);
+        if (ev_flags) cudaEventDestroy(ev_flags);
+        if (h_totals) cudaFreeHost(h_totals);
+        if (h_digests) cudaFreeHost(h_digests);
+        d_pcm.release(); d_totals.release(); d_flags.release();
+    }
+};
+
+void fb_ctx_free_jobs(flacb200_ctx* ctx) {
+    for (auto& j : ctx->jobs) if (j) { j->destroy(); delete j; j = nullptr; }
+}
+
+bool fb_ctx_jobs_in_flight(flacb200_ctx* ctx) { for (auto& j : ctx->jobs) if (j && j->active) return true; return false; }
+
+static void chunk_bounds(int ns, const uint64_t* stream_samples, int nchunks, std::vector<int>& cs) {
+    cs.assign(nchunks + 1, 0);
+    uint64_t tot = 0; for (int s = 0; s < ns; s++) tot += stream_samples[s];
+    uint64_t acc = 0; int c = 1;
+    for (int s = 0; s < ns && c < nchunks; s++) {
+        acc += stream_samples[s];
+        if (acc * nchunks >= tot * c && s + 1 >= c) { cs[c++] = s + 1; }
+    }
+    for (; c <= nchunks; c++) cs[c] = ns;
+    cs[nchunks] = ns;
+}
+
+// the drain thread of one job: D2H of every chunk as soon as its byte count is known, then the index, then the digests
+static void drain_job(flacb200_ctx* ctx, flacb200_ctx::HostJob* J) {
+    cudaSetDevice(ctx->device);
+    flacb200_ctx::OutSet& S = ctx->sets[J->set_idx];
+    auto failj = [&](const char* what, cudaError_t e) { J->rc = FLACB200_ERR_CUDA; J->err = std::string(what) + ": " + cudaGetErrorString(e); };
+#define CKD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { failj(#call, e_); return; } } while (0)
+    const int nchunks = J->nchunks, nf = J->nf, ns = J->ns;
+    std::vector<uint64_t> host_base(nchunks + 1, 0);
+    for (int c = 0; c < nchunks; c++) {
+        CKD(cudaEventSynchronize(J->ev_done[c]));
+        const uint64_t bytes = J->h_totals[c];
+        if (host_base[c] + bytes > J->arena_cap) { J->rc = FLACB200_ERR_ARG; J->err = "arena too small"; return; }
+        if (bytes) CKD(cudaMemcpyAsync(J->arena + host_base[c], (const uint8_t*)S.arena.p + J->dev_base[c], bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        host_base[c + 1] = host_base[c] + bytes;
+    }
+    std::vector<uint64_t> tmp_off; std::vector<flacb200_stream_info> tmp_info;
+    uint64_t* foff_host = J->frame_off;
+    if (!foff_host) { tmp_off.resize(nf); foff_host = tmp_off.data(); }
+    CKD(cudaMemcpyAsync(foff_host, S.foff.p, sizeof(uint64_t) * nf, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (J->frame_len) CKD(cudaMemcpyAsync(J->frame_len, S.flen.p, sizeof(uint32_t) * nf, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    flacb200_stream_info* info_host = J->streams;
+    if (!info_host) { tmp_info.resize(ns); info_host = tmp_info.data(); }
+    CKD(cudaMemcpyAsync(info_host, S.sinfo.p, sizeof(StreamInfoOut) * ns, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CKD(cudaEventRecord(J->ev_d2h, ctx->d2h_stream));
+    CKD(cudaEventSynchronize(J->ev_d2h));
+    std::vector<uint8_t> host_dig;
+    const uint8_t* dig = nullptr;
+    if (J->want_md5) {
+        if (J->gpu_md5) { CKD(cudaEventSynchronize(J->ev_md5)); dig = J->h_digests; }
+        else {
+            // sample sizes md5_kernel has no staged path for: hashed here, sixteen streams per SIMD pass where the bytes allow
+            host_dig.assign((size_t)ns * 16, 0);
+            for (int s = 0; s < ns; s++) {
+                fb::Md5 m; m.init();
+                m.update_samples((const uint8_t*)J->pcm_host + J->s_off[s] * J->cont, (size_t)J->s_smp[s] * J->chn, J->cont, J->bytes_per);
+                m.final(&host_dig[(size_t)s * 16]);
+            }
+            dig = host_dig.data();
+        }
+    }
+#undef CKD
+    for (int c = 0; c < nchunks; c++) {
+        const int s0 = J->cs[c], s1 = J->cs[c + 1];
+        const int f0 = s0 < ns ? (int)J->stream_first[s0] : nf, f1 = s1 < ns ? (int)J->stream_first[s1] : nf;
+        for (int f = f0; f < f1; f++) foff_host[f] = foff_host[f] - J->dev_base[c] + host_base[c];
+        for (int s = s0; s < s1; s++) {
+            flacb200_stream_info& si = info_host[s];
+            if (si.n_frames) si.byte_off = si.byte_off - J->dev_base[c] + host_base[c];
+            if (dig) {
+                memcpy(si.md5, dig + (size_t)s * 16, 16);
+                if (J->pro && si.n_frames) memcpy(J->arena + si.byte_off + 26, si.md5, 16);
+            }
+        }
+    }
+    J->total = host_base[nchunks];
+}
+
+extern "C" int flacb200_encode_host_submit(flacb200_ctx* ctx, const flacb200_enc_config* cfg, const void* pcm_host, uint64_t pcm_elems,
+                                           uint32_t n_streams, const uint64_t* stream_off, const uint64_t* stream_samples,
+                                           uint8_t* arena, size_t arena_cap, uint64_t* frame_off, uint32_t* frame_len,
+                                           flacb200_stream_info* streams, int* ticket) {
+    if (!ctx) return FLACB200_ERR_NO_DEVICE;
+    if (!cfg || !pcm_host || !arena || !ticket || (n_streams && (!stream_off || !stream_samples))) return fail(ctx, FLACB200_ERR_ARG, "null argument");
+    cudaSetDevice(ctx->device);
+    for (uint32_t s = 0; s < n_streams; s++)
+        if (stream_off[s] + stream_samples[s] * cfg->channels > pcm_elems) return fail(ctx, FLACB200_ERR_ARG, "stream exceeds pcm buffer");
+    const int slot = ctx->next_job;
+    if (!ctx->jobs[slot]) { ctx->jobs[slot] = new flacb200_ctx::HostJob(); ctx->jobs[slot]->init(); }
+    flacb200_ctx::HostJob* J = ctx->jobs[slot];
+    if (J->active) return fail(ctx, FLACB200_ERR_ARG, "too many batches in flight: collect the oldest ticket first");
+    if (ctx->prev_ca_pending || !same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr)) {
+        // the frame table on the device is shared by the batches in flight: a new layout waits for them
+        for (auto& j : ctx->jobs) if (j && j->active) return fail(ctx, FLACB200_ERR_ARG, "collect the batches in flight before submitting a different layout");
+        ctx->have_batch = false;
+        for (auto& S : ctx->sets) if (S.busy) { CK(cudaStreamSynchronize(S.side)); S.busy = false; }
+        int rc = plan_batch(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr);
+        if (rc) return rc;
+    }
+    const EncParams& P = ctx->P;
+    const int nf = ctx->n_frames, ns = ctx->n_streams;
+    const uint32_t cont = cfg->container_bytes;
+    cudaStream_t st = ctx->stream;
+    J->rc = 0; J->err.clear(); J->total = 0;
+    J->nf = nf; J->ns = ns; J->arena = arena; J->arena_cap = arena_cap; J->frame_off = frame_off; J->frame_len = frame_len; J->streams = streams;
+    J->pcm_host = pcm_host; J->cont = cont; J->chn = P.channels; J->bytes_per = (P.bps + 7) / 8;
+    J->want_md5 = cfg->do_md5 != 0;
+    J->gpu_md5 = J->want_md5 && (J->bytes_per == cont || (J->bytes_per == 3 && cont == 4));
+    J->pro = cfg->write_prologue ? (uint32_t)kStreamPrologueBytes : 0u;
+    J->nchunks = 0;
+    *ticket = slot;
+    if (nf == 0) { J->active = true; ctx->next_job = (slot + 1) % flacb200_ctx::kJobs; return 0; }
+    CK(J->d_pcm.reserve((size_t)pcm_elems * cont + 64));
+    CK(J->d_totals.reserve(sizeof(uint64_t) * flacb200_ctx::kMaxChunks));
+    if (J->gpu_md5 && (size_t)ns * 16 > J->h_digests_cap) {
+        if (J->h_digests) cudaFreeHost(J->h_digests);
+        J->h_digests = nullptr; J->h_digests_cap = 0;
+        CK(cudaHostAlloc((void**)&J->h_digests, (size_t)ns * 16 + 64, cudaHostAllocDefault));
+        J->h_digests_cap = (size_t)ns * 16 + 64;
+    }
+    if (!J->gpu_md5 && J->want_md5) { J->s_off.assign(stream_off, stream_off + ns); J->s_smp.assign(stream_samples, stream_samples + ns); }
+    int nchunks = 12;
+    if (const char* ev = getenv("FLACB200_CHUNKS")) { const int v = atoi(ev); if (v > 0 && v <= flacb200_ctx::kMaxChunks) nchunks = v; }
+    if (nchunks > ns) nchunks = ns;
+    J->nchunks = nchunks;
+    chunk_bounds(ns, stream_samples, nchunks, J->cs);
+    const std::vector<int>& cs = J->cs;
+    J->stream_first = ctx->h_stream_first;
+    // the output set: rotate like the device-resident path; its previous user (MD5 patch on the side stream) must be done
+    ctx->cur = (ctx->cur + 1) % flacb200_ctx::kSets;
+    J->set_idx = ctx->cur;
+    flacb200_ctx::OutSet& S = ctx->sets[J->set_idx];
+    if (S.busy) { CK(cudaStreamWaitEvent(st, S.ev_free, 0)); S.busy = false; }
+    CK(cudaMemsetAsync(S.stats.p, 0, sizeof(EncStats), st));
+    bool monotonic = true;
+    for (int s = 1; s < ns; s++) if (stream_off[s] < stream_off[s - 1] + stream_samples[s - 1] * P.channels) { monotonic = false; break; }
+    if (J->gpu_md5) {
+        // ONE md5_kernel launch per batch, ahead of the data (see Md5Gate): every chain starts when its chunk has landed
+        CK(J->d_flags.reserve(sizeof(uint32_t) * flacb200_ctx::kMaxChunks));
+        CK(cudaMemsetAsync(J->d_flags.p, 0, sizeof(uint32_t) * flacb200_ctx::kMaxChunks, ctx->h2d_stream));
+        CK(cudaEventRecord(J->ev_flags, ctx->h2d_stream));
+        CK(cudaStreamWaitEvent(S.side, J->ev_flags, 0));
+        Md5Gate gate; gate.flags = (const uint32_t*)J->d_flags.p; gate.nchunks = nchunks;
+        for (int c = 0; c <= nchunks && c < 17; c++) gate.cs[c] = cs[c];
+        launch_md5_gated(J->d_pcm.p, cont, (const uint64_t*)ctx->d_soff.p, (const uint64_t*)ctx->d_ssamples.p, ns, P.channels, P.bps, (uint8_t*)S.md5.p, gate, S.side);
+        ctx->launches++;
+    }
+    for (int c = 0; c < nchunks; c++) {
+        const int s0 = cs[c], s1 = cs[c + 1];
+        if (s1 > s0) {
+            if (monotonic) {
+                const uint64_t e0 = stream_off[s0], e1 = stream_off[s1 - 1] + stream_samples[s1 - 1] * P.channels;
+                CK(cudaMemcpyAsync((uint8_t*)J->d_pcm.p + e0 * cont, (const uint8_t*)pcm_host + e0 * cont, (e1 - e0) * cont, cudaMemcpyHostToDevice, ctx->h2d_stream));
+            } else {
+                for (int s = s0; s < s1; s++)
+                    CK(cudaMemcpyAsync((uint8_t*)J->d_pcm.p + stream_off[s] * cont, (const uint8_t*)pcm_host + stream_off[s] * cont,
+                                       stream_samples[s] * P.channels * cont, cudaMemcpyHostToDevice, ctx->h2d_stream));
+            }
+        }
+        if (J->gpu_md5) CK(cudaMemsetAsync((uint32_t*)J->d_flags.p + c, 0xff, sizeof(uint32_t), ctx->h2d_stream));
+        CK(cudaEventRecord(J->ev_h2d[c], ctx->h2d_stream));
+    }
+    J->dev_base.assign(nchunks + 1, 0);
+    for (int c = 0; c < nchunks; c++) {
+        const int s0 = cs[c], s1 = cs[c + 1];
+        const int f0 = s0 < ns ? (int)ctx->h_stream_first[s0] : nf, f1 = s1 < ns ? (int)ctx->h_stream_first[s1] : nf;
+        const int cnf = f1 - f0, cns = s1 - s0;
+        J->dev_base[c + 1] = J->dev_base[c] + (((uint64_t)cnf * ctx->scratch_stride + (uint64_t)cns * kStreamPrologueBytes + 255) / 256) * 256;
+        CK(cudaStreamWaitEvent(st, J->ev_h2d[c], 0));
+        if (cnf > 0) {
+            int n_an = 0;
+            if (ctx->use_fused) {
+                launch_autoc_unshifted(J->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf,
+                                       (uint8_t*)ctx->d_work.p + (size_t)f0 * analyze_work_stride(P), st);
+                launch_fused(J->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, P, cnf, (const uint8_t*)ctx->d_work.p + (size_t)f0 * analyze_work_stride(P) + 64,
+                             analyze_work_stride(P), (SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals, (uint8_t*)ctx->d_ca.p + f0, (EncStats*)S.stats.p,
+                             (uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride, (uint32_t*)S.flen.p + f0, st, nullptr);
+                n_an = (P.max_lpc_order > 0 ? 1 : 0) + 1;
+            } else {
+                n_an = launch_analyze(J->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, (const float*)ctx->d_windows.p, P, cnf,
+                                      (SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals, (uint8_t*)ctx->d_ca.p + f0, nullptr, (EncStats*)S.stats.p,
+                                      analyze_smem_bytes(P), (uint8_t*)ctx->d_work.p + (size_t)f0 * analyze_work_stride(P), st, nullptr);
+                launch_pack(J->d_pcm.p, (const FrameDesc*)ctx->d_frames.p + f0, P, cnf, (const SubframePlan*)ctx->d_plans.p + (size_t)f0 * P.n_signals,
+                            (const uint8_t*)ctx->d_ca.p + f0, (uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride,
+                            (uint32_t*)S.flen.p + f0, st);
+            }
+            launch_layout((const uint32_t*)S.flen.p + f0, (const FrameDesc*)ctx->d_frames.p + f0, cnf, J->pro, J->dev_base[c],
+                          (uint64_t*)S.foff.p + f0, (uint64_t*)J->d_totals.p + c, st);
+            launch_compact((const uint8_t*)ctx->d_scratch.p + (size_t)f0 * ctx->scratch_stride, ctx->scratch_stride, (const uint32_t*)S.flen.p + f0,
+                           (const uint64_t*)S.foff.p + f0, (uint8_t*)S.arena.p, cnf, st);
+            launch_finalize((const uint32_t*)S.flen.p, (const uint64_t*)S.foff.p, (const uint32_t*)ctx->d_sfirst.p + s0,
+                            (const uint32_t*)ctx->d_snframes.p + s0, (const uint64_t*)ctx->d_ssamples.p + s0, nullptr, cns, P, J->pro ? 1u : 0u,
+                            (uint8_t*)S.arena.p, (StreamInfoOut*)S.sinfo.p + s0, st);
+            ctx->launches += 4 + n_an;
+        } else {
+            CK(cudaMemsetAsync((uint64_t*)J->d_totals.p + c, 0, 8, st));
+        }
+        CK(cudaMemcpyAsync(J->h_totals + c, (uint64_t*)J->d_totals.p + c, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(J->ev_done[c], st));
+    }
+    if (J->dev_base[nchunks] > S.arena.cap) return fail(ctx, FLACB200_ERR_CUDA, "device arena too small");
+    if (J->gpu_md5) {
+        CK(cudaMemcpyAsync(J->h_digests, S.md5.p, (size_t)ns * 16, cudaMemcpyDeviceToHost, S.side));
+        CK(cudaEventRecord(J->ev_md5, S.side));
+        CK(cudaEventRecord(S.ev_free, S.side)); S.busy = true;          // the set is free again when its digests have left
+    }
+    CK(cudaGetLastError());
+    J->active = true;
+    ctx->next_job = (slot + 1) % flacb200_ctx::kJobs;
+    J->drain = std::thread(drain_job, ctx, J);
+    return 0;
+}
+
+extern "C" int flacb200_encode_host_collect(flacb200_ctx* ctx, int ticket, uint64_t* total_bytes) {
+    if (!ctx) return FLACB200_ERR_NO_DEVICE;
+    if (ticket < 0 || ticket >= flacb200_ctx::kJobs || !ctx->jobs[ticket] || !ctx->jobs[ticket]->active) return fail(ctx, FLACB200_ERR_ARG, "no such batch in flight");
+    flacb200_ctx::HostJob* J = ctx->jobs[ticket];
+    if (J->drain.joinable()) J->drain.join();
+    J->active = false;
+    if (total_bytes) *total_bytes = J->total;
+    if (J->rc) return fail(ctx, J->rc, J->err.c_str());
+    ctx->e2e_last_bytes = J->total;
     return 0;
 }

@@ -82,6 +82,13 @@ struct EncStats {
     unsigned long long frames;
 };
 
+// md5_kernel launched ahead of its input (host -> host path): flags[c] != 0 once chunk c = streams cs[c] .. cs[c+1]-1 is in HBM.
+struct Md5Gate {
+    const uint32_t* flags;       // nullptr: the PCM is already there
+    int nchunks;
+    int cs[17];
+};
+
 // Per-stream results of the finalize step.
 struct StreamInfoOut {
     uint64_t total_samples;

@@ -412,3 +412,39 @@ def test_host_path_md5_placement(eng, checkers, monkeypatch, bps):
                 nb = (bps + 7) // 8
                 le = x.reshape(-1).astype("<i4").view(np.uint8).reshape(-1, 4)[:, :nb].tobytes()
                 assert bytes(si.md5) == hashlib.md5(le).digest()
+
+
+@pytest.mark.parametrize("bps", [16, 24, 12])
+def test_host_pipelined_submit_collect(eng, checkers, bps):
+    """flacb200_encode_host_submit / _collect: seven batches of one layout and different audio, three in flight; every collected
+    batch (images, index, digests from md5_kernel; host-hashed for the 12-bit-in-int16 case) equals the reference's output."""
+    from pyflac_b200 import _native as nat
+    ch = 2 if bps != 24 else 1
+    dt = np.int16 if bps <= 16 else np.int32
+    lens = [4096 * 2 + 311 * s for s in range(20)]
+    sizes = np.array([n * ch for n in lens], np.uint64)
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+    cfg = nat.Engine.make_config(48000, ch, bps, 5, 4096)
+    batches = [[music_like(n, ch, 48000, bps, seed=1000 * b + s) for s, n in enumerate(lens)] for b in range(7)]
+    flats = [np.concatenate([x.reshape(-1) for x in xs]).astype(dt) for xs in batches]
+    inflight, done = [], []
+    for b in range(7):
+        if len(inflight) == 3:
+            done.append(eng.collect_host(inflight.pop(0)))
+        inflight.append(eng.submit_host(cfg, flats[b], offs, sizes // ch))
+    with pytest.raises(nat.NativeError):                               # a synchronous host call must not run over batches in flight
+        eng.encode_host_to_host(cfg, flats[0], offs, sizes // ch)
+    while inflight:
+        done.append(eng.collect_host(inflight.pop(0)))
+    nb = (bps + 7) // 8
+    for b, out in enumerate(done):
+        for s, x in enumerate(batches[b]):
+            si = out["streams"][s]
+            blob = out["arena"][int(si.byte_off): int(si.byte_off + si.byte_len)].tobytes()
+            assert blob == checkers.oracle_encode(x, 48000, bps, 5, 4096), (b, s)
+            le = x.reshape(-1).astype("<i4").view(np.uint8).reshape(-1, 4)[:, :nb].tobytes()
+            assert bytes(si.md5) == hashlib.md5(le).digest()
+    # and the synchronous call works again afterwards
+    out = eng.encode_host_to_host(cfg, flats[1], offs, sizes // ch)
+    si = out["streams"][3]
+    assert out["arena"][int(si.byte_off): int(si.byte_off + si.byte_len)].tobytes() == checkers.oracle_encode(batches[1][3], 48000, bps, 5, 4096)
