@@ -119,6 +119,9 @@ int  flacb200_encode_result(flacb200_ctx *ctx, flacb200_enc_result *res);
  * per-stream info hold them too. */
 int  flacb200_encode_result_frames(flacb200_ctx *ctx, flacb200_enc_result *res);
 int  flacb200_encode_fetch_md5(flacb200_ctx *ctx, uint8_t *digests, size_t cap);
+/* The digests of an earlier batch of the same layout (back = 1: the batch before the last, up to 4): a pipeline of rounds
+ * collects them one round late, when that chain has long finished, instead of waiting for the last batch's. */
+int  flacb200_encode_fetch_md5_back(flacb200_ctx *ctx, int back, uint8_t *digests, size_t cap);
 /* Copy results to host memory (any pointer may be NULL). arena_cap in bytes. */
 int  flacb200_encode_fetch(flacb200_ctx *ctx, uint8_t *arena, size_t arena_cap,
                            uint64_t *frame_off, uint32_t *frame_len, uint32_t *frame_samples,
@@ -229,6 +232,15 @@ int  flacb200_host_path_info(flacb200_ctx *ctx, double *v, int n);
  * coalesced into shared GPU batches by a per-device dispatcher; this reports how many batches / jobs it has run.  Handles
  * choose their device from FLACB200_DEVICE=<index> or round-robin over FLACB200_DEVICES=<i,j,...> (default 0). */
 int  flacb200_dispatch_stats(int device, uint64_t *batches, uint64_t *jobs);
+/* libm-log guard.  libFLAC's LPC order guess and its "don't even try" test compare costs computed with libm log(); CUDA's log is within
+ * an ulp of glibc's but not bit-identical.  Every such decision whose runner-up lies within 1e-12 relative of the winner (thousands of ulps)
+ * is logged by the kernels and repeated on the host with the libm the reference links against; when the host decides otherwise the
+ * batch is encoded once more with the host's decisions before any result is handed out.  v[0] decisions inside the band in the last
+ * batch, v[1] confirmed by the host, v[2] overridden (second pass ran), v[3] not checked (more than 1024 in one batch; also reported as
+ * flacb200_enc_result.log_guard_hits).  flacb200_set_log_guard is a test hook: band width, and flip != 0 makes the kernels take the
+ * runner-up inside the band, i.e. decide wrongly on purpose. */
+int  flacb200_log_guard_info(flacb200_ctx *ctx, uint64_t *v);
+int  flacb200_set_log_guard(flacb200_ctx *ctx, double rel, int flip);
 /* Kernel launches issued by this ctx so far (bench.py's gpu_launches). */
 uint64_t flacb200_launch_count(const flacb200_ctx *ctx);
 

@@ -99,6 +99,9 @@ def lib():
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64),
                                              C.c_void_p, C.c_void_p, C.c_void_p]
     L.flacb200_host_path_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.flacb200_log_guard_info.argtypes = [C.c_void_p, C.c_void_p]
+    L.flacb200_set_log_guard.argtypes = [C.c_void_p, C.c_double, C.c_int]
+    L.flacb200_encode_fetch_md5_back.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.flacb200_encode_host_submit.argtypes = [C.c_void_p, C.POINTER(EncConfig), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     L.flacb200_encode_host_collect.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
@@ -147,6 +150,15 @@ class Engine:
     def join(self):
         """Make the engine stream wait for the side-stream work (MD5, finalize) of all in-flight batches."""
         self._check(self._L.flacb200_join(self._h))
+
+    def set_log_guard(self, rel=1e-12, flip=False):
+        """Test hook for the libm-log guard: band width and deliberately wrong device decisions (flacb200_set_log_guard)."""
+        self._check(self._L.flacb200_set_log_guard(self._h, float(rel), int(flip)))
+
+    def log_guard_info(self):
+        v = np.zeros(4, np.uint64)
+        self._check(self._L.flacb200_log_guard_info(self._h, v.ctypes.data))
+        return dict(in_band=int(v[0]), confirmed=int(v[1]), overridden=int(v[2]), unchecked=int(v[3]))
 
     def set_profiling(self, on=True):
         self._check(self._L.flacb200_set_profiling(self._h, int(on)))
@@ -209,6 +221,13 @@ class Engine:
             n = int(self.result(wait_md5=False).n_streams)
         out = np.zeros((max(n, 1), 16), np.uint8)
         self._check(self._L.flacb200_encode_fetch_md5(self._h, out.ctypes.data, out.nbytes))
+        return out[:n]
+
+    def fetch_md5_back(self, back=1):
+        """Digests of the batch `back` batches before the last one (same layout); see flacb200_encode_fetch_md5_back."""
+        n = self._last_n_streams
+        out = np.zeros((max(n, 1), 16), np.uint8)
+        self._check(self._L.flacb200_encode_fetch_md5_back(self._h, int(back), out.ctypes.data, out.nbytes))
         return out[:n]
 
     def fetch(self):

@@ -777,6 +777,8 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
 
         // up: lpc.c FLAC__lpc_compute_best_order -- first strict minimum, initial best (uint32_t)-1
         int guess;
+        uint32_t guard_kind = 0;
+        const uint32_t guard_overhead = (uint32_t)sbps + P.qlp_precision;
         {
             const double escale = FB_DDIV(0.5, (double)N);
             const uint32_t overhead = (uint32_t)sbps + P.qlp_precision;
@@ -793,20 +795,26 @@ analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frame
                 if (ob < bb || (ob == bb && oi < bi)) { bb = ob; bi = oi; }
             }
             guess = (bb < 4294967295.0) ? bi : 1;
-            // guard band: a runner-up within 1e-12 relative (several thousand ulps of the log) of the winner could flip under a libm log that
-            // differs in the last ulp (DESIGN.md "log guard"); counted, never silently ignored
+            // guard band: a runner-up within guard_rel (1e-12 relative: several thousand ulps of the log) of the winner could flip under a libm
+            // log that differs in the last ulp: the decision is logged and the host repeats it with the reference's libm (DESIGN.md "log guard")
             const int ul_best = __shfl_sync(0xffffffffu, (int)ul, guess & 31);
-            const bool amb = (lane >= 1 && lane <= max_this && lane != guess) && (ul || ul_best) &&
-                             fabs(bits - bb) <= 1e-12 * fabs(bb);
-            if (__any_sync(0xffffffffu, amb) && lane == 0 && stats) atomicAdd(&stats->log_ambiguous, 1ull);
+            const bool amb = (lane >= 1 && lane <= max_this && lane != guess) && (ul || ul_best) && fabs(bits - bb) <= P.guard_rel * fabs(bb);
+            const unsigned amb_mask = __ballot_sync(0xffffffffu, amb);
+            guard_kind = amb_mask ? 1u : 0u;
+            if (amb_mask && P.guard_flip) guess = __ffs((int)amb_mask) - 1;
         }
         if (dg && step < kMaxApodSteps) { if (lane < max_this) dg->lpc_err[step][lane] = ws.lperr[lane]; if (lane == 0) dg->lpc_order[step] = guess; }
 
+        const LogGuardOverride* g_ov = P.guard_n_ovr ? guard_find(P, fd, s, step) : nullptr;
+        if (g_ov) guess = g_ov->guess;
         const int order = guess;
         bool ul2;
         const double rbps = expected_bits_per_sample(ws.lperr[order - 1], FB_DDIV(0.5, (double)(N - order)), &ul2);
-        if (ul2 && fabs(rbps - (double)sbps) <= 1e-12 * (double)sbps && lane == 0 && stats) atomicAdd(&stats->log_ambiguous, 1ull);
-        if (!(rbps >= (double)sbps)) {
+        bool g_skip = rbps >= (double)sbps;
+        if (ul2 && fabs(rbps - (double)sbps) <= P.guard_rel * (double)sbps) { guard_kind |= 2u; if (P.guard_flip) g_skip = !g_skip; }
+        if (g_ov) g_skip = g_ov->skip != 0;
+        else if (guard_kind) guard_record(P, stats, fd, s, step, N, sbps, max_this, guard_overhead, ws.lperr, guess, g_skip, guard_kind, lane);
+        if (!g_skip) {
             int prec = (int)P.qlp_precision;
             if (sbps <= 17) prec = min(prec, 32 - sbps - (int)ilog2_u32((uint32_t)order));
             if (lane == 0) {

@@ -17,6 +17,30 @@ struct __align__(16) WarpScratch {
     int32_t  misc[8];
 };
 
+// ---- libm-log guard: lookup of a host override / logging of a decision inside the band (warp-uniform calls) ----
+__device__ __forceinline__ const LogGuardOverride* guard_find(const EncParams& P, const FrameDesc& fd, int s, int step) {
+    for (uint32_t i = 0; i < P.guard_n_ovr; i++) {
+        const LogGuardOverride* o = P.guard_ovr + i;
+        if (o->stream == fd.stream && o->frame_number == fd.frame_number && o->signal == (uint32_t)s && o->step == (uint32_t)step) return o;
+    }
+    return nullptr;
+}
+__device__ __forceinline__ void guard_record(const EncParams& P, EncStats* stats, const FrameDesc& fd, int s, int step, int N, int sbps, int max_order,
+                                             uint32_t overhead, const double* lperr, int guess, bool skip, uint32_t kind, int lane) {
+    if (!stats) return;
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(&stats->log_ambiguous, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (!P.guard_log || slot >= P.guard_cap) return;
+    LogGuardEntry* e = P.guard_log + slot;
+    if (lane == 0) {
+        e->stream = fd.stream; e->frame_number = fd.frame_number; e->signal = (uint32_t)s; e->step = (uint32_t)step;
+        e->N = (uint32_t)N; e->sbps = (uint32_t)sbps; e->max_order = (uint32_t)max_order; e->overhead = overhead;
+        e->guess = guess; e->skip = skip ? 1 : 0; e->kind = kind; e->pad = 0;
+    }
+    if (lane < kMaxOrder) e->lperr[lane] = lane < max_order ? lperr[lane] : 0.0;
+}
+
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

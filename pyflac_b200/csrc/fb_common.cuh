@@ -38,7 +38,23 @@ struct EncParams {
     uint32_t an_stride;          // analysis kernel: int32 words staged per signal (32 padded rows)
     uint32_t loose_frames;       // loose mid/side (levels 1, 4 on stereo): a full L/R/M/S decision every this many frames; 0 = off
     uint32_t limit_min_bitrate;  // up: process_subframes_ -- never emit a frame made of constant subframes only
+    // libm-log guard (DESIGN.md "log guard"): decisions whose runner-up lies within guard_rel (relative) are logged for the host,
+    // which repeats them with the libm log the reference links against and sends back overrides when it decides otherwise
+    uint32_t guard_flip;         // test hook: take the runner-up inside the band (a deliberately wrong device decision)
+    uint32_t guard_cap, guard_n_ovr, guard_pad;
+    double   guard_rel;
+    struct LogGuardEntry* guard_log;
+    const struct LogGuardOverride* guard_ovr;
 };
+
+struct LogGuardEntry {
+    uint32_t stream, frame_number, signal, step;
+    uint32_t N, sbps, max_order, overhead;
+    int32_t  guess, skip;        // what the device decided: LPC order, and whether the candidate was dropped as hopeless
+    uint32_t kind, pad;          // bit 0: the order choice was inside the band, bit 1: the "don't even try" test was
+    double   lperr[kMaxOrder];
+};
+struct LogGuardOverride { uint32_t stream, frame_number, signal, step; int32_t guess, skip; };
 
 struct FrameDesc {
     uint64_t pcm_off;            // element offset (samples*channels) of the frame's first sample in the PCM buffer

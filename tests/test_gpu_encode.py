@@ -448,3 +448,61 @@ def test_host_pipelined_submit_collect(eng, checkers, bps):
     out = eng.encode_host_to_host(cfg, flats[1], offs, sizes // ch)
     si = out["streams"][3]
     assert out["arena"][int(si.byte_off): int(si.byte_off + si.byte_len)].tobytes() == checkers.oracle_encode(batches[1][3], 48000, bps, 5, 4096)
+
+
+def test_fetch_md5_of_the_previous_batch(eng):
+    """flacb200_encode_fetch_md5_back: while batch B's chain may still run, the digests of batch A (same layout) are available"""
+    from pyflac_b200 import _native as nat
+    lens = [4096 * 6 + 17 * s for s in range(12)]
+    sizes = np.array([2 * n for n in lens], np.uint64)
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+    cfg = nat.Engine.make_config(48000, 2, 16, 5, 0)
+    A = [music_like(n, 2, 48000, 16, seed=40 + s) for s, n in enumerate(lens)]
+    B = [music_like(n, 2, 48000, 16, seed=90 + s) for s, n in enumerate(lens)]
+    eng.encode_host(cfg, np.concatenate([x.reshape(-1) for x in A]), offs, sizes // 2)
+    eng.result(wait_md5=False)
+    eng.encode_host(cfg, np.concatenate([x.reshape(-1) for x in B]), offs, sizes // 2)
+    eng.result(wait_md5=False)
+    da, db = eng.fetch_md5_back(1), eng.fetch_md5()
+    for s in range(len(lens)):
+        assert bytes(da[s]) == hashlib.md5(A[s].tobytes()).digest()
+        assert bytes(db[s]) == hashlib.md5(B[s].tobytes()).digest()
+
+
+@pytest.mark.parametrize("path", ["device", "host_call", "submit_collect"])
+@pytest.mark.parametrize("level,bps,ch", [(5, 16, 2), (8, 24, 1)])
+def test_log_guard_host_redecision(checkers, path, level, bps, ch):
+    """decisions that depend on libm log() inside the guard band are repeated on the host.  With the band widened to
+    1e-2 many decisions are logged and the host confirms them (same bytes as the reference); with the kernels told to take the
+    runner-up inside the band the host overrides every wrong decision and the second pass still yields the reference's bytes."""
+    from pyflac_b200 import _native as nat
+    eng = nat.Engine(0)
+    xs = [music_like(4096 * 3 + 100 * s, ch, 48000, bps, seed=500 + s) for s in range(6)]
+    dt = np.int16 if bps <= 16 else np.int32
+    flat = np.concatenate([x.reshape(-1) for x in xs]).astype(dt)
+    sizes = np.array([x.size for x in xs], np.uint64)
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+    cfg = nat.Engine.make_config(48000, ch, bps, level, 4096)
+    want = [checkers.oracle_encode(x, 48000, bps, level, 4096) for x in xs]
+
+    def run():
+        if path == "device":
+            eng.encode_host(cfg, flat, offs, sizes // ch)
+            out = eng.fetch()
+        elif path == "host_call":
+            out = eng.encode_host_to_host(cfg, flat, offs, sizes // ch)
+        else:
+            out = eng.collect_host(eng.submit_host(cfg, flat, offs, sizes // ch))
+        return [out["arena"][int(si.byte_off): int(si.byte_off + si.byte_len)].tobytes() for si in out["streams"]]
+
+    assert run() == want and eng.log_guard_info()["in_band"] == 0       # the real band: nothing inside it
+    eng.set_log_guard(1e-2, flip=False)
+    assert run() == want
+    gi = eng.log_guard_info()
+    assert gi["in_band"] > 0 and gi["confirmed"] == gi["in_band"] - gi["unchecked"] and gi["overridden"] == 0, gi
+    eng.set_log_guard(1e-2, flip=True)
+    assert run() == want
+    gi = eng.log_guard_info()
+    assert gi["overridden"] > 0 and gi["unchecked"] == 0, gi
+    eng.set_log_guard(1e-12, flip=False)
+    assert run() == want
