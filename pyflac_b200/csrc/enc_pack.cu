@@ -501,7 +501,14 @@ __device__ __noinline__ void md5_wait_for_chunk(const Md5Gate& gate, int n_strea
     // every lane polls (one broadcast load per try): a single polling lane left the warp split behind the wait -- lane 0 and
     // lanes 1..31 then ran the whole hash as two passes, 2x the time -- whatever __syncwarp() followed
     const volatile uint32_t* f = gate.flags + c;
-    while (__any_sync(0xffffffffu, *f == 0u)) __nanosleep(500);
+    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (__any_sync(0xffffffffu, *f == 0u)) {
+        __nanosleep(500);
+        // the flag is set by the copy stream; if that stream cannot make progress while this kernel runs (a profiler that
+        // serialises all work) give up loudly after 4 s instead of hanging the GPU
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) __trap();
+    }
     __threadfence();
 }
 template <typename PcmT, bool K24>
