@@ -1,27 +1,25 @@
-// enc_fused.cu -- the whole per-frame encode path in ONE kernel for 16-bit stereo (the headline layout):
+// enc_fused.cu -- the per-frame encode path for 16-bit stereo (the headline layout) on TMA-staged frame tiles:
 //
-//   stage (TMA) -> OR/AND -> [autocorrelation || fixed predictors] -> LPC candidates -> choose -> pack -> CRC-16 -> store
+//   autoc_kernel (enc_analyze.cu, un-shifted mode: window + f64 autocorrelation chains, no OR/AND pass in front)
+//   -> fused_analyze_kernel: stage (TMA) -> OR/AND -> fixed predictors -> LPC candidates -> choose        (rows E2-E11)
+//   -> fused_pack_kernel:    stage (TMA) -> Rice bodies -> frame image -> CRC-16 -> store                 (row E12)
 //
-// One CTA of eight warps per frame, several CTAs resident per SM.  The frame -- 16 KiB of interleaved int16 pairs for a
-// 4096-sample block -- crosses HBM exactly once: warp 0 issues one cp.async.bulk (TMA, SASS UBLKCP) per tile row, the
-// copies complete on an mbarrier, and every later phase (scope rows E2-E12) works on the shared-memory tile.  Nothing
-// but the finished frame bytes and 4 bytes of length goes back to HBM (the multi-kernel path of enc_analyze.cu /
-// enc_pack.cu re-reads the PCM four times and round-trips plans and autocorrelations; it remains the path for the other
-// layouts, loose mid/side and debug traces).
+// The frame -- 16 KiB of interleaved int16 pairs for a 4096-sample block -- is staged once per kernel: warp 0 issues one
+// cp.async.bulk (TMA, SASS UBLKCP) per tile row, the copies complete on an mbarrier, and every phase works on the
+// shared-memory tile.  Between the kernels travel the autocorrelations (HBM scratch, 512 B per frame), two 128-byte plans
+// and the channel assignment per frame.  A first version ran everything in ONE kernel per frame; phases of very different
+// parallelism (a few sequential f64 chains next to thousands of independent samples) idled at its barriers, and splitting at
+// the two natural boundaries was faster although the tile is staged twice.  The multi-kernel path of enc_analyze.cu /
+// enc_pack.cu stages with plain loads and remains the path for the other layouts, loose mid/side and debug traces.
 //
 // Tile layout: 32 rows of B0w = roundup4(ceil(N/32)) packed words (L | R << 16), row stride RS = B0w (+4 so that RS/4
 // is odd).  Lane p of an analysis warp streams row p with 16-byte shared loads: eight consecutive lanes hit eight
 // different 16-byte bank groups, so the quarter-warp wavefronts of LDS.128 are conflict free, and the row starts stay
 // 16-byte aligned, which is what lets TMA write them.
 //
-// Phases that cannot fill a CTA overlap: the autocorrelation (a handful of strictly sequential f64 chains, latency
-// bound) runs on one or a few warps while the other warps do the integer fixed-predictor analysis; the other CTAs of
-// the SM are in different phases and fill the issue slots.
-//
 // Instruction diet against the multi-kernel path (which was issue bound):
 //  * fixed predictors: ONE pass yields the five error sums AND the per-partition sums of all five orders; the
 //    residual pass of the chosen order is gone (|k-th difference| is the order-k residual);
-//  * autocorrelation: a lane owns two lags (not four) of one signal, so a frame's 36 chains use 20 lanes of one warp;
 //  * pack: a lane codes 16 consecutive samples; its bits form one contiguous run that is assembled in a register
 //    and stored word by word -- only the first and last word of a run are shared with a neighbour and need atomicOr.
 //

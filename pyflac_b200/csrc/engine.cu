@@ -1,9 +1,11 @@
 // engine.cu -- host side of the batch encoder: settings resolution, frame slicing, window tables,
 // device buffers, kernel sequencing.  C ABI in include/flacb200.h.
 //
-// Pipeline per batch (all on one CUDA stream, MD5 forked onto a side stream):
-//   [H2D pcm if host] -> analyze_kernel -> pack_kernel -> scan_kernel -> compact_kernel -> finalize_kernel
-//                     \-> md5_kernel ---------------------------------------------------/
+// Pipeline per batch (all on one CUDA stream, MD5 forked onto the output set's side stream):
+//   [H2D pcm if host] -> autoc -> analyze -> pack -> scan_kernel -> compact_kernel -> finalize_kernel
+//                     \-> md5_kernel ------------------------------------------------> md5_patch_kernel
+// Host -> host: flacb200_encode_batch_host (one synchronous call, chunks of streams pipelined over H2D / kernels / D2H) and
+// flacb200_encode_host_submit / _collect (the same with up to three batches in flight).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
