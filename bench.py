@@ -645,6 +645,10 @@ def main():
                              "flacb200_encode_host_submit / _collect, 3 batches in flight: step i copies its PCM in from pinned host memory and "
                              "reads batch i-2's images + index + STREAMINFO digests back; all K batches collected inside the timed region"),
                     "bytes_identical_to_sync_call": pipe_bad == 0.0,
+                    # the step is the H2D copy: what the host's PCIe / memory fabric gives each GPU when all N ranks copy at once
+                    "link_GBps": {"h2d_per_gpu": pcm_bytes / (pipe_ms_max / args.steps * 1e-3) / 1e9,
+                                  "d2h_per_gpu": out_bytes / (pipe_ms_max / args.steps * 1e-3) / 1e9,
+                                  "h2d_plus_d2h_all_gpus": world * (pcm_bytes + out_bytes) / (pipe_ms_max / args.steps * 1e-3) / 1e9},
                     "sync_call": {"value": sync_val, "unit": UNIT, "ms_per_step": e2e_ms_max / args.steps,
                                   "what": "flacb200_encode_batch_host: one synchronous call per step, complete results (incl. MD5) on return",
                                   "last_call_breakdown_ms": host_path_ms}},
