@@ -54,6 +54,18 @@ typedef struct {
     uint32_t streamable_subset;   /* validation only (stream_encoder.h:1005-1017) */
     uint32_t debug_trace;         /* 1: keep per-signal analysis traces (tests) */
     uint32_t limit_min_bitrate;   /* FLAC__stream_encoder_set_limit_min_bitrate (stream_encoder.h:1105-1115) */
+    /* Fine-grained settings (builder/encoder.py:274-284; libFLAC's set_do_mid_side_stereo ... set_apodization).  tune != 0: the seven
+     * fields below replace what the compression level stands for (all of them: fill in the level's own values where nothing changes);
+     * tune == 0: they are ignored.  Supported range of this build: max_lpc_order <= 12, max_residual_partition_order <= 6, one
+     * apodization of the tukey family -- apod_parts 1 = tukey(apod_p), 2 or 3 = subdivide_tukey(parts/apod_p) -- anything else is
+     * FLACB200_ERR_UNSUPPORTED. */
+    uint32_t tune;
+    uint32_t do_mid_side, loose_mid_side;
+    uint32_t max_lpc_order;       /* 0 = fixed predictors only */
+    uint32_t qlp_coeff_precision; /* 0 = libFLAC's automatic choice, else 5..15 */
+    uint32_t max_residual_partition_order;
+    uint32_t apod_parts;
+    float    apod_p;
 } flacb200_enc_config;
 
 typedef struct {

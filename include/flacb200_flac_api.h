@@ -95,8 +95,10 @@ FLAC__bool FLAC__stream_encoder_set_blocksize(FLAC__StreamEncoder *encoder, uint
 FLAC__bool FLAC__stream_encoder_set_streamable_subset(FLAC__StreamEncoder *encoder, FLAC__bool value);
 FLAC__bool FLAC__stream_encoder_set_limit_min_bitrate(FLAC__StreamEncoder *encoder, FLAC__bool value);
 FLAC__bool FLAC__stream_encoder_set_total_samples_estimate(FLAC__StreamEncoder *encoder, FLAC__uint64 value);
-/* in pyFLAC's cdef (builder/encoder.py:274-284) but never called by pyFLAC: accepted, and init fails loudly
- * if they were used to leave the compression-level presets */
+/* in pyFLAC's cdef (builder/encoder.py:274-284), never called by pyFLAC.  Applied like libFLAC's (after the compression level's presets);
+ * bit-exact within this build's range: max_lpc_order <= 12, max_residual_partition_order <= 6, qlp_coeff_precision 0 / 5..15, mid/side
+ * and loose mid/side, apodization "tukey(P)" or "subdivide_tukey(N[/P])" with N <= 3.  Outside it (exhaustive model / precision
+ * search, a minimum partition order, other window families or lists) init returns ENCODER_ERROR instead of encoding something else. */
 FLAC__bool FLAC__stream_encoder_set_do_mid_side_stereo(FLAC__StreamEncoder *encoder, FLAC__bool value);
 FLAC__bool FLAC__stream_encoder_set_loose_mid_side_stereo(FLAC__StreamEncoder *encoder, FLAC__bool value);
 FLAC__bool FLAC__stream_encoder_set_apodization(FLAC__StreamEncoder *encoder, const char *specification);

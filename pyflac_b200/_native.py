@@ -27,7 +27,10 @@ class EncConfig(C.Structure):
     _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32),
                 ("compression_level", C.c_uint32), ("blocksize", C.c_uint32), ("container_bytes", C.c_uint32),
                 ("write_prologue", C.c_uint32), ("do_md5", C.c_uint32), ("streamable_subset", C.c_uint32),
-                ("debug_trace", C.c_uint32), ("limit_min_bitrate", C.c_uint32)]
+                ("debug_trace", C.c_uint32), ("limit_min_bitrate", C.c_uint32),
+                ("tune", C.c_uint32), ("do_mid_side", C.c_uint32), ("loose_mid_side", C.c_uint32), ("max_lpc_order", C.c_uint32),
+                ("qlp_coeff_precision", C.c_uint32), ("max_residual_partition_order", C.c_uint32), ("apod_parts", C.c_uint32),
+                ("apod_p", C.c_float)]
 
 
 class StreamInfo(C.Structure):
@@ -181,11 +184,22 @@ class Engine:
     # ------------------------------------------------------------ encode
     @staticmethod
     def make_config(sample_rate, channels, bits_per_sample, compression_level=5, blocksize=0, container_bytes=None,
-                    write_prologue=True, do_md5=True, streamable_subset=True, debug_trace=False, limit_min_bitrate=False):
+                    write_prologue=True, do_md5=True, streamable_subset=True, debug_trace=False, limit_min_bitrate=False, tune=None):
+        """tune: None (the level's presets) or a dict with any of do_mid_side, loose_mid_side, max_lpc_order, qlp_coeff_precision,
+        max_residual_partition_order, apod_parts, apod_p -- the fields it leaves out keep the level's values."""
         if container_bytes is None:
             container_bytes = 2 if bits_per_sample <= 16 else 4
-        return EncConfig(sample_rate, channels, bits_per_sample, compression_level, blocksize, container_bytes,
-                         int(write_prologue), int(do_md5), int(streamable_subset), int(debug_trace), int(limit_min_bitrate))
+        cfg = EncConfig(sample_rate, channels, bits_per_sample, compression_level, blocksize, container_bytes,
+                        int(write_prologue), int(do_md5), int(streamable_subset), int(debug_trace), int(limit_min_bitrate))
+        if tune is not None:
+            ms, loose, lpc, po, parts = [(0, 0, 0, 3, 1), (1, 1, 0, 3, 1), (1, 0, 0, 3, 1), (0, 0, 6, 4, 1), (1, 1, 8, 4, 1), (1, 0, 8, 5, 1), (1, 0, 8, 6, 2),
+                                         (1, 0, 12, 6, 2), (1, 0, 12, 6, 3)][min(int(compression_level), 8)]
+            cfg.tune = 1
+            cfg.do_mid_side = int(tune.get("do_mid_side", ms)); cfg.loose_mid_side = int(tune.get("loose_mid_side", loose))
+            cfg.max_lpc_order = int(tune.get("max_lpc_order", lpc)); cfg.qlp_coeff_precision = int(tune.get("qlp_coeff_precision", 0))
+            cfg.max_residual_partition_order = int(tune.get("max_residual_partition_order", po))
+            cfg.apod_parts = int(tune.get("apod_parts", parts)); cfg.apod_p = float(tune.get("apod_p", 0.5))
+        return cfg
 
     def encode_device(self, cfg, pcm_ptr, pcm_elems, stream_off, stream_samples, first_frame_number=None):
         """Asynchronous batch encode of PCM resident in HBM. stream_off/stream_samples: uint64 numpy arrays."""

@@ -209,10 +209,13 @@ extern "C" int flacb200_enc_validate(const flacb200_enc_config* c) {
     if (c->bits_per_sample < 4 || c->bits_per_sample > 32) return 5;
     if (c->sample_rate > 1048575u) return 6;
     const uint32_t lvl = c->compression_level > 8 ? 8 : c->compression_level;
-    const uint32_t maxlpc = kLevels[lvl].max_lpc;
+    const uint32_t maxlpc = c->tune ? c->max_lpc_order : kLevels[lvl].max_lpc;
+    const uint32_t maxpo = c->tune ? c->max_residual_partition_order : kLevels[lvl].max_po;
     uint32_t bs = c->blocksize ? c->blocksize : (maxlpc == 0 ? 1152u : 4096u);
     if (bs < 16 || bs > 65535) return 7;
+    if (maxlpc > 32) return 8;                                           // INVALID_MAX_LPC_ORDER
     if (bs < maxlpc) return 10;
+    if (c->tune && c->qlp_coeff_precision != 0 && (c->qlp_coeff_precision < 5 || c->qlp_coeff_precision > 15)) return 9;   // INVALID_QLP_COEFF_PRECISION
     if (c->streamable_subset) {
         const uint32_t b = c->bits_per_sample;
         if (!(b == 8 || b == 12 || b == 16 || b == 20 || b == 24 || b == 32)) return 11;
@@ -220,6 +223,7 @@ extern "C" int flacb200_enc_validate(const flacb200_enc_config* c) {
         if (bs > 16384) return 11;
         // a subset frame header must be able to carry the rate: above 16 bits only multiples of 10 Hz can (format.h:  FLAC__format_sample_rate_is_subset)
         if (c->sample_rate >= (1u << 16) && c->sample_rate % 10u != 0u) return 11;
+        if (maxpo > 8) return 11;                                        // FLAC__SUBSET_MAX_RICE_PARTITION_ORDER
     }
     return 0;
 }
@@ -230,15 +234,25 @@ static int resolve_params(flacb200_ctx* ctx, const flacb200_enc_config& c, EncPa
     const uint32_t lvl = c.compression_level > 8 ? 8 : c.compression_level;
     memset(&P, 0, sizeof P);
     P.channels = c.channels; P.bps = c.bits_per_sample; P.sample_rate = c.sample_rate;
-    P.max_lpc_order = kLevels[lvl].max_lpc;
+    // the level's presets, or the caller's fine-grained settings (stream_encoder.h: set_do_mid_side_stereo ... set_apodization)
+    bool ms = kLevels[lvl].ms != 0, loose = kLevels[lvl].loose != 0;
+    P.max_lpc_order = kLevels[lvl].max_lpc; P.max_part_order = kLevels[lvl].max_po; P.apod_parts = (uint32_t)kLevels[lvl].parts;
+    uint32_t qlp = 0;
+    if (c.tune) {
+        ms = c.do_mid_side != 0; loose = c.loose_mid_side != 0;
+        P.max_lpc_order = c.max_lpc_order; P.max_part_order = c.max_residual_partition_order > 15 ? 15 : c.max_residual_partition_order;
+        P.apod_parts = c.apod_parts; qlp = c.qlp_coeff_precision;
+        if (P.max_lpc_order > (uint32_t)kMaxOrder || P.max_part_order > (uint32_t)kMaxPartOrder || P.apod_parts < 1 || P.apod_parts > 3 ||
+            qlp > 15 || !(c.apod_p >= 0.0f && c.apod_p <= 1.0f))
+            return fail(ctx, FLACB200_ERR_UNSUPPORTED, "fine-grained settings outside this build's range (max_lpc_order <= 12, max_residual_partition_order <= 6, tukey / subdivide_tukey(2..3), qlp_coeff_precision <= 15)");
+    }
     P.blocksize = c.blocksize ? c.blocksize : (P.max_lpc_order == 0 ? 1152u : 4096u);
-    P.do_mid_side = (kLevels[lvl].ms && c.channels == 2) ? 1u : 0u;
-    P.max_part_order = kLevels[lvl].max_po;
-    P.apod_parts = (uint32_t)kLevels[lvl].parts;
+    P.do_mid_side = (ms && c.channels == 2) ? 1u : 0u;
     P.rice_limit = c.bits_per_sample > 16 ? 31u : 15u;
     P.container_bytes = c.container_bytes;
     P.n_signals = c.channels + (P.do_mid_side ? 2u : 0u);
-    if (c.bits_per_sample < 16) { uint32_t p = 2 + c.bits_per_sample / 2; P.qlp_precision = p < 5 ? 5 : p; }
+    if (qlp) P.qlp_precision = qlp;
+    else if (c.bits_per_sample < 16) { uint32_t p = 2 + c.bits_per_sample / 2; P.qlp_precision = p < 5 ? 5 : p; }
     else if (c.bits_per_sample == 16) {
         const uint32_t b = P.blocksize;
         P.qlp_precision = b <= 192 ? 7 : b <= 384 ? 8 : b <= 576 ? 9 : b <= 1152 ? 10 : b <= 2304 ? 11 : b <= 4608 ? 12 : 13;
@@ -247,7 +261,7 @@ static int resolve_params(flacb200_ctx* ctx, const flacb200_enc_config& c, EncPa
         P.qlp_precision = b <= 384 ? 13 : b <= 1152 ? 14 : 15;
     }
     // up: FLAC__stream_encoder_init_*: loose_mid_side_stereo_frames = (uint32_t)(sample_rate * 0.4 / blocksize + 0.5), at least 1
-    if (kLevels[lvl].loose && P.do_mid_side) {
+    if (loose && P.do_mid_side) {
         P.loose_frames = (uint32_t)((double)c.sample_rate * 0.4 / (double)P.blocksize + 0.5);
         if (P.loose_frames == 0) P.loose_frames = 1;
     }
@@ -411,7 +425,8 @@ static int plan_batch(flacb200_ctx* ctx, const flacb200_enc_config& cfg, uint32_
     EncParams P;
     int rc = resolve_params(ctx, cfg, P);
     if (rc) return rc;
-    const float wp = P.apod_parts == 1 ? 0.5f : 0.5f / (float)P.apod_parts;   // up: set_apodization: p/parts in float
+    const float ap = cfg.tune ? cfg.apod_p : 0.5f;
+    const float wp = P.apod_parts == 1 ? ap : ap / (float)P.apod_parts;       // up: set_apodization: tukey(p); subdivide_tukey: p/parts in float
     if (wp != ctx->window_p) { ctx->h_windows.clear(); ctx->window_off.clear(); ctx->window_p = wp; }
     ctx->h_frames.clear();
     ctx->h_stream_first.assign(ns, 0); ctx->h_stream_nframes.assign(ns, 0);

@@ -258,7 +258,12 @@ struct EncImpl {
     FLAC__bool verify = 0, streamable_subset = 1, limit_min_bitrate = 0;
     uint32_t channels = 2, bps = 16, sample_rate = 44100, level = 5, blocksize = 0;
     uint64_t total_samples_estimate = 0;
-    bool custom_tuning = false;            // a fine-grained setter moved away from the level presets
+    // fine-grained settings (stream_encoder.h:  set_do_mid_side_stereo ... set_apodization): set_compression_level writes the level's
+    // presets into them, the individual setters change them afterwards, exactly as in libFLAC
+    FLAC__bool ms = 1, loose = 0, prec_search = 0, exhaustive = 0;
+    uint32_t max_lpc = 8, qlp_prec = 0, min_po = 0, max_po = 5, rice_dist = 0, apod_parts = 1;
+    float apod_p = 0.5f;
+    bool custom_tuning = false;            // a setting this build cannot honour (exhaustive searches, other window families): init fails loudly
     int state = ST_UNINITIALIZED;
     // session
     FLAC__StreamEncoderWriteCallback write_cb = nullptr; FLAC__StreamEncoderSeekCallback seek_cb = nullptr;
@@ -282,10 +287,23 @@ struct EncImpl {
 struct Handle { FLAC__StreamEncoder pub; EncImpl impl; };
 inline EncImpl* I(const FLAC__StreamEncoder* e) { return e ? (EncImpl*)e->private_ : nullptr; }
 
+// level presets (stream_encoder.h:845-853)
+static const struct { int ms, loose; uint32_t lpc, po, parts; } kLv[9] = {{0,0,0,3,1},{1,1,0,3,1},{1,0,0,3,1},{0,0,6,4,1},{1,1,8,4,1},{1,0,8,5,1},{1,0,8,6,2},{1,0,12,6,2},{1,0,12,6,3}};
+void apply_level(EncImpl* m, uint32_t v) {
+    m->level = v > 8 ? 8 : v;
+    m->ms = kLv[m->level].ms; m->loose = kLv[m->level].loose; m->max_lpc = kLv[m->level].lpc; m->max_po = kLv[m->level].po;
+    m->apod_parts = kLv[m->level].parts; m->apod_p = 0.5f;
+    m->qlp_prec = 0; m->min_po = 0; m->rice_dist = 0; m->prec_search = 0; m->exhaustive = 0; m->custom_tuning = false;
+}
 void reset_settings(EncImpl* m) {
     m->verify = 0; m->streamable_subset = 1; m->limit_min_bitrate = 0;
-    m->channels = 2; m->bps = 16; m->sample_rate = 44100; m->level = 5; m->blocksize = 0;
-    m->total_samples_estimate = 0; m->custom_tuning = false;
+    m->channels = 2; m->bps = 16; m->sample_rate = 44100; m->blocksize = 0;
+    m->total_samples_estimate = 0;
+    apply_level(m, 5);
+}
+void fill_tuning(const EncImpl* m, flacb200_enc_config* cfg) {
+    cfg->tune = 1; cfg->do_mid_side = m->ms ? 1u : 0u; cfg->loose_mid_side = m->loose ? 1u : 0u; cfg->max_lpc_order = m->max_lpc;
+    cfg->qlp_coeff_precision = m->qlp_prec; cfg->max_residual_partition_order = m->max_po; cfg->apod_parts = m->apod_parts; cfg->apod_p = m->apod_p;
 }
 
 // ref: format.h:546-557 -- the 34-byte STREAMINFO body
@@ -336,8 +354,9 @@ bool encode_pending(FLAC__StreamEncoder* e, uint64_t n) {
     job.cfg.compression_level = m->level; job.cfg.blocksize = m->N; job.cfg.container_bytes = 4;
     job.cfg.write_prologue = 0; job.cfg.do_md5 = 0; job.cfg.streamable_subset = 0; job.cfg.debug_trace = 0;
     job.cfg.limit_min_bitrate = m->limit_min_bitrate ? 1u : 0u;
+    fill_tuning(m, &job.cfg);
     job.pcm = m->pending.data(); job.n = n; job.ffn = m->frame_number; job.prev_ca = m->last_ca;
-    job.loose = (m->level == 1 || m->level == 4) && m->channels == 2;
+    job.loose = m->loose && m->ms && m->channels == 2;
     job.verify = m->verify != 0;
     m->disp->submit(&job);
     if (job.rc == 1) { m->state = ST_FRAMING_ERROR; return false; }
@@ -372,13 +391,14 @@ int init_common(FLAC__StreamEncoder* e) {
     flacb200_enc_config cfg{};
     cfg.sample_rate = m->sample_rate; cfg.channels = m->channels; cfg.bits_per_sample = m->bps; cfg.compression_level = m->level;
     cfg.blocksize = m->blocksize; cfg.container_bytes = 4; cfg.streamable_subset = (uint32_t)m->streamable_subset;
+    fill_tuning(m, &cfg);
     const int st = flacb200_enc_validate(&cfg);
     if (st != 0) return st;
-    static const uint32_t kMaxLpc[9] = {0, 0, 0, 6, 8, 8, 8, 12, 12};
-    const uint32_t lvl = m->level > 8 ? 8 : m->level;
-    m->N = m->blocksize ? m->blocksize : (kMaxLpc[lvl] == 0 ? 1152u : 4096u);
-    // limits of this build fail loudly here instead of producing a different stream (DESIGN.md "limits")
-    if (m->custom_tuning) { m->state = ST_FRAMING_ERROR; return INIT_ENCODER_ERROR; }
+    m->N = m->blocksize ? m->blocksize : (m->max_lpc == 0 ? 1152u : 4096u);
+    // limits of this build fail loudly here instead of producing a different stream (DESIGN.md "limits"): searches libFLAC's presets
+    // never run (exhaustive model / precision search, a minimum partition order), window families other than tukey, orders above 12
+    if (m->custom_tuning || m->exhaustive || m->prec_search || (m->min_po != 0 && m->max_po != 0) || m->max_lpc > 12 || m->max_po > 6 || m->qlp_prec > 15 ||
+        m->apod_parts < 1 || m->apod_parts > 3) { m->state = ST_FRAMING_ERROR; return INIT_ENCODER_ERROR; }
     {
         Dispatcher* d = dispatcher(pick_device());
         std::lock_guard<std::mutex> lk(d->mu);
@@ -450,22 +470,43 @@ FLAC__bool FLAC__stream_encoder_set_total_samples_estimate(FLAC__StreamEncoder* 
 }
 FLAC__bool FLAC__stream_encoder_set_compression_level(FLAC__StreamEncoder* e, uint32_t v) {
     EncImpl* m = I(e); if (!m || m->state != ST_UNINITIALIZED) return 0;
-    m->level = v > 8 ? 8 : v; m->custom_tuning = false; return 1;
+    apply_level(m, v); return 1;
 }
 // tuning knobs outside pyFLAC's surface: remember that the presets were left, init then refuses (fails loudly)
-#define TUNING(name, type) FLAC__bool FLAC__stream_encoder_set_##name(FLAC__StreamEncoder* e, type) { \
-    EncImpl* m = I(e); if (!m || m->state != ST_UNINITIALIZED) return 0; m->custom_tuning = true; return 1; }
-TUNING(do_mid_side_stereo, FLAC__bool)
-TUNING(loose_mid_side_stereo, FLAC__bool)
-TUNING(apodization, const char*)
-TUNING(max_lpc_order, uint32_t)
-TUNING(qlp_coeff_precision, uint32_t)
-TUNING(do_qlp_coeff_prec_search, FLAC__bool)
-TUNING(do_exhaustive_model_search, FLAC__bool)
-TUNING(min_residual_partition_order, uint32_t)
-TUNING(max_residual_partition_order, uint32_t)
-TUNING(rice_parameter_search_dist, uint32_t)
-#undef TUNING
+#define SETTER(name, type, stmt) FLAC__bool FLAC__stream_encoder_set_##name(FLAC__StreamEncoder* e, type v) { \
+    EncImpl* m = I(e); if (!m || m->state != ST_UNINITIALIZED) return 0; stmt; return 1; }
+SETTER(do_mid_side_stereo, FLAC__bool, m->ms = v)
+SETTER(loose_mid_side_stereo, FLAC__bool, m->loose = v)
+SETTER(max_lpc_order, uint32_t, m->max_lpc = v)
+SETTER(qlp_coeff_precision, uint32_t, m->qlp_prec = v)
+SETTER(do_qlp_coeff_prec_search, FLAC__bool, m->prec_search = v)
+SETTER(do_exhaustive_model_search, FLAC__bool, m->exhaustive = v)
+SETTER(min_residual_partition_order, uint32_t, m->min_po = v)
+SETTER(max_residual_partition_order, uint32_t, m->max_po = v)
+SETTER(rice_parameter_search_dist, uint32_t, (void)v)                    // accepted and dropped, as libFLAC 1.4.3 does (the getter keeps reading 0)
+#undef SETTER
+// up: FLAC__stream_encoder_set_apodization.  One window of the tukey family is what this build runs: "tukey(P)" and
+// "subdivide_tukey(N[/P])" (the two every compression level uses); a list, or any other family, makes init fail loudly.
+FLAC__bool FLAC__stream_encoder_set_apodization(FLAC__StreamEncoder* e, const char* spec) {
+    EncImpl* m = I(e);
+    if (!m || m->state != ST_UNINITIALIZED || !spec) return 0;
+    m->custom_tuning = false;
+    const size_t n = strlen(spec);
+    if (strchr(spec, ';') && strchr(spec, ';')[1] != 0) { m->custom_tuning = true; return 1; }
+    if (n > 7 && strncmp(spec, "tukey(", 6) == 0) {
+        const float p = (float)strtod(spec + 6, nullptr);
+        m->apod_parts = 1; m->apod_p = (p >= 0.0f && p <= 1.0f) ? p : 0.5f;        // out of range: libFLAC falls back to its default tukey(0.5)
+    } else if (n > 16 && strncmp(spec, "subdivide_tukey(", 16) == 0) {
+        const int parts = (int)strtod(spec + 16, nullptr);
+        if (parts > 1) {
+            const char* sl = strchr(spec, '/');
+            float p = sl ? (float)strtod(sl + 1, nullptr) : 0.5f;
+            if (p > 1.0f) p = 1.0f; else if (p < 0.0f) p = 0.0f;
+            m->apod_parts = (uint32_t)parts; m->apod_p = p;
+        } else { m->apod_parts = 1; m->apod_p = 0.5f; }
+    } else m->custom_tuning = true;
+    return 1;
+}
 
 int FLAC__stream_encoder_get_state(const FLAC__StreamEncoder* e) { return I(e) ? I(e)->state : ST_UNINITIALIZED; }
 const char* FLAC__stream_encoder_get_resolved_state_string(const FLAC__StreamEncoder* e) { return FLAC__StreamEncoderStateString[FLAC__stream_encoder_get_state(e)]; }
@@ -481,18 +522,16 @@ uint32_t FLAC__stream_encoder_get_channels(const FLAC__StreamEncoder* e) { retur
 uint32_t FLAC__stream_encoder_get_bits_per_sample(const FLAC__StreamEncoder* e) { return I(e)->bps; }
 uint32_t FLAC__stream_encoder_get_sample_rate(const FLAC__StreamEncoder* e) { return I(e)->sample_rate; }
 uint32_t FLAC__stream_encoder_get_blocksize(const FLAC__StreamEncoder* e) { return I(e)->state == ST_UNINITIALIZED ? I(e)->blocksize : I(e)->N; }
-// level presets (stream_encoder.h:845-853)
-static const struct { int ms, loose; uint32_t lpc, po; } kLv[9] = {{0,0,0,3},{1,1,0,3},{1,0,0,3},{0,0,6,4},{1,1,8,4},{1,0,8,5},{1,0,8,6},{1,0,12,6},{1,0,12,6}};
-FLAC__bool FLAC__stream_encoder_get_do_mid_side_stereo(const FLAC__StreamEncoder* e) { return kLv[I(e)->level].ms; }
-FLAC__bool FLAC__stream_encoder_get_loose_mid_side_stereo(const FLAC__StreamEncoder* e) { return kLv[I(e)->level].loose; }
-uint32_t FLAC__stream_encoder_get_max_lpc_order(const FLAC__StreamEncoder* e) { return kLv[I(e)->level].lpc; }
-uint32_t FLAC__stream_encoder_get_qlp_coeff_precision(const FLAC__StreamEncoder*) { return 0; }
-FLAC__bool FLAC__stream_encoder_get_do_qlp_coeff_prec_search(const FLAC__StreamEncoder*) { return 0; }
+FLAC__bool FLAC__stream_encoder_get_do_mid_side_stereo(const FLAC__StreamEncoder* e) { return I(e)->ms; }
+FLAC__bool FLAC__stream_encoder_get_loose_mid_side_stereo(const FLAC__StreamEncoder* e) { return I(e)->loose; }
+uint32_t FLAC__stream_encoder_get_max_lpc_order(const FLAC__StreamEncoder* e) { return I(e)->max_lpc; }
+uint32_t FLAC__stream_encoder_get_qlp_coeff_precision(const FLAC__StreamEncoder* e) { return I(e)->qlp_prec; }
+FLAC__bool FLAC__stream_encoder_get_do_qlp_coeff_prec_search(const FLAC__StreamEncoder* e) { return I(e)->prec_search; }
 FLAC__bool FLAC__stream_encoder_get_do_escape_coding(const FLAC__StreamEncoder*) { return 0; }
-FLAC__bool FLAC__stream_encoder_get_do_exhaustive_model_search(const FLAC__StreamEncoder*) { return 0; }
-uint32_t FLAC__stream_encoder_get_min_residual_partition_order(const FLAC__StreamEncoder*) { return 0; }
-uint32_t FLAC__stream_encoder_get_max_residual_partition_order(const FLAC__StreamEncoder* e) { return kLv[I(e)->level].po; }
-uint32_t FLAC__stream_encoder_get_rice_parameter_search_dist(const FLAC__StreamEncoder*) { return 0; }
+FLAC__bool FLAC__stream_encoder_get_do_exhaustive_model_search(const FLAC__StreamEncoder* e) { return I(e)->exhaustive; }
+uint32_t FLAC__stream_encoder_get_min_residual_partition_order(const FLAC__StreamEncoder* e) { return I(e)->min_po; }
+uint32_t FLAC__stream_encoder_get_max_residual_partition_order(const FLAC__StreamEncoder* e) { return I(e)->max_po; }
+uint32_t FLAC__stream_encoder_get_rice_parameter_search_dist(const FLAC__StreamEncoder* e) { return I(e)->rice_dist; }
 FLAC__uint64 FLAC__stream_encoder_get_total_samples_estimate(const FLAC__StreamEncoder* e) { return I(e)->total_samples_estimate; }
 FLAC__bool FLAC__stream_encoder_get_limit_min_bitrate(const FLAC__StreamEncoder* e) { return I(e)->limit_min_bitrate; }
 

@@ -56,7 +56,7 @@ def _proto(L):
 
 
 def encode_session(L, pcm, sample_rate, bps, level=5, blocksize=0, chunks=None, seekable=True, metadata=True,
-                   verify=False, streamable_subset=True, init_only=False, no_tell=False, limit_min_bitrate=False):
+                   verify=False, streamable_subset=True, init_only=False, no_tell=False, limit_min_bitrate=False, setters=()):
     """Run one StreamEncoder session; returns dict(init_status, log=[(event, ...)], file=bytes image, ok=bool).
     log events: ('write', bytes, samples, frame) | ('seek', off) | ('tell', off) | ('meta', dict)."""
     _proto(L)
@@ -101,6 +101,11 @@ def encode_session(L, pcm, sample_rate, bps, level=5, blocksize=0, chunks=None, 
     L.FLAC__stream_encoder_set_blocksize(e, blocksize)
     L.FLAC__stream_encoder_set_streamable_subset(e, int(streamable_subset))
     L.FLAC__stream_encoder_set_limit_min_bitrate(e, int(limit_min_bitrate))
+    for name, v in setters:                                     # fine-grained settings, applied after the compression level like a libFLAC client
+        f = getattr(L, "FLAC__stream_encoder_set_" + name)
+        f.argtypes = [C.c_void_p, C.c_char_p if name == "apodization" else C.c_uint32]
+        f.restype = C.c_int
+        f(e, v.encode() if name == "apodization" else v)
     null = lambda T: C.cast(None, T)  # noqa: E731
     st = L.FLAC__stream_encoder_init_stream(e, wcb, scb if seekable else null(SEEK_CB),
                                             null(TELL_CB) if (not seekable or no_tell) else tcb,

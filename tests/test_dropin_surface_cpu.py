@@ -86,6 +86,45 @@ def test_encoder_setters_round_trip_like_libflac(libs):
         assert a == b
 
 
+def test_fine_grained_setters_round_trip_like_libflac(libs):
+    """builder/encoder.py:274-284: the setters pyFLAC declares but never calls store what they are given (validation happens at init)
+    and a later set_compression_level writes the level's presets over them"""
+    script = [("do_mid_side_stereo", 0), ("loose_mid_side_stereo", 1), ("max_lpc_order", 3), ("max_lpc_order", 40), ("qlp_coeff_precision", 9),
+              ("qlp_coeff_precision", 2), ("do_qlp_coeff_prec_search", 1), ("do_exhaustive_model_search", 1), ("min_residual_partition_order", 2),
+              ("max_residual_partition_order", 4), ("max_residual_partition_order", 20), ("rice_parameter_search_dist", 3),
+              ("compression_level", 7), ("max_lpc_order", 11), ("compression_level", 2), ("do_mid_side_stereo", 1)]
+    snaps = []
+    for L in libs:
+        e = L.FLAC__stream_encoder_new()
+        s = []
+        for name, v in script:
+            s.append((name, v, _set(L, e, name, v), _enc_snapshot(L, e)))
+        L.FLAC__stream_encoder_delete(e)
+        snaps.append(s)
+    for a, b in zip(*snaps):
+        assert a == b
+
+
+def test_fine_grained_init_validation_matches_libflac(libs):
+    """values libFLAC rejects at init are rejected with its status; values it accepts are OK -- or ENCODER_ERROR here (no device / outside
+    this build's range, which fails loudly instead of encoding something else)"""
+    import numpy as np
+    import _flacapi as fa
+    ours, ref = libs
+    x = np.zeros((4, 2), np.int16)
+    cases = [[("max_lpc_order", 33)], [("max_lpc_order", 32)], [("max_lpc_order", 13)], [("max_lpc_order", 5)], [("qlp_coeff_precision", 4)],
+             [("qlp_coeff_precision", 5)], [("qlp_coeff_precision", 16)], [("max_residual_partition_order", 9)], [("max_residual_partition_order", 16)],
+             [("max_lpc_order", 20), ("qlp_coeff_precision", 3)], [("apodization", "hann")], [("apodization", "tukey(0.25)")],
+             [("do_exhaustive_model_search", 1)], [("min_residual_partition_order", 3)]]
+    for setters in cases:
+        for subset in (True, False):
+            for bs in (0, 16, 4096):
+                kw = dict(sample_rate=48000, bps=16, level=5, blocksize=bs, streamable_subset=subset, init_only=True, setters=setters)
+                a = fa.encode_session(ours, x, **kw)["init_status"]
+                b = fa.encode_session(ref, x, **kw)["init_status"]
+                assert (a == b) if b != 0 else (a in (0, 1)), (setters, subset, bs, a, b)
+
+
 def test_uninitialised_calls_behave_like_libflac(libs):
     """process / finish on a handle that was never initialised, and the decoder's defaults"""
     res = []

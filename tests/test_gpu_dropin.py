@@ -274,3 +274,32 @@ def test_decoder_md5_checking_matches_libflac(ours, ref, checkers):
             assert a["events"] == b["events"], i
     assert scripted_decode_session(ours, bad, [('end',)], md5_checking=True)["finish"] is False
     assert scripted_decode_session(ours, flac, [('end',)], md5_checking=True)["finish"] is True
+
+
+TUNINGS = [
+    [("max_lpc_order", 4)], [("max_lpc_order", 11)], [("max_lpc_order", 1)], [("max_lpc_order", 0)],
+    [("max_residual_partition_order", 2)], [("max_residual_partition_order", 0)], [("max_residual_partition_order", 6)],
+    [("qlp_coeff_precision", 8)], [("qlp_coeff_precision", 15)], [("qlp_coeff_precision", 5)],
+    [("do_mid_side_stereo", 0)], [("do_mid_side_stereo", 1), ("loose_mid_side_stereo", 1)],
+    [("apodization", "tukey(0.25)")], [("apodization", "tukey(1)")], [("apodization", "tukey(0)")], [("apodization", "subdivide_tukey(2)")],
+    [("apodization", "subdivide_tukey(3/0.3)")], [("apodization", "tukey(7)")], [("rice_parameter_search_dist", 4)],
+    [("max_lpc_order", 6), ("qlp_coeff_precision", 10), ("max_residual_partition_order", 3), ("apodization", "subdivide_tukey(2/0.8)"), ("do_mid_side_stereo", 0)],
+    [("do_exhaustive_model_search", 0), ("do_qlp_coeff_prec_search", 0), ("min_residual_partition_order", 0)],
+]
+
+
+@pytest.mark.parametrize("bps,ch,level", [(16, 2, 5), (24, 1, 3), (16, 2, 1), (8, 2, 8)])
+def test_fine_grained_settings_match_libflac(ours, ref, bps, ch, level):
+    """builder/encoder.py:274-284 (set_do_mid_side_stereo ... set_apodization): applied after the compression level, the stream is
+    libFLAC's byte for byte -- on the TMA path (16-bit stereo) and the generic one; settings outside this build's range fail at init"""
+    from _flacapi import encode_session
+    x = music_like(4096 * 3 + 517, ch, 48000, bps, seed=bps + level)
+    for setters in TUNINGS:
+        a = encode_session(ours, x, 48000, bps, level, 0, setters=setters)
+        b = encode_session(ref, x, 48000, bps, level, 0, setters=setters)
+        assert a["init_status"] == b["init_status"] == 0, setters
+        assert a["file"] == b["file"], setters
+    for setters in ([("max_lpc_order", 16)], [("do_exhaustive_model_search", 1)], [("apodization", "hann")], [("apodization", "tukey(0.5);hann")],
+                    [("max_residual_partition_order", 7)], [("min_residual_partition_order", 2)], [("apodization", "subdivide_tukey(4)")]):
+        a = encode_session(ours, x, 48000, bps, level, 0, setters=setters, streamable_subset=False)
+        assert a["init_status"] == 1 and a["file"] == b"", setters          # FLAC__STREAM_ENCODER_INIT_STATUS_ENCODER_ERROR, nothing written
