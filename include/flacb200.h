@@ -238,6 +238,7 @@ int  flacb200_host_path_info(flacb200_ctx *ctx, double *v, int n);
  *   FLACB200_CHUNKS       pieces the PCM of flacb200_encode_batch_host is cut into for the H2D / kernel / D2H pipeline (default 12)
  *   FLACB200_MD5_THREADS  host threads hashing the caller's PCM meanwhile (default: calibrated so they finish with the H2D copy,
  *                         at most this rank's share of the host: affinity mask / FLACB200_LOCAL_RANKS or LOCAL_WORLD_SIZE)
+ *   FLACB200_MD5_WARPS    chain warps per md5_kernel CTA, 1..4 (default 4: one per SM sub-partition, the fewest SMs shared with the encode kernels)
  *   FLACB200_MD5_GPU_CHUNKS  leading chunks whose streams md5_kernel hashes instead of the host (default: balanced automatically)
  *   FLACB200_DEC_CHUNKS   groups of streams flacb200_decode_batch_host pipelines (default: one per 200 MB of FLAC, at most 12) */
 /* Drop-in layer (flacb200_flac_api.h): concurrent FLAC__stream_encoder_process_interleaved() calls of different handles are

@@ -8,6 +8,8 @@
 // CRC-16 is computed over 256 parallel chunks and combined in GF(2)[x]/(x^16+x^15+x^2+1).
 // up: stream_encoder_framing.c FLAC__frame_add_header / FLAC__subframe_add_* ,
 //     bitwriter.c FLAC__bitwriter_write_rice_signed_block (ref: format.h:209-475).
+#include <stdlib.h>
+#include <algorithm>
 #include "fb_common.cuh"
 #include "fb_math.cuh"
 #include "enc_dev.cuh"
@@ -495,7 +497,7 @@ constexpr int kMd5Piece = 256, kMd5Row = kMd5Piece + 16, kMd5Ring = 4;
 // cs[c] .. cs[c+1]-1) is in HBM.  The warp waits for the chunk of its last stream (chunks land in order), so every chain starts
 // the moment its bytes are there and all chains of a batch run side by side in ONE launch.
 __device__ __noinline__ void md5_wait_for_chunk(const Md5Gate& gate, int n_streams) {
-    const int last = min((int)blockIdx.x * 32 + 31, n_streams - 1);
+    const int last = min(((int)blockIdx.x * (int)(blockDim.x >> 5) + (int)(threadIdx.x >> 5)) * 32 + 31, n_streams - 1);
     int c = 0;
     while (c + 1 < gate.nchunks && last >= gate.cs[c + 1]) c++;
     // every lane polls (one broadcast load per try): a single polling lane left the warp split behind the wait -- lane 0 and
@@ -512,16 +514,21 @@ __device__ __noinline__ void md5_wait_for_chunk(const Md5Gate& gate, int n_strea
     __threadfence();
 }
 template <typename PcmT, bool K24>
-__global__ void __launch_bounds__(32) md5_kernel(const PcmT* __restrict__ pcm, const uint64_t* __restrict__ stream_pcm_off,
+__global__ void __launch_bounds__(128) md5_kernel(const PcmT* __restrict__ pcm, const uint64_t* __restrict__ stream_pcm_off,
                            const uint64_t* __restrict__ stream_samples, int n_streams, uint32_t channels, uint32_t bps,
                            uint8_t* __restrict__ digest_out, Md5Gate gate) {
-    __shared__ __align__(16) uint8_t ring[kMd5Ring][32][kMd5Row];
-    const int lane = threadIdx.x, s = blockIdx.x * 32 + lane;
+    // one warp = 32 chains; the warps of a CTA never meet (no CTA barrier): a CTA of four warps puts one chain warp on each SM
+    // sub-partition, so a batch of 256 streams occupies 2 SMs instead of 8 (see launch_md5_gated)
+    extern __shared__ __align__(16) uint8_t md5_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w0 = (blockIdx.x * (blockDim.x >> 5) + wib) * 32, s = w0 + lane;
+    if (w0 >= n_streams) return;                                           // whole warp past the end
+    uint8_t (*ring)[32][kMd5Row] = reinterpret_cast<uint8_t (*)[32][kMd5Row]>(md5_smem + (size_t)wib * (kMd5Ring * 32 * kMd5Row));
     const bool live = s < n_streams;
     if (gate.flags) md5_wait_for_chunk(gate, n_streams);               // host -> host path: launched ahead of its input
     const uint32_t bytes_per = (bps + 7) / 8;
     // lanes past the last stream mirror the warp's first stream for the copies (valid addresses, nothing hashed)
-    const PcmT* p = pcm + stream_pcm_off[live ? s : blockIdx.x * 32];
+    const PcmT* p = pcm + stream_pcm_off[live ? s : w0];
     const uint64_t nvals = live ? stream_samples[s] * channels : 0ull;
     Md5Feeder f; f.init();
     const bool fast = live && bytes_per == (K24 ? 3u : (uint32_t)sizeof(PcmT)) && (((uintptr_t)p) & 15u) == 0;
@@ -598,11 +605,28 @@ __global__ void __launch_bounds__(32) md5_kernel(const PcmT* __restrict__ pcm, c
 
 void launch_md5_gated(const void* pcm, uint32_t container_bytes, const uint64_t* stream_pcm_off, const uint64_t* stream_samples,
                       int n_streams, uint32_t channels, uint32_t bps, uint8_t* digest_out, const Md5Gate& gate, cudaStream_t stream) {
-    // one warp per CTA: the chains are latency-bound, spreading them over SMs costs nothing
-    const int threads = 32, blocks = (n_streams + threads - 1) / threads;
-    if (container_bytes == 2) md5_kernel<int16_t, false><<<blocks, threads, 0, stream>>>((const int16_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out, gate);
-    else if ((bps + 7) / 8 == 3) md5_kernel<int32_t, true><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out, gate);
-    else md5_kernel<int32_t, false><<<blocks, threads, 0, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out, gate);
+    // Chains are latency bound: one warp (32 streams) per SM sub-partition is as fast as it gets (two warps on one sub-partition share
+    // its ALU pipe: 8 of every 12 cycles each).  Four warps per CTA = one per sub-partition.  An MD5 CTA sits on its SM for 13-16 ms,
+    // the lifetime of hundreds of encode CTAs, next to which it costs the encode kernels far more than its issue slots (measured:
+    // 24 one-warp CTAs in flight on 24 SMs slowed the encode step by 0.7 ms); packed four to a CTA the chains of a 256-stream batch
+    // touch 2 SMs.  The SM cannot change its L1 / shared-memory split while a CTA is resident, hence the largest carve-out.
+    const int wpc = getenv("FLACB200_MD5_WARPS") ? std::max(1, std::min(4, atoi(getenv("FLACB200_MD5_WARPS")))) : 4;
+    const int threads = 32 * wpc, nwarps = (n_streams + 31) / 32, blocks = (nwarps + wpc - 1) / wpc;
+    const size_t smem = (size_t)wpc * kMd5Ring * 32 * kMd5Row;            // (a larger request that keeps encode CTAs off these SMs altogether gained nothing)
+    static bool attr_set = false;
+    if (!attr_set) {
+        attr_set = true;
+        const int mx = 4 * kMd5Ring * 32 * kMd5Row;
+        cudaFuncSetAttribute(md5_kernel<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(md5_kernel<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(md5_kernel<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(md5_kernel<int16_t, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(md5_kernel<int32_t, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(md5_kernel<int32_t, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    if (container_bytes == 2) md5_kernel<int16_t, false><<<blocks, threads, smem, stream>>>((const int16_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out, gate);
+    else if ((bps + 7) / 8 == 3) md5_kernel<int32_t, true><<<blocks, threads, smem, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out, gate);
+    else md5_kernel<int32_t, false><<<blocks, threads, smem, stream>>>((const int32_t*)pcm, stream_pcm_off, stream_samples, n_streams, channels, bps, digest_out, gate);
 }
 void launch_md5(const void* pcm, uint32_t container_bytes, const uint64_t* stream_pcm_off, const uint64_t* stream_samples,
                 int n_streams, uint32_t channels, uint32_t bps, uint8_t* digest_out, cudaStream_t stream) {
