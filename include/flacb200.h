@@ -91,14 +91,15 @@ typedef struct {
 int  flacb200_create(flacb200_ctx **out, int device);
 void flacb200_destroy(flacb200_ctx *ctx);
 const char *flacb200_last_error(const flacb200_ctx *ctx);
-/* Run all work of this ctx on an existing CUDA stream (cudaStream_t as void*, e.g. torch's current
- * stream) so callers can bracket it with their own events.  NULL = ctx-owned stream. */
+/* The caller's CUDA stream (cudaStream_t as void*, e.g. torch's current stream; NULL = a ctx-owned one).  Decode work runs on it.
+ * Encode work runs on the engine's own streams, ordered behind this stream as it stands when flacb200_encode_batch is called (so
+ * PCM produced by earlier work on it is complete) -- and behind nothing else: the MD5 chain of a batch does not queue behind the
+ * encode kernels of earlier batches. */
 int  flacb200_set_stream(flacb200_ctx *ctx, void *cuda_stream);
 int  flacb200_sync(flacb200_ctx *ctx);
-/* Batches overlap: the MD5 + STREAMINFO finalisation of a batch run on a side stream while the next batch's kernels
- * start (five rotating output sets).  flacb200_join makes the ctx stream wait for all of them, so that an event
- * recorded on it afterwards covers every batch issued so far; result/fetch/sync do this implicitly.  The PCM of a
- * batch must stay unchanged until then. */
+/* Batches overlap: encode kernels on the engine's encode stream, the MD5 + STREAMINFO patch of each batch on a side stream (five
+ * rotating output sets).  flacb200_join makes the caller's stream wait for all of it, so that an event recorded there afterwards
+ * covers every batch issued so far; result / fetch / sync wait on the host.  The PCM of a batch must stay unchanged until then. */
 int  flacb200_join(flacb200_ctx *ctx);
 
 /* libFLAC's init-time validation for these settings: returns the FLAC__StreamEncoderInitStatus

@@ -488,11 +488,15 @@ struct Md5Feeder {
 // gathered with one PRMT per hashed word).  The chain's static schedule is 12 cycles per step (LEA.HI -> LOP3 -> IADD3),
 // 768 cycles per 64-byte block -- about one DRAM round trip, and the instructions that feed it sit in the same in-order
 // issue stream, so: the bytes travel global -> shared with cp.async in 256-byte pieces per stream (half a warp copies one
-// stream's piece: whole 128-byte lines instead of 32 scattered 16-byte sectors per request), kMd5Ring pieces deep, from
+// stream's piece: whole 128-byte lines instead of 32 scattered 16-byte sectors per request), kMd5Ring pieces deep (two: the next piece lands while this one is hashed; shared memory is what a chain CTA takes from the
+// encode CTAs next to it), from
 // register-resident source addresses (three instructions per copy); each lane reads its own row back 16 bytes at a time
 // (row stride 272 bytes: the eight lanes of an LDS.128 phase fall in distinct banks).  Measured on the bench batch
-// (256 streams of 1.92 MB): 21.1 ms with per-lane loads one block ahead -> 15.6 ms.
-constexpr int kMd5Piece = 256, kMd5Row = kMd5Piece + 16, kMd5Ring = 4;
+// (256 streams of 1.92 MB): 21.1 ms with per-lane loads one block ahead -> 13.3 ms alone.
+#ifndef FB_MD5_RING
+#define FB_MD5_RING 4
+#endif
+constexpr int kMd5Piece = 256, kMd5Row = kMd5Piece + 16, kMd5Ring = FB_MD5_RING;
 // Host -> host path: the kernel is launched before the PCM has arrived; the copy stream sets flag c when chunk c (streams
 // cs[c] .. cs[c+1]-1) is in HBM.  The warp waits for the chunk of its last stream (chunks land in order), so every chain starts
 // the moment its bytes are there and all chains of a batch run side by side in ONE launch.
@@ -566,7 +570,8 @@ __global__ void __launch_bounds__(128) md5_kernel(const PcmT* __restrict__ pcm, 
         for (int q = 0; q < kMd5Ring - 1; q++) request((uint64_t)q);
         for (uint64_t q = 0; q < np_max; q++) {
             asm volatile("cp.async.wait_group %0;" :: "n"(kMd5Ring - 2) : "memory");
-            __syncwarp();
+            __syncwarp();                                                  // piece q is there for every lane, and every lane is done with piece q-1
+            request(q + kMd5Ring - 1);                                     // into the slot of piece q-1: a whole piece (3000 cycles of hashing) ahead even with two slots
             const uint4* row = reinterpret_cast<const uint4*>(&ring[q % kMd5Ring][lane][0]);
             if (q < np_own) {                                              // uniform while q < np_all
                 if (K24) {
@@ -592,8 +597,6 @@ __global__ void __launch_bounds__(128) md5_kernel(const PcmT* __restrict__ pcm, 
                     }
                 }
             }
-            __syncwarp();                                                  // every lane is done with the slot the next request refills
-            request(q + kMd5Ring - 1);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
@@ -612,11 +615,17 @@ void launch_md5_gated(const void* pcm, uint32_t container_bytes, const uint64_t*
     // touch 2 SMs.  The SM cannot change its L1 / shared-memory split while a CTA is resident, hence the largest carve-out.
     const int wpc = getenv("FLACB200_MD5_WARPS") ? std::max(1, std::min(4, atoi(getenv("FLACB200_MD5_WARPS")))) : 4;
     const int threads = 32 * wpc, nwarps = (n_streams + 31) / 32, blocks = (nwarps + wpc - 1) / wpc;
-    const size_t smem = (size_t)wpc * kMd5Ring * 32 * kMd5Row;            // (a larger request that keeps encode CTAs off these SMs altogether gained nothing)
+    // ... and it asks for (nearly) the whole shared memory of its SM, although the rings take 139 KB: encode CTAs that squeeze in next to
+    // a chain CTA run at a fraction of their speed and hold up the end of every encode kernel (measured, 20 steps of the bench batch:
+    // 5.62 ms per step with 70 KB chain CTAs, 5.13 with 139 KB, 4.88 with 190-226 KB; 4.64 without MD5).  Only while the chain CTAs are
+    // few: a 4096-stream batch would take 32 SMs out of the encode kernels' hands.
+    size_t smem = (size_t)wpc * kMd5Ring * 32 * kMd5Row;
+    if (wpc == 4 && blocks <= 16) smem = std::max<size_t>(smem, (size_t)200 * 1024);
+    if (const char* ev = getenv("FLACB200_MD5_SMEM_KB")) smem = std::max<size_t>((size_t)wpc * kMd5Ring * 32 * kMd5Row, (size_t)atoi(ev) * 1024);
     static bool attr_set = false;
     if (!attr_set) {
         attr_set = true;
-        const int mx = 4 * kMd5Ring * 32 * kMd5Row;
+        const int mx = 227 * 1024;
         cudaFuncSetAttribute(md5_kernel<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(md5_kernel<int32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(md5_kernel<int32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);

@@ -110,8 +110,13 @@ static unsigned host_thread_budget() {
 
 struct flacb200_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, own_stream = nullptr, md5_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // stream = the caller's stream (flacb200_set_stream; default: own_stream): the engine only records / waits on it.  All encode
+    // work runs on enc_stream, which waits for the caller's stream as it was at the call (whatever produced the PCM), and the MD5
+    // chain of a batch waits for exactly that too -- NOT for the encode kernels of earlier batches, which on one shared stream
+    // stood between the call and its chain and left every run with an MD5 tail behind its last batch.  flacb200_join / result / fetch
+    // make the caller's stream (or the host) wait for the engine.
+    cudaStream_t stream = nullptr, own_stream = nullptr, md5_stream = nullptr, enc_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_user = nullptr;
     bool profiling = false;
     cudaEvent_t ev_k[10] = {nullptr};      // analysis start, analysis end, pack end, layout end, compact end, finalize end, md5 start, md5 end, OR/AND end, autocorrelation end
     std::string err;
@@ -157,7 +162,7 @@ struct flacb200_ctx {
     double guard_rel = 1e-12; uint32_t guard_flip = 0;
     std::vector<LogGuardOverride> h_ovr; DevBuf d_guard_ovr;
     uint64_t guard_info[4] = {0, 0, 0, 0};    // last batch: decisions inside the band, confirmed by the host, overridden, not checked (log full)
-    const void* last_d_pcm = nullptr; bool in_rerun = false;
+    const void* last_d_pcm = nullptr; bool last_pcm_staged = false; bool in_rerun = false;
     uint64_t batch_seq = 0, settled_seq = 0;   // the guard of a batch is settled once, however often its result is asked for
     struct HostJob;                       // one in-flight flacb200_encode_host_submit (defined below)
     static constexpr int kJobs = 3;
@@ -309,6 +314,8 @@ extern "C" int flacb200_create(flacb200_ctx** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return FLACB200_ERR_NO_DEVICE; }
     cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->md5_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->enc_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_user, cudaEventDisableTiming);
     for (auto& S : ctx->sets) {
         cudaStreamCreateWithFlags(&S.side, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&S.ev_main, cudaEventDisableTiming);
@@ -336,6 +343,7 @@ extern "C" int flacb200_create(flacb200_ctx** out, int device) {
 extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->enc_stream);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_guard_ovr, &ctx->d_flags, &ctx->d_pcm, &ctx->d_frames, &ctx->d_windows, &ctx->d_plans, &ctx->d_ca, &ctx->d_scratch, &ctx->d_work, &ctx->d_sfirst, &ctx->d_snframes,
                       &ctx->d_soff, &ctx->d_ssamples, &ctx->d_debug};
@@ -348,7 +356,8 @@ extern "C" void flacb200_destroy(flacb200_ctx* ctx) {
         if (S.ev_free) cudaEventDestroy(S.ev_free);
         if (S.side) cudaStreamDestroy(S.side);
     }
-    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_user);
+    cudaStreamSynchronize(ctx->enc_stream); cudaStreamDestroy(ctx->enc_stream);
     for (auto& e : ctx->ev_k) cudaEventDestroy(e);
     for (auto& e : ctx->ev_h2d) cudaEventDestroy(e);
     for (auto& e : ctx->ev_done) cudaEventDestroy(e);
@@ -370,6 +379,7 @@ extern "C" int flacb200_set_stream(flacb200_ctx* ctx, void* s) { if (!ctx) retur
 extern "C" int flacb200_sync(flacb200_ctx* ctx) {
     if (!ctx) return FLACB200_ERR_ARG;
     cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->enc_stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto& S : ctx->sets) if (S.busy) CK(cudaStreamSynchronize(S.side));
     return 0;
@@ -383,7 +393,13 @@ void fb_ctx_add_launches(flacb200_ctx* c, uint64_t n) { c->launches += n; }
 
 // Make the ctx stream wait for every side stream (MD5 + finalize of in-flight batches): after this, an event recorded
 // on the ctx stream covers all work issued so far.
-extern "C" int flacb200_join(flacb200_ctx* ctx) { if (!ctx) return FLACB200_ERR_ARG; cudaSetDevice(ctx->device); return wait_all_sets(ctx, ctx->stream); }
+extern "C" int flacb200_join(flacb200_ctx* ctx) {
+    if (!ctx) return FLACB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaEventRecord(ctx->ev_join, ctx->enc_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    return wait_all_sets(ctx, ctx->stream);
+}
 
 extern "C" int flacb200_host_path_times(flacb200_ctx* ctx, double* ms) { if (!ctx || !ms) return FLACB200_ERR_ARG; for (int i = 0; i < 6; i++) ms[i] = ctx->e2e_ms[i]; return 0; }
 extern "C" int flacb200_host_path_info(flacb200_ctx* ctx, double* v, int n) { if (!ctx || !v || n < 0) return FLACB200_ERR_ARG; for (int i = 0; i < n && i < 10; i++) v[i] = ctx->e2e_ms[i]; return 0; }
@@ -394,7 +410,7 @@ extern "C" int flacb200_set_profiling(flacb200_ctx* ctx, int on) { if (!ctx) ret
 extern "C" int flacb200_kernel_times(flacb200_ctx* ctx, float* ms) {
     if (!ctx || !ms || !ctx->profiling || !ctx->have_batch) return FLACB200_ERR_ARG;
     cudaSetDevice(ctx->device);
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->enc_stream));
     for (auto& S : ctx->sets) CK(cudaStreamSynchronize(S.side));
     for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&ms[i], ctx->ev_k[i], ctx->ev_k[i + 1]));
     ms[5] = 0.0f;
@@ -474,7 +490,7 @@ static int plan_batch(flacb200_ctx* ctx, const flacb200_enc_config& cfg, uint32_
         return fail(ctx, FLACB200_ERR_UNSUPPORTED, "blocksize x channels exceeds the shared-memory frame tile of this build");
 
     const int nf = ctx->n_frames;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->enc_stream;
     CK(ctx->d_frames.reserve(sizeof(FrameDesc) * (size_t)(nf ? nf : 1)));
     CK(ctx->d_plans.reserve(sizeof(SubframePlan) * (size_t)(nf ? nf : 1) * P.n_signals));
     CK(ctx->d_work.reserve(analyze_work_stride(P) * (size_t)(nf ? nf : 1)));
@@ -563,10 +579,12 @@ static int guard_settle(flacb200_ctx* ctx, flacb200_ctx::OutSet& S, uint64_t see
     return 0;
 }
 
-static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
-    ctx->last_d_pcm = d_pcm; ctx->batch_seq++;
+// pcm_staged: the PCM was copied into ctx->d_pcm on the encode stream (host input): the MD5 chain waits for that copy; otherwise it
+// waits for the caller's stream as it was at the call (ev_user) and for nothing else
+static int run_batch(flacb200_ctx* ctx, const void* d_pcm, bool pcm_staged) {
+    ctx->last_d_pcm = d_pcm; ctx->last_pcm_staged = pcm_staged; ctx->batch_seq++;
     const int nf = ctx->n_frames, ns = ctx->n_streams;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->enc_stream;
     ctx->cur = (ctx->cur + 1) % flacb200_ctx::kSets;
     flacb200_ctx::OutSet& S = ctx->set();
     const EncParams P = params_for_set(ctx, S);
@@ -577,8 +595,8 @@ static int run_batch(flacb200_ctx* ctx, const void* d_pcm) {
     const bool md5 = ctx->cfg.do_md5 != 0;
     const bool prof = ctx->profiling;
     if (md5) {
-        CK(cudaEventRecord(ctx->ev_fork, st));
-        CK(cudaStreamWaitEvent(S.side, ctx->ev_fork, 0));
+        if (pcm_staged) { CK(cudaEventRecord(ctx->ev_fork, st)); CK(cudaStreamWaitEvent(S.side, ctx->ev_fork, 0)); }
+        else CK(cudaStreamWaitEvent(S.side, ctx->ev_user, 0));
         if (prof) CK(cudaEventRecord(ctx->ev_k[6], S.side));
         launch_md5(d_pcm, P.container_bytes, (const uint64_t*)ctx->d_soff.p, (const uint64_t*)ctx->d_ssamples.p, ns, P.channels, P.bps,
                    (uint8_t*)S.md5.p, S.side);
@@ -640,21 +658,26 @@ extern "C" int flacb200_encode_batch(flacb200_ctx* ctx, const flacb200_enc_confi
         if (stream_off[s] + stream_samples[s] * cfg->channels > pcm_elems) return fail(ctx, FLACB200_ERR_ARG, "stream exceeds pcm buffer");
     if (ctx->prev_ca_pending || !same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, first_frame_number)) {
         ctx->have_batch = false;
+        CK(cudaStreamSynchronize(ctx->enc_stream));
         for (auto& S : ctx->sets) if (S.busy) { CK(cudaStreamSynchronize(S.side)); S.busy = false; }
         int rc = plan_batch(ctx, *cfg, n_streams, stream_off, stream_samples, first_frame_number);
         if (rc) return rc;
     }
+    // the encode stream picks up behind whatever the caller's stream holds right now (the producer of the PCM)
+    CK(cudaEventRecord(ctx->ev_user, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->enc_stream, ctx->ev_user, 0));
     const void* d_pcm = pcm;
     if (!pcm_is_device) {
         const size_t bytes = (size_t)pcm_elems * cfg->container_bytes;
         // the MD5 of an earlier host-PCM batch may still be reading the staging buffer on its side stream
-        { int wrc = wait_all_sets(ctx, ctx->stream); if (wrc) return wrc; }
+        { int wrc = wait_all_sets(ctx, ctx->enc_stream); if (wrc) return wrc; }
         if (bytes + 64 > ctx->d_pcm.cap) for (auto& S : ctx->sets) if (S.busy) { CK(cudaStreamSynchronize(S.side)); S.busy = false; }   // about to free it
+        if (bytes + 64 > ctx->d_pcm.cap) CK(cudaStreamSynchronize(ctx->enc_stream));
         CK(ctx->d_pcm.reserve(bytes + 64));
-        CK(cudaMemcpyAsync(ctx->d_pcm.p, pcm, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_pcm.p, pcm, bytes, cudaMemcpyHostToDevice, ctx->enc_stream));
         d_pcm = ctx->d_pcm.p;
     }
-    return run_batch(ctx, d_pcm);
+    return run_batch(ctx, d_pcm, !pcm_is_device);
 }
 
 extern "C" int flacb200_encode_set_prev_assignment(flacb200_ctx* ctx, const uint8_t* prev, uint32_t n_streams) {
@@ -671,8 +694,8 @@ extern "C" int flacb200_encode_fetch_assignments(flacb200_ctx* ctx, uint8_t* fra
     if (cap < (size_t)ctx->n_frames) return fail(ctx, FLACB200_ERR_ARG, "assignment buffer too small");
     cudaSetDevice(ctx->device);
     if (ctx->n_frames) {
-        CK(cudaMemcpyAsync(frame_ca, ctx->d_ca.p, (size_t)ctx->n_frames, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpyAsync(frame_ca, ctx->d_ca.p, (size_t)ctx->n_frames, cudaMemcpyDeviceToHost, ctx->enc_stream));
+        CK(cudaStreamSynchronize(ctx->enc_stream));
     }
     return 0;
 }
@@ -710,9 +733,9 @@ static int encode_result_impl(flacb200_ctx* ctx, flacb200_enc_result* res, bool 
     if (!ctx->have_batch) return fail(ctx, FLACB200_ERR_ARG, "no batch");
     cudaSetDevice(ctx->device);
     uint64_t total = 0; EncStats stt{};
-    CK(cudaMemcpyAsync(&total, ctx->set().total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(&stt, ctx->set().stats.p, sizeof stt, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(&total, ctx->set().total.p, 8, cudaMemcpyDeviceToHost, ctx->enc_stream));
+    CK(cudaMemcpyAsync(&stt, ctx->set().stats.p, sizeof stt, cudaMemcpyDeviceToHost, ctx->enc_stream));
+    CK(cudaStreamSynchronize(ctx->enc_stream));
     if (ctx->n_frames && !ctx->in_rerun && ctx->settled_seq != ctx->batch_seq) {
         ctx->settled_seq = ctx->batch_seq;
         // decisions inside the libm-log guard band: the host repeats them; if it decides otherwise the batch is encoded once more
@@ -722,7 +745,7 @@ static int encode_result_impl(flacb200_ctx* ctx, flacb200_enc_result* res, bool 
         if (grc) return grc;
         if (n_new) {
             ctx->in_rerun = true;
-            int rrc = run_batch(ctx, ctx->last_d_pcm);
+            int rrc = run_batch(ctx, ctx->last_d_pcm, ctx->last_pcm_staged);
             if (!rrc) rrc = encode_result_impl(ctx, res, wait_md5);
             ctx->in_rerun = false; ctx->h_ovr.clear(); ctx->settled_seq = ctx->batch_seq;
             if (rrc) return rrc;
@@ -742,7 +765,7 @@ extern "C" int flacb200_encode_fetch(flacb200_ctx* ctx, uint8_t* arena, size_t a
     flacb200_enc_result r;
     int rc = flacb200_encode_result(ctx, &r);
     if (rc) return rc;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->enc_stream;
     if (arena) {
         if (arena_cap < r.total_bytes) return fail(ctx, FLACB200_ERR_ARG, "arena too small");
         if (r.total_bytes) CK(cudaMemcpyAsync(arena, ctx->set().arena.p, r.total_bytes, cudaMemcpyDeviceToHost, st));
@@ -765,7 +788,7 @@ extern "C" int flacb200_encode_fetch_trace(flacb200_ctx* ctx, void* plans, size_
     cudaSetDevice(ctx->device);
     const size_t np = sizeof(SubframePlan) * (size_t)ctx->n_frames * ctx->P.n_signals;
     const size_t nd = sizeof(SignalDebug) * (size_t)ctx->n_frames * ctx->P.n_signals;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->enc_stream));
     if (plans) { if (plans_bytes < np) return fail(ctx, FLACB200_ERR_ARG, "plans buffer too small"); CK(cudaMemcpy(plans, ctx->d_plans.p, np, cudaMemcpyDeviceToHost)); }
     if (frame_ca) CK(cudaMemcpy(frame_ca, ctx->d_ca.p, (size_t)ctx->n_frames, cudaMemcpyDeviceToHost));
     if (debug) {
@@ -794,6 +817,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
         if (stream_off[s] + stream_samples[s] * cfg->channels > pcm_elems) return fail(ctx, FLACB200_ERR_ARG, "stream exceeds pcm buffer");
     if (ctx->prev_ca_pending || !same_layout(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr)) {
         ctx->have_batch = false;
+        CK(cudaStreamSynchronize(ctx->enc_stream));
         for (auto& S : ctx->sets) if (S.busy) { CK(cudaStreamSynchronize(S.side)); S.busy = false; }
         int rc = plan_batch(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr);
         if (rc) return rc;
@@ -803,7 +827,7 @@ extern "C" int flacb200_encode_batch_host(flacb200_ctx* ctx, const flacb200_enc_
     const uint32_t cont = cfg->container_bytes;
     if (total_bytes) *total_bytes = 0;
     if (nf == 0) return 0;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->enc_stream;
     CK(ctx->d_pcm.reserve((size_t)pcm_elems * cont + 64));
     CK(ctx->d_totals.reserve(sizeof(uint64_t) * flacb200_ctx::kMaxChunks));
 
@@ -1229,6 +1253,7 @@ extern "C" int flacb200_encode_host_submit(flacb200_ctx* ctx, const flacb200_enc
         // the frame table on the device is shared by the batches in flight: a new layout waits for them
         for (auto& j : ctx->jobs) if (j && j->active) return fail(ctx, FLACB200_ERR_ARG, "collect the batches in flight before submitting a different layout");
         ctx->have_batch = false;
+        CK(cudaStreamSynchronize(ctx->enc_stream));
         for (auto& S : ctx->sets) if (S.busy) { CK(cudaStreamSynchronize(S.side)); S.busy = false; }
         int rc = plan_batch(ctx, *cfg, n_streams, stream_off, stream_samples, nullptr);
         if (rc) return rc;
@@ -1236,7 +1261,7 @@ extern "C" int flacb200_encode_host_submit(flacb200_ctx* ctx, const flacb200_enc
     ctx->h_ovr.clear();
     const int nf = ctx->n_frames, ns = ctx->n_streams;
     const uint32_t cont = cfg->container_bytes;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->enc_stream;
     J->rc = 0; J->err.clear(); J->total = 0; J->pcm_elems = pcm_elems; J->h_stats->log_ambiguous = 0;
     const EncParams P = params_for_set(ctx, ctx->sets[(ctx->cur + 1) % flacb200_ctx::kSets]);
     J->nf = nf; J->ns = ns; J->arena = arena; J->arena_cap = arena_cap; J->frame_off = frame_off; J->frame_len = frame_len; J->streams = streams;
