@@ -534,7 +534,10 @@ struct AnShared {
 #define FB_AN_MIN_CTAS 8
 #endif
 template <typename PcmT, bool PACKED>
-__global__ void __launch_bounds__(kAnThreads, PACKED ? FB_AN_MIN_CTAS : 3)
+#ifndef FB_AN_MIN_CTAS_WIDE
+#define FB_AN_MIN_CTAS_WIDE 4      // measured on the 24-bit mono level-8 shape (configs[2]): 150 registers at 3 CTAs/SM 4.74 ms, 114 at 4: 4.33, 96 (spills) at 5: 4.28
+#endif
+__global__ void __launch_bounds__(kAnThreads, PACKED ? FB_AN_MIN_CTAS : FB_AN_MIN_CTAS_WIDE)
 analyze_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames, const float* __restrict__ windows,
                EncParams P, SubframePlan* __restrict__ plans, uint8_t* __restrict__ frame_ca,
                SignalDebug* __restrict__ dbg, EncStats* __restrict__ stats, int pass,
