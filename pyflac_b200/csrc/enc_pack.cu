@@ -613,6 +613,7 @@ void launch_md5_gated(const void* pcm, uint32_t container_bytes, const uint64_t*
     // the lifetime of hundreds of encode CTAs, next to which it costs the encode kernels far more than its issue slots (measured:
     // 24 one-warp CTAs in flight on 24 SMs slowed the encode step by 0.7 ms); packed four to a CTA the chains of a 256-stream batch
     // touch 2 SMs.  The SM cannot change its L1 / shared-memory split while a CTA is resident, hence the largest carve-out.
+    // (eight warps on one SM with a two-slot ring: 4.81 instead of 4.87 ms per step, at twice the latency of a single batch's digests)
     const int wpc = getenv("FLACB200_MD5_WARPS") ? std::max(1, std::min(4, atoi(getenv("FLACB200_MD5_WARPS")))) : 4;
     const int threads = 32 * wpc, nwarps = (n_streams + 31) / 32, blocks = (nwarps + wpc - 1) / wpc;
     // ... and it asks for (nearly) the whole shared memory of its SM, although the rings take 139 KB: encode CTAs that squeeze in next to
@@ -620,7 +621,7 @@ void launch_md5_gated(const void* pcm, uint32_t container_bytes, const uint64_t*
     // 5.62 ms per step with 70 KB chain CTAs, 5.13 with 139 KB, 4.88 with 190-226 KB; 4.64 without MD5).  Only while the chain CTAs are
     // few: a 4096-stream batch would take 32 SMs out of the encode kernels' hands.
     size_t smem = (size_t)wpc * kMd5Ring * 32 * kMd5Row;
-    if (wpc == 4 && blocks <= 16) smem = std::max<size_t>(smem, (size_t)200 * 1024);
+    if (wpc >= 4 && blocks <= 16) smem = std::max<size_t>(smem, (size_t)200 * 1024);
     if (const char* ev = getenv("FLACB200_MD5_SMEM_KB")) smem = std::max<size_t>((size_t)wpc * kMd5Ring * 32 * kMd5Row, (size_t)atoi(ev) * 1024);
     static bool attr_set = false;
     if (!attr_set) {
