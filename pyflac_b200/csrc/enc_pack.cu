@@ -511,9 +511,9 @@ __device__ __noinline__ void md5_wait_for_chunk(const Md5Gate& gate, int n_strea
     while (__any_sync(0xffffffffu, *f == 0u)) {
         __nanosleep(500);
         // the flag is set by the copy stream; if that stream cannot make progress while this kernel runs (a profiler that
-        // serialises all work) give up loudly after 4 s instead of hanging the GPU
+        // serialises all work) give up loudly after 30 s instead of hanging the GPU
         unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 4000000000ull) __trap();
+        if (t1 - t0 > 30000000000ull) __trap();
     }
     __threadfence();
 }
