@@ -38,9 +38,15 @@ def launches(path):
         if len(r) <= vi:
             continue
         name = r[ni].split("(")[0].replace("void fb::", "").replace("void ", "")
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        if v != v:                              # "nan": the launch the capture was cut at
+            continue
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
-        a[1] += float(r[vi].replace(",", ""))
+        a[1] += v
     tot = sum(a[1] for a in agg.values())
     print(f"# {path}: ncu --metrics gpu__time_duration.sum --clock-control none (per-launch, cold-cache, serialised): compare SHARES, not absolutes")
     print(f"{'kernel':60s} {'launches':>8s} {'total ms':>10s} {'share':>7s}")
