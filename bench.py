@@ -659,7 +659,9 @@ def main():
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                         "kernel_ms": kt_acc},
+                         "kernel_ms": kt_acc,
+                         "kernel_ms_note": "CUDA events on the launching streams around each kernel of the LAST timed step (steady state; the step "
+                                           "time above is the average over all timed steps)"},
             "roofline_md5": {"bound": "hbm", "kernel": "md5_kernel (side stream, overlapped with the next batches)",
                              "achieved": pcm_bytes / (max(kt_acc.get("md5", 0.0), 1e-6) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": pcm_bytes / (max(kt_acc.get("md5", 0.0), 1e-6) * 1e-3) / 1e9 / peak,
