@@ -215,7 +215,7 @@ int  flacb200_decode_batch_host(flacb200_ctx *ctx, const uint8_t *blob, uint64_t
                                 const uint64_t *stream_off, const uint64_t *stream_len, uint32_t out_container_bytes,
                                 const flacb200_dec_raw_params *raw, void *pcm, size_t pcm_cap, uint64_t *total_elems,
                                 flacb200_dec_stream_info *streams);
-/* ms[0..5] = metadata+sync scan, candidate decode, chain+layout, post (CRC/interleave), 0, 0 */
+/* ms[0..5] = metadata+sync scan, candidate decode + CRC-16, chain+layout, post (undo stereo / interleave), the CRC-16 kernel's share of ms[1], 0 */
 int  flacb200_decode_kernel_times(flacb200_ctx *ctx, float *ms);
 
 /* Per-kernel device times of the last batch, measured with CUDA events on the launching streams:

@@ -447,7 +447,7 @@ def _engine_decode_kernel_times(self):
     _dec_proto(self._L)
     ms = np.zeros(6, np.float32)
     self._check(self._L.flacb200_decode_kernel_times(self._h, ms.ctypes.data))
-    return dict(zip(["sync_scan", "frame_decode", "chain_layout", "post"], [float(v) for v in ms[:4]]))
+    return dict(zip(["sync_scan", "frame_decode", "chain_layout", "post", "crc16"], [float(v) for v in ms[:5]]))
 
 
 Engine.decode_device = _engine_decode_device

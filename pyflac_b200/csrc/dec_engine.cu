@@ -64,7 +64,7 @@ struct DecState {
     uint64_t total_elems = 0;
     uint32_t out_bytes = 0;
     bool have = false;
-    cudaEvent_t ev[5] = {nullptr};
+    cudaEvent_t ev[6] = {nullptr};      // [5]: between the frame decode and the CRC kernel
     std::vector<DecStreamResult> h_res;
     DecState* alt = nullptr;                // second state for flacb200_decode_batch_host's double buffering
     // pipelined host path
@@ -225,6 +225,7 @@ static int decode_core(flacb200_ctx* ctx, DecState* d, cudaStream_t st, const ui
         CKD(d->samples.reserve(4 * (size_t)(h_slots + 16)));
         launch_dec_frames(d_blob, (const uint64_t*)d->soff.p, (const uint64_t*)d->slen.p, (DecCand*)d->cands.p, nc, (const uint64_t*)d->slotoff.p, (int32_t*)d->samples.p, st);
     }
+    CKD(cudaEventRecord(d->ev[5], st));
     if (nc) launch_dec_crc(d_blob, (const uint64_t*)d->soff.p, (DecCand*)d->cands.p, nc, st);
     CKD(cudaEventRecord(d->ev[2], st));
     // total (8 bytes) is followed by the "some stream has silence to fill" flag
@@ -435,6 +436,7 @@ extern "C" int flacb200_decode_kernel_times(flacb200_ctx* ctx, float* ms) {
     cudaSetDevice(fb_ctx_device(ctx));
     CKD(cudaStreamSynchronize(fb_ctx_stream(ctx)));
     for (int i = 0; i < 4; i++) CKD(cudaEventElapsedTime(&ms[i], d->ev[i], d->ev[i + 1]));
-    ms[4] = ms[5] = 0.0f;
+    CKD(cudaEventElapsedTime(&ms[4], d->ev[5], d->ev[2]));       // the CRC-16 share of ms[1]
+    ms[5] = 0.0f;
     return 0;
 }

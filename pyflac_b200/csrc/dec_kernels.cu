@@ -261,80 +261,85 @@ __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, u
 }
 
 // ------------------------------------------------------------------ frame decode: one thread per candidate ----
-// MSB-first bit reader over global memory.  The window is 64 bits in two registers (ahi:alo, n valid bits from the top);
-// a refill adds one 32-bit word whenever n <= 32 and is branch-free apart from the chunk rotation, so the 32 lanes of a
-// warp -- each decoding its own frame -- stay converged: a byte-wise refill loop entered by every lane at a different
-// symbol would serialise.
+// MSB-first bit reader.  The 32 lanes of a warp each decode their own frame, so anything a lane does "now and then" is
+// done by SOME lane at practically every symbol and a branch around it buys nothing: the warp runs the body every time and
+// pays for the divergence on top (the first version branched around a 27-39 instruction refill: 85 instructions per sample).
+// The reader is therefore split by how often a step is due:
+//  * fill_fast(), once per symbol, has no branch and no bookkeeping.  The only state is the bit position: with
+//    j = word holding the next bit and r = its offset in that word, the window is  ahi = bits [pos, pos+32)  and
+//    alo = word[j+1] << r.  After any consume of up to 32 bits ahi still holds every bit of words j' and (if the position
+//    stayed in the same word) j'+1 that belong in it, so "OR in word[j'+1] >> (32 - r'), set alo = word[j'+1] << r'" is
+//    right whether or not a word boundary was crossed (OR-ing bits that are already there changes nothing):
+//    two address instructions, one shared load, a byte swap, two shifts and an OR;
+//  * top_up(), once per four symbols in the hot loop, keeps the ring ahead of the reader: every 16-byte chunk up to three
+//    past the current one is requested with cp.async (one group per chunk) and all but the newest have landed when it
+//    returns -- enough for the words four fast-path symbols (at most 32 bits each) can reach.
+// The bytes travel global -> shared with cp.async and are read back a word at a time; loads into registers would not do:
+// the lanes reach their chunk boundaries at different symbols but share one register scoreboard, so every lane's refill
+// would wait for the load another lane issued an iteration earlier (measured: 62 % of all stall samples).
 constexpr int kDecFrameThreads = 64;
-#ifndef FB_DEC_RING
-#define FB_DEC_RING 4
-#endif
-constexpr int kDecRing = FB_DEC_RING;  // 16-byte chunks per thread in the shared-memory ring (power of two); kDecRing - 2 chunks are in flight
+constexpr int kDecRing = 4;             // 16-byte chunks per thread in the shared-memory ring: 64 contiguous bytes per thread
 
 struct BitReader {
     const uint4* c16;                   // 16-byte aligned address at or below the first byte read
-    uint32_t wi;                        // next word to consume, counted from c16 (32-bit bookkeeping: no pointer compares in the loop)
-    uint32_t wend;                      // first word index past the stream (aligned up)
-    uint32_t nchunk;                    // chunks that may be loaded (those that start before the stream's end); later ones read as zero
-    int64_t  off0;                      // byte offset of c16 relative to the stream start (for bit positions)
-    uint32_t ahi, alo; int n;           // n valid bits at the top of ahi:alo, zeros below
-    uint32_t ring;                      // shared-memory address of this thread's slot 0; slot s is kDecFrameThreads * 16 * s further
-    // The bytes travel global -> shared with cp.async, two chunks (about 20 symbols) ahead of their use, and are read
-    // back one word at a time.  Loads into registers would not do: the 32 lanes of a warp reach their chunk boundaries
-    // at different symbols but share one register scoreboard, so every lane's refill would wait for the load another
-    // lane issued an iteration earlier (measured: 62 % of all stall samples).  cp.async has no destination register.
+    uint32_t bq;                        // 32 + bit offset (from c16) of the next unread bit: bq >> 5 is the word fill_fast() merges
+    uint32_t wendb;                     // byte offset of the first word past the stream (aligned up); 0 once a parse has given up
+    uint32_t req;                       // next chunk to request
+    uint32_t ahi, alo;                  // the 32 bits at the position; word[bq >> 5] << (bq & 31)
+    uint32_t ring;                      // shared-memory address of this thread's 64-byte ring (64-byte aligned)
     __device__ __forceinline__ void request(uint32_t ci) const {
-        const uint32_t dst = ring + (ci & (uint32_t)(kDecRing - 1)) * (uint32_t)(kDecFrameThreads * 16);
-        const bool in = ci < nchunk;
+        const uint32_t dst = ring | ((ci & (uint32_t)(kDecRing - 1)) << 4);
+        const bool in = (ci << 4) < wendb;                                      // chunks that start past the stream read as zero
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(c16 + (in ? ci : 0u)), "r"(in ? 16u : 0u) : "memory");   // size 0: zero fill
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    // raw word wi, then advance; at a chunk boundary ask for the chunk after next and make sure the new one has landed
-    __device__ __forceinline__ uint32_t take() {
-        uint32_t raw;
-        const uint32_t src = ring + ((wi >> 2) & (uint32_t)(kDecRing - 1)) * (uint32_t)(kDecFrameThreads * 16) + (wi & 3u) * 4u;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(src) : "memory");
-        wi++;
-        if ((wi & 3u) == 0u) {
-            request((wi >> 2) + (uint32_t)(kDecRing - 2));
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group %0;" :: "n"(kDecRing - 2) : "memory");
+    // chunks cur .. cur+2 resident and cur+3 on its way, cur = the chunk of the word the next fill merges
+    __device__ __forceinline__ void top_up() {
+        const uint32_t want = (bq >> 7) + (uint32_t)kDecRing;
+        if (req < want) {
+#pragma unroll 1
+            do { request(req); req++; } while (req < want);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
         }
-        return raw;
+    }
+    __device__ __forceinline__ uint32_t ring_word(uint32_t byte_off) const {
+        uint32_t raw;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(ring | (byte_off & (uint32_t)(kDecRing * 16 - 4))));
+        return __byte_perm(raw, 0, 0x0123);
     }
     __device__ __forceinline__ void init(const uint8_t* base, uint64_t start, uint64_t slen, uint32_t ring_addr) {
         const uint8_t* p = base + start;
         const uintptr_t a = (uintptr_t)p, a16 = a & ~(uintptr_t)15;
         c16 = reinterpret_cast<const uint4*>(a16);
-        off0 = (int64_t)a16 - (int64_t)(uintptr_t)base;
-        const uint64_t end_rel = (uint64_t)((int64_t)slen - off0);      // stream end relative to c16 (bytes)
-        wend = (uint32_t)((end_rel + 3u) >> 2);
-        nchunk = (uint32_t)((end_rel + 15u) >> 4);
-        wi = (uint32_t)((a - a16) >> 2);
-        ring = ring_addr;
+        const uint64_t end_rel = slen - start + (uint64_t)(a - a16);    // stream end relative to c16 (bytes)
+        wendb = (uint32_t)(end_rel < 0xFFFFFFE0ull ? end_rel + 3u : 0xFFFFFFE0ull) & ~3u;   // (streams are shorter than 4 GiB)
+        // (through a volatile asm: left to itself the compiler rebuilds the address from %tid at every use, five instructions per symbol)
+        asm volatile("mov.u32 %0, %1;" : "=r"(ring) : "r"(ring_addr));
 #pragma unroll
-        for (int i = 0; i < kDecRing - 1; i++) { request((uint32_t)i); asm volatile("cp.async.commit_group;" ::: "memory"); }
+        for (int i = 0; i < kDecRing; i++) request((uint32_t)i);
+        req = (uint32_t)kDecRing;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        const uint32_t skip = (uint32_t)(a & 3) * 8u;
-        ahi = __byte_perm(take(), 0, 0x0123) << skip; alo = 0u;
-        n = 32 - (int)skip;
+        const uint32_t bp = (uint32_t)(a - a16) * 8u;                   // first bit, a multiple of 8
+        bq = bp + 32u;
+        ahi = ring_word(bp >> 3) << (bp & 31u);                          // the part of the first word that belongs to the stream
+        alo = 0u;
         fill();
     }
-    // invariant after fill(): n >= 32.  Before it n <= 32 means every valid bit sits in ahi and alo is zero.
-    __device__ __forceinline__ void fill() {
-        if (n <= 32) {
-            const uint32_t w = __byte_perm(take(), 0, 0x0123);
-            ahi |= __funnelshift_rc(w, 0u, (uint32_t)n);                // w >> n, 0 when n == 32
-            alo = __funnelshift_lc(0u, w, (uint32_t)(32 - n));          // w << (32 - n), 0 when n == 0
-            n += 32;
-        }
+    // Needs word bq >> 5 resident (top_up).  See the header comment: right with and without a word boundary behind us.
+    __device__ __forceinline__ void fill_fast() {
+        const uint32_t w = ring_word(bq >> 3);
+        ahi |= __funnelshift_l(w, 0u, bq);                               // w >> (32 - r), 0 when r == 0
+        alo = __funnelshift_l(0u, w, bq);                                // w << r
     }
-    __device__ __forceinline__ void consume(uint32_t len) {             // len <= 32
+    __device__ __forceinline__ void fill() { top_up(); fill_fast(); }
+    __device__ __forceinline__ void consume(uint32_t len) {             // len <= 32, straight after a fill
         ahi = __funnelshift_lc(alo, ahi, len);
         alo = __funnelshift_lc(0u, alo, len);
-        n -= (int)len;
+        bq += len;
     }
-    // words taken beyond the end of the stream (two may sit unread in the window of a frame that ends with the stream)
-    __device__ __forceinline__ bool overrun() const { return wi > wend + 2u; }
+    // bits consumed beyond the end of the stream (aligned up to a word)
+    __device__ __forceinline__ bool overrun() const { return ((bq - 32u) >> 3) >= wendb + 4u; }
+    __device__ __forceinline__ void give_up() { wendb = 0u; bq |= 0x100u; }     // overrun() from now on; later chunks read as zero
     __device__ __forceinline__ uint32_t get(uint32_t k) {          // k <= 32
         fill();
         const uint32_t v = __funnelshift_rc(ahi, 0u, 32u - k);      // ahi >> (32 - k), 0 when k == 0
@@ -352,31 +357,38 @@ struct BitReader {
         while (ahi == 0u) {                                        // rare: more than 31 zeros in a row
             q += 32; consume(32);
             fill();
-            if (overrun() || q > (1u << 26)) { wi = wend + 3u; return q; }
+            if (overrun() || q > (1u << 26)) { give_up(); return q; }
         }
         const uint32_t z = (uint32_t)__clz((int)ahi);
         q += z;
         consume(z + 1u);
         return q;
     }
-    // one Rice code with parameter k (< 31): when the unary zeros, the stop bit and the k low bits all lie in the 32 valid
-    // bits at the top of the window this is one refill check and one extraction; anything longer takes the generic path
+    // one Rice code with parameter k (< 31): when the unary zeros, the stop bit and the k low bits all lie in the 32 bits
+    // of ahi this is one branch-free refill and one extraction; anything longer takes the generic path.
+    // FAST: the caller has called top_up() at most four fast-path symbols ago.
+    template <bool FAST>
     __device__ __forceinline__ int32_t rice(uint32_t k) {
-        fill();
+        if (FAST) fill_fast(); else fill();
         const uint32_t z = (uint32_t)__clz((int)ahi);              // 32 when ahi == 0
+        const uint32_t len = z + 1u + k;
         uint32_t u;
-        if (z + 1u + k <= 32u) {
-            const uint32_t t = __funnelshift_lc(alo, ahi, z + 1u); // the bits after the stop bit
+        if (len <= 32u) {
+            const uint32_t t = __funnelshift_l(alo, ahi, z + 1u);   // the bits after the stop bit (z + 1 <= 32 - k < 32 ... or k == 0)
             u = (z << k) | __funnelshift_rc(t, 0u, 32u - k);
-            consume(z + 1u + k);
+            ahi = __funnelshift_lc(alo, ahi, len);                  // consume; alo is rebuilt by the next fill
+            bq += len;
         } else {
             const uint32_t qv = unary();
             u = (qv << k) | get(k);
         }
         return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u);
     }
-    // bit offset (from the stream start) of the next unread bit
-    __device__ __forceinline__ uint64_t bit_position() const { return (uint64_t)((int64_t)wi * 4 + off0) * 8ull - (uint64_t)n; }
+    // bit offset (from the stream start) of the next unread bit; start = byte offset handed to init()
+    __device__ __forceinline__ uint64_t bit_position(const uint8_t* base, uint64_t start) const {
+        const int64_t off0 = (int64_t)start - (int64_t)((uintptr_t)(base + start) & 15u);
+        return (uint64_t)(off0 * 8ll + (int64_t)bq - 32ll);
+    }
 };
 
 #ifndef FB_DEC_MIN_CTAS
@@ -413,13 +425,14 @@ __device__ __forceinline__ void restore4(int32_t (&h)[kDecFastOrder], const int3
 __global__ void __launch_bounds__(kDecFrameThreads, FB_DEC_MIN_CTAS)
 dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, const uint64_t* __restrict__ stream_len,
                  DecCand* __restrict__ cands, int n_cands, const uint64_t* __restrict__ slot_off, int32_t* __restrict__ samples) {
-    __shared__ uint4 ring_buf[kDecRing][kDecFrameThreads];
+    __shared__ __align__(64) uint4 ring_buf[kDecFrameThreads][kDecRing];
     const int ci = blockIdx.x * kDecFrameThreads + threadIdx.x;
     if (ci >= n_cands) return;
     DecCand c = cands[ci];
     const uint8_t* sbase = blob + stream_off[c.stream];
     const uint64_t slen = stream_len[c.stream];
-    BitReader br; br.init(sbase, (uint64_t)c.pos + c.hdr_bytes, slen, (uint32_t)__cvta_generic_to_shared(&ring_buf[0][threadIdx.x]));
+    const uint64_t body = (uint64_t)c.pos + c.hdr_bytes;
+    BitReader br; br.init(sbase, body, slen, (uint32_t)__cvta_generic_to_shared(&ring_buf[threadIdx.x][0]));
     const uint32_t N = c.blocksize;
     int32_t* out = samples + slot_off[ci];                                  // 16-byte aligned (dec_cand_size_kernel pads the slots)
     int status = kDecOk;
@@ -494,7 +507,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
                 for (uint32_t i = order; i < N; i++) {
                     while (left == 0) { left = (N >> po) - (first ? order : 0u); first = false; k = br.get(plen); raw = (k == pesc) ? br.get(5) : 0u; }
                     left--;
-                    const int32_t r = (k == pesc) ? br.get_signed(raw) : br.rice(k);
+                    const int32_t r = (k == pesc) ? br.get_signed(raw) : br.rice<false>(k);
                     long long sacc = 0;
                     for (uint32_t j = 0; j < order; j++) sacc += (long long)qq[j] * hh[(i - 1 - j) & 31u];
                     const long long v = (long long)r + (sacc >> shift);
@@ -552,7 +565,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
         for (; i < scalar_end; i++) {
             while (left == 0) { left = psize - (first ? order : 0u); first = false; k = br.get(plen); raw = (k == pesc) ? br.get(5) : 0u; }
             left--;
-            const int32_t r = (k == pesc) ? br.get_signed(raw) : br.rice(k);
+            const int32_t r = (k == pesc) ? br.get_signed(raw) : br.rice<false>(k);
             long long s = 0;
 #pragma unroll
             for (int j = 0; j < kDecFastOrder; j++) s += (long long)q[j] * (long long)h[j];
@@ -571,13 +584,14 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
                 const int cls = (int)__reduce_max_sync(__activemask(), (unsigned)cls_own);
                 while (left == 0) { left = psize - (first ? order : 0u); first = false; k = br.get(plen); raw = (k == pesc) ? br.get(5) : 0u; }
                 left -= 4;
+                br.top_up();                                                     // covers the four fast-path symbols below
                 int32_t r[4];
                 if (k == pesc) {
 #pragma unroll
                     for (int u = 0; u < 4; u++) r[u] = br.get_signed(raw);
                 } else {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) r[u] = br.rice(k);
+                    for (int u = 0; u < 4; u++) r[u] = br.rice<true>(k);
                 }
                 int4 v4;
                 if (!wide) {
@@ -596,7 +610,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
         }
         if (br.overrun()) status = kDecIncomplete;
     }
-    uint64_t endbit = br.bit_position();
+    uint64_t endbit = br.bit_position(sbase, body);
     if (status == kDecOk) {
         // zero padding to the byte boundary, then CRC-16 (checked by the post kernel)
         const uint32_t padbits = (uint32_t)((8 - (endbit & 7)) & 7);
@@ -607,7 +621,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
         c.end_pos = (uint32_t)(endbyte + 2);
     }
     if (status != kDecOk) {                         // where the parse stopped: the resynchronisation scan goes on from here
-        const uint64_t stop = (br.bit_position() + 7ull) >> 3;
+        const uint64_t stop = br.wendb == 0u ? slen : (br.bit_position(sbase, body) + 7ull) >> 3;      // (a parse that gave up: the whole rest)
         c.end_pos = (uint32_t)(stop < slen ? stop : slen);
     }
     cands[ci].status = status;
@@ -617,6 +631,79 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
 // ------------------------------------------------------------------ CRC-16 of every decodable candidate: one warp each ----
 // (ref: format.h:467-475.)  Runs before the chain walk so that the walk can treat a frame with a bad checksum exactly as
 // libFLAC does: report it, drop it and search on from just behind its sync code.
+#ifndef FB_DEC_CRC_STAGED
+#define FB_DEC_CRC_STAGED 0
+#endif
+#if FB_DEC_CRC_STAGED
+// The frame is cut into 64-byte chunks counted from its END (so every chunk but the first is whole and the positional
+// weights are x^(512 j)); lane l of tile t takes chunk 32 t + l.  A tile's 2 KiB travel global -> shared as whole 16-byte
+// pieces, coalesced (four per lane: 64 sectors per tile; a lane fetching its own chunk word by word touched 1024), and
+// each lane then reads its chunk back from shared memory a word at a time.  Lanes are 64 bytes apart, so the tile is kept
+// skewed by one word per 64 bytes (byte b at word (b >> 2) + (b >> 6)): lane l's k-th word falls into bank 17 l + const.
+constexpr int kCrcTileBytes = 2048;
+__global__ void __launch_bounds__(128)
+dec_crc_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, DecCand* __restrict__ cands, int n_cands) {
+    __shared__ __align__(16) uint16_t tabs[4][256];
+    __shared__ uint32_t tile_buf[4][(kCrcTileBytes + 32) / 4 + (kCrcTileBytes + 32) / 64 + 1];
+    for (int i = threadIdx.x; i < 256; i += 128) reinterpret_cast<uint2*>(&tabs[0][0])[i] = reinterpret_cast<const uint2*>(&g_crc16_slice.t[0][0])[i];
+    __syncthreads();
+    const int ci = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (ci >= n_cands) return;
+    const DecCand c = cands[ci];
+    if (c.status != kDecOk) return;
+    const uint8_t* fb = blob + stream_off[c.stream] + c.pos;
+    const uint32_t nb = c.end_pos - c.pos - 2u;
+    uint32_t* tile = tile_buf[threadIdx.x >> 5];
+    auto tword = [&](uint32_t b) -> uint32_t& { return tile[(b >> 2) + (b >> 6)]; };           // b = byte offset in the tile, multiple of 4
+    const uint32_t nchunks = (nb + 63u) >> 6;
+    uint32_t acc = 0;
+    for (uint32_t t0 = 0; t0 < nchunks; t0 += 32) {
+        // tile = frame bytes [lo, hi), hi = nb - 64 t0; staged from the 16-byte boundary at or below fb + lo
+        const uint32_t hi = nb - (t0 << 6), lo = hi > (uint32_t)kCrcTileBytes ? hi - (uint32_t)kCrcTileBytes : 0u;
+        const uint8_t* g0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(fb + lo) & ~(uintptr_t)15);
+        const uint32_t shift = (uint32_t)((fb + lo) - g0);                      // tile byte b of the frame sits at tile[shift + b - lo]
+        const uint32_t pieces = (shift + (hi - lo) + 15u) >> 4;                 // <= 129
+        __syncwarp();
+        for (uint32_t pi = (uint32_t)lane; pi < pieces; pi += 32) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(g0) + pi);
+            uint32_t* d = &tword(pi << 4);                                      // a 16-byte piece never straddles a 64-byte block
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        __syncwarp();
+        const uint32_t j = t0 + (uint32_t)lane;
+        if (j < nchunks) {
+            const uint32_t end = nb - (j << 6);                                  // chunk = frame bytes [end - 64, end) or [0, end)
+            uint32_t crc = 0;
+            if (end >= 64u) {
+                const uint32_t o = shift + (end - 64u - lo), sh8 = (o & 3u) * 8u;
+                const uint32_t ob = o & ~3u;
+                uint32_t prev = tword(ob);
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t nxt = tword(ob + 4u * (uint32_t)(i + 1));
+                    const uint32_t w = __funnelshift_r(prev, nxt, sh8);
+                    prev = nxt;
+                    crc = (uint32_t)tabs[3][(crc >> 8) ^ (w & 0xffu)] ^ tabs[2][(crc & 0xffu) ^ ((w >> 8) & 0xffu)] ^ tabs[1][(w >> 16) & 0xffu] ^ tabs[0][w >> 24];
+                }
+            } else {
+                for (uint32_t b = 0; b < end; b++) {
+                    const uint32_t tb = shift + b - lo;
+                    crc = ((crc << 8) & 0xffffu) ^ tabs[0][(crc >> 8) ^ ((tword(tb & ~3u) >> ((tb & 3u) * 8u)) & 0xffu)];
+                }
+            }
+            uint16_t c16 = (uint16_t)crc;
+            if (j) c16 = crc16_mulmod(c16, g_crc_pos.lo[j & 255u]);
+            if (j >> 8) c16 = crc16_mulmod(c16, g_crc_pos.hi[(j >> 8) & 15u]);
+            acc ^= c16;
+        }
+    }
+    acc = __reduce_xor_sync(0xffffffffu, acc);
+    if (lane == 0) {
+        const uint16_t stored = (uint16_t)((uint16_t)fb[nb] << 8 | fb[nb + 1]);
+        if ((uint16_t)acc != stored) cands[ci].status = kDecCrcMismatch;
+    }
+}
+#else
 __global__ void __launch_bounds__(128)
 dec_crc_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, DecCand* __restrict__ cands, int n_cands) {
     __shared__ __align__(16) uint16_t tabs[4][256];
@@ -657,6 +744,7 @@ dec_crc_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ st
         if ((uint16_t)acc != stored) cands[ci].status = kDecCrcMismatch;
     }
 }
+#endif
 
 // ------------------------------------------------------------------ chain walk: one thread per stream ----
 // The sequential part of libFLAC's stream_decoder.c (frame_sync_ / read_frame_) over the candidate table, incl. what
