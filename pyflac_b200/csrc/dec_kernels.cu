@@ -271,57 +271,85 @@ __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, u
 //    stayed in the same word) j'+1 that belong in it, so "OR in word[j'+1] >> (32 - r'), set alo = word[j'+1] << r'" is
 //    right whether or not a word boundary was crossed (OR-ing bits that are already there changes nothing):
 //    two address instructions, one shared load, a byte swap, two shifts and an OR;
-//  * top_up(), once per four symbols in the hot loop, keeps the ring ahead of the reader: every 16-byte chunk up to three
-//    past the current one is requested with cp.async (one group per chunk) and all but the newest have landed when it
-//    returns -- enough for the words four fast-path symbols (at most 32 bits each) can reach.
+//  * top_up_hot(), once per four symbols in the hot loop, keeps the ring ahead of the reader: a lane asks for the next
+//    16-byte chunk with cp.async whenever fewer than kDecRing chunks from its current one are requested (a predicated copy, no
+//    branch), and EVERY lane closes one cp.async group per iteration.  Groups belong to threads, but the hardware counts
+//    them per warp: when only the lanes that had requested something closed a group and waited for "all but my newest",
+//    the warp as a whole waited for nearly every lane's newest request -- a full memory latency per iteration (51 % of all
+//    stall samples).  With one group per iteration for the whole warp, "all but the four newest" means "everything asked
+//    for at least four iterations ago", and that is enough: four fast-path symbols take at most 128 bits = one chunk, so
+//    a chunk that is needed now (the current one or the next) lay at least kDecRing - 1 = 7 chunks ahead when it was
+//    requested, i.e. at least five iterations ago.  Anything that can take more than 32 bits at a time (headers, escape
+//    codes, long unary runs, the scalar loops) goes through top_up(), which requests what is missing and waits for all of it.
 // The bytes travel global -> shared with cp.async and are read back a word at a time; loads into registers would not do:
 // the lanes reach their chunk boundaries at different symbols but share one register scoreboard, so every lane's refill
 // would wait for the load another lane issued an iteration earlier (measured: 62 % of all stall samples).
 constexpr int kDecFrameThreads = 64;
-constexpr int kDecRing = 4;             // 16-byte chunks per thread in the shared-memory ring: 64 contiguous bytes per thread
+constexpr int kDecRing = 8;             // 16-byte chunks per thread in the shared-memory ring: 128 contiguous bytes per thread
+constexpr int kDecHotGroups = 4;        // top_up_hot(): cp.async groups (= loop iterations) that may still be in flight
 
 struct BitReader {
-    const uint4* c16;                   // 16-byte aligned address at or below the first byte read
+    // Bank conflicts: a thread's ring is 128 contiguous bytes, so word w of every lane sits in bank w, and the lanes of a warp
+    // run within a few words of each other (same blocksize, similar bit rates): up to 32-way conflicts on the one shared load
+    // per symbol saturated the shared-memory pipe (40 % of all stall samples).  Lane l therefore counts its chunks from l & 7:
+    // positions, chunk numbers and the end mark below are all BIASED by (l & 7) chunks = 16 (l & 7) bytes = 128 (l & 7) bits,
+    // c16 is moved back by as many chunks, and nothing in the hot path knows: the low five bits of a bit position and the
+    // source address c16 + chunk are unchanged, while chunk c of lane l lands in ring slot (c + l) & 7.
+    const uint4* c16;                   // 16-byte aligned address at or below the first byte read, minus the bias
+    const uint4* safe;                  // some valid address for copies that are switched off (zero fill)
     uint32_t bq;                        // 32 + bit offset (from c16) of the next unread bit: bq >> 5 is the word fill_fast() merges
     uint32_t wendb;                     // byte offset of the first word past the stream (aligned up); 0 once a parse has given up
     uint32_t req;                       // next chunk to request
     uint32_t ahi, alo;                  // the 32 bits at the position; word[bq >> 5] << (bq & 31)
-    uint32_t ring;                      // shared-memory address of this thread's 64-byte ring (64-byte aligned)
-    __device__ __forceinline__ void request(uint32_t ci) const {
+    uint32_t ring;                      // shared-memory address of this thread's ring (kDecRing * 16 bytes, aligned to its size)
+    // chunk ci -> its ring slot when on is set (a predicated copy: no branch); chunks that start past the stream read as zero
+    __device__ __forceinline__ void request(uint32_t ci, bool on) const {
         const uint32_t dst = ring | ((ci & (uint32_t)(kDecRing - 1)) << 4);
-        const bool in = (ci << 4) < wendb;                                      // chunks that start past the stream read as zero
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(c16 + (in ? ci : 0u)), "r"(in ? 16u : 0u) : "memory");   // size 0: zero fill
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        const bool in = (ci << 4) < wendb;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 16, %2;\n\t}"
+                     :: "r"(dst), "l"(in ? c16 + ci : safe), "r"(in ? 16u : 0u), "r"((uint32_t)on) : "memory");   // size 0: zero fill
     }
-    // chunks cur .. cur+2 resident and cur+3 on its way, cur = the chunk of the word the next fill merges
+    // generic: chunks cur .. cur + kDecRing - 1 requested and resident, cur = the chunk of the word the next fill merges
     __device__ __forceinline__ void top_up() {
         const uint32_t want = (bq >> 7) + (uint32_t)kDecRing;
         if (req < want) {
 #pragma unroll 1
-            do { request(req); req++; } while (req < want);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            do { request(req, true); req++; } while (req < want);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+    }
+    // hot loop, once per iteration by every lane (see the header comment)
+    __device__ __forceinline__ void top_up_hot() {
+        const uint32_t want = (bq >> 7) + (uint32_t)kDecRing;
+        const bool need = req < want;
+        request(req, need);
+        req += need ? 1u : 0u;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" :: "n"(kDecHotGroups) : "memory");
     }
     __device__ __forceinline__ uint32_t ring_word(uint32_t byte_off) const {
         uint32_t raw;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(ring | (byte_off & (uint32_t)(kDecRing * 16 - 4))));
         return __byte_perm(raw, 0, 0x0123);
     }
-    __device__ __forceinline__ void init(const uint8_t* base, uint64_t start, uint64_t slen, uint32_t ring_addr) {
+    __device__ __forceinline__ void init(const uint8_t* base, uint64_t start, uint64_t slen, uint32_t ring_addr, const void* safe_addr) {
         const uint8_t* p = base + start;
         const uintptr_t a = (uintptr_t)p, a16 = a & ~(uintptr_t)15;
-        c16 = reinterpret_cast<const uint4*>(a16);
-        const uint64_t end_rel = slen - start + (uint64_t)(a - a16);    // stream end relative to c16 (bytes)
-        wendb = (uint32_t)(end_rel < 0xFFFFFFE0ull ? end_rel + 3u : 0xFFFFFFE0ull) & ~3u;   // (streams are shorter than 4 GiB)
+        const uint32_t lb = threadIdx.x & (uint32_t)(kDecRing - 1);     // the bias, in chunks
+        { const uint4* biased = reinterpret_cast<const uint4*>(a16) - lb; asm volatile("mov.u64 %0, %1;" : "=l"(c16) : "l"(biased)); }   // (kept as one value: see ring below)
+        safe = reinterpret_cast<const uint4*>(safe_addr);
+        const uint64_t end_rel = slen - start + (uint64_t)(a - a16);    // stream end relative to the unbiased c16 (bytes)
+        wendb = ((uint32_t)(end_rel < 0xFFFFFF00ull ? end_rel + 3u : 0xFFFFFF00ull) & ~3u) + 16u * lb;   // (streams are shorter than 4 GiB)
         // (through a volatile asm: left to itself the compiler rebuilds the address from %tid at every use, five instructions per symbol)
         asm volatile("mov.u32 %0, %1;" : "=r"(ring) : "r"(ring_addr));
 #pragma unroll
-        for (int i = 0; i < kDecRing; i++) request((uint32_t)i);
-        req = (uint32_t)kDecRing;
+        for (int i = 0; i < kDecRing; i++) request((uint32_t)i + lb, true);
+        req = (uint32_t)kDecRing + lb;
+        asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        const uint32_t bp = (uint32_t)(a - a16) * 8u;                   // first bit, a multiple of 8
-        bq = bp + 32u;
-        ahi = ring_word(bp >> 3) << (bp & 31u);                          // the part of the first word that belongs to the stream
+        bq = (uint32_t)(a - a16) * 8u + 32u + 128u * lb;                // the first bit is a multiple of 8
+        ahi = ring_word((bq - 32u) >> 3) << (bq & 31u);                  // the part of the first word that belongs to the stream
         alo = 0u;
         fill();
     }
@@ -351,6 +379,18 @@ struct BitReader {
         const uint32_t v = get(k);
         return (int32_t)(v << (32 - k)) >> (32 - k);
     }
+    // the same two for the hot loop (k <= 32; covered by top_up_hot() like the fast-path Rice codes)
+    __device__ __forceinline__ uint32_t get_hot(uint32_t k) {
+        fill_fast();
+        const uint32_t v = __funnelshift_rc(ahi, 0u, 32u - k);
+        consume(k);
+        return v;
+    }
+    __device__ __forceinline__ int32_t get_signed_hot(uint32_t k) {
+        if (k == 0) return 0;
+        const uint32_t v = get_hot(k);
+        return (int32_t)(v << (32 - k)) >> (32 - k);
+    }
     __device__ __forceinline__ uint32_t unary() {
         fill();
         uint32_t q = 0;
@@ -366,7 +406,7 @@ struct BitReader {
     }
     // one Rice code with parameter k (< 31): when the unary zeros, the stop bit and the k low bits all lie in the 32 bits
     // of ahi this is one branch-free refill and one extraction; anything longer takes the generic path.
-    // FAST: the caller has called top_up() at most four fast-path symbols ago.
+    // FAST: the caller has called top_up_hot() at most four fast-path symbols ago.
     template <bool FAST>
     __device__ __forceinline__ int32_t rice(uint32_t k) {
         if (FAST) fill_fast(); else fill();
@@ -387,7 +427,7 @@ struct BitReader {
     // bit offset (from the stream start) of the next unread bit; start = byte offset handed to init()
     __device__ __forceinline__ uint64_t bit_position(const uint8_t* base, uint64_t start) const {
         const int64_t off0 = (int64_t)start - (int64_t)((uintptr_t)(base + start) & 15u);
-        return (uint64_t)(off0 * 8ll + (int64_t)bq - 32ll);
+        return (uint64_t)(off0 * 8ll + (int64_t)bq - 32ll - 128ll * (long long)(threadIdx.x & (uint32_t)(kDecRing - 1)));
     }
 };
 
@@ -407,12 +447,12 @@ __device__ __forceinline__ void restore4(int32_t (&h)[kDecFastOrder], const int3
         if (WIDE) {
             long long s = 0;
 #pragma unroll
-            for (int j = 0; j < TAPS; j++) s += (long long)q[j] * (long long)h[j];
+            for (int j = TAPS - 1; j >= 0; j--) s += (long long)q[j] * (long long)h[j];     // the newest sample's product last: one multiply-add on the sample-to-sample chain
             v[u] = (int32_t)((long long)r[u] + (s >> shift));
         } else {
             int s = 0;
 #pragma unroll
-            for (int j = 0; j < TAPS; j++) s += q[j] * h[j];
+            for (int j = TAPS - 1; j >= 0; j--) s += q[j] * h[j];
             v[u] = r[u] + (s >> shift);
         }
 #pragma unroll
@@ -425,14 +465,14 @@ __device__ __forceinline__ void restore4(int32_t (&h)[kDecFastOrder], const int3
 __global__ void __launch_bounds__(kDecFrameThreads, FB_DEC_MIN_CTAS)
 dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ stream_off, const uint64_t* __restrict__ stream_len,
                  DecCand* __restrict__ cands, int n_cands, const uint64_t* __restrict__ slot_off, int32_t* __restrict__ samples) {
-    __shared__ __align__(64) uint4 ring_buf[kDecFrameThreads][kDecRing];
+    __shared__ __align__(128) uint4 ring_buf[kDecFrameThreads][kDecRing];
     const int ci = blockIdx.x * kDecFrameThreads + threadIdx.x;
     if (ci >= n_cands) return;
     DecCand c = cands[ci];
     const uint8_t* sbase = blob + stream_off[c.stream];
     const uint64_t slen = stream_len[c.stream];
     const uint64_t body = (uint64_t)c.pos + c.hdr_bytes;
-    BitReader br; br.init(sbase, body, slen, (uint32_t)__cvta_generic_to_shared(&ring_buf[threadIdx.x][0]));
+    BitReader br; br.init(sbase, body, slen, (uint32_t)__cvta_generic_to_shared(&ring_buf[threadIdx.x][0]), cands);
     const uint32_t N = c.blocksize;
     int32_t* out = samples + slot_off[ci];                                  // 16-byte aligned (dec_cand_size_kernel pads the slots)
     int status = kDecOk;
@@ -577,18 +617,17 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
             if (br.overrun()) break;
         }
         if (quads && !br.overrun()) {
-            const int cls_own = order <= 4u ? 0 : (order <= 8u ? 1 : 2);
+            // the lanes that arrive here together all take the widest class any of them needs (surplus taps multiply zero
+            // coefficients): one body per warp and iteration instead of up to three run one after the other
+            const int cls = (int)__reduce_max_sync(__activemask(), order <= 4u ? 0u : (order <= 8u ? 1u : 2u));
             for (; i < N; i += 4) {
-                // the lanes that are here together all take the widest class any of them needs (surplus taps multiply zero
-                // coefficients): one body per warp and iteration instead of up to three run one after the other
-                const int cls = (int)__reduce_max_sync(__activemask(), (unsigned)cls_own);
-                while (left == 0) { left = psize - (first ? order : 0u); first = false; k = br.get(plen); raw = (k == pesc) ? br.get(5) : 0u; }
+                br.top_up_hot();                                                 // covers this iteration: at most 2 x 10 + 4 x 32 bits outside the generic path
+                while (left == 0) { left = psize - (first ? order : 0u); first = false; k = br.get_hot(plen); raw = (k == pesc) ? br.get_hot(5) : 0u; }
                 left -= 4;
-                br.top_up();                                                     // covers the four fast-path symbols below
                 int32_t r[4];
                 if (k == pesc) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) r[u] = br.get_signed(raw);
+                    for (int u = 0; u < 4; u++) r[u] = br.get_signed_hot(raw);
                 } else {
 #pragma unroll
                     for (int u = 0; u < 4; u++) r[u] = br.rice<true>(k);
@@ -605,7 +644,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
                 }
                 v4.x <<= wsh; v4.y <<= wsh; v4.z <<= wsh; v4.w <<= wsh;
                 *reinterpret_cast<int4*>(o + i) = v4;
-                if (br.overrun()) break;
+                if (br.wendb == 0u) break;                                       // a parse that ran off the end (zeros: the generic path gives up)
             }
         }
         if (br.overrun()) status = kDecIncomplete;
@@ -632,7 +671,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
 // (ref: format.h:467-475.)  Runs before the chain walk so that the walk can treat a frame with a bad checksum exactly as
 // libFLAC does: report it, drop it and search on from just behind its sync code.
 #ifndef FB_DEC_CRC_STAGED
-#define FB_DEC_CRC_STAGED 0
+#define FB_DEC_CRC_STAGED 1
 #endif
 #if FB_DEC_CRC_STAGED
 // The frame is cut into 64-byte chunks counted from its END (so every chunk but the first is whole and the positional
@@ -965,7 +1004,15 @@ void launch_dec_cand_size(const DecCand* cands, int n, uint32_t* sizes, cudaStre
     if (n) dec_cand_size_kernel<<<(n + 255) / 256, 256, 0, st>>>(cands, n, sizes);
 }
 void launch_dec_frames(const uint8_t* blob, const uint64_t* soff, const uint64_t* slen, DecCand* cands, int n, const uint64_t* slot_off, int32_t* samples, cudaStream_t st) {
-    if (n) dec_frame_kernel<<<(n + kDecFrameThreads - 1) / kDecFrameThreads, kDecFrameThreads, 0, st>>>(blob, soff, slen, cands, n, slot_off, samples);
+    if (!n) return;
+    // sixteen CTAs per SM need 16 x (8 KiB of rings + 1 KiB reserved): ask for the large shared-memory carve-out once per device
+    static unsigned long long carved = 0ull;
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !((carved >> dev) & 1ull)) {
+        cudaFuncSetAttribute(dec_frame_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carved |= 1ull << dev;
+    }
+    dec_frame_kernel<<<(n + kDecFrameThreads - 1) / kDecFrameThreads, kDecFrameThreads, 0, st>>>(blob, soff, slen, cands, n, slot_off, samples);
 }
 void launch_dec_chain(DecCand* cands, const uint32_t* cand_first, const DecStreamMeta* meta, const uint64_t* slen, int ns, int eof, DecStreamResult* res,
                       uint32_t* ss32, unsigned int* any_gap, cudaStream_t st) {
