@@ -256,8 +256,9 @@ dec_scan_u32_kernel(const uint32_t* __restrict__ in, int n, uint32_t* __restrict
 __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, uint32_t* __restrict__ sizes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     // 32-bit stereo: a side subframe may hold 33-bit samples; they are kept as (sample >> 1) plus a bitmap of the dropped bits
-    // slots are padded to four elements so that every frame's planes start 16-byte aligned (dec_frame_kernel stores int4)
-    if (i < n) sizes[i] = (cands[i].blocksize * cands[i].channels + ((cands[i].bps == 32 && cands[i].channels == 2) ? (cands[i].blocksize + 31) / 32 : 0u) + 3u) & ~3u;
+    // slots are padded so that every frame's planes start 32-byte aligned
+    // (eight elements: dec_frame_kernel stores 32 bytes at a time where the blocksize allows)
+    if (i < n) sizes[i] = (cands[i].blocksize * cands[i].channels + ((cands[i].bps == 32 && cands[i].channels == 2) ? (cands[i].blocksize + 31) / 32 : 0u) + 7u) & ~7u;
 }
 
 // ------------------------------------------------------------------ frame decode: one thread per candidate ----
@@ -285,8 +286,24 @@ __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, u
 // the lanes reach their chunk boundaries at different symbols but share one register scoreboard, so every lane's refill
 // would wait for the load another lane issued an iteration earlier (measured: 62 % of all stall samples).
 constexpr int kDecFrameThreads = 64;
-constexpr int kDecRing = 8;             // 16-byte chunks per thread in the shared-memory ring: 128 contiguous bytes per thread
-constexpr int kDecHotGroups = 4;        // top_up_hot(): cp.async groups (= loop iterations) that may still be in flight
+#ifndef FB_DEC_RING
+#define FB_DEC_RING 4
+#endif
+#ifndef FB_DEC_CARVE
+#define FB_DEC_CARVE 0
+#endif
+#ifndef FB_DEC_CG
+#define FB_DEC_CG 0
+#endif
+#ifndef FB_DEC_ST256
+#define FB_DEC_ST256 1
+#endif
+constexpr int kDecRing = FB_DEC_RING;   // 16-byte chunks per thread in the shared-memory ring (8: 128 contiguous bytes per thread)
+// top_up_hot(): cp.async groups (= loop iterations) that may still be in flight.  A chunk that is needed now lay at least kDecRing
+// chunk numbers ahead of the position at the top-up before the one that requested it, i.e. (kDecRing - 1) * 128 + 1 bits, and an
+// iteration takes at most 148 bits outside the generic path: ring 8 -> requested >= 5 iterations ago, ring 4 -> >= 1.
+constexpr int kDecHotGroups = kDecRing == 8 ? 4 : 1;
+static_assert(kDecRing == 8 || kDecRing == 4, "ring depth");
 
 struct BitReader {
     // Bank conflicts: a thread's ring is 128 contiguous bytes, so word w of every lane sits in bank w, and the lanes of a warp
@@ -306,7 +323,11 @@ struct BitReader {
     __device__ __forceinline__ void request(uint32_t ci, bool on) const {
         const uint32_t dst = ring | ((ci & (uint32_t)(kDecRing - 1)) << 4);
         const bool in = (ci << 4) < wendb;
+#if FB_DEC_CG
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}"
+#else
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 16, %2;\n\t}"
+#endif
                      :: "r"(dst), "l"(in ? c16 + ci : safe), "r"(in ? 16u : 0u), "r"((uint32_t)on) : "memory");   // size 0: zero fill
     }
     // generic: chunks cur .. cur + kDecRing - 1 requested and resident, cur = the chunk of the word the next fill merges
@@ -325,6 +346,8 @@ struct BitReader {
         const bool need = req < want;
         request(req, need);
         req += need ? 1u : 0u;
+#pragma unroll 1
+        while (req < want) { request(req, true); req++; }               // (an iteration that took more than 128 bits can cross two chunk boundaries)
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group %0;" :: "n"(kDecHotGroups) : "memory");
     }
@@ -600,7 +623,11 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
         // samples, one partition test per four.  Scalar iterations lead up to the first multiple of four; everything
         // else is scalar throughout.  Lanes of a warp keep their own counters, so mixed orders stay converged.
         const bool quads = ((N | psize) & 3u) == 0u;
-        const uint32_t scalar_end = quads ? min(N, (order + 3u) & ~3u) : N;
+        // Stores: what bounds this kernel once the instruction count is down is the number of memory REQUESTS an SM can send
+        // (every lane writes its own plane: 32 separate requests per warp store, about one per four cycles per SM), so two
+        // quads leave as one 32-byte store (STG.256) where the blocksize is a multiple of eight.
+        const bool octs = FB_DEC_ST256 && (N & 7u) == 0u;
+        const uint32_t scalar_end = quads ? min(N, octs ? (order + 7u) & ~7u : (order + 3u) & ~3u) : N;
         uint32_t i = order;
         for (; i < scalar_end; i++) {
             while (left == 0) { left = psize - (first ? order : 0u); first = false; k = br.get(plen); raw = (k == pesc) ? br.get(5) : 0u; }
@@ -620,6 +647,7 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
             // the lanes that arrive here together all take the widest class any of them needs (surplus taps multiply zero
             // coefficients): one body per warp and iteration instead of up to three run one after the other
             const int cls = (int)__reduce_max_sync(__activemask(), order <= 4u ? 0u : (order <= 8u ? 1u : 2u));
+            int4 stash = make_int4(0, 0, 0, 0);
             for (; i < N; i += 4) {
                 br.top_up_hot();                                                 // covers this iteration: at most 2 x 10 + 4 x 32 bits outside the generic path
                 while (left == 0) { left = psize - (first ? order : 0u); first = false; k = br.get_hot(plen); raw = (k == pesc) ? br.get_hot(5) : 0u; }
@@ -643,7 +671,10 @@ dec_frame_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ 
                     else restore4<12, true>(h, q, r, shift, v4);
                 }
                 v4.x <<= wsh; v4.y <<= wsh; v4.z <<= wsh; v4.w <<= wsh;
-                *reinterpret_cast<int4*>(o + i) = v4;
+                if (!octs) *reinterpret_cast<int4*>(o + i) = v4;
+                else if (i & 4u) asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(o + i - 4), "r"(stash.x), "r"(stash.y), "r"(stash.z), "r"(stash.w),
+                                              "r"(v4.x), "r"(v4.y), "r"(v4.z), "r"(v4.w) : "memory");
+                else stash = v4;
                 if (br.wendb == 0u) break;                                       // a parse that ran off the end (zeros: the generic path gives up)
             }
         }
@@ -1008,7 +1039,7 @@ void launch_dec_frames(const uint8_t* blob, const uint64_t* soff, const uint64_t
     // sixteen CTAs per SM need 16 x (8 KiB of rings + 1 KiB reserved): ask for the large shared-memory carve-out once per device
     static unsigned long long carved = 0ull;
     int dev = 0; cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !((carved >> dev) & 1ull)) {
+    if (FB_DEC_CARVE && dev >= 0 && dev < 64 && !((carved >> dev) & 1ull)) {
         cudaFuncSetAttribute(dec_frame_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         carved |= 1ull << dev;
     }

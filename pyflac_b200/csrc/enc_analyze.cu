@@ -520,6 +520,147 @@ autoc_kernel(const PcmT* __restrict__ pcm, const FrameDesc* __restrict__ frames,
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same autocorrelation for the headline layout (16-bit stereo staged as packed words, L / R / mid / side, at most nine
+// lags: levels 3-7), with the chains dealt differently: TWO lanes per job, five chains per lane (lags 0-4 and 4-8; lag 4 is
+// computed twice), SIXTEEN jobs = four (frame, window) sources per warp, all 32 lanes busy.  autoc_kernel spends three lanes
+// x four chains = twelve chains on a nine-lag job and keeps 24 lanes busy: per job and step 0.5 FP64 warp instructions and
+// 0.31 shared-memory wavefronts against 0.31 and 0.19 here -- and these two are what bounds the kernel (dependent DFMA
+// chains fed from shared memory).  Each chain is still one strictly sequential sum in ascending sample order.
+constexpr int kAc5Jobs = 16, kAc5Src = 4;
+#ifndef FB_AC5_MIN_CTAS
+#define FB_AC5_MIN_CTAS 5
+#endif
+struct AcRaw4 { int wd[kAc5Src]; float wv[kAc5Src]; };
+
+__device__ __forceinline__ void ac5_load(AcRaw4& R, const AcSource (&src)[kAc5Src], const float* __restrict__ windows, int i) {
+#pragma unroll
+    for (int u = 0; u < kAc5Src; u++) {
+        R.wv[u] = 0.0f; R.wd[u] = 0;
+        if (i < src[u].len && i < 2 * src[u].part) {
+            R.wv[u] = __ldg(windows + (i < src[u].part ? src[u].wofs : src[u].wtail) + i);
+            if ((reinterpret_cast<uintptr_t>(src[u].base) & 3u) == 0) R.wd[u] = __ldg(reinterpret_cast<const int*>(src[u].base) + i);
+            else R.wd[u] = (int)((uint32_t)(uint16_t)__ldg(src[u].base + 2 * i) | ((uint32_t)(uint16_t)__ldg(src[u].base + 2 * i + 1) << 16));
+        }
+    }
+}
+// windowed sample of the four signals of every source -> the jobs' ring slots (as doubles)
+__device__ __forceinline__ void ac5_store(double* __restrict__ ring, const AcRaw4& R, const AcSource (&src)[kAc5Src], int pos, bool mirror, int mpos) {
+#pragma unroll
+    for (int u = 0; u < kAc5Src; u++) {
+        const int lo = (int)(short)R.wd[u], hi = R.wd[u] >> 16;
+        const float wv = R.wv[u];
+        const uint32_t sp = src[u].shpack;
+        double d[4];
+        d[0] = (double)FB_FMUL(__int2float_rn(lo >> (sp & 0xff)), wv);
+        d[1] = (double)FB_FMUL(__int2float_rn(hi >> ((sp >> 8) & 0xff)), wv);
+        d[2] = (double)FB_FMUL(__int2float_rn((lo + hi) >> ((sp >> 16) & 0xff)), wv);
+        d[3] = (double)FB_FMUL(__int2float_rn((lo - hi) >> (sp >> 24)), wv);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            ring[(4 * u + q) * kAcRing + pos] = d[q];
+            if (mirror) ring[(4 * u + q) * kAcRing + mpos] = d[q];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kAcThreads, FB_AC5_MIN_CTAS)
+autoc5_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict__ frames, int n_frames, const float* __restrict__ windows,
+              EncParams P, unsigned char* __restrict__ work, size_t work_stride, int unshifted) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int nsig = 4, ch = 2;
+    const int nwin = (int)(P.apod_parts * (P.apod_parts + 1) / 2);
+    double* ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * kAc5Jobs * kAcRing;
+    AcJob* jobs = reinterpret_cast<AcJob*>(smem_raw + (size_t)(kAcThreads / 32) * kAc5Jobs * kAcRing * 8) + warp * kAc5Jobs;
+
+    // ---- which jobs does this warp own?  depth b = 1..parts, each depth padded to whole warps (as autoc_kernel) ----
+    long long W = (long long)blockIdx.x * (kAcThreads / 32) + warp;
+    int b = 1;
+    for (;; b++) {
+        if (b > (int)P.apod_parts) return;
+        const long long nj = (long long)n_frames * nsig * b, nw = (nj + kAc5Jobs - 1) / kAc5Jobs;
+        if (W < nw) break;
+        W -= nw;
+    }
+    const long long r0 = W * kAc5Jobs, nj = (long long)n_frames * nsig * b;
+    if (lane < kAc5Jobs) {
+        AcJob J;
+        J.base = nullptr; J.sel = 0; J.sh = 0; J.len = 0; J.part = 0; J.N = 0; J.woff = 0;
+        const long long r = r0 + lane;
+        if (r < nj) {
+            const int f = (int)(r / (nsig * b)), rem = (int)(r - (long long)f * (nsig * b)), k = rem / nsig, s = rem - k * nsig;
+            const FrameDesc fd = frames[f];
+            const int N = (int)fd.blocksize;
+            if (N > 4 && !(b > 1 && N / b <= 32)) {
+                const FrameBits* fb = frame_bits(work, work_stride, f);
+                const int wst = unshifted ? 0 : wasted_from_or(fb->or_[s], (int)P.bps, false);
+                const int off = (k * N) / b;
+                J.base = pcm + fd.pcm_off + (size_t)off * ch;
+                J.sh = (s == ch) ? wst + 1 : wst;                        // mid: (L + R) >> 1
+                J.len = N / b; J.part = (b == 1) ? N : N / b / 2; J.N = N; J.woff = fd.window_off;
+            }
+        }
+        jobs[lane] = J;
+    }
+    for (int idx = lane; idx < kAc5Jobs * 16; idx += 32) ring[(idx >> 4) * kAcRing + (idx & 15)] = 0.0;
+    __syncwarp();
+    int maxlen = 0;
+    for (int q = 0; q < kAc5Jobs; q++) maxlen = max(maxlen, jobs[q].len);
+    if (maxlen == 0) return;
+
+    AcSource src[kAc5Src];                  // the four jobs of one (frame, window) read the same words and window values
+#pragma unroll
+    for (int u = 0; u < kAc5Src; u++) {
+        const AcJob& J0 = jobs[u * nsig];
+        src[u].base = reinterpret_cast<const int16_t*>(J0.base); src[u].len = J0.len;
+        src[u].part = J0.part; src[u].wofs = (int)J0.woff; src[u].wtail = (int)J0.woff + J0.N - 2 * J0.part;
+        uint32_t shp = 0;
+        for (int s2 = 0; s2 < nsig; s2++) shp |= (uint32_t)(jobs[u * nsig + s2].sh & 0xff) << (8 * s2);
+        src[u].shpack = shp;
+    }
+    AcRaw4 raw;
+    ac5_load(raw, src, windows, lane);
+    ac5_store(ring, raw, src, 16 + lane, false, 0);
+    __syncwarp();
+
+    const int jb = lane >> 1, qd = lane & 1;
+    const double* jobring = ring + jb * kAcRing;
+    const int lag0 = 4 * qd;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;      // chains of lags lag0 .. lag0+4
+    double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;                 // lagged operands of the four previous steps
+    const int nchunks = (maxlen + 31) >> 5;
+    for (int c = 0; c < nchunks; c++) {
+        const int slot = c & 1;
+        ac5_load(raw, src, windows, (c + 1) * 32 + lane);          // in flight while the chains run
+        {
+            const double* curp = jobring + 16 + slot * 32;
+            const double* lagp = curp - lag0;
+#pragma unroll
+            for (int s = 0; s < 32; s += 2) {
+                const double2 c2 = *reinterpret_cast<const double2*>(curp + s);
+                const double2 l2 = *reinterpret_cast<const double2*>(lagp + s);
+                a0 = fma(c2.x, l2.x, a0); a1 = fma(c2.x, p1, a1); a2 = fma(c2.x, p2, a2); a3 = fma(c2.x, p3, a3); a4 = fma(c2.x, p4, a4);
+                a0 = fma(c2.y, l2.y, a0); a1 = fma(c2.y, l2.x, a1); a2 = fma(c2.y, p1, a2); a3 = fma(c2.y, p2, a3); a4 = fma(c2.y, p3, a4);
+                p4 = p2; p3 = p1; p2 = l2.x; p1 = l2.y;
+            }
+        }
+        __syncwarp();
+        // the next chunk into the other slot; slot 1's tail is mirrored in front of slot 0
+        ac5_store(ring, raw, src, 16 + (slot ^ 1) * 32 + lane, slot == 0 && lane >= 16, lane - 16);
+        __syncwarp();
+    }
+    {
+        const long long r = r0 + jb;
+        if (r < nj && jobs[jb].len > 0) {
+            const int f = (int)(r / (nsig * b)), rem = (int)(r - (long long)f * (nsig * b)), k = rem / nsig, s = rem - k * nsig;
+            double* dst = frame_ac(work, work_stride, f) + ((size_t)s * nwin + (b - 1) * b / 2 + k) * kAcStoreStride + lag0;
+            dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
+            if (qd == 1) dst[4] = a4;                              // lag 8 (lane 0's fifth chain is lag 4 again)
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct AnShared {
     uint32_t sig_or[kMaxSignals], sig_and[kMaxSignals];
     uint32_t best_bits[kMaxSignals];                 // winner of the fixed task, then of the whole signal
@@ -950,6 +1091,19 @@ void launch_autoc_unshifted(const void* pcm, const FrameDesc* frames, const floa
     if (P.max_lpc_order == 0 || n_frames == 0) return;
     const size_t stride = analyze_work_stride(P);
     const int lags = (int)P.max_lpc_order + 1, lpj = (lags + 3) / 4;
+#ifndef FB_AC5
+#define FB_AC5 1
+#endif
+    if (FB_AC5 && P.n_signals == 4 && lags > 4 && lags <= 9) {                 // two lanes x five chains per job, sixteen jobs per warp
+        long long warps5 = 0;
+        for (uint32_t b = 1; b <= P.apod_parts; b++) warps5 += ((long long)n_frames * 4 * b + kAc5Jobs - 1) / kAc5Jobs;
+        const size_t smem5 = (size_t)(kAcThreads / 32) * kAc5Jobs * (kAcRing * 8 + sizeof(AcJob));
+        static bool attr_set = false;       // (an attribute of the function, the same value on every device)
+        if (!attr_set) { cudaFuncSetAttribute(autoc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5); attr_set = true; }
+        const unsigned blocks5 = (unsigned)((warps5 + kAcThreads / 32 - 1) / (kAcThreads / 32));
+        autoc5_kernel<<<blocks5, kAcThreads, smem5, stream>>>((const int16_t*)pcm, frames, n_frames, windows, P, (unsigned char*)work, stride, 1);
+        return;
+    }
     int jpw = (32 / lpj) < kAcJobsMax ? (32 / lpj) : kAcJobsMax;
     if (jpw > 2 * (int)P.n_signals) jpw = 2 * (int)P.n_signals;
     jpw = jpw / (int)P.n_signals * (int)P.n_signals;
