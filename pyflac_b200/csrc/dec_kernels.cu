@@ -277,14 +277,22 @@ __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, u
 //    branch), and EVERY lane closes one cp.async group per iteration.  Groups belong to threads, but the hardware counts
 //    them per warp: when only the lanes that had requested something closed a group and waited for "all but my newest",
 //    the warp as a whole waited for nearly every lane's newest request -- a full memory latency per iteration (51 % of all
-//    stall samples).  With one group per iteration for the whole warp, "all but the four newest" means "everything asked
-//    for at least four iterations ago", and that is enough: four fast-path symbols take at most 128 bits = one chunk, so
-//    a chunk that is needed now (the current one or the next) lay at least kDecRing - 1 = 7 chunks ahead when it was
-//    requested, i.e. at least five iterations ago.  Anything that can take more than 32 bits at a time (headers, escape
-//    codes, long unary runs, the scalar loops) goes through top_up(), which requests what is missing and waits for all of it.
+//    stall samples, profiles/r02d).  With one group per iteration for the whole warp, "all but the newest" means "everything
+//    asked for in an earlier iteration", and that is enough: outside the generic path an iteration takes at most
+//    2 x 10 + 4 x 32 = 148 bits, and a chunk that is needed now lay kDecRing chunk numbers (at least 3 x 128 + 1 bits) ahead
+//    of the position at the top-up BEFORE the one that requested it -- more than two iterations' worth, so the request is at
+//    least one iteration old (kDecHotGroups below; a ring of eight allows four groups in flight and measured slower).
+//    Anything that can take more than 32 bits at a time (long unary runs, the scalar loops, subframe headers) goes through
+//    top_up(), which requests what is missing and waits for all of it.
 // The bytes travel global -> shared with cp.async and are read back a word at a time; loads into registers would not do:
 // the lanes reach their chunk boundaries at different symbols but share one register scoreboard, so every lane's refill
 // would wait for the load another lane issued an iteration earlier (measured: 62 % of all stall samples).
+//
+// What bounds the kernel once the instruction count is down (85 -> 48 per sample) is neither issue slots nor bytes but the
+// number of memory REQUESTS an SM can send: every lane reads its own stream and writes its own plane, so a warp-wide store
+// or cp.async is 32 separate requests, about one per four cycles per SM all told, and shared loads queue behind them
+// (400-cycle LDS latencies in profiles/r02d).  Hence the 32-byte plane stores in the hot loop (STG.256: 4.57 -> 2.44 ms).
+// Compile-time knobs below: the measured alternatives (gpurun_out/ab_decode_quick.log, ab_mixed.log).
 constexpr int kDecFrameThreads = 64;
 #ifndef FB_DEC_RING
 #define FB_DEC_RING 4
@@ -306,12 +314,11 @@ constexpr int kDecHotGroups = kDecRing == 8 ? 4 : 1;
 static_assert(kDecRing == 8 || kDecRing == 4, "ring depth");
 
 struct BitReader {
-    // Bank conflicts: a thread's ring is 128 contiguous bytes, so word w of every lane sits in bank w, and the lanes of a warp
-    // run within a few words of each other (same blocksize, similar bit rates): up to 32-way conflicts on the one shared load
-    // per symbol saturated the shared-memory pipe (40 % of all stall samples).  Lane l therefore counts its chunks from l & 7:
-    // positions, chunk numbers and the end mark below are all BIASED by (l & 7) chunks = 16 (l & 7) bytes = 128 (l & 7) bits,
-    // c16 is moved back by as many chunks, and nothing in the hot path knows: the low five bits of a bit position and the
-    // source address c16 + chunk are unchanged, while chunk c of lane l lands in ring slot (c + l) & 7.
+    // Bank conflicts: a thread's ring is contiguous, so word w of lanes l and l + 2 (ring of four chunks) sits in the same bank,
+    // and the lanes of a warp run within a few words of each other (same blocksize, similar bit rates).  Lane l therefore counts
+    // its chunks from l mod kDecRing: positions, chunk numbers and the end mark below are all BIASED by that many chunks
+    // (16 bytes = 128 bits each), c16 is moved back by as many chunks, and nothing in the hot path knows: the low five bits of
+    // a bit position and the source address c16 + chunk are unchanged, while chunk c of lane l lands in ring slot (c + l) mod kDecRing.
     const uint4* c16;                   // 16-byte aligned address at or below the first byte read, minus the bias
     const uint4* safe;                  // some valid address for copies that are switched off (zero fill)
     uint32_t bq;                        // 32 + bit offset (from c16) of the next unread bit: bq >> 5 is the word fill_fast() merges
@@ -455,7 +462,7 @@ struct BitReader {
 };
 
 #ifndef FB_DEC_MIN_CTAS
-#define FB_DEC_MIN_CTAS 16     // 64 registers (a few spilled words) at 32 warps/SM: measured 5.0 ms for 131 072 frames against 6.8 ms at 12 CTAs / 78 registers
+#define FB_DEC_MIN_CTAS 14     // 72 registers: the stash of the 32-byte stores stays in registers (16 CTAs / 64 registers spill it: 2.62 ms against 2.44 for 131 072 frames)
 #endif
 
 constexpr int kDecFastOrder = 12;      // predictor orders up to this keep history and coefficients in registers
