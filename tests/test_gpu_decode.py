@@ -222,3 +222,33 @@ def test_full_size_config4_decode_4096_streams(eng):
         assert np.array_equal(out[s], uniq[s % 64])
     total = sum(int(si.total_samples) for si in infos)
     assert total == 4096 * 131072
+
+
+def test_decode_hot_loop_long_codes(eng, checkers):
+    """The frame kernel's hot loop tops its ring up once per four symbols and reads partition headers, escape codes and Rice codes
+    of up to 32 bits without looking again (dec_kernels.cu: top_up_hot): loud noise (codes of 15-22 bits at high Rice
+    parameters: about 90 of the 128 bits a quad may take outside the generic path), impulses in silence (long unary runs -> generic path in
+    the middle of a quad) and 32 streams side by side whose lanes drift apart, all against the oracle's bytes."""
+    from pyflac_b200 import _native as nat
+    rng = np.random.default_rng(77)
+    xs, blobs = [], []
+    for lane in range(32):
+        n = 4096 * 3 + 8 * lane
+        if lane % 4 == 0:
+            x = rng.integers(-8192, 8192, (n, 2)).astype(np.int16)                      # ~15-bit codes (full scale would go out verbatim)
+        elif lane % 4 == 1:
+            x = np.zeros((n, 2), np.int16); x[rng.integers(0, n, 40), rng.integers(0, 2, 40)] = 32767   # impulses: unary runs past 32 zeros
+        elif lane % 4 == 2:
+            x = (rng.integers(-32768, 32768, (n, 2)) * (np.arange(n)[:, None] % 512 < 16)).astype(np.int16)  # bursts: mixed partitions
+        else:
+            x = corpus_signal("music", n, 2, 16, seed=lane)
+        xs.append(x)
+        blobs.append(checkers.oracle_encode(x, 48000, 16, (0, 3, 5, 8)[lane % 4 if lane % 4 != 3 else 2], 4096))
+    x24 = rng.integers(-(1 << 20), 1 << 20, (4096 * 2 + 24, 2)).astype(np.int32)        # ~22-bit codes: 90 bits per quad
+    out, infos = nat.decode_streams(eng, blobs)
+    for lane, (x, o, si) in enumerate(zip(xs, out, infos)):
+        assert si.status == 0, (lane, nat.DEC_STATUS.get(si.status))
+        assert np.array_equal(o, x), lane
+    out, infos = nat.decode_streams(eng, [checkers.oracle_encode(x24, 96000, 24, 5, 4096)] * 3)
+    for o, si in zip(out, infos):
+        assert si.status == 0 and np.array_equal(o, x24)
