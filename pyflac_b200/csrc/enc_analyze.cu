@@ -623,7 +623,13 @@ autoc5_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict__ fra
     ac5_store(ring, raw, src, 16 + lane, false, 0);
     __syncwarp();
 
-    const int jb = lane >> 1, qd = lane & 1;
+    // lanes 0-15 take the low halves (lags 0-4) of the sixteen jobs, lanes 16-31 the high halves: a quarter warp then reads eight
+    // different jobs' rings (16 bytes each, 4 banks apart: conflict free); with the two halves of a job in neighbouring lanes the
+    // high half's -32 bytes put jobs j and j + 2 into the same banks
+#ifndef FB_AC5_PAIRED
+#define FB_AC5_PAIRED 0
+#endif
+    const int jb = FB_AC5_PAIRED ? lane >> 1 : lane & 15, qd = FB_AC5_PAIRED ? lane & 1 : lane >> 4;
     const double* jobring = ring + jb * kAcRing;
     const int lag0 = 4 * qd;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;      // chains of lags lag0 .. lag0+4
@@ -638,6 +644,7 @@ autoc5_kernel(const int16_t* __restrict__ pcm, const FrameDesc* __restrict__ fra
 #pragma unroll
             for (int s = 0; s < 32; s += 2) {
                 const double2 c2 = *reinterpret_cast<const double2*>(curp + s);
+                // (the low halves' lagged operands are the current ones; loading them only in lanes 16-31 measured slower: 0.75 against 0.72 ms)
                 const double2 l2 = *reinterpret_cast<const double2*>(lagp + s);
                 a0 = fma(c2.x, l2.x, a0); a1 = fma(c2.x, p1, a1); a2 = fma(c2.x, p2, a2); a3 = fma(c2.x, p3, a3); a4 = fma(c2.x, p4, a4);
                 a0 = fma(c2.y, l2.y, a0); a1 = fma(c2.y, l2.x, a1); a2 = fma(c2.y, p1, a2); a3 = fma(c2.y, p2, a3); a4 = fma(c2.y, p3, a4);
