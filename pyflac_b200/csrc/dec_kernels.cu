@@ -292,7 +292,7 @@ __global__ void dec_cand_size_kernel(const DecCand* __restrict__ cands, int n, u
 // number of memory REQUESTS an SM can send: every lane reads its own stream and writes its own plane, so a warp-wide store
 // or cp.async is 32 separate requests, about one per four cycles per SM all told, and shared loads queue behind them
 // (400-cycle LDS latencies in profiles/r02d).  Hence the 32-byte plane stores in the hot loop (STG.256: 4.57 -> 2.44 ms).
-// Compile-time knobs below: the measured alternatives (gpurun_out/ab_decode_quick.log, ab_mixed.log).
+// Compile-time knobs below: the measured alternatives (profiles/r02d_ab_logs.txt).
 constexpr int kDecFrameThreads = 64;
 #ifndef FB_DEC_RING
 #define FB_DEC_RING 4
