@@ -9,4 +9,4 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:"aut
     python tools/prof_encode.py 5 256 > gpurun_out/prof_r2d_enc.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"dec_" -c 16 -f -o gpurun_out/prof_r2f_dec \
     python tools/prof_decode.py 4096 131072 > gpurun_out/prof_r2f_dec.log 2>&1
-tail -2 gpurun_out/prof_r2d_enc.log gpurun_out/prof_r2f_dec.log
+tail -n 2 gpurun_out/prof_r2d_enc.log; tail -n 2 gpurun_out/prof_r2f_dec.log
