@@ -768,10 +768,7 @@ dec_crc_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ st
                     crc = ((crc << 8) & 0xffffu) ^ tabs[0][(crc >> 8) ^ ((tword(tb & ~3u) >> ((tb & 3u) * 8u)) & 0xffu)];
                 }
             }
-            uint16_t c16 = (uint16_t)crc;
-            if (j) c16 = crc16_mulmod(c16, g_crc_pos.lo[j & 255u]);
-            if (j >> 8) c16 = crc16_mulmod(c16, g_crc_pos.hi[(j >> 8) & 15u]);
-            acc ^= c16;
+            acc ^= crc16_weigh_chunk((uint16_t)crc, j, g_crc_pos);          // (any frame size: a decoder can meet frames of 256 KiB and more)
         }
     }
     acc = __reduce_xor_sync(0xffffffffu, acc);
@@ -810,10 +807,7 @@ dec_crc_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ st
         } else {
             for (uint32_t b = 0; b < end; b++) crc = ((crc << 8) & 0xffffu) ^ tabs[0][(crc >> 8) ^ (word_at(b) & 0xffu)];
         }
-        uint16_t c16 = (uint16_t)crc;
-        if (j) c16 = crc16_mulmod(c16, g_crc_pos.lo[j & 255u]);
-        if (j >> 8) c16 = crc16_mulmod(c16, g_crc_pos.hi[(j >> 8) & 15u]);
-        acc ^= c16;
+        acc ^= crc16_weigh_chunk((uint16_t)crc, j, g_crc_pos);
     }
     acc = __reduce_xor_sync(0xffffffffu, acc);
     if (lane == 0) {

@@ -184,7 +184,6 @@ FB_HD uint16_t crc16_mulmod(uint16_t a, uint16_t b) {
     return (uint16_t)r;
 }
 
-#if defined(__CUDACC__)
 // Positional weights for a CTA-parallel CRC-16: the frame is cut into 64-byte chunks counted from its END,
 // chunk j's CRC is multiplied by x^(512 j) mod P (so that it stands where the chunk stands) and everything is
 // XORed: crc(A||B) = crc(A) * x^(8|B|) + crc(B).  lo[j] = x^(512 j), j < 256; hi[h] = x^(512*256*h), h < 16.
@@ -206,6 +205,21 @@ constexpr CrcPosTable make_crc_pos_table() {
     for (int j = 1; j < 16; j++) t.hi[j] = crc16_mulmod_c(t.hi[j - 1], step_hi);
     return t;
 }
+// Weight of chunk j for ANY j: the tables cover j < 4096 (frames under 256 KiB -- everything the encoder can produce, whose frames
+// must fit shared memory); a decoder can meet bigger frames (blocksize 65535, or many wide channels), and there the remaining factor
+// x^(512 * 4096 * (j >> 12)) comes from square-and-multiply.  Host and device (tests/test_abi_cpu.py checks it against a bytewise CRC).
+FB_HD uint16_t crc16_weigh_chunk(uint16_t c16, uint32_t j, const CrcPosTable& t) {
+    if (j) c16 = crc16_mulmod(c16, t.lo[j & 255u]);
+    if (j >> 8) c16 = crc16_mulmod(c16, t.hi[(j >> 8) & 15u]);
+    uint32_t h = j >> 12;
+    if (h) {
+        uint16_t step = crc16_mulmod(t.hi[15], t.hi[1]);                // x^(512 * 4096)
+        for (; h; h >>= 1) { if (h & 1u) c16 = crc16_mulmod(c16, step); step = crc16_mulmod(step, step); }
+    }
+    return c16;
+}
+
+#if defined(__CUDACC__)
 static __device__ const CrcPosTable g_crc_pos = make_crc_pos_table();
 
 // Slice-by-4 tables for the same CRC: t[0] is the plain byte table, t[k][x] = CRC of byte x followed by k zero bytes, so

@@ -69,6 +69,10 @@ def fbmath():
     L = C.CDLL(so)
     L.t_crc16_mulmod.restype = C.c_uint16
     L.t_crc16_byte.restype = C.c_uint16
+    L.t_crc16_chunked.restype = C.c_uint16
+    L.t_crc16_chunked.argtypes = [C.c_void_p, C.c_uint32]
+    L.t_crc16_plain.restype = C.c_uint16
+    L.t_crc16_plain.argtypes = [C.c_void_p, C.c_uint32]
     L.t_rice_parameter.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
     L.t_rice_bits.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
     return L
@@ -162,3 +166,13 @@ def test_host_multibuffer_md5_matches_hashlib():
                 got = np.zeros(16 * n, np.uint8)
                 assert L.t_md5_group(blob.ctypes.data, off.ctypes.data, ls.ctypes.data, n, lanes, got.ctypes.data) == 0
                 assert got.tobytes() == want, (lens[:n], lanes)
+
+
+def test_crc16_chunk_weights_any_frame_size(fbmath):
+    """dec_crc_kernel's combination of per-chunk CRCs (pyflac_b200/csrc/fb_math.cuh: crc16_weigh_chunk) equals the bytewise CRC-16
+    for every size, including frames of 256 KiB and more, where the chunk number runs past the two weight tables (a 65535-sample
+    verbatim stereo frame is 262 160 bytes)."""
+    rng = np.random.default_rng(5)
+    for n in (1, 63, 64, 65, 4096, 16383, 16384 + 7, 262143, 262144, 262145, 262144 + 64 * 5 + 3, 600001, 1 << 20, (1 << 21) + 12345, 5000000):
+        buf = rng.integers(0, 256, n).astype(np.uint8)
+        assert fbmath.t_crc16_chunked(buf.ctypes.data, n) == fbmath.t_crc16_plain(buf.ctypes.data, n), n
