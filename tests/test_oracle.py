@@ -211,3 +211,20 @@ def test_oracle_decodes_reference_fixtures(checkers):
         raw = pcm.astype("<i4").tobytes()
         le = b"".join(raw[i:i + width] for i in range(0, len(raw), 4)) if width != 4 else raw
         assert hashlib.md5(le).digest() == data[26:42], f
+
+
+def test_oracle_frames_of_256_kib_and_more(checkers):
+    """the stream behind tests/test_gpu_decode.py::test_decode_frames_of_256_kib_and_more: 16384 samples x 8 channels of
+    incompressible noise go out as VERBATIM subframes, 262 158 bytes per frame; the restatement round-trips it and (where the
+    reference binary is present) writes the binary's bytes, and the binary decodes them."""
+    rng = np.random.default_rng(3)
+    x = rng.integers(-32768, 32768, (16384 * 2 + 100, 8)).astype(np.int16)
+    blob = checkers.oracle_encode(x, 96000, 16, 5, 16384)
+    assert len(blob) > 2 * 262144
+    dec, info = checkers.oracle_decode(blob)
+    assert info["bps"] == 16 and np.array_equal(dec.reshape(x.shape), x)
+    if checkers.ref_available():
+        assert checkers.ref_encode(x, 96000, 16, 5, 16384) == blob
+        out = checkers.ref_decode(blob)
+        pcm = out[0] if isinstance(out, tuple) else out
+        assert np.array_equal(np.asarray(pcm).reshape(x.shape), x)
