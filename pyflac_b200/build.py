@@ -38,9 +38,29 @@ def _deps_mtime():
 
 
 def build(force=False, verbose=False):
-    """One nvcc -c per source (in parallel, objects cached under csrc/_obj), then one link."""
+    """One nvcc -c per source (in parallel, objects cached under csrc/_obj), then one link.  Safe when several processes get here
+    at once (the ranks of a torchrun launch on a box whose copy of the tree looks stale): one builds under a file lock, the
+    others wait and find the library fresh; the library itself appears atomically (link to a temporary name, then rename)."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    try:
+        lock = open(os.path.join(HERE, ".build.lock"), "w")
+    except OSError:
+        lock = None                                     # read-only tree: nothing to serialise against, the build below fails loudly
+    try:
+        if lock is not None:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():             # another process built it while this one waited
+            return LIB
+        return _build_locked(force, verbose)
+    finally:
+        if lock is not None:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+            lock.close()
+
+
+def _build_locked(force, verbose):
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = os.path.join(CSRC, "_obj")
@@ -65,11 +85,15 @@ def build(force=False, verbose=False):
     if verbose:
         for _, log in res:
             print(log)
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB] + [o for o, _ in res] + ["-lpthread"]
+    tmp = LIB + ".tmp%d" % os.getpid()
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", tmp] + [o for o, _ in res] + ["-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed linking libflacb200.so")
+    os.replace(tmp, LIB)
     return LIB
 
 
