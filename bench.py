@@ -255,7 +255,7 @@ def main():
     def step_device():
         eng.encode_device(cfg, d_pcm.data_ptr(), d_pcm.numel(), stream_off, stream_samples)
 
-    for _ in range(args.warmup):
+    for _ in range(max(1, args.warmup)):           # (at least one: the first batch also sizes the result buffers below)
         step_device()
     torch.cuda.synchronize()
     res = eng.result()
