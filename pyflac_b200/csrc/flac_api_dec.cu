@@ -69,6 +69,8 @@ struct DecImpl {
     FLAC__StreamDecoderLengthCallback length_cb = nullptr; FLAC__StreamDecoderEofCallback eof_cb = nullptr;
     void* client = nullptr;
     uint32_t meta_calls_pending = 0;      // libFLAC's process_single reads ONE metadata block per call: calls still owed for the blocks parsed at once
+    bool meta_trunc_seen = false;         // the input ended inside the metadata blocks ...
+    uint32_t meta_trunc_owed = 0;         // ... and this many process_single calls still succeed (one per block that was complete)
     uint64_t first_frame_offset = 0;      // byte offset of the first audio frame (behind the metadata blocks)
     // MD5 of the delivered samples against STREAMINFO's (stream_decoder.h: set_md5_checking; off once a seek or flush happened)
     bool md5_active = false; fb::Md5 md5; uint8_t stored_md5[16] = {0}; std::vector<int32_t> md5_tmp;
@@ -103,45 +105,72 @@ bool pull(FLAC__StreamDecoder* d, size_t want) {
     return true;
 }
 
-// parse "fLaC" + metadata blocks once enough bytes are buffered. returns 1 done, 0 need more, -1 fatal
+// STREAMINFO (34 bytes at q) into the decoder's fields and, if there is one, the metadata callback
+void take_streaminfo(FLAC__StreamDecoder* d, const uint8_t* q, uint32_t len, bool last) {
+    DecImpl* m = D(d);
+    m->blocksize = (uint32_t)q[2] << 8 | q[3]; m->min_blocksize = (uint32_t)q[0] << 8 | q[1];
+    m->sample_rate = (uint32_t)q[10] << 12 | (uint32_t)q[11] << 4 | (q[12] >> 4);
+    m->channels = ((q[12] >> 1) & 7) + 1;
+    m->bps = (((uint32_t)q[12] & 1) << 4 | (q[13] >> 4)) + 1;
+    m->total_samples = ((uint64_t)(q[13] & 0xF) << 32) | (uint64_t)q[14] << 24 | (uint64_t)q[15] << 16 | (uint64_t)q[16] << 8 | q[17];
+    memcpy(m->stored_md5, q + 18, 16);
+    { bool any = false; for (int i = 0; i < 16; i++) any |= q[18 + i] != 0; if (!any) m->md5_active = false; }   // an unset MD5 is not checked
+    if (m->meta_cb) {
+        FLAC__StreamMetadata md; memset(&md, 0, sizeof md);
+        md.type = 0; md.is_last = last; md.length = len;
+        md.data.stream_info.min_blocksize = (uint32_t)q[0] << 8 | q[1]; md.data.stream_info.max_blocksize = m->blocksize;
+        md.data.stream_info.min_framesize = (uint32_t)q[4] << 16 | (uint32_t)q[5] << 8 | q[6];
+        md.data.stream_info.max_framesize = (uint32_t)q[7] << 16 | (uint32_t)q[8] << 8 | q[9];
+        md.data.stream_info.sample_rate = m->sample_rate; md.data.stream_info.channels = m->channels;
+        md.data.stream_info.bits_per_sample = m->bps; md.data.stream_info.total_samples = m->total_samples;
+        memcpy(md.data.stream_info.md5sum, q + 18, 16);
+        m->meta_cb(d, &md, m->client);
+    }
+}
+
+// parse "fLaC" + metadata blocks once ALL of them are buffered.  returns 1 done, 0 need more, -1 fatal, -2 the input ended inside
+// the metadata (libFLAC reads block by block: the blocks that were complete are read -- STREAMINFO reaches the metadata callback,
+// one process_single succeeds per block -- and the call that meets the end returns false in END_OF_STREAM; step() plays that out)
 int parse_metadata(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
-    if (m->in.size() < 4) return m->eof ? -1 : 0;
+    auto truncated = [&](uint32_t complete_blocks) {
+        if (!m->meta_trunc_seen) {
+            m->meta_trunc_seen = true; m->meta_trunc_owed = complete_blocks;
+            if (complete_blocks) {                                      // (only reached with "fLaC" and a complete first block in place)
+                const uint8_t* p = m->in.data() + 4;
+                const uint32_t len = (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+                if ((p[0] & 0x7f) == 0 && len >= 34) take_streaminfo(d, p + 4, len, false);
+            }
+        }
+        return -2;
+    };
+    if (m->in.size() < 4) return m->eof ? truncated(0) : 0;
     if (memcmp(m->in.data(), "fLaC", 4) != 0) {
         // libFLAC would hunt for a frame sync in arbitrary data and report LOST_SYNC; without STREAMINFO there is nothing
         // this build can decode (pyFLAC's tests expect the error, tests/test_decoder.py:59-66)
         report(d, ERR_LOST_SYNC);
         return -1;
     }
+    // first pass, no side effects: wait until every metadata block is buffered.  A block can be larger than one input slice
+    // (cover art, a long PADDING) and take several pulls; the blocks are parsed -- and STREAMINFO handed to the metadata
+    // callback -- once, when all of them are here
+    {
+        uint32_t complete = 0;
+        for (size_t p0 = 4;;) {
+            if (p0 + 4 > m->in.size()) return m->eof ? truncated(complete) : 0;
+            const uint8_t* p = m->in.data() + p0;
+            const size_t len = (size_t)p[1] << 16 | (size_t)p[2] << 8 | p[3];
+            if (p0 + 4 + len > m->in.size()) return m->eof ? truncated(complete) : 0;
+            p0 += 4 + len; complete++;
+            if (p[0] >> 7) break;
+        }
+    }
     size_t pos = 4; bool last = false, have_si = false; uint32_t nblocks = 0;
     while (!last) {
-        if (pos + 4 > m->in.size()) return m->eof ? -1 : 0;
         const uint8_t* p = m->in.data() + pos;
         const uint32_t type = p[0] & 0x7f, len = (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
         last = (p[0] >> 7) != 0;
-        if (pos + 4 + len > m->in.size()) return m->eof ? -1 : 0;
-        if (type == 0 && len >= 34) {
-            const uint8_t* q = p + 4;
-            m->blocksize = (uint32_t)q[2] << 8 | q[3]; m->min_blocksize = (uint32_t)q[0] << 8 | q[1];
-            m->sample_rate = (uint32_t)q[10] << 12 | (uint32_t)q[11] << 4 | (q[12] >> 4);
-            m->channels = ((q[12] >> 1) & 7) + 1;
-            m->bps = (((uint32_t)q[12] & 1) << 4 | (q[13] >> 4)) + 1;
-            m->total_samples = ((uint64_t)(q[13] & 0xF) << 32) | (uint64_t)q[14] << 24 | (uint64_t)q[15] << 16 | (uint64_t)q[16] << 8 | q[17];
-            have_si = true;
-            memcpy(m->stored_md5, q + 18, 16);
-            { bool any = false; for (int i = 0; i < 16; i++) any |= q[18 + i] != 0; if (!any) m->md5_active = false; }   // an unset MD5 is not checked
-            if (m->meta_cb) {
-                FLAC__StreamMetadata md; memset(&md, 0, sizeof md);
-                md.type = 0; md.is_last = last; md.length = len;
-                md.data.stream_info.min_blocksize = (uint32_t)q[0] << 8 | q[1]; md.data.stream_info.max_blocksize = m->blocksize;
-                md.data.stream_info.min_framesize = (uint32_t)q[4] << 16 | (uint32_t)q[5] << 8 | q[6];
-                md.data.stream_info.max_framesize = (uint32_t)q[7] << 16 | (uint32_t)q[8] << 8 | q[9];
-                md.data.stream_info.sample_rate = m->sample_rate; md.data.stream_info.channels = m->channels;
-                md.data.stream_info.bits_per_sample = m->bps; md.data.stream_info.total_samples = m->total_samples;
-                memcpy(md.data.stream_info.md5sum, q + 18, 16);
-                m->meta_cb(d, &md, m->client);
-            }
-        }
+        if (type == 0 && len >= 34) { take_streaminfo(d, p + 4, len, last); have_si = true; }
         pos += 4 + len; nblocks++;
     }
     if (!have_si) { report(d, ERR_BAD_METADATA); return -1; }
@@ -267,6 +296,10 @@ int step(FLAC__StreamDecoder* d, bool until_end) {
         if (!m->metadata_done) {
             const int r = parse_metadata(d);
             if (r == 1) return 1;
+            if (r == -2) {                                               // the input ended inside the metadata (see parse_metadata)
+                if (!until_end && m->meta_trunc_owed) { m->meta_trunc_owed--; m->state = DS_READ_METADATA; return 1; }
+                m->meta_trunc_owed = 0; m->state = DS_END_OF_STREAM; return -1;
+            }
             if (r < 0) { m->state = m->eof ? DS_END_OF_STREAM : DS_ABORTED; return m->eof ? 0 : -1; }
             if (!pull(d, kSlice)) return -1;
             continue;
@@ -319,6 +352,7 @@ static int init_common(FLAC__StreamDecoder* d) {
     m->in.clear(); m->eof = false; m->metadata_done = false; m->ready.clear(); m->frame_index = 0; m->bytes_consumed = 0;
     m->sample_rate = m->channels = m->bps = m->blocksize = 0; m->total_samples = 0; m->min_blocksize = 0;
     m->have_last = false; m->next_sample = 0; m->last_blocksize = 0; m->first_frame_offset = 0; m->meta_calls_pending = 0;
+    m->meta_trunc_seen = false; m->meta_trunc_owed = 0;
     m->md5_active = m->md5_checking != 0; m->md5.init(); memset(m->stored_md5, 0, 16);
     {
         std::lock_guard<std::mutex> lk(g_dec_mu);
@@ -407,6 +441,7 @@ FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) {
     if (m->file) { if (m->file == stdin) return 0; if (fseeko(m->file, 0, SEEK_SET) != 0) return 0; }
     else if (m->seek_cb && m->seek_cb(d, 0, m->client) == 1) return 0;          // seekable and the seek fails: reset fails
     m->metadata_done = false; m->eof = false; m->frame_index = 0; m->bytes_consumed = 0; m->next_sample = 0; m->last_blocksize = 0;
+    m->meta_trunc_seen = false; m->meta_trunc_owed = 0;
     m->md5_active = m->md5_checking != 0; m->md5.init();
     m->state = DS_SEARCH_FOR_METADATA;
     return 1;

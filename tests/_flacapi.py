@@ -192,11 +192,13 @@ DEC_LENGTH_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void
 DEC_EOF_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
 
 
-def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, path=None):
+def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, path=None, meta=False, read_chunk=None):
     """A StreamDecoder session driven by a script, over seekable callbacks (or a file when `path` is given).
     ops: ('seek', sample) | ('single', n) | ('end',) | ('flush',) | ('reset',) | ('meta',).
     Returns dict(events=[...], finish=bool): events are ('w', number_type, sample_number, blocksize, crc32 of the samples),
-    ('e', status) and ('ret', op, return value, decoder state) in the order they happened."""
+    ('e', status) and ('ret', op, return value, decoder state) in the order they happened; with meta=True a metadata callback is
+    registered and logs ('m', type, is_last, length, sample_rate, channels, bits_per_sample, total_samples).  read_chunk caps what
+    one read callback hands over (None: as much as is asked for)."""
     import zlib
     for n, at, rt in [("new", [], C.c_void_p), ("delete", [C.c_void_p], None), ("finish", [C.c_void_p], C.c_int),
                       ("get_state", [C.c_void_p], C.c_int), ("process_until_end_of_stream", [C.c_void_p], C.c_int),
@@ -215,7 +217,7 @@ def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, pat
     events = []
 
     def r(dec, buf, pbytes, cd):
-        k = min(pbytes[0], len(data) - pos[0])
+        k = min(pbytes[0], len(data) - pos[0], read_chunk or (1 << 62))
         if k == 0:
             pbytes[0] = 0
             return 1
@@ -223,6 +225,13 @@ def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, pat
         pos[0] += k
         pbytes[0] = k
         return 0
+
+    def mcb(dec, md, cd):
+        v = C.cast(md, C.POINTER(StreamInfoView)).contents
+        if v.type == 0:
+            events.append(('m', 0, int(v.is_last), int(v.length), int(v.sample_rate), int(v.channels), int(v.bits_per_sample), int(v.total_samples)))
+        else:
+            events.append(('m', int(v.type), int(v.is_last), int(v.length)))
 
     def sk(dec, off, cd):
         pos[0] = min(int(off), len(data))
@@ -251,16 +260,18 @@ def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, pat
         events.append(('e', int(status)))
 
     cbs = (DEC_READ_CB(r), DEC_SEEK_CB(sk), DEC_TELL_CB(tl), DEC_LENGTH_CB(ln), DEC_EOF_CB(ef), DEC_WRITE_CB(w), DEC_ERROR_CB(e))
+    mcb_c = META_CB(mcb)
+    mptr = C.cast(mcb_c, C.c_void_p) if meta else None
     null = lambda T: C.cast(None, T)  # noqa: E731
     d = L.FLAC__stream_decoder_new()
     L.FLAC__stream_decoder_set_md5_checking(d, int(md5_checking))
     if path is not None:
-        st = L.FLAC__stream_decoder_init_file(d, path.encode(), cbs[5], None, cbs[6], None)
+        st = L.FLAC__stream_decoder_init_file(d, path.encode(), cbs[5], mptr, cbs[6], None)
     elif seekable:
-        st = L.FLAC__stream_decoder_init_stream(d, cbs[0], cbs[1], cbs[2], cbs[3], cbs[4], cbs[5], None, cbs[6], None)
+        st = L.FLAC__stream_decoder_init_stream(d, cbs[0], cbs[1], cbs[2], cbs[3], cbs[4], cbs[5], mptr, cbs[6], None)
     else:
         st = L.FLAC__stream_decoder_init_stream(d, cbs[0], null(DEC_SEEK_CB), null(DEC_TELL_CB), null(DEC_LENGTH_CB), null(DEC_EOF_CB),
-                                                cbs[5], None, cbs[6], None)
+                                                cbs[5], mptr, cbs[6], None)
     res = dict(init_status=st, events=events)
     if st == 0:
         for op in ops:

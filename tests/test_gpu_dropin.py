@@ -276,6 +276,32 @@ def test_decoder_md5_checking_matches_libflac(ours, ref, checkers):
     assert scripted_decode_session(ours, flac, [('end',)], md5_checking=True)["finish"] is True
 
 
+def test_decoder_metadata_larger_than_one_read(ours, ref, checkers):
+    """A metadata block larger than one input slice (cover art, long PADDING: here 100 B ... 3 MB of PADDING behind STREAMINFO): the
+    metadata callback sees STREAMINFO once, one process_single per block, then the frames -- the same event log as libFLAC whatever
+    the read callback hands over per call.  (The metadata part of this log is also compared on the CPU by tools/host_logic_check.sh.)"""
+    from _flacapi import scripted_decode_session
+    x = music_like(4096 * 3 + 77, 2, 44100, 16, seed=21)
+    data = checkers.ref_encode(x, 44100, 16, 5, 0)
+    assert data[:4] == b"fLaC" and data[4] == 0 and data[5:8] == (34).to_bytes(3, "big")      # STREAMINFO first and not the last block
+    for padlen in (100, 70000, 3000000):
+        big = data[:42] + bytes([1]) + padlen.to_bytes(3, "big") + bytes(padlen) + data[42:]
+        for ops in ([('single', 1)] * 5 + [('end',)], [('meta',), ('end',)], [('end',)]):
+            for rc in (8192, None):
+                a = scripted_decode_session(ours, big, ops, meta=True, seekable=False, read_chunk=rc, md5_checking=True)
+                b = scripted_decode_session(ref, big, ops, meta=True, seekable=False, read_chunk=rc, md5_checking=True)
+                assert a["events"] == b["events"], (padlen, ops, rc)
+                assert a["finish"] is True and b["finish"] is True
+                assert sum(1 for e in a["events"] if e[0] == 'm') == 1
+    # the input ends inside the metadata: the complete blocks are read (callback, one process_single each), the call that meets the
+    # end returns false in END_OF_STREAM
+    for cut in (0, 3, 20, 42, 45, 60):
+        for ops in ([('single', 1)] * 4, [('meta',)], [('end',)], [('single', 1), ('end',)]):
+            a = scripted_decode_session(ours, data[:cut], ops, meta=True, seekable=False)
+            b = scripted_decode_session(ref, data[:cut], ops, meta=True, seekable=False)
+            assert a["events"] == b["events"], (cut, ops)
+
+
 TUNINGS = [
     [("max_lpc_order", 4)], [("max_lpc_order", 11)], [("max_lpc_order", 1)], [("max_lpc_order", 0)],
     [("max_residual_partition_order", 2)], [("max_residual_partition_order", 0)], [("max_residual_partition_order", 6)],
