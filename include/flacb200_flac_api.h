@@ -49,11 +49,60 @@ typedef struct {
     FLAC__uint64 total_samples;
     FLAC__byte md5sum[16];
 } FLAC__StreamMetadata_StreamInfo;
+/* builder/decoder.py:256-349 -- the other block types, as the decoder's metadata callback hands them over once
+ * FLAC__stream_decoder_set_metadata_respond*() asked for them (the encoder only ever delivers STREAMINFO).  Pointers inside a
+ * block are valid for the duration of the callback. */
+typedef struct { int dummy; } FLAC__StreamMetadata_Padding;
+typedef struct { FLAC__byte id[4]; FLAC__byte *data; } FLAC__StreamMetadata_Application;
+typedef struct { FLAC__uint64 sample_number, stream_offset; uint32_t frame_samples; } FLAC__StreamMetadata_SeekPoint;
+typedef struct { uint32_t num_points; FLAC__StreamMetadata_SeekPoint *points; } FLAC__StreamMetadata_SeekTable;
+typedef struct { uint32_t length; FLAC__byte *entry; } FLAC__StreamMetadata_VorbisComment_Entry;
 typedef struct {
-    int type;                 /* FLAC__MetadataType: 0 = STREAMINFO */
+    FLAC__StreamMetadata_VorbisComment_Entry vendor_string;
+    uint32_t num_comments;
+    FLAC__StreamMetadata_VorbisComment_Entry *comments;
+} FLAC__StreamMetadata_VorbisComment;
+typedef struct { FLAC__uint64 offset; FLAC__byte number; } FLAC__StreamMetadata_CueSheet_Index;
+typedef struct {
+    FLAC__uint64 offset;
+    FLAC__byte number;
+    char isrc[13];
+    uint32_t type : 1;
+    uint32_t pre_emphasis : 1;
+    FLAC__byte num_indices;
+    FLAC__StreamMetadata_CueSheet_Index *indices;
+} FLAC__StreamMetadata_CueSheet_Track;
+typedef struct {
+    char media_catalog_number[129];
+    FLAC__uint64 lead_in;
+    FLAC__bool is_cd;
+    uint32_t num_tracks;
+    FLAC__StreamMetadata_CueSheet_Track *tracks;
+} FLAC__StreamMetadata_CueSheet;
+typedef struct {
+    int type;                 /* FLAC__StreamMetadata_Picture_Type */
+    char *mime_type;
+    FLAC__byte *description;
+    uint32_t width, height, depth, colors;
+    uint32_t data_length;
+    FLAC__byte *data;
+} FLAC__StreamMetadata_Picture;
+typedef struct { FLAC__byte *data; } FLAC__StreamMetadata_Unknown;
+typedef struct {
+    int type;                 /* FLAC__MetadataType: 0 STREAMINFO, 1 PADDING, 2 APPLICATION, 3 SEEKTABLE, 4 VORBIS_COMMENT, 5 CUESHEET, 6 PICTURE */
     FLAC__bool is_last;
     uint32_t length;
-    union { FLAC__StreamMetadata_StreamInfo stream_info; uint64_t pad_[24]; } data;
+    union {
+        FLAC__StreamMetadata_StreamInfo stream_info;
+        FLAC__StreamMetadata_Padding padding;
+        FLAC__StreamMetadata_Application application;
+        FLAC__StreamMetadata_SeekTable seek_table;
+        FLAC__StreamMetadata_VorbisComment vorbis_comment;
+        FLAC__StreamMetadata_CueSheet cue_sheet;
+        FLAC__StreamMetadata_Picture picture;
+        FLAC__StreamMetadata_Unknown unknown;
+        uint64_t pad_[24];
+    } data;
 } FLAC__StreamMetadata;
 
 /* builder/decoder.py:146-231 -- decode write-callback payload.  pyFLAC reads header.{blocksize,sample_rate,
@@ -161,6 +210,7 @@ extern const char *const FLAC__StreamDecoderErrorStatusString[];  /* pyflac/deco
 FLAC__StreamDecoder *FLAC__stream_decoder_new(void);
 void FLAC__stream_decoder_delete(FLAC__StreamDecoder *decoder);
 FLAC__bool FLAC__stream_decoder_set_md5_checking(FLAC__StreamDecoder *decoder, FLAC__bool value);
+/* builder/decoder.py:392-397 -- which metadata blocks reach the metadata callback (default: STREAMINFO only), as libFLAC's filter */
 FLAC__bool FLAC__stream_decoder_set_metadata_respond(FLAC__StreamDecoder *decoder, int type);
 FLAC__bool FLAC__stream_decoder_set_metadata_respond_application(FLAC__StreamDecoder *decoder, const FLAC__byte id[4]);
 FLAC__bool FLAC__stream_decoder_set_metadata_respond_all(FLAC__StreamDecoder *decoder);

@@ -68,9 +68,18 @@ struct DecImpl {
     FLAC__StreamDecoderSeekCallback seek_cb = nullptr; FLAC__StreamDecoderTellCallback tell_cb = nullptr;
     FLAC__StreamDecoderLengthCallback length_cb = nullptr; FLAC__StreamDecoderEofCallback eof_cb = nullptr;
     void* client = nullptr;
-    uint32_t meta_calls_pending = 0;      // libFLAC's process_single reads ONE metadata block per call: calls still owed for the blocks parsed at once
-    bool meta_trunc_seen = false;         // the input ended inside the metadata blocks ...
-    uint32_t meta_trunc_owed = 0;         // ... and this many process_single calls still succeed (one per block that was complete)
+    // Metadata: parse_metadata() waits until all blocks are buffered and lists them; they are then read one per process_single, as
+    // libFLAC does (the block's callback fires inside the call that reads it).  meta_truncated: the input ended inside the
+    // metadata -- the complete blocks are read, the call that meets the end fails in END_OF_STREAM.
+    struct MetaBlock { uint32_t type, len; bool last; size_t off; };     // off: first data byte in meta_blob
+    std::vector<uint8_t> meta_blob; std::vector<MetaBlock> meta_blocks; size_t meta_next = 0;
+    bool meta_parsed = false, meta_truncated = false;
+    bool is_seeking = false;              // metadata read on behalf of a seek is not reported (stream_decoder.c: is_seeking)
+    // FLAC__stream_decoder_set_metadata_respond* / _ignore*: one switch per block type (default: STREAMINFO only) and, for
+    // APPLICATION blocks, the ids that are exceptions to their type's switch
+    bool meta_filter[128]; std::vector<uint32_t> meta_ids;
+    void filter_defaults() { for (bool& f : meta_filter) f = false; meta_filter[0] = true; meta_ids.clear(); }
+    DecImpl() { filter_defaults(); }
     uint64_t first_frame_offset = 0;      // byte offset of the first audio frame (behind the metadata blocks)
     // MD5 of the delivered samples against STREAMINFO's (stream_decoder.h: set_md5_checking; off once a seek or flush happened)
     bool md5_active = false; fb::Md5 md5; uint8_t stored_md5[16] = {0}; std::vector<int32_t> md5_tmp;
@@ -105,7 +114,7 @@ bool pull(FLAC__StreamDecoder* d, size_t want) {
     return true;
 }
 
-// STREAMINFO (34 bytes at q) into the decoder's fields and, if there is one, the metadata callback
+// STREAMINFO (34 bytes at q) into the decoder's fields and, if it is asked for, the metadata callback
 void take_streaminfo(FLAC__StreamDecoder* d, const uint8_t* q, uint32_t len, bool last) {
     DecImpl* m = D(d);
     m->blocksize = (uint32_t)q[2] << 8 | q[3]; m->min_blocksize = (uint32_t)q[0] << 8 | q[1];
@@ -115,7 +124,7 @@ void take_streaminfo(FLAC__StreamDecoder* d, const uint8_t* q, uint32_t len, boo
     m->total_samples = ((uint64_t)(q[13] & 0xF) << 32) | (uint64_t)q[14] << 24 | (uint64_t)q[15] << 16 | (uint64_t)q[16] << 8 | q[17];
     memcpy(m->stored_md5, q + 18, 16);
     { bool any = false; for (int i = 0; i < 16; i++) any |= q[18 + i] != 0; if (!any) m->md5_active = false; }   // an unset MD5 is not checked
-    if (m->meta_cb) {
+    if (m->meta_cb && m->meta_filter[0] && !m->is_seeking) {
         FLAC__StreamMetadata md; memset(&md, 0, sizeof md);
         md.type = 0; md.is_last = last; md.length = len;
         md.data.stream_info.min_blocksize = (uint32_t)q[0] << 8 | q[1]; md.data.stream_info.max_blocksize = m->blocksize;
@@ -128,58 +137,159 @@ void take_streaminfo(FLAC__StreamDecoder* d, const uint8_t* q, uint32_t len, boo
     }
 }
 
-// parse "fLaC" + metadata blocks once ALL of them are buffered.  returns 1 done, 0 need more, -1 fatal, -2 the input ended inside
-// the metadata (libFLAC reads block by block: the blocks that were complete are read -- STREAMINFO reaches the metadata callback,
-// one process_single succeeds per block -- and the call that meets the end returns false in END_OF_STREAM; step() plays that out)
+inline uint32_t be32(const uint8_t* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
+inline uint64_t be64(const uint8_t* p) { return (uint64_t)be32(p) << 32 | be32(p + 4); }
+inline uint32_t le32(const uint8_t* p) { return (uint32_t)p[3] << 24 | (uint32_t)p[2] << 16 | (uint32_t)p[1] << 8 | p[0]; }
+
+// One metadata block to the metadata callback if the filter asks for it (up: read_metadata_, stream_decoder.c; layouts:
+// builder/decoder.py:256-365).  Everything the block points to lives in the locals below for the duration of the callback.
+// Returns 0 (reported, or not asked for) or what libFLAC 1.4.3 was seen to do with a block it cannot use (pinned on the binary by
+// tools/host_logic_check.py): kMetaBad -- content that does not fit the block's length: BAD_METADATA is reported, metadata reading
+// ends and the frame search starts inside the block; kMetaRefused -- a VORBIS_COMMENT that claims more than 100 000 comments: the
+// call fails, the next one reads the next block; kMetaFatal -- an APPLICATION block shorter than its id: MEMORY_ALLOCATION_ERROR;
+// kMetaStuck -- a SEEKTABLE whose length is not a whole number of points: this and every later call fail.
+enum { kMetaOk = 0, kMetaBad = 1, kMetaRefused = 2, kMetaFatal = 3, kMetaStuck = 4 };
+int deliver_meta_block(FLAC__StreamDecoder* d, const DecImpl::MetaBlock& b) {
+    DecImpl* m = D(d);
+    const uint8_t* q = m->meta_blob.data() + b.off;
+    if (b.type == 0) { if (b.len >= 34) take_streaminfo(d, q, b.len, b.last); return kMetaOk; }
+    bool want = b.type < 128 && m->meta_filter[b.type];
+    if (b.type == 2) {                                                  // APPLICATION: the listed ids are the exceptions
+        if (b.len < 4) return kMetaFatal;
+        const uint32_t id = be32(q);
+        if (!m->meta_ids.empty()) for (uint32_t v : m->meta_ids) if (v == id) { want = !want; break; }
+    }
+    if (b.type == 3 && b.len % 18 != 0) return kMetaStuck;               // (the seek table is read whether or not it is asked for)
+    if (!want) return kMetaOk;                                          // blocks nobody asked for are skipped unread
+    if (b.type == 3 && b.len == 0) return kMetaOk;                      // an empty SEEKTABLE is not reported
+    FLAC__StreamMetadata md; memset(&md, 0, sizeof md);
+    md.type = (int)b.type; md.is_last = b.last; md.length = b.len;
+    const uint8_t* e = q + b.len;
+    std::vector<uint8_t> bytes;                                         // NUL-terminated copies of the block's strings, packed
+    std::vector<size_t> str_off;                                        // ... and where each starts (pointers are taken at the end)
+    auto keep = [&](const uint8_t* p, size_t n) { str_off.push_back(bytes.size()); bytes.insert(bytes.end(), p, p + n); bytes.push_back(0); };
+    std::vector<FLAC__StreamMetadata_SeekPoint> points;
+    std::vector<FLAC__StreamMetadata_VorbisComment_Entry> comments;
+    std::vector<FLAC__StreamMetadata_CueSheet_Track> tracks;
+    std::vector<std::vector<FLAC__StreamMetadata_CueSheet_Index>> indices;
+    switch (b.type) {
+    case 1: break;                                                      // PADDING: nothing but its length
+    case 2:
+        memcpy(md.data.application.id, q, 4);
+        md.data.application.data = b.len > 4 ? const_cast<FLAC__byte*>(q + 4) : nullptr;
+        break;
+    case 3: {
+        const uint32_t n = b.len / 18;
+        points.resize(n);
+        for (uint32_t i = 0; i < n; i++) { const uint8_t* p = q + 18 * (size_t)i; points[i].sample_number = be64(p); points[i].stream_offset = be64(p + 8); points[i].frame_samples = (uint32_t)p[16] << 8 | p[17]; }
+        md.data.seek_table.num_points = n; md.data.seek_table.points = n ? points.data() : nullptr;
+        break;
+    }
+    case 4: {
+        const uint8_t* p = q;
+        if (e - p < 8) return kMetaBad;
+        const uint32_t vl = le32(p); p += 4;
+        if ((size_t)(e - p) < (size_t)vl + 4) return kMetaBad;
+        keep(p, vl); p += vl;
+        uint32_t nc = le32(p); p += 4;
+        const uint32_t nc_said = nc;
+        if (nc > 100000) return kMetaRefused;
+        for (uint32_t i = 0; i < nc_said; i++) {
+            if (e - p < 4) { if (p != e) return kMetaBad; nc = i; break; }   // the block ends behind an entry, earlier than announced: the entries that are there count
+            const uint32_t cl = le32(p); p += 4;
+            if ((size_t)(e - p) < cl) return kMetaBad;
+            FLAC__StreamMetadata_VorbisComment_Entry c; c.length = cl; c.entry = nullptr; comments.push_back(c);
+            keep(p, cl); p += cl;
+        }
+        if (p != e) return kMetaBad;
+        md.data.vorbis_comment.vendor_string.length = vl; md.data.vorbis_comment.vendor_string.entry = bytes.data() + str_off[0];
+        for (uint32_t i = 0; i < nc; i++) comments[i].entry = bytes.data() + str_off[1 + i];
+        md.data.vorbis_comment.num_comments = nc; md.data.vorbis_comment.comments = nc ? comments.data() : nullptr;
+        break;
+    }
+    case 5: {
+        const uint8_t* p = q;
+        if (e - p < 128 + 8 + 259 + 1) return kMetaBad;
+        memcpy(md.data.cue_sheet.media_catalog_number, p, 128); md.data.cue_sheet.media_catalog_number[128] = 0; p += 128;
+        md.data.cue_sheet.lead_in = be64(p); p += 8;
+        md.data.cue_sheet.is_cd = p[0] >> 7; p += 259;
+        const uint32_t nt = *p++;
+        tracks.resize(nt); indices.resize(nt);
+        for (uint32_t t = 0; t < nt; t++) {
+            if (e - p < 8 + 1 + 12 + 14 + 1) return kMetaBad;
+            FLAC__StreamMetadata_CueSheet_Track& T = tracks[t]; memset(&T, 0, sizeof T);
+            T.offset = be64(p); p += 8; T.number = *p++;
+            memcpy(T.isrc, p, 12); T.isrc[12] = 0; p += 12;
+            T.type = p[0] >> 7; T.pre_emphasis = (p[0] >> 6) & 1; p += 14;
+            T.num_indices = *p++;
+            if ((size_t)(e - p) < (size_t)T.num_indices * 12) return kMetaBad;
+            indices[t].resize(T.num_indices);
+            for (uint32_t i = 0; i < T.num_indices; i++) { indices[t][i].offset = be64(p); indices[t][i].number = p[8]; p += 12; }
+            T.indices = T.num_indices ? indices[t].data() : nullptr;
+        }
+        if (p != e) return kMetaBad;
+        md.data.cue_sheet.num_tracks = nt; md.data.cue_sheet.tracks = nt ? tracks.data() : nullptr;
+        break;
+    }
+    case 6: {
+        const uint8_t* p = q;
+        if (e - p < 8) return kMetaBad;
+        md.data.picture.type = (int)be32(p); p += 4;
+        const uint32_t ml = be32(p); p += 4;
+        if ((size_t)(e - p) < (size_t)ml + 4) return kMetaBad;
+        keep(p, ml); p += ml;
+        const uint32_t dl = be32(p); p += 4;
+        if ((size_t)(e - p) < (size_t)dl + 20) return kMetaBad;
+        keep(p, dl); p += dl;
+        md.data.picture.width = be32(p); md.data.picture.height = be32(p + 4); md.data.picture.depth = be32(p + 8); md.data.picture.colors = be32(p + 12);
+        md.data.picture.data_length = be32(p + 16); p += 20;
+        if ((size_t)(e - p) != md.data.picture.data_length) return kMetaBad;
+        md.data.picture.data = md.data.picture.data_length ? const_cast<FLAC__byte*>(p) : nullptr;
+        md.data.picture.mime_type = reinterpret_cast<char*>(bytes.data() + str_off[0]); md.data.picture.description = bytes.data() + str_off[1];
+        break;
+    }
+    default:
+        md.data.unknown.data = b.len ? const_cast<FLAC__byte*>(q) : nullptr;
+        break;
+    }
+    if (m->meta_cb && !m->is_seeking) m->meta_cb(d, &md, m->client);
+    return kMetaOk;
+}
+
+// "fLaC" + metadata blocks: waits until ALL of them are buffered, then lists them in meta_blocks (a block can be larger than one
+// input slice -- cover art, a long PADDING -- and take several pulls; nothing is reported before all of them are here).
+// returns 1 listed, 0 need more input, -1 fatal.  When the input ends inside the metadata the complete blocks are listed and
+// meta_truncated is set.
 int parse_metadata(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
-    auto truncated = [&](uint32_t complete_blocks) {
-        if (!m->meta_trunc_seen) {
-            m->meta_trunc_seen = true; m->meta_trunc_owed = complete_blocks;
-            if (complete_blocks) {                                      // (only reached with "fLaC" and a complete first block in place)
-                const uint8_t* p = m->in.data() + 4;
-                const uint32_t len = (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
-                if ((p[0] & 0x7f) == 0 && len >= 34) take_streaminfo(d, p + 4, len, false);
-            }
-        }
-        return -2;
-    };
-    if (m->in.size() < 4) return m->eof ? truncated(0) : 0;
+    m->meta_blocks.clear(); m->meta_next = 0; m->meta_truncated = false;
+    if (m->in.size() < 4) { if (!m->eof) return 0; m->meta_truncated = true; m->meta_parsed = true; return 1; }
     if (memcmp(m->in.data(), "fLaC", 4) != 0) {
         // libFLAC would hunt for a frame sync in arbitrary data and report LOST_SYNC; without STREAMINFO there is nothing
         // this build can decode (pyFLAC's tests expect the error, tests/test_decoder.py:59-66)
         report(d, ERR_LOST_SYNC);
         return -1;
     }
-    // first pass, no side effects: wait until every metadata block is buffered.  A block can be larger than one input slice
-    // (cover art, a long PADDING) and take several pulls; the blocks are parsed -- and STREAMINFO handed to the metadata
-    // callback -- once, when all of them are here
-    {
-        uint32_t complete = 0;
-        for (size_t p0 = 4;;) {
-            if (p0 + 4 > m->in.size()) return m->eof ? truncated(complete) : 0;
-            const uint8_t* p = m->in.data() + p0;
-            const size_t len = (size_t)p[1] << 16 | (size_t)p[2] << 8 | p[3];
-            if (p0 + 4 + len > m->in.size()) return m->eof ? truncated(complete) : 0;
-            p0 += 4 + len; complete++;
-            if (p[0] >> 7) break;
-        }
-    }
-    size_t pos = 4; bool last = false, have_si = false; uint32_t nblocks = 0;
-    while (!last) {
+    size_t pos = 4; bool have_si = false;
+    for (;;) {
+        if (pos + 4 > m->in.size()) { if (!m->eof) return 0; m->meta_truncated = true; break; }
         const uint8_t* p = m->in.data() + pos;
-        const uint32_t type = p[0] & 0x7f, len = (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
-        last = (p[0] >> 7) != 0;
-        if (type == 0 && len >= 34) { take_streaminfo(d, p + 4, len, last); have_si = true; }
-        pos += 4 + len; nblocks++;
+        const uint32_t len = (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+        if (pos + 4 + (size_t)len > m->in.size()) { if (!m->eof) return 0; m->meta_truncated = true; break; }
+        const DecImpl::MetaBlock b = {(uint32_t)(p[0] & 0x7f), len, (p[0] >> 7) != 0, pos + 4};
+        m->meta_blocks.push_back(b);
+        have_si |= b.type == 0 && len >= 34;
+        pos += 4 + (size_t)len;
+        if (b.last) break;
     }
-    if (!have_si) { report(d, ERR_BAD_METADATA); return -1; }
-    m->in.erase(m->in.begin(), m->in.begin() + (long)pos);
-    m->bytes_consumed += pos;
-    m->first_frame_offset = m->bytes_consumed;
-    m->metadata_done = true;
-    m->meta_calls_pending = nblocks - 1;
-    m->state = m->meta_calls_pending ? DS_READ_METADATA : DS_SEARCH_FOR_FRAME_SYNC;
+    if (!m->meta_truncated && !have_si) { m->meta_blocks.clear(); report(d, ERR_BAD_METADATA); return -1; }
+    m->meta_blob.assign(m->in.begin(), m->in.begin() + (long)pos);
+    if (!m->meta_truncated) {
+        m->in.erase(m->in.begin(), m->in.begin() + (long)pos);
+        m->bytes_consumed += pos;
+        m->first_frame_offset = m->bytes_consumed;
+    }
+    m->meta_parsed = true;
     return 1;
 }
 
@@ -287,22 +397,40 @@ int step(FLAC__StreamDecoder* d, bool until_end) {
     const size_t kSlice = until_end ? (1u << 20) : (1u << 16);
     for (;;) {
         if (m->state == DS_ABORTED || m->state == DS_END_OF_STREAM) return m->state == DS_ABORTED ? -1 : 0;
-        if (m->meta_calls_pending) {                                     // one process_single per metadata block, as libFLAC
-            if (until_end) m->meta_calls_pending = 0; else m->meta_calls_pending--;
-            if (!m->meta_calls_pending) m->state = DS_SEARCH_FOR_FRAME_SYNC;
-            if (!until_end) return 1;
+        if (!m->ready.empty()) {
+            const bool was_error = m->ready.front().error >= 0;
+            if (!deliver_one(d)) return -1;
+            if (was_error && !until_end) continue;                       // an error callback does not end a process_single: it goes on to the next frame
+            return 1;
         }
-        if (!m->ready.empty()) return deliver_one(d) ? 1 : -1;
         if (!m->metadata_done) {
-            const int r = parse_metadata(d);
-            if (r == 1) return 1;
-            if (r == -2) {                                               // the input ended inside the metadata (see parse_metadata)
-                if (!until_end && m->meta_trunc_owed) { m->meta_trunc_owed--; m->state = DS_READ_METADATA; return 1; }
-                m->meta_trunc_owed = 0; m->state = DS_END_OF_STREAM; return -1;
+            if (!m->meta_parsed) {
+                const int r = parse_metadata(d);
+                if (r < 0) { m->state = m->eof ? DS_END_OF_STREAM : DS_ABORTED; return m->eof ? 0 : -1; }
+                if (r == 0) { if (!pull(d, kSlice)) return -1; continue; }
             }
-            if (r < 0) { m->state = m->eof ? DS_END_OF_STREAM : DS_ABORTED; return m->eof ? 0 : -1; }
-            if (!pull(d, kSlice)) return -1;
-            continue;
+            // one block per process_single, as libFLAC (all of them for the until-end calls)
+            if (m->meta_next < m->meta_blocks.size()) {
+                const DecImpl::MetaBlock b = m->meta_blocks[m->meta_next++];
+                const bool done = m->meta_next == m->meta_blocks.size() && !m->meta_truncated;
+                if (done) m->metadata_done = true;
+                m->state = done ? DS_SEARCH_FOR_FRAME_SYNC : DS_READ_METADATA;
+                const int rc = deliver_meta_block(d, b);
+                if (rc == kMetaBad) {
+                    report(d, ERR_BAD_METADATA);
+                    if (!m->meta_truncated) { m->meta_next = m->meta_blocks.size(); m->metadata_done = true; }
+                    m->state = DS_SEARCH_FOR_FRAME_SYNC;
+                    PendingFrame pf; pf.blocksize = 0; pf.error = ERR_LOST_SYNC; m->ready.push_back(std::move(pf));   // the rest of the metadata is junk in front of the first frame
+                    return -1;
+                }
+                if (rc == kMetaRefused) return -1;
+                if (rc == kMetaFatal) { m->state = DS_MEMORY_ALLOCATION_ERROR; return -1; }
+                if (rc == kMetaStuck) { m->meta_next--; m->metadata_done = false; m->state = DS_READ_METADATA; return -1; }
+                if (!until_end) return 1;
+                continue;
+            }
+            m->state = DS_END_OF_STREAM;                                // the input ended inside the metadata
+            return -1;
         }
         // need more frames: decode what is buffered once a slice (or the tail) is available
         if (!m->eof && m->in.size() < 16) { if (!pull(d, kSlice)) return -1; continue; }
@@ -329,12 +457,47 @@ void FLAC__stream_decoder_delete(FLAC__StreamDecoder* d) {
     delete reinterpret_cast<DHandle*>(d);
 }
 FLAC__bool FLAC__stream_decoder_set_md5_checking(FLAC__StreamDecoder* d, FLAC__bool v) { DecImpl* m = D(d); if (m->state != DS_UNINITIALIZED) return 0; m->md5_checking = v; return 1; }
-FLAC__bool FLAC__stream_decoder_set_metadata_respond(FLAC__StreamDecoder* d, int) { return D(d)->state == DS_UNINITIALIZED; }
-FLAC__bool FLAC__stream_decoder_set_metadata_respond_application(FLAC__StreamDecoder* d, const FLAC__byte*) { return D(d)->state == DS_UNINITIALIZED; }
-FLAC__bool FLAC__stream_decoder_set_metadata_respond_all(FLAC__StreamDecoder* d) { return D(d)->state == DS_UNINITIALIZED; }
-FLAC__bool FLAC__stream_decoder_set_metadata_ignore(FLAC__StreamDecoder* d, int) { return D(d)->state == DS_UNINITIALIZED; }
-FLAC__bool FLAC__stream_decoder_set_metadata_ignore_application(FLAC__StreamDecoder* d, const FLAC__byte*) { return D(d)->state == DS_UNINITIALIZED; }
-FLAC__bool FLAC__stream_decoder_set_metadata_ignore_all(FLAC__StreamDecoder* d) { return D(d)->state == DS_UNINITIALIZED; }
+// up: FLAC__stream_decoder_set_metadata_respond* / _ignore* (stream_decoder.h:847-948; builder/decoder.py:392-397): settable before
+// init only; naming the APPLICATION type as a whole forgets the listed ids; an id named while its type's switch already says the
+// same changes nothing
+FLAC__bool FLAC__stream_decoder_set_metadata_respond(FLAC__StreamDecoder* d, int type) {
+    DecImpl* m = D(d);
+    if (m->state != DS_UNINITIALIZED || type < 0 || type > 126) return 0;
+    m->meta_filter[type] = true; if (type == 2) m->meta_ids.clear();
+    return 1;
+}
+FLAC__bool FLAC__stream_decoder_set_metadata_respond_application(FLAC__StreamDecoder* d, const FLAC__byte* id) {
+    DecImpl* m = D(d);
+    if (m->state != DS_UNINITIALIZED || !id) return 0;
+    if (!m->meta_filter[2]) m->meta_ids.push_back(be32(id));
+    return 1;
+}
+FLAC__bool FLAC__stream_decoder_set_metadata_respond_all(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    if (m->state != DS_UNINITIALIZED) return 0;
+    for (bool& f : m->meta_filter) f = true;
+    m->meta_ids.clear();
+    return 1;
+}
+FLAC__bool FLAC__stream_decoder_set_metadata_ignore(FLAC__StreamDecoder* d, int type) {
+    DecImpl* m = D(d);
+    if (m->state != DS_UNINITIALIZED || type < 0 || type > 126) return 0;
+    m->meta_filter[type] = false; if (type == 2) m->meta_ids.clear();
+    return 1;
+}
+FLAC__bool FLAC__stream_decoder_set_metadata_ignore_application(FLAC__StreamDecoder* d, const FLAC__byte* id) {
+    DecImpl* m = D(d);
+    if (m->state != DS_UNINITIALIZED || !id) return 0;
+    if (m->meta_filter[2]) m->meta_ids.push_back(be32(id));
+    return 1;
+}
+FLAC__bool FLAC__stream_decoder_set_metadata_ignore_all(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    if (m->state != DS_UNINITIALIZED) return 0;
+    for (bool& f : m->meta_filter) f = false;
+    m->meta_ids.clear();
+    return 1;
+}
 int FLAC__stream_decoder_get_state(const FLAC__StreamDecoder* d) { return D(d)->state; }
 const char* FLAC__stream_decoder_get_resolved_state_string(const FLAC__StreamDecoder* d) { return FLAC__StreamDecoderStateString[D(d)->state]; }
 FLAC__bool FLAC__stream_decoder_get_md5_checking(const FLAC__StreamDecoder* d) { return D(d)->md5_checking; }
@@ -351,8 +514,8 @@ static int init_common(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
     m->in.clear(); m->eof = false; m->metadata_done = false; m->ready.clear(); m->frame_index = 0; m->bytes_consumed = 0;
     m->sample_rate = m->channels = m->bps = m->blocksize = 0; m->total_samples = 0; m->min_blocksize = 0;
-    m->have_last = false; m->next_sample = 0; m->last_blocksize = 0; m->first_frame_offset = 0; m->meta_calls_pending = 0;
-    m->meta_trunc_seen = false; m->meta_trunc_owed = 0;
+    m->have_last = false; m->next_sample = 0; m->last_blocksize = 0; m->first_frame_offset = 0;
+    m->meta_parsed = false; m->meta_truncated = false; m->meta_blocks.clear(); m->meta_blob.clear(); m->meta_next = 0; m->is_seeking = false;
     m->md5_active = m->md5_checking != 0; m->md5.init(); memset(m->stored_md5, 0, 16);
     {
         std::lock_guard<std::mutex> lk(g_dec_mu);
@@ -411,6 +574,7 @@ FLAC__bool FLAC__stream_decoder_finish(FLAC__StreamDecoder* d) {
     m->read_cb = nullptr; m->write_cb = nullptr; m->error_cb = nullptr; m->meta_cb = nullptr; m->client = nullptr;   // stream_decoder.h: finish resets the callbacks too
     m->seek_cb = nullptr; m->tell_cb = nullptr; m->length_cb = nullptr; m->eof_cb = nullptr;
     m->md5_checking = 0; m->md5_active = false;
+    m->filter_defaults();                                              // (finish puts every setting back to its default)
     m->state = DS_UNINITIALIZED;
     return md5_failed ? 0 : 1;
 }
@@ -428,7 +592,8 @@ static bool input_length(FLAC__StreamDecoder* d, uint64_t* len) {
 FLAC__bool FLAC__stream_decoder_flush(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
     if (m->state == DS_UNINITIALIZED) return 0;
-    m->in.clear(); m->ready.clear(); m->md5_active = false; m->have_last = false; m->meta_calls_pending = 0;
+    m->in.clear(); m->ready.clear(); m->md5_active = false; m->have_last = false;
+    if (m->meta_parsed && !m->meta_truncated) { m->meta_next = m->meta_blocks.size(); m->metadata_done = true; }   // blocks not read yet are skipped
     m->state = DS_SEARCH_FOR_FRAME_SYNC;
     return 1;
 }
@@ -441,7 +606,7 @@ FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) {
     if (m->file) { if (m->file == stdin) return 0; if (fseeko(m->file, 0, SEEK_SET) != 0) return 0; }
     else if (m->seek_cb && m->seek_cb(d, 0, m->client) == 1) return 0;          // seekable and the seek fails: reset fails
     m->metadata_done = false; m->eof = false; m->frame_index = 0; m->bytes_consumed = 0; m->next_sample = 0; m->last_blocksize = 0;
-    m->meta_trunc_seen = false; m->meta_trunc_owed = 0;
+    m->meta_parsed = false; m->meta_truncated = false; m->meta_blocks.clear(); m->meta_next = 0;
     m->md5_active = m->md5_checking != 0; m->md5.init();
     m->state = DS_SEARCH_FOR_METADATA;
     return 1;
@@ -449,20 +614,19 @@ FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) {
 
 FLAC__bool FLAC__stream_decoder_process_single(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
-    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED) return 0;
+    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
     if (m->state == DS_END_OF_STREAM) return 1;
     return step(d, false) >= 0;
 }
 FLAC__bool FLAC__stream_decoder_process_until_end_of_metadata(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
-    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED) return 0;
+    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
     while (!m->metadata_done && m->state != DS_END_OF_STREAM) if (step(d, false) < 0) return 0;
-    if (m->meta_calls_pending) { m->meta_calls_pending = 0; m->state = DS_SEARCH_FOR_FRAME_SYNC; }
     return 1;
 }
 FLAC__bool FLAC__stream_decoder_process_until_end_of_stream(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
-    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED) return 0;
+    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
     for (;;) {
         const int r = step(d, true);
         if (r < 0) return 0;
@@ -471,7 +635,7 @@ FLAC__bool FLAC__stream_decoder_process_until_end_of_stream(FLAC__StreamDecoder*
 }
 FLAC__bool FLAC__stream_decoder_skip_single_frame(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
-    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED) return 0;
+    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
     FLAC__StreamDecoderWriteCallback keep = m->write_cb;
     m->write_cb = [](const FLAC__StreamDecoder*, const FLAC__Frame*, const FLAC__int32* const*, void*) -> int { return 0; };
     const int r = step(d, false);
@@ -494,10 +658,12 @@ FLAC__bool FLAC__stream_decoder_seek_absolute(FLAC__StreamDecoder* d, FLAC__uint
     uint64_t length = 0;
     if (!input_length(d, &length)) return 0;
     if (!m->metadata_done) {
-        if (!FLAC__stream_decoder_process_until_end_of_metadata(d) || !m->metadata_done) return 0;
+        m->is_seeking = true;                                          // metadata read on behalf of a seek is not reported
+        const bool ok = FLAC__stream_decoder_process_until_end_of_metadata(d) && m->metadata_done;
+        m->is_seeking = false;
+        if (!ok) return 0;
         if (m->total_samples > 0 && sample >= m->total_samples) return 0;
     }
-    m->meta_calls_pending = 0;
     uint64_t lo = m->first_frame_offset, hi = length;                  // the target frame starts in [lo, hi)
     uint64_t lo_s = 0, hi_s = m->total_samples;                        // stream positions at those bytes (hi_s == 0: unknown)
     size_t window = 1u << 18;

@@ -31,6 +31,45 @@ class FrameHeaderView(C.Structure):
                 ("number", C.c_uint64), ("crc", C.c_uint8)]
 
 
+def metadata_view(md):
+    """What a metadata callback can see of a FLAC__StreamMetadata (builder/decoder.py:233-365), read through the C layout of
+    libFLAC 1.4.3 on LP64: ('m', type, is_last, length, ...content of the block...)."""
+    def u32(a): return C.c_uint32.from_address(a).value
+    def u64(a): return C.c_uint64.from_address(a).value
+    def ptr(a): return C.c_void_p.from_address(a).value or 0
+    def raw(a, n): return C.string_at(a, n) if a and n else b""
+    v = C.cast(md, C.POINTER(StreamInfoView)).contents
+    t, base = int(v.type), (md if isinstance(md, int) else C.cast(md, C.c_void_p).value) + 16       # the union starts at byte 16
+    head = ('m', t, int(v.is_last), int(v.length))
+    if t == 0:
+        return head + (int(v.sample_rate), int(v.channels), int(v.bits_per_sample), int(v.total_samples))
+    if t == 1:
+        return head
+    if t == 2:      # id[4], data*
+        return head + (raw(base, 4), raw(ptr(base + 8), v.length - 4))
+    if t == 3:      # num_points, points* -> {u64 sample_number, u64 stream_offset, u32 frame_samples} (24 bytes each)
+        n, pts = u32(base), ptr(base + 8)
+        return head + (tuple((u64(pts + 24 * i), u64(pts + 24 * i + 8), u32(pts + 24 * i + 16)) for i in range(n)),)
+    if t == 4:      # vendor {u32 length, entry*}, num_comments, comments* -> {u32 length, entry*} (16 bytes each); entries are NUL-terminated
+        def entry(a): return raw(ptr(a + 8), u32(a) + 1)
+        n, cs = u32(base + 16), ptr(base + 24)
+        return head + (entry(base), tuple(entry(cs + 16 * i) for i in range(n)))
+    if t == 5:      # char mcn[129], u64 lead_in @136, int is_cd @144, u32 num_tracks @148, tracks* @152
+        nt, ts = u32(base + 148), ptr(base + 152)
+        tracks = []
+        for i in range(nt):     # u64 offset, u8 number @8, char isrc[13] @9, type:1 pre_emphasis:1 @22, u8 num_indices @23, indices* @24 (32 bytes)
+            a = ts + 32 * i
+            ni, ix = raw(a + 23, 1)[0], ptr(a + 24)
+            tracks.append((u64(a), raw(a + 8, 1)[0], raw(a + 9, 13), raw(a + 22, 1)[0] & 3, ni,
+                           tuple((u64(ix + 16 * k), raw(ix + 16 * k + 8, 1)[0]) for k in range(ni))))
+        return head + (raw(base, 129), u64(base + 136), u32(base + 144), tuple(tracks))
+    if t == 6:      # int type, char* mime @8, byte* description @16, u32 width @24, height, depth, colors, data_length @40, data* @48
+        mime, desc = ptr(base + 8), ptr(base + 16)
+        return head + (u32(base), C.string_at(mime) if mime else None, C.string_at(desc) if desc else None,
+                       u32(base + 24), u32(base + 28), u32(base + 32), u32(base + 36), u32(base + 40), raw(ptr(base + 48), u32(base + 40)))
+    return head + (raw(ptr(base), v.length),)
+
+
 def _proto(L):
     L.FLAC__stream_encoder_new.restype = C.c_void_p
     for n in ["delete", "finish"]:
@@ -192,13 +231,14 @@ DEC_LENGTH_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void
 DEC_EOF_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
 
 
-def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, path=None, meta=False, read_chunk=None):
+def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, path=None, meta=False, read_chunk=None, respond=()):
     """A StreamDecoder session driven by a script, over seekable callbacks (or a file when `path` is given).
     ops: ('seek', sample) | ('single', n) | ('end',) | ('flush',) | ('reset',) | ('meta',).
     Returns dict(events=[...], finish=bool): events are ('w', number_type, sample_number, blocksize, crc32 of the samples),
     ('e', status) and ('ret', op, return value, decoder state) in the order they happened; with meta=True a metadata callback is
     registered and logs ('m', type, is_last, length, sample_rate, channels, bits_per_sample, total_samples).  read_chunk caps what
-    one read callback hands over (None: as much as is asked for)."""
+    one read callback hands over (None: as much as is asked for).  respond: filter calls made before init, in order, e.g.
+    ('respond_all',), ('ignore', 4), ('respond_application', b"abcd"); their return values are logged as ('set', name, value)."""
     import zlib
     for n, at, rt in [("new", [], C.c_void_p), ("delete", [C.c_void_p], None), ("finish", [C.c_void_p], C.c_int),
                       ("get_state", [C.c_void_p], C.c_int), ("process_until_end_of_stream", [C.c_void_p], C.c_int),
@@ -227,11 +267,7 @@ def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, pat
         return 0
 
     def mcb(dec, md, cd):
-        v = C.cast(md, C.POINTER(StreamInfoView)).contents
-        if v.type == 0:
-            events.append(('m', 0, int(v.is_last), int(v.length), int(v.sample_rate), int(v.channels), int(v.bits_per_sample), int(v.total_samples)))
-        else:
-            events.append(('m', int(v.type), int(v.is_last), int(v.length)))
+        events.append(metadata_view(md))
 
     def sk(dec, off, cd):
         pos[0] = min(int(off), len(data))
@@ -265,6 +301,19 @@ def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, pat
     null = lambda T: C.cast(None, T)  # noqa: E731
     d = L.FLAC__stream_decoder_new()
     L.FLAC__stream_decoder_set_md5_checking(d, int(md5_checking))
+    for call in respond:
+        f = getattr(L, "FLAC__stream_decoder_set_metadata_" + call[0])
+        f.restype = C.c_int
+        if len(call) == 1:
+            f.argtypes = [C.c_void_p]
+            rv = f(d)
+        elif isinstance(call[1], bytes):
+            f.argtypes = [C.c_void_p, C.c_char_p]
+            rv = f(d, call[1])
+        else:
+            f.argtypes = [C.c_void_p, C.c_int]
+            rv = f(d, call[1])
+        events.append(('set', call[0], int(rv)))
     if path is not None:
         st = L.FLAC__stream_decoder_init_file(d, path.encode(), cbs[5], mptr, cbs[6], None)
     elif seekable:

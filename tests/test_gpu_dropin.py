@@ -302,6 +302,35 @@ def test_decoder_metadata_larger_than_one_read(ours, ref, checkers):
             assert a["events"] == b["events"], (cut, ops)
 
 
+def test_decoder_metadata_callback_every_block_type(ours, ref, checkers):
+    """FLAC__stream_decoder_set_metadata_respond* / _ignore* (builder/decoder.py:392-397) and the metadata callback for every block type
+    pyFLAC's cdef declares (builder/decoder.py:233-365: PADDING, APPLICATION, SEEKTABLE, VORBIS_COMMENT, CUESHEET, PICTURE, unknown
+    types): the same blocks, field for field, in the same calls as libFLAC, then the same frames.  (The metadata part of these logs is
+    also compared on the CPU, with more filters and malformed blocks, by tools/host_logic_check.sh.)"""
+    from _flacapi import scripted_decode_session
+    from _metablocks import block, picture, rich_stream
+    x = music_like(4096 * 3 + 77, 2, 44100, 16, seed=21)
+    data = checkers.ref_encode(x, 44100, 16, 5, 0)
+    rich, nb = rich_stream(data)
+    filters = [(), (('respond_all',),), (('respond', 2), ('ignore_application', b"abcd")), (('respond_application', b"wxyz"), ('respond', 6)),
+               (('respond_all',), ('ignore', 0), ('ignore', 5)), (('ignore_all',), ('respond', 3), ('respond', 50))]
+    for resp in filters:
+        for ops in ([('single', nb + 2), ('end',)], [('meta',), ('end',)], [('end',)], [('seek', 5000), ('end',)]):
+            a = scripted_decode_session(ours, rich, ops, meta=True, seekable=True, read_chunk=8192, respond=resp, md5_checking=True)
+            b = scripted_decode_session(ref, rich, ops, meta=True, seekable=True, read_chunk=8192, respond=resp, md5_checking=True)
+            assert a["events"] == b["events"], (resp, ops)
+            assert a["finish"] == b["finish"]
+    kinds = {e[1] for e in scripted_decode_session(ours, rich, [('meta',)], meta=True, respond=(('respond_all',),))["events"] if e[0] == 'm'}
+    assert kinds == {0, 1, 2, 3, 4, 5, 6, 50}
+    # a block whose content does not fit its length: BAD_METADATA, metadata reading ends, the frame search starts inside the block
+    bad = data[:42] + block(6, picture(3, b"image/png", b"d", 1, 1, 8, 0, bytes(100))[:-10]) + data[42:]
+    for ops in ([('single', 4), ('end',)], [('meta',), ('end',)], [('end',), ('end',)]):
+        a = scripted_decode_session(ours, bad, ops, meta=True, seekable=False, respond=(('respond_all',),))
+        b = scripted_decode_session(ref, bad, ops, meta=True, seekable=False, respond=(('respond_all',),))
+        assert a["events"] == b["events"], ops
+        assert ('e', 4) in a["events"] and sum(1 for e in a["events"] if e[0] == 'w') == 4
+
+
 TUNINGS = [
     [("max_lpc_order", 4)], [("max_lpc_order", 11)], [("max_lpc_order", 1)], [("max_lpc_order", 0)],
     [("max_residual_partition_order", 2)], [("max_residual_partition_order", 0)], [("max_residual_partition_order", 6)],

@@ -31,6 +31,71 @@ for padlen in (None, 0, 100, 70000, 300000, 3000000):      # None: the stream as
                 if a["events"] != b["events"]:
                     bad += 1
                     print("DIFF", padlen, ops, seek, rc, "\n ours", a["events"][:8], "\n ref ", b["events"][:8])
+# every block type through the metadata callback under the respond / ignore filters (tests/_metablocks.py)
+from _metablocks import rich_stream, block, vorbis_comment, picture, cuesheet   # noqa: E402
+rich, nb = rich_stream(data)
+FILTERS = [(), (('respond_all',),), (('respond', 4),), (('respond', 2), ('ignore_application', b"abcd")), (('respond_application', b"wxyz"),),
+           (('respond_all',), ('ignore', 0)), (('respond_all',), ('ignore', 2), ('respond_application', b"abcd"), ('respond_application', b"none")),
+           (('ignore_all',), ('respond', 3), ('respond', 6), ('respond', 50)), (('respond_all',), ('ignore_application', b"wxyz"), ('respond', 2)),
+           (('respond', 127),), (('respond', 126), ('ignore', 1), ('respond', 5)), (('respond_all',), ('ignore_all',), ('respond', 1))]
+for resp in FILTERS:
+    for ops in ([('single', 1)] * nb, [('meta',)], [('single', 3), ('meta',)], [('meta',), ('reset',), ('single', 2)]):
+        for rc in (1000, None):
+            a = scripted_decode_session(ours, rich, ops, meta=True, seekable=True, read_chunk=rc, respond=resp)
+            b = scripted_decode_session(ref, rich, ops, meta=True, seekable=True, read_chunk=rc, respond=resp)
+            n += 1
+            if a["events"] != b["events"]:
+                bad += 1
+                for i, (ea, eb) in enumerate(zip(a["events"], b["events"])):
+                    if ea != eb:
+                        print("DIFF rich", resp, ops, rc, "event", i, "\n ours", str(ea)[:300], "\n ref ", str(eb)[:300])
+                        break
+                else:
+                    print("DIFF rich (length)", resp, ops, rc, len(a["events"]), len(b["events"]))
+# filter calls after init are refused; finish() puts the filter back to its default
+for L in (ours, ref):
+    pass
+# blocks whose content does not fit their length
+odd = {
+    "vorbis comment cut inside an entry": block(4, vorbis_comment(b"vendor", [b"A=1", b"B=2"])[:-2]),
+    "vorbis comment with a huge count": block(4, vorbis_comment(b"vendor", [])[:-4] + (1 << 30).to_bytes(4, "little")),
+    "vorbis comment of 4 bytes": block(4, bytes(4)),
+    "picture cut inside its data": block(6, picture(3, b"image/png", b"d", 1, 1, 8, 0, bytes(100))[:-10]),
+    "cuesheet cut inside a track": block(5, cuesheet(b"", 0, False, [(0, 1, b"", 0, 0, [(0, 1)])])[:-5]),
+    "seektable of 20 bytes": block(3, bytes(20)),
+    "application of 3 bytes": block(2, b"abc"),
+}
+import struct                                              # noqa: E402
+odd.update({
+    "vorbis vendor longer than the block": block(4, struct.pack("<I", 1000) + b"short" + struct.pack("<I", 0)),
+    "vorbis entry longer than the block": block(4, vorbis_comment(b"v", [b"A=1"])[:-3] + b"" ) ,
+    "vorbis entry length far too big": block(4, struct.pack("<I", 1) + b"v" + struct.pack("<I", 1) + struct.pack("<I", 5000) + b"abc"),
+    "vorbis trailing bytes": block(4, vorbis_comment(b"v", [b"A=1"]) + b"extra"),
+    "vorbis fewer entries than announced": block(4, vorbis_comment(b"v", [b"A=1"])[:5] + struct.pack("<I", 3) + struct.pack("<I", 3) + b"A=1"),
+    "picture mime longer than the block": block(6, struct.pack(">II", 3, 5000) + b"image/png"),
+    "picture trailing bytes": block(6, picture(3, b"image/png", b"d", 1, 1, 8, 0, bytes(10)) + b"extra"),
+    "picture data_length too big": block(6, picture(3, b"image/png", b"d", 1, 1, 8, 0, bytes(10))[:-10 - 4] + struct.pack(">I", 500) + bytes(10)),
+    "cuesheet trailing bytes": block(5, cuesheet(b"", 0, False, [(0, 1, b"", 0, 0, [(0, 1)])]) + b"xx"),
+    "cuesheet of 10 bytes": block(5, bytes(10)),
+    "streaminfo of 40 bytes then padding": block(1, bytes(7)),
+    "unknown type, empty": block(77, b""),
+    "vorbis two junk bytes where an entry should start": block(4, vorbis_comment(b"v", [b"A=1"])[:5] + struct.pack("<I", 3) + struct.pack("<I", 3) + b"A=1" + b"zz"),
+    "vorbis count 100000": block(4, struct.pack("<I", 1) + b"v" + struct.pack("<I", 100000)),
+    "vorbis count 100001": block(4, struct.pack("<I", 1) + b"v" + struct.pack("<I", 100001)),
+    "vorbis vendor only, no count": block(4, struct.pack("<I", 4) + b"vend"),
+    "application of 4 bytes": block(2, b"abcd"),
+    "seektable of 17 bytes": block(3, bytes(17)),
+    "seektable of 36 bytes": block(3, bytes(36)),
+})
+for name, blk in odd.items():
+    strm = data[:42] + blk + data[42:]
+    for ops in ([('single', 1)] * 2, [('meta',)]):       # (behind a block reported as BAD_METADATA the sessions reach audio frames: GPU tests)
+        a = scripted_decode_session(ours, strm, ops, meta=True, seekable=False, respond=(('respond_all',),))
+        b = scripted_decode_session(ref, strm, ops, meta=True, seekable=False, respond=(('respond_all',),))
+        n += 1
+        if a["events"] != b["events"]:
+            bad += 1
+            print("DIFF odd block:", name, ops, "\n ours", str(a["events"])[:400], "\n ref ", str(b["events"])[:400])
 # truncated metadata: the stream ends inside a block
 meta_end = 46 + int.from_bytes(data[43:46], 'big')         # STREAMINFO ends at byte 42, the VORBIS_COMMENT block behind it here
 assert data[42] == 0x84 and meta_end < 200
