@@ -39,7 +39,7 @@ typedef uint64_t FLAC__uint64;
 typedef struct { void *protected_; void *private_; } FLAC__StreamEncoder;
 typedef struct { void *protected_; void *private_; } FLAC__StreamDecoder;
 
-/* builder/encoder.py:129-137 + :234-248 -- only STREAMINFO is ever delivered (metadata callback at finish) */
+/* builder/encoder.py:129-137 + :234-248 -- the encoder only ever delivers STREAMINFO (metadata callback at finish) */
 typedef struct {
     uint32_t min_blocksize, max_blocksize;
     uint32_t min_framesize, max_framesize;
