@@ -92,6 +92,10 @@ struct DecImpl {
     bool have_last = false; uint64_t next_sample = 0; uint32_t last_blocksize = 0;     // stream position behind the last delivered frame
     std::deque<PendingFrame> ready;       // decoded frames not yet delivered
     FLAC__Frame frame;                    // callback payload (header filled per frame)
+    // what FLAC__stream_decoder_get_channels / _bits_per_sample / _sample_rate / _blocksize report: the header of the last frame
+    // that was delivered, as libFLAC (0 before the first frame, whatever STREAMINFO said)
+    uint32_t hdr_channels = 0, hdr_bps = 0, hdr_sample_rate = 0, hdr_blocksize = 0;
+    uint64_t meta_base = 0;               // stream offset of "fLaC" (the decode position moves block by block through the metadata)
 };
 struct DHandle { FLAC__StreamDecoder pub; DecImpl impl; };
 inline DecImpl* D(const FLAC__StreamDecoder* d) { return d ? (DecImpl*)d->private_ : nullptr; }
@@ -284,10 +288,10 @@ int parse_metadata(FLAC__StreamDecoder* d) {
     }
     if (!m->meta_truncated && !have_si) { m->meta_blocks.clear(); report(d, ERR_BAD_METADATA); return -1; }
     m->meta_blob.assign(m->in.begin(), m->in.begin() + (long)pos);
+    m->meta_base = m->bytes_consumed;
     if (!m->meta_truncated) {
         m->in.erase(m->in.begin(), m->in.begin() + (long)pos);
-        m->bytes_consumed += pos;
-        m->first_frame_offset = m->bytes_consumed;
+        m->first_frame_offset = m->meta_base + pos;
     }
     m->meta_parsed = true;
     return 1;
@@ -377,6 +381,7 @@ bool deliver_one(FLAC__StreamDecoder* d) {
     // libFLAC hands every frame over with its sample number, whatever the header carried (stream_decoder.c read_frame_header_)
     m->frame.header.channel_assignment = 0; m->frame.header.bits_per_sample = m->bps; m->frame.header.number_type = 1;
     m->frame.header.number.sample_number = pf.first_sample;
+    m->hdr_channels = m->channels; m->hdr_bps = m->bps; m->hdr_sample_rate = m->sample_rate; m->hdr_blocksize = pf.blocksize;
     if (m->md5_active) {
         m->md5_tmp.resize((size_t)pf.blocksize * m->channels);
         for (uint32_t c = 0; c < m->channels; c++) for (uint32_t i = 0; i < pf.blocksize; i++) m->md5_tmp[(size_t)i * m->channels + c] = planes[c][i];
@@ -414,11 +419,12 @@ int step(FLAC__StreamDecoder* d, bool until_end) {
                 const DecImpl::MetaBlock b = m->meta_blocks[m->meta_next++];
                 const bool done = m->meta_next == m->meta_blocks.size() && !m->meta_truncated;
                 if (done) m->metadata_done = true;
+                if (!m->meta_truncated) m->bytes_consumed = m->meta_base + b.off + b.len;      // FLAC__stream_decoder_get_decode_position: behind this block
                 m->state = done ? DS_SEARCH_FOR_FRAME_SYNC : DS_READ_METADATA;
                 const int rc = deliver_meta_block(d, b);
                 if (rc == kMetaBad) {
                     report(d, ERR_BAD_METADATA);
-                    if (!m->meta_truncated) { m->meta_next = m->meta_blocks.size(); m->metadata_done = true; }
+                    if (!m->meta_truncated) { m->meta_next = m->meta_blocks.size(); m->metadata_done = true; m->bytes_consumed = m->first_frame_offset; }
                     m->state = DS_SEARCH_FOR_FRAME_SYNC;
                     PendingFrame pf; pf.blocksize = 0; pf.error = ERR_LOST_SYNC; m->ready.push_back(std::move(pf));   // the rest of the metadata is junk in front of the first frame
                     return -1;
@@ -502,11 +508,11 @@ int FLAC__stream_decoder_get_state(const FLAC__StreamDecoder* d) { return D(d)->
 const char* FLAC__stream_decoder_get_resolved_state_string(const FLAC__StreamDecoder* d) { return FLAC__StreamDecoderStateString[D(d)->state]; }
 FLAC__bool FLAC__stream_decoder_get_md5_checking(const FLAC__StreamDecoder* d) { return D(d)->md5_checking; }
 FLAC__uint64 FLAC__stream_decoder_get_total_samples(const FLAC__StreamDecoder* d) { return D(d)->total_samples; }
-uint32_t FLAC__stream_decoder_get_channels(const FLAC__StreamDecoder* d) { return D(d)->channels; }
+uint32_t FLAC__stream_decoder_get_channels(const FLAC__StreamDecoder* d) { return D(d)->hdr_channels; }
 int FLAC__stream_decoder_get_channel_assignment(const FLAC__StreamDecoder*) { return 0; }
-uint32_t FLAC__stream_decoder_get_bits_per_sample(const FLAC__StreamDecoder* d) { return D(d)->bps; }
-uint32_t FLAC__stream_decoder_get_sample_rate(const FLAC__StreamDecoder* d) { return D(d)->sample_rate; }
-uint32_t FLAC__stream_decoder_get_blocksize(const FLAC__StreamDecoder* d) { return D(d)->blocksize; }
+uint32_t FLAC__stream_decoder_get_bits_per_sample(const FLAC__StreamDecoder* d) { return D(d)->hdr_bps; }
+uint32_t FLAC__stream_decoder_get_sample_rate(const FLAC__StreamDecoder* d) { return D(d)->hdr_sample_rate; }
+uint32_t FLAC__stream_decoder_get_blocksize(const FLAC__StreamDecoder* d) { return D(d)->hdr_blocksize; }
 // stream_decoder.h:1083-1099: needs a tell callback (FILE input always has one)
 FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder* d, FLAC__uint64* p) { const DecImpl* m = D(d); if (!p || (!m->file && !m->tell_cb)) return 0; *p = m->bytes_consumed; return 1; }
 
@@ -516,6 +522,7 @@ static int init_common(FLAC__StreamDecoder* d) {
     m->sample_rate = m->channels = m->bps = m->blocksize = 0; m->total_samples = 0; m->min_blocksize = 0;
     m->have_last = false; m->next_sample = 0; m->last_blocksize = 0; m->first_frame_offset = 0;
     m->meta_parsed = false; m->meta_truncated = false; m->meta_blocks.clear(); m->meta_blob.clear(); m->meta_next = 0; m->is_seeking = false;
+    m->hdr_channels = m->hdr_bps = m->hdr_sample_rate = m->hdr_blocksize = 0; m->meta_base = 0;
     m->md5_active = m->md5_checking != 0; m->md5.init(); memset(m->stored_md5, 0, 16);
     {
         std::lock_guard<std::mutex> lk(g_dec_mu);
@@ -592,8 +599,9 @@ static bool input_length(FLAC__StreamDecoder* d, uint64_t* len) {
 FLAC__bool FLAC__stream_decoder_flush(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
     if (m->state == DS_UNINITIALIZED) return 0;
+    if (m->meta_parsed && !m->meta_truncated && !m->metadata_done) { m->meta_next = m->meta_blocks.size(); m->metadata_done = true; m->bytes_consumed = m->first_frame_offset; }   // blocks not read yet are skipped
+    if (m->meta_parsed) m->bytes_consumed += m->in.size();             // the decode position moves behind the input that is dropped
     m->in.clear(); m->ready.clear(); m->md5_active = false; m->have_last = false;
-    if (m->meta_parsed && !m->meta_truncated) { m->meta_next = m->meta_blocks.size(); m->metadata_done = true; }   // blocks not read yet are skipped
     m->state = DS_SEARCH_FOR_FRAME_SYNC;
     return 1;
 }
@@ -607,6 +615,7 @@ FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) {
     else if (m->seek_cb && m->seek_cb(d, 0, m->client) == 1) return 0;          // seekable and the seek fails: reset fails
     m->metadata_done = false; m->eof = false; m->frame_index = 0; m->bytes_consumed = 0; m->next_sample = 0; m->last_blocksize = 0;
     m->meta_parsed = false; m->meta_truncated = false; m->meta_blocks.clear(); m->meta_next = 0;
+    m->total_samples = 0;                                              // (FLAC__stream_decoder_get_total_samples: 0 until STREAMINFO has been read again)
     m->md5_active = m->md5_checking != 0; m->md5.init();
     m->state = DS_SEARCH_FOR_METADATA;
     return 1;

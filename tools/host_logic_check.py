@@ -31,6 +31,82 @@ for padlen in (None, 0, 100, 70000, 300000, 3000000):      # None: the stream as
                 if a["events"] != b["events"]:
                     bad += 1
                     print("DIFF", padlen, ops, seek, rc, "\n ours", a["events"][:8], "\n ref ", b["events"][:8])
+def control_session(L, data, seekable=True):
+    """Getters, refused calls and return values around init / metadata / flush / reset / finish (no audio frame is reached)."""
+    log = []
+    P = "FLAC__stream_decoder_"
+    def f(name, res=C.c_int, args=(C.c_void_p,)):
+        fn = getattr(L, P + name); fn.restype = res; fn.argtypes = list(args); return fn
+    new = f("new", C.c_void_p, ())
+    getters = [("get_state", C.c_int), ("get_md5_checking", C.c_int), ("get_total_samples", C.c_uint64), ("get_channels", C.c_uint32),
+               ("get_channel_assignment", C.c_int), ("get_bits_per_sample", C.c_uint32), ("get_sample_rate", C.c_uint32), ("get_blocksize", C.c_uint32)]
+    def snap(tag, with_pos=True):
+        vals = [int(f(n, r)(d)) for n, r in getters]
+        s = f("get_resolved_state_string", C.c_char_p)(d)
+        pos = C.c_uint64(12345)
+        rv = f("get_decode_position", C.c_int, (C.c_void_p, C.POINTER(C.c_uint64)))(d, C.byref(pos))
+        log.append((tag, vals, s, rv, pos.value if rv and with_pos else None))
+    pos = [0]
+    def r(dec, buf, pbytes, cd):
+        k = min(pbytes[0], len(data) - pos[0])
+        if k == 0:
+            pbytes[0] = 0; return 1
+        C.memmove(buf, data[pos[0]:pos[0]+k], k); pos[0] += k; pbytes[0] = k; return 0
+    def sk(dec, off, cd): pos[0] = min(int(off), len(data)); return 0
+    def tl(dec, poff, cd): poff[0] = pos[0]; return 0
+    def ln(dec, plen, cd): plen[0] = len(data); return 0
+    def ef(dec, cd): return int(pos[0] >= len(data))
+    def w(dec, frame, buffers, cd): return 0
+    def e(dec, status, cd): log.append(('e', status))
+    cbs = (DEC_READ_CB(r), DEC_SEEK_CB(sk), DEC_TELL_CB(tl), DEC_LENGTH_CB(ln), DEC_EOF_CB(ef), DEC_WRITE_CB(w), DEC_ERROR_CB(e))
+    null = lambda T: C.cast(None, T)
+    d = new()
+    snap("new")
+    for name in ("process_single", "process_until_end_of_metadata", "process_until_end_of_stream", "skip_single_frame", "flush", "reset", "finish"):
+        log.append((name + " uninit", f(name)(d)))
+    log.append(("seek uninit", f("seek_absolute", C.c_int, (C.c_void_p, C.c_uint64))(d, 0)))
+    log.append(("set_md5", f("set_md5_checking", C.c_int, (C.c_void_p, C.c_int))(d, 1)))
+    snap("after set_md5")
+    init = getattr(L, P + "init_stream"); init.restype = C.c_int
+    init.argtypes = [C.c_void_p, DEC_READ_CB, DEC_SEEK_CB, DEC_TELL_CB, DEC_LENGTH_CB, DEC_EOF_CB, DEC_WRITE_CB, C.c_void_p, DEC_ERROR_CB, C.c_void_p]
+    # invalid callback sets
+    log.append(("init no read", init(d, null(DEC_READ_CB), cbs[1], cbs[2], cbs[3], cbs[4], cbs[5], None, cbs[6], None)))
+    log.append(("init seek w/o tell", init(d, cbs[0], cbs[1], null(DEC_TELL_CB), cbs[3], cbs[4], cbs[5], None, cbs[6], None)))
+    snap("after bad init")
+    if seekable:
+        log.append(("init", init(d, cbs[0], cbs[1], cbs[2], cbs[3], cbs[4], cbs[5], None, cbs[6], None)))
+    else:
+        log.append(("init", init(d, cbs[0], null(DEC_SEEK_CB), null(DEC_TELL_CB), null(DEC_LENGTH_CB), null(DEC_EOF_CB), cbs[5], None, cbs[6], None)))
+    snap("after init")
+    log.append(("init again", init(d, cbs[0], cbs[1], cbs[2], cbs[3], cbs[4], cbs[5], None, cbs[6], None)))
+    log.append(("set_md5 after init", f("set_md5_checking", C.c_int, (C.c_void_p, C.c_int))(d, 0)))
+    log.append(("respond_all after init", f("set_metadata_respond_all")(d)))
+    log.append(("single", f("process_single")(d))); snap("after single")
+    log.append(("single", f("process_single")(d))); snap("after single 2")
+    log.append(("meta", f("process_until_end_of_metadata")(d))); snap("after meta")
+    log.append(("meta again", f("process_until_end_of_metadata")(d))); snap("after meta again")
+    log.append(("flush", f("flush")(d))); snap("after flush", with_pos=False)     # (how far each library had read ahead)
+    if seekable:
+        log.append(("reset", f("reset")(d))); snap("after reset")
+        log.append(("meta", f("process_until_end_of_metadata")(d))); snap("after meta 2")
+    log.append(("finish", f("finish")(d))); snap("after finish")
+    log.append(("finish again", f("finish")(d)))
+    f("delete", None)(d)
+    return log
+
+
+from _flacapi import DEC_READ_CB, DEC_SEEK_CB, DEC_TELL_CB, DEC_LENGTH_CB, DEC_EOF_CB, DEC_WRITE_CB, DEC_ERROR_CB   # noqa: E402
+from _metablocks import rich_stream as _rich                 # noqa: E402
+for dat in (data, _rich(data)[0]):
+    for seekable in (True, False):
+        a, b = control_session(ours, dat, seekable), control_session(ref, dat, seekable)
+        n += 1
+        if a != b:
+            bad += 1
+            for ea, eb in zip(a, b):
+                if ea != eb:
+                    print("DIFF control surface, seekable =", seekable, "\n ours", ea, "\n ref ", eb)
+
 # every block type through the metadata callback under the respond / ignore filters (tests/_metablocks.py)
 from _metablocks import rich_stream, block, vorbis_comment, picture, cuesheet   # noqa: E402
 rich, nb = rich_stream(data)
