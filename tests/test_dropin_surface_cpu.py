@@ -151,6 +151,26 @@ def test_uninitialised_calls_behave_like_libflac(libs):
         f.argtypes = [C.c_void_p, C.c_int]
         f.restype = C.c_int
         r.append(("set_md5_checking", f(d, 1), L.FLAC__stream_decoder_get_md5_checking(d)))
+        # the metadata filter (builder/decoder.py:392-397): settable on an uninitialised handle, type codes up to 126
+        for name in ["respond_all", "ignore_all"]:
+            f = getattr(L, "FLAC__stream_decoder_set_metadata_" + name)
+            f.argtypes = [C.c_void_p]
+            f.restype = C.c_int
+            r.append((name, f(d)))
+        for name in ["respond", "ignore"]:
+            f = getattr(L, "FLAC__stream_decoder_set_metadata_" + name)
+            f.argtypes = [C.c_void_p, C.c_int]
+            f.restype = C.c_int
+            r.append((name, [f(d, t) for t in (0, 1, 6, 7, 126, 127)]))      # (libFLAC asserts on larger codes)
+        for name in ["respond_application", "ignore_application"]:
+            f = getattr(L, "FLAC__stream_decoder_set_metadata_" + name)
+            f.argtypes = [C.c_void_p, C.c_char_p]
+            f.restype = C.c_int
+            r.append((name, f(d, b"abcd")))
+        f = L.FLAC__stream_decoder_get_decode_position
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        f.restype = C.c_int
+        r.append(("get_decode_position", f(d, C.byref(C.c_uint64(0)))))
         L.FLAC__stream_decoder_delete.argtypes = [C.c_void_p]
         L.FLAC__stream_decoder_delete(d)
         res.append(r)
