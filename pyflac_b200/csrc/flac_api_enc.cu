@@ -587,17 +587,21 @@ FLAC__bool FLAC__stream_encoder_process(FLAC__StreamEncoder* e, const FLAC__int3
 FLAC__bool FLAC__stream_encoder_finish(FLAC__StreamEncoder* e) {
     EncImpl* m = I(e);
     if (!m || m->state == ST_UNINITIALIZED) return 1;
-    bool ok = (m->state == ST_OK);
-    if (ok) {
+    // up: FLAC__stream_encoder_finish (pinned on the binary, tools/host_logic_check.py and tests/test_gpu_dropin.py): only what goes
+    // wrong INSIDE this call makes it fail and leaves the error state standing -- the last frame, the STREAMINFO rewrite.  An
+    // encoder that was already in an error state (a process() call failed) is simply reset: true, UNINITIALIZED.
+    bool ok = true;
+    if (m->state == ST_OK) {
         const uint64_t have = m->pending.size() / m->channels;
         if (have > 0) ok = encode_pending(e, have);           // remainder -> final (possibly short) frame
     }
     uint8_t digest[16];
     m->md5.final(digest);
-    if (ok) {
+    if (m->state == ST_OK) {
         // up: update_metadata_ -- rewrite STREAMINFO in place: MD5 @26 (16 B), total samples @21 (5 B), frame sizes @12 (6 B)
         uint8_t si[34];
-        put_streaminfo(si, m, m->min_fs, m->max_fs, m->samples_written, digest);
+        const uint32_t min_fs = m->min_fs ? m->min_fs : 0xFFFFFFu;      // no frame at all: libFLAC's minimum is still where it started (2^24 - 1)
+        put_streaminfo(si, m, min_fs, m->max_fs, m->samples_written, digest);
         // offsets are relative to the STREAMINFO block header (4 when the stream starts at byte 0): +22, +17, +8
         const uint64_t so = m->file ? 4 : (m->streaminfo_offset ? m->streaminfo_offset : 4);
         struct { uint64_t off; const uint8_t* p; size_t n; } patch[3] = {{so + 22, si + 18, 16}, {so + 17, si + 13, 5}, {so + 8, si + 4, 6}};
@@ -614,7 +618,7 @@ FLAC__bool FLAC__stream_encoder_finish(FLAC__StreamEncoder* e) {
             FLAC__StreamMetadata md; memset(&md, 0, sizeof md);
             md.type = 0; md.is_last = 0; md.length = 34;
             md.data.stream_info.min_blocksize = md.data.stream_info.max_blocksize = m->N;
-            md.data.stream_info.min_framesize = m->min_fs; md.data.stream_info.max_framesize = m->max_fs;
+            md.data.stream_info.min_framesize = min_fs; md.data.stream_info.max_framesize = m->max_fs;
             md.data.stream_info.sample_rate = m->sample_rate; md.data.stream_info.channels = m->channels;
             md.data.stream_info.bits_per_sample = m->bps; md.data.stream_info.total_samples = m->samples_written;
             memcpy(md.data.stream_info.md5sum, digest, 16);
@@ -626,7 +630,7 @@ FLAC__bool FLAC__stream_encoder_finish(FLAC__StreamEncoder* e) {
     m->pending.clear();
     if (m->counted && m->disp) { m->disp->active.fetch_sub(1); m->counted = false; }
     reset_settings(m);                                         // stream_encoder.h:225-227: back to defaults
-    m->state = ST_UNINITIALIZED;
+    if (ok) m->state = ST_UNINITIALIZED;
     return ok ? 1 : 0;
 }
 

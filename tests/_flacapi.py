@@ -95,9 +95,11 @@ def _proto(L):
 
 
 def encode_session(L, pcm, sample_rate, bps, level=5, blocksize=0, chunks=None, seekable=True, metadata=True,
-                   verify=False, streamable_subset=True, init_only=False, no_tell=False, limit_min_bitrate=False, setters=()):
+                   verify=False, streamable_subset=True, init_only=False, no_tell=False, limit_min_bitrate=False, setters=(),
+                   fail=None):
     """Run one StreamEncoder session; returns dict(init_status, log=[(event, ...)], file=bytes image, ok=bool).
-    log events: ('write', bytes, samples, frame) | ('seek', off) | ('tell', off) | ('meta', dict)."""
+    log events: ('write', bytes, samples, frame) | ('seek', off) | ('tell', off) | ('meta', dict).
+    fail: {'write' | 'seek' | 'tell': k} makes the k-th call (from 0) of that callback report an error."""
     _proto(L)
     x = np.ascontiguousarray(pcm)
     if x.ndim == 1:
@@ -105,22 +107,34 @@ def encode_session(L, pcm, sample_rate, bps, level=5, blocksize=0, chunks=None, 
     n, ch = x.shape
     x32 = np.ascontiguousarray(x.astype(np.int32))
     log, image, pos = [], bytearray(), [0]
+    calls = {"write": 0, "seek": 0, "tell": 0}
+
+    def failing(kind):
+        k = calls[kind]
+        calls[kind] += 1
+        return bool(fail) and fail.get(kind) == k
 
     def w(enc, buf, nbytes, samples, frame, cd):
         b = bytes(buf[:nbytes])
         log.append(("write", b, samples, frame))
+        if failing("write"):
+            return 1
         image[pos[0]:pos[0] + nbytes] = b
         pos[0] += nbytes
         return 0
 
     def s(enc, off, cd):
         log.append(("seek", off))
+        if failing("seek"):
+            return 1
         pos[0] = off
         return 0
 
     def t(enc, poff, cd):
-        poff[0] = pos[0]
         log.append(("tell", pos[0]))
+        if failing("tell"):
+            return 1
+        poff[0] = pos[0]
         return 0
 
     def m(enc, md, cd):
@@ -150,6 +164,7 @@ def encode_session(L, pcm, sample_rate, bps, level=5, blocksize=0, chunks=None, 
                                             null(TELL_CB) if (not seekable or no_tell) else tcb,
                                             mcb if metadata else null(META_CB), None)
     res = dict(init_status=st, log=log, ok=True)
+    res["state_after_init_call"] = L.FLAC__stream_encoder_get_state(e)
     if st == 0 and not init_only:
         res["state_after_init"] = L.FLAC__stream_encoder_get_state(e)
         if chunks is None:

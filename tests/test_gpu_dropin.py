@@ -82,6 +82,27 @@ def test_stream_encoder_verify(ours, ref):
         assert _norm(a["log"]) == _norm(b["log"]) and a["file"] == b["file"]
 
 
+def test_stream_encoder_failing_callbacks_and_empty_stream(ours, ref):
+    """A write / tell / seek callback that reports an error at any point of a session -- the header at init, a frame inside process(),
+    the last short frame or the STREAMINFO rewrite inside finish(): the same callback log, return values and states as libFLAC
+    (finish() fails and keeps the error state only for what goes wrong inside it; an encoder already in an error state is reset and
+    finish() returns true).  And a stream without a single sample (min framesize stays 2^24 - 1)."""
+    from _flacapi import encode_session
+    x = music_like(4096 * 3 + 77, 2, 44100, 16, seed=21)
+    for fail in [None] + [{k: i} for k in ("write", "tell") for i in range(9)] + [{"seek": i} for i in range(3)]:
+        a = encode_session(ours, x, 44100, 16, 5, 0, fail=fail, chunks=[4097, 4096, 5000])
+        b = encode_session(ref, x, 44100, 16, 5, 0, fail=fail, chunks=[4097, 4096, 5000])
+        assert _norm(a.pop("log")) == _norm(b.pop("log")), fail
+        assert a == b, fail
+    for ch, bps in ((2, 16), (1, 24), (8, 8)):
+        e = np.zeros((0, ch), np.int32)
+        for seekable in (True, False):
+            a = encode_session(ours, e, 48000, bps, 5, 0, seekable=seekable)
+            b = encode_session(ref, e, 48000, bps, 5, 0, seekable=seekable)
+            assert _norm(a.pop("log")) == _norm(b.pop("log")), (ch, bps, seekable)
+            assert a == b and (not seekable or a["file"][12:15] == b"\xff\xff\xff")
+
+
 def test_stream_encoder_init_errors(ours, ref):
     """reference tests/test_encoder.py:139-164,202-207"""
     from _flacapi import encode_session

@@ -183,5 +183,24 @@ for cut in (0, 3, 4, 7, 20, 41, 42, 45, 46, 60, meta_end - 1):     # (from meta_
         if a["events"] != b["events"]:
             bad += 1
             print("DIFF truncated at", cut, ops, "\n ours", a["events"], "\n ref ", b["events"])
+# encoder: a stream without a single sample never reaches a kernel -- header writes, tell / seek traffic, the STREAMINFO rewrite at
+# finish (min framesize 2^24 - 1: no frame ever lowered it), the metadata callback, and what happens when a callback fails
+import numpy as np                                         # noqa: E402
+from _flacapi import encode_session                        # noqa: E402
+for ch, bps, sr, level, bs in ((2, 16, 44100, 5, 0), (1, 24, 96000, 8, 4096), (8, 8, 8000, 0, 1152), (2, 32, 192000, 3, 256), (3, 12, 22050, 5, 0)):
+    x = np.zeros((0, ch), np.int32)
+    for seekable in (True, False):
+        for meta in (True, False):
+            fails = [None] + [{k: i} for k in ("write", "seek", "tell") for i in range(7)] if seekable else [None] + [{"write": i} for i in range(4)]
+            for fail in fails:
+                a = encode_session(ours, x, sr, bps, level, bs, seekable=seekable, metadata=meta, fail=fail)
+                b = encode_session(ref, x, sr, bps, level, bs, seekable=seekable, metadata=meta, fail=fail)
+                n += 1
+                if a != b:
+                    bad += 1
+                    print("DIFF empty encode", (ch, bps, sr, level, bs), seekable, meta, fail)
+                    for k in a:
+                        if a[k] != b.get(k):
+                            print("  ", k, "\n    ours", str(a[k])[-400:], "\n    ref ", str(b.get(k))[-400:])
 print(f"{n} sessions, {bad} differ from libFLAC")
 sys.exit(1 if bad else 0)
