@@ -202,5 +202,34 @@ for ch, bps, sr, level, bs in ((2, 16, 44100, 5, 0), (1, 24, 96000, 8, 4096), (8
                     for k in a:
                         if a[k] != b.get(k):
                             print("  ", k, "\n    ours", str(a[k])[-400:], "\n    ref ", str(b.get(k))[-400:])
+# the same through FLAC__stream_encoder_init_file (FileEncoder): statuses, states, the file on disk
+import tempfile                                            # noqa: E402
+
+
+def file_session(L, path, ch, bps, sr, est):
+    e = L.FLAC__stream_encoder_new()
+    L.FLAC__stream_encoder_set_channels(e, ch)
+    L.FLAC__stream_encoder_set_bits_per_sample(e, bps)
+    L.FLAC__stream_encoder_set_sample_rate(e, sr)
+    if est is not None:
+        L.FLAC__stream_encoder_set_total_samples_estimate.argtypes = [C.c_void_p, C.c_uint64]
+        L.FLAC__stream_encoder_set_total_samples_estimate(e, est)
+    st = L.FLAC__stream_encoder_init_file(e, path.encode(), None, None)
+    s1 = L.FLAC__stream_encoder_get_state(e)
+    st2 = L.FLAC__stream_encoder_init_file(e, path.encode(), None, None)         # ALREADY_INITIALIZED
+    fin = L.FLAC__stream_encoder_finish(e)
+    s2 = L.FLAC__stream_encoder_get_state(e)
+    L.FLAC__stream_encoder_delete(e)
+    return st, s1, st2, fin, s2, open(path, "rb").read() if os.path.exists(path) else None
+
+
+with tempfile.TemporaryDirectory() as tmp:
+    for ch, bps, sr, est, name in ((2, 16, 44100, None, "a.flac"), (1, 24, 96000, 1000, "a.flac"), (6, 20, 48000, 0, "a.flac"), (2, 16, 44100, None, "no/such/dir.flac")):
+        a = file_session(ours, os.path.join(tmp, "ours_" + name), ch, bps, sr, est)
+        b = file_session(ref, os.path.join(tmp, "ref_" + name), ch, bps, sr, est)
+        n += 1
+        if a != b:
+            bad += 1
+            print("DIFF file encode", (ch, bps, sr, est, name), "\n ours", a, "\n ref ", b)
 print(f"{n} sessions, {bad} differ from libFLAC")
 sys.exit(1 if bad else 0)
