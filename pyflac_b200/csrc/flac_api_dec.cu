@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <algorithm>
 #include <deque>
 #include <mutex>
 #include <vector>
@@ -74,6 +75,9 @@ struct DecImpl {
     struct MetaBlock { uint32_t type, len; bool last; size_t off; };     // off: first data byte in meta_blob
     std::vector<uint8_t> meta_blob; std::vector<MetaBlock> meta_blocks; size_t meta_next = 0;
     bool meta_parsed = false, meta_truncated = false;
+    // the search for "fLaC" in front of the blocks (find_magic): resumable, because the errors it reports must be reported once
+    size_t find_scan = 0; int find_i = 0, find_id = 0, id3_need = 0; bool find_first = true; uint32_t id3_size = 0; uint64_t find_skip = 0;
+    void find_reset() { find_scan = 0; find_i = find_id = id3_need = 0; find_first = true; id3_size = 0; find_skip = 0; }
     bool is_seeking = false;              // metadata read on behalf of a seek is not reported (stream_decoder.c: is_seeking)
     // FLAC__stream_decoder_set_metadata_respond* / _ignore*: one switch per block type (default: STREAMINFO only) and, for
     // APPLICATION blocks, the ids that are exceptions to their type's switch
@@ -100,7 +104,7 @@ struct DecImpl {
 struct DHandle { FLAC__StreamDecoder pub; DecImpl impl; };
 inline DecImpl* D(const FLAC__StreamDecoder* d) { return d ? (DecImpl*)d->private_ : nullptr; }
 
-void report(FLAC__StreamDecoder* d, int status) { DecImpl* m = D(d); if (m->error_cb) m->error_cb(d, status, m->client); }
+void report(FLAC__StreamDecoder* d, int status) { DecImpl* m = D(d); if (m->error_cb && !m->is_seeking) m->error_cb(d, status, m->client); }   // (nothing met on behalf of a seek is reported)
 
 // pull one slice of input; returns false on abort
 bool pull(FLAC__StreamDecoder* d, size_t want) {
@@ -264,17 +268,72 @@ int deliver_meta_block(FLAC__StreamDecoder* d, const DecImpl::MetaBlock& b) {
 // input slice -- cover art, a long PADDING -- and take several pulls; nothing is reported before all of them are here).
 // returns 1 listed, 0 need more input, -1 fatal.  When the input ends inside the metadata the complete blocks are listed and
 // meta_truncated is set.
+// The search for "fLaC" at the head of the input (up: find_metadata_, stream_decoder.c; pinned on the binary by
+// tools/host_logic_check.py): an ID3v2 tag in front of it is skipped without a word; any other byte that is not part of the marker
+// is reported as LOST_SYNC -- once per run of such bytes, a run ending wherever a byte continues the marker; bytes other than the
+// marker behind an ID3v2 tag make the call fail once and the next call search afresh.  returns 1 found (find_scan stands behind
+// the marker), 0 need more input, -1 a frame sync code came first (a stream without metadata: not decodable by this build),
+// -2 the input ended, -3 this call fails and the next one searches on.
+int find_magic(FLAC__StreamDecoder* d) {
+    DecImpl* m = D(d);
+    const std::vector<uint8_t>& in = m->in;
+    static const uint8_t kMagic[4] = {'f', 'L', 'a', 'C'}, kId3[3] = {'I', 'D', '3'};
+    while (m->find_i < 4) {
+        if (m->find_skip) {                                             // inside an ID3v2 tag
+            const uint64_t k = std::min<uint64_t>(m->find_skip, in.size() - m->find_scan);
+            m->find_scan += (size_t)k; m->find_skip -= k;
+            if (m->find_skip) return m->eof ? -2 : 0;
+            continue;
+        }
+        if (m->find_scan >= in.size()) return m->eof ? -2 : 0;
+        const uint8_t x = in[m->find_scan];
+        if (m->id3_need) {                                              // the rest of an ID3v2 header: version (2), flags (1), size (4 x 7 bits)
+            m->find_scan++;
+            if (m->id3_need <= 4) m->id3_size = (m->id3_size << 7) | (x & 0x7fu);
+            if (--m->id3_need == 0) m->find_skip = m->id3_size;
+            continue;
+        }
+        const bool marker = x == kMagic[m->find_i];
+        const bool id3 = !marker && m->find_id < 3 && x == kId3[m->find_id];
+        if (!marker && !id3 && m->find_id < 3 && x == 0xff && m->find_scan + 1 >= in.size()) return m->eof ? -2 : 0;   // needs the byte behind it
+        m->find_scan++;
+        if (marker) { m->find_first = true; m->find_i++; m->find_id = 0; continue; }
+        if (m->find_id >= 3) { m->find_i = m->find_id = 0; m->find_first = true; return -3; }
+        if (id3) { m->find_i = 0; if (++m->find_id == 3) { m->id3_need = 7; m->id3_size = 0; } continue; }
+        m->find_id = 0;
+        if (x == 0xff) {
+            const uint8_t y = in[m->find_scan];
+            if (y != 0xff) {                                            // (a second 0xff is looked at again: it may start the sync code)
+                m->find_scan++;
+                if ((y >> 1) == 0x7c) return -1;
+            }
+        }
+        m->find_i = 0;
+        if (m->find_first) { report(d, ERR_LOST_SYNC); m->find_first = false; }
+    }
+    return 1;
+}
+
 int parse_metadata(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
     m->meta_blocks.clear(); m->meta_next = 0; m->meta_truncated = false;
-    if (m->in.size() < 4) { if (!m->eof) return 0; m->meta_truncated = true; m->meta_parsed = true; return 1; }
-    if (memcmp(m->in.data(), "fLaC", 4) != 0) {
-        // libFLAC would hunt for a frame sync in arbitrary data and report LOST_SYNC; without STREAMINFO there is nothing
-        // this build can decode (pyFLAC's tests expect the error, tests/test_decoder.py:59-66)
-        report(d, ERR_LOST_SYNC);
+    const int found = find_magic(d);
+    if (found == 0 || found == -3) {
+        // a long stretch without the marker (or a large ID3v2 tag) is not kept: the input buffer holds what is still needed
+        if (m->find_scan > (1u << 20) && m->find_i == 0 && m->id3_need == 0) {
+            m->in.erase(m->in.begin(), m->in.begin() + (long)m->find_scan);
+            m->bytes_consumed += m->find_scan; m->find_scan = 0;
+        }
+        return found;
+    }
+    if (found == -2) { m->meta_truncated = true; m->meta_parsed = true; m->bytes_consumed += m->in.size(); m->in.clear(); return 1; }   // (all of the input was read)
+    if (found == -1) {
+        // libFLAC goes on to decode such frames without STREAMINFO; this build cannot (pyFLAC's tests expect an error for
+        // arbitrary data, tests/test_decoder.py:59-66)
+        if (m->find_first) report(d, ERR_LOST_SYNC);
         return -1;
     }
-    size_t pos = 4; bool have_si = false;
+    size_t pos = m->find_scan; bool have_si = false;
     for (;;) {
         if (pos + 4 > m->in.size()) { if (!m->eof) return 0; m->meta_truncated = true; break; }
         const uint8_t* p = m->in.data() + pos;
@@ -411,6 +470,7 @@ int step(FLAC__StreamDecoder* d, bool until_end) {
         if (!m->metadata_done) {
             if (!m->meta_parsed) {
                 const int r = parse_metadata(d);
+                if (r == -3) return -1;                                  // this call fails, the state stands, the next call searches on
                 if (r < 0) { m->state = m->eof ? DS_END_OF_STREAM : DS_ABORTED; return m->eof ? 0 : -1; }
                 if (r == 0) { if (!pull(d, kSlice)) return -1; continue; }
             }
@@ -514,7 +574,7 @@ uint32_t FLAC__stream_decoder_get_bits_per_sample(const FLAC__StreamDecoder* d) 
 uint32_t FLAC__stream_decoder_get_sample_rate(const FLAC__StreamDecoder* d) { return D(d)->hdr_sample_rate; }
 uint32_t FLAC__stream_decoder_get_blocksize(const FLAC__StreamDecoder* d) { return D(d)->hdr_blocksize; }
 // stream_decoder.h:1083-1099: needs a tell callback (FILE input always has one)
-FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder* d, FLAC__uint64* p) { const DecImpl* m = D(d); if (!p || (!m->file && !m->tell_cb)) return 0; *p = m->bytes_consumed; return 1; }
+FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder* d, FLAC__uint64* p) { const DecImpl* m = D(d); if (!p || (!m->file && !m->tell_cb)) return 0; *p = m->bytes_consumed + (m->meta_parsed ? 0 : m->find_scan);   /* (while the marker is still being looked for: what the search has read) */ return 1; }
 
 static int init_common(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
@@ -522,6 +582,7 @@ static int init_common(FLAC__StreamDecoder* d) {
     m->sample_rate = m->channels = m->bps = m->blocksize = 0; m->total_samples = 0; m->min_blocksize = 0;
     m->have_last = false; m->next_sample = 0; m->last_blocksize = 0; m->first_frame_offset = 0;
     m->meta_parsed = false; m->meta_truncated = false; m->meta_blocks.clear(); m->meta_blob.clear(); m->meta_next = 0; m->is_seeking = false;
+    m->find_reset();
     m->hdr_channels = m->hdr_bps = m->hdr_sample_rate = m->hdr_blocksize = 0; m->meta_base = 0;
     m->md5_active = m->md5_checking != 0; m->md5.init(); memset(m->stored_md5, 0, 16);
     {
@@ -601,6 +662,7 @@ FLAC__bool FLAC__stream_decoder_flush(FLAC__StreamDecoder* d) {
     if (m->state == DS_UNINITIALIZED) return 0;
     if (m->meta_parsed && !m->meta_truncated && !m->metadata_done) { m->meta_next = m->meta_blocks.size(); m->metadata_done = true; m->bytes_consumed = m->first_frame_offset; }   // blocks not read yet are skipped
     if (m->meta_parsed) m->bytes_consumed += m->in.size();             // the decode position moves behind the input that is dropped
+    else m->find_reset();                                              // (nothing of the dropped input is looked at again)
     m->in.clear(); m->ready.clear(); m->md5_active = false; m->have_last = false;
     m->state = DS_SEARCH_FOR_FRAME_SYNC;
     return 1;
@@ -614,7 +676,7 @@ FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) {
     if (m->file) { if (m->file == stdin) return 0; if (fseeko(m->file, 0, SEEK_SET) != 0) return 0; }
     else if (m->seek_cb && m->seek_cb(d, 0, m->client) == 1) return 0;          // seekable and the seek fails: reset fails
     m->metadata_done = false; m->eof = false; m->frame_index = 0; m->bytes_consumed = 0; m->next_sample = 0; m->last_blocksize = 0;
-    m->meta_parsed = false; m->meta_truncated = false; m->meta_blocks.clear(); m->meta_next = 0;
+    m->meta_parsed = false; m->meta_truncated = false; m->meta_blocks.clear(); m->meta_next = 0; m->find_reset();
     m->total_samples = 0;                                              // (FLAC__stream_decoder_get_total_samples: 0 until STREAMINFO has been read again)
     m->md5_active = m->md5_checking != 0; m->md5.init();
     m->state = DS_SEARCH_FOR_METADATA;

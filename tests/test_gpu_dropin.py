@@ -314,6 +314,17 @@ def test_decoder_metadata_larger_than_one_read(ours, ref, checkers):
                 assert a["events"] == b["events"], (padlen, ops, rc)
                 assert a["finish"] is True and b["finish"] is True
                 assert sum(1 for e in a["events"] if e[0] == 'm') == 1
+    # bytes in front of "fLaC": an ID3v2 tag is skipped without a word, anything else is reported as LOST_SYNC (once per run), bytes
+    # behind a tag make one call fail; then the stream decodes as usual (positions, seeks and the MD5 check included)
+    def id3(nbytes):
+        return b"ID3\x03\x00\x00" + bytes([(nbytes >> 21) & 0x7f, (nbytes >> 14) & 0x7f, (nbytes >> 7) & 0x7f, nbytes & 0x7f]) + bytes(nbytes)
+    for head in (id3(5000), id3(300000), b"0123456789", id3(10) + b"xy", bytes(1000)):
+        for ops in ([('single', 3), ('end',)], [('end',), ('end',)], [('seek', 5000), ('end',)]):
+            a = scripted_decode_session(ours, head + data, ops, meta=True, seekable=True, read_chunk=8192, md5_checking=True)
+            b = scripted_decode_session(ref, head + data, ops, meta=True, seekable=True, read_chunk=8192, md5_checking=True)
+            assert a["events"] == b["events"], (head[:12], ops)
+            assert a["finish"] == b["finish"]
+            assert sum(1 for e in a["events"] if e[0] == 'w') in (3, 4)
     # the input ends inside the metadata: the complete blocks are read (callback, one process_single each), the call that meets the
     # end returns false in END_OF_STREAM
     for cut in (0, 3, 20, 42, 45, 60):
