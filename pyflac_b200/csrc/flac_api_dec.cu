@@ -242,7 +242,7 @@ int deliver_meta_block(FLAC__StreamDecoder* d, const DecImpl::MetaBlock& b) {
     case 6: {
         const uint8_t* p = q;
         if (e - p < 8) return kMetaBad;
-        md.data.picture.type = (int)be32(p); p += 4;
+        { const uint32_t t = be32(p); md.data.picture.type = t <= 20 ? (int)t : 0; } p += 4;   // (a type beyond the defined ones is handed over as OTHER)
         const uint32_t ml = be32(p); p += 4;
         if ((size_t)(e - p) < (size_t)ml + 4) return kMetaBad;
         keep(p, ml); p += ml;

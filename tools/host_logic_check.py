@@ -162,6 +162,9 @@ odd.update({
     "application of 4 bytes": block(2, b"abcd"),
     "seektable of 17 bytes": block(3, bytes(17)),
     "seektable of 36 bytes": block(3, bytes(36)),
+    "picture type 20": block(6, picture(20, b"image/png", b"d", 1, 1, 8, 0, bytes(4))),
+    "picture type 21": block(6, picture(21, b"image/png", b"d", 1, 1, 8, 0, bytes(4))),
+    "picture type 2^32 - 1": block(6, picture(0xffffffff, b"image/png", b"d", 1, 1, 8, 0, bytes(4))),
 })
 for name, blk in odd.items():
     strm = data[:42] + blk + data[42:]
