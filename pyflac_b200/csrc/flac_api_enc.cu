@@ -587,7 +587,7 @@ FLAC__bool FLAC__stream_encoder_process(FLAC__StreamEncoder* e, const FLAC__int3
 FLAC__bool FLAC__stream_encoder_finish(FLAC__StreamEncoder* e) {
     EncImpl* m = I(e);
     if (!m || m->state == ST_UNINITIALIZED) return 1;
-    // up: FLAC__stream_encoder_finish (pinned on the binary, tools/host_logic_check.py and tests/test_gpu_dropin.py): only what goes
+    // up: FLAC__stream_encoder_finish (pinned on the binary, tools/host_logic_check.py and tests/test_gpu_zz_host_logic.py): only what goes
     // wrong INSIDE this call makes it fail and leaves the error state standing -- the last frame, the STREAMINFO rewrite.  An
     // encoder that was already in an error state (a process() call failed) is simply reset: true, UNINITIALIZED.
     bool ok = true;
