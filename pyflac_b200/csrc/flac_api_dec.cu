@@ -69,12 +69,13 @@ struct DecImpl {
     FLAC__StreamDecoderSeekCallback seek_cb = nullptr; FLAC__StreamDecoderTellCallback tell_cb = nullptr;
     FLAC__StreamDecoderLengthCallback length_cb = nullptr; FLAC__StreamDecoderEofCallback eof_cb = nullptr;
     void* client = nullptr;
-    // Metadata: parse_metadata() waits until all blocks are buffered and lists them; they are then read one per process_single, as
-    // libFLAC does (the block's callback fires inside the call that reads it).  meta_truncated: the input ended inside the
-    // metadata -- the complete blocks are read, the call that meets the end fails in END_OF_STREAM.
-    struct MetaBlock { uint32_t type, len; bool last; size_t off; };     // off: first data byte in meta_blob
-    std::vector<uint8_t> meta_blob; std::vector<MetaBlock> meta_blocks; size_t meta_next = 0;
-    bool meta_parsed = false, meta_truncated = false;
+    // Metadata is read the way libFLAC reads it: the stream marker first (find_magic), then one block per process_single -- a block
+    // is read (and its callback fires) in the call that finds all of it buffered; `in` keeps the metadata bytes until the last block
+    // has been read.  meta_pos: offset in `in` of the next block header.  meta_skip: a block could not be used (BAD_METADATA): the
+    // blocks behind it are walked without a word on the way to the first frame.
+    struct MetaBlock { uint32_t type, len; bool last; size_t off; };     // off: first data byte in `in`
+    size_t meta_pos = 0; bool have_si = false, meta_skip = false;
+    void meta_reset() { meta_pos = 0; have_si = false; meta_skip = false; find_reset(); }
     // the search for "fLaC" in front of the blocks (find_magic): resumable, because the errors it reports must be reported once
     size_t find_scan = 0; int find_i = 0, find_id = 0, id3_need = 0; bool find_first = true; uint32_t id3_size = 0; uint64_t find_skip = 0;
     void find_reset() { find_scan = 0; find_i = find_id = id3_need = 0; find_first = true; id3_size = 0; find_skip = 0; }
@@ -99,7 +100,6 @@ struct DecImpl {
     // what FLAC__stream_decoder_get_channels / _bits_per_sample / _sample_rate / _blocksize report: the header of the last frame
     // that was delivered, as libFLAC (0 before the first frame, whatever STREAMINFO said)
     uint32_t hdr_channels = 0, hdr_bps = 0, hdr_sample_rate = 0, hdr_blocksize = 0;
-    uint64_t meta_base = 0;               // stream offset of "fLaC" (the decode position moves block by block through the metadata)
 };
 struct DHandle { FLAC__StreamDecoder pub; DecImpl impl; };
 inline DecImpl* D(const FLAC__StreamDecoder* d) { return d ? (DecImpl*)d->private_ : nullptr; }
@@ -118,7 +118,7 @@ bool pull(FLAC__StreamDecoder* d, size_t want) {
     if (st == 2) { m->in.resize(old); m->state = DS_ABORTED; return false; }
     if (st == 1) { m->eof = true; if (got > want) got = 0; }
     m->in.resize(old + (st == 1 && !m->file ? got : got));
-    if (got == 0 && st != 1 && !m->file) { /* spurious empty read: treat like libFLAC (abort) */ m->state = DS_ABORTED; return false; }
+    // (a read callback that hands over nothing and says CONTINUE is simply asked again, as libFLAC does)
     return true;
 }
 
@@ -159,7 +159,7 @@ inline uint32_t le32(const uint8_t* p) { return (uint32_t)p[3] << 24 | (uint32_t
 enum { kMetaOk = 0, kMetaBad = 1, kMetaRefused = 2, kMetaFatal = 3, kMetaStuck = 4 };
 int deliver_meta_block(FLAC__StreamDecoder* d, const DecImpl::MetaBlock& b) {
     DecImpl* m = D(d);
-    const uint8_t* q = m->meta_blob.data() + b.off;
+    const uint8_t* q = m->in.data() + b.off;
     if (b.type == 0) { if (b.len >= 34) take_streaminfo(d, q, b.len, b.last); return kMetaOk; }
     bool want = b.type < 128 && m->meta_filter[b.type];
     if (b.type == 2) {                                                  // APPLICATION: the listed ids are the exceptions
@@ -264,10 +264,6 @@ int deliver_meta_block(FLAC__StreamDecoder* d, const DecImpl::MetaBlock& b) {
     return kMetaOk;
 }
 
-// "fLaC" + metadata blocks: waits until ALL of them are buffered, then lists them in meta_blocks (a block can be larger than one
-// input slice -- cover art, a long PADDING -- and take several pulls; nothing is reported before all of them are here).
-// returns 1 listed, 0 need more input, -1 fatal.  When the input ends inside the metadata the complete blocks are listed and
-// meta_truncated is set.
 // The search for "fLaC" at the head of the input (up: find_metadata_, stream_decoder.c; pinned on the binary by
 // tools/host_logic_check.py): an ID3v2 tag in front of it is skipped without a word; any other byte that is not part of the marker
 // is reported as LOST_SYNC -- once per run of such bytes, a run ending wherever a byte continues the marker; bytes other than the
@@ -314,46 +310,88 @@ int find_magic(FLAC__StreamDecoder* d) {
     return 1;
 }
 
-int parse_metadata(FLAC__StreamDecoder* d) {
+// the metadata is behind us: the input buffer starts at the first frame
+void finish_metadata(DecImpl* m) {
+    m->in.erase(m->in.begin(), m->in.begin() + (long)m->meta_pos);
+    m->bytes_consumed += m->meta_pos; m->meta_pos = 0;
+    m->first_frame_offset = m->bytes_consumed;
+    m->metadata_done = true;
+}
+// the input ended before the metadata did: everything was read
+int end_inside_metadata(DecImpl* m) {
+    m->bytes_consumed += m->in.size(); m->in.clear(); m->meta_pos = 0; m->find_scan = 0;
+    m->state = DS_END_OF_STREAM;
+    return -1;
+}
+
+// One step through the head of the stream: the marker, then ONE metadata block (up: find_metadata_ / read_metadata_,
+// stream_decoder.c).  returns 1 a block was read (or, in the until-end calls, the metadata is done), 0 more input was pulled,
+// -1 the call fails (the state says why), 2 go on with the frames.
+int metadata_step(FLAC__StreamDecoder* d, bool until_end, size_t slice) {
     DecImpl* m = D(d);
-    m->meta_blocks.clear(); m->meta_next = 0; m->meta_truncated = false;
-    const int found = find_magic(d);
-    if (found == 0 || found == -3) {
-        // a long stretch without the marker (or a large ID3v2 tag) is not kept: the input buffer holds what is still needed
-        if (m->find_scan > (1u << 20) && m->find_i == 0 && m->id3_need == 0) {
-            m->in.erase(m->in.begin(), m->in.begin() + (long)m->find_scan);
-            m->bytes_consumed += m->find_scan; m->find_scan = 0;
+    if (m->find_i < 4) {                                                // still looking for the marker
+        const int r = find_magic(d);
+        if (r == 0 || r == -3) {
+            // a long stretch without the marker (or a large ID3v2 tag) is not kept: the input buffer holds what is still needed
+            if (m->find_scan > (1u << 20) && m->find_i == 0 && m->id3_need == 0) {
+                m->in.erase(m->in.begin(), m->in.begin() + (long)m->find_scan);
+                m->bytes_consumed += m->find_scan; m->find_scan = 0;
+            }
+            if (r == -3) return -1;                                     // this call fails, the state stands, the next call searches on
+            return pull(d, slice) ? 0 : -1;
         }
-        return found;
+        if (r == -2) return end_inside_metadata(m);
+        if (r == -1) {
+            // libFLAC goes on to decode such frames without STREAMINFO; this build cannot (pyFLAC's tests expect an error for
+            // arbitrary data, tests/test_decoder.py:59-66)
+            if (m->find_first) report(d, ERR_LOST_SYNC);
+            m->state = m->eof ? DS_END_OF_STREAM : DS_ABORTED;
+            return -1;
+        }
+        m->meta_pos = m->find_scan;
     }
-    if (found == -2) { m->meta_truncated = true; m->meta_parsed = true; m->bytes_consumed += m->in.size(); m->in.clear(); return 1; }   // (all of the input was read)
-    if (found == -1) {
-        // libFLAC goes on to decode such frames without STREAMINFO; this build cannot (pyFLAC's tests expect an error for
-        // arbitrary data, tests/test_decoder.py:59-66)
-        if (m->find_first) report(d, ERR_LOST_SYNC);
-        return -1;
-    }
-    size_t pos = m->find_scan; bool have_si = false;
     for (;;) {
-        if (pos + 4 > m->in.size()) { if (!m->eof) return 0; m->meta_truncated = true; break; }
-        const uint8_t* p = m->in.data() + pos;
-        const uint32_t len = (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
-        if (pos + 4 + (size_t)len > m->in.size()) { if (!m->eof) return 0; m->meta_truncated = true; break; }
-        const DecImpl::MetaBlock b = {(uint32_t)(p[0] & 0x7f), len, (p[0] >> 7) != 0, pos + 4};
-        m->meta_blocks.push_back(b);
-        have_si |= b.type == 0 && len >= 34;
-        pos += 4 + (size_t)len;
-        if (b.last) break;
+        // the next block, once all of it is buffered
+        const size_t avail = m->in.size() - m->meta_pos;
+        const uint8_t* p = m->in.data() + m->meta_pos;
+        const bool have_hdr = avail >= 4;
+        const uint32_t type = have_hdr ? (uint32_t)(p[0] & 0x7f) : 0u, len = have_hdr ? ((uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]) : 0u;
+        if (!have_hdr || avail < 4 + (size_t)len) {
+            const bool ended = m->eof;
+            if (!ended && pull(d, slice)) return 0;
+            // the input ended, or the read callback aborted, inside the metadata: a block that was being read for the client (neither
+            // skipped nor one of the two libFLAC keeps for itself) is reported as BAD_METADATA on the way out
+            if (m->meta_skip) { if (ended) report(d, ERR_LOST_SYNC); }
+            else if (have_hdr && type != 0 && type != 3 && m->meta_filter[type]) report(d, ERR_BAD_METADATA);
+            return ended ? end_inside_metadata(m) : -1;
+        }
+        const DecImpl::MetaBlock b = {type, len, (p[0] >> 7) != 0, m->meta_pos + 4};
+        m->meta_pos += 4 + (size_t)len;
+        if (m->meta_skip) {                                             // behind a block that could not be used: on to the first frame
+            if (!b.last) continue;
+            finish_metadata(m);
+            PendingFrame pf; pf.blocksize = 0; pf.error = ERR_LOST_SYNC; m->ready.push_back(std::move(pf));   // what lay between that block and the first frame
+            return 2;
+        }
+        m->have_si |= type == 0 && len >= 34;
+        m->state = b.last ? DS_SEARCH_FOR_FRAME_SYNC : DS_READ_METADATA;
+        const int rc = deliver_meta_block(d, b);                        // (reads the block where it lies in `in`)
+        if (rc == kMetaStuck) { m->meta_pos -= 4 + (size_t)len; m->state = DS_READ_METADATA; return -1; }
+        if (rc == kMetaFatal) { m->state = DS_MEMORY_ALLOCATION_ERROR; return -1; }
+        if (rc == kMetaBad) {
+            report(d, ERR_BAD_METADATA);
+            m->state = DS_SEARCH_FOR_FRAME_SYNC;
+            if (b.last) { finish_metadata(m); PendingFrame pf; pf.blocksize = 0; pf.error = ERR_LOST_SYNC; m->ready.push_back(std::move(pf)); }
+            else m->meta_skip = true;
+            return -1;
+        }
+        if (b.last) {
+            if (!m->have_si) { report(d, ERR_BAD_METADATA); m->state = m->eof ? DS_END_OF_STREAM : DS_ABORTED; return -1; }   // nothing this build can decode without STREAMINFO
+            finish_metadata(m);
+        }
+        if (rc == kMetaRefused) return -1;
+        if (!until_end || b.last) return 1;
     }
-    if (!m->meta_truncated && !have_si) { m->meta_blocks.clear(); report(d, ERR_BAD_METADATA); return -1; }
-    m->meta_blob.assign(m->in.begin(), m->in.begin() + (long)pos);
-    m->meta_base = m->bytes_consumed;
-    if (!m->meta_truncated) {
-        m->in.erase(m->in.begin(), m->in.begin() + (long)pos);
-        m->first_frame_offset = m->meta_base + pos;
-    }
-    m->meta_parsed = true;
-    return 1;
 }
 
 // decode every complete frame currently buffered (one GPU batch); returns false on fatal error.  What libFLAC 1.4.3
@@ -468,35 +506,10 @@ int step(FLAC__StreamDecoder* d, bool until_end) {
             return 1;
         }
         if (!m->metadata_done) {
-            if (!m->meta_parsed) {
-                const int r = parse_metadata(d);
-                if (r == -3) return -1;                                  // this call fails, the state stands, the next call searches on
-                if (r < 0) { m->state = m->eof ? DS_END_OF_STREAM : DS_ABORTED; return m->eof ? 0 : -1; }
-                if (r == 0) { if (!pull(d, kSlice)) return -1; continue; }
-            }
-            // one block per process_single, as libFLAC (all of them for the until-end calls)
-            if (m->meta_next < m->meta_blocks.size()) {
-                const DecImpl::MetaBlock b = m->meta_blocks[m->meta_next++];
-                const bool done = m->meta_next == m->meta_blocks.size() && !m->meta_truncated;
-                if (done) m->metadata_done = true;
-                if (!m->meta_truncated) m->bytes_consumed = m->meta_base + b.off + b.len;      // FLAC__stream_decoder_get_decode_position: behind this block
-                m->state = done ? DS_SEARCH_FOR_FRAME_SYNC : DS_READ_METADATA;
-                const int rc = deliver_meta_block(d, b);
-                if (rc == kMetaBad) {
-                    report(d, ERR_BAD_METADATA);
-                    if (!m->meta_truncated) { m->meta_next = m->meta_blocks.size(); m->metadata_done = true; m->bytes_consumed = m->first_frame_offset; }
-                    m->state = DS_SEARCH_FOR_FRAME_SYNC;
-                    PendingFrame pf; pf.blocksize = 0; pf.error = ERR_LOST_SYNC; m->ready.push_back(std::move(pf));   // the rest of the metadata is junk in front of the first frame
-                    return -1;
-                }
-                if (rc == kMetaRefused) return -1;
-                if (rc == kMetaFatal) { m->state = DS_MEMORY_ALLOCATION_ERROR; return -1; }
-                if (rc == kMetaStuck) { m->meta_next--; m->metadata_done = false; m->state = DS_READ_METADATA; return -1; }
-                if (!until_end) return 1;
-                continue;
-            }
-            m->state = DS_END_OF_STREAM;                                // the input ended inside the metadata
-            return -1;
+            const int r = metadata_step(d, until_end, kSlice);
+            if (r == 0 || r == 2) continue;
+            if (r == 1 && until_end) continue;                           // (the until-end calls go straight on with the frames)
+            return r;
         }
         // need more frames: decode what is buffered once a slice (or the tail) is available
         if (!m->eof && m->in.size() < 16) { if (!pull(d, kSlice)) return -1; continue; }
@@ -574,16 +587,15 @@ uint32_t FLAC__stream_decoder_get_bits_per_sample(const FLAC__StreamDecoder* d) 
 uint32_t FLAC__stream_decoder_get_sample_rate(const FLAC__StreamDecoder* d) { return D(d)->hdr_sample_rate; }
 uint32_t FLAC__stream_decoder_get_blocksize(const FLAC__StreamDecoder* d) { return D(d)->hdr_blocksize; }
 // stream_decoder.h:1083-1099: needs a tell callback (FILE input always has one)
-FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder* d, FLAC__uint64* p) { const DecImpl* m = D(d); if (!p || (!m->file && !m->tell_cb)) return 0; *p = m->bytes_consumed + (m->meta_parsed ? 0 : m->find_scan);   /* (while the marker is still being looked for: what the search has read) */ return 1; }
+FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder* d, FLAC__uint64* p) { const DecImpl* m = D(d); if (!p || (!m->file && !m->tell_cb)) return 0; *p = m->bytes_consumed + (m->metadata_done ? 0 : m->find_i == 4 ? m->meta_pos : m->find_scan);   /* (inside the head of the stream: what the marker search and the blocks have taken) */ return 1; }
 
 static int init_common(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
     m->in.clear(); m->eof = false; m->metadata_done = false; m->ready.clear(); m->frame_index = 0; m->bytes_consumed = 0;
     m->sample_rate = m->channels = m->bps = m->blocksize = 0; m->total_samples = 0; m->min_blocksize = 0;
     m->have_last = false; m->next_sample = 0; m->last_blocksize = 0; m->first_frame_offset = 0;
-    m->meta_parsed = false; m->meta_truncated = false; m->meta_blocks.clear(); m->meta_blob.clear(); m->meta_next = 0; m->is_seeking = false;
-    m->find_reset();
-    m->hdr_channels = m->hdr_bps = m->hdr_sample_rate = m->hdr_blocksize = 0; m->meta_base = 0;
+    m->meta_reset(); m->is_seeking = false;
+    m->hdr_channels = m->hdr_bps = m->hdr_sample_rate = m->hdr_blocksize = 0;
     m->md5_active = m->md5_checking != 0; m->md5.init(); memset(m->stored_md5, 0, 16);
     {
         std::lock_guard<std::mutex> lk(g_dec_mu);
@@ -660,9 +672,9 @@ static bool input_length(FLAC__StreamDecoder* d, uint64_t* len) {
 FLAC__bool FLAC__stream_decoder_flush(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
     if (m->state == DS_UNINITIALIZED) return 0;
-    if (m->meta_parsed && !m->meta_truncated && !m->metadata_done) { m->meta_next = m->meta_blocks.size(); m->metadata_done = true; m->bytes_consumed = m->first_frame_offset; }   // blocks not read yet are skipped
-    if (m->meta_parsed) m->bytes_consumed += m->in.size();             // the decode position moves behind the input that is dropped
-    else m->find_reset();                                              // (nothing of the dropped input is looked at again)
+    if (!m->metadata_done && m->find_i == 4) { m->metadata_done = true; m->meta_pos = 0; m->meta_skip = false; }   // inside the blocks: the ones not read yet are dropped with the input
+    if (m->metadata_done) m->bytes_consumed += m->in.size();           // the decode position moves behind the input that is dropped
+    else m->find_reset();                                              // (still looking for the marker: nothing of the dropped input is looked at again)
     m->in.clear(); m->ready.clear(); m->md5_active = false; m->have_last = false;
     m->state = DS_SEARCH_FOR_FRAME_SYNC;
     return 1;
@@ -676,7 +688,7 @@ FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) {
     if (m->file) { if (m->file == stdin) return 0; if (fseeko(m->file, 0, SEEK_SET) != 0) return 0; }
     else if (m->seek_cb && m->seek_cb(d, 0, m->client) == 1) return 0;          // seekable and the seek fails: reset fails
     m->metadata_done = false; m->eof = false; m->frame_index = 0; m->bytes_consumed = 0; m->next_sample = 0; m->last_blocksize = 0;
-    m->meta_parsed = false; m->meta_truncated = false; m->meta_blocks.clear(); m->meta_next = 0; m->find_reset();
+    m->meta_reset();
     m->total_samples = 0;                                              // (FLAC__stream_decoder_get_total_samples: 0 until STREAMINFO has been read again)
     m->md5_active = m->md5_checking != 0; m->md5.init();
     m->state = DS_SEARCH_FOR_METADATA;
@@ -685,19 +697,22 @@ FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder* d) {
 
 FLAC__bool FLAC__stream_decoder_process_single(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
-    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
+    if (m->state == DS_UNINITIALIZED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
+    if (m->state == DS_ABORTED) return 1;                               // (only the call in which the client aborted fails; as END_OF_STREAM, libFLAC)
     if (m->state == DS_END_OF_STREAM) return 1;
     return step(d, false) >= 0;
 }
 FLAC__bool FLAC__stream_decoder_process_until_end_of_metadata(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
-    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
-    while (!m->metadata_done && m->state != DS_END_OF_STREAM) if (step(d, false) < 0) return 0;
+    if (m->state == DS_UNINITIALIZED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
+    if (m->state == DS_ABORTED) return 1;                               // (only the call in which the client aborted fails; as END_OF_STREAM, libFLAC)
+    while (!m->metadata_done && !m->meta_skip && m->state != DS_END_OF_STREAM) if (step(d, false) < 0) return 0;
     return 1;
 }
 FLAC__bool FLAC__stream_decoder_process_until_end_of_stream(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
-    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
+    if (m->state == DS_UNINITIALIZED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
+    if (m->state == DS_ABORTED) return 1;                               // (only the call in which the client aborted fails; as END_OF_STREAM, libFLAC)
     for (;;) {
         const int r = step(d, true);
         if (r < 0) return 0;
@@ -706,7 +721,8 @@ FLAC__bool FLAC__stream_decoder_process_until_end_of_stream(FLAC__StreamDecoder*
 }
 FLAC__bool FLAC__stream_decoder_skip_single_frame(FLAC__StreamDecoder* d) {
     DecImpl* m = D(d);
-    if (m->state == DS_UNINITIALIZED || m->state == DS_ABORTED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
+    if (m->state == DS_UNINITIALIZED || m->state == DS_MEMORY_ALLOCATION_ERROR) return 0;
+    if (m->state == DS_ABORTED) return 1;                               // (only the call in which the client aborted fails; as END_OF_STREAM, libFLAC)
     FLAC__StreamDecoderWriteCallback keep = m->write_cb;
     m->write_cb = [](const FLAC__StreamDecoder*, const FLAC__Frame*, const FLAC__int32* const*, void*) -> int { return 0; };
     const int r = step(d, false);

@@ -246,14 +246,17 @@ DEC_LENGTH_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void
 DEC_EOF_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
 
 
-def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, path=None, meta=False, read_chunk=None, respond=()):
+def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, path=None, meta=False, read_chunk=None, respond=(),
+                            read_script=None):
     """A StreamDecoder session driven by a script, over seekable callbacks (or a file when `path` is given).
     ops: ('seek', sample) | ('single', n) | ('end',) | ('flush',) | ('reset',) | ('meta',).
     Returns dict(events=[...], finish=bool): events are ('w', number_type, sample_number, blocksize, crc32 of the samples),
     ('e', status) and ('ret', op, return value, decoder state) in the order they happened; with meta=True a metadata callback is
     registered and logs ('m', type, is_last, length, sample_rate, channels, bits_per_sample, total_samples).  read_chunk caps what
     one read callback hands over (None: as much as is asked for).  respond: filter calls made before init, in order, e.g.
-    ('respond_all',), ('ignore', 4), ('respond_application', b"abcd"); their return values are logged as ('set', name, value)."""
+    ('respond_all',), ('ignore', 4), ('respond_application', b"abcd"); their return values are logged as ('set', name, value).
+    read_script: {k: 'abort' | 'empty' | 'eof'} makes the k-th read callback (from 0) abort, hand over nothing with CONTINUE, or
+    claim the end of the stream."""
     import zlib
     for n, at, rt in [("new", [], C.c_void_p), ("delete", [C.c_void_p], None), ("finish", [C.c_void_p], C.c_int),
                       ("get_state", [C.c_void_p], C.c_int), ("process_until_end_of_stream", [C.c_void_p], C.c_int),
@@ -271,7 +274,19 @@ def scripted_decode_session(L, data, ops, md5_checking=False, seekable=True, pat
     pos = [0]
     events = []
 
+    reads = [0]
+
     def r(dec, buf, pbytes, cd):
+        what = (read_script or {}).get(reads[0])
+        reads[0] += 1
+        if what == 'abort':
+            return 2
+        if what == 'empty':
+            pbytes[0] = 0
+            return 0
+        if what == 'eof':
+            pbytes[0] = 0
+            return 1
         k = min(pbytes[0], len(data) - pos[0], read_chunk or (1 << 62))
         if k == 0:
             pbytes[0] = 0

@@ -168,7 +168,7 @@ odd.update({
 })
 for name, blk in odd.items():
     strm = data[:42] + blk + data[42:]
-    for ops in ([('single', 1)] * 2, [('meta',)]):       # (behind a block reported as BAD_METADATA the sessions reach audio frames: GPU tests)
+    for ops in ([('single', 1)] * 2, [('meta',)], [('meta',), ('meta',)]):       # (behind a block reported as BAD_METADATA the sessions reach audio frames: GPU tests)
         a = scripted_decode_session(ours, strm, ops, meta=True, seekable=False, respond=(('respond_all',),))
         b = scripted_decode_session(ref, strm, ops, meta=True, seekable=False, respond=(('respond_all',),))
         n += 1
@@ -224,6 +224,32 @@ for name, head in heads.items():
         for ea, eb in zip(a, b):
             if ea != eb:
                 print("DIFF head, control surface:", name, "\n ours", ea, "\n ref ", eb)
+
+# a read callback that aborts, hands over nothing, or claims the end of the stream while the metadata is being read (small reads, so
+# that both libraries are still inside the metadata at that call); and the same sessions over a FILE
+for k in range(0, 12):
+    for what in ("abort", "empty", "eof"):
+        for ops in ([('meta',)], [('single', 1)] * 4, [('meta',), ('meta',)] + ([('single', 1)] if what != 'empty' else [])):
+            a = scripted_decode_session(ours, _rich(data)[0], ops, meta=True, seekable=False, read_chunk=64, respond=(('respond_all',),), read_script={k: what})
+            b = scripted_decode_session(ref, _rich(data)[0], ops, meta=True, seekable=False, read_chunk=64, respond=(('respond_all',),), read_script={k: what})
+            n += 1
+            if a["events"] != b["events"]:
+                bad += 1
+                print("DIFF read callback", k, what, ops, "\n ours", str(a["events"])[-300:], "\n ref ", str(b["events"])[-300:])
+import tempfile as _tf                                     # noqa: E402
+with _tf.TemporaryDirectory() as tmp:
+    for name, blob in (("plain", data), ("rich", _rich(data)[0]), ("id3", id3(5000) + data), ("junk", b"0123456789" + data), ("cut", data[:60]), ("empty", b"")):
+        fn = os.path.join(tmp, name + ".flac")
+        with open(fn, "wb") as f:
+            f.write(blob)
+        for ops in ([('meta',)], [('single', 1)] * 2, [('meta',), ('reset',), ('meta',)]):
+            for resp in ((), (('respond_all',),)):
+                a = scripted_decode_session(ours, blob, ops, meta=True, path=fn, respond=resp)
+                b = scripted_decode_session(ref, blob, ops, meta=True, path=fn, respond=resp)
+                n += 1
+                if a != b:
+                    bad += 1
+                    print("DIFF file decode", name, ops, resp, "\n ours", str(a)[-400:], "\n ref ", str(b)[-400:])
 
 # encoder: a stream without a single sample never reaches a kernel -- header writes, tell / seek traffic, the STREAMINFO rewrite at
 # finish (min framesize 2^24 - 1: no frame ever lowered it), the metadata callback, and what happens when a callback fails
