@@ -279,6 +279,7 @@ struct EncImpl {
     uint64_t vstat_sample = 0; uint32_t vstat_channel = 0; int32_t vstat_expected = 0, vstat_got = 0;   // verify mismatch report
     uint64_t samples_written = 0, bytes_written = 0;
     uint32_t min_fs = 0, max_fs = 0, frames_written = 0;
+    bool being_deleted = false;            // FLAC__stream_encoder_delete on an encoder that was not finished: finish() without flush or callbacks
     uint64_t streaminfo_offset = 0;        // byte position of the STREAMINFO block header as told by the tell callback
     Md5 md5;
     std::vector<uint8_t> arena; std::vector<uint64_t> foff; std::vector<uint32_t> flen, fsmp;
@@ -448,6 +449,10 @@ FLAC__StreamEncoder* FLAC__stream_encoder_new(void) {
 }
 void FLAC__stream_encoder_delete(FLAC__StreamEncoder* e) {
     if (!e) return;
+    // up: FLAC__stream_encoder_delete (pinned on the binary, tools/host_logic_check.py): an encoder that is deleted without finish()
+    // is torn down without a word -- no last frame, no STREAMINFO rewrite, no callback of any kind (a Python object may be collected
+    // long after its callbacks stopped making sense)
+    I(e)->being_deleted = true;
     if (I(e)->state != ST_UNINITIALIZED) FLAC__stream_encoder_finish(e);
     delete reinterpret_cast<Handle*>(e);
 }
@@ -591,13 +596,13 @@ FLAC__bool FLAC__stream_encoder_finish(FLAC__StreamEncoder* e) {
     // wrong INSIDE this call makes it fail and leaves the error state standing -- the last frame, the STREAMINFO rewrite.  An
     // encoder that was already in an error state (a process() call failed) is simply reset: true, UNINITIALIZED.
     bool ok = true;
-    if (m->state == ST_OK) {
+    if (m->state == ST_OK && !m->being_deleted) {
         const uint64_t have = m->pending.size() / m->channels;
         if (have > 0) ok = encode_pending(e, have);           // remainder -> final (possibly short) frame
     }
     uint8_t digest[16];
     m->md5.final(digest);
-    if (m->state == ST_OK) {
+    if (m->state == ST_OK && !m->being_deleted) {
         // up: update_metadata_ -- rewrite STREAMINFO in place: MD5 @26 (16 B), total samples @21 (5 B), frame sizes @12 (6 B)
         uint8_t si[34];
         const uint32_t min_fs = m->min_fs ? m->min_fs : 0xFFFFFFu;      // no frame at all: libFLAC's minimum is still where it started (2^24 - 1)

@@ -299,5 +299,54 @@ with tempfile.TemporaryDirectory() as tmp:
         if a != b:
             bad += 1
             print("DIFF file encode", (ch, bps, sr, est, name), "\n ours", a, "\n ref ", b)
+# an encoder deleted without finish(): torn down without a callback (samples that never filled a block are dropped, the file keeps
+# the STREAMINFO written at init)
+from _flacapi import WRITE_CB, SEEK_CB, TELL_CB, META_CB, _proto   # noqa: E402
+
+
+def delete_session(L, x, path=None):
+    _proto(L)
+    log = []
+
+    def w(enc, buf, nbytes, samples, frame, cd):
+        log.append(('write', bytes(buf[:nbytes]), samples, frame))
+        return 0
+
+    def s_(enc, off, cd):
+        log.append(('seek', off))
+        return 0
+
+    def t(enc, poff, cd):
+        poff[0] = 0
+        log.append(('tell',))
+        return 0
+
+    def m(enc, md, cd):
+        log.append(('meta',))
+    cbs = (WRITE_CB(w), SEEK_CB(s_), TELL_CB(t), META_CB(m))
+    e = L.FLAC__stream_encoder_new()
+    L.FLAC__stream_encoder_set_channels(e, x.shape[1])
+    L.FLAC__stream_encoder_set_bits_per_sample(e, 16)
+    L.FLAC__stream_encoder_set_sample_rate(e, 44100)
+    st = L.FLAC__stream_encoder_init_file(e, path.encode(), None, None) if path else L.FLAC__stream_encoder_init_stream(e, cbs[0], cbs[1], cbs[2], cbs[3], None)
+    x32 = np.ascontiguousarray(x.astype(np.int32))
+    ok = L.FLAC__stream_encoder_process_interleaved(e, x32.ctypes.data, len(x32)) if len(x32) else 1
+    log.append(('processed', st, ok, L.FLAC__stream_encoder_get_state(e)))
+    L.FLAC__stream_encoder_delete(e)
+    log.append(('deleted', open(path, "rb").read() if path else None))
+    return log
+
+
+with tempfile.TemporaryDirectory() as tmp:
+    for nsamp in (0, 1, 100, 4096):                       # (4097 samples would fill a block: a frame, a kernel)
+        for ch in (1, 2):
+            xs = (np.arange(nsamp * ch, dtype=np.int32).reshape(nsamp, ch) * 37) % 2000 - 1000
+            for path in (None, os.path.join(tmp, "d.flac")):
+                a = delete_session(ours, xs, path)
+                b = delete_session(ref, xs, path)
+                n += 1
+                if a != b:
+                    bad += 1
+                    print("DIFF delete without finish", nsamp, ch, bool(path), "\n ours", str(a)[-300:], "\n ref ", str(b)[-300:])
 print(f"{n} sessions, {bad} differ from libFLAC")
 sys.exit(1 if bad else 0)
