@@ -262,6 +262,7 @@ struct EncImpl {
     // presets into them, the individual setters change them afterwards, exactly as in libFLAC
     FLAC__bool ms = 1, loose = 0, prec_search = 0, exhaustive = 0;
     uint32_t max_lpc = 8, qlp_prec = 0, min_po = 0, max_po = 5, rice_dist = 0, apod_parts = 1;
+    uint32_t qlp_resolved = 0;             // what get_qlp_coeff_precision reports while the encoder is initialised
     float apod_p = 0.5f;
     bool custom_tuning = false;            // a setting this build cannot honour (exhaustive searches, other window families): init fails loudly
     int state = ST_UNINITIALIZED;
@@ -294,7 +295,7 @@ void apply_level(EncImpl* m, uint32_t v) {
     m->level = v > 8 ? 8 : v;
     m->ms = kLv[m->level].ms; m->loose = kLv[m->level].loose; m->max_lpc = kLv[m->level].lpc; m->max_po = kLv[m->level].po;
     m->apod_parts = kLv[m->level].parts; m->apod_p = 0.5f;
-    m->qlp_prec = 0; m->min_po = 0; m->rice_dist = 0; m->prec_search = 0; m->exhaustive = 0; m->custom_tuning = false;
+    m->qlp_prec = 0; m->qlp_resolved = 0; m->min_po = 0; m->rice_dist = 0; m->prec_search = 0; m->exhaustive = 0; m->custom_tuning = false;
 }
 void reset_settings(EncImpl* m) {
     m->verify = 0; m->streamable_subset = 1; m->limit_min_bitrate = 0;
@@ -396,6 +397,14 @@ int init_common(FLAC__StreamEncoder* e) {
     const int st = flacb200_enc_validate(&cfg);
     if (st != 0) return st;
     m->N = m->blocksize ? m->blocksize : (m->max_lpc == 0 ? 1152u : 4096u);
+    // up: init_stream_internal_ -- mid/side is a two-channel matter, loose mid/side a mid/side matter: the getters say so from here on
+    if (m->channels != 2) { m->ms = 0; m->loose = 0; } else if (!m->ms) m->loose = 0;
+    // up: init_stream_internal_ resolves a precision of 0 ("let the encoder choose") from the sample size and the blocksize, and
+    // FLAC__stream_encoder_get_qlp_coeff_precision reports that value from then on (the kernels resolve it the same way: engine.cu)
+    m->qlp_resolved = m->qlp_prec ? m->qlp_prec
+                    : m->bps < 16 ? (2 + m->bps / 2 < 5 ? 5u : 2 + m->bps / 2)
+                    : m->bps == 16 ? (m->N <= 192 ? 7u : m->N <= 384 ? 8u : m->N <= 576 ? 9u : m->N <= 1152 ? 10u : m->N <= 2304 ? 11u : m->N <= 4608 ? 12u : 13u)
+                    : (m->N <= 384 ? 13u : m->N <= 1152 ? 14u : 15u);
     // limits of this build fail loudly here instead of producing a different stream (DESIGN.md "limits"): searches libFLAC's presets
     // never run (exhaustive model / precision search, a minimum partition order), window families other than tukey, orders above 12
     if (m->custom_tuning || m->exhaustive || m->prec_search || (m->min_po != 0 && m->max_po != 0) || m->max_lpc > 12 || m->max_po > 6 || m->qlp_prec > 15 ||
@@ -530,7 +539,7 @@ uint32_t FLAC__stream_encoder_get_blocksize(const FLAC__StreamEncoder* e) { retu
 FLAC__bool FLAC__stream_encoder_get_do_mid_side_stereo(const FLAC__StreamEncoder* e) { return I(e)->ms; }
 FLAC__bool FLAC__stream_encoder_get_loose_mid_side_stereo(const FLAC__StreamEncoder* e) { return I(e)->loose; }
 uint32_t FLAC__stream_encoder_get_max_lpc_order(const FLAC__StreamEncoder* e) { return I(e)->max_lpc; }
-uint32_t FLAC__stream_encoder_get_qlp_coeff_precision(const FLAC__StreamEncoder* e) { return I(e)->qlp_prec; }
+uint32_t FLAC__stream_encoder_get_qlp_coeff_precision(const FLAC__StreamEncoder* e) { const EncImpl* m = I(e); return m->state != ST_UNINITIALIZED && m->qlp_resolved ? m->qlp_resolved : m->qlp_prec; }
 FLAC__bool FLAC__stream_encoder_get_do_qlp_coeff_prec_search(const FLAC__StreamEncoder* e) { return I(e)->prec_search; }
 FLAC__bool FLAC__stream_encoder_get_do_escape_coding(const FLAC__StreamEncoder*) { return 0; }
 FLAC__bool FLAC__stream_encoder_get_do_exhaustive_model_search(const FLAC__StreamEncoder* e) { return I(e)->exhaustive; }

@@ -2,7 +2,7 @@
 decoder handles (blocks larger than one read, every block type through the metadata callback, the respond / ignore filters, an
 ID3v2 tag or junk in front of the stream marker, input that ends inside the metadata) and what the encoder handles do when a
 callback fails or no sample is ever fed.  Everything in these sessions that does not need a kernel -- i.e. all of it up to the first
-audio frame -- is compared with libFLAC on the CPU by tools/host_logic_check.sh (1013 sessions through a scratch build); what is left
+audio frame -- is compared with libFLAC on the CPU by tools/host_logic_check.sh (3429 sessions through a scratch build); what is left
 for the GPU is the ordinary frame path behind it.  Their first run on hardware is the round-end run, hence the non-strict xfail: a
 failure here must not hide the results of the files that sort after test_gpu_dropin.py (this file sorts last for the same reason)."""
 import ctypes as C

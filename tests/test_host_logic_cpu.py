@@ -26,4 +26,4 @@ def test_handle_api_host_logic_matches_libflac(checkers, tmp_path):
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     last = r.stdout.strip().splitlines()[-1]
-    assert last.endswith(" 0 differ from libFLAC") and int(last.split()[0]) >= 1000, tail
+    assert last.endswith(" 0 differ from libFLAC") and int(last.split()[0]) >= 3400, tail

@@ -299,6 +299,60 @@ with tempfile.TemporaryDirectory() as tmp:
         if a != b:
             bad += 1
             print("DIFF file encode", (ch, bps, sr, est, name), "\n ours", a, "\n ref ", b)
+# what an initialised encoder's getters report (the blocksize, precision and mid/side switches as init resolved them), that setters
+# are refused from then on, and process() calls that do not fill a block
+ENC_GETTERS = ["state", "verify", "streamable_subset", "channels", "bits_per_sample", "sample_rate", "blocksize", "do_mid_side_stereo",
+               "loose_mid_side_stereo", "max_lpc_order", "qlp_coeff_precision", "do_qlp_coeff_prec_search", "do_escape_coding",
+               "do_exhaustive_model_search", "min_residual_partition_order", "max_residual_partition_order", "rice_parameter_search_dist",
+               "limit_min_bitrate"]
+
+
+def getter_session(L, ch, bps, sr, level, bs, subset):
+    from _flacapi import WRITE_CB as _W, SEEK_CB as _S, TELL_CB as _T, META_CB as _M, _proto as _p
+    _p(L)
+
+    def snap(e):
+        out = []
+        for g in ENC_GETTERS:
+            f = getattr(L, "FLAC__stream_encoder_get_" + g)
+            f.argtypes = [C.c_void_p]
+            f.restype = C.c_uint32
+            out.append(f(e))
+        return out
+    w = _W(lambda *a: 0)
+    e = L.FLAC__stream_encoder_new()
+    L.FLAC__stream_encoder_set_channels(e, ch)
+    L.FLAC__stream_encoder_set_bits_per_sample(e, bps)
+    L.FLAC__stream_encoder_set_sample_rate(e, sr)
+    L.FLAC__stream_encoder_set_compression_level(e, level)
+    L.FLAC__stream_encoder_set_blocksize(e, bs)
+    L.FLAC__stream_encoder_set_streamable_subset(e, subset)
+    null = lambda T: C.cast(None, T)  # noqa: E731
+    st = L.FLAC__stream_encoder_init_stream(e, w, null(_S), null(_T), null(_M), None)
+    a = snap(e) if st == 0 else None                     # (after a refused init libFLAC's getters show how far its init got)
+    r = [L.FLAC__stream_encoder_set_channels(e, 1), L.FLAC__stream_encoder_set_blocksize(e, 1234), L.FLAC__stream_encoder_set_compression_level(e, 0)] if st == 0 else None
+    x = np.zeros((10, ch), np.int32)
+    p0 = L.FLAC__stream_encoder_process_interleaved(e, x.ctypes.data, 0) if st == 0 else None
+    p1 = L.FLAC__stream_encoder_process_interleaved(e, x.ctypes.data, 10) if st == 0 else None
+    b = snap(e) if st == 0 else None
+    L.FLAC__stream_encoder_delete(e)
+    return st, a, r, p0, p1, b
+
+
+for ch in (1, 2, 8):
+    for bps in (8, 16, 24, 32):
+        for sr in (8000, 44100, 96000, 384000, 1048575):
+            for level in (0, 2, 5, 8):
+                for bs in (0, 16, 1152, 4608, 16384):
+                    for subset in (1, 0):
+                        a = getter_session(ours, ch, bps, sr, level, bs, subset)
+                        b = getter_session(ref, ch, bps, sr, level, bs, subset)
+                        n += 1
+                        if a != b:
+                            bad += 1
+                            if bad < 20:
+                                print("DIFF encoder getters", (ch, bps, sr, level, bs, subset), "\n ours", a, "\n ref ", b)
+
 # an encoder deleted without finish(): torn down without a callback (samples that never filled a block are dropped, the file keeps
 # the STREAMINFO written at init)
 from _flacapi import WRITE_CB, SEEK_CB, TELL_CB, META_CB, _proto   # noqa: E402
