@@ -14,7 +14,7 @@ import pytest
 from pyflac_b200.synth import music_like
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.timeout(600),      # (pytest-timeout: a session that never returns must not stall the files' worth of results before it)
+              pytest.mark.timeout(600, method="signal"),   # (pytest-timeout: a session that does not return fails here instead of stalling the run)
               pytest.mark.xfail(strict=False, reason="first run on hardware is the round-end run (host logic checked on the CPU: tools/host_logic_check.sh)")]
 
 
